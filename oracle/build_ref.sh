@@ -1,0 +1,31 @@
+#!/bin/bash
+# oracle/build_ref.sh -- builds oracle/_ref/kdtree2_ref from the reference's OWN pre-built
+# object utils/libutils.a:kdtree2.o (linked where it lies; nothing is copied into the repo
+# except the resulting binary under the git-ignored oracle/_ref/).  Needs /root/reference and a
+# libgfortran.so.5 (the one bundled with scipy's wheel).  Exits 0 with a message if either is
+# missing: the binary is optional test infrastructure.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${MCT_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -f "$REF/utils/libutils.a" ]; then echo "build_ref: $REF/utils/libutils.a not present, skipping"; exit 0; fi
+GF="$(python - <<'PY'
+import glob, os, sys
+try:
+    import scipy
+    base = os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs")
+    c = sorted(glob.glob(os.path.join(base, "libgfortran*.so.5*")))
+    print(c[0] if c else "")
+except Exception:
+    print("")
+PY
+)"
+if [ -z "$GF" ]; then echo "build_ref: no libgfortran.so.5 found, skipping"; exit 0; fi
+mkdir -p "$OUT"
+TMP="$(mktemp -d)"
+( cd "$TMP" && ar x "$REF/utils/libutils.a" kdtree2.o )
+# -no-pie: the object carries R_X86_64_32 relocations (non-PIC build)
+gcc -O1 -no-pie -ffp-contract=off -o "$OUT/kdtree2_ref" "$HERE/ref_harness/kdtree2_harness.c" \
+    "$TMP/kdtree2.o" "$GF" -Wl,-rpath,"$(dirname "$GF")" -lm
+rm -rf "$TMP"
+echo "build_ref: built $OUT/kdtree2_ref (libgfortran: $GF)"

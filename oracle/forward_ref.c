@@ -1,0 +1,169 @@
+/*
+ * oracle/forward_ref.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the glue between the gridded model and the 1-D solver:
+ * vs2vp_3d / vp2rho_3d, check_model, convert_to_layer and the OpenMP column loop of
+ * surf_likelihood / program modelling.  Used as the parity checker and as the timed
+ * CPU baseline (bench.py cpu_baseline / --impl reference).  See the headers of
+ * surfdisp96_ref.c ("parity unpinned") and kdtree2_ref.c ("pinned").
+ *
+ * Reference lines restated (relative to /root/reference):
+ *   src/utils.f90:102-112,125-134           vs2vp_3d, vp2rho_3d
+ *   src/likelihood_surf.F90:631-646         check_model
+ *   src/likelihood_surf.F90:523-629         convert_to_layer (EPS=1e-10, /scaling)
+ *   src/forward_modelling.f90:72-175        convert_to_layer twin (EPS=1e-5, no scaling)
+ *   src/likelihood_surf.F90:186-206         output presets + OpenMP column loop
+ *   src/likelihood_surf_mmode.F90           same with np*nmodes outputs (surfmmodes)
+ * Compile with -ffp-contract=off -fopenmp.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../mctomo_b200/csrc/mct_math.h"
+
+typedef struct {
+  int nx, ny, nz;
+  double xmin, ymin, zmin, dx, dy, dz;
+  double waterDepth, scaling;
+} orc_grid;
+
+int orc_surfmodes(const double* thick, const double* vp, const double* vs, const double* rho, int n,
+                  const double* freqs, int np, int modetype, int phaseGroup, int nmodes, double dc,
+                  int math_mode, double* phase, double* group, int* ierr, int64_t* counters);
+
+/* vs2vp_3d + vp2rho_3d: `vp = vs*POISSON` (POISSON = 1.730, a default-real literal stored in a
+ * double) and `rho = 1.74*vp**0.25` (src/utils.f90:107-110,131-133). */
+void orc_vs2vp_rho(const double* vs, double* vp, double* rho, int64_t n, int math_mode) {
+  const double POISSON = (double)1.730f;
+  const double c174 = (double)1.74f;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    vp[i] = vs[i] * POISSON;
+    rho[i] = c174 * (math_mode ? mct_pow025(vp[i]) : pow(vp[i], 0.25));
+  }
+}
+
+/* check_model: .true. (1) = model must be discarded */
+int orc_check_model(const double* vs, int nx, int ny, int nz) {
+  for (int64_t c = 0; c < (int64_t)nx * ny; ++c) {
+    const double* col = vs + c * nz;
+    for (int k = 1; k < nz; ++k)
+      if (col[k] < col[0]) return 1;
+  }
+  return 0;
+}
+
+#define NMAXL 256 /* reference: NMAX = 100 (likelihood_surf.F90:30); anything above is UB there */
+
+/*
+ * convert_to_layer for one column.  layer_eps: 1e-10f (likelihood_surf.F90:37) or 1e-5f
+ * (forward_modelling.f90:27) widened to double; water_thresh: EPS (likelihood_surf.F90:546)
+ * or 0 (forward_modelling.f90:91).  Returns nlayers.
+ */
+int orc_convert_column(const double* vp, const double* vs, const double* rho, int nz, double dz,
+                       double waterDepth, double scaling, double layer_eps, double water_thresh,
+                       double* thick, double* alpha, double* beta, double* rho_k) {
+  int nlayers;
+  if (waterDepth > water_thresh) {
+    nlayers = 1;
+    alpha[0] = 1.5; /* waterVel */
+    beta[0] = 0;
+    rho_k[0] = 1; /* waterDensity */
+    thick[0] = waterDepth;
+  } else {
+    nlayers = 0;
+  }
+  double last_vp = vp[0], last_vs = vs[0], last_rho = rho[0];
+  int last_k = 1;
+  for (int k = 2; k <= nz; ++k) {
+    if (fabs(vs[k - 1] - last_vs) > layer_eps) {
+      nlayers = nlayers + 1;
+      if (nlayers >= NMAXL) return -1;
+      alpha[nlayers - 1] = last_vp;
+      beta[nlayers - 1] = last_vs;
+      rho_k[nlayers - 1] = last_rho;
+      thick[nlayers - 1] = (k - last_k) * dz;
+      last_vp = vp[k - 1];
+      last_vs = vs[k - 1];
+      last_rho = rho[k - 1];
+      last_k = k;
+    }
+  }
+  nlayers = nlayers + 1;
+  /* both branches of :576-603 (vbnd absent) end with the bottom cell's values and thick = 0 */
+  alpha[nlayers - 1] = vp[nz - 1];
+  beta[nlayers - 1] = vs[nz - 1];
+  rho_k[nlayers - 1] = rho[nz - 1];
+  thick[nlayers - 1] = 0;
+  for (int i = 0; i < nlayers; ++i) thick[i] = thick[i] / scaling; /* :615 */
+  if (waterDepth > 0) thick[0] = waterDepth;                       /* :617 */
+  return nlayers;
+}
+
+/*
+ * The dispersion block of surf_likelihood (likelihood_surf.F90:155-206) over the 1-based
+ * inclusive column window ix0..ix1, iy0..iy1 (already clamped).
+ *   pvel, gvel : (np*nm, iy0:iy1, ix0:ix1), nm = max(nmodes,1); preset to `preset`
+ *                (100.0 in likelihood_surf.F90:188-189, 1000.0 in forward_modelling.f90:410-411)
+ *   ierr       : (iy0:iy1, ix0:ix1); 0/1 from surfdisp96, 2 = column needs the GRT branch
+ *   counters   : [0] dltar calls, [1] layer steps, summed over columns (may be NULL)
+ * nmodes <= 0: surfmodes/surfdisp96; nmodes >= 1: surfmmodes/surfdisp_mmodes.
+ * Returns the number of columns that would have taken the GRT branch.
+ */
+int orc_surf_dispersion(const double* vp, const double* vs, const double* rho, const orc_grid* g, int ix0,
+                        int ix1, int iy0, int iy1, const double* freqs, int np, int raylov, int phaseGroup,
+                        int nmodes, double dphase, double layer_eps, double water_thresh, double preset,
+                        int math_mode, int nthreads, double* pvel, double* gvel, int* ierr,
+                        int64_t* counters) {
+  const int nm = nmodes <= 0 ? 1 : nmodes;
+  const int wy = iy1 - iy0 + 1;
+  int nunsup = 0;
+  int64_t c0 = 0, c1 = 0;
+  if (nthreads <= 0) nthreads = 1;
+#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(+ : nunsup, c0, c1)
+  for (int i = ix0; i <= ix1; ++i) {
+    double thick[NMAXL], alpha[NMAXL], beta[NMAXL], rho_k[NMAXL];
+    for (int j = iy0; j <= iy1; ++j) {
+      size_t col = (size_t)(i - 1) * g->ny + (size_t)(j - 1);
+      size_t oc = (size_t)(i - ix0) * wy + (size_t)(j - iy0);
+      double* pv = pvel + oc * (size_t)np * nm;
+      double* gv = gvel + oc * (size_t)np * nm;
+      for (int q = 0; q < np * nm; ++q) { pv[q] = preset; gv[q] = preset; }
+      ierr[oc] = 0;
+      int n = orc_convert_column(vp + col * g->nz, vs + col * g->nz, rho + col * g->nz, g->nz, g->dz,
+                                 g->waterDepth, g->scaling, layer_eps, water_thresh, thick, alpha, beta,
+                                 rho_k);
+      int64_t cnt[2] = {0, 0};
+      int e = 0;
+      int rc = (n < 0) ? 3 : orc_surfmodes(thick, alpha, beta, rho_k, n, freqs, np, raylov, phaseGroup,
+                                           nmodes, dphase, math_mode, pv, gv, &e, cnt);
+      if (rc == 0) ierr[oc] = e;
+      else { ierr[oc] = rc; nunsup++; }
+      c0 += cnt[0];
+      c1 += cnt[1];
+    }
+  }
+  if (counters) { counters[0] += c0; counters[1] += c1; }
+  return nunsup;
+}
+
+/* Map assembly of surf_likelihood (likelihood_surf.F90:259-264): copy the window into the padded
+ * (np, ny+2, nx+2) field and replicate the edges the window touches. */
+void orc_assemble_vel(const double* pvel, int np, int nx, int ny, int ix0, int ix1, int iy0, int iy1,
+                      double* vel) {
+  const int wy = iy1 - iy0 + 1;
+  const size_t sy = (size_t)np, sx = (size_t)np * (ny + 2);
+  for (int i = ix0; i <= ix1; ++i)
+    for (int j = iy0; j <= iy1; ++j)
+      memcpy(vel + (size_t)i * sx + (size_t)j * sy, pvel + ((size_t)(i - ix0) * wy + (j - iy0)) * np,
+             sizeof(double) * np);
+  if (ix0 == 1) memcpy(vel, vel + sx, sizeof(double) * sx);
+  if (ix1 == nx) memcpy(vel + (size_t)(nx + 1) * sx, vel + (size_t)nx * sx, sizeof(double) * sx);
+  if (iy0 == 1)
+    for (int i = 0; i < nx + 2; ++i) memcpy(vel + i * sx, vel + i * sx + sy, sizeof(double) * np);
+  if (iy1 == ny)
+    for (int i = 0; i < nx + 2; ++i)
+      memcpy(vel + i * sx + (size_t)(ny + 1) * sy, vel + i * sx + (size_t)ny * sy, sizeof(double) * np);
+}
