@@ -1,0 +1,182 @@
+/*
+ * mctomo_b200.h -- C ABI of the B200-native surface-wave forward-modelling hot path of MCTomo.
+ *
+ * This is the drop-in boundary: plain C, raw pointers and sizes, arrays in the Fortran
+ * (column-major) layout the reference already uses across its C++ boundary
+ * (src/cgal_delaunay.cpp:470-478; src/fastMarching_wrapper.f90:18-29).  The Fortran host
+ * reaches it through ISO_C_BINDING interfaces (fortran/mctomo_b200_shim.f90);
+ * the bodies it replaces are cited per function (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - 3-D model arrays are (nz,ny,nx) column-major: element (k,j,i), 1-based, lives at
+ *     [((i-1)*ny + (j-1))*nz + (k-1)].
+ *   - Column windows ix0..ix1, iy0..iy1 are 1-based and inclusive, as in the Fortran.
+ *   - Every function returns an int status: 0 = OK, > 0 = data condition (see MCT_E_*),
+ *     < 0 = CUDA/runtime failure (text via mct_last_error()).  The library never exits.
+ *   - Host-pointer entry points are synchronous: on return all outputs are in host memory.
+ *     *_dev entry points take device pointers and enqueue on `stream` (a cudaStream_t cast to
+ *     void*; NULL = the library's own stream) without synchronising.
+ *   - The caller owns every array; the library keeps no host pointer after returning.
+ *   - There is no CPU fallback: without a usable CUDA device mct_init fails and every other
+ *     call returns MCT_E_NOINIT.
+ */
+#ifndef MCTOMO_B200_H
+#define MCTOMO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCT_OK 0
+#define MCT_E_INVALID_ARG 1    /* bad sizes / NULL pointers */
+#define MCT_E_GRT_NEEDED 2     /* >= 1 column has a low-velocity layer (surfmodes.f90:84-87,96-99): ierr=2 */
+#define MCT_E_TOO_MANY_LAYERS 3 /* a column needs more than MCT_MAX_LAYERS layers: ierr=3 */
+#define MCT_E_DEGENERATE_NUCLEI 4 /* > 12 coincident nuclei: the reference kd-tree build never terminates */
+#define MCT_E_FLUID_BELOW_TOP 5 /* vs ~ 0 below the first layer: the reference `stop`s (surfmodes.f90:342-345): ierr=4 */
+#define MCT_E_NOINIT (-1)
+#define MCT_E_CUDA (-2)
+
+#define MCT_MAX_LAYERS 200 /* NL of surfdisp96.f:57 */
+#define MCT_MAX_PERIODS 60 /* NP of surfdisp96.f:59 */
+
+/* Mirrors the fields of T_GRID (src/settings.f90:20-28) the hot path reads. */
+typedef struct {
+  int32_t nx, ny, nz;
+  double xmin, ymin, zmin;
+  double dx, dy, dz;
+  double waterDepth; /* grid%waterDepth */
+  double scaling;    /* grid%scaling (thick = thick/scaling, likelihood_surf.F90:615) */
+} mct_grid;
+
+/* Options of the dispersion call; mirrors T_MODES_PARA (surfmodes.f90:23-30) plus the two
+ * constants in which the reference's two layering routines differ. */
+typedef struct {
+  int32_t raylov;     /* paras%modetype: 1 Rayleigh, 0 Love */
+  int32_t phaseGroup; /* 0 phase only, 1 phase + group (surfdisp96 igr) */
+  int32_t nmodes;     /* <= 0: surfmodes -> surfdisp96 (fundamental, outputs preset to 100.0)
+                         >= 1: surfmmodes -> surfdisp_mmodes with that many modes (outputs preset to 0) */
+  double dphase;      /* paras%dc = settings%dPhaseVel */
+  double layer_eps;   /* new layer when |vs(k)-vs_run| > layer_eps: (double)1e-10f in
+                         likelihood_surf.F90:37,560; (double)1e-5f in forward_modelling.f90:27 */
+  double water_thresh; /* water layer iff waterDepth > water_thresh: (double)1e-10f
+                          (likelihood_surf.F90:546) or 0 (forward_modelling.f90:91) */
+  double preset;      /* value left in pvel/gvel for columns the solver never ran on (ierr >= 2):
+                         100.0 (likelihood_surf.F90:188-189) or 1000.0 (forward_modelling.f90:410-411) */
+} mct_disp_opts;
+
+/* Counters accumulated since mct_init / mct_reset_stats. */
+typedef struct {
+  int64_t n_dltar;       /* secular-function evaluations (surfdisp96.f:1036) */
+  int64_t n_layer_steps; /* layer steps inside them (loops surfdisp96.f:1078,1159) */
+  int64_t n_columns;     /* columns solved */
+  int64_t n_nodes;       /* grid nodes assigned by the nearest-nucleus kernel */
+  int64_t n_launches;    /* kernels launched by this library */
+} mct_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int mct_init(int device);       /* selects the device, creates the stream; idempotent */
+int mct_shutdown(void);         /* frees every device/pinned buffer */
+const char* mct_last_error(void);
+int mct_get_stats(mct_stats* out);
+int mct_reset_stats(void);
+/* Enables (1) / disables (0) the per-column work counters inside the dispersion kernel.
+ * Default on; they cost two integer adds per layer step. */
+int mct_set_counters(int on);
+
+/* ---- stage 1: Voronoi -> grid ---------------------------------------------------------
+ * Replaces the body of kdtree_to_grid (src/mcmc_loc2.f90:2029-2078): kdtree2_create over
+ * points(:,1:ncells), the OpenMP loop of kdtree2_n_nearest(nn=1) over the nodes inside
+ * bnd_box, and the writes of sites_id / vp / vs / rho.  Results are identical to kdtree2's,
+ * including which nucleus wins an exact distance tie.
+ *   points  (3,ncells)  RTI%points     params (3,ncells) RTI%parameters = (vp,vs,rho)
+ *   box     {x0,y0,z0,x1,y1,z1}        bnd_box(1:2)
+ *   pm      NULL, or {vp,vs,rho}: only nodes with |vs-pm.vs|<1e-8 and |vp-pm.vp|<1e-8 are
+ *           reassigned (mcmc_loc2.f90:2055-2062)
+ *   vp,vs,rho,sites_id  (nz,ny,nx) host arrays, updated in place inside the window only.
+ */
+int mct_voronoi_to_grid(const double* points, const double* params, int ncells, const mct_grid* g,
+                        const double box[6], const double* pm, double* vp, double* vs, double* rho,
+                        int32_t* sites_id);
+
+/* Device-pointer form: nuclei are still host arrays (48 B each; the tree is built on the
+ * host and uploaded), the model arrays are device pointers. */
+int mct_voronoi_to_grid_dev(const double* points, const double* params, int ncells, const mct_grid* g,
+                            const double box[6], const double* pm, double* d_vp, double* d_vs,
+                            double* d_rho, int32_t* d_sites_id, void* stream);
+
+/* Index window of a box, exactly as mcmc_loc2.f90:2034-2045 computes it (1-based, clamped):
+ * w = {ix0,ix1,iy0,iy1,iz0,iz1}. */
+int mct_box_window(const mct_grid* g, const double box[6], int32_t w[6]);
+
+/* ---- datatype-2 property maps -----------------------------------------------------------
+ * vs2vp_3d + vp2rho_3d over n values (src/utils.f90:102-112,125-134; called from
+ * src/likelihood.f90:75-76): vp = vs*1.730, rho = 1.74*vp**0.25. */
+int mct_vs2vp_rho(const double* vs, double* vp, double* rho, int64_t n);
+int mct_vs2vp_rho_dev(const double* d_vs, double* d_vp, double* d_rho, int64_t n, void* stream);
+
+/* ---- stage 2: per-column modal dispersion ------------------------------------------------
+ * Replaces surf_likelihood's block likelihood_surf.F90:161-206 (check_model,
+ * convert_to_layer, the OpenMP loop over surfmodes) and the twin in
+ * forward_modelling.f90:393-429.
+ *   vp,vs,rho   (nz,ny,nx) host arrays (whole grid: check_model scans all of vs)
+ *   ix0..iy1    clamped 1-based inclusive column window (likelihood_surf.F90:155-169)
+ *   freqs       np frequencies in Hz (dat%freqs; periods = 1/freqs must ascend)
+ *   pvel, gvel  (np*nm, iy0:iy1, ix0:ix1), nm = max(nmodes,1); mode-major inside a column:
+ *               index ifreq + (imode-1)*np (surfmodes.f90:179-180)
+ *   ierr        (iy0:iy1, ix0:ix1): 0/1 as surfdisp96 sets it; 2/3/4 see MCT_E_*
+ *   model_invalid  out: 1 if check_model(vs) is .true. (likelihood_surf.F90:161-164,631-646);
+ *               the reference then returns before solving anything, and so does this call
+ *               (outputs untouched).  Pass NULL to skip the check (forward_modelling.f90 has none).
+ * Returns MCT_OK, or the largest per-column condition code >= 2 that occurred.
+ */
+int mct_surf_dispersion(const double* vp, const double* vs, const double* rho, const mct_grid* g, int ix0,
+                        int ix1, int iy0, int iy1, const double* freqs, int np, const mct_disp_opts* opt,
+                        double* pvel, double* gvel, int32_t* ierr, int32_t* model_invalid);
+
+int mct_surf_dispersion_dev(const double* d_vp, const double* d_vs, const double* d_rho, const mct_grid* g,
+                            int ix0, int ix1, int iy0, int iy1, const double* freqs, int np,
+                            const mct_disp_opts* opt, double* d_pvel, double* d_gvel, int32_t* d_ierr,
+                            int32_t* d_flags /* [0]=model_invalid, [1]=max condition code; may be NULL */,
+                            void* stream);
+
+/* surfmodes / surfmmodes for columns that are already layered (surfmodes.f90:39-49,110-120):
+ * column c owns layers offsets[c] .. offsets[c+1]-1 of thick/vp/vs/rho (top to bottom, last
+ * one the half-space).  phase, group: (np*nm, ncol); ierr: (ncol). */
+int mct_surfmodes_batch(const double* thick, const double* vp, const double* vs, const double* rho,
+                        const int64_t* offsets, int ncol, const double* freqs, int np,
+                        const mct_disp_opts* opt, double* phase, double* group, int32_t* ierr);
+
+/* ---- fused forward evaluation --------------------------------------------------------------
+ * Stage 1 over the whole grid, the datatype-2 property maps, check_model and stage 2 over all
+ * columns, with the gridded model staying in HBM (the sequence kdtree_to_grid -> likelihood ->
+ * surf_likelihood of mcmc_loc2.f90:139-143 for a full bounding box).  Only the nuclei go in and
+ * only the dispersion maps (+ optionally the gridded model) come out.
+ *   derive_vp_rho  1: datatype 2 (vp, rho recomputed from vs over the grid); 0: keep params' vp, rho
+ *   vp,vs,rho,sites_id  optional host outputs (NULL = leave on device)
+ */
+int mct_forward_eval(const double* points, const double* params, int ncells, const mct_grid* g,
+                     int derive_vp_rho, const double* freqs, int np, const mct_disp_opts* opt, double* pvel,
+                     double* gvel, int32_t* ierr, int32_t* model_invalid, double* vp, double* vs,
+                     double* rho, int32_t* sites_id);
+
+/* Same with device outputs (d_pvel/d_gvel (np*nm,ny,nx), d_ierr (ny,nx), d_flags[2]) and an
+ * x-slab restriction ixs0..ixs1 (1-based inclusive; whole grid = 1..nx) used to shard the
+ * columns of one chain across GPUs: only that slab is gridded and solved, outputs are indexed
+ * relative to the slab.  d_model = {d_vp,d_vs,d_rho,d_sites} whole-grid device arrays. */
+int mct_forward_eval_dev(const double* points, const double* params, int ncells, const mct_grid* g,
+                         int derive_vp_rho, int ixs0, int ixs1, const double* freqs, int np,
+                         const mct_disp_opts* opt, double* d_vp, double* d_vs, double* d_rho,
+                         int32_t* d_sites_id, double* d_pvel, double* d_gvel, int32_t* d_ierr,
+                         int32_t* d_flags, void* stream);
+
+/* Map assembly of likelihood_surf.F90:259-264 on the device: scatter a window of pvel into the
+ * padded (np, ny+2, nx+2) field and replicate the edges the window touches. */
+int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, int ix1, int iy0, int iy1,
+                         double* d_vel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCTOMO_B200_H */

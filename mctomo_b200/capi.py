@@ -1,0 +1,314 @@
+"""ctypes binding of libmctomo_b200.so (include/mctomo_b200.h) plus a thin host-side mirror of
+the two reference subroutines the library stands behind:
+
+  kdtree_to_grid(RTI, grid, bnd_box, model, pm)      reference src/mcmc_loc2.f90:2002-2082
+  surf_likelihood's dispersion block                  reference src/likelihood_surf.F90:155-231
+
+The production host is Fortran (fortran/mctomo_b200_shim.f90); this module exists so the parity
+tests and bench.py can drive the very same C entry points from Python.  There is no fallback:
+if the shared library is missing or no CUDA device is usable, importing/initialising raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmctomo_b200.so")
+
+MCT_OK = 0
+MCT_E_INVALID_ARG = 1
+MCT_E_GRT_NEEDED = 2
+MCT_E_TOO_MANY_LAYERS = 3
+MCT_E_DEGENERATE_NUCLEI = 4
+MCT_E_FLUID_BELOW_TOP = 5
+MCT_E_NOINIT = -1
+MCT_E_CUDA = -2
+
+# default-real Fortran literals widened to double, as the reference stores them
+EPS_LIKELIHOOD = float(np.float32(1e-10))   # likelihood_surf.F90:37
+EPS_MODELLING = float(np.float32(1e-5))     # forward_modelling.f90:27
+DPHASE_DEFAULT = 1e-3                       # examples/example1/MCTomo.inp:48
+
+
+class MctError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mctomo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class mct_grid(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("xmin", C.c_double), ("ymin", C.c_double), ("zmin", C.c_double),
+                ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+                ("waterDepth", C.c_double), ("scaling", C.c_double)]
+
+
+class mct_disp_opts(C.Structure):
+    _fields_ = [("raylov", C.c_int32), ("phaseGroup", C.c_int32), ("nmodes", C.c_int32),
+                ("dphase", C.c_double), ("layer_eps", C.c_double), ("water_thresh", C.c_double),
+                ("preset", C.c_double)]
+
+
+class mct_stats(C.Structure):
+    _fields_ = [("n_dltar", C.c_int64), ("n_layer_steps", C.c_int64), ("n_columns", C.c_int64),
+                ("n_nodes", C.c_int64), ("n_launches", C.c_int64)]
+
+
+@dataclass
+class Grid:
+    """Mirror of T_GRID + grid_setup (reference src/settings.f90:20-28,100-123)."""
+    nx: int
+    ny: int
+    nz: int
+    xmin: float
+    xmax: float
+    ymin: float
+    ymax: float
+    zmin: float
+    zmax: float
+    waterDepth: float = 0.0
+    scaling: float = 1.0
+
+    def __post_init__(self):
+        # grid_setup: zmin/zmax are scaled, spacing = extent/(n-1)
+        self.zmin = self.zmin * self.scaling
+        self.zmax = self.zmax * self.scaling
+        self.dx = (self.xmax - self.xmin) / (self.nx - 1)
+        self.dy = (self.ymax - self.ymin) / (self.ny - 1)
+        self.dz = (self.zmax - self.zmin) / (self.nz - 1)
+
+    def c(self) -> mct_grid:
+        return mct_grid(self.nx, self.ny, self.nz, self.xmin, self.ymin, self.zmin, self.dx, self.dy, self.dz,
+                        self.waterDepth, self.scaling)
+
+    @property
+    def shape(self):
+        """numpy shape of a (nz,ny,nx) Fortran array viewed C-contiguously: [ix][iy][iz]."""
+        return (self.nx, self.ny, self.nz)
+
+    def full_box(self):
+        return np.array([self.xmin, self.ymin, self.zmin, self.xmax, self.ymax, self.zmax], dtype=np.float64)
+
+
+def disp_opts(raylov=1, phaseGroup=0, nmodes=0, dphase=DPHASE_DEFAULT, variant="likelihood") -> mct_disp_opts:
+    """variant 'likelihood' = likelihood_surf.F90 constants, 'modelling' = forward_modelling.f90 constants."""
+    if variant == "likelihood":
+        return mct_disp_opts(raylov, phaseGroup, nmodes, dphase, EPS_LIKELIHOOD, EPS_LIKELIHOOD, 100.0)
+    if variant == "modelling":
+        return mct_disp_opts(raylov, phaseGroup, nmodes, dphase, EPS_MODELLING, 0.0, 1000.0)
+    raise ValueError(variant)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    gp = C.POINTER(mct_grid)
+    op = C.POINTER(mct_disp_opts)
+    L.mct_last_error.restype = C.c_char_p
+    L.mct_init.argtypes = [C.c_int]
+    L.mct_get_stats.argtypes = [C.POINTER(mct_stats)]
+    L.mct_set_counters.argtypes = [C.c_int]
+    L.mct_box_window.argtypes = [gp, vp, vp]
+    L.mct_voronoi_to_grid.argtypes = [vp, vp, C.c_int, gp, vp, vp, vp, vp, vp, vp]
+    L.mct_voronoi_to_grid_dev.argtypes = [vp, vp, C.c_int, gp, vp, vp, vp, vp, vp, vp, vp]
+    L.mct_vs2vp_rho.argtypes = [vp, vp, vp, C.c_int64]
+    L.mct_vs2vp_rho_dev.argtypes = [vp, vp, vp, C.c_int64, vp]
+    L.mct_surf_dispersion.argtypes = [vp, vp, vp, gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, op, vp, vp, vp, vp]
+    L.mct_surf_dispersion_dev.argtypes = [vp, vp, vp, gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, op, vp, vp, vp, vp, vp]
+    L.mct_surfmodes_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, op, vp, vp, vp]
+    L.mct_forward_eval.argtypes = [vp, vp, C.c_int, gp, C.c_int, vp, C.c_int, op, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.mct_forward_eval_dev.argtypes = [vp, vp, C.c_int, gp, C.c_int, C.c_int, C.c_int, vp, C.c_int, op,
+                                       vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.mct_assemble_vel_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int, allow=()):
+    if rc != MCT_OK and rc not in allow:
+        raise MctError(rc, lib().mct_last_error().decode())
+    return rc
+
+
+def init(device: int = 0):
+    _check(lib().mct_init(device))
+
+
+def shutdown():
+    _check(lib().mct_shutdown())
+
+
+def stats() -> dict:
+    s = mct_stats()
+    _check(lib().mct_get_stats(C.byref(s)))
+    return {k: getattr(s, k) for k, _ in mct_stats._fields_}
+
+
+def reset_stats():
+    _check(lib().mct_reset_stats())
+
+
+def set_counters(on: bool):
+    _check(lib().mct_set_counters(1 if on else 0))
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def box_window(grid: Grid, box) -> np.ndarray:
+    w = np.zeros(6, np.int32)
+    b = _f64(box)
+    _check(lib().mct_box_window(C.byref(grid.c()), b.ctypes.data, w.ctypes.data))
+    return w
+
+
+def kdtree_to_grid(points, params, grid: Grid, bnd_box, vp, vs, rho, sites_id, pm=None):
+    """Drop-in for kdtree_to_grid (reference src/mcmc_loc2.f90:2002-2082).
+
+    points, params: (ncells,3) C-contiguous == Fortran (3,ncells); vp, vs, rho (float64) and sites_id
+    (int32) have shape grid.shape == Fortran (nz,ny,nx) and are updated IN PLACE inside the window.
+    """
+    points = _f64(points)
+    params = _f64(params)
+    for a, dt in ((vp, np.float64), (vs, np.float64), (rho, np.float64), (sites_id, np.int32)):
+        assert a.dtype == dt and a.flags.c_contiguous and a.shape == grid.shape
+    box = _f64(bnd_box)
+    pmv = None if pm is None else _f64(pm)
+    _check(lib().mct_voronoi_to_grid(points.ctypes.data, params.ctypes.data, len(points), C.byref(grid.c()),
+                                     box.ctypes.data, _ptr(pmv), vp.ctypes.data, vs.ctypes.data, rho.ctypes.data,
+                                     sites_id.ctypes.data))
+
+
+def vs2vp_rho(vs):
+    """vs2vp_3d + vp2rho_3d (reference src/utils.f90:102-134)."""
+    vs = _f64(vs)
+    vp = np.empty_like(vs)
+    rho = np.empty_like(vs)
+    _check(lib().mct_vs2vp_rho(vs.ctypes.data, vp.ctypes.data, rho.ctypes.data, vs.size))
+    return vp, rho
+
+
+def surf_dispersion(vp, vs, rho, grid: Grid, window, freqs, opts: mct_disp_opts, check=True):
+    """The dispersion block of surf_likelihood (reference src/likelihood_surf.F90:155-231).
+
+    window = (ix0, ix1, iy0, iy1), 1-based inclusive.  Returns (pvel, gvel, ierr, model_invalid, rc) with
+    pvel/gvel of shape (wx, wy, nm*np) and ierr (wx, wy).
+    """
+    vp, vs, rho, freqs = _f64(vp), _f64(vs), _f64(rho), _f64(freqs)
+    ix0, ix1, iy0, iy1 = (int(v) for v in window)
+    wx, wy = ix1 - ix0 + 1, iy1 - iy0 + 1
+    nm = max(opts.nmodes, 1)
+    pvel = np.zeros((wx, wy, nm * len(freqs)))
+    gvel = np.zeros_like(pvel)
+    ierr = np.zeros((wx, wy), np.int32)
+    inval = C.c_int32(0)
+    rc = _check(lib().mct_surf_dispersion(vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, C.byref(grid.c()), ix0, ix1,
+                                          iy0, iy1, freqs.ctypes.data, len(freqs), C.byref(opts), pvel.ctypes.data,
+                                          gvel.ctypes.data, ierr.ctypes.data, C.byref(inval) if check else None),
+                allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+    return pvel, gvel, ierr, inval.value, rc
+
+
+def surfmodes_batch(thick, vp, vs, rho, offsets, freqs, opts: mct_disp_opts):
+    """surfmodes / surfmmodes over pre-layered columns (reference surfmodes/surfmodes.f90:39-183)."""
+    thick, vp, vs, rho, freqs = _f64(thick), _f64(vp), _f64(vs), _f64(rho), _f64(freqs)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    ncol = len(offsets) - 1
+    nm = max(opts.nmodes, 1)
+    phase = np.zeros((ncol, nm * len(freqs)))
+    group = np.zeros_like(phase)
+    ierr = np.zeros(ncol, np.int32)
+    rc = _check(lib().mct_surfmodes_batch(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data,
+                                          offsets.ctypes.data, ncol, freqs.ctypes.data, len(freqs), C.byref(opts),
+                                          phase.ctypes.data, group.ctypes.data, ierr.ctypes.data),
+                allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+    return phase, group, ierr, rc
+
+
+def forward_eval(points, params, grid: Grid, freqs, opts: mct_disp_opts, derive_vp_rho=True, want_model=False,
+                 out=None):
+    """kdtree_to_grid (full box) -> vs2vp/vp2rho -> check_model -> dispersion, model resident in HBM.
+
+    `out` may hold preallocated (ideally pinned) arrays 'pvel','gvel','ierr' to avoid allocations.
+    """
+    points, params, freqs = _f64(points), _f64(params), _f64(freqs)
+    nm = max(opts.nmodes, 1)
+    if out is None:
+        out = {}
+    pvel = out.get("pvel")
+    if pvel is None:
+        pvel = np.zeros((grid.nx, grid.ny, nm * len(freqs)))
+    gvel = out.get("gvel")
+    if gvel is None:
+        gvel = np.zeros_like(pvel)
+    ierr = out.get("ierr")
+    if ierr is None:
+        ierr = np.zeros((grid.nx, grid.ny), np.int32)
+    inval = C.c_int32(0)
+    vp = vs = rho = sid = None
+    if want_model:
+        vp = np.zeros(grid.shape)
+        vs = np.zeros(grid.shape)
+        rho = np.zeros(grid.shape)
+        sid = np.zeros(grid.shape, np.int32)
+    rc = _check(lib().mct_forward_eval(points.ctypes.data, params.ctypes.data, len(points), C.byref(grid.c()),
+                                       1 if derive_vp_rho else 0, freqs.ctypes.data, len(freqs), C.byref(opts),
+                                       pvel.ctypes.data, gvel.ctypes.data, ierr.ctypes.data, C.byref(inval), _ptr(vp),
+                                       _ptr(vs), _ptr(rho), _ptr(sid)),
+                allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+    res = {"pvel": pvel, "gvel": gvel, "ierr": ierr, "model_invalid": inval.value, "rc": rc}
+    if want_model:
+        res.update(vp=vp, vs=vs, rho=rho, sites_id=sid)
+    return res
+
+
+# ---- device-pointer forms (torch tensors give the pointers and the stream) -----------------------
+
+def forward_eval_dev(points, params, grid: Grid, freqs, opts: mct_disp_opts, d_vp, d_vs, d_rho, d_sites, d_pvel,
+                     d_gvel, d_ierr, d_flags, stream, derive_vp_rho=True, slab=None):
+    """mct_forward_eval_dev: arguments are raw device pointers (ints) and a cudaStream_t handle (int)."""
+    points, params, freqs = _f64(points), _f64(params), _f64(freqs)
+    ixs0, ixs1 = (1, grid.nx) if slab is None else slab
+    return _check(lib().mct_forward_eval_dev(points.ctypes.data, params.ctypes.data, len(points), C.byref(grid.c()),
+                                             1 if derive_vp_rho else 0, ixs0, ixs1, freqs.ctypes.data, len(freqs),
+                                             C.byref(opts), d_vp, d_vs, d_rho, d_sites, d_pvel, d_gvel, d_ierr, d_flags,
+                                             stream))
+
+
+def surf_dispersion_dev(d_vp, d_vs, d_rho, grid: Grid, window, freqs, opts, d_pvel, d_gvel, d_ierr, d_flags, stream):
+    freqs = _f64(freqs)
+    ix0, ix1, iy0, iy1 = (int(v) for v in window)
+    return _check(lib().mct_surf_dispersion_dev(d_vp, d_vs, d_rho, C.byref(grid.c()), ix0, ix1, iy0, iy1,
+                                                freqs.ctypes.data, len(freqs), C.byref(opts), d_pvel, d_gvel, d_ierr,
+                                                d_flags, stream))
+
+
+def voronoi_to_grid_dev(points, params, grid: Grid, box, d_vp, d_vs, d_rho, d_sites, stream, pm=None):
+    points, params, box = _f64(points), _f64(params), _f64(box)
+    pmv = None if pm is None else _f64(pm)
+    return _check(lib().mct_voronoi_to_grid_dev(points.ctypes.data, params.ctypes.data, len(points), C.byref(grid.c()),
+                                                box.ctypes.data, _ptr(pmv), d_vp, d_vs, d_rho, d_sites, stream))
+
+
+def assemble_vel_dev(d_pvel, np_, nx, ny, window, d_vel, stream):
+    ix0, ix1, iy0, iy1 = (int(v) for v in window)
+    return _check(lib().mct_assemble_vel_dev(d_pvel, np_, nx, ny, ix0, ix1, iy0, iy1, d_vel, stream))

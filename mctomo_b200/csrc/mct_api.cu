@@ -1,0 +1,682 @@
+// mct_api.cu -- the C ABI of include/mctomo_b200.h: context, device buffers, host-side kd-tree
+// build, kernel launches and the host<->device staging of the host-pointer entry points.
+//
+// Host logic mirrored here (reference lines per function in the header):
+//   kdtree_to_grid   src/mcmc_loc2.f90:2002-2082        -> mct_voronoi_to_grid[_dev]
+//   surf_likelihood  src/likelihood_surf.F90:155-231    -> mct_surf_dispersion[_dev]
+//   program modelling src/forward_modelling.f90:393-429 -> same, with its layer_eps / preset
+//   surfmodes / surfmmodes surfmodes/surfmodes.f90:39-183 -> mct_surfmodes_batch
+// There is no CPU implementation of any kernel in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "../../include/mctomo_b200.h"
+#include "k1_voronoi.cuh"
+#include "k2_dispersion.cuh"
+#include "kdtree_build.h"
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Ctx {
+  bool init = false;
+  int device = -1;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int count_on = 1;
+  char err[512] = {0};
+  // nuclei / tree
+  DevBuf nodes, rpts, ind, params;
+  HostKdTree tree;
+  // staged model (host-pointer entry points)
+  DevBuf m_vp, m_vs, m_rho, m_sites;
+  // layered columns
+  DevBuf lay, nlay, status;
+  // outputs (host-pointer entry points)
+  DevBuf o_pvel, o_gvel, o_ierr;
+  // prelayered staging
+  DevBuf pl_thick, pl_vp, pl_vs, pl_rho, pl_off;
+  DevBuf flags;    // int32[4]: [0] model_invalid, [1] max status, [2] k1 error
+  DevBuf counters; // u64[4]
+  PinBuf pin_a, pin_b, pin_small;
+  mct_stats host_stats = {0, 0, 0, 0, 0};
+};
+
+Ctx g;
+std::mutex g_mu;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g.err, sizeof g.err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(MCT_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define NEED_INIT()                                                            \
+  do {                                                                         \
+    if (!g.init) return fail(MCT_E_NOINIT, "mct_init has not been called");    \
+  } while (0)
+
+int ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return MCT_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return MCT_OK;
+}
+int ensure_pin(PinBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return MCT_OK;
+  if (b.p) CK(cudaFreeHost(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMallocHost(&b.p, want));
+  b.cap = want;
+  return MCT_OK;
+}
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+void release(PinBuf& b) {
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+inline cudaStream_t pick(void* stream) { return stream ? (cudaStream_t)stream : g.stream; }
+
+bool grid_ok(const mct_grid* gr) {
+  return gr && gr->nx >= 1 && gr->ny >= 1 && gr->nz >= 1 && gr->dx > 0 && gr->dy > 0 && gr->dz > 0;
+}
+
+// floor((b - min)/d) + 1, clamped: src/mcmc_loc2.f90:2034-2045
+void box_window(const mct_grid* gr, const double box[6], int32_t w[6]) {
+  w[0] = (int32_t)std::floor((box[0] - gr->xmin) / gr->dx) + 1;
+  w[1] = (int32_t)std::floor((box[3] - gr->xmin) / gr->dx) + 1;
+  w[2] = (int32_t)std::floor((box[1] - gr->ymin) / gr->dy) + 1;
+  w[3] = (int32_t)std::floor((box[4] - gr->ymin) / gr->dy) + 1;
+  w[4] = (int32_t)std::floor((box[2] - gr->zmin) / gr->dz) + 1;
+  w[5] = (int32_t)std::floor((box[5] - gr->zmin) / gr->dz) + 1;
+  if (w[0] < 1) w[0] = 1;
+  if (w[2] < 1) w[2] = 1;
+  if (w[4] < 1) w[4] = 1;
+  if (w[1] > gr->nx) w[1] = gr->nx;
+  if (w[3] > gr->ny) w[3] = gr->ny;
+  if (w[5] > gr->nz) w[5] = gr->nz;
+}
+
+// Build the tree on the host and upload it together with the nuclei parameters.
+int upload_nuclei(const double* points, const double* params, int ncells, cudaStream_t st) {
+  if (!points || !params || ncells < 1) return fail(MCT_E_INVALID_ARG, "nuclei: NULL pointer or ncells < 1");
+  KdBuilder(points, ncells, g.tree).run();
+  if (g.tree.degenerate)
+    return fail(MCT_E_DEGENERATE_NUCLEI, "more than 13 nuclei coincide: the reference kd-tree build does not terminate");
+  const size_t nb_nodes = g.tree.nodes.size() * sizeof(KdNodeDev);
+  const size_t nb_pts = 3 * sizeof(double) * (size_t)ncells;
+  const size_t nb_ind = sizeof(int32_t) * (size_t)ncells;
+  int rc;
+  if ((rc = ensure(g.nodes, nb_nodes))) return rc;
+  if ((rc = ensure(g.rpts, nb_pts))) return rc;
+  if ((rc = ensure(g.ind, nb_ind))) return rc;
+  if ((rc = ensure(g.params, nb_pts))) return rc;
+  // one pinned staging block so the four small copies are true async DMA
+  const size_t tot = nb_nodes + 2 * nb_pts + nb_ind;
+  if ((rc = ensure_pin(g.pin_small, tot))) return rc;
+  CK(cudaStreamSynchronize(st)); // the staging block may still be in flight from the previous call
+  char* h = (char*)g.pin_small.p;
+  memcpy(h, g.tree.nodes.data(), nb_nodes);
+  memcpy(h + nb_nodes, g.tree.rpts.data(), nb_pts);
+  memcpy(h + nb_nodes + nb_pts, params, nb_pts);
+  memcpy(h + nb_nodes + 2 * nb_pts, g.tree.ind.data(), nb_ind);
+  CK(cudaMemcpyAsync(g.nodes.p, h, nb_nodes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.rpts.p, h + nb_nodes, nb_pts, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.params.p, h + nb_nodes + nb_pts, nb_pts, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.ind.p, h + nb_nodes + 2 * nb_pts, nb_ind, cudaMemcpyHostToDevice, st));
+  return MCT_OK;
+}
+
+int grid_blocks(long long work_items, int threads, int per_sm) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)g.sm_count * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// Launch K1 on device arrays with the given array geometry.
+int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* d_vp, double* d_vs, double* d_rho,
+              int32_t* d_sites, int ia0, int ja0, int ka0, int ny_a, int nz_a, cudaStream_t st) {
+  K1Params P;
+  P.nodes = (const KdNodeDev*)g.nodes.p;
+  P.rpts = (const double*)g.rpts.p;
+  P.ind = (const int32_t*)g.ind.p;
+  P.params = (const double*)g.params.p;
+  P.root = g.tree.root;
+  P.ix0 = w[0]; P.iy0 = w[2]; P.iz0 = w[4];
+  P.wx = w[1] - w[0] + 1; P.wy = w[3] - w[2] + 1; P.wz = w[5] - w[4] + 1;
+  if (P.wx <= 0 || P.wy <= 0 || P.wz <= 0) return MCT_OK; // empty window: the Fortran loops do nothing
+  P.xmin = gr->xmin; P.ymin = gr->ymin; P.zmin = gr->zmin;
+  P.dx = gr->dx; P.dy = gr->dy; P.dz = gr->dz;
+  P.ia0 = ia0; P.ja0 = ja0; P.ka0 = ka0; P.ny_a = ny_a; P.nz_a = nz_a;
+  P.vp = d_vp; P.vs = d_vs; P.rho = d_rho; P.sites = d_sites;
+  P.use_pm = pm ? 1 : 0;
+  P.pm_vp = pm ? pm[0] : 0.0;
+  P.pm_vs = pm ? pm[1] : 0.0;
+  P.pm_eps = (double)1e-8f; // real(kind=ii10), parameter :: eps = 1e-8 (mcmc_loc2.f90:51)
+  P.err = (int32_t*)g.flags.p + 2;
+  const long long total = (long long)P.wx * P.wy * P.wz;
+  k1_voronoi_kernel<<<grid_blocks(total, 256, 16), 256, 0, st>>>(P);
+  CK(cudaGetLastError());
+  g.host_stats.n_nodes += total;
+  g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+
+struct DispPlan {
+  int ix0, ix1, iy0, iy1, wx, wy, ncol, stride, nm, nout;
+};
+
+int plan_disp(const mct_grid* gr, int ix0, int ix1, int iy0, int iy1, int np, const mct_disp_opts* opt, DispPlan& pl) {
+  if (!grid_ok(gr) || !opt) return fail(MCT_E_INVALID_ARG, "dispersion: bad grid or NULL options");
+  if (np < 1 || np > MCT_MAX_PERIODS) return fail(MCT_E_INVALID_ARG, "dispersion: np must be in 1..%d", MCT_MAX_PERIODS);
+  if (ix0 < 1 || iy0 < 1 || ix1 > gr->nx || iy1 > gr->ny || ix1 < ix0 || iy1 < iy0)
+    return fail(MCT_E_INVALID_ARG, "dispersion: window %d..%d x %d..%d outside the %d x %d grid", ix0, ix1, iy0, iy1, gr->nx, gr->ny);
+  if (opt->raylov != 0 && opt->raylov != 1) return fail(MCT_E_INVALID_ARG, "dispersion: raylov must be 0 (Love) or 1 (Rayleigh)");
+  if (!(gr->scaling != 0.0)) return fail(MCT_E_INVALID_ARG, "dispersion: grid scaling must be non-zero");
+  pl.ix0 = ix0; pl.ix1 = ix1; pl.iy0 = iy0; pl.iy1 = iy1;
+  pl.wx = ix1 - ix0 + 1; pl.wy = iy1 - iy0 + 1;
+  pl.ncol = pl.wx * pl.wy;
+  pl.stride = (pl.ncol + 31) & ~31;
+  pl.nm = opt->nmodes <= 0 ? 1 : opt->nmodes;
+  pl.nout = np * pl.nm;
+  return MCT_OK;
+}
+
+int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_opts* opt, double* d_pvel, double* d_gvel,
+              int32_t* d_ierr, const int32_t* d_skip, cudaStream_t st) {
+  K2Params P;
+  P.lay = (const float4*)g.lay.p;
+  P.nlay = (const int32_t*)g.nlay.p;
+  P.status = (const int32_t*)g.status.p;
+  P.ncol = ncol;
+  P.stride = stride;
+  P.kmax = np;
+  P.nmode = opt->nmodes <= 0 ? 1 : opt->nmodes;
+  P.mmode = opt->nmodes <= 0 ? 0 : 1;
+  P.ifunc = opt->raylov == 1 ? 2 : 1; // surfmodes.f90:82,94: iwave 2 Rayleigh, 1 Love
+  P.igr = opt->phaseGroup;
+  P.count = g.count_on;
+  P.ddc0 = (float)opt->dphase; // ddc0 = dphase (surfdisp96.f:130)
+  P.preset_unsolved = opt->preset;
+  P.pvel = d_pvel;
+  P.gvel = d_gvel;
+  P.ierr = d_ierr;
+  P.skip = d_skip;
+  P.counters = (unsigned long long*)g.counters.p;
+  for (int i = 0; i < MCT_MAX_PERIODS; ++i) P.t[i] = (i < np) ? 1 / freqs[i] : 0.0; // dble(1/freqs), surfmodes.f90:82
+  k2_dispersion_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+
+// check_model + layerize + K2 on device-resident whole-grid arrays.
+int disp_core(const double* d_vp, const double* d_vs, const double* d_rho, const mct_grid* gr, const DispPlan& pl,
+              const double* freqs, int np, const mct_disp_opts* opt, bool do_check, long long check_col0,
+              long long check_ncols, double* d_pvel, double* d_gvel, int32_t* d_ierr, int32_t* d_flags, cudaStream_t st) {
+  int rc;
+  if ((rc = ensure(g.lay, sizeof(float4) * (size_t)pl.stride * (size_t)(gr->nz + 1)))) return rc;
+  if ((rc = ensure(g.nlay, sizeof(int32_t) * (size_t)pl.stride))) return rc;
+  if ((rc = ensure(g.status, sizeof(int32_t) * (size_t)pl.stride))) return rc;
+  CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int32_t), st));
+  if (do_check) {
+    check_model_kernel<<<grid_blocks(check_ncols * 32, 256, 8), 256, 0, st>>>(d_vs, check_col0, check_ncols, gr->nz, d_flags);
+    CK(cudaGetLastError());
+    g.host_stats.n_launches += 1;
+  }
+  LayParams L;
+  L.vp = d_vp; L.vs = d_vs; L.rho = d_rho;
+  L.ny = gr->ny; L.nz = gr->nz;
+  L.ix0 = pl.ix0; L.iy0 = pl.iy0; L.wx = pl.wx; L.wy = pl.wy;
+  L.dz = gr->dz; L.waterDepth = gr->waterDepth; L.scaling = gr->scaling;
+  L.layer_eps = opt->layer_eps; L.water_thresh = opt->water_thresh;
+  L.modetype = opt->raylov;
+  L.lay = (float4*)g.lay.p; L.nlay = (int32_t*)g.nlay.p; L.status = (int32_t*)g.status.p;
+  L.stride = pl.stride;
+  L.flags = d_flags;
+  layerize_kernel<<<(pl.ncol + 127) / 128, 128, 0, st>>>(L);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  return launch_k2(pl.ncol, pl.stride, freqs, np, opt, d_pvel, d_gvel, d_ierr, do_check ? d_flags : nullptr, st);
+}
+
+} // namespace
+
+extern "C" {
+
+const char* mct_last_error(void) { return g.err; }
+
+int mct_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g.init) {
+    if (device == g.device) return MCT_OK;
+    return fail(MCT_E_INVALID_ARG, "already initialised on device %d", g.device);
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(MCT_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(MCT_E_INVALID_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  g.sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  g.device = device;
+  int rc;
+  if ((rc = ensure(g.flags, 4 * sizeof(int32_t)))) return rc;
+  if ((rc = ensure(g.counters, 4 * sizeof(unsigned long long)))) return rc;
+  CK(cudaMemset(g.flags.p, 0, 4 * sizeof(int32_t)));
+  CK(cudaMemset(g.counters.p, 0, 4 * sizeof(unsigned long long)));
+  g.host_stats = mct_stats{0, 0, 0, 0, 0};
+  g.init = true;
+  return MCT_OK;
+}
+
+int mct_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.init) return MCT_OK;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.nlay, &g.status,
+                    &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters};
+  for (DevBuf* b : bufs) release(*b);
+  release(g.pin_a);
+  release(g.pin_b);
+  release(g.pin_small);
+  cudaStreamDestroy(g.stream);
+  g.stream = nullptr;
+  g.init = false;
+  return MCT_OK;
+}
+
+int mct_set_counters(int on) {
+  g.count_on = on ? 1 : 0;
+  return MCT_OK;
+}
+
+int mct_reset_stats(void) {
+  NEED_INIT();
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaMemset(g.counters.p, 0, 4 * sizeof(unsigned long long)));
+  g.host_stats = mct_stats{0, 0, 0, 0, 0};
+  return MCT_OK;
+}
+
+int mct_get_stats(mct_stats* out) {
+  NEED_INIT();
+  if (!out) return fail(MCT_E_INVALID_ARG, "NULL stats pointer");
+  unsigned long long c[4];
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(c, g.counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  *out = g.host_stats;
+  out->n_dltar = (int64_t)c[0];
+  out->n_layer_steps = (int64_t)c[1];
+  out->n_columns = (int64_t)c[2];
+  return MCT_OK;
+}
+
+int mct_box_window(const mct_grid* gr, const double box[6], int32_t w[6]) {
+  if (!grid_ok(gr) || !box || !w) return fail(MCT_E_INVALID_ARG, "box_window: bad arguments");
+  box_window(gr, box, w);
+  return MCT_OK;
+}
+
+int mct_voronoi_to_grid_dev(const double* points, const double* params, int ncells, const mct_grid* gr, const double box[6],
+                            const double* pm, double* d_vp, double* d_vs, double* d_rho, int32_t* d_sites_id, void* stream) {
+  NEED_INIT();
+  if (!grid_ok(gr) || !box || !d_vp || !d_vs || !d_rho || !d_sites_id) return fail(MCT_E_INVALID_ARG, "voronoi_to_grid: bad arguments");
+  cudaStream_t st = pick(stream);
+  int rc = upload_nuclei(points, params, ncells, st);
+  if (rc) return rc;
+  int32_t w[6];
+  box_window(gr, box, w);
+  return launch_k1(gr, w, pm, d_vp, d_vs, d_rho, d_sites_id, 1, 1, 1, gr->ny, gr->nz, st);
+}
+
+int mct_voronoi_to_grid(const double* points, const double* params, int ncells, const mct_grid* gr, const double box[6],
+                        const double* pm, double* vp, double* vs, double* rho, int32_t* sites_id) {
+  NEED_INIT();
+  if (!grid_ok(gr) || !box || !vp || !vs || !rho || !sites_id) return fail(MCT_E_INVALID_ARG, "voronoi_to_grid: bad arguments");
+  cudaStream_t st = g.stream;
+  int rc = upload_nuclei(points, params, ncells, st);
+  if (rc) return rc;
+  int32_t w[6];
+  box_window(gr, box, w);
+  const int wx = w[1] - w[0] + 1, wy = w[3] - w[2] + 1, wz = w[5] - w[4] + 1;
+  if (wx <= 0 || wy <= 0 || wz <= 0) return MCT_OK;
+  // The window is staged as a packed (wz,wy,wx) block: gather (pm mode only) -> H2D -> K1 -> D2H -> scatter.
+  const size_t nn = (size_t)wx * wy * wz;
+  if ((rc = ensure(g.m_vp, nn * 8))) return rc;
+  if ((rc = ensure(g.m_vs, nn * 8))) return rc;
+  if ((rc = ensure(g.m_rho, nn * 8))) return rc;
+  if ((rc = ensure(g.m_sites, nn * 4))) return rc;
+  if ((rc = ensure_pin(g.pin_a, nn * 28))) return rc;
+  double* h_vp = (double*)g.pin_a.p;
+  double* h_vs = h_vp + nn;
+  double* h_rho = h_vs + nn;
+  int32_t* h_sid = (int32_t*)(h_rho + nn);
+  const size_t ny = gr->ny, nz = gr->nz;
+  const bool full_z = (wz == gr->nz);
+  auto for_rows = [&](auto&& fn) { // fn(src offset in the user arrays, dst offset in the packed block, run length)
+    for (int i = 0; i < wx; ++i)
+      for (int j = 0; j < wy; ++j) {
+        const size_t uo = ((size_t)(w[0] - 1 + i) * ny + (size_t)(w[2] - 1 + j)) * nz + (size_t)(w[4] - 1);
+        const size_t po = ((size_t)i * wy + j) * wz;
+        fn(uo, po, (size_t)wz);
+      }
+  };
+  (void)full_z;
+  if (pm) {
+    for_rows([&](size_t uo, size_t po, size_t n) {
+      memcpy(h_vp + po, vp + uo, n * 8);
+      memcpy(h_vs + po, vs + uo, n * 8);
+      memcpy(h_rho + po, rho + uo, n * 8);
+      memcpy(h_sid + po, sites_id + uo, n * 4);
+    });
+    CK(cudaMemcpyAsync(g.m_vp.p, h_vp, nn * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.m_vs.p, h_vs, nn * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.m_rho.p, h_rho, nn * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.m_sites.p, h_sid, nn * 4, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync((int32_t*)g.flags.p + 2, 0, sizeof(int32_t), st));
+  rc = launch_k1(gr, w, pm, (double*)g.m_vp.p, (double*)g.m_vs.p, (double*)g.m_rho.p, (int32_t*)g.m_sites.p, w[0], w[2], w[4], wy, wz, st);
+  if (rc) return rc;
+  int32_t k1err = 0;
+  CK(cudaMemcpyAsync(h_vp, g.m_vp.p, nn * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_vs, g.m_vs.p, nn * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_rho, g.m_rho.p, nn * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_sid, g.m_sites.p, nn * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&k1err, (int32_t*)g.flags.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (k1err) return fail(MCT_E_CUDA, "nearest-nucleus traversal stack overflow (tree deeper than %d)", K1_STACK);
+  for_rows([&](size_t uo, size_t po, size_t n) {
+    memcpy(vp + uo, h_vp + po, n * 8);
+    memcpy(vs + uo, h_vs + po, n * 8);
+    memcpy(rho + uo, h_rho + po, n * 8);
+    memcpy(sites_id + uo, h_sid + po, n * 4);
+  });
+  return MCT_OK;
+}
+
+int mct_vs2vp_rho_dev(const double* d_vs, double* d_vp, double* d_rho, int64_t n, void* stream) {
+  NEED_INIT();
+  if (!d_vs || !d_vp || !d_rho || n < 0) return fail(MCT_E_INVALID_ARG, "vs2vp_rho: bad arguments");
+  if (n == 0) return MCT_OK;
+  vs2vp_rho_kernel<<<grid_blocks(n, 256, 8), 256, 0, pick(stream)>>>(d_vs, d_vp, d_rho, (long long)n);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+
+int mct_vs2vp_rho(const double* vs, double* vp, double* rho, int64_t n) {
+  NEED_INIT();
+  if (!vs || !vp || !rho || n < 0) return fail(MCT_E_INVALID_ARG, "vs2vp_rho: bad arguments");
+  if (n == 0) return MCT_OK;
+  int rc;
+  if ((rc = ensure(g.m_vs, (size_t)n * 8))) return rc;
+  if ((rc = ensure(g.m_vp, (size_t)n * 8))) return rc;
+  if ((rc = ensure(g.m_rho, (size_t)n * 8))) return rc;
+  cudaStream_t st = g.stream;
+  CK(cudaMemcpyAsync(g.m_vs.p, vs, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if ((rc = mct_vs2vp_rho_dev((double*)g.m_vs.p, (double*)g.m_vp.p, (double*)g.m_rho.p, n, st))) return rc;
+  CK(cudaMemcpyAsync(vp, g.m_vp.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rho, g.m_rho.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MCT_OK;
+}
+
+int mct_surf_dispersion_dev(const double* d_vp, const double* d_vs, const double* d_rho, const mct_grid* gr, int ix0, int ix1,
+                            int iy0, int iy1, const double* freqs, int np, const mct_disp_opts* opt, double* d_pvel,
+                            double* d_gvel, int32_t* d_ierr, int32_t* d_flags, void* stream) {
+  NEED_INIT();
+  if (!d_vp || !d_vs || !d_rho || !freqs || !d_pvel || !d_gvel || !d_ierr) return fail(MCT_E_INVALID_ARG, "surf_dispersion: NULL pointer");
+  DispPlan pl;
+  int rc = plan_disp(gr, ix0, ix1, iy0, iy1, np, opt, pl);
+  if (rc) return rc;
+  const bool chk = d_flags != nullptr;
+  int32_t* fl = d_flags ? d_flags : (int32_t*)g.flags.p;
+  return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, chk, 0, (long long)gr->nx * gr->ny, d_pvel, d_gvel, d_ierr, fl,
+                   pick(stream));
+}
+
+int mct_surf_dispersion(const double* vp, const double* vs, const double* rho, const mct_grid* gr, int ix0, int ix1, int iy0,
+                        int iy1, const double* freqs, int np, const mct_disp_opts* opt, double* pvel, double* gvel,
+                        int32_t* ierr, int32_t* model_invalid) {
+  NEED_INIT();
+  if (!vp || !vs || !rho || !freqs || !pvel || !gvel || !ierr) return fail(MCT_E_INVALID_ARG, "surf_dispersion: NULL pointer");
+  DispPlan pl;
+  int rc = plan_disp(gr, ix0, ix1, iy0, iy1, np, opt, pl);
+  if (rc) return rc;
+  cudaStream_t st = g.stream;
+  const size_t ncell = (size_t)gr->nx * gr->ny * gr->nz;
+  if ((rc = ensure(g.m_vp, ncell * 8))) return rc;
+  if ((rc = ensure(g.m_vs, ncell * 8))) return rc;
+  if ((rc = ensure(g.m_rho, ncell * 8))) return rc;
+  const size_t nbo = (size_t)pl.ncol * pl.nout * 8;
+  if ((rc = ensure(g.o_pvel, nbo))) return rc;
+  if ((rc = ensure(g.o_gvel, nbo))) return rc;
+  if ((rc = ensure(g.o_ierr, (size_t)pl.ncol * 4))) return rc;
+  // vs: whole grid when check_model is requested (it scans every column), else the window's x-range;
+  // vp, rho: the window's x-range only (each x index is one contiguous (nz,ny) slab).
+  const size_t slab = (size_t)gr->ny * gr->nz;
+  const size_t xoff = (size_t)(pl.ix0 - 1) * slab, xlen = (size_t)pl.wx * slab;
+  if (model_invalid) CK(cudaMemcpyAsync(g.m_vs.p, vs, ncell * 8, cudaMemcpyHostToDevice, st));
+  else CK(cudaMemcpyAsync((double*)g.m_vs.p + xoff, vs + xoff, xlen * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((double*)g.m_vp.p + xoff, vp + xoff, xlen * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((double*)g.m_rho.p + xoff, rho + xoff, xlen * 8, cudaMemcpyHostToDevice, st));
+  int32_t* fl = (int32_t*)g.flags.p;
+  rc = disp_core((double*)g.m_vp.p, (double*)g.m_vs.p, (double*)g.m_rho.p, gr, pl, freqs, np, opt, model_invalid != nullptr, 0,
+                 (long long)gr->nx * gr->ny, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, fl, st);
+  if (rc) return rc;
+  int32_t hflags[2] = {0, 0};
+  CK(cudaMemcpyAsync(hflags, fl, sizeof hflags, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (model_invalid) *model_invalid = hflags[0];
+  if (model_invalid && hflags[0]) return MCT_OK; // reference returns before solving (likelihood_surf.F90:161-164)
+  CK(cudaMemcpyAsync(pvel, g.o_pvel.p, nbo, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(gvel, g.o_gvel.p, nbo, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ierr, g.o_ierr.p, (size_t)pl.ncol * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hflags[1] >= 2) {
+    const int code = hflags[1] == 2 ? MCT_E_GRT_NEEDED : (hflags[1] == 3 ? MCT_E_TOO_MANY_LAYERS : MCT_E_FLUID_BELOW_TOP);
+    return fail(code, "dispersion: at least one column reported condition %d (see ierr)", hflags[1]);
+  }
+  return MCT_OK;
+}
+
+int mct_surfmodes_batch(const double* thick, const double* vp, const double* vs, const double* rho, const int64_t* offsets,
+                        int ncol, const double* freqs, int np, const mct_disp_opts* opt, double* phase, double* group,
+                        int32_t* ierr) {
+  NEED_INIT();
+  if (!thick || !vp || !vs || !rho || !offsets || !freqs || !opt || !phase || !group || !ierr || ncol < 1)
+    return fail(MCT_E_INVALID_ARG, "surfmodes_batch: bad arguments");
+  if (np < 1 || np > MCT_MAX_PERIODS) return fail(MCT_E_INVALID_ARG, "surfmodes_batch: np must be in 1..%d", MCT_MAX_PERIODS);
+  if (opt->raylov != 0 && opt->raylov != 1) return fail(MCT_E_INVALID_ARG, "surfmodes_batch: raylov must be 0 or 1");
+  const int64_t ntot = offsets[ncol] - offsets[0];
+  int maxl = 1;
+  for (int c = 0; c < ncol; ++c) {
+    const int64_t n = offsets[c + 1] - offsets[c];
+    if (n < 1) return fail(MCT_E_INVALID_ARG, "surfmodes_batch: column %d has no layers", c);
+    if (n > maxl) maxl = (int)(n > MCT_MAX_LAYERS ? MCT_MAX_LAYERS : n);
+  }
+  cudaStream_t st = g.stream;
+  const int stride = (ncol + 31) & ~31;
+  const int nm = opt->nmodes <= 0 ? 1 : opt->nmodes;
+  const size_t nbo = (size_t)ncol * np * nm * 8;
+  int rc;
+  if ((rc = ensure(g.pl_thick, (size_t)ntot * 8))) return rc;
+  if ((rc = ensure(g.pl_vp, (size_t)ntot * 8))) return rc;
+  if ((rc = ensure(g.pl_vs, (size_t)ntot * 8))) return rc;
+  if ((rc = ensure(g.pl_rho, (size_t)ntot * 8))) return rc;
+  if ((rc = ensure(g.pl_off, (size_t)(ncol + 1) * 8))) return rc;
+  if ((rc = ensure(g.lay, sizeof(float4) * (size_t)stride * (size_t)maxl))) return rc;
+  if ((rc = ensure(g.nlay, 4 * (size_t)stride))) return rc;
+  if ((rc = ensure(g.status, 4 * (size_t)stride))) return rc;
+  if ((rc = ensure(g.o_pvel, nbo))) return rc;
+  if ((rc = ensure(g.o_gvel, nbo))) return rc;
+  if ((rc = ensure(g.o_ierr, (size_t)ncol * 4))) return rc;
+  const int64_t o0 = offsets[0];
+  CK(cudaMemcpyAsync(g.pl_thick.p, thick + o0, (size_t)ntot * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.pl_vp.p, vp + o0, (size_t)ntot * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.pl_vs.p, vs + o0, (size_t)ntot * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.pl_rho.p, rho + o0, (size_t)ntot * 8, cudaMemcpyHostToDevice, st));
+  std::vector<long long> rel((size_t)ncol + 1);
+  for (int c = 0; c <= ncol; ++c) rel[c] = (long long)(offsets[c] - o0);
+  CK(cudaMemcpyAsync(g.pl_off.p, rel.data(), (size_t)(ncol + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st)); // rel is a stack-lifetime pageable buffer
+  int32_t* fl = (int32_t*)g.flags.p;
+  CK(cudaMemsetAsync(fl, 0, 2 * sizeof(int32_t), st));
+  PreLayParams L;
+  L.thick = (const double*)g.pl_thick.p; L.vp = (const double*)g.pl_vp.p; L.vs = (const double*)g.pl_vs.p; L.rho = (const double*)g.pl_rho.p;
+  L.offsets = (const long long*)g.pl_off.p;
+  L.ncol = ncol; L.modetype = opt->raylov; L.stride = stride;
+  L.lay = (float4*)g.lay.p; L.nlay = (int32_t*)g.nlay.p; L.status = (int32_t*)g.status.p; L.flags = fl;
+  prelayered_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(L);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  if ((rc = launch_k2(ncol, stride, freqs, np, opt, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, nullptr, st))) return rc;
+  int32_t hflags[2] = {0, 0};
+  CK(cudaMemcpyAsync(phase, g.o_pvel.p, nbo, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(group, g.o_gvel.p, nbo, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ierr, g.o_ierr.p, (size_t)ncol * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hflags, fl, sizeof hflags, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hflags[1] >= 2) {
+    const int code = hflags[1] == 2 ? MCT_E_GRT_NEEDED : (hflags[1] == 3 ? MCT_E_TOO_MANY_LAYERS : MCT_E_FLUID_BELOW_TOP);
+    return fail(code, "surfmodes_batch: at least one column reported condition %d (see ierr)", hflags[1]);
+  }
+  return MCT_OK;
+}
+
+int mct_forward_eval_dev(const double* points, const double* params, int ncells, const mct_grid* gr, int derive_vp_rho,
+                         int ixs0, int ixs1, const double* freqs, int np, const mct_disp_opts* opt, double* d_vp,
+                         double* d_vs, double* d_rho, int32_t* d_sites_id, double* d_pvel, double* d_gvel, int32_t* d_ierr,
+                         int32_t* d_flags, void* stream) {
+  NEED_INIT();
+  if (!d_vp || !d_vs || !d_rho || !d_sites_id || !d_pvel || !d_gvel || !d_ierr || !d_flags || !freqs)
+    return fail(MCT_E_INVALID_ARG, "forward_eval: NULL pointer");
+  DispPlan pl;
+  int rc = plan_disp(gr, ixs0, ixs1, 1, gr ? gr->ny : 0, np, opt, pl);
+  if (rc) return rc;
+  cudaStream_t st = pick(stream);
+  if ((rc = upload_nuclei(points, params, ncells, st))) return rc;
+  const int32_t w[6] = {ixs0, ixs1, 1, gr->ny, 1, gr->nz};
+  CK(cudaMemsetAsync((int32_t*)g.flags.p + 2, 0, sizeof(int32_t), st));
+  if ((rc = launch_k1(gr, w, nullptr, d_vp, d_vs, d_rho, d_sites_id, 1, 1, 1, gr->ny, gr->nz, st))) return rc;
+  const size_t slab = (size_t)gr->ny * gr->nz;
+  const size_t xoff = (size_t)(ixs0 - 1) * slab;
+  if (derive_vp_rho) {
+    if ((rc = mct_vs2vp_rho_dev(d_vs + xoff, d_vp + xoff, d_rho + xoff, (int64_t)((size_t)pl.wx * slab), st))) return rc;
+  }
+  return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, true, (long long)(ixs0 - 1) * gr->ny, (long long)pl.wx * gr->ny,
+                   d_pvel, d_gvel, d_ierr, d_flags, st);
+}
+
+int mct_forward_eval(const double* points, const double* params, int ncells, const mct_grid* gr, int derive_vp_rho,
+                     const double* freqs, int np, const mct_disp_opts* opt, double* pvel, double* gvel, int32_t* ierr,
+                     int32_t* model_invalid, double* vp, double* vs, double* rho, int32_t* sites_id) {
+  NEED_INIT();
+  if (!pvel || !gvel || !ierr || !freqs) return fail(MCT_E_INVALID_ARG, "forward_eval: NULL pointer");
+  DispPlan pl;
+  int rc = plan_disp(gr, 1, gr ? gr->nx : 0, 1, gr ? gr->ny : 0, np, opt, pl);
+  if (rc) return rc;
+  cudaStream_t st = g.stream;
+  const size_t ncell = (size_t)gr->nx * gr->ny * gr->nz;
+  if ((rc = ensure(g.m_vp, ncell * 8))) return rc;
+  if ((rc = ensure(g.m_vs, ncell * 8))) return rc;
+  if ((rc = ensure(g.m_rho, ncell * 8))) return rc;
+  if ((rc = ensure(g.m_sites, ncell * 4))) return rc;
+  const size_t nbo = (size_t)pl.ncol * pl.nout * 8;
+  if ((rc = ensure(g.o_pvel, nbo))) return rc;
+  if ((rc = ensure(g.o_gvel, nbo))) return rc;
+  if ((rc = ensure(g.o_ierr, (size_t)pl.ncol * 4))) return rc;
+  int32_t* fl = (int32_t*)g.flags.p;
+  rc = mct_forward_eval_dev(points, params, ncells, gr, derive_vp_rho, 1, gr->nx, freqs, np, opt, (double*)g.m_vp.p,
+                            (double*)g.m_vs.p, (double*)g.m_rho.p, (int32_t*)g.m_sites.p, (double*)g.o_pvel.p,
+                            (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, fl, st);
+  if (rc) return rc;
+  int32_t hflags[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(hflags, fl, sizeof hflags, cudaMemcpyDeviceToHost, st));
+  if (vp) CK(cudaMemcpyAsync(vp, g.m_vp.p, ncell * 8, cudaMemcpyDeviceToHost, st));
+  if (vs) CK(cudaMemcpyAsync(vs, g.m_vs.p, ncell * 8, cudaMemcpyDeviceToHost, st));
+  if (rho) CK(cudaMemcpyAsync(rho, g.m_rho.p, ncell * 8, cudaMemcpyDeviceToHost, st));
+  if (sites_id) CK(cudaMemcpyAsync(sites_id, g.m_sites.p, ncell * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hflags[2]) return fail(MCT_E_CUDA, "nearest-nucleus traversal stack overflow (tree deeper than %d)", K1_STACK);
+  if (model_invalid) *model_invalid = hflags[0];
+  if (hflags[0]) return MCT_OK;
+  CK(cudaMemcpyAsync(pvel, g.o_pvel.p, nbo, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(gvel, g.o_gvel.p, nbo, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ierr, g.o_ierr.p, (size_t)pl.ncol * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hflags[1] >= 2) {
+    const int code = hflags[1] == 2 ? MCT_E_GRT_NEEDED : (hflags[1] == 3 ? MCT_E_TOO_MANY_LAYERS : MCT_E_FLUID_BELOW_TOP);
+    return fail(code, "forward_eval: at least one column reported condition %d (see ierr)", hflags[1]);
+  }
+  return MCT_OK;
+}
+
+int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, int ix1, int iy0, int iy1, double* d_vel,
+                         void* stream) {
+  NEED_INIT();
+  if (!d_pvel || !d_vel || np < 1 || ix0 < 1 || iy0 < 1 || ix1 > nx || iy1 > ny || ix1 < ix0 || iy1 < iy0)
+    return fail(MCT_E_INVALID_ARG, "assemble_vel: bad arguments");
+  cudaStream_t st = pick(stream);
+  const int wx = ix1 - ix0 + 1, wy = iy1 - iy0 + 1;
+  assemble_scatter_kernel<<<grid_blocks((long long)wx * wy * np, 256, 8), 256, 0, st>>>(d_pvel, np, ny, ix0, iy0, wx, wy, d_vel);
+  CK(cudaGetLastError());
+  const int ex0 = ix0 == 1, ex1 = ix1 == nx, ey0 = iy0 == 1, ey1 = iy1 == ny;
+  if (ex0 || ex1) {
+    assemble_edges_kernel<<<grid_blocks((long long)np * (ny + 2), 256, 8), 256, 0, st>>>(d_vel, np, nx, ny, ex0, ex1, ey0, ey1, 0);
+    CK(cudaGetLastError());
+    g.host_stats.n_launches += 1;
+  }
+  if (ey0 || ey1) {
+    assemble_edges_kernel<<<grid_blocks((long long)np * (nx + 2), 256, 8), 256, 0, st>>>(d_vel, np, nx, ny, ex0, ex1, ey0, ey1, 1);
+    CK(cudaGetLastError());
+    g.host_stats.n_launches += 1;
+  }
+  g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,194 @@
+"""ctypes wrapper of oracle/liboracle.so -- the CPU restatement used as the parity checker.
+TEST INFRASTRUCTURE ONLY: nothing under mctomo_b200/ may import this."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "kdtree2_ref")
+
+LIBM, PORTABLE = 0, 1
+
+
+class orc_grid(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("xmin", C.c_double), ("ymin", C.c_double),
+                ("zmin", C.c_double), ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+                ("waterDepth", C.c_double), ("scaling", C.c_double)]
+
+
+_L = None
+
+
+def L():
+    global _L
+    if _L is None:
+        p = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(p):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+        _L = C.CDLL(p)
+        vp = C.c_void_p
+        _L.orc_kdtree2_create.restype = vp
+        _L.orc_kdtree2_create.argtypes = [vp, C.c_int]
+        _L.orc_kdtree2_destroy.argtypes = [vp]
+        _L.orc_kdtree2_nearest_batch.argtypes = [vp, vp, C.c_int64, vp, vp]
+        _L.orc_kdtree_to_grid.argtypes = [vp, vp, C.c_int, C.POINTER(orc_grid), vp, vp, vp, vp, vp, vp]
+        _L.orc_box_window.argtypes = [C.POINTER(orc_grid), vp, vp]
+        _L.orc_surfmodes.argtypes = [vp] * 4 + [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                                vp, vp, vp, vp]
+        _L.orc_vs2vp_rho.argtypes = [vp, vp, vp, C.c_int64, C.c_int]
+        _L.orc_check_model.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        _L.orc_convert_column.argtypes = [vp, vp, vp, C.c_int] + [C.c_double] * 5 + [vp] * 4
+        _L.orc_surf_dispersion.argtypes = [vp, vp, vp, C.POINTER(orc_grid)] + [C.c_int] * 4 + [vp, C.c_int, C.c_int,
+                                          C.c_int, C.c_int] + [C.c_double] * 4 + [C.c_int, C.c_int, vp, vp, vp, vp]
+        _L.orc_assemble_vel.argtypes = [vp] + [C.c_int] * 7 + [vp]
+        _L.orc_mct_exp.restype = C.c_double
+        _L.orc_mct_exp.argtypes = [C.c_double]
+        _L.orc_mct_sincos.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _L.orc_mct_pow025.restype = C.c_double
+        _L.orc_mct_pow025.argtypes = [C.c_double]
+        _L.orc_gtsolh.restype = C.c_float
+        _L.orc_gtsolh.argtypes = [C.c_float, C.c_float]
+        _L.orc_nlvls1.argtypes = [vp, vp, C.c_int, C.c_int]
+    return _L
+
+
+def ogrid(g):
+    return orc_grid(g.nx, g.ny, g.nz, g.xmin, g.ymin, g.zmin, g.dx, g.dy, g.dz, g.waterDepth, g.scaling)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def kd_nearest(points, queries):
+    """Oracle kdtree2 1-NN: returns (idx 1-based int32, squared distance)."""
+    points, queries = f64(points), f64(queries)
+    T = L().orc_kdtree2_create(points.ctypes.data, len(points))
+    if not T:
+        raise ValueError("degenerate nuclei")
+    idx = np.zeros(len(queries), np.int32)
+    dis = np.zeros(len(queries))
+    L().orc_kdtree2_nearest_batch(T, queries.ctypes.data, len(queries), idx.ctypes.data, dis.ctypes.data)
+    L().orc_kdtree2_destroy(T)
+    return idx, dis
+
+
+def have_ref_binary():
+    return os.path.exists(REF_BIN)
+
+
+def ref_kd_nearest(points, queries):
+    """The reference's own kdtree2.o (oracle/_ref/kdtree2_ref, built by oracle/build_ref.sh)."""
+    points, queries = f64(points), f64(queries)
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "in.bin"), "wb") as f:
+            f.write(np.array([len(points), len(queries)], np.int64).tobytes())
+            f.write(points.tobytes())
+            f.write(queries.tobytes())
+        subprocess.check_call([REF_BIN, os.path.join(d, "in.bin"), os.path.join(d, "out.bin")])
+        b = open(os.path.join(d, "out.bin"), "rb").read()
+    n = len(queries)
+    return np.frombuffer(b[:4 * n], np.int32).copy(), np.frombuffer(b[4 * n:], np.float64).copy()
+
+
+def kdtree_to_grid(points, params, grid, box, vp, vs, rho, sites_id, pm=None):
+    points, params, box = f64(points), f64(params), f64(box)
+    pmv = None if pm is None else f64(pm)
+    og = ogrid(grid)
+    rc = L().orc_kdtree_to_grid(points.ctypes.data, params.ctypes.data, len(points), C.byref(og), box.ctypes.data,
+                                None if pmv is None else pmv.ctypes.data, vp.ctypes.data, vs.ctypes.data,
+                                rho.ctypes.data, sites_id.ctypes.data)
+    if rc:
+        raise ValueError("degenerate nuclei")
+
+
+def box_window(grid, box):
+    w = np.zeros(6, np.int32)
+    box = f64(box)
+    og = ogrid(grid)
+    L().orc_box_window(C.byref(og), box.ctypes.data, w.ctypes.data)
+    return w
+
+
+def surfmodes(thick, vp, vs, rho, freqs, modetype=1, phaseGroup=0, nmodes=0, dc=1e-3, math_mode=PORTABLE):
+    thick, vp, vs, rho, freqs = f64(thick), f64(vp), f64(vs), f64(rho), f64(freqs)
+    nm = max(nmodes, 1)
+    ph = np.zeros(len(freqs) * nm)
+    gr = np.zeros(len(freqs) * nm)
+    ierr = C.c_int(0)
+    cnt = np.zeros(2, np.int64)
+    rc = L().orc_surfmodes(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, len(thick),
+                           freqs.ctypes.data, len(freqs), modetype, phaseGroup, nmodes, dc, math_mode, ph.ctypes.data,
+                           gr.ctypes.data, C.byref(ierr), cnt.ctypes.data)
+    return rc, ph, gr, ierr.value, cnt
+
+
+def vs2vp_rho(vs, math_mode=PORTABLE):
+    vs = f64(vs)
+    vp = np.empty_like(vs)
+    rho = np.empty_like(vs)
+    L().orc_vs2vp_rho(vs.ctypes.data, vp.ctypes.data, rho.ctypes.data, vs.size, math_mode)
+    return vp, rho
+
+
+def check_model(vs, grid):
+    vs = f64(vs)
+    return L().orc_check_model(vs.ctypes.data, grid.nx, grid.ny, grid.nz)
+
+
+def surf_dispersion(vp, vs, rho, grid, window, freqs, raylov=1, phaseGroup=0, nmodes=0, dphase=1e-3,
+                    layer_eps=float(np.float32(1e-10)), water_thresh=float(np.float32(1e-10)), preset=100.0,
+                    math_mode=PORTABLE, nthreads=None):
+    vp, vs, rho, freqs = f64(vp), f64(vs), f64(rho), f64(freqs)
+    ix0, ix1, iy0, iy1 = (int(v) for v in window)
+    wx, wy = ix1 - ix0 + 1, iy1 - iy0 + 1
+    nm = max(nmodes, 1)
+    pvel = np.zeros((wx, wy, nm * len(freqs)))
+    gvel = np.zeros_like(pvel)
+    ierr = np.zeros((wx, wy), np.int32)
+    cnt = np.zeros(2, np.int64)
+    og = ogrid(grid)
+    if nthreads is None:
+        nthreads = os.cpu_count() or 1
+    nun = L().orc_surf_dispersion(vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, C.byref(og), ix0, ix1, iy0, iy1,
+                                  freqs.ctypes.data, len(freqs), raylov, phaseGroup, nmodes, dphase, layer_eps,
+                                  water_thresh, preset, math_mode, nthreads, pvel.ctypes.data, gvel.ctypes.data,
+                                  ierr.ctypes.data, cnt.ctypes.data)
+    return pvel, gvel, ierr, cnt, nun
+
+
+def convert_column(vp, vs, rho, dz, waterDepth=0.0, scaling=1.0, layer_eps=float(np.float32(1e-10)),
+                   water_thresh=float(np.float32(1e-10))):
+    vp, vs, rho = f64(vp), f64(vs), f64(rho)
+    out = [np.zeros(256) for _ in range(4)]
+    n = L().orc_convert_column(vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, len(vs), dz, waterDepth, scaling,
+                               layer_eps, water_thresh, *[o.ctypes.data for o in out])
+    return n, [o[:max(n, 0)] for o in out]  # thick, alpha, beta, rho
+
+
+def assemble_vel(pvel, np_, nx, ny, window, vel):
+    ix0, ix1, iy0, iy1 = (int(v) for v in window)
+    pvel = f64(pvel)
+    L().orc_assemble_vel(pvel.ctypes.data, np_, nx, ny, ix0, ix1, iy0, iy1, vel.ctypes.data)
+
+
+def forward_eval(points, params, grid, freqs, derive_vp_rho=True, math_mode=PORTABLE, nthreads=None, **kw):
+    """Oracle version of the fused forward evaluation: kdtree_to_grid(full box) -> vs2vp/rho -> check -> dispersion."""
+    vp = np.zeros(grid.shape)
+    vs = np.zeros(grid.shape)
+    rho = np.zeros(grid.shape)
+    sid = np.zeros(grid.shape, np.int32)
+    kdtree_to_grid(points, params, grid, grid.full_box(), vp, vs, rho, sid)
+    if derive_vp_rho:
+        vp, rho = vs2vp_rho(vs, math_mode)
+    inval = check_model(vs, grid)
+    res = dict(vp=vp, vs=vs, rho=rho, sites_id=sid, model_invalid=inval)
+    if not inval:
+        pv, gv, ie, cnt, nun = surf_dispersion(vp, vs, rho, grid, (1, grid.nx, 1, grid.ny), freqs,
+                                               math_mode=math_mode, nthreads=nthreads, **kw)
+        res.update(pvel=pv, gvel=gv, ierr=ie, counters=cnt)
+    return res
