@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of MCTomo's surface-wave forward model on N B200s, next to the reference's CPU path.
+
+One "step" = one pass of the hot path over one batch of synthetic models:
+    Voronoi->grid (K1) -> vs2vp/vp2rho -> check_model -> column->layers -> modal dispersion (K2)
+for `--batch` independent models (chains) of the workload grid.  Default workload = BASELINE config C2
+(64x64x40 grid, 20 periods, Rayleigh fundamental phase velocity, 300 nuclei, batch of 32 forward evaluations).
+
+  value : (column x period) dispersion solves/s, whole job, nuclei trees + all model arrays resident in HBM
+          (timed with CUDA events on the launching stream, max over ranks)
+  e2e   : same metric through the host-pointer C-ABI call mct_forward_eval_batch: nuclei come from host memory,
+          trees are built, everything runs, the dispersion maps are copied back to pinned host memory.
+  N > 1 : one process per GPU (torchrun), every rank evaluates its own batch of chains (config C4's
+          "chains sharded over GPUs, no inter-GPU traffic"): weak scaling, no data-path collective.
+          `--config C5` instead shards the columns of ONE model over the ranks in x-slabs and all-gathers
+          the dispersion map with NCCL (config 5).
+
+--impl reference times the reference's CPU path (the C restatement under oracle/, libm math, OpenMP over x
+like the reference) on this box's host cores, for the same metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_LAYER_R, F_CALL_R = 184, 31  # nominal FP64 ops per layer step / per call, Rayleigh
+F_LAYER_L, F_CALL_L = 27, 8    # Love
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--batch", type=int, default=0, help="models per GPU per step (default: 32 for C2, 8 for C4, else 1)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args, rank, world):
+    from mctomo_b200 import synth
+    c = dict(synth.CONFIGS[args.config])
+    batch = args.batch or {"C2": 32, "C4": 8}.get(args.config, 1)
+    grid = synth.make_grid(c["nx"], c["ny"], c["nz"])
+    cid = int(args.config[1:])
+    rng_nc = np.random.default_rng(77 + rank)
+    models = []
+    for b in range(batch):
+        chain = rank * batch + b
+        ncells = c["ncells"] if args.config != "C4" else int(rng_nc.integers(25, 301))
+        models.append(synth.generate_model(grid, ncells, 1000 + cid + chain))
+    freqs = synth.example1_freqs() if args.config == "C1" else synth.freqs(c["np"])
+    spec = dict(raylov=1, phaseGroup=0, nmodes=0)
+    if args.config == "C3":
+        spec = dict(raylov=1, phaseGroup=1, nmodes=2)  # the Rayleigh half of C3; Love is a second pass
+    return grid, models, freqs, batch, spec
+
+
+def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
+    """Times the oracle (libm math = what the Fortran binary calls) on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    solves = 0
+    t_used = 0.0
+    n_evals = 0
+    nm = max(spec["nmodes"], 1)
+    # a bounded x-slab of each model keeps the sample within the budget on big grids
+    per_eval_cols = grid.nx * grid.ny
+    probe_cols = min(per_eval_cols, 64 * nthreads)
+    wx = max(1, min(grid.nx, probe_cols // grid.ny))
+    detail = None
+    for pts, par in models:
+        t0 = time.perf_counter()
+        vp = np.zeros(grid.shape); vs = np.zeros(grid.shape); rho = np.zeros(grid.shape); sid = np.zeros(grid.shape, np.int32)
+        orc.kdtree_to_grid(pts, par, grid, grid.full_box(), vp, vs, rho, sid)
+        t1 = time.perf_counter()
+        vp, rho = orc.vs2vp_rho(vs, orc.LIBM)
+        inval = orc.check_model(vs, grid)
+        t2 = time.perf_counter()
+        pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (1, wx, 1, grid.ny), freqs, math_mode=orc.LIBM,
+                                                 nthreads=nthreads, **spec)
+        t3 = time.perf_counter()
+        frac = wx / grid.nx  # K1/property maps covered the whole grid: charge them pro rata to the solved slab
+        t_used += (t1 - t0) * frac + (t2 - t1) * frac + (t3 - t2)
+        solves += wx * grid.ny * len(freqs) * nm
+        n_evals += frac
+        detail = {"kdtree_to_grid_s_full_grid": t1 - t0, "maps_check_s_full_grid": t2 - t1, "dispersion_s_slab": t3 - t2,
+                  "slab_columns": wx * grid.ny}
+        if t_used > budget_s:
+            break
+    return solves / t_used, n_evals / t_used, f"{n_evals:.2f} forward evals ({solves} solves) of the workload, {t_used:.1f} s", detail
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    grid, models, freqs, batch, spec = workload(args, 0, 1)
+    cores = os.cpu_count() or 1
+    times = []
+    rate = evr = 0.0
+    sample = ""
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    wall = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r, e, sample, _ = cpu_sample(grid, models[s % len(models):] + models[:s % len(models)], freqs, spec, per_step_budget, cores)
+        if s >= args.warmup:
+            times.append((r, e))
+            wall.append(time.perf_counter() - t0)
+    per_step_ms = statistics.mean(wall) * 1e3
+    rate = statistics.mean(t[0] for t in times)
+    evr = statistics.mean(t[1] for t in times)
+    out = {"impl": "reference", "metric": "dispersion_solves_per_sec", "value": rate, "unit": "column*period solves/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "forward_evals_per_sec": evr,
+           "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
+                                  f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={max(spec['nmodes'],1)}",
+                      "per_step": "bounded sample of the workload on the host CPU"},
+           "cpu_baseline": {"value": rate, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": rate, "unit": "column*period solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from mctomo_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.init(local)
+
+    column_sharded = args.config == "C5" and world > 1
+    grid, models, freqs, batch, spec = workload(args, 0 if column_sharded else rank, world)
+    opts = capi.disp_opts(**spec)
+    nm = max(spec["nmodes"], 1)
+    nout = nm * len(freqs)
+    pts, par, off = capi.pack_models(models)
+    # x-slab of this rank (column sharding) or the whole grid
+    if column_sharded:
+        per = (grid.nx + world - 1) // world
+        slab = (rank * per + 1, min(grid.nx, (rank + 1) * per))
+    else:
+        slab = (1, grid.nx)
+    wx = slab[1] - slab[0] + 1
+    ncell = grid.nx * grid.ny * grid.nz
+    d_vp = torch.empty(batch * ncell, dtype=torch.float64, device=dev)
+    d_vs = torch.empty_like(d_vp)
+    d_rho = torch.empty_like(d_vp)
+    d_sid = torch.empty(batch * ncell, dtype=torch.int32, device=dev)
+    d_pv = torch.empty(batch * wx * grid.ny * nout, dtype=torch.float64, device=dev)
+    d_gv = torch.empty_like(d_pv)
+    d_ie = torch.empty(batch * wx * grid.ny, dtype=torch.int32, device=dev)
+    d_fl = torch.zeros(2 * batch, dtype=torch.int32, device=dev)
+    gathered = torch.empty(world * d_pv.numel(), dtype=torch.float64, device=dev) if column_sharded else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # a dedicated (non-default) stream: the library launches on the handle it is given, torch's events and
+    # NCCL calls are recorded on the same one
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def resident_step():
+        capi.forward_batch_dev(grid, batch, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
+                               d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream, slab=slab)
+        if column_sharded:
+            dist.all_gather_into_tensor(gathered, d_pv)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    capi.set_nuclei_batch(pts, par, off)
+    solves_per_step_rank = batch * wx * grid.ny * nout
+    # ---- warm-up
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    # ---- resident timing: EXACTLY K steps, CUDA events per step on the launching stream, L2 flushed between steps
+    capi.reset_stats()
+    capi.set_profiling(True)
+    capi.kernel_times(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        resident_step()
+        b.record()
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kt = capi.kernel_times(reset=True)
+    st = capi.stats()
+    capi.set_profiling(False)
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = solves_per_step_rank * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host nuclei -> C ABI -> host maps (pinned), every step
+    e2e = None
+    if not column_sharded:
+        h_pv = torch.empty((batch, grid.nx, grid.ny, nout), dtype=torch.float64).pin_memory()
+        h_gv = torch.empty_like(h_pv).pin_memory()
+        h_ie = torch.empty((batch, grid.nx, grid.ny), dtype=torch.int32).pin_memory()
+        out = {"pvel": h_pv.numpy(), "gvel": h_gv.numpy(), "ierr": h_ie.numpy()}
+        for _ in range(max(1, args.warmup - 1)):
+            capi.forward_eval_batch(pts, par, off, grid, freqs, opts, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = capi.forward_eval_batch(pts, par, off, grid, freqs, opts, out=out)  # synchronous: results are in host memory
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        assert int(r["ierr"].max()) <= 1
+        e2e = {"value": solves_per_step_rank * world * args.steps / float(t_e2e.item()), "unit": "column*period solves/s",
+               "h2d_bytes_per_step": int(pts.nbytes + par.nbytes + off.nbytes) * 2,
+               "d2h_bytes_per_step": int(h_pv.numel() * 8 * 2 + h_ie.numel() * 4),
+               "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
+               "api": "mct_forward_eval_batch (host pointers in/out, tree build + H2D + kernels + D2H inside the timed region)"}
+
+    if rank == 0:
+        fl, fc = (F_LAYER_R, F_CALL_R) if spec["raylov"] == 1 else (F_LAYER_L, F_CALL_L)
+        w2 = st["n_dltar"] * fc + st["n_layer_steps"] * fl      # nominal FP64 ops of all timed K2 launches on rank 0
+        k2_s = kt["k2_ms"] * 1e-3
+        probe = capi.fp64_peak_probe()
+        achieved = w2 / k2_s / 1e12 if k2_s > 0 else None
+        roof = {"bound": "fp64", "achieved": achieved, "peak": probe["dfma_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / probe["dfma_tflops"] if achieved else None, "traffic": None,
+                "kernel": "k2_dispersion_kernel", "k2_ms_per_step": kt["k2_ms"] / args.steps,
+                "k2_share_of_step": kt["k2_ms"] / sum(step_ms),
+                "peak_source": "measured live: 8 independent DFMA chains/thread (mct_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
+                "peak_dmul_dadd_tflops": probe["dmul_dadd_tflops"],
+                "note": "achieved = nominal FP64 ops (184/layer step + 31/call, Rayleigh; SURVEY 8d) / K2 time; the kernel is "
+                        "compiled without FMA contraction for bit-parity, so its ceiling is the DMUL+DADD rate",
+                "layer_steps_per_s": st["n_layer_steps"] / k2_s if k2_s > 0 else None,
+                "k1_ms_per_step": kt["k1_ms"] / args.steps,
+                "k1_hbm_gbs": (28.0 * batch * wx * grid.ny * grid.nz) * args.steps / (kt["k1_ms"] * 1e-3) / 1e9 if kt["k1_ms"] > 0 else None}
+        cpu = None
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            r, e, sample, detail = cpu_sample(grid, models, freqs, spec, args.cpu_seconds, cores)
+            cpu = {"value": r, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample,
+                   "forward_evals_per_sec": e, "detail": detail}
+        out = {"metric": "dispersion_solves_per_sec", "value": value, "unit": "column*period solves/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+               "scaling": "strong" if column_sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "forward_evals_per_sec": batch * world * args.steps / (total_ms * 1e-3) if not column_sharded else args.steps / (total_ms * 1e-3),
+               "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
+                                      f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={nm}, "
+                                      f"{len(models[0][0])} nuclei",
+                          "batch_per_gpu": batch, "parallelism": ("x-slab column sharding + NCCL all_gather" if column_sharded
+                                                                 else f"chains sharded, {world} x {batch} independent models, no collective"),
+                          "l2": "256 MiB buffer written between timed steps (L2 flush); model arrays per step also exceed L2"
+                          if batch * ncell * 28 > (126 << 20) else "256 MiB buffer written between timed steps (L2 flush)"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["n_launches"]), "roofline": roof, "cpu_baseline": cpu,
+               "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
+                        "columns_per_step": st["n_columns"] / args.steps}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    capi.shutdown()
+
+
+if __name__ == "__main__":
+    main()

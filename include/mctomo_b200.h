@@ -171,6 +171,34 @@ int mct_forward_eval_dev(const double* points, const double* params, int ncells,
                          int32_t* d_sites_id, double* d_pvel, double* d_gvel, int32_t* d_ierr,
                          int32_t* d_flags, void* stream);
 
+/* ---- batches of independent models (chains) ---------------------------------------------------
+ * MCTomo runs one independent chain per MPI rank (src/MCTomo.F90:82-86,131-133).  Several chains that
+ * share a GPU are evaluated as ONE batch: model b owns nuclei offsets[b]..offsets[b+1]-1; every model
+ * array gains a slowest axis of length nb ((nz,ny,nx,nb), outputs (np*nm,ny,nx,nb), ierr (ny,nx,nb),
+ * flags int32[2*nb] = {model_invalid, max condition code} per model).  mct_set_nuclei_batch builds the
+ * nb search trees on the host and makes them resident; mct_forward_batch_dev then runs every kernel of
+ * the forward evaluation on the resident set without touching host memory. */
+int mct_set_nuclei_batch(const double* points, const double* params, const int64_t* offsets, int nb);
+int mct_forward_batch_dev(const mct_grid* g, int nb, int derive_vp_rho, int ixs0, int ixs1, const double* freqs,
+                          int np, const mct_disp_opts* opt, double* d_vp, double* d_vs, double* d_rho,
+                          int32_t* d_sites_id, double* d_pvel, double* d_gvel, int32_t* d_ierr, int32_t* d_flags,
+                          void* stream);
+/* Host-pointer form: nuclei in, maps out;
+ * model_invalid int32[nb]; vp/vs/rho/sites_id optional (NULL = stay on the device). */
+int mct_forward_eval_batch(const double* points, const double* params, const int64_t* offsets, int nb,
+                           const mct_grid* g, int derive_vp_rho, const double* freqs, int np,
+                           const mct_disp_opts* opt, double* pvel, double* gvel, int32_t* ierr,
+                           int32_t* model_invalid, double* vp, double* vs, double* rho, int32_t* sites_id);
+
+/* ---- measurement helpers ----------------------------------------------------------------------
+ * mct_set_profiling(1) brackets every kernel launch with CUDA events on the launching stream;
+ * mct_kernel_times returns accumulated milliseconds {K1 nearest-nucleus, K2 dispersion, other kernels,
+ * number of timed launches} (and zeroes them when reset != 0).  mct_fp64_peak_probe measures this
+ * GPU's FP64 pipe with 8 independent chains per thread: DFMA (2 flop/instr) and DMUL+DADD. */
+int mct_set_profiling(int on);
+int mct_kernel_times(double ms[4], int reset);
+int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add);
+
 /* Map assembly of likelihood_surf.F90:259-264 on the device: scatter a window of pvel into the
  * padded (np, ny+2, nx+2) field and replicate the edges the window touches. */
 int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, int ix1, int iy0, int iy1,

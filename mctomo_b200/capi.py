@@ -312,3 +312,98 @@ def voronoi_to_grid_dev(points, params, grid: Grid, box, d_vp, d_vs, d_rho, d_si
 def assemble_vel_dev(d_pvel, np_, nx, ny, window, d_vel, stream):
     ix0, ix1, iy0, iy1 = (int(v) for v in window)
     return _check(lib().mct_assemble_vel_dev(d_pvel, np_, nx, ny, ix0, ix1, iy0, iy1, d_vel, stream))
+
+
+# ---- batches of independent models (chains sharing one GPU) ---------------------------------------
+
+def _bind_batch():
+    L = lib()
+    if getattr(L, "_batch_bound", False):
+        return L
+    vp = C.c_void_p
+    gp = C.POINTER(mct_grid)
+    op = C.POINTER(mct_disp_opts)
+    L.mct_set_nuclei_batch.argtypes = [vp, vp, vp, C.c_int]
+    L.mct_forward_batch_dev.argtypes = [gp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, op] + [vp] * 9
+    L.mct_forward_eval_batch.argtypes = [vp, vp, vp, C.c_int, gp, C.c_int, vp, C.c_int, op] + [vp] * 8
+    L.mct_set_profiling.argtypes = [C.c_int]
+    L.mct_kernel_times.argtypes = [vp, C.c_int]
+    L.mct_fp64_peak_probe.argtypes = [vp, vp]
+    L._batch_bound = True
+    return L
+
+
+def pack_models(models):
+    """models: list of (points (n_b,3), params (n_b,3)) -> (points_all, params_all, offsets int64[nb+1])."""
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(m[0], dtype=np.float64) for m in models]))
+    par = np.ascontiguousarray(np.concatenate([np.asarray(m[1], dtype=np.float64) for m in models]))
+    off = np.zeros(len(models) + 1, np.int64)
+    off[1:] = np.cumsum([len(m[0]) for m in models])
+    return pts, par, off
+
+
+def set_nuclei_batch(points, params, offsets):
+    L = _bind_batch()
+    points, params = _f64(points), _f64(params)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    _check(L.mct_set_nuclei_batch(points.ctypes.data, params.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+
+def forward_batch_dev(grid: Grid, nb, freqs, opts, d_vp, d_vs, d_rho, d_sites, d_pvel, d_gvel, d_ierr, d_flags, stream,
+                      derive_vp_rho=True, slab=None):
+    L = _bind_batch()
+    freqs = _f64(freqs)
+    ixs0, ixs1 = (1, grid.nx) if slab is None else slab
+    return _check(L.mct_forward_batch_dev(C.byref(grid.c()), nb, 1 if derive_vp_rho else 0, ixs0, ixs1, freqs.ctypes.data,
+                                          len(freqs), C.byref(opts), d_vp, d_vs, d_rho, d_sites, d_pvel, d_gvel, d_ierr,
+                                          d_flags, stream))
+
+
+def forward_eval_batch(points, params, offsets, grid: Grid, freqs, opts, derive_vp_rho=True, out=None, want_model=False):
+    """nb independent models in one call: nuclei (host) in, dispersion maps (host) out."""
+    L = _bind_batch()
+    points, params, freqs = _f64(points), _f64(params), _f64(freqs)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    nb = len(offsets) - 1
+    nm = max(opts.nmodes, 1)
+    out = {} if out is None else out
+    pvel = out.get("pvel")
+    if pvel is None:
+        pvel = np.zeros((nb, grid.nx, grid.ny, nm * len(freqs)))
+    gvel = out.get("gvel")
+    if gvel is None:
+        gvel = np.zeros_like(pvel)
+    ierr = out.get("ierr")
+    if ierr is None:
+        ierr = np.zeros((nb, grid.nx, grid.ny), np.int32)
+    inval = np.zeros(nb, np.int32)
+    vp = vs = rho = sid = None
+    if want_model:
+        vp, vs, rho = (np.zeros((nb,) + grid.shape) for _ in range(3))
+        sid = np.zeros((nb,) + grid.shape, np.int32)
+    rc = _check(L.mct_forward_eval_batch(points.ctypes.data, params.ctypes.data, offsets.ctypes.data, nb,
+                                         C.byref(grid.c()), 1 if derive_vp_rho else 0, freqs.ctypes.data, len(freqs),
+                                         C.byref(opts), pvel.ctypes.data, gvel.ctypes.data, ierr.ctypes.data,
+                                         inval.ctypes.data, _ptr(vp), _ptr(vs), _ptr(rho), _ptr(sid)),
+                allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+    res = {"pvel": pvel, "gvel": gvel, "ierr": ierr, "model_invalid": inval, "rc": rc}
+    if want_model:
+        res.update(vp=vp, vs=vs, rho=rho, sites_id=sid)
+    return res
+
+
+def set_profiling(on: bool):
+    _check(_bind_batch().mct_set_profiling(1 if on else 0))
+
+
+def kernel_times(reset=True) -> dict:
+    ms = np.zeros(4)
+    _check(_bind_batch().mct_kernel_times(ms.ctypes.data, 1 if reset else 0))
+    return {"k1_ms": ms[0], "k2_ms": ms[1], "other_ms": ms[2], "launches": int(ms[3])}
+
+
+def fp64_peak_probe() -> dict:
+    a = C.c_double(0)
+    b = C.c_double(0)
+    _check(_bind_batch().mct_fp64_peak_probe(C.byref(a), C.byref(b)))
+    return {"dfma_tflops": a.value, "dmul_dadd_tflops": b.value}

@@ -156,28 +156,34 @@ __global__ void __launch_bounds__(256) vs2vp_rho_kernel(const double* __restrict
 
 // check_model (src/likelihood_surf.F90:631-646) over columns [col0, col0+ncols): flag[0] |= any(vs(2:,j,i) < vs(1,j,i)).
 // One warp per column, lanes strided over z (coalesced).
-__global__ void __launch_bounds__(256) check_model_kernel(const double* __restrict__ vs, long long col0, long long ncols,
-                                                          int nz, int32_t* flag) {
+// Batched form: model b = c / cols_per_model reads its columns at vs + b*model_stride + (col0 + c%cols_per_model)*nz and
+// raises flag[2*b].
+__global__ void __launch_bounds__(256) check_model_kernel(const double* __restrict__ vs, long long col0, long long cols_per_model,
+                                                          int nmodels, long long model_stride, int nz, int32_t* flag) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long ncols = cols_per_model * nmodels;
   for (long long c = warp; c < ncols; c += nwarps) {
-    const double* col = vs + (col0 + c) * nz;
+    const long long b = c / cols_per_model, cm = c - b * cols_per_model;
+    const double* col = vs + b * model_stride + (col0 + cm) * nz;
     const double v1 = col[0];
     bool bad = false;
     for (int k = 1 + lane; k < nz; k += 32) bad |= (col[k] < v1);
-    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 1);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&flag[2 * b], 1);
   }
 }
 
 struct LayParams {
   const double* vp; const double* vs; const double* rho; // whole-grid (nz,ny,nx) arrays
   int32_t ny, nz;
-  int32_t ix0, iy0, wx, wy; // 1-based window origin and extent
+  int32_t ix0, iy0, wx, wy; // 1-based window origin and extent (per model)
+  int32_t nmodels;          // models stacked along the slowest axis: model b starts at b*model_stride
+  long long model_stride;   // nx*ny*nz
   double dz, waterDepth, scaling, layer_eps, water_thresh;
   int32_t modetype; // 1 Rayleigh, 0 Love (for the nlvls1 predicate)
   float4* lay; int32_t* nlay; int32_t* status; int32_t stride;
-  int32_t* flags; // flags[1] = max status code
+  int32_t* flags; // per model b: flags[2*b+1] = max status code
 };
 
 // convert_to_layer (src/likelihood_surf.F90:523-629 / forward_modelling.f90:72-175) + the real(.,4)
@@ -185,10 +191,11 @@ struct LayParams {
 // One thread per column of the window; column index c = (i-ix0)*wy + (j-iy0).
 __global__ void __launch_bounds__(128) layerize_kernel(const __grid_constant__ LayParams P) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ncol = P.wx * P.wy;
-  if (c >= ncol) return;
-  const int i = P.ix0 + c / P.wy, j = P.iy0 + c % P.wy;
-  const size_t base = ((size_t)(i - 1) * P.ny + (size_t)(j - 1)) * P.nz;
+  const int cpm = P.wx * P.wy;
+  if (c >= cpm * P.nmodels) return;
+  const int b = c / cpm, cm = c - b * cpm;
+  const int i = P.ix0 + cm / P.wy, j = P.iy0 + cm % P.wy;
+  const size_t base = (size_t)b * (size_t)P.model_stride + ((size_t)(i - 1) * P.ny + (size_t)(j - 1)) * P.nz;
   const double* vp = P.vp + base;
   const double* vs = P.vs + base;
   const double* rho = P.rho + base;
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(128) layerize_kernel(const __grid_constant__ L
   if (st == 0 && nlvls1 != 0) st = 2;
   P.nlay[c] = nl > MCT_MAX_LAYERS ? MCT_MAX_LAYERS : nl;
   P.status[c] = st;
-  if (st != 0 && P.flags) atomicMax(&P.flags[1], st);
+  if (st != 0 && P.flags) atomicMax(&P.flags[2 * b + 1], st);
 }
 
 // Layering of pre-layered columns (mct_surfmodes_batch): narrow to float4, evaluate the same predicate.
