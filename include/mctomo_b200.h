@@ -198,6 +198,10 @@ int mct_forward_eval_batch(const double* points, const double* params, const int
 int mct_set_profiling(int on);
 int mct_kernel_times(double ms[4], int reset);
 int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add);
+/* Device self-test: the shared-reciprocal division the dispersion kernel uses is compared, bit for
+ * bit, with the compiler's IEEE division on *tested random operand pairs whose exponents are drawn
+ * from [-emax, emax]; *mismatches must come back 0. */
+int mct_selftest_division(int emax, int64_t* tested, int64_t* mismatches);
 
 /* Map assembly of likelihood_surf.F90:259-264 on the device: scatter a window of pvel into the
  * padded (np, ny+2, nx+2) field and replicate the edges the window touches. */

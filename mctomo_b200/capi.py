@@ -407,3 +407,13 @@ def fp64_peak_probe() -> dict:
     b = C.c_double(0)
     _check(_bind_batch().mct_fp64_peak_probe(C.byref(a), C.byref(b)))
     return {"dfma_tflops": a.value, "dmul_dadd_tflops": b.value}
+
+
+def selftest_division(emax: int = 300):
+    """(tested, mismatches) of the shared-reciprocal division against IEEE `/` on the device."""
+    L = _bind_batch()
+    L.mct_selftest_division.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    t = C.c_int64(0)
+    m = C.c_int64(0)
+    _check(L.mct_selftest_division(emax, C.byref(t), C.byref(m)))
+    return t.value, m.value

@@ -56,7 +56,7 @@ struct Ctx {
   DevBuf m_vp, m_vs, m_rho, m_sites;
   // layered columns, their processing order, sort scratch
   DevBuf lay, nlay, status, perm, bins;
-  int k2_variant = 3; // launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
+  int k2_variant = 7; // launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
   // outputs (host-pointer entry points)
   DevBuf o_pvel, o_gvel, o_ierr;
   // prelayered staging
@@ -331,7 +331,11 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
       case 1: k2_dispersion_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P); break; // sorted, 128-thread blocks
       case 2: k2_dispersion_w32r160<<<nw, 32, 0, st>>>(P); break;
       case 4: k2_dispersion_w32r96<<<nw, 32, 0, st>>>(P); break;
-      default: k2_dispersion_w32r128<<<nw, 32, 0, st>>>(P); break; // 3
+      case 5: k2_dispersion_w32r80<<<nw, 32, 0, st>>>(P); break;
+      case 3: k2_dispersion_w32r128<<<nw, 32, 0, st>>>(P); break;
+      case 6: k2_dispersion_fast_r160<<<nw, 32, 0, st>>>(P); break;
+      case 8: k2_dispersion_fast_r96<<<nw, 32, 0, st>>>(P); break;
+      default: k2_dispersion_fast_r128<<<nw, 32, 0, st>>>(P); break; // 7
     }
   }
   CK(cudaGetLastError());
@@ -890,6 +894,22 @@ int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add) {
   release(out);
   *tflops_fma = res[0];
   *tflops_mul_add = res[1];
+  return MCT_OK;
+}
+
+int mct_selftest_division(int emax, int64_t* tested, int64_t* mismatches) {
+  NEED_INIT();
+  if (!tested || !mismatches || emax < 0 || emax > 1000) return fail(MCT_E_INVALID_ARG, "selftest_division: bad arguments");
+  unsigned long long* d = (unsigned long long*)g.counters.p + 3;
+  CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), g.stream));
+  const int blocks = g.sm_count * 8, threads = 256, iters = 2048;
+  div_selftest_kernel<<<blocks, threads, 0, g.stream>>>(0x1234567ull + (unsigned long long)emax, iters, emax, d);
+  CK(cudaGetLastError());
+  unsigned long long h = 0;
+  CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  *tested = 3ll * blocks * threads * iters;
+  *mismatches = (int64_t)h;
   return MCT_OK;
 }
 

@@ -11,18 +11,67 @@
  * add / mul / fma, so host (gcc, -ffp-contract=off, hardware FMA) and device
  * (nvcc -fmad=false, explicit __fma_rn) produce identical bits.
  *
- * Accuracy (measured against mpmath in tests/test_mct_math.py): < 1.5 ulp for
- * |x| <= 1e4 (sin/cos), < 1 ulp on [-700, 0] (exp).  Domain notes:
- *   mct_exp    : intended for x <= 0 (the reference only ever calls exp(-2p), p<16,
- *                exp(-exa), exa<60); valid for -700 <= x <= 700, returns 0 below.
- *   mct_sincos : 3-term Cody-Waite reduction; accurate for |x| < ~1e5, deterministic
- *                (and identical on both sides) for any finite x with |x| < 2^50.
+ * Shape.  The polynomials are evaluated with Estrin's scheme (independent partial sums)
+ * instead of Horner's: a dependent DFMA costs ~8 cycles of latency on sm_100a, and a
+ * 13-step Horner chain left the FP64 pipe idle most of the time (profiles/).  On the device
+ * the coefficients live in __constant__ memory so they arrive as constant-bank operands
+ * rather than as two UMOV immediates per DFMA.
+ *
+ * Accuracy (tests/test_mct_math.py, against mpmath): sin/cos < 1.5 ulp for |x| <= 1e4,
+ * exp < 1 ulp on [-700, 700].  Domain notes:
+ *   mct_exp_core : no argument checks; requires |x| <= 700.  The kernels only ever need
+ *                  x in [-60, 0] (exp(-2p), p < 16; exp(-exa), exa < 60).
+ *   mct_exp      : adds the checks (0 below -700, clamps above 700, NaN through).
+ *   mct_sincos   : 3-term Cody-Waite reduction; accurate for |x| < ~1e5, deterministic
+ *                  (and identical on both sides) for any finite x with |x| < 2^50.
  */
 #ifndef MCT_MATH_H
 #define MCT_MATH_H
 
 #include <stdint.h>
 #include <string.h>
+
+/* coefficient table: one definition, two storage classes */
+#define MCT_KTAB_INIT                                                                         \
+  {                                                                                           \
+    /*  0 S1 */ -1.66666666666666324348e-01, /*  1 S2 */ 8.33333333332248946124e-03,          \
+    /*  2 S3 */ -1.98412698298579493134e-04, /*  3 S4 */ 2.75573137070700676789e-06,          \
+    /*  4 S5 */ -2.50507602534068634195e-08, /*  5 S6 */ 1.58969099521155010221e-10,          \
+    /*  6 C1 */ 4.16666666666666019037e-02,  /*  7 C2 */ -1.38888888888741095749e-03,         \
+    /*  8 C3 */ 2.48015872894767294178e-05,  /*  9 C4 */ -2.75573143513906633035e-07,         \
+    /* 10 C5 */ 2.08757232129817482790e-09,  /* 11 C6 */ -1.13596475577881948265e-11,         \
+    /* 12 2/pi */ 6.36619772367581382433e-01, /* 13 P1 */ 1.5707963267948966e+00,             \
+    /* 14 P2 */ 6.123233995736766e-17,       /* 15 P3 */ -1.4973849048591698e-33,             \
+    /* 16 1/ln2 */ 1.44269504088896338700e+00, /* 17 LN2_HI */ 6.93147180369123816490e-01,    \
+    /* 18 LN2_LO */ 1.90821492927058770002e-10,                                               \
+    /* 19.. 1/n!, n = 2..13 */ 0.5, 0x1.5555555555555p-3, 0x1.5555555555555p-5,               \
+    0x1.1111111111111p-7, 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-16, \
+    0x1.71de3a556c734p-19, 0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26,                      \
+    0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33                                              \
+  }
+#define MCT_K_S(i) MCT_K((i) - 1)        /* S1..S6 */
+#define MCT_K_C(i) MCT_K(6 + (i) - 1)    /* C1..C6 */
+#define MCT_K_2OPI MCT_K(12)
+#define MCT_K_P1 MCT_K(13)
+#define MCT_K_P2 MCT_K(14)
+#define MCT_K_P3 MCT_K(15)
+#define MCT_K_INVLN2 MCT_K(16)
+#define MCT_K_LN2HI MCT_K(17)
+#define MCT_K_LN2LO MCT_K(18)
+#define MCT_K_F(n) MCT_K(19 + (n) - 2)   /* 1/n!, n = 2..13 */
+
+#if defined(__CUDACC__)
+__constant__ double mct_ktab_dev[31] = MCT_KTAB_INIT;
+static const double mct_ktab_host[31] = MCT_KTAB_INIT;
+#if defined(__CUDA_ARCH__)
+#define MCT_K(i) mct_ktab_dev[i]
+#else
+#define MCT_K(i) mct_ktab_host[i]
+#endif
+#else
+static const double mct_ktab_host[31] = MCT_KTAB_INIT;
+#define MCT_K(i) mct_ktab_host[i]
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define MCT_HD __device__ __forceinline__
@@ -69,83 +118,80 @@ MCT_HD uint64_t mct_d2bits(double d) {
  * that integer in the low mantissa bits. */
 #define MCT_MAGIC 6755399441055744.0
 
-/* ---- sin & cos on the reduced argument |r| <= pi/4 (fdlibm-style minimax polynomials) */
+/* ---- sin & cos on the reduced argument |r| <= pi/4 (fdlibm's minimax coefficients, Estrin order) */
 MCT_HD double mct_ksin(double r) {
-  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-               S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-               S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-  double z = MCT_MUL(r, r);
-  double p = MCT_FMA(z, S6, S5);
-  p = MCT_FMA(z, p, S4);
-  p = MCT_FMA(z, p, S3);
-  p = MCT_FMA(z, p, S2);
-  p = MCT_FMA(z, p, S1);
+  const double z = MCT_MUL(r, r);
+  const double z2 = MCT_MUL(z, z);
+  const double a = MCT_FMA(z, MCT_K_S(2), MCT_K_S(1));
+  const double b = MCT_FMA(z, MCT_K_S(4), MCT_K_S(3));
+  const double c = MCT_FMA(z, MCT_K_S(6), MCT_K_S(5));
+  const double z4 = MCT_MUL(z2, z2);
+  double p = MCT_FMA(b, z2, a);
+  p = MCT_FMA(c, z4, p);
   return MCT_FMA(MCT_MUL(z, r), p, r);
 }
 MCT_HD double mct_kcos(double r) {
-  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-               C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-               C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-  double z = MCT_MUL(r, r);
-  double p = MCT_FMA(z, C6, C5);
-  p = MCT_FMA(z, p, C4);
-  p = MCT_FMA(z, p, C3);
-  p = MCT_FMA(z, p, C2);
-  p = MCT_FMA(z, p, C1);
+  const double z = MCT_MUL(r, r);
+  const double z2 = MCT_MUL(z, z);
+  const double a = MCT_FMA(z, MCT_K_C(2), MCT_K_C(1));
+  const double b = MCT_FMA(z, MCT_K_C(4), MCT_K_C(3));
+  const double c = MCT_FMA(z, MCT_K_C(6), MCT_K_C(5));
+  const double z4 = MCT_MUL(z2, z2);
+  double p = MCT_FMA(b, z2, a);
+  p = MCT_FMA(c, z4, p);
   /* 1 - z/2 + z^2 p, the -z/2 split off exactly (hz exact, 1-hz rounded once, error recovered) */
-  double hz = MCT_MUL(0.5, z);
-  double w = MCT_ADD(1.0, -hz);
-  double e = MCT_ADD(MCT_ADD(1.0, -w), -hz); /* exact rounding error of w */
-  return MCT_ADD(w, MCT_FMA(MCT_MUL(z, z), p, e));
+  const double hz = MCT_MUL(0.5, z);
+  const double w = MCT_ADD(1.0, -hz);
+  const double e = MCT_ADD(MCT_ADD(1.0, -w), -hz); /* exact rounding error of w */
+  return MCT_ADD(w, MCT_FMA(z2, p, e));
 }
 
 /* sin(x) and cos(x) together.  */
 MCT_HD void mct_sincos(double x, double* sn, double* cs) {
-  const double TWO_OVER_PI = 6.36619772367581382433e-01; /* 0x1.45f306dc9c883p-1 */
-  const double P1 = 1.5707963267948966e+00;              /* 0x1.921fb54442d18p+0 */
-  const double P2 = 6.123233995736766e-17;               /* 0x1.1a62633145c07p-54 */
-  const double P3 = -1.4973849048591698e-33;             /* -0x1.f1976b7ed8fbcp-110 */
-  double t = MCT_FMA(x, TWO_OVER_PI, MCT_MAGIC);
-  uint32_t q = (uint32_t)mct_d2bits(t);
-  double k = MCT_ADD(t, -MCT_MAGIC);
-  double r = MCT_FMA(-k, P1, x);
-  r = MCT_FMA(-k, P2, r);
-  r = MCT_FMA(-k, P3, r);
-  double s = mct_ksin(r), c = mct_kcos(r);
-  double a = (q & 1u) ? c : s;
-  double b = (q & 1u) ? s : c;
+  const double t = MCT_FMA(x, MCT_K_2OPI, MCT_MAGIC);
+  const uint32_t q = (uint32_t)mct_d2bits(t);
+  const double k = MCT_ADD(t, -MCT_MAGIC);
+  double r = MCT_FMA(-k, MCT_K_P1, x);
+  r = MCT_FMA(-k, MCT_K_P2, r);
+  r = MCT_FMA(-k, MCT_K_P3, r);
+  const double s = mct_ksin(r), c = mct_kcos(r);
+  const double a = (q & 1u) ? c : s;
+  const double b = (q & 1u) ? s : c;
   *sn = (q & 2u) ? -a : a;
   *cs = ((q + 1u) & 2u) ? -b : b;
 }
 
-/* exp(x).  k = rint(x/ln2), r = x - k ln2 (2-term), degree-13 Taylor, scale by 2^k
- * through the exponent field (result is always normal on the stated domain). */
+/* exp(x) for |x| <= 700, no argument checks.  k = rint(x/ln2), r = x - k ln2 (2-term),
+ * degree-13 Taylor polynomial in Estrin order, scaled by 2^k through the exponent field. */
+MCT_HD double mct_exp_core(double x) {
+  const double t = MCT_FMA(x, MCT_K_INVLN2, MCT_MAGIC);
+  const int32_t ki = (int32_t)(uint32_t)mct_d2bits(t);
+  const double k = MCT_ADD(t, -MCT_MAGIC);
+  double r = MCT_FMA(-k, MCT_K_LN2HI, x);
+  r = MCT_FMA(-k, MCT_K_LN2LO, r);
+  const double r2 = MCT_MUL(r, r);
+  const double a1 = MCT_FMA(MCT_K_F(3), r, MCT_K_F(2));
+  const double a2 = MCT_FMA(MCT_K_F(5), r, MCT_K_F(4));
+  const double a3 = MCT_FMA(MCT_K_F(7), r, MCT_K_F(6));
+  const double a4 = MCT_FMA(MCT_K_F(9), r, MCT_K_F(8));
+  const double a5 = MCT_FMA(MCT_K_F(11), r, MCT_K_F(10));
+  const double a6 = MCT_FMA(MCT_K_F(13), r, MCT_K_F(12));
+  const double r4 = MCT_MUL(r2, r2);
+  const double b1 = MCT_FMA(a2, r2, a1); /* r^2..r^5 terms, divided by r^2 */
+  const double b2 = MCT_FMA(a4, r2, a3); /* r^6..r^9 */
+  const double b3 = MCT_FMA(a6, r2, a5); /* r^10..r^13 */
+  const double r8 = MCT_MUL(r4, r4);
+  const double d = MCT_FMA(b2, r4, b1);
+  const double q = MCT_FMA(b3, r8, d);   /* (exp(r) - 1 - r) / r^2 */
+  const double s = MCT_FMA(q, r2, r);    /* exp(r) - 1, small: only the final 1 + s rounds at ulp(1) */
+  const double p = MCT_ADD(1.0, s);
+  return mct_bits2d(mct_d2bits(p) + ((uint64_t)(int64_t)ki << 52));
+}
+
 MCT_HD double mct_exp(double x) {
-  const double INV_LN2 = 1.44269504088896338700e+00; /* 0x1.71547652b82fep+0 */
-  const double LN2_HI = 6.93147180369123816490e-01;  /* 0x1.62e42fee00000p-1 */
-  const double LN2_LO = 1.90821492927058770002e-10;  /* 0x1.a39ef35793c76p-33 */
   if (!(x >= -700.0)) return (x != x) ? x : 0.0;
   if (x > 700.0) x = 700.0;
-  double t = MCT_FMA(x, INV_LN2, MCT_MAGIC);
-  int32_t ki = (int32_t)(uint32_t)mct_d2bits(t);
-  double k = MCT_ADD(t, -MCT_MAGIC);
-  double r = MCT_FMA(-k, LN2_HI, x);
-  r = MCT_FMA(-k, LN2_LO, r);
-  double p = 0x1.6124613a86d09p-33;           /* 1/13! */
-  p = MCT_FMA(p, r, 0x1.1eed8eff8d898p-29);   /* 1/12! */
-  p = MCT_FMA(p, r, 0x1.ae64567f544e4p-26);   /* 1/11! */
-  p = MCT_FMA(p, r, 0x1.27e4fb7789f5cp-22);   /* 1/10! */
-  p = MCT_FMA(p, r, 0x1.71de3a556c734p-19);   /* 1/9!  */
-  p = MCT_FMA(p, r, 0x1.a01a01a01a01ap-16);   /* 1/8!  */
-  p = MCT_FMA(p, r, 0x1.a01a01a01a01ap-13);   /* 1/7!  */
-  p = MCT_FMA(p, r, 0x1.6c16c16c16c17p-10);   /* 1/6!  */
-  p = MCT_FMA(p, r, 0x1.1111111111111p-7);    /* 1/5!  */
-  p = MCT_FMA(p, r, 0x1.5555555555555p-5);    /* 1/4!  */
-  p = MCT_FMA(p, r, 0x1.5555555555555p-3);    /* 1/3!  */
-  p = MCT_FMA(p, r, 0.5);
-  p = MCT_FMA(p, r, 1.0);
-  p = MCT_FMA(p, r, 1.0);
-  return mct_bits2d(mct_d2bits(p) + ((uint64_t)(int64_t)ki << 52));
+  return mct_exp_core(x);
 }
 
 /* x^(1/4) for x > 0: sqrt(sqrt(x)) followed by one Newton correction carried out

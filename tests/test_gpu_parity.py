@@ -219,3 +219,10 @@ def test_vs2vp_rho(mct):
     assert np.array_equal(vp, vo) and np.array_equal(rho, ro)
     vl, rl = orc.vs2vp_rho(vs, orc.LIBM)
     assert np.array_equal(vp, vl) and np.abs(rho - rl).max() <= np.spacing(rl.max())
+
+
+@pytest.mark.parametrize("emax", [8, 60, 390, 1000])
+def test_division_selftest(mct, emax):
+    """The kernel's shared-reciprocal division must be bit-identical to IEEE division (what the oracle does)."""
+    tested, bad = mct.selftest_division(emax)
+    assert tested > 10 ** 9 and bad == 0, f"{bad} of {tested} quotients differ from IEEE division"
