@@ -33,7 +33,9 @@ struct RangeTrack {
 };
 
 // ---- the plainly written layer step (exact path) ------------------------------------------------------
-__device__ __noinline__ void layer_step_exact(const float4 L, double wvno, double wvno2, double omega, EVec& E) {
+// (E goes in and out BY VALUE: taking its address for a non-inlined call would pin the five running
+// values to local memory for every step of the hot loop.)
+__device__ __noinline__ EVec layer_step_exact(const float4 L, double wvno, double wvno2, double omega, const EVec E) {
   const double xka = omega / (double)L.y;
   const double xkb = omega / (double)L.z;
   const double t = (double)L.z / omega;
@@ -89,7 +91,9 @@ __device__ __noinline__ void layer_step_exact(const float4 L, double wvno, doubl
   if (fabs(ee4) > t1) t1 = fabs(ee4);
   if (fabs(ee5) > t1) t1 = fabs(ee5);
   if (t1 < 1.e-40) t1 = 1.0;
-  E.e1 = ee1 / t1; E.e2 = ee2 / t1; E.e3 = ee3 / t1; E.e4 = ee4 / t1; E.e5 = ee5 / t1;
+  EVec O;
+  O.e1 = ee1 / t1; O.e2 = ee2 / t1; O.e3 = ee3 / t1; O.e4 = ee4 / t1; O.e5 = ee5 / t1;
+  return O;
 }
 
 // ---- the fast layer step ----------------------------------------------------------------------------
@@ -252,7 +256,7 @@ __device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, i
   for (int m = mmax - 2; m >= llw - 1; --m) {
     const float4 Lc = L;
     if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]); // next layer's record is in flight during this step
-    if (!(om_ok && layer_step_fast(Lc, wvno, wvno2, omega, y_om, E))) layer_step_exact(Lc, wvno, wvno2, omega, E);
+    if (!(om_ok && layer_step_fast(Lc, wvno, wvno2, omega, y_om, E))) E = layer_step_exact(Lc, wvno, wvno2, omega, E);
   }
   if (llw != 1) {
     // water layer on top (:1196-1212): var(p, znul, ra, znul, wvno, xka, znul, dpth, ...)
