@@ -198,6 +198,11 @@ int mct_forward_eval_batch(const double* points, const double* params, const int
 int mct_set_profiling(int on);
 int mct_kernel_times(double ms[4], int reset);
 int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add);
+/* Shape of the dispersion kernel.  mode 0 (default): batches of up to coop_max_columns columns (default
+ * 16384; pass -1 to keep) run one WARP per column -- the lanes split getsol's bracketing scan, which cuts
+ * the latency of a proposal-sized call by an order of magnitude -- larger batches run one THREAD per
+ * column (highest throughput).  mode 1 / 2 force one or the other.  Results are identical either way. */
+int mct_set_k2_mode(int mode, int coop_max_columns);
 /* Device self-test: the shared-reciprocal division the dispersion kernel uses is compared, bit for
  * bit, with the compiler's IEEE division on *tested random operand pairs whose exponents are drawn
  * from [-emax, emax]; *mismatches must come back 0. */

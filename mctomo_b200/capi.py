@@ -409,6 +409,13 @@ def fp64_peak_probe() -> dict:
     return {"dfma_tflops": a.value, "dmul_dadd_tflops": b.value}
 
 
+def set_k2_mode(mode: int = 0, coop_max_columns: int = -1):
+    """0 auto (warp per column up to coop_max_columns, else thread per column), 1 thread per column, 2 warp per column."""
+    L = _bind_batch()
+    L.mct_set_k2_mode.argtypes = [C.c_int, C.c_int]
+    _check(L.mct_set_k2_mode(mode, coop_max_columns))
+
+
 def selftest_division(emax: int = 300):
     """(tested, mismatches) of the shared-reciprocal division against IEEE `/` on the device."""
     L = _bind_batch()

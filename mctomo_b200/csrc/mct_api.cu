@@ -56,6 +56,8 @@ struct Ctx {
   DevBuf m_vp, m_vs, m_rho, m_sites;
   // layered columns, their processing order, sort scratch
   DevBuf lay, nlay, status, perm, bins;
+  int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
+  int k2_coop_max = 16384;  // auto: batches up to this many columns take the warp-cooperative kernel
   int k2_variant = 7; // launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
   // outputs (host-pointer entry points)
   DevBuf o_pvel, o_gvel, o_ierr;
@@ -326,7 +328,10 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   {
     ProfScope ps(1, st);
     const int nw = (ncol + 31) / 32;
-    switch (variant) {
+    // Proposal-sized batches cannot fill the GPU with one thread per column: give each column a warp.
+    const bool coop = (g.k2_mode == 2) || (g.k2_mode == 0 && ncol <= g.k2_coop_max);
+    if (coop) k2_coop_kernel<<<ncol, 32, 0, st>>>(P);
+    else switch (variant) {
       case 0: k2_dispersion_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P); break;
       case 1: k2_dispersion_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P); break; // sorted, 128-thread blocks
       case 2: k2_dispersion_w32r160<<<nw, 32, 0, st>>>(P); break;
@@ -894,6 +899,13 @@ int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add) {
   release(out);
   *tflops_fma = res[0];
   *tflops_mul_add = res[1];
+  return MCT_OK;
+}
+
+int mct_set_k2_mode(int mode, int coop_max_columns) {
+  if (mode < 0 || mode > 2) return fail(MCT_E_INVALID_ARG, "set_k2_mode: mode must be 0 (auto), 1 (thread per column) or 2 (warp per column)");
+  g.k2_mode = mode;
+  if (coop_max_columns >= 0) g.k2_coop_max = coop_max_columns;
   return MCT_OK;
 }
 

@@ -104,10 +104,19 @@ def _model(grid, ncells, seed, math_mode=orc.PORTABLE):
 
 
 def _check_disp(mct, grid, vp, vs, rho, window, freqs, raylov, pg, nmodes, variant="likelihood"):
+    """Runs the dispersion block with BOTH kernel shapes (one thread per column, one warp per column);
+    the two must agree bit for bit with each other and with the oracle, counters included."""
     opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nmodes, variant=variant)
-    mct.reset_stats()
-    pv, gv, ie, inval, rc = mct.surf_dispersion(vp, vs, rho, grid, window, freqs, opts)
-    st = mct.stats()
+    res = []
+    for mode in (1, 2):
+        mct.set_k2_mode(mode)
+        mct.reset_stats()
+        res.append(mct.surf_dispersion(vp, vs, rho, grid, window, freqs, opts) + (mct.stats(),))
+    mct.set_k2_mode(0)
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert np.array_equal(a, b), "thread-per-column and warp-per-column kernels disagree"
+    assert res[0][5]["n_dltar"] == res[1][5]["n_dltar"] and res[0][5]["n_layer_steps"] == res[1][5]["n_layer_steps"]
+    pv, gv, ie, inval, rc, st = res[1]
     kw = dict(raylov=raylov, phaseGroup=pg, nmodes=nmodes, layer_eps=opts.layer_eps, water_thresh=opts.water_thresh,
               preset=opts.preset)
     po, go, io, cnt, nun = orc.surf_dispersion(vp, vs, rho, grid, window, freqs, math_mode=orc.PORTABLE, **kw)
@@ -226,3 +235,37 @@ def test_division_selftest(mct, emax):
     """The kernel's shared-reciprocal division must be bit-identical to IEEE division (what the oracle does)."""
     tested, bad = mct.selftest_division(emax)
     assert tested > 10 ** 9 and bad == 0, f"{bad} of {tested} quotients differ from IEEE division"
+
+
+@pytest.mark.parametrize("raylov", [1, 0])
+def test_full_size_c3_sampled_against_oracle(mct, raylov):
+    """BASELINE config C3 at full size (256x256x60, 40 periods, phase+group, fundamental + 1st overtone):
+    every column is solved on the GPU; 300 randomly chosen columns are re-solved by the oracle and must be
+    bit-identical; size-independent properties are checked on all 65536 columns."""
+    grid, pts, par, freqs = synth.config("C3")
+    opts = disp_opts(raylov=raylov, phaseGroup=1, nmodes=2)
+    r = mct.forward_eval(pts, par, grid, freqs, opts, want_model=True)
+    assert r["model_invalid"] == 0 and r["rc"] == 0
+    np_ = len(freqs)
+    pv = r["pvel"].reshape(grid.nx, grid.ny, 2, np_)
+    gv = r["gvel"].reshape(grid.nx, grid.ny, 2, np_)
+    ie = r["ierr"]
+    assert set(np.unique(ie)) <= {0, 1}
+    # fundamental found everywhere, velocities inside the model's range, no mode crossing where the overtone exists
+    assert (pv[:, :, 0] > 1.5).all() and (pv[:, :, 0] < 6.1).all()
+    found = pv[:, :, 1] > 0
+    assert found.any() and (pv[:, :, 1][found] > pv[:, :, 0][found]).all()
+    # once an overtone is lost at some period it stays lost (ift, surfdisp96.f:566,688-695)
+    assert (np.diff(found.astype(np.int8), axis=-1) <= 0).all()
+    # cell map: brute-force check of a sample of nodes (ties have measure zero for random nuclei)
+    rng = np.random.default_rng(0)
+    ii = rng.integers(0, grid.nx, 2000); jj = rng.integers(0, grid.ny, 2000); kk = rng.integers(0, grid.nz, 2000)
+    q = np.stack([grid.xmin + ii * grid.dx, grid.ymin + jj * grid.dy, grid.zmin + kk * grid.dz], 1)
+    d = ((q[:, None, :] - pts[None]) ** 2).sum(-1)
+    assert np.array_equal(r["sites_id"][ii, jj, kk], d.argmin(1) + 1)
+    # sampled columns against the oracle
+    for i, j in zip(rng.integers(0, grid.nx, 300), rng.integers(0, grid.ny, 300)):
+        n, (th, al, be, rk) = orc.convert_column(r["vp"][i, j], r["vs"][i, j], r["rho"][i, j], grid.dz)
+        rc, p0, g0, e0, _ = orc.surfmodes(th, al, be, rk, freqs, raylov, 1, 2)
+        assert rc == 0 and e0 == ie[i, j]
+        assert np.array_equal(p0, r["pvel"][i, j]) and np.array_equal(g0, r["gvel"][i, j])
