@@ -198,6 +198,10 @@ int mct_forward_eval_batch(const double* points, const double* params, const int
 int mct_set_profiling(int on);
 int mct_kernel_times(double ms[4], int reset);
 int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add);
+/* Shape of the nearest-nucleus kernel.  mode 0 (default): one warp per grid column, brute force over the
+ * nuclei that survive a conservative per-column cull, kdtree2's traversal replayed only for (near-)tied
+ * nodes.  mode 1: kdtree2's traversal for every node.  Results are identical either way. */
+int mct_set_k1_mode(int mode);
 /* Shape of the dispersion kernel.  mode 0 (default): batches of up to coop_max_columns columns (default
  * 16384; pass -1 to keep) run one WARP per column -- the lanes split getsol's bracketing scan, which cuts
  * the latency of a proposal-sized call by an order of magnitude -- larger batches run one THREAD per

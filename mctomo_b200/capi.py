@@ -409,6 +409,13 @@ def fp64_peak_probe() -> dict:
     return {"dfma_tflops": a.value, "dmul_dadd_tflops": b.value}
 
 
+def set_k1_mode(mode: int = 0):
+    """0 culled brute force per column (default), 1 kdtree2 traversal for every node."""
+    L = _bind_batch()
+    L.mct_set_k1_mode.argtypes = [C.c_int]
+    _check(L.mct_set_k1_mode(mode))
+
+
 def set_k2_mode(mode: int = 0, coop_max_columns: int = -1):
     """0 auto (warp per column up to coop_max_columns, else thread per column), 1 thread per column, 2 warp per column."""
     L = _bind_batch()

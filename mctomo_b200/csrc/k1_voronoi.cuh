@@ -36,6 +36,7 @@ struct K1Params {
   const int32_t* ind;    // rearranged position -> original 1-based nucleus index
   const double* params;  // (3, n): vp, vs, rho per ORIGINAL nucleus
   int32_t root;
+  int32_t n;             // number of nuclei
   // window (1-based inclusive) and grid geometry
   int32_t ix0, iy0, iz0, wx, wy, wz;
   double xmin, ymin, zmin, dx, dy, dz;
@@ -141,6 +142,8 @@ __global__ void __launch_bounds__(256) k1_voronoi_kernel(const __grid_constant__
     P.rho[o] = pr[2];
   }
 }
+
+#include "k1_column.cuh" // k1_column_kernel: culled brute force per column, tree walk only for (near-)ties
 
 // vs2vp_3d + vp2rho_3d (src/utils.f90:107-110,131-133), elementwise over n values.
 __global__ void __launch_bounds__(256) vs2vp_rho_kernel(const double* __restrict__ vs, double* __restrict__ vp,

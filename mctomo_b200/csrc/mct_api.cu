@@ -56,6 +56,7 @@ struct Ctx {
   DevBuf m_vp, m_vs, m_rho, m_sites;
   // layered columns, their processing order, sort scratch
   DevBuf lay, nlay, status, perm, bins;
+  int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
   int k2_coop_max = 16384;  // auto: batches up to this many columns take the warp-cooperative kernel
   int k2_variant = 7; // launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
@@ -250,9 +251,21 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
   P.pm_eps = (double)1e-8f; // real(kind=ii10), parameter :: eps = 1e-8 (mcmc_loc2.f90:51)
   P.err = (int32_t*)g.flags.p + 2;
   const long long total = (long long)P.wx * P.wy * P.wz;
+  P.n = g.ncell[model];
   {
     ProfScope ps(0, st);
-    k1_voronoi_kernel<<<grid_blocks(total, 256, 16), 256, 0, st>>>(P);
+    if (g.k1_mode == 1) {
+      k1_voronoi_kernel<<<grid_blocks(total, 256, 16), 256, 0, st>>>(P); // exact tree walk for every node
+    } else {
+      static bool smem_set = false;
+      if (!smem_set) {
+        CK(cudaFuncSetAttribute(k1_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1C_SMEM_BYTES));
+        smem_set = true;
+      }
+      const long long ntiles = (long long)((P.wx + K1C_TILE - 1) / K1C_TILE) * ((P.wy + K1C_TILE - 1) / K1C_TILE);
+      const int blocks = (int)std::min<long long>(ntiles, (long long)g.sm_count * 3);
+      k1_column_kernel<<<blocks, 32 * K1C_WARPS, K1C_SMEM_BYTES, st>>>(P);
+    }
   }
   CK(cudaGetLastError());
   g.host_stats.n_nodes += total;
@@ -899,6 +912,12 @@ int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add) {
   release(out);
   *tflops_fma = res[0];
   *tflops_mul_add = res[1];
+  return MCT_OK;
+}
+
+int mct_set_k1_mode(int mode) {
+  if (mode < 0 || mode > 1) return fail(MCT_E_INVALID_ARG, "set_k1_mode: mode must be 0 (culled brute force) or 1 (tree walk)");
+  g.k1_mode = mode;
   return MCT_OK;
 }
 

@@ -22,12 +22,18 @@ def _empty_model(grid):
 
 
 def _both_k1(mct, pts, par, grid, box, pm=None, init=None):
+    """GPU (both kernel shapes: culled brute force per column, tree walk per node) and oracle."""
     outs = []
-    for fn in (mct.kdtree_to_grid, orc.kdtree_to_grid):
+    for mode in (1, 0):
+        mct.set_k1_mode(mode)
         vp, vs, rho, sid = _empty_model(grid) if init is None else [a.copy() for a in init]
-        fn(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
+        mct.kdtree_to_grid(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
         outs.append((vp, vs, rho, sid))
-    return outs
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y), "the two nearest-nucleus kernels disagree"
+    vp, vs, rho, sid = _empty_model(grid) if init is None else [a.copy() for a in init]
+    orc.kdtree_to_grid(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
+    return [outs[1], (vp, vs, rho, sid)]
 
 
 def _assert_k1_equal(a, b):
@@ -83,6 +89,18 @@ def test_k1_ties_lattice_and_duplicates(mct):
     par = np.stack([np.arange(len(nuc)) + 1.0, np.arange(len(nuc)) + 0.5, np.ones(len(nuc))], 1)
     grid = Grid(9, 9, 9, 0.0, 4.0, 0.0, 4.0, 0.0, 4.0)  # spacing 0.5: every other node is equidistant
     g, o = _both_k1(mct, nuc, par, grid, grid.full_box())
+    _assert_k1_equal(g, o)
+
+
+def test_k1_many_nuclei_and_thin_window(mct):
+    """5000 nuclei (config C5's count: the per-column candidate stage overflows for some columns and falls back to
+    the tree walk) and a window one node thick."""
+    grid = synth.make_grid(20, 18, 80)
+    pts, par = synth.generate_model(grid, 5000, 31)
+    g, o = _both_k1(mct, pts, par, grid, grid.full_box())
+    _assert_k1_equal(g, o)
+    box = np.array([-5.0, -5.0, 6.0, 5.0, 5.0, 6.05])
+    g, o = _both_k1(mct, pts, par, grid, box)
     _assert_k1_equal(g, o)
 
 
