@@ -33,7 +33,20 @@
 
 __device__ __forceinline__ unsigned long long k1c_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
-__global__ void __launch_bounds__(32 * K1C_WARPS) k1_column_kernel(const __grid_constant__ K1Params P) {
+__global__ void __launch_bounds__(32 * K1C_WARPS) k1_column_kernel(const __grid_constant__ K1Params P0) {
+  // batch form: blockIdx.y selects the model; rebase the tree / nuclei / output pointers once
+  K1Params P = P0;
+  if (P0.models) {
+    const K1Model M = P0.models[blockIdx.y];
+    P.nodes = P0.nodes + M.node_off;
+    P.rpts = P0.rpts + 3 * M.pt_off;
+    P.ind = P0.ind + M.pt_off;
+    P.params = P0.params + 3 * M.pt_off;
+    P.root = M.root;
+    P.n = M.n;
+    const long long o = (long long)blockIdx.y * P0.model_stride;
+    P.vp = P0.vp + o; P.vs = P0.vs + o; P.rho = P0.rho + o; P.sites = P0.sites + o;
+  }
   // dynamic shared memory (K1C_SMEM_BYTES, above the 48 KB static limit): per-warp stages + the tile list
   extern __shared__ __align__(16) unsigned char k1c_smem[];
   double (*s_p)[K1C_MAXC] = reinterpret_cast<double (*)[K1C_MAXC]>(k1c_smem);

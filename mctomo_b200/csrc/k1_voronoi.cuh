@@ -30,7 +30,17 @@ struct KdNodeDev {
   int32_t pad;
 };
 
+// One entry per model of a batch (chains sharing a GPU): where its tree and nuclei start.
+struct K1Model {
+  long long node_off, pt_off;
+  int32_t root, n;
+};
+
 struct K1Params {
+  // batch form (k1_column_kernel, blockIdx.y = model): the four pointers below are the BASES of the packed
+  // arrays and models[b] gives the offsets; outputs of model b start at b*model_stride.  NULL = single model.
+  const K1Model* models;
+  long long model_stride;
   const KdNodeDev* nodes;
   const double* rpts;    // rearranged points (3, n)
   const int32_t* ind;    // rearranged position -> original 1-based nucleus index

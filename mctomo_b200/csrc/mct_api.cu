@@ -42,7 +42,7 @@ struct Ctx {
   int count_on = 1;
   char err[512] = {0};
   // resident nuclei set: nb trees packed back to back
-  DevBuf nodes, rpts, ind, params;
+  DevBuf nodes, rpts, ind, params, kmodels;
   HostKdTree tree;
   int nset = 0;                       // models in the resident set
   std::vector<long long> node_off, pt_off; // per model offsets into nodes / points
@@ -180,19 +180,26 @@ int upload_nuclei(const double* points, const double* params, const long long* o
   if ((rc = ensure(g.rpts, nb_pts))) return rc;
   if ((rc = ensure(g.ind, nb_ind))) return rc;
   if ((rc = ensure(g.params, nb_pts))) return rc;
-  // one pinned staging block so the four small copies are true async DMA
-  const size_t tot = nb_nodes + 2 * nb_pts + nb_ind;
+  // per-model descriptors for the batched nearest-nucleus launch
+  std::vector<K1Model> km((size_t)nb);
+  for (int b = 0; b < nb; ++b) km[b] = K1Model{g.node_off[b], g.pt_off[b], g.roots[b], g.ncell[b]};
+  const size_t nb_km = sizeof(K1Model) * (size_t)nb;
+  if ((rc = ensure(g.kmodels, nb_km))) return rc;
+  // one pinned staging block so the five small copies are true async DMA
+  const size_t tot = nb_nodes + 2 * nb_pts + nb_ind + nb_km;
   if ((rc = ensure_pin(g.pin_small, tot))) return rc;
   CK(cudaStreamSynchronize(st)); // the staging block may still be in flight from the previous call
   char* h = (char*)g.pin_small.p;
   memcpy(h, all_nodes.data(), nb_nodes);
   memcpy(h + nb_nodes, all_rpts.data(), nb_pts);
   memcpy(h + nb_nodes + nb_pts, params + 3 * o0, nb_pts);
-  memcpy(h + nb_nodes + 2 * nb_pts, all_ind.data(), nb_ind);
+  memcpy(h + nb_nodes + 2 * nb_pts, km.data(), nb_km); // (8-byte aligned: before the int32 block)
+  memcpy(h + nb_nodes + 2 * nb_pts + nb_km, all_ind.data(), nb_ind);
   CK(cudaMemcpyAsync(g.nodes.p, h, nb_nodes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(g.rpts.p, h + nb_nodes, nb_pts, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(g.params.p, h + nb_nodes + nb_pts, nb_pts, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(g.ind.p, h + nb_nodes + 2 * nb_pts, nb_ind, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.kmodels.p, h + nb_nodes + 2 * nb_pts, nb_km, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.ind.p, h + nb_nodes + 2 * nb_pts + nb_km, nb_ind, cudaMemcpyHostToDevice, st));
   g.nset = nb;
   return MCT_OK;
 }
@@ -231,12 +238,18 @@ int grid_blocks(long long work_items, int threads, int per_sm) {
 
 // Launch K1 on device arrays with the given array geometry.
 int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* d_vp, double* d_vs, double* d_rho,
-              int32_t* d_sites, int ia0, int ja0, int ka0, int ny_a, int nz_a, cudaStream_t st, int model = 0) {
+              int32_t* d_sites, int ia0, int ja0, int ka0, int ny_a, int nz_a, cudaStream_t st, int model = 0,
+              int nbatch = 0, long long model_stride = 0) {
+  // nbatch > 0: all models of the resident set in ONE launch (culled brute-force kernel only); model b's
+  // arrays start at b*model_stride.
+  const bool batched = nbatch > 0 && g.k1_mode != 1;
   K1Params P;
-  P.nodes = (const KdNodeDev*)g.nodes.p + g.node_off[model];
-  P.rpts = (const double*)g.rpts.p + 3 * g.pt_off[model];
-  P.ind = (const int32_t*)g.ind.p + g.pt_off[model];
-  P.params = (const double*)g.params.p + 3 * g.pt_off[model];
+  P.models = batched ? (const K1Model*)g.kmodels.p : nullptr;
+  P.model_stride = model_stride;
+  P.nodes = (const KdNodeDev*)g.nodes.p + (batched ? 0 : g.node_off[model]);
+  P.rpts = (const double*)g.rpts.p + (batched ? 0 : 3 * g.pt_off[model]);
+  P.ind = (const int32_t*)g.ind.p + (batched ? 0 : g.pt_off[model]);
+  P.params = (const double*)g.params.p + (batched ? 0 : 3 * g.pt_off[model]);
   P.root = g.roots[model];
   P.ix0 = w[0]; P.iy0 = w[2]; P.iz0 = w[4];
   P.wx = w[1] - w[0] + 1; P.wy = w[3] - w[2] + 1; P.wz = w[5] - w[4] + 1;
@@ -263,12 +276,13 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
         smem_set = true;
       }
       const long long ntiles = (long long)((P.wx + K1C_TILE - 1) / K1C_TILE) * ((P.wy + K1C_TILE - 1) / K1C_TILE);
-      const int blocks = (int)std::min<long long>(ntiles, (long long)g.sm_count * 3);
-      k1_column_kernel<<<blocks, 32 * K1C_WARPS, K1C_SMEM_BYTES, st>>>(P);
+      const int nby = batched ? nbatch : 1;
+      const int blocks = (int)std::min<long long>(ntiles, std::max<long long>(1, (long long)g.sm_count * 3 / nby));
+      k1_column_kernel<<<dim3(blocks, nby), 32 * K1C_WARPS, K1C_SMEM_BYTES, st>>>(P);
     }
   }
   CK(cudaGetLastError());
-  g.host_stats.n_nodes += total;
+  g.host_stats.n_nodes += total * (batched ? nbatch : 1);
   g.host_stats.n_launches += 1;
   return MCT_OK;
 }
@@ -410,9 +424,13 @@ int forward_core(const mct_grid* gr, int nb, int derive_vp_rho, const DispPlan& 
   const size_t xoff = (size_t)(pl.ix0 - 1) * slab;
   int rc;
   CK(cudaMemsetAsync((int32_t*)g.flags.p + 2, 0, sizeof(int32_t), st));
-  for (int b = 0; b < nb; ++b) {
-    const size_t mo = (size_t)b * model_stride;
-    if ((rc = launch_k1(gr, w, nullptr, d_vp + mo, d_vs + mo, d_rho + mo, d_sites + mo, 1, 1, 1, gr->ny, gr->nz, st, b))) return rc;
+  if (g.k1_mode != 1) { // one launch for the whole batch (blockIdx.y = model)
+    if ((rc = launch_k1(gr, w, nullptr, d_vp, d_vs, d_rho, d_sites, 1, 1, 1, gr->ny, gr->nz, st, 0, nb, (long long)model_stride))) return rc;
+  } else {
+    for (int b = 0; b < nb; ++b) {
+      const size_t mo = (size_t)b * model_stride;
+      if ((rc = launch_k1(gr, w, nullptr, d_vp + mo, d_vs + mo, d_rho + mo, d_sites + mo, 1, 1, 1, gr->ny, gr->nz, st, b))) return rc;
+    }
   }
   if (derive_vp_rho) {
     ProfScope ps(2, st);
@@ -493,7 +511,7 @@ int mct_shutdown(void) {
   if (!g.init) return MCT_OK;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.nlay, &g.status, &g.perm, &g.bins,
+  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.nlay, &g.status, &g.perm, &g.bins,
                     &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters};
   for (DevBuf* b : bufs) release(*b);
   release(g.pin_a);

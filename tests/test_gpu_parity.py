@@ -287,3 +287,32 @@ def test_full_size_c3_sampled_against_oracle(mct, raylov):
         rc, p0, g0, e0, _ = orc.surfmodes(th, al, be, rk, freqs, raylov, 1, 2)
         assert rc == 0 and e0 == ie[i, j]
         assert np.array_equal(p0, r["pvel"][i, j]) and np.array_equal(g0, r["gvel"][i, j])
+
+
+def test_forward_eval_batch_of_chains(mct):
+    """Several independent models (chains) with different numbers of nuclei in ONE call (config C4's shape)."""
+    grid = synth.make_grid(20, 18, 30)
+    freqs = synth.freqs(12)
+    models = [synth.generate_model(grid, n, 500 + n) for n in (25, 300, 77, 150)]
+    opts = disp_opts(raylov=1, phaseGroup=1, nmodes=0)
+    pts, par, off = mct.pack_models(models)
+    for k1 in (0, 1):
+        mct.set_k1_mode(k1)
+        r = mct.forward_eval_batch(pts, par, off, grid, freqs, opts, want_model=True)
+        assert r["rc"] == 0 and not r["model_invalid"].any()
+        for b, (p, q) in enumerate(models):
+            o = orc.forward_eval(p, q, grid, freqs, phaseGroup=1)
+            for k in ("sites_id", "vs", "vp", "rho"):
+                assert np.array_equal(r[k][b], o[k]), (b, k)
+            assert np.array_equal(r["ierr"][b], o["ierr"])
+            assert np.array_equal(r["pvel"][b], o["pvel"]) and np.array_equal(r["gvel"][b], o["gvel"])
+    mct.set_k1_mode(0)
+    # one model of the batch is invalid (a deeper vs below the top vs): only that model is rejected
+    bad = [(p.copy(), q.copy()) for p, q in models]
+    top = np.argmin(bad[2][0][:, 2])
+    bad[2][1][top, 1] = 9.0  # the shallowest nucleus gets the highest vs
+    pts, par, off = mct.pack_models(bad)
+    r = mct.forward_eval_batch(pts, par, off, grid, freqs, opts)
+    assert list(r["model_invalid"]) == [0, 0, 1, 0]
+    o = orc.forward_eval(bad[3][0], bad[3][1], grid, freqs, phaseGroup=1)
+    assert np.array_equal(r["pvel"][3], o["pvel"])
