@@ -316,3 +316,59 @@ def test_forward_eval_batch_of_chains(mct):
     assert list(r["model_invalid"]) == [0, 0, 1, 0]
     o = orc.forward_eval(bad[3][0], bad[3][1], grid, freqs, phaseGroup=1)
     assert np.array_equal(r["pvel"][3], o["pvel"])
+
+
+def test_edge_cases_single_cell_halfspace_and_limits(mct):
+    """ncells = 1 (every column is a bare half-space, mmax = 1), the NP = 60 period limit, bad arguments."""
+    grid = synth.make_grid(5, 4, 12)
+    pts = np.array([[0.3, -0.2, 5.0]])
+    par = np.array([[1.73 * 3.0, 3.0, 2.5]])
+    freqs = 1.0 / np.linspace(0.5, 30.0, 60)
+    for raylov in (1, 0):
+        opts = disp_opts(raylov=raylov, phaseGroup=1, nmodes=0)
+        r = mct.forward_eval(pts, par, grid, freqs, opts, want_model=True)
+        o = orc.forward_eval(pts, par, grid, freqs, raylov=raylov, phaseGroup=1)
+        assert (r["sites_id"] == 1).all()
+        assert np.array_equal(r["ierr"], o["ierr"]) and np.array_equal(r["pvel"], o["pvel"]) and np.array_equal(r["gvel"], o["gvel"])
+        assert (r["ierr"] == (0 if raylov == 1 else 1)).all()  # no Love wave in a half-space
+    with pytest.raises(mct.MctError) as e:
+        mct.forward_eval(pts, par, grid, 1.0 / np.linspace(0.5, 30.0, 61), disp_opts())
+    assert e.value.code == mct.MCT_E_INVALID_ARG
+    with pytest.raises(mct.MctError):
+        mct.surf_dispersion(np.zeros(grid.shape), np.zeros(grid.shape), np.zeros(grid.shape), grid, (0, 3, 1, 2), freqs[:5], disp_opts())
+
+
+def test_water_layer_love_and_rayleigh_overtones(mct):
+    grid = synth.make_grid(9, 7, 30, waterDepth=1.2)
+    vp, vs, rho = _model(grid, 70, 77)
+    _check_disp(mct, grid, vp, vs, rho, (1, 9, 1, 7), synth.freqs(12), 0, 1, 2)
+    _check_disp(mct, grid, vp, vs, rho, (2, 8, 1, 7), synth.freqs(12), 1, 1, 2)
+
+
+def test_failing_columns_ierr_and_zeroed_group(mct):
+    """Very long periods push the root to betmx: surfdisp96 gives up (ierr = 1, cg zeroed from the failing
+    period on, surfdisp96.f:333-376).  The GPU must fail in exactly the same places."""
+    grid = synth.make_grid(8, 6, 20)
+    vp, vs, rho = _model(grid, 40, 78)
+    freqs = 1.0 / np.geomspace(0.5, 3000.0, 24)
+    pv, gv, ie = _check_disp(mct, grid, vp, vs, rho, (1, 8, 1, 6), freqs, 0, 1, 0)
+    assert (ie == 1).any() and (gv == 0.0).any() and (pv == 100.0).any()
+
+
+def test_assemble_vel_dev(mct):
+    import torch
+    nx, ny, np_ = 9, 7, 5
+    rng = np.random.default_rng(4)
+    st = torch.cuda.Stream()
+    for win in [(1, 9, 1, 7), (3, 6, 2, 5), (1, 4, 3, 7), (5, 9, 1, 2)]:
+        wx, wy = win[1] - win[0] + 1, win[3] - win[2] + 1
+        pvel = rng.uniform(1, 5, (wx, wy, np_))
+        vel0 = rng.uniform(10, 20, (nx + 2, ny + 2, np_))
+        ref = vel0.copy()
+        orc.assemble_vel(pvel, np_, nx, ny, win, ref)
+        d_p = torch.from_numpy(pvel).cuda()
+        d_v = torch.from_numpy(vel0.copy()).cuda()
+        with torch.cuda.stream(st):
+            mct.assemble_vel_dev(d_p.data_ptr(), np_, nx, ny, win, d_v.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        assert np.array_equal(d_v.cpu().numpy(), ref), win
