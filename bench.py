@@ -109,7 +109,7 @@ def workload(args, rank, world):
     freqs = synth.example1_freqs() if args.config == "C1" else synth.freqs(c["np"])
     spec = dict(raylov=1, phaseGroup=0, nmodes=0)
     if args.config == "C3":
-        spec = dict(raylov=1, phaseGroup=1, nmodes=2)  # the Rayleigh half of C3; Love is a second pass
+        spec = dict(raylov=1, phaseGroup=1, nmodes=2)  # Rayleigh pass; the Love pass of C3 is `love_spec` below
     return grid, models, freqs, batch, spec
 
 
@@ -120,7 +120,6 @@ def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
     solves = 0
     t_used = 0.0
     n_evals = 0
-    nm = max(spec["nmodes"], 1)
     # a bounded x-slab of each model keeps the sample within the budget on big grids
     per_eval_cols = grid.nx * grid.ny
     probe_cols = min(per_eval_cols, 64 * nthreads)
@@ -129,17 +128,19 @@ def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
     for pts, par in models:
         t0 = time.perf_counter()
         vp = np.zeros(grid.shape); vs = np.zeros(grid.shape); rho = np.zeros(grid.shape); sid = np.zeros(grid.shape, np.int32)
-        orc.kdtree_to_grid(pts, par, grid, grid.full_box(), vp, vs, rho, sid)
+        orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
         t1 = time.perf_counter()
         vp, rho = orc.vs2vp_rho(vs, orc.LIBM)
         inval = orc.check_model(vs, grid)
         t2 = time.perf_counter()
-        pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (1, wx, 1, grid.ny), freqs, math_mode=orc.LIBM,
-                                                 nthreads=nthreads, **spec)
+        specs = spec if isinstance(spec, list) else [spec]
+        for sp in specs:
+            pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (1, wx, 1, grid.ny), freqs, math_mode=orc.LIBM,
+                                                     nthreads=nthreads, **sp)
+            solves += wx * grid.ny * len(freqs) * max(sp["nmodes"], 1)
         t3 = time.perf_counter()
         frac = wx / grid.nx  # K1/property maps covered the whole grid: charge them pro rata to the solved slab
         t_used += (t1 - t0) * frac + (t2 - t1) * frac + (t3 - t2)
-        solves += wx * grid.ny * len(freqs) * nm
         n_evals += frac
         detail = {"kdtree_to_grid_s_full_grid": t1 - t0, "maps_check_s_full_grid": t2 - t1, "dispersion_s_slab": t3 - t2,
                   "slab_columns": wx * grid.ny}
@@ -162,7 +163,8 @@ def run_reference(args):
     wall = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r, e, sample, _ = cpu_sample(grid, models[s % len(models):] + models[:s % len(models)], freqs, spec, per_step_budget, cores)
+        cspec = [spec, dict(raylov=0, phaseGroup=1, nmodes=2)] if args.config == "C3" else spec
+        r, e, sample, _ = cpu_sample(grid, models[s % len(models):] + models[:s % len(models)], freqs, cspec, per_step_budget, cores)
         if s >= args.warmup:
             times.append((r, e))
             wall.append(time.perf_counter() - t0)
@@ -233,9 +235,20 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
+    # config C3 = Rayleigh AND Love, phase + group, fundamental + first overtone: the Love maps are a second
+    # dispersion pass over the model the first pass left resident (stage 1 runs once, as in the reference)
+    love = args.config == "C3"
+    love_opts = capi.disp_opts(raylov=0, phaseGroup=1, nmodes=2) if love else None
+    if love:
+        d_pv2 = torch.empty_like(d_pv); d_gv2 = torch.empty_like(d_pv); d_ie2 = torch.empty_like(d_ie)
+        d_fl2 = torch.zeros(2 * batch, dtype=torch.int32, device=dev)
+
     def resident_step():
         capi.forward_batch_dev(grid, batch, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
                                d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream, slab=slab)
+        if love:
+            capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, (slab[0], slab[1], 1, grid.ny), freqs,
+                                     love_opts, d_pv2.data_ptr(), d_gv2.data_ptr(), d_ie2.data_ptr(), d_fl2.data_ptr(), stream)
         if column_sharded:
             dist.all_gather_into_tensor(gathered, d_pv)
 
@@ -246,7 +259,9 @@ def main():
         torch.cuda.synchronize()
 
     capi.set_nuclei_batch(pts, par, off)
-    solves_per_step_rank = batch * wx * grid.ny * nout
+    solves_per_step_rank = batch * wx * grid.ny * nout * (2 if love else 1)
+    if love:
+        assert batch == 1
     # ---- warm-up
     for _ in range(args.warmup):
         resident_step()
@@ -269,6 +284,29 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kt = capi.kernel_times(reset=True)
     st = capi.stats()
+    if love:  # roofline figures refer to the Rayleigh pass only: re-measure it alone (untimed for `value`)
+        capi.reset_stats()
+        for _ in range(args.steps):
+            capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, (slab[0], slab[1], 1, grid.ny), freqs,
+                                     opts, d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream)
+        kt_all = kt
+        kt = capi.kernel_times(reset=True)
+        kt["k1_ms"] = kt_all["k1_ms"]
+        st = dict(capi.stats(), n_launches=st["n_launches"])
+    # latency of a proposal-sized call (20 x 20 columns of model 0, device-resident): what one rjMCMC step issues
+    pw = (1, min(20, grid.nx), 1, min(20, grid.ny))
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_pp = torch.empty(400 * nout, dtype=torch.float64, device=dev); d_pg = torch.empty_like(d_pp)
+    d_pi = torch.empty(400, dtype=torch.int32, device=dev); d_pf = torch.zeros(2, dtype=torch.int32, device=dev)
+    for it in range(4):
+        if it == 1:
+            pa.record()
+        capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, pw, freqs, opts, d_pp.data_ptr(),
+                                 d_pg.data_ptr(), d_pi.data_ptr(), d_pf.data_ptr(), stream)
+    pb.record()
+    torch.cuda.synchronize()
+    proposal_ms = pa.elapsed_time(pb) / 3
+    capi.kernel_times(reset=True)
     capi.set_profiling(False)
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -278,7 +316,7 @@ def main():
 
     # ---- e2e: host nuclei -> C ABI -> host maps (pinned), every step
     e2e = None
-    if not column_sharded:
+    if not column_sharded and not love:
         h_pv = torch.empty((batch, grid.nx, grid.ny, nout), dtype=torch.float64).pin_memory()
         h_gv = torch.empty_like(h_pv).pin_memory()
         h_ie = torch.empty((batch, grid.nx, grid.ny), dtype=torch.int32).pin_memory()
@@ -319,13 +357,15 @@ def main():
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
-            r, e, sample, detail = cpu_sample(grid, models, freqs, spec, args.cpu_seconds, cores)
+            cspec = [spec, dict(raylov=0, phaseGroup=1, nmodes=2)] if love else spec
+            r, e, sample, detail = cpu_sample(grid, models, freqs, cspec, args.cpu_seconds, cores)
             cpu = {"value": r, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample,
                    "forward_evals_per_sec": e, "detail": detail}
         out = {"metric": "dispersion_solves_per_sec", "value": value, "unit": "column*period solves/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                "scaling": "strong" if column_sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "forward_evals_per_sec": batch * world * args.steps / (total_ms * 1e-3) if not column_sharded else args.steps / (total_ms * 1e-3),
+               "waves": "Rayleigh + Love" if love else "Rayleigh",
                "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
                                       f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={nm}, "
                                       f"{len(models[0][0])} nuclei",
@@ -334,6 +374,8 @@ def main():
                           "l2": "256 MiB buffer written between timed steps (L2 flush); model arrays per step also exceed L2"
                           if batch * ncell * 28 > (126 << 20) else "256 MiB buffer written between timed steps (L2 flush)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["n_launches"]), "roofline": roof, "cpu_baseline": cpu,
+               "proposal_latency": {"columns": (pw[1] - pw[0] + 1) * (pw[3] - pw[2] + 1), "ms": proposal_ms,
+                                    "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, warp-per-column kernel"},
                "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
                         "columns_per_step": st["n_columns"] / args.steps}}
         print(json.dumps(out))

@@ -91,7 +91,18 @@ class Grid:
         return (self.nx, self.ny, self.nz)
 
     def full_box(self):
+        """The box the reference passes for "the whole grid": (xmin,ymin,zmin)-(xmax,ymax,zmax).  NOTE: the
+        reference turns a box into indices with floor((b-min)/d)+1 (src/mcmc_loc2.f90:2034-2045); when
+        (zmax-zmin)/dz rounds just below nz-1 (e.g. nz = 60 over 12 km) the LAST PLANE is not covered.  That
+        is the reference's behaviour and is reproduced; use cover_box() to address every node."""
         return np.array([self.xmin, self.ymin, self.zmin, self.xmax, self.ymax, self.zmax], dtype=np.float64)
+
+    def cover_box(self):
+        """full_box() grown by half a cell on every side: its index window is exactly 1..n in each dimension."""
+        h = 0.5 * np.array([self.dx, self.dy, self.dz])
+        lo = np.array([self.xmin, self.ymin, self.zmin]) - h
+        hi = np.array([self.xmax, self.ymax, self.zmax]) + h
+        return np.concatenate([lo, hi]).astype(np.float64)
 
 
 def disp_opts(raylov=1, phaseGroup=0, nmodes=0, dphase=DPHASE_DEFAULT, variant="likelihood") -> mct_disp_opts:

@@ -1,0 +1,91 @@
+// k2_love_fast.cuh -- the production form of the Love secular function (dltar1, reference
+// surfmodes/surfdisp96.f:1056-1115): same IEEE operations and results as dltar1_dev in k2_dispersion.cuh,
+// organised like k2_rayleigh_fast.cuh -- refined reciprocals instead of five compiler divisions per layer
+// step, two straight-line cases (S oscillatory / S evanescent), one operand-range check per step, the
+// plainly written step as fallback.
+#pragma once
+
+struct E2 { double e1, e2; };
+
+__device__ __noinline__ E2 love_step_exact(const float4 L, double wvno, double omega, const E2 E) {
+  const double beta1 = (double)L.z;
+  const double rho1 = (double)L.w;
+  const double dm = (double)L.x;
+  const double xmu = rho1 * beta1 * beta1;
+  const double xkb = omega / beta1;
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  const double q = dm * rb;
+  double cosq, y, z, ex;
+  eig_pair(q, rb, wvno, xkb, dm, cosq, y, z, ex);
+  const double e10 = E.e1 * cosq + E.e2 * xmu * z;
+  const double e20 = E.e1 * y / xmu + E.e2 * cosq;
+  double xnor = fabs(e10);
+  const double ynor = fabs(e20);
+  if (ynor > xnor) xnor = ynor;
+  if (xnor < 1.e-40) xnor = 1.0;
+  E2 O;
+  O.e1 = e10 / xnor;
+  O.e2 = e20 / xnor;
+  return O;
+}
+
+__device__ __forceinline__ bool love_step_fast(const float4 L, double wvno, double omega, E2& E) {
+  RangeTrack R;
+  const double b = (double)L.z, rho = (double)L.w, dm = (double)L.x;
+  const double xmu = rho * b * b;
+  const double y_b = mct_rcp(b), y_mu = mct_rcp(xmu);
+  const double xkb = mct_div_r(omega, b, y_b);
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  const double q = dm * rb;
+  const double y_rb = mct_rcp(rb);
+  R.add(b); R.add(xmu); R.add(rb); // rb = 0 (wvno == xkb, the reference's equality branch) -> exact path
+  double cosq, sinq, z;
+  if (wvno < xkb) {
+    mct_sincos(q, &sinq, &cosq);
+    z = -rb * sinq;
+  } else {
+    const bool nq_ = q < 16.0;
+    const double f = mct_exp_core(nq_ ? -2.0 * q : -1.0);
+    const double fac = nq_ ? f : 0.0;
+    cosq = (1.0 + fac) * 0.5;
+    sinq = (1.0 - fac) * 0.5;
+    z = rb * sinq;
+  }
+  R.add(sinq);
+  const double y = mct_div_r(sinq, rb, y_rb);
+  const double e10 = E.e1 * cosq + E.e2 * xmu * z;
+  const double n20 = E.e1 * y;
+  R.add(n20);
+  const double e20 = mct_div_r(n20, xmu, y_mu) + E.e2 * cosq;
+  double xnor = fmax(fabs(e10), fabs(e20));
+  if (xnor < 1.e-40) xnor = 1.0;
+  const double y_n = mct_rcp(xnor);
+  R.add(xnor); R.add(e10); R.add(e20);
+  if (!R.ok()) return false;
+  E.e1 = mct_div_r(e10, xnor, y_n);
+  E.e2 = mct_div_r(e20, xnor, y_n);
+  return true;
+}
+
+__device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, int stride, int mmax, int llw,
+                                               double wvno, double omega) {
+  const bool om_ok = mct_exp_ok(omega);
+  E2 E;
+  {
+    const float4 L = __ldg(&lay[(size_t)(mmax - 1) * stride]);
+    const double beta1 = (double)L.z;
+    const double rho1 = (double)L.w;
+    const double xkb = omega / beta1;
+    const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    E.e1 = rho1 * rb;
+    E.e2 = 1.0 / (beta1 * beta1);
+  }
+  float4 L = __ldg(&lay[(size_t)max(mmax - 2, 0) * stride]);
+#pragma unroll 1
+  for (int m = mmax - 2; m >= llw - 1; --m) {
+    const float4 Lc = L;
+    if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]);
+    if (!(om_ok && love_step_fast(Lc, wvno, omega, E))) E = love_step_exact(Lc, wvno, omega, E);
+  }
+  return E.e1;
+}

@@ -182,7 +182,7 @@ def forward_eval(points, params, grid, freqs, derive_vp_rho=True, math_mode=PORT
     vs = np.zeros(grid.shape)
     rho = np.zeros(grid.shape)
     sid = np.zeros(grid.shape, np.int32)
-    kdtree_to_grid(points, params, grid, grid.full_box(), vp, vs, rho, sid)
+    kdtree_to_grid(points, params, grid, grid.cover_box(), vp, vs, rho, sid)  # every node, like mct_forward_eval
     if derive_vp_rho:
         vp, rho = vs2vp_rho(vs, math_mode)
     inval = check_model(vs, grid)

@@ -74,3 +74,15 @@ def test_kdtree_to_grid_window_and_pm():
     inside = np.zeros(grid.shape, bool)
     inside[w[0] - 1:w[1], w[2] - 1:w[3], w[4] - 1:w[5]] = True
     assert (s2[~inside] == -1).all() and np.array_equal(s2[inside], sid[inside])
+
+
+def test_full_box_rounding_quirk_is_reference_behaviour():
+    """floor((zmax-zmin)/dz)+1 can land on nz-1: the reference's "whole grid" box then skips the last plane
+    (src/mcmc_loc2.f90:2034-2045).  Reproduced, not fixed; cover_box() addresses every node."""
+    from mctomo_b200 import synth
+    grid = synth.make_grid(256, 256, 60)           # config C3: 12/(12/59) = 58.999999999999993
+    w = orc.box_window(grid, grid.full_box())
+    assert w[5] == 59 and w[1] == 256
+    assert list(orc.box_window(grid, grid.cover_box())) == [1, 256, 1, 256, 1, 60]
+    grid = synth.make_grid(101, 101, 121)          # example1's grid is unaffected
+    assert list(orc.box_window(grid, grid.full_box())) == [1, 101, 1, 101, 1, 121]

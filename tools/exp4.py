@@ -15,11 +15,11 @@ for name in sys.argv[1:] or ["C2", "C1", "C3"]:
         capi.set_k1_mode(mode)
         for b in bufs: b.zero_()
         for _ in range(2):
-            capi.voronoi_to_grid_dev(pts, par, grid, grid.full_box(), *[b.data_ptr() for b in bufs], s)
+            capi.voronoi_to_grid_dev(pts, par, grid, grid.cover_box(), *[b.data_ptr() for b in bufs], s)
         torch.cuda.synchronize()
         capi.set_profiling(True); capi.kernel_times(reset=True)
         for _ in range(5):
-            capi.voronoi_to_grid_dev(pts, par, grid, grid.full_box(), *[b.data_ptr() for b in bufs], s)
+            capi.voronoi_to_grid_dev(pts, par, grid, grid.cover_box(), *[b.data_ptr() for b in bufs], s)
         kt = capi.kernel_times(reset=True); capi.set_profiling(False)
         ms = kt["k1_ms"] / 5
         res.append([b.clone() for b in bufs])
