@@ -80,12 +80,17 @@ __device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, i
     E.e1 = rho1 * rb;
     E.e2 = 1.0 / (beta1 * beta1);
   }
-  float4 L = __ldg(&lay[(size_t)max(mmax - 2, 0) * stride]);
+  int m = mmax - 2;
+  if (om_ok) {
+    float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
 #pragma unroll 1
-  for (int m = mmax - 2; m >= llw - 1; --m) {
-    const float4 Lc = L;
-    if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]);
-    if (!(om_ok && love_step_fast(Lc, wvno, omega, E))) E = love_step_exact(Lc, wvno, omega, E);
+    for (; m >= llw - 1; --m) {
+      const float4 Lc = L;
+      if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]);
+      if (!love_step_fast(Lc, wvno, omega, E)) break;
+    }
   }
+#pragma unroll 1
+  for (; m >= llw - 1; --m) E = love_step_exact(__ldg(&lay[(size_t)m * stride]), wvno, omega, E); // cold
   return E.e1;
 }

@@ -251,12 +251,23 @@ __device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, i
     E.e4 = rho1 * rb;
     E.e5 = wvno2 - ra * rb;
   }
-  float4 L = __ldg(&lay[(size_t)max(mmax - 2, 0) * stride]);
+  // Hot loop: fast steps only.  A step that declines (rare: zero operands, wvno == omega/alpha, absurd
+  // magnitudes) leaves the loop; the remaining layers are then finished by the plainly written step in a
+  // separate cold loop, which keeps the non-inlined call and its register shuffling out of the hot body.
+  int m = mmax - 2;
+  if (om_ok) {
+    float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
 #pragma unroll 1
-  for (int m = mmax - 2; m >= llw - 1; --m) {
-    const float4 Lc = L;
-    if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]); // next layer's record is in flight during this step
-    if (!(om_ok && layer_step_fast(Lc, wvno, wvno2, omega, y_om, E))) E = layer_step_exact(Lc, wvno, wvno2, omega, E);
+    for (; m >= llw - 1; --m) {
+      const float4 Lc = L;
+      if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]); // next layer's record is in flight during this step
+      if (!layer_step_fast(Lc, wvno, wvno2, omega, y_om, E)) break;
+    }
+  }
+#pragma unroll 1
+  for (; m >= llw - 1; --m) {
+    E = layer_step_exact(__ldg(&lay[(size_t)m * stride]), wvno, wvno2, omega, E);
+    // (after one exact step the fast path could resume; not worth the control flow for a rare event)
   }
   if (llw != 1) {
     // water layer on top (:1196-1212): var(p, znul, ra, znul, wvno, xka, znul, dpth, ...)

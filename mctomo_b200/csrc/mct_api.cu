@@ -358,17 +358,8 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
     // Proposal-sized batches cannot fill the GPU with one thread per column: give each column a warp.
     const bool coop = (g.k2_mode == 2) || (g.k2_mode == 0 && ncol <= g.k2_coop_max);
     if (coop) k2_coop_kernel<<<ncol, 32, 0, st>>>(P);
-    else switch (variant) {
-      case 0: k2_dispersion_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P); break;
-      case 1: k2_dispersion_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P); break; // sorted, 128-thread blocks
-      case 2: k2_dispersion_w32r160<<<nw, 32, 0, st>>>(P); break;
-      case 4: k2_dispersion_w32r96<<<nw, 32, 0, st>>>(P); break;
-      case 5: k2_dispersion_w32r80<<<nw, 32, 0, st>>>(P); break;
-      case 3: k2_dispersion_w32r128<<<nw, 32, 0, st>>>(P); break;
-      case 6: k2_dispersion_fast_r160<<<nw, 32, 0, st>>>(P); break;
-      case 8: k2_dispersion_fast_r96<<<nw, 32, 0, st>>>(P); break;
-      default: k2_dispersion_fast_r128<<<nw, 32, 0, st>>>(P); break; // 7
-    }
+    else if (variant == 3 || variant == 0) k2_dispersion_plain<<<nw, 32, 0, st>>>(P); // A/B reference (0: unsorted too)
+    else k2_dispersion_fast_r128<<<nw, 32, 0, st>>>(P);
   }
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
