@@ -343,9 +343,16 @@ def main():
         k2_s = kt["k2_ms"] * 1e-3
         probe = capi.fp64_peak_probe()
         achieved = w2 / k2_s / 1e12 if k2_s > 0 else None
+        traffic = None
+        try:  # DRAM bytes per K2 launch from the committed ncu capture of this same workload (default config only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+            if args.config == "C2" and batch == 32 and not column_sharded:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "fp64", "achieved": achieved, "peak": probe["dfma_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / probe["dfma_tflops"] if achieved else None, "traffic": None,
-                "kernel": "k2_dispersion_kernel", "k2_ms_per_step": kt["k2_ms"] / args.steps,
+                "frac": achieved / probe["dfma_tflops"] if achieved else None, "traffic": traffic,
+                "kernel": "k2_dispersion_fast_r128" if batch * wx * grid.ny > 16384 else "k2_coop_kernel", "k2_ms_per_step": kt["k2_ms"] / args.steps,
                 "k2_share_of_step": kt["k2_ms"] / sum(step_ms),
                 "peak_source": "measured live: 8 independent DFMA chains/thread (mct_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_dmul_dadd_tflops": probe["dmul_dadd_tflops"],
