@@ -206,11 +206,13 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, double wvno, dou
   // ee(i) = sum_j e(j)*ca(j,i), left to right from 0 (:1184-1190); ca(2,5)=ca(1,4), ca(4,4)=ca(2,2), ca(4,5)=ca(1,2),
   // ca(5,2)=ca(4,1), ca(5,4)=ca(2,1), ca(5,5)=ca(1,1)
   const double e1 = E.e1, e2 = E.e2, e3 = E.e3, e4 = E.e4, e5 = E.e5;
-  double ee1 = 0.0 + e1 * ca11; ee1 = ee1 + e2 * ca21; ee1 = ee1 + e3 * ca31; ee1 = ee1 + e4 * ca41; ee1 = ee1 + e5 * ca51;
-  double ee2 = 0.0 + e1 * ca12; ee2 = ee2 + e2 * ca22; ee2 = ee2 + e3 * ca32; ee2 = ee2 + e4 * ca42; ee2 = ee2 + e5 * ca41;
-  double ee3 = 0.0 + e1 * ca13; ee3 = ee3 + e2 * ca23; ee3 = ee3 + e3 * ca33; ee3 = ee3 + e4 * ca43; ee3 = ee3 + e5 * ca53;
-  double ee4 = 0.0 + e1 * ca14; ee4 = ee4 + e2 * ca24; ee4 = ee4 + e3 * ca34; ee4 = ee4 + e4 * ca22; ee4 = ee4 + e5 * ca21;
-  double ee5 = 0.0 + e1 * ca15; ee5 = ee5 + e2 * ca14; ee5 = ee5 + e3 * ca35; ee5 = ee5 + e4 * ca12; ee5 = ee5 + e5 * ca11;
+  // (the reference starts every sum from 0.0; 0.0 + x differs from x only for x = -0.0, and that can matter only
+  //  if the whole sum stays zero -- in which case the range check below rejects the step: dropping the add is exact)
+  double ee1 = e1 * ca11; ee1 = ee1 + e2 * ca21; ee1 = ee1 + e3 * ca31; ee1 = ee1 + e4 * ca41; ee1 = ee1 + e5 * ca51;
+  double ee2 = e1 * ca12; ee2 = ee2 + e2 * ca22; ee2 = ee2 + e3 * ca32; ee2 = ee2 + e4 * ca42; ee2 = ee2 + e5 * ca41;
+  double ee3 = e1 * ca13; ee3 = ee3 + e2 * ca23; ee3 = ee3 + e3 * ca33; ee3 = ee3 + e4 * ca43; ee3 = ee3 + e5 * ca53;
+  double ee4 = e1 * ca14; ee4 = ee4 + e2 * ca24; ee4 = ee4 + e3 * ca34; ee4 = ee4 + e4 * ca22; ee4 = ee4 + e5 * ca21;
+  double ee5 = e1 * ca15; ee5 = ee5 + e2 * ca14; ee5 = ee5 + e3 * ca35; ee5 = ee5 + e4 * ca12; ee5 = ee5 + e5 * ca11;
   // normc (:1350-1360): max |ee|, then five quotients by the same scale
   double t1 = fmax(fmax(fmax(fabs(ee1), fabs(ee2)), fmax(fabs(ee3), fabs(ee4))), fabs(ee5));
   if (t1 < 1.e-40) t1 = 1.0;
