@@ -29,11 +29,12 @@ __device__ __noinline__ E2 love_step_exact(const float4 L, double wvno, double o
   return O;
 }
 
-__device__ __forceinline__ bool love_step_fast(const float4 L, double wvno, double omega, E2& E) {
+// Rc = {1/beta, 1/(rho beta^2), -, -} from layer_recips_kernel
+__device__ __forceinline__ bool love_step_fast(const float4 L, const double4 Rc, double wvno, double omega, E2& E) {
   RangeTrack R;
   const double b = (double)L.z, rho = (double)L.w, dm = (double)L.x;
   const double xmu = rho * b * b;
-  const double y_b = mct_rcp(b), y_mu = mct_rcp(xmu);
+  const double y_b = Rc.x, y_mu = Rc.y;
   const double xkb = mct_div_r(omega, b, y_b);
   const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
   const double q = dm * rb;
@@ -67,8 +68,8 @@ __device__ __forceinline__ bool love_step_fast(const float4 L, double wvno, doub
   return true;
 }
 
-__device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, int stride, int mmax, int llw,
-                                               double wvno, double omega) {
+__device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, const double4* __restrict__ layr, int stride,
+                                               int mmax, int llw, double wvno, double omega) {
   const bool om_ok = mct_exp_ok(omega);
   E2 E;
   {
@@ -83,11 +84,16 @@ __device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, i
   int m = mmax - 2;
   if (om_ok) {
     float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
+    double4 Rn = layr[(size_t)max(m, 0) * stride];
 #pragma unroll 1
     for (; m >= llw - 1; --m) {
       const float4 Lc = L;
-      if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]);
-      if (!love_step_fast(Lc, wvno, omega, E)) break;
+      const double4 Rc = Rn;
+      if (m > 0) {
+        L = __ldg(&lay[(size_t)(m - 1) * stride]);
+        Rn = layr[(size_t)(m - 1) * stride];
+      }
+      if (!love_step_fast(Lc, Rc, wvno, omega, E)) break;
     }
   }
 #pragma unroll 1

@@ -98,14 +98,13 @@ __device__ __noinline__ EVec layer_step_exact(const float4 L, double wvno, doubl
 
 // ---- the fast layer step ----------------------------------------------------------------------------
 // Returns false (E untouched) when the step must be redone by layer_step_exact.
-__device__ __forceinline__ bool layer_step_fast(const float4 L, double wvno, double wvno2, double omega, double y_om, EVec& E) {
+// Rc = {1/alpha, 1/beta, 1/rho, 1/rho^2}: the refined reciprocals of this layer's constants, computed once per
+// forward evaluation by layer_recips_kernel with the same mct_rcp sequence (bit-identical to computing them here).
+__device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc, double wvno, double wvno2, double omega, double y_om, EVec& E) {
   RangeTrack R;
   const double a = (double)L.y, b = (double)L.z, dpth = (double)L.x, rho = (double)L.w;
   const double rho2 = rho * rho;
-  // three independent reciprocals (alpha, beta, rho) + 1/rho^2 from 1/rho
-  const double y_a = mct_rcp(a), y_b = mct_rcp(b), y_rho = mct_rcp(rho);
-  double y_rho2 = __dmul_rn(y_rho, y_rho);
-  y_rho2 = __fma_rn(y_rho2, __fma_rn(-rho2, y_rho2, 1.0), y_rho2);
+  const double y_a = Rc.x, y_b = Rc.y, y_rho = Rc.z, y_rho2 = Rc.w;
   R.add(a); R.add(b); R.add(rho); R.add(rho2);
   const double xka = mct_div_r(omega, a, y_a);
   const double xkb = mct_div_r(omega, b, y_b);
@@ -228,8 +227,8 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, double wvno, dou
 }
 
 // ---- dltar4: half-space start vector, layer recursion bottom -> top, optional water layer ---------------
-__device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, int stride, int mmax, int llw,
-                                               double wvno, double omga) {
+__device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, const double4* __restrict__ layr, int stride,
+                                               int mmax, int llw, double wvno, double omga) {
   double omega = omga;
   if (omega < 1.0e-4) omega = 1.0e-4;
   const double wvno2 = wvno * wvno;
@@ -259,11 +258,16 @@ __device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, i
   int m = mmax - 2;
   if (om_ok) {
     float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
+    double4 Rn = layr[(size_t)max(m, 0) * stride];
 #pragma unroll 1
     for (; m >= llw - 1; --m) {
       const float4 Lc = L;
-      if (m > 0) L = __ldg(&lay[(size_t)(m - 1) * stride]); // next layer's record is in flight during this step
-      if (!layer_step_fast(Lc, wvno, wvno2, omega, y_om, E)) break;
+      const double4 Rc = Rn;
+      if (m > 0) { // next layer's records are in flight during this step
+        L = __ldg(&lay[(size_t)(m - 1) * stride]);
+        Rn = layr[(size_t)(m - 1) * stride];
+      }
+      if (!layer_step_fast(Lc, Rc, wvno, wvno2, omega, y_om, E)) break;
     }
   }
 #pragma unroll 1

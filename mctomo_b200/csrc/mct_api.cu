@@ -55,7 +55,7 @@ struct Ctx {
   // staged model (host-pointer entry points)
   DevBuf m_vp, m_vs, m_rho, m_sites;
   // layered columns, their processing order, sort scratch
-  DevBuf lay, nlay, status, perm, bins;
+  DevBuf lay, layr, nlay, status, perm, bins;
   int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
   int k2_coop_max = 16384;  // auto: batches up to this many columns take the warp-cooperative kernel
@@ -313,7 +313,7 @@ int plan_disp(const mct_grid* gr, int ix0, int ix1, int iy0, int iy1, int np, co
 }
 
 int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_opts* opt, double* d_pvel, double* d_gvel,
-              int32_t* d_ierr, const int32_t* d_skip, int cols_per_model, cudaStream_t st) {
+              int32_t* d_ierr, const int32_t* d_skip, int cols_per_model, int max_layers, cudaStream_t st) {
   K2Params P;
   P.lay = (const float4*)g.lay.p;
   P.nlay = (const int32_t*)g.nlay.p;
@@ -335,6 +335,16 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   P.cols_per_model = cols_per_model > 0 ? cols_per_model : ncol;
   P.counters = (unsigned long long*)g.counters.p;
   for (int i = 0; i < MCT_MAX_PERIODS; ++i) P.t[i] = (i < np) ? 1 / freqs[i] : 0.0; // dble(1/freqs), surfmodes.f90:82
+  // Per-layer reciprocal table for the fast secular functions.
+  {
+    int rc;
+    if ((rc = ensure(g.layr, sizeof(double4) * (size_t)stride * (size_t)max_layers))) return rc;
+    ProfScope ps(2, st);
+    layer_recips_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P.lay, P.nlay, ncol, stride, P.ifunc, (double4*)g.layr.p);
+    g.host_stats.n_launches += 1;
+    P.layr = (const double4*)g.layr.p;
+  }
+  CK(cudaGetLastError());
   // Order the columns by layer count (descending) so every warp runs one layer-loop trip count.
   const int variant = g.k2_variant;
   P.perm = nullptr;
@@ -401,7 +411,7 @@ int disp_core(const double* d_vp, const double* d_vs, const double* d_rho, const
   }
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
-  return launch_k2(pl.ncol, pl.stride, freqs, np, opt, d_pvel, d_gvel, d_ierr, do_check ? d_flags : nullptr, pl.cpm, st);
+  return launch_k2(pl.ncol, pl.stride, freqs, np, opt, d_pvel, d_gvel, d_ierr, do_check ? d_flags : nullptr, pl.cpm, gr->nz + 1, st);
 }
 
 // K1 per model + property maps + disp_core over the x-slab ixs0..ixs1 of every model of the resident set.
@@ -502,7 +512,7 @@ int mct_shutdown(void) {
   if (!g.init) return MCT_OK;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.nlay, &g.status, &g.perm, &g.bins,
+  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins,
                     &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters};
   for (DevBuf* b : bufs) release(*b);
   release(g.pin_a);
@@ -759,7 +769,7 @@ int mct_surfmodes_batch(const double* thick, const double* vp, const double* vs,
   prelayered_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(L);
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
-  if ((rc = launch_k2(ncol, stride, freqs, np, opt, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, nullptr, ncol, st))) return rc;
+  if ((rc = launch_k2(ncol, stride, freqs, np, opt, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, nullptr, ncol, maxl, st))) return rc;
   int32_t hflags[2] = {0, 0};
   CK(cudaMemcpyAsync(phase, g.o_pvel.p, nbo, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(group, g.o_gvel.p, nbo, cudaMemcpyDeviceToHost, st));
