@@ -180,11 +180,30 @@ def run_reference(args):
                       "per_step": "bounded sample of the workload on the host CPU"},
            "cpu_baseline": {"value": rate, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": rate, "unit": "column*period solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    GUARD.emit(json.dumps(out))
+
+
+class StdoutGuard:
+    """Keeps stdout clean for the ONE JSON line: anything libraries print to fd 1 meanwhile (NCCL's version banner,
+    torchrun notices) is sent to stderr; emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+GUARD = None
 
 
 def main():
+    global GUARD
     args = parse()
+    GUARD = StdoutGuard()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -385,7 +404,7 @@ def main():
                                     "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, warp-per-column kernel"},
                "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
                         "columns_per_step": st["n_columns"] / args.steps}}
-        print(json.dumps(out))
+        GUARD.emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
