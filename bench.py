@@ -81,6 +81,13 @@ class ClockSampler:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
+        if not any(len(r) >= 9 for r in self.rows):  # region shorter than the sampling period: one immediate sample
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout
+                self.rows += [[c.strip() for c in line.split(",")] for line in out.splitlines()]
+            except Exception:
+                pass
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
