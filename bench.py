@@ -394,6 +394,13 @@ def main():
             r, e, sample, detail = cpu_sample(grid, models, freqs, cspec, args.cpu_seconds, cores)
             cpu = {"value": r, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample,
                    "forward_evals_per_sec": e, "detail": detail}
+            if e2e:
+                # share of the forward model's wall time that now runs on the GPU: what is left on the host in the
+                # end-to-end call (tree build, staging, launches) against the CPU path's time for the same evaluations
+                host_ms = max(0.0, e2e["ms_per_step"] - (kt["k1_ms"] + kt["k2_ms"] + kt["other_ms"]) / args.steps)
+                cpu_ms = batch / e * 1e3
+                cpu["gpu_share_of_forward_wall_time"] = 1.0 - host_ms / cpu_ms
+                cpu["host_residual_ms_per_step"] = host_ms
         out = {"metric": "dispersion_solves_per_sec", "value": value, "unit": "column*period solves/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                "scaling": "strong" if column_sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
