@@ -372,3 +372,52 @@ def test_assemble_vel_dev(mct):
             mct.assemble_vel_dev(d_p.data_ptr(), np_, nx, ny, win, d_v.data_ptr(), st.cuda_stream)
         st.synchronize()
         assert np.array_equal(d_v.cpu().numpy(), ref), win
+
+
+@pytest.mark.parametrize("seed,raylov,pg,nm", [(1, 1, 0, 0), (2, 1, 1, 2), (3, 0, 1, 0), (4, 0, 0, 3), (5, 1, 1, 0)])
+def test_fuzz_random_layer_stacks(mct, seed, raylov, pg, nm):
+    """1500 random pre-layered columns per case through mct_surfmodes_batch: thin and very thick layers (the
+    exp-skipping branches p >= 16, exa >= 60), vp/vs from 1.45 to 2.6, strong and tiny velocity contrasts,
+    water layers, periods from 0.1 s to 80 s.  Every column must match the oracle bit for bit, including the
+    columns the reference routes to the GRT branch (ierr = 2) and the ones whose search fails (ierr = 1)."""
+    rng = np.random.default_rng(seed)
+    ncol = 1500
+    cols, offs = [], [0]
+    for c in range(ncol):
+        n = int(rng.integers(1, 14))
+        water = rng.random() < 0.15 and n >= 2
+        vs = np.sort(rng.uniform(0.3, 5.0, n))
+        if rng.random() < 0.2:                      # near-identical neighbours
+            vs[1:] = vs[:-1] + rng.uniform(1e-7, 1e-3, n - 1)
+        if rng.random() < 0.1 and n >= 3:           # a low-velocity layer somewhere: GRT branch in the reference
+            k = int(rng.integers(1, n - 1))
+            vs[k] = vs[0] * rng.uniform(0.5, 0.99)
+        ratio = rng.uniform(1.45, 2.6, n)
+        vp = vs * ratio
+        rho = rng.uniform(1.0, 3.5, n)
+        th = rng.choice([rng.uniform(1e-3, 0.05), rng.uniform(0.1, 3.0), rng.uniform(5.0, 60.0)], size=n)
+        th[-1] = 0.0
+        if water:
+            vs[0], vp[0], rho[0], th[0] = 0.0, 1.5, 1.0, rng.uniform(0.05, 4.0)
+        cols.append(np.stack([th, vp, vs, rho], 1))
+        offs.append(offs[-1] + n)
+    a = np.concatenate(cols)
+    periods = np.sort(rng.choice(np.geomspace(0.1, 80.0, 40), 14, replace=False))
+    freqs = 1.0 / periods
+    opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nm)
+    for mode in (1, 2):
+        mct.set_k2_mode(mode)
+        ph, gr, ie, rc = mct.surfmodes_batch(a[:, 0], a[:, 1], a[:, 2], a[:, 3], offs, freqs, opts)
+        seen = {0: 0, 1: 0, 2: 0}
+        for c in range(ncol):
+            s = slice(offs[c], offs[c + 1])
+            rc0, p0, g0, e0, _ = orc.surfmodes(a[s, 0], a[s, 1], a[s, 2], a[s, 3], freqs, raylov, pg, nm)
+            if rc0 == 2:
+                assert ie[c] == 2, c
+                seen[2] += 1
+                continue
+            assert rc0 == 0 and e0 == ie[c], (c, rc0, e0, ie[c])
+            assert np.array_equal(ph[c], p0) and np.array_equal(gr[c], g0), (c, np.abs(ph[c] - p0).max())
+            seen[e0] += 1
+        assert seen[0] + seen[1] > 1000 and seen[0] > 100 and seen[2] > 20
+    mct.set_k2_mode(0)
