@@ -38,7 +38,7 @@ module m_mctomo_b200
 
     ! mirrors `mct_disp_opts`
     type, bind(C) :: mct_disp_opts
-        integer(c_int32_t) :: raylov, phaseGroup, nmodes
+        integer(c_int32_t) :: raylov, phaseGroup, nmodes, check_scope
         real(c_double)     :: dphase, layer_eps, water_thresh, preset
     end type
 
@@ -69,6 +69,17 @@ module m_mctomo_b200
             import :: c_int, c_ptr, c_int64_t
             type(c_ptr), value :: vs, vp, rho
             integer(c_int64_t), value :: n
+        end function
+        integer(c_int) function mct_vs2vp_rho_window(vs, vp, rho, g, w) bind(C, name='mct_vs2vp_rho_window')
+            import :: c_int, c_ptr, mct_grid
+            type(c_ptr), value :: vs, vp, rho
+            type(mct_grid), intent(in) :: g
+            type(c_ptr), value :: w                      ! integer(c_int32_t) (6): ix0,ix1,iy0,iy1,iz0,iz1
+        end function
+        integer(c_int) function mct_box_window(g, box, w) bind(C, name='mct_box_window')
+            import :: c_int, c_ptr, mct_grid
+            type(mct_grid), intent(in) :: g
+            type(c_ptr), value :: box, w
         end function
         integer(c_int) function mct_surf_dispersion(vp, vs, rho, g, ix0, ix1, iy0, iy1, freqs, np, opt, &
                 pvel, gvel, ierr, model_invalid) bind(C, name='mct_surf_dispersion')
@@ -136,11 +147,25 @@ contains
         if (rc /= 0) call fail('mct_voronoi_to_grid', rc)
     end subroutine
 
-    ! vs2vp_3d + vp2rho_3d (src/likelihood.f90:75-76)
-    subroutine vs2vp_rho_b200(model)
+    ! vs2vp_3d + vp2rho_3d (src/likelihood.f90:75-76).  With bnd_box present only the nodes kdtree_to_grid just
+    ! rewrote are recomputed -- the rest of vp, rho is unchanged since the previous call, so the result equals the
+    ! reference's whole-grid pass at a fraction of the transfers.
+    subroutine vs2vp_rho_b200(model, grid, bnd_box)
         type(T_MOD), intent(inout), target :: model
+        type(T_GRID), intent(in), optional :: grid
+        type(d3), dimension(2), intent(in), optional :: bnd_box
+        real(c_double), target :: box(6)
+        integer(c_int32_t), target :: w(6)
+        type(mct_grid) :: g
         integer(c_int) :: rc
-        rc = mct_vs2vp_rho(c_loc(model%vs), c_loc(model%vp), c_loc(model%rho), int(size(model%vs), c_int64_t))
+        if (present(grid) .and. present(bnd_box)) then
+            g = c_grid(grid)
+            box = [bnd_box(1)%x, bnd_box(1)%y, bnd_box(1)%z, bnd_box(2)%x, bnd_box(2)%y, bnd_box(2)%z]
+            rc = mct_box_window(g, c_loc(box), c_loc(w))
+            if (rc == 0) rc = mct_vs2vp_rho_window(c_loc(model%vs), c_loc(model%vp), c_loc(model%rho), g, c_loc(w))
+        else
+            rc = mct_vs2vp_rho(c_loc(model%vs), c_loc(model%vp), c_loc(model%rho), int(size(model%vs), c_int64_t))
+        endif
         if (rc /= 0) call fail('mct_vs2vp_rho', rc)
     end subroutine
 
@@ -173,6 +198,9 @@ contains
         opt%raylov = raylov
         opt%phaseGroup = phaseGroup
         opt%nmodes = nmodes
+        ! 0 = check_model over the whole grid, exactly as the reference; 1 = over the window only (equivalent in the
+        ! sampler, where the model outside the perturbed box is the previously accepted, valid one) and cheaper
+        opt%check_scope = 0
         opt%dphase = dPhaseVel
         if (var == 0) then
             opt%layer_eps = real(1.0E-10, c_double)      ! EPS, likelihood_surf.F90:37 (a default-real literal)

@@ -57,6 +57,10 @@ typedef struct {
   int32_t phaseGroup; /* 0 phase only, 1 phase + group (surfdisp96 igr) */
   int32_t nmodes;     /* <= 0: surfmodes -> surfdisp96 (fundamental, outputs preset to 100.0)
                          >= 1: surfmmodes -> surfdisp_mmodes with that many modes (outputs preset to 0) */
+  int32_t check_scope; /* columns check_model scans: 0 = the whole grid (the reference, likelihood_surf.F90:631-646);
+                          1 = only the window's columns.  In the sampler the model outside the perturbed box is
+                          the previously accepted -- hence valid -- model, so both give the same answer there,
+                          and scope 1 spares the host-pointer call the upload of the whole vs grid. */
   double dphase;      /* paras%dc = settings%dPhaseVel */
   double layer_eps;   /* new layer when |vs(k)-vs_run| > layer_eps: (double)1e-10f in
                          likelihood_surf.F90:37,560; (double)1e-5f in forward_modelling.f90:27 */
@@ -115,6 +119,10 @@ int mct_box_window(const mct_grid* g, const double box[6], int32_t w[6]);
  * src/likelihood.f90:75-76): vp = vs*1.730, rho = 1.74*vp**0.25. */
 int mct_vs2vp_rho(const double* vs, double* vp, double* rho, int64_t n);
 int mct_vs2vp_rho_dev(const double* d_vs, double* d_vp, double* d_rho, int64_t n, void* stream);
+/* Same maps restricted to the nodes of an index window w = {ix0,ix1,iy0,iy1,iz0,iz1} (1-based inclusive, e.g. from
+ * mct_box_window) of (nz,ny,nx) host arrays.  After a kdtree_to_grid call on a box only those nodes of vs have
+ * changed, so this leaves vp and rho exactly as the reference's whole-grid recomputation does. */
+int mct_vs2vp_rho_window(const double* vs, double* vp, double* rho, const mct_grid* g, const int32_t w[6]);
 
 /* ---- stage 2: per-column modal dispersion ------------------------------------------------
  * Replaces surf_likelihood's block likelihood_surf.F90:161-206 (check_model,

@@ -48,7 +48,7 @@ class mct_grid(C.Structure):
 
 
 class mct_disp_opts(C.Structure):
-    _fields_ = [("raylov", C.c_int32), ("phaseGroup", C.c_int32), ("nmodes", C.c_int32),
+    _fields_ = [("raylov", C.c_int32), ("phaseGroup", C.c_int32), ("nmodes", C.c_int32), ("check_scope", C.c_int32),
                 ("dphase", C.c_double), ("layer_eps", C.c_double), ("water_thresh", C.c_double),
                 ("preset", C.c_double)]
 
@@ -105,12 +105,13 @@ class Grid:
         return np.concatenate([lo, hi]).astype(np.float64)
 
 
-def disp_opts(raylov=1, phaseGroup=0, nmodes=0, dphase=DPHASE_DEFAULT, variant="likelihood") -> mct_disp_opts:
-    """variant 'likelihood' = likelihood_surf.F90 constants, 'modelling' = forward_modelling.f90 constants."""
+def disp_opts(raylov=1, phaseGroup=0, nmodes=0, dphase=DPHASE_DEFAULT, variant="likelihood", check_scope=0) -> mct_disp_opts:
+    """variant 'likelihood' = likelihood_surf.F90 constants, 'modelling' = forward_modelling.f90 constants;
+    check_scope 0 = check_model over the whole grid (reference), 1 = over the window's columns only."""
     if variant == "likelihood":
-        return mct_disp_opts(raylov, phaseGroup, nmodes, dphase, EPS_LIKELIHOOD, EPS_LIKELIHOOD, 100.0)
+        return mct_disp_opts(raylov, phaseGroup, nmodes, check_scope, dphase, EPS_LIKELIHOOD, EPS_LIKELIHOOD, 100.0)
     if variant == "modelling":
-        return mct_disp_opts(raylov, phaseGroup, nmodes, dphase, EPS_MODELLING, 0.0, 1000.0)
+        return mct_disp_opts(raylov, phaseGroup, nmodes, check_scope, dphase, EPS_MODELLING, 0.0, 1000.0)
     raise ValueError(variant)
 
 
@@ -216,6 +217,16 @@ def vs2vp_rho(vs):
     rho = np.empty_like(vs)
     _check(lib().mct_vs2vp_rho(vs.ctypes.data, vp.ctypes.data, rho.ctypes.data, vs.size))
     return vp, rho
+
+
+def vs2vp_rho_window(vs, vp, rho, grid: Grid, w):
+    """vs2vp_3d + vp2rho_3d restricted to the index window w = (ix0,ix1,iy0,iy1,iz0,iz1); vp, rho updated in place."""
+    L = lib()
+    L.mct_vs2vp_rho_window.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(mct_grid), C.c_void_p]
+    for a in (vs, vp, rho):
+        assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == grid.shape
+    wv = np.ascontiguousarray(w, dtype=np.int32)
+    _check(L.mct_vs2vp_rho_window(vs.ctypes.data, vp.ctypes.data, rho.ctypes.data, C.byref(grid.c()), wv.ctypes.data))
 
 
 def surf_dispersion(vp, vs, rho, grid: Grid, window, freqs, opts: mct_disp_opts, check=True):

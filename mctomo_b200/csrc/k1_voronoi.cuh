@@ -167,19 +167,20 @@ __global__ void __launch_bounds__(256) vs2vp_rho_kernel(const double* __restrict
   }
 }
 
-// check_model (src/likelihood_surf.F90:631-646) over columns [col0, col0+ncols): flag[0] |= any(vs(2:,j,i) < vs(1,j,i)).
-// One warp per column, lanes strided over z (coalesced).
-// Batched form: model b = c / cols_per_model reads its columns at vs + b*model_stride + (col0 + c%cols_per_model)*nz and
-// raises flag[2*b].
-__global__ void __launch_bounds__(256) check_model_kernel(const double* __restrict__ vs, long long col0, long long cols_per_model,
+// check_model (src/likelihood_surf.F90:631-646) over the columns ix0..ix0+wx-1, iy0..iy0+wy-1 (1-based; the reference
+// scans the whole grid = 1..nx, 1..ny): flag |= any(vs(2:,j,i) < vs(1,j,i)).  One warp per column, lanes strided over z
+// (coalesced).  Batched form: model b = c / (wx*wy) reads its columns at vs + b*model_stride and raises flag[2*b].
+__global__ void __launch_bounds__(256) check_model_kernel(const double* __restrict__ vs, int ix0, int iy0, int wx, int wy, int ny,
                                                           int nmodels, long long model_stride, int nz, int32_t* flag) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long cols_per_model = (long long)wx * wy;
   const long long ncols = cols_per_model * nmodels;
   for (long long c = warp; c < ncols; c += nwarps) {
     const long long b = c / cols_per_model, cm = c - b * cols_per_model;
-    const double* col = vs + b * model_stride + (col0 + cm) * nz;
+    const long long i = ix0 + cm / wy, j = iy0 + cm % wy;
+    const double* col = vs + b * model_stride + ((i - 1) * ny + (j - 1)) * nz;
     const double v1 = col[0];
     bool bad = false;
     for (int k = 1 + lane; k < nz; k += 32) bad |= (col[k] < v1);

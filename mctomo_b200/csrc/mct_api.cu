@@ -379,8 +379,8 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
 // check_model + layerize + K2 on device-resident whole-grid arrays (pl.nb models stacked along x).
 // d_flags: int32[2*nb]: per model {model_invalid, max condition code}.
 int disp_core(const double* d_vp, const double* d_vs, const double* d_rho, const mct_grid* gr, const DispPlan& pl,
-              const double* freqs, int np, const mct_disp_opts* opt, bool do_check, long long check_col0,
-              long long check_cols_per_model, double* d_pvel, double* d_gvel, int32_t* d_ierr, int32_t* d_flags, cudaStream_t st) {
+              const double* freqs, int np, const mct_disp_opts* opt, bool do_check, const int cw[4] /* check_model region:
+              ix0, iy0, wx, wy */, double* d_pvel, double* d_gvel, int32_t* d_ierr, int32_t* d_flags, cudaStream_t st) {
   int rc;
   const long long model_stride = (long long)gr->nx * gr->ny * gr->nz;
   if ((rc = ensure(g.lay, sizeof(float4) * (size_t)pl.stride * (size_t)(gr->nz + 1)))) return rc;
@@ -389,8 +389,8 @@ int disp_core(const double* d_vp, const double* d_vs, const double* d_rho, const
   CK(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int32_t) * (size_t)pl.nb, st));
   if (do_check) {
     ProfScope ps(2, st);
-    check_model_kernel<<<grid_blocks(check_cols_per_model * pl.nb * 32, 256, 8), 256, 0, st>>>(
-        d_vs, check_col0, check_cols_per_model, pl.nb, model_stride, gr->nz, d_flags);
+    check_model_kernel<<<grid_blocks((long long)cw[2] * cw[3] * pl.nb * 32, 256, 8), 256, 0, st>>>(
+        d_vs, cw[0], cw[1], cw[2], cw[3], gr->ny, pl.nb, model_stride, gr->nz, d_flags);
     g.host_stats.n_launches += 1;
   }
   CK(cudaGetLastError());
@@ -444,8 +444,8 @@ int forward_core(const mct_grid* gr, int nb, int derive_vp_rho, const DispPlan& 
       }
     }
   }
-  return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, true, (long long)(pl.ix0 - 1) * gr->ny, (long long)pl.wx * gr->ny,
-                   d_pvel, d_gvel, d_ierr, d_flags, st);
+  const int cw[4] = {pl.ix0, 1, pl.wx, gr->ny}; // check_model over this rank's slab (whole grid when unsharded)
+  return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, true, cw, d_pvel, d_gvel, d_ierr, d_flags, st);
 }
 
 int flags_to_code(int maxst) {
@@ -660,6 +660,44 @@ int mct_vs2vp_rho(const double* vs, double* vp, double* rho, int64_t n) {
   return MCT_OK;
 }
 
+int mct_vs2vp_rho_window(const double* vs, double* vp, double* rho, const mct_grid* gr, const int32_t w[6]) {
+  NEED_INIT();
+  if (!vs || !vp || !rho || !grid_ok(gr) || !w) return fail(MCT_E_INVALID_ARG, "vs2vp_rho_window: bad arguments");
+  const int wx = w[1] - w[0] + 1, wy = w[3] - w[2] + 1, wz = w[5] - w[4] + 1;
+  if (wx <= 0 || wy <= 0 || wz <= 0) return MCT_OK;
+  if (w[0] < 1 || w[2] < 1 || w[4] < 1 || w[1] > gr->nx || w[3] > gr->ny || w[5] > gr->nz)
+    return fail(MCT_E_INVALID_ARG, "vs2vp_rho_window: window outside the grid");
+  // packed (wz,wy,wx) staging, like mct_voronoi_to_grid
+  const size_t nn = (size_t)wx * wy * wz;
+  int rc;
+  if ((rc = ensure(g.m_vs, nn * 8))) return rc;
+  if ((rc = ensure(g.m_vp, nn * 8))) return rc;
+  if ((rc = ensure(g.m_rho, nn * 8))) return rc;
+  if ((rc = ensure_pin(g.pin_a, nn * 24))) return rc;
+  cudaStream_t st = g.stream;
+  double* h_vs = (double*)g.pin_a.p;
+  double* h_vp = h_vs + nn;
+  double* h_rho = h_vp + nn;
+  const size_t ny = gr->ny, nz = gr->nz;
+  for (int i = 0; i < wx; ++i)
+    for (int j = 0; j < wy; ++j)
+      memcpy(h_vs + ((size_t)i * wy + j) * wz, vs + ((size_t)(w[0] - 1 + i) * ny + (size_t)(w[2] - 1 + j)) * nz + (size_t)(w[4] - 1),
+             (size_t)wz * 8);
+  CK(cudaMemcpyAsync(g.m_vs.p, h_vs, nn * 8, cudaMemcpyHostToDevice, st));
+  if ((rc = mct_vs2vp_rho_dev((double*)g.m_vs.p, (double*)g.m_vp.p, (double*)g.m_rho.p, (int64_t)nn, st))) return rc;
+  CK(cudaMemcpyAsync(h_vp, g.m_vp.p, nn * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_rho, g.m_rho.p, nn * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < wx; ++i)
+    for (int j = 0; j < wy; ++j) {
+      const size_t uo = ((size_t)(w[0] - 1 + i) * ny + (size_t)(w[2] - 1 + j)) * nz + (size_t)(w[4] - 1);
+      const size_t po = ((size_t)i * wy + j) * wz;
+      memcpy(vp + uo, h_vp + po, (size_t)wz * 8);
+      memcpy(rho + uo, h_rho + po, (size_t)wz * 8);
+    }
+  return MCT_OK;
+}
+
 int mct_surf_dispersion_dev(const double* d_vp, const double* d_vs, const double* d_rho, const mct_grid* gr, int ix0, int ix1,
                             int iy0, int iy1, const double* freqs, int np, const mct_disp_opts* opt, double* d_pvel,
                             double* d_gvel, int32_t* d_ierr, int32_t* d_flags, void* stream) {
@@ -670,7 +708,8 @@ int mct_surf_dispersion_dev(const double* d_vp, const double* d_vs, const double
   if (rc) return rc;
   const bool chk = d_flags != nullptr;
   int32_t* fl = d_flags ? d_flags : (int32_t*)g.flags.p;
-  return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, chk, 0, (long long)gr->nx * gr->ny, d_pvel, d_gvel, d_ierr, fl,
+  const int whole[4] = {1, 1, gr->nx, gr->ny}, win[4] = {pl.ix0, pl.iy0, pl.wx, pl.wy};
+  return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, chk, opt->check_scope == 1 ? win : whole, d_pvel, d_gvel, d_ierr, fl,
                    pick(stream));
 }
 
@@ -691,17 +730,21 @@ int mct_surf_dispersion(const double* vp, const double* vs, const double* rho, c
   if ((rc = ensure(g.o_pvel, nbo))) return rc;
   if ((rc = ensure(g.o_gvel, nbo))) return rc;
   if ((rc = ensure(g.o_ierr, (size_t)pl.ncol * 4))) return rc;
-  // vs: whole grid when check_model is requested (it scans every column), else the window's x-range;
-  // vp, rho: the window's x-range only (each x index is one contiguous (nz,ny) slab).
+  // Only the columns the kernels will read are sent: the window's columns (for each x index of the window the
+  // wy columns are one contiguous run of wy*nz values: a 2-D copy with the (ny*nz) slab as pitch) -- plus, when
+  // check_model runs with the reference's whole-grid scope, all of vs.
   const size_t slab = (size_t)gr->ny * gr->nz;
-  const size_t xoff = (size_t)(pl.ix0 - 1) * slab, xlen = (size_t)pl.wx * slab;
-  if (model_invalid) CK(cudaMemcpyAsync(g.m_vs.p, vs, ncell * 8, cudaMemcpyHostToDevice, st));
-  else CK(cudaMemcpyAsync((double*)g.m_vs.p + xoff, vs + xoff, xlen * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync((double*)g.m_vp.p + xoff, vp + xoff, xlen * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync((double*)g.m_rho.p + xoff, rho + xoff, xlen * 8, cudaMemcpyHostToDevice, st));
+  const size_t woff = (size_t)(pl.ix0 - 1) * slab + (size_t)(pl.iy0 - 1) * gr->nz;
+  const size_t wrow = (size_t)pl.wy * gr->nz * 8;
+  const bool whole_check = model_invalid != nullptr && opt->check_scope != 1;
+  if (whole_check) CK(cudaMemcpyAsync(g.m_vs.p, vs, ncell * 8, cudaMemcpyHostToDevice, st));
+  else CK(cudaMemcpy2DAsync((double*)g.m_vs.p + woff, slab * 8, vs + woff, slab * 8, wrow, (size_t)pl.wx, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpy2DAsync((double*)g.m_vp.p + woff, slab * 8, vp + woff, slab * 8, wrow, (size_t)pl.wx, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpy2DAsync((double*)g.m_rho.p + woff, slab * 8, rho + woff, slab * 8, wrow, (size_t)pl.wx, cudaMemcpyHostToDevice, st));
   int32_t* fl = (int32_t*)g.flags.p;
-  rc = disp_core((double*)g.m_vp.p, (double*)g.m_vs.p, (double*)g.m_rho.p, gr, pl, freqs, np, opt, model_invalid != nullptr, 0,
-                 (long long)gr->nx * gr->ny, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, fl, st);
+  const int whole[4] = {1, 1, gr->nx, gr->ny}, win[4] = {pl.ix0, pl.iy0, pl.wx, pl.wy};
+  rc = disp_core((double*)g.m_vp.p, (double*)g.m_vs.p, (double*)g.m_rho.p, gr, pl, freqs, np, opt, model_invalid != nullptr,
+                 whole_check ? whole : win, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, fl, st);
   if (rc) return rc;
   int32_t hflags[2] = {0, 0};
   CK(cudaMemcpyAsync(hflags, fl, sizeof hflags, cudaMemcpyDeviceToHost, st));

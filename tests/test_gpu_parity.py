@@ -421,3 +421,31 @@ def test_fuzz_random_layer_stacks(mct, seed, raylov, pg, nm):
             seen[e0] += 1
         assert seen[0] + seen[1] > 1000 and seen[0] > 100 and seen[2] > 20
     mct.set_k2_mode(0)
+
+
+def test_windowed_maps_and_window_scoped_check(mct):
+    """mct_vs2vp_rho_window touches only the window; check_scope = 1 looks only at the window's columns."""
+    grid = synth.make_grid(14, 12, 20)
+    vp, vs, rho = _model(grid, 50, 90)
+    vp2 = np.full(grid.shape, -1.0)
+    rho2 = np.full(grid.shape, -1.0)
+    w = (3, 9, 2, 7, 4, 15)
+    mct.vs2vp_rho_window(vs, vp2, rho2, grid, w)
+    inside = np.zeros(grid.shape, bool)
+    inside[w[0] - 1:w[1], w[2] - 1:w[3], w[4] - 1:w[5]] = True
+    assert np.array_equal(vp2[inside], vp[inside]) and np.array_equal(rho2[inside], rho[inside])
+    assert (vp2[~inside] == -1).all() and (rho2[~inside] == -1).all()
+    # an invalid column OUTSIDE the window: scope 0 (reference) rejects, scope 1 does not and solves the window
+    bad = vs.copy()
+    bad[12, 10, 8] = 0.5 * bad[12, 10, 0]
+    freqs = synth.freqs(6)
+    win = (3, 9, 2, 7)
+    r0 = mct.surf_dispersion(vp, bad, rho, grid, win, freqs, disp_opts(check_scope=0))
+    r1 = mct.surf_dispersion(vp, bad, rho, grid, win, freqs, disp_opts(check_scope=1))
+    assert r0[3] == 1 and r1[3] == 0
+    po, go, io, cnt, nun = orc.surf_dispersion(vp, bad, rho, grid, win, freqs)
+    assert np.array_equal(r1[0], po) and np.array_equal(r1[2], io)
+    # ... and an invalid column INSIDE the window is caught by both
+    bad2 = vs.copy()
+    bad2[4, 4, 8] = 0.5 * bad2[4, 4, 0]
+    assert mct.surf_dispersion(vp, bad2, rho, grid, win, freqs, disp_opts(check_scope=1))[3] == 1
