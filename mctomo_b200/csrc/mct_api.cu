@@ -59,7 +59,8 @@ struct Ctx {
   int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
   int k2_coop_max = 16384;  // auto: batches up to this many columns take the warp-cooperative kernel
-  int k2_variant = 7; // launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
+  int sort_stable = 1;      // stable counting sort of the columns (MCT_SORT_STABLE=0: atomic-cursor sort)
+  int k2_variant = 7; // 7 production, 3 plain secular functions (A/B reference), 0 plain + unsorted: launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
   // outputs (host-pointer entry points)
   DevBuf o_pvel, o_gvel, o_ierr;
   // prelayered staging
@@ -351,13 +352,21 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   if (variant != 0) {
     int rc;
     if ((rc = ensure(g.perm, sizeof(int32_t) * (size_t)stride))) return rc;
-    if ((rc = ensure(g.bins, sizeof(int32_t) * 256))) return rc;
-    CK(cudaMemsetAsync(g.bins.p, 0, sizeof(int32_t) * 256, st));
-    ProfScope ps(2, st);
     const int nb256 = (ncol + 255) / 256;
-    sort_hist_kernel<<<nb256, 256, 0, st>>>(P.nlay, ncol, (int32_t*)g.bins.p);
-    sort_scan_kernel<<<1, 32, 0, st>>>((int32_t*)g.bins.p);
-    sort_scatter_kernel<<<nb256, 256, 0, st>>>(P.nlay, ncol, (int32_t*)g.bins.p, (int32_t*)g.perm.p);
+    if ((rc = ensure(g.bins, sizeof(int32_t) * 256 * ((size_t)nb256 + 1)))) return rc;
+    ProfScope ps(2, st);
+    if (g.sort_stable) { // deterministic, keeps spatial neighbours together inside a bin
+      int32_t* bin_base = (int32_t*)g.bins.p;
+      int32_t* blk = bin_base + 256;
+      ssort_hist_kernel<<<nb256, SORT_BLOCK, 0, st>>>(P.nlay, ncol, blk);
+      ssort_offsets_kernel<<<1, 256, 0, st>>>(blk, nb256, bin_base);
+      ssort_scatter_kernel<<<nb256, SORT_BLOCK, 0, st>>>(P.nlay, ncol, blk, bin_base, (int32_t*)g.perm.p);
+    } else {
+      CK(cudaMemsetAsync(g.bins.p, 0, sizeof(int32_t) * 256, st));
+      sort_hist_kernel<<<nb256, 256, 0, st>>>(P.nlay, ncol, (int32_t*)g.bins.p);
+      sort_scan_kernel<<<1, 32, 0, st>>>((int32_t*)g.bins.p);
+      sort_scatter_kernel<<<nb256, 256, 0, st>>>(P.nlay, ncol, (int32_t*)g.bins.p, (int32_t*)g.perm.p);
+    }
     g.host_stats.n_launches += 3;
     P.perm = (const int32_t*)g.perm.p;
   }
@@ -503,6 +512,7 @@ int mct_init(int device) {
   CK(cudaMemset(g.counters.p, 0, 4 * sizeof(unsigned long long)));
   g.host_stats = mct_stats{0, 0, 0, 0, 0};
   if (const char* v = getenv("MCT_K2_VARIANT")) g.k2_variant = atoi(v);
+  if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
   g.init = true;
   return MCT_OK;
 }
