@@ -206,6 +206,13 @@ int mct_forward_eval_batch(const double* points, const double* params, const int
 int mct_set_profiling(int on);
 int mct_kernel_times(double ms[4], int reset);
 int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add);
+/* Posterior accumulation of `program sample` (src/sample.f90:481-487), on the device: after a full-grid
+ * mct_voronoi_to_grid_dev of a kept sample, aveS += vs, stdS += vs**2, aveP += vp, stdP += vp**2 elementwise
+ * over n = nx*ny*nz values (same operations, same order: bit-identical sums).  Keeps the thousands of regrids
+ * the post-processor issues resident in HBM; only the four accumulators are read back at the end. */
+int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_aveS, double* d_stdS, double* d_aveP,
+                             double* d_stdP, int64_t n, void* stream);
+
 /* Shape of the nearest-nucleus kernel.  mode 0 (default): one warp per grid column, brute force over the
  * nuclei that survive a conservative per-column cull, kdtree2's traversal replayed only for (near-)tied
  * nodes.  mode 1: kdtree2's traversal for every node.  Results are identical either way. */

@@ -331,6 +331,13 @@ def voronoi_to_grid_dev(points, params, grid: Grid, box, d_vp, d_vs, d_rho, d_si
                                                 box.ctypes.data, _ptr(pmv), d_vp, d_vs, d_rho, d_sites, stream))
 
 
+def accumulate_stats_dev(d_vs, d_vp, d_aveS, d_stdS, d_aveP, d_stdP, n, stream):
+    """aveS += vs, stdS += vs**2, aveP += vp, stdP += vp**2 on the device (reference src/sample.f90:483-486)."""
+    L = lib()
+    L.mct_accumulate_stats_dev.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+    return _check(L.mct_accumulate_stats_dev(d_vs, d_vp, d_aveS, d_stdS, d_aveP, d_stdP, n, stream))
+
+
 def assemble_vel_dev(d_pvel, np_, nx, ny, window, d_vel, stream):
     ix0, ix1, iy0, iy1 = (int(v) for v in window)
     return _check(lib().mct_assemble_vel_dev(d_pvel, np_, nx, ny, ix0, ix1, iy0, iy1, d_vel, stream))

@@ -167,6 +167,21 @@ __global__ void __launch_bounds__(256) vs2vp_rho_kernel(const double* __restrict
   }
 }
 
+// Posterior accumulation of the post-processor (src/sample.f90:483-486): aveS += vs, stdS += vs**2, aveP += vp,
+// stdP += vp**2, elementwise over the grid, after every kept sample's full-grid regrid.  Kept on the device so
+// the thousands of regrids `program sample` issues never leave HBM.
+__global__ void __launch_bounds__(256) accumulate_stats_kernel(const double* __restrict__ vs, const double* __restrict__ vp,
+                                                               double* __restrict__ aveS, double* __restrict__ stdS,
+                                                               double* __restrict__ aveP, double* __restrict__ stdP, long long n) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const double s = vs[t], p = vp[t];
+    aveS[t] = aveS[t] + s;
+    stdS[t] = stdS[t] + s * s;
+    aveP[t] = aveP[t] + p;
+    stdP[t] = stdP[t] + p * p;
+  }
+}
+
 // check_model (src/likelihood_surf.F90:631-646) over the columns ix0..ix0+wx-1, iy0..iy0+wy-1 (1-based; the reference
 // scans the whole grid = 1..nx, 1..ny): flag |= any(vs(2:,j,i) < vs(1,j,i)).  One warp per column, lanes strided over z
 // (coalesced).  Batched form: model b = c / (wx*wy) reads its columns at vs + b*model_stride and raises flag[2*b].

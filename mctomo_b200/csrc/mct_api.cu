@@ -987,6 +987,17 @@ int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add) {
   return MCT_OK;
 }
 
+int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_aveS, double* d_stdS, double* d_aveP,
+                             double* d_stdP, int64_t n, void* stream) {
+  NEED_INIT();
+  if (!d_vs || !d_vp || !d_aveS || !d_stdS || !d_aveP || !d_stdP || n < 0) return fail(MCT_E_INVALID_ARG, "accumulate_stats: bad arguments");
+  if (n == 0) return MCT_OK;
+  accumulate_stats_kernel<<<grid_blocks(n, 256, 8), 256, 0, pick(stream)>>>(d_vs, d_vp, d_aveS, d_stdS, d_aveP, d_stdP, (long long)n);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+
 int mct_set_k1_mode(int mode) {
   if (mode < 0 || mode > 1) return fail(MCT_E_INVALID_ARG, "set_k1_mode: mode must be 0 (culled brute force) or 1 (tree walk)");
   g.k1_mode = mode;
