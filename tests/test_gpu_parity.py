@@ -449,3 +449,31 @@ def test_windowed_maps_and_window_scoped_check(mct):
     bad2 = vs.copy()
     bad2[4, 4, 8] = 0.5 * bad2[4, 4, 0]
     assert mct.surf_dispersion(vp, bad2, rho, grid, win, freqs, disp_opts(check_scope=1))[3] == 1
+
+
+def test_sample_postprocessor_accumulation(mct):
+    """program sample's loop (src/sample.f90:481-487): regrid every kept sample over the full grid and accumulate
+    sum(vs), sum(vs^2), sum(vp), sum(vp^2) -- here entirely on the device; compared with the oracle's regrids
+    accumulated by numpy in the same order (bit-identical sums)."""
+    import torch
+    grid = synth.make_grid(22, 19, 25)
+    n = grid.nx * grid.ny * grid.nz
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream()
+    d = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(3)] + [torch.zeros(n, dtype=torch.int32, device=dev)]
+    acc = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(4)]
+    ref = [np.zeros(grid.shape) for _ in range(4)]
+    for k in range(7):
+        pts, par = synth.generate_model(grid, 30 + 11 * k, 300 + k)
+        with torch.cuda.stream(st):
+            mct.voronoi_to_grid_dev(pts, par, grid, grid.cover_box(), *[t.data_ptr() for t in d], st.cuda_stream)
+            mct.accumulate_stats_dev(d[1].data_ptr(), d[0].data_ptr(), *[t.data_ptr() for t in acc], n, st.cuda_stream)
+        vp, vs, rho, sid = _empty_model(grid)
+        orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
+        ref[0] = ref[0] + vs
+        ref[1] = ref[1] + vs * vs
+        ref[2] = ref[2] + vp
+        ref[3] = ref[3] + vp * vp
+    st.synchronize()
+    for a, r in zip(acc, ref):
+        assert np.array_equal(a.cpu().numpy().reshape(grid.shape), r)
