@@ -378,7 +378,9 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
     const bool coop = (g.k2_mode == 2) || (g.k2_mode == 0 && ncol <= g.k2_coop_max);
     if (coop) k2_coop_kernel<<<ncol, 32, 0, st>>>(P);
     else if (variant == 3 || variant == 0) k2_dispersion_plain<<<nw, 32, 0, st>>>(P); // A/B reference (0: unsorted too)
-    else k2_dispersion_fast_r128<<<nw, 32, 0, st>>>(P);
+    else {
+      k2_dispersion_fast_r128<<<nw, 32, 0, st>>>(P);
+    }
   }
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
@@ -512,8 +514,7 @@ int mct_init(int device) {
   CK(cudaMemset(g.counters.p, 0, 4 * sizeof(unsigned long long)));
   g.host_stats = mct_stats{0, 0, 0, 0, 0};
   if (const char* v = getenv("MCT_K2_VARIANT")) g.k2_variant = atoi(v);
-  if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
-  g.init = true;
+  if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);  g.init = true;
   return MCT_OK;
 }
 
