@@ -1,4 +1,4 @@
-"""K1 timing: tree walk per node vs culled brute force per column (device-resident, one model)."""
+"""tools/k1_bench.py -- K1 timing: tree walk per node vs culled brute force per column (device-resident, one model)."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, '.')

@@ -1,4 +1,4 @@
-"""Latency of a proposal-sized dispersion call: thread-per-column vs warp-per-column K2 (device-resident inputs)."""
+"""tools/latency_bench.py -- latency of a proposal-sized dispersion call: thread-per-column vs warp-per-column K2 (device-resident inputs)."""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
