@@ -406,6 +406,8 @@ def main():
                "scaling": "strong" if column_sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "forward_evals_per_sec": batch * world * args.steps / (total_ms * 1e-3) if not column_sharded else args.steps / (total_ms * 1e-3),
                "waves": "Rayleigh + Love" if love else "Rayleigh",
+               # one solve = one (column, period, wave, mode) output; a group-velocity output costs two root searches
+               "getsol_calls_per_sec": value * (2 if spec["phaseGroup"] else 1),
                "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
                                       f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={nm}, "
                                       f"{len(models[0][0])} nuclei",
