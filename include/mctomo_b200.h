@@ -217,11 +217,14 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
  * nuclei that survive a conservative per-column cull, kdtree2's traversal replayed only for (near-)tied
  * nodes.  mode 1: kdtree2's traversal for every node.  Results are identical either way. */
 int mct_set_k1_mode(int mode);
-/* Shape of the dispersion kernel.  mode 0 (default): batches of up to coop_max_columns columns (default
- * 16384; pass -1 to keep) run one WARP per column -- the lanes split getsol's bracketing scan, which cuts
- * the latency of a proposal-sized call by an order of magnitude -- larger batches run one THREAD per
- * column (highest throughput).  mode 1 / 2 force one or the other.  Results are identical either way. */
+/* Shape of the dispersion kernel.  mode 0 (default): batches of fewer than coop_max_columns columns (default 0 =
+ * the GPU's resident-lane capacity, 75 776 on a B200; pass -1 to keep) give every column a GROUP OF G LANES that
+ * split getsol's bracketing scan -- G = 32 (a whole warp: an order of magnitude lower latency for a
+ * proposal-sized call) down to 2, the smallest power of two that still fills the GPU -- larger batches run one
+ * THREAD per column (highest throughput).  mode 1 / 2 force one or the other; mct_set_k2_lanes fixes G
+ * (0 = automatic).  Results are identical in every shape. */
 int mct_set_k2_mode(int mode, int coop_max_columns);
+int mct_set_k2_lanes(int lanes_per_column);
 /* Device self-test: the shared-reciprocal division the dispersion kernel uses is compared, bit for
  * bit, with the compiler's IEEE division on *tested random operand pairs whose exponents are drawn
  * from [-emax, emax]; *mismatches must come back 0. */

@@ -452,6 +452,13 @@ def set_k2_mode(mode: int = 0, coop_max_columns: int = -1):
     _check(L.mct_set_k2_mode(mode, coop_max_columns))
 
 
+def set_k2_lanes(lanes_per_column: int = 0):
+    """Lanes per column of the cooperative dispersion kernel: 0 automatic, else 2, 4, 8, 16 or 32."""
+    L = _bind_batch()
+    L.mct_set_k2_lanes.argtypes = [C.c_int]
+    _check(L.mct_set_k2_lanes(lanes_per_column))
+
+
 def selftest_division(emax: int = 300):
     """(tested, mismatches) of the shared-reciprocal division against IEEE `/` on the device."""
     L = _bind_batch()

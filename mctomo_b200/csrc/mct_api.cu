@@ -58,7 +58,9 @@ struct Ctx {
   DevBuf lay, layr, nlay, status, perm, bins;
   int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
-  int k2_coop_max = 16384;  // auto: batches up to this many columns take the warp-cooperative kernel
+  int k2_coop_max = 0;      // auto mode: batches below this many columns take the lane-cooperative kernels
+                            // (0 = the resident-lane capacity of the GPU, 75 776 on a B200)
+  int k2_coop_lanes = 0;    // lanes per column of the cooperative kernel: 0 = choose per launch (MCT_K2_COOP_LANES)
   int sort_stable = 1;      // stable counting sort of the columns (MCT_SORT_STABLE=0: atomic-cursor sort)
   int k2_variant = 7; // 7 production, 3 plain secular functions (A/B reference), 0 plain + unsorted: launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
   // outputs (host-pointer entry points)
@@ -374,9 +376,24 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   {
     ProfScope ps(1, st);
     const int nw = (ncol + 31) / 32;
-    // Proposal-sized batches cannot fill the GPU with one thread per column: give each column a warp.
-    const bool coop = (g.k2_mode == 2) || (g.k2_mode == 0 && ncol <= g.k2_coop_max);
-    if (coop) k2_coop_kernel<<<ncol, 32, 0, st>>>(P);
+    // Batches that cannot fill the GPU with one thread per column get G lanes per column: the smallest power of
+    // two that still (nearly) fills the resident-lane capacity, up to a whole warp (proposal-sized batches).
+    const long long capacity = (long long)g.sm_count * 16 * 32; // resident lanes of the dispersion kernels
+    const int coop_max = g.k2_coop_max > 0 ? g.k2_coop_max : (int)std::min<long long>(capacity, 1 << 30);
+    const bool coop = (g.k2_mode == 2) || (g.k2_mode == 0 && ncol < coop_max);
+    if (coop) {
+      int G = 32;
+      if (g.k2_coop_lanes > 0) G = g.k2_coop_lanes;
+      else while (G > 2 && (long long)ncol * (G / 2) * 5 >= capacity * 4) G /= 2; // halve while 80 % of capacity stays filled
+      const int nblk = (ncol + (32 / G) - 1) / (32 / G);
+      switch (G) {
+        case 2: k2_coop2_kernel<<<nblk, 32, 0, st>>>(P); break;
+        case 4: k2_coop4_kernel<<<nblk, 32, 0, st>>>(P); break;
+        case 8: k2_coop8_kernel<<<nblk, 32, 0, st>>>(P); break;
+        case 16: k2_coop16_kernel<<<nblk, 32, 0, st>>>(P); break;
+        default: k2_coop_kernel<<<nblk, 32, 0, st>>>(P); break;
+      }
+    }
     else if (variant == 3 || variant == 0) k2_dispersion_plain<<<nw, 32, 0, st>>>(P); // A/B reference (0: unsorted too)
     else {
       k2_dispersion_fast_r128<<<nw, 32, 0, st>>>(P);
@@ -514,7 +531,8 @@ int mct_init(int device) {
   CK(cudaMemset(g.counters.p, 0, 4 * sizeof(unsigned long long)));
   g.host_stats = mct_stats{0, 0, 0, 0, 0};
   if (const char* v = getenv("MCT_K2_VARIANT")) g.k2_variant = atoi(v);
-  if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);  g.init = true;
+  if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
+  if (const char* v = getenv("MCT_K2_COOP_LANES")) g.k2_coop_lanes = atoi(v);  g.init = true;
   return MCT_OK;
 }
 
@@ -1009,6 +1027,14 @@ int mct_set_k2_mode(int mode, int coop_max_columns) {
   if (mode < 0 || mode > 2) return fail(MCT_E_INVALID_ARG, "set_k2_mode: mode must be 0 (auto), 1 (thread per column) or 2 (warp per column)");
   g.k2_mode = mode;
   if (coop_max_columns >= 0) g.k2_coop_max = coop_max_columns;
+  return MCT_OK;
+}
+
+int mct_set_k2_lanes(int lanes_per_column) {
+  if (lanes_per_column != 0 && lanes_per_column != 2 && lanes_per_column != 4 && lanes_per_column != 8 && lanes_per_column != 16 &&
+      lanes_per_column != 32)
+    return fail(MCT_E_INVALID_ARG, "set_k2_lanes: lanes per column must be 0 (auto), 2, 4, 8, 16 or 32");
+  g.k2_coop_lanes = lanes_per_column;
   return MCT_OK;
 }
 

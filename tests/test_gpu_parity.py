@@ -126,14 +126,17 @@ def _check_disp(mct, grid, vp, vs, rho, window, freqs, raylov, pg, nmodes, varia
     the two must agree bit for bit with each other and with the oracle, counters included."""
     opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nmodes, variant=variant)
     res = []
-    for mode in (1, 2):
+    for mode, lanes in ((1, 0), (2, 32), (2, 16), (2, 8), (2, 4), (2, 2)):
         mct.set_k2_mode(mode)
+        mct.set_k2_lanes(lanes)
         mct.reset_stats()
         res.append(mct.surf_dispersion(vp, vs, rho, grid, window, freqs, opts) + (mct.stats(),))
     mct.set_k2_mode(0)
-    for a, b in zip(res[0][:3], res[1][:3]):
-        assert np.array_equal(a, b), "thread-per-column and warp-per-column kernels disagree"
-    assert res[0][5]["n_dltar"] == res[1][5]["n_dltar"] and res[0][5]["n_layer_steps"] == res[1][5]["n_layer_steps"]
+    mct.set_k2_lanes(0)
+    for r in res[1:]:
+        for a, b in zip(res[0][:3], r[:3]):
+            assert np.array_equal(a, b), "thread-per-column and lane-cooperative kernels disagree"
+        assert res[0][5]["n_dltar"] == r[5]["n_dltar"] and res[0][5]["n_layer_steps"] == r[5]["n_layer_steps"]
     pv, gv, ie, inval, rc, st = res[1]
     kw = dict(raylov=raylov, phaseGroup=pg, nmodes=nmodes, layer_eps=opts.layer_eps, water_thresh=opts.water_thresh,
               preset=opts.preset)
@@ -405,8 +408,9 @@ def test_fuzz_random_layer_stacks(mct, seed, raylov, pg, nm):
     periods = np.sort(rng.choice(np.geomspace(0.1, 80.0, 40), 14, replace=False))
     freqs = 1.0 / periods
     opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nm)
-    for mode in (1, 2):
+    for mode, lanes in ((1, 0), (2, 32), (2, 8), (2, 2)):
         mct.set_k2_mode(mode)
+        mct.set_k2_lanes(lanes)
         ph, gr, ie, rc = mct.surfmodes_batch(a[:, 0], a[:, 1], a[:, 2], a[:, 3], offs, freqs, opts)
         seen = {0: 0, 1: 0, 2: 0}
         for c in range(ncol):
@@ -421,6 +425,7 @@ def test_fuzz_random_layer_stacks(mct, seed, raylov, pg, nm):
             seen[e0] += 1
         assert seen[0] + seen[1] > 1000 and seen[0] > 100 and seen[2] > 20
     mct.set_k2_mode(0)
+    mct.set_k2_lanes(0)
 
 
 def test_windowed_maps_and_window_scoped_check(mct):

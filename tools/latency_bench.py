@@ -22,7 +22,7 @@ for (wx, wy) in [(4, 4), (10, 10), (20, 20), (32, 32), (64, 64), (grid.nx, grid.
     wx = min(wx, grid.nx); wy = min(wy, grid.ny)
     win = (1, wx, 1, wy)
     out = []
-    for mode in (1, 2):
+    for mode in (1, 0):   # 1 = one thread per column, 0 = automatic (lane-cooperative below the GPU's capacity)
         capi.set_k2_mode(mode)
         for _ in range(2):
             capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, win, freqs, opts, d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), s)
@@ -33,8 +33,12 @@ for (wx, wy) in [(4, 4), (10, 10), (20, 20), (32, 32), (64, 64), (grid.nx, grid.
             capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, win, freqs, opts, d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), s)
         b.record(); torch.cuda.synchronize()
         out.append(a.elapsed_time(b) / 3)
+        capi.set_profiling(True); capi.kernel_times(reset=True)
+        capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, win, freqs, opts, d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), s)
+        kt = capi.kernel_times(reset=True); capi.set_profiling(False)
+        brk = f"[K2 {kt['k2_ms']:.2f} ms, other kernels {kt['other_ms']:.2f} ms]"
         res = d_pv[: wx * wy * nout].clone()
         if mode == 1: r1 = res
     same = bool(torch.equal(r1, res))
-    print(f"{wx*wy:6d} columns: thread/col {out[0]:8.2f} ms   warp/col {out[1]:8.2f} ms   speedup {out[0]/out[1]:5.2f}x  identical={same}")
+    print(f"{wx*wy:6d} columns: thread/col {out[0]:8.2f} ms   auto (G lanes/col) {out[1]:8.2f} ms   speedup {out[0]/out[1]:5.2f}x  identical={same}  auto: {brk}")
 capi.set_k2_mode(0)
