@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmctomo_b200.so")
+LIB_PATH = os.environ.get("MCT_LIB", os.path.join(_HERE, "libmctomo_b200.so"))  # MCT_LIB: A/B against another build
 
 MCT_OK = 0
 MCT_E_INVALID_ARG = 1
