@@ -39,7 +39,7 @@ __device__ __forceinline__ bool love_step_fast(const float4 L, const double4 Rc,
   const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
   const double q = dm * rb;
   const double y_rb = mct_rcp(rb);
-  R.add(b); R.add(xmu); R.add(rb); // rb = 0 (wvno == xkb, the reference's equality branch) -> exact path
+  R.add(rb); // b, xmu: checked by layer_recips_kernel (NaN-poisoned y_b reaches rb);  rb = 0 (wvno == xkb, the reference's equality branch) -> exact path
   double cosq, sinq, z;
   if (wvno < xkb) {
     mct_sincos(q, &sinq, &cosq);
@@ -61,7 +61,7 @@ __device__ __forceinline__ bool love_step_fast(const float4 L, const double4 Rc,
   double xnor = fmax(fabs(e10), fabs(e20));
   if (xnor < 1.e-40) xnor = 1.0;
   const double y_n = mct_rcp(xnor);
-  R.add(xnor); R.add(e10); R.add(e20);
+  R.add(e10); R.add(e20); // xnor is one of them (or 1.0)
   if (!R.ok()) return false;
   E.e1 = mct_div_r(e10, xnor, y_n);
   E.e2 = mct_div_r(e20, xnor, y_n);

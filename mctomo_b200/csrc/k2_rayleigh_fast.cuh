@@ -105,7 +105,8 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc
   const double a = (double)L.y, b = (double)L.z, dpth = (double)L.x, rho = (double)L.w;
   const double rho2 = rho * rho;
   const double y_a = Rc.x, y_b = Rc.y, y_rho = Rc.z, y_rho2 = Rc.w;
-  R.add(a); R.add(b); R.add(rho); R.add(rho2);
+  // (a, b, rho, rho2 are range-checked once per layer by layer_recips_kernel: an out-of-range constant poisons
+  //  y_a with NaN, which reaches ra below and sends the step to the exact path)
   const double xka = mct_div_r(omega, a, y_a);
   const double xkb = mct_div_r(omega, b, y_b);
   const double t = mct_div_r(b, omega, y_om);
@@ -216,7 +217,7 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc
   double t1 = fmax(fmax(fmax(fabs(ee1), fabs(ee2)), fmax(fabs(ee3), fabs(ee4))), fabs(ee5));
   if (t1 < 1.e-40) t1 = 1.0;
   const double y_t1 = mct_rcp(t1);
-  R.add(t1); R.add(ee1); R.add(ee2); R.add(ee3); R.add(ee4); R.add(ee5);
+  /* t1 is one of the |ee| (or 1.0) */ R.add(ee1); R.add(ee2); R.add(ee3); R.add(ee4); R.add(ee5);
   if (!R.ok()) return false;
   E.e1 = mct_div_r(ee1, t1, y_t1);
   E.e2 = mct_div_r(ee2, t1, y_t1);

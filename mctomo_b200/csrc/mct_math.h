@@ -47,7 +47,10 @@
     /* 19.. 1/n!, n = 2..13 */ 0.5, 0x1.5555555555555p-3, 0x1.5555555555555p-5,               \
     0x1.1111111111111p-7, 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-16, \
     0x1.71de3a556c734p-19, 0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26,                      \
-    0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33                                              \
+    0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33,                                             \
+    /* 31 64/ln2 */ 0x1.71547652b82fep+6,                                                     \
+    /* 32 ln2/64 hi (28 trailing zero bits: n*HI is exact) */ 0x1.62e42f0000000p-7,           \
+    /* 33 ln2/64 lo */ 0x1.df473de6af279p-32                                                  \
   }
 #define MCT_K_S(i) MCT_K((i) - 1)        /* S1..S6 */
 #define MCT_K_C(i) MCT_K(6 + (i) - 1)    /* C1..C6 */
@@ -61,15 +64,15 @@
 #define MCT_K_F(n) MCT_K(19 + (n) - 2)   /* 1/n!, n = 2..13 */
 
 #if defined(__CUDACC__)
-__constant__ double mct_ktab_dev[31] = MCT_KTAB_INIT;
-static const double mct_ktab_host[31] = MCT_KTAB_INIT;
+__constant__ double mct_ktab_dev[34] = MCT_KTAB_INIT;
+static const double mct_ktab_host[34] = MCT_KTAB_INIT;
 #if defined(__CUDA_ARCH__)
 #define MCT_K(i) mct_ktab_dev[i]
 #else
 #define MCT_K(i) mct_ktab_host[i]
 #endif
 #else
-static const double mct_ktab_host[31] = MCT_KTAB_INIT;
+static const double mct_ktab_host[34] = MCT_KTAB_INIT;
 #define MCT_K(i) mct_ktab_host[i]
 #endif
 
@@ -182,10 +185,19 @@ MCT_HD void mct_sincos(double x, double* sn, double* cs) {
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0       \
   }
 #if defined(__CUDACC__)
-__device__ const double mct_exptab_dev[64] = MCT_EXPTAB_INIT; /* global memory: lanes index it independently (L1) */
+/* Lanes index the table independently, so it cannot live in the constant bank (a divergent LDC serialises).
+ * It is staged in shared memory: one LDS per lookup, against an LDG plus 64-bit address arithmetic plus two
+ * R2UR descriptor moves from global memory (profiles/: 12 of ~230 non-FP64 instructions per layer step).
+ * Every kernel that evaluates mct_exp* must call mct_exptab_stage() first. */
+__device__ const double mct_exptab_dev[64] = MCT_EXPTAB_INIT;
+__shared__ double mct_exptab_s[64];
 static const double mct_exptab_host[64] = MCT_EXPTAB_INIT;
+__device__ __forceinline__ void mct_exptab_stage() {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) mct_exptab_s[i] = mct_exptab_dev[i];
+  __syncthreads();
+}
 #if defined(__CUDA_ARCH__)
-#define MCT_EXPTAB(j) __ldg(&mct_exptab_dev[j])
+#define MCT_EXPTAB(j) mct_exptab_s[j]
 #else
 #define MCT_EXPTAB(j) mct_exptab_host[j]
 #endif
@@ -198,9 +210,7 @@ static const double mct_exptab_host[64] = MCT_EXPTAB_INIT;
  * exp(x) = 2^k * 2^(j/64) * (1 + expm1(r)), expm1 by a degree-6 Taylor polynomial (truncation 3e-20).
  * 11 FP64 operations and one table load; half the length of a table-free polynomial. */
 MCT_HD double mct_exp_core(double x) {
-  const double INV = 0x1.71547652b82fep+6;  /* 64/ln2 */
-  const double HI = 0x1.62e42f0000000p-7;   /* ln2/64, 28 trailing zero bits: n*HI is exact */
-  const double LO = 0x1.df473de6af279p-32;
+  const double INV = MCT_K(31), HI = MCT_K(32), LO = MCT_K(33); /* 64/ln2; ln2/64 split */
   const double t = MCT_FMA(x, INV, MCT_MAGIC);
   const int32_t n = (int32_t)(uint32_t)mct_d2bits(t);
   const double nf = MCT_ADD(t, -MCT_MAGIC);
