@@ -58,6 +58,7 @@ struct Ctx {
   DevBuf lay, layr, nlay, status, perm, bins;
   int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
+  int k2_warps_per_smsp_x4 = 16; // multi-warp columns are used while the launch stays within this many warps per SM sub-partition (in quarters): 4 warps = full residency (lanes sweep, tools/lanes_sweep.py)
   int k2_coop_max = 0;      // auto mode: batches below this many columns take the lane-cooperative kernels
                             // (0 = the resident-lane capacity of the GPU, 75 776 on a B200)
   int k2_coop_lanes = 0;    // lanes per column of the cooperative kernel: 0 = choose per launch (MCT_K2_COOP_LANES)
@@ -385,8 +386,16 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
       int G = 32;
       if (g.k2_coop_lanes > 0) G = g.k2_coop_lanes;
       else while (G > 2 && (long long)ncol * (G / 2) * 5 >= capacity * 4) G /= 2; // halve while 80 % of capacity stays filled
-      const int nblk = (ncol + (32 / G) - 1) / (32 / G);
+      // The smallest batches get several warps per column (one block per column, its warps on different SM
+      // sub-partitions): as many as keep the total at or below g.k2_warps_per_smsp warps per sub-partition.
+      if (g.k2_coop_lanes == 0 && G == 32) {
+        const long long slots = (long long)g.sm_count * 4 * g.k2_warps_per_smsp_x4 / 4;
+        while (G < 128 && (long long)ncol * (G / 32) * 2 <= slots) G *= 2;
+      }
+      const int nblk = G > 32 ? ncol : (ncol + (32 / G) - 1) / (32 / G);
       switch (G) {
+        case 64: k2_coopw2_kernel<<<nblk, 64, 0, st>>>(P); break;
+        case 128: k2_coopw4_kernel<<<nblk, 128, 0, st>>>(P); break;
         case 2: k2_coop2_kernel<<<nblk, 32, 0, st>>>(P); break;
         case 4: k2_coop4_kernel<<<nblk, 32, 0, st>>>(P); break;
         case 8: k2_coop8_kernel<<<nblk, 32, 0, st>>>(P); break;
@@ -1031,9 +1040,9 @@ int mct_set_k2_mode(int mode, int coop_max_columns) {
 }
 
 int mct_set_k2_lanes(int lanes_per_column) {
-  if (lanes_per_column != 0 && lanes_per_column != 2 && lanes_per_column != 4 && lanes_per_column != 8 && lanes_per_column != 16 &&
-      lanes_per_column != 32)
-    return fail(MCT_E_INVALID_ARG, "set_k2_lanes: lanes per column must be 0 (auto), 2, 4, 8, 16 or 32");
+  const int l = lanes_per_column;
+  if (l != 0 && (l < 2 || l > 128 || (l & (l - 1)) != 0))
+    return fail(MCT_E_INVALID_ARG, "set_k2_lanes: lanes per column must be 0 (auto) or a power of two from 2 to 128");
   g.k2_coop_lanes = lanes_per_column;
   return MCT_OK;
 }
