@@ -142,6 +142,8 @@ __device__ __forceinline__ bool apply_ca_from(const CaMat& Mine, int src, double
   double t1 = fmax(fmax(fmax(fabs(ee1), fabs(ee2)), fmax(fabs(ee3), fabs(ee4))), fabs(ee5));
   if (t1 < 1.e-40) t1 = 1.0;
   const double y_t1 = mct_rcp(t1);
+  // (starting the reciprocal for all five candidates before the maximum is known shortens the dependent chain by
+  //  three compare/select levels but adds 20 FP64 instructions; measured: no gain)
   RangeTrack R;
   /* t1 is one of the |ee| (or 1.0) */ R.add(ee1); R.add(ee2); R.add(ee3); R.add(ee4); R.add(ee5);
   if (!R.ok()) return false;
@@ -166,11 +168,15 @@ __device__ __noinline__ bool dltar4_layerpar_dev(const float4* __restrict__ lay,
   EVec E;
   {
     const float4 L = __ldg(&lay[(size_t)(mmax - 1) * stride]);
-    const double xka = omega / (double)L.y;
-    const double xkb = omega / (double)L.z;
+    const double4 Rh = layr[(size_t)(mmax - 1) * stride];
+    // the three divisions of the half-space start vector through the reciprocal table when it vouches for the
+    // layer constants (a NaN first entry means it does not) -- same bits as `/`, a fraction of its latency
+    const bool tab = (true /* omega checked above */) && Rh.x == Rh.x;
+    const double xka = tab ? mct_div_r(omega, (double)L.y, Rh.x) : omega / (double)L.y;
+    const double xkb = tab ? mct_div_r(omega, (double)L.z, Rh.y) : omega / (double)L.z;
     const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
     const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const double t = (double)L.z / omega;
+    const double t = tab ? mct_div_r((double)L.z, omega, y_om) : (double)L.z / omega;
     const double gammk = 2.0 * t * t;
     const double gam = gammk * wvno2;
     const double gamm1 = gam - 1.0;

@@ -76,7 +76,8 @@ __device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, c
     const float4 L = __ldg(&lay[(size_t)(mmax - 1) * stride]);
     const double beta1 = (double)L.z;
     const double rho1 = (double)L.w;
-    const double xkb = omega / beta1;
+    const double4 Rh = layr[(size_t)(mmax - 1) * stride];
+    const double xkb = (om_ok && Rh.x == Rh.x) ? mct_div_r(omega, beta1, Rh.x) : omega / beta1; // table-vouched: same bits as `/`
     const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
     E.e1 = rho1 * rb;
     E.e2 = 1.0 / (beta1 * beta1);

@@ -238,11 +238,15 @@ __device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, c
   EVec E;
   {
     const float4 L = __ldg(&lay[(size_t)(mmax - 1) * stride]);
-    const double xka = omega / (double)L.y;
-    const double xkb = omega / (double)L.z;
+    const double4 Rh = layr[(size_t)(mmax - 1) * stride];
+    // the three divisions of the half-space start vector through the reciprocal table when it vouches for the
+    // layer constants (a NaN first entry means it does not) -- same bits as `/`, a fraction of its latency
+    const bool tab = (om_ok) && Rh.x == Rh.x;
+    const double xka = tab ? mct_div_r(omega, (double)L.y, Rh.x) : omega / (double)L.y;
+    const double xkb = tab ? mct_div_r(omega, (double)L.z, Rh.y) : omega / (double)L.z;
     const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
     const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const double t = (double)L.z / omega;
+    const double t = tab ? mct_div_r((double)L.z, omega, y_om) : (double)L.z / omega;
     const double gammk = 2.0 * t * t;
     const double gam = gammk * wvno2;
     const double gamm1 = gam - 1.0;

@@ -122,11 +122,11 @@ def _model(grid, ncells, seed, math_mode=orc.PORTABLE):
 
 
 def _check_disp(mct, grid, vp, vs, rho, window, freqs, raylov, pg, nmodes, variant="likelihood"):
-    """Runs the dispersion block with BOTH kernel shapes (one thread per column, one warp per column);
-    the two must agree bit for bit with each other and with the oracle, counters included."""
+    """Runs the dispersion block with EVERY kernel shape (one thread per column; 2..32 lanes per column; 2 and 4
+    warps per column); all must agree bit for bit with each other and with the oracle, counters included."""
     opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nmodes, variant=variant)
     res = []
-    for mode, lanes in ((1, 0), (2, 32), (2, 16), (2, 8), (2, 4), (2, 2)):
+    for mode, lanes in ((1, 0), (2, 128), (2, 64), (2, 32), (2, 16), (2, 8), (2, 4), (2, 2)):
         mct.set_k2_mode(mode)
         mct.set_k2_lanes(lanes)
         mct.reset_stats()
@@ -408,7 +408,7 @@ def test_fuzz_random_layer_stacks(mct, seed, raylov, pg, nm):
     periods = np.sort(rng.choice(np.geomspace(0.1, 80.0, 40), 14, replace=False))
     freqs = 1.0 / periods
     opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nm)
-    for mode, lanes in ((1, 0), (2, 32), (2, 8), (2, 2)):
+    for mode, lanes in ((1, 0), (2, 128), (2, 32), (2, 8), (2, 2)):
         mct.set_k2_mode(mode)
         mct.set_k2_lanes(lanes)
         ph, gr, ie, rc = mct.surfmodes_batch(a[:, 0], a[:, 1], a[:, 2], a[:, 3], offs, freqs, opts)
