@@ -377,15 +377,18 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   {
     ProfScope ps(1, st);
     const int nw = (ncol + 31) / 32;
-    // Batches that cannot fill the GPU with one thread per column get G lanes per column: the smallest power of
-    // two that still (nearly) fills the resident-lane capacity, up to a whole warp (proposal-sized batches).
+    // Batches that cannot fill the GPU with one thread per column get G lanes per column: the largest power of
+    // two, up to a whole warp, that keeps the launch within about two waves of resident lanes.
     const long long capacity = (long long)g.sm_count * 16 * 32; // resident lanes of the dispersion kernels
-    const int coop_max = g.k2_coop_max > 0 ? g.k2_coop_max : (int)std::min<long long>(capacity, 1 << 30);
+    // Hand-over to one thread per column: two lanes per column stay ahead until ~1.7x the resident lanes (65 536
+    // columns: 78 ms against 94 ms), and are level with it at 131 072 (tools/lanes_sweep.py X huge).
+    const int coop_max = g.k2_coop_max > 0 ? g.k2_coop_max : (int)std::min<long long>(capacity * 17 / 10, 1 << 30);
     const bool coop = (g.k2_mode == 2) || (g.k2_mode == 0 && ncol < coop_max);
     if (coop) {
       int G = 32;
       if (g.k2_coop_lanes > 0) G = g.k2_coop_lanes;
-      else while (G > 2 && (long long)ncol * (G / 2) * 5 >= capacity * 4) G /= 2; // halve while 80 % of capacity stays filled
+      else while (G > 2 && (long long)ncol * G * 5 > capacity * 11) G /= 2; // largest G within 2.2x the resident lanes:
+      // measured optimum (tools/lanes_sweep.py big): shorter serial chains beat a fully resident grid up to ~2 waves
       // The smallest batches get several warps per column (one block per column, its warps on different SM
       // sub-partitions): as many as keep the total at or below g.k2_warps_per_smsp warps per sub-partition.
       if (g.k2_coop_lanes == 0 && G == 32) {

@@ -7,7 +7,12 @@ sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from mctomo_b200 import capi, synth
 capi.init(0)
 dev = torch.device('cuda', 0)
-grid, pts, par, freqs = synth.config(sys.argv[1] if len(sys.argv) > 1 else "C2")
+if len(sys.argv) > 1 and sys.argv[1] == "X":   # 256 x 256 x 40 grid, 20 periods: the hand-over to one thread per column
+    grid = synth.make_grid(256, 256, 40)
+    pts, par = synth.generate_model(grid, 1200, 77)
+    freqs = synth.freqs(20)
+else:
+    grid, pts, par, freqs = synth.config(sys.argv[1] if len(sys.argv) > 1 else "C2")
 opts = capi.disp_opts(raylov=1, phaseGroup=0, nmodes=0)
 ncell = grid.nx * grid.ny * grid.nz
 d_vp = torch.empty(ncell, dtype=torch.float64, device=dev); d_vs = torch.empty_like(d_vp); d_rho = torch.empty_like(d_vp)
@@ -36,12 +41,18 @@ def run(win, n=3):
 
 
 capi.set_k2_mode(2)
-for (wx, wy) in [(4, 4), (8, 8), (12, 12), (16, 16), (20, 20), (24, 24), (32, 32), (45, 45)]:
+BIG = len(sys.argv) > 2 and sys.argv[2] == "big"
+HUGE = len(sys.argv) > 2 and sys.argv[2] == "huge"
+WINS = [(90, 90), (128, 128), (181, 181), (222, 222), (256, 256)] if HUGE else [(45, 45), (64, 64), (80, 80), (grid.nx, grid.ny)] if BIG else [(4, 4), (8, 8), (12, 12), (16, 16), (20, 20), (24, 24), (32, 32), (45, 45)]
+LANES = (1, 2, 4, 8, 16, 0) if HUGE else (2, 4, 8, 16, 32, 0) if BIG else (16, 32, 64, 128, 0)   # 1 = one thread per column
+for (wx, wy) in WINS:
+    wx = min(wx, grid.nx); wy = min(wy, grid.ny)
     win = (1, wx, 1, wy)
     row = []
     base = None
-    for lanes in (16, 32, 64, 128, 0):
-        capi.set_k2_lanes(lanes)
+    for lanes in LANES:
+        capi.set_k2_mode(1 if lanes == 1 else 2)
+        capi.set_k2_lanes(0 if lanes == 1 else lanes)
         ms = run(win)
         res = d_pv[: wx * wy * nout].clone()
         if base is None:
