@@ -236,6 +236,34 @@ int mct_selftest_division(int emax, int64_t* tested, int64_t* mismatches);
 int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, int ix1, int iy0, int iy1,
                          double* d_vel, void* stream);
 
+/* ---- resident session: one chain's model kept in HBM between proposals -------------------------------------
+ * Replaces, for a sampler that adopts it, the per-iteration sequence of src/mcmc_loc2.f90:199-228,556-566 +
+ * src/likelihood.f90:75-83 + src/likelihood_surf.F90:155-231 -- backup, kdtree_to_grid(box), vs2vp_3d/vp2rho_3d,
+ * check_model (whole grid), dispersion of the box's columns + one-column halo, keep or restore -- with calls that
+ * move only the nuclei (48 B each) in and the window's dispersion maps out.  Same results as the host-pointer
+ * entry points (tests/test_gpu_session.py).  Not thread-safe per session; one pending proposal at a time. */
+typedef struct mct_session mct_session;
+int mct_session_create(const mct_grid* g, const double* freqs, int np, const mct_disp_opts* opt, int derive_vp_rho,
+                       mct_session** out);
+int mct_session_destroy(mct_session* s);
+/* Full evaluation of a nuclei set (every node, every column); it becomes the current model.  Host outputs
+ * pvel/gvel (nout,ny,nx), ierr (ny,nx), model_invalid are optional (NULL: results stay on the device). */
+int mct_session_set_model(mct_session* s, const double* points, const double* params, int ncells, double* pvel,
+                          double* gvel, int32_t* ierr, int32_t* model_invalid);
+/* One proposal: nuclei AFTER the move, the box handed to kdtree_to_grid, pm = NULL or the moved cell's
+ * (vp,vs,rho) for a value-only move.  Out: win = {ix0,ix1,iy0,iy1} (1-based; box columns + halo) and that
+ * window's maps packed (nout,wy,wx) / (wy,wx); the caller provides room for nx*ny columns.  When check_model
+ * rejects the model (*model_invalid = 1) nothing is solved and the map buffers are not meaningful.  The call
+ * commits nothing: follow it with mct_session_accept or mct_session_reject. */
+int mct_session_propose(mct_session* s, const double* points, const double* params, int ncells, const double box[6],
+                        const double* pm, int32_t win[4], double* pvel_win, double* gvel_win, int32_t* ierr_win,
+                        int32_t* model_invalid);
+int mct_session_accept(mct_session* s);
+int mct_session_reject(mct_session* s);
+/* Read the resident arrays back (checkpoint/restart, tests); any pointer may be NULL. */
+int mct_session_get_model(mct_session* s, double* vp, double* vs, double* rho, int32_t* sites_id);
+int mct_session_get_maps(mct_session* s, double* pvel, double* gvel, int32_t* ierr);
+
 #ifdef __cplusplus
 }
 #endif

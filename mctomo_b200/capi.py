@@ -467,3 +467,95 @@ def selftest_division(emax: int = 300):
     m = C.c_int64(0)
     _check(L.mct_selftest_division(emax, C.byref(t), C.byref(m)))
     return t.value, m.value
+
+
+class Session:
+    """One chain's model resident in HBM between proposals (mct_session_*, include/mctomo_b200.h).
+
+    set_model(points, params) -> full evaluation;  propose(points, params, box[, pm]) -> (window, pvel, gvel, ierr,
+    model_invalid) for the box's columns + halo;  accept() / reject() commit or restore."""
+
+    def __init__(self, grid: Grid, freqs, opts: mct_disp_opts, derive_vp_rho=True):
+        L = lib()
+        vp = C.c_void_p
+        L.mct_session_create.argtypes = [C.POINTER(mct_grid), vp, C.c_int, C.POINTER(mct_disp_opts), C.c_int, C.POINTER(vp)]
+        L.mct_session_destroy.argtypes = [vp]
+        L.mct_session_set_model.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        L.mct_session_propose.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.mct_session_accept.argtypes = [vp]
+        L.mct_session_reject.argtypes = [vp]
+        L.mct_session_get_model.argtypes = [vp, vp, vp, vp, vp]
+        L.mct_session_get_maps.argtypes = [vp, vp, vp, vp]
+        self._L = L
+        self.grid = grid
+        self.freqs = _f64(freqs)
+        self.opts = opts
+        self.nout = len(self.freqs) * max(opts.nmodes, 1)
+        h = vp()
+        _check(L.mct_session_create(C.byref(grid.c()), self.freqs.ctypes.data, len(self.freqs), C.byref(opts),
+                                    1 if derive_vp_rho else 0, C.byref(h)))
+        self._h = h
+        ncol = grid.nx * grid.ny
+        self._pv = np.zeros(ncol * self.nout)      # staging for the largest possible window
+        self._gv = np.zeros(ncol * self.nout)
+        self._ie = np.zeros(ncol, np.int32)
+
+    def close(self):
+        if self._h:
+            self._L.mct_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_model(self, points, params, want_maps=True):
+        points, params = _f64(points), _f64(params)
+        g = self.grid
+        inval = C.c_int32(0)
+        pv = np.zeros((g.nx, g.ny, self.nout)) if want_maps else None
+        gv = np.zeros((g.nx, g.ny, self.nout)) if want_maps else None
+        ie = np.zeros((g.nx, g.ny), np.int32) if want_maps else None
+        rc = _check(self._L.mct_session_set_model(self._h, points.ctypes.data, params.ctypes.data, len(points),
+                                                  pv.ctypes.data if want_maps else None, gv.ctypes.data if want_maps else None,
+                                                  ie.ctypes.data if want_maps else None, C.addressof(inval)),
+                    allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+        return dict(pvel=pv, gvel=gv, ierr=ie, model_invalid=inval.value, rc=rc)
+
+    def propose(self, points, params, box, pm=None):
+        points, params, box = _f64(points), _f64(params), _f64(box)
+        pmv = None if pm is None else _f64(pm)
+        win = np.zeros(4, np.int32)
+        inval = C.c_int32(0)
+        rc = _check(self._L.mct_session_propose(self._h, points.ctypes.data, params.ctypes.data, len(points), box.ctypes.data,
+                                                None if pmv is None else pmv.ctypes.data, win.ctypes.data, self._pv.ctypes.data,
+                                                self._gv.ctypes.data, self._ie.ctypes.data, C.addressof(inval)),
+                    allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+        wx, wy = int(win[1] - win[0] + 1), int(win[3] - win[2] + 1)
+        n = max(wx, 0) * max(wy, 0)
+        pv = self._pv[: n * self.nout].reshape(max(wx, 0), max(wy, 0), self.nout)
+        gv = self._gv[: n * self.nout].reshape(max(wx, 0), max(wy, 0), self.nout)
+        ie = self._ie[:n].reshape(max(wx, 0), max(wy, 0))
+        return dict(window=tuple(int(v) for v in win), pvel=pv, gvel=gv, ierr=ie, model_invalid=inval.value, rc=rc)
+
+    def accept(self):
+        _check(self._L.mct_session_accept(self._h))
+
+    def reject(self):
+        _check(self._L.mct_session_reject(self._h))
+
+    def get_model(self):
+        g = self.grid
+        vp, vs, rho = np.zeros(g.shape), np.zeros(g.shape), np.zeros(g.shape)
+        sid = np.zeros(g.shape, np.int32)
+        _check(self._L.mct_session_get_model(self._h, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, sid.ctypes.data))
+        return vp, vs, rho, sid
+
+    def get_maps(self):
+        g = self.grid
+        pv, gv = np.zeros((g.nx, g.ny, self.nout)), np.zeros((g.nx, g.ny, self.nout))
+        ie = np.zeros((g.nx, g.ny), np.int32)
+        _check(self._L.mct_session_get_maps(self._h, pv.ctypes.data, gv.ctypes.data, ie.ctypes.data))
+        return pv, gv, ie

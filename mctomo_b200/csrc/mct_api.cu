@@ -1091,3 +1091,5 @@ int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, 
 }
 
 } // extern "C"
+
+#include "mct_session.cuh" // mct_session_*: a chain's model resident in HBM between proposals

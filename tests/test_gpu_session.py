@@ -1,0 +1,131 @@
+"""Resident session (mct_session_*): a random walk of rjMCMC-style proposals -- moves, value changes, births,
+deaths, accepted and rejected, valid and invalid -- must leave the device-resident model and maps identical, bit
+for bit, to what the oracle computes from scratch for the chain's current nuclei, and every proposal's window
+maps must equal the oracle's (reference call sequence: src/mcmc_loc2.f90:199-228,556-566,
+src/likelihood.f90:75-83, src/likelihood_surf.F90:155-231)."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from mctomo_b200 import synth
+from mctomo_b200.capi import disp_opts
+
+pytestmark = pytest.mark.gpu
+
+F1730 = float(np.float32(1.730))
+
+
+def _full_model(grid, pts, par):
+    vp, vs, rho = np.zeros(grid.shape), np.zeros(grid.shape), np.zeros(grid.shape)
+    sid = np.zeros(grid.shape, np.int32)
+    orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
+    vp, rho = orc.vs2vp_rho(vs)
+    return vp, vs, rho, sid
+
+
+def _box_of(grid, mask):
+    ii, jj, kk = np.nonzero(mask)
+    lo = np.array([grid.xmin + ii.min() * grid.dx, grid.ymin + jj.min() * grid.dy, grid.zmin + kk.min() * grid.dz])
+    hi = np.array([grid.xmin + ii.max() * grid.dx, grid.ymin + jj.max() * grid.dy, grid.zmin + kk.max() * grid.dz])
+    return np.concatenate([lo - 1e-9, hi + 1e-9])
+
+
+@pytest.mark.parametrize("raylov,pg,nm", [(1, 1, 0), (0, 0, 2)])
+def test_session_random_walk(mct, raylov, pg, nm):
+    grid = synth.make_grid(20, 18, 30)
+    freqs = synth.freqs(8)
+    opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nm)
+    okw = dict(raylov=raylov, phaseGroup=pg, nmodes=nm)
+    rng = np.random.default_rng(77 + raylov)
+    pts, par = synth.generate_model(grid, 40, 4242)
+    S = mct.Session(grid, freqs, opts)
+    r0 = S.set_model(pts, par)
+    cur = _full_model(grid, pts, par)
+    o = orc.surf_dispersion(cur[0], cur[1], cur[2], grid, (1, grid.nx, 1, grid.ny), freqs, **okw)
+    assert r0["model_invalid"] == 0 and orc.check_model(cur[1], grid) == 0
+    assert np.array_equal(r0["pvel"], o[0]) and np.array_equal(r0["gvel"], o[1]) and np.array_equal(r0["ierr"], o[2])
+    maps = [o[0].copy(), o[1].copy(), o[2].copy()]
+    seen = dict(accept=0, reject=0, invalid=0, value=0, birth=0, death=0, move=0)
+    lo = np.array([grid.xmin, grid.ymin, grid.zmin])
+    hi = np.array([grid.xmax, grid.ymax, grid.zmax])
+    for step in range(36):
+        kind = ("move", "move", "vmove", "value", "birth", "death")[step % 6]
+        n = len(pts)
+        pts2, par2, pm = pts.copy(), par.copy(), None
+        i = int(rng.integers(n))
+        if kind == "move":
+            pts2[i] = np.clip(pts[i] + rng.normal(0, 0.5, 3) * np.array([1.0, 1.0, 0.0]), lo, hi)
+        elif kind == "vmove":     # vertical moves break vs(z) monotonicity now and then: check_model rejects
+            pts2[i] = np.clip(pts[i] + rng.normal(0, 2.5, 3) * np.array([0.2, 0.2, 1.0]), lo, hi)
+        elif kind == "value":
+            par2[i, 1] = par[i, 1] * (1.0 + 0.01 * rng.normal())
+            par2[i, 0] = 1.73 * par2[i, 1]
+            pm = np.array([par[i, 1] * F1730, par[i, 1], 0.0])  # what the gridded model holds for that cell
+        elif kind == "birth":
+            p = lo + rng.random(3) * (hi - lo)
+            vs = 2.0 + (p[2] - grid.zmin) * 4.0 / (grid.zmax - grid.zmin)
+            pts2 = np.vstack([pts, p])
+            par2 = np.vstack([par, [1.73 * vs, vs, 2.4]])
+        else:                     # death of the last nucleus: the numbering of the others is unchanged
+            pts2, par2 = pts[:-1].copy(), par[:-1].copy()
+            i = n - 1
+        new = _full_model(grid, pts2, par2)
+        changed = (new[3] != cur[3]) | (new[1] != cur[1])
+        if kind == "value":
+            changed |= cur[3] == i + 1
+        if not changed.any():
+            continue
+        box = _box_of(grid, changed)
+        r = S.propose(pts2, par2, box, pm=pm)
+        w = orc.box_window(grid, box)
+        win = (max(w[0] - 1, 1), min(w[1] + 1, grid.nx), max(w[2] - 1, 1), min(w[3] + 1, grid.ny))
+        assert r["window"] == tuple(int(v) for v in win)
+        inval = orc.check_model(new[1], grid)
+        assert r["model_invalid"] == inval
+        # the proposed model is on the device
+        got = S.get_model()
+        for a, b in zip(got, new):
+            assert np.array_equal(a, b), kind
+        if not inval:
+            ow = orc.surf_dispersion(new[0], new[1], new[2], grid, win, freqs, **okw)
+            assert np.array_equal(r["pvel"], ow[0]) and np.array_equal(r["gvel"], ow[1]) and np.array_equal(r["ierr"], ow[2]), kind
+        accept = bool(rng.random() < 0.6) and not inval
+        if inval:
+            seen["invalid"] += 1
+        if accept:
+            S.accept()
+            pts, par, cur = pts2, par2, new
+            sx, sy = slice(win[0] - 1, win[1]), slice(win[2] - 1, win[3])
+            maps[0][sx, sy], maps[1][sx, sy], maps[2][sx, sy] = ow[0], ow[1], ow[2]
+            seen["accept"] += 1
+        else:
+            S.reject()
+            seen["reject"] += 1
+        seen[kind if kind != "vmove" else "move"] += 1
+        got = S.get_model()
+        for a, b in zip(got, cur):
+            assert np.array_equal(a, b), (kind, accept)
+        gm = S.get_maps()
+        assert np.array_equal(gm[0], maps[0]) and np.array_equal(gm[1], maps[1]) and np.array_equal(gm[2], maps[2])
+    # after the walk the resident maps are the from-scratch maps of the current nuclei
+    o = orc.surf_dispersion(cur[0], cur[1], cur[2], grid, (1, grid.nx, 1, grid.ny), freqs, **okw)
+    gm = S.get_maps()
+    assert np.array_equal(gm[0], o[0]) and np.array_equal(gm[1], o[1]) and np.array_equal(gm[2], o[2])
+    assert seen["accept"] >= 8 and seen["reject"] >= 6 and seen["invalid"] >= 1 and seen["value"] >= 3
+    S.close()
+
+
+def test_session_protocol_errors(mct):
+    grid = synth.make_grid(8, 8, 10)
+    S = mct.Session(grid, synth.freqs(4), disp_opts())
+    pts, par = synth.generate_model(grid, 10, 1)
+    with pytest.raises(mct.MctError):
+        S.propose(pts, par, grid.cover_box())          # no current model yet
+    S.set_model(pts, par)
+    with pytest.raises(mct.MctError):
+        S.accept()                                     # nothing pending
+    S.propose(pts, par, grid.cover_box())
+    with pytest.raises(mct.MctError):
+        S.propose(pts, par, grid.cover_box())          # previous proposal unresolved
+    S.reject()
+    S.close()
