@@ -15,6 +15,7 @@ freqs = synth.example1_freqs()
 opts = capi.disp_opts(raylov=1, phaseGroup=0, nmodes=0)
 opts_w = capi.disp_opts(raylov=1, phaseGroup=0, nmodes=0, check_scope=1)
 WINDOWED = len(sys.argv) > 1 and sys.argv[1] == 'windowed'
+SESSION = len(sys.argv) > 1 and sys.argv[1] == 'session'
 rng = np.random.default_rng(1)
 out = {}
 for ncells in (100, 300):
@@ -24,6 +25,9 @@ for ncells in (100, 300):
     O = [a.copy() for a in G]
     VPG, RHOG = capi.vs2vp_rho(G[1])
     tg, tc, cols = [], [], []
+    if SESSION:
+        S = capi.Session(grid, freqs, opts)
+        S.set_model(pts, par, want_maps=False)
     for step in range(24):
         i = int(rng.integers(ncells))
         pts2 = pts.copy()
@@ -39,15 +43,26 @@ for ncells in (100, 300):
         w = capi.box_window(grid, box)
         win = (max(w[0] - 1, 1), min(w[1] + 1, grid.nx), max(w[2] - 1, 1), min(w[3] + 1, grid.ny))
         t0 = time.perf_counter()
-        capi.kdtree_to_grid(pts2, par, grid, box, *G)
-        if WINDOWED:   # only what changed travels: windowed property maps, window-scoped check_model
+        if SESSION:    # nuclei in, window maps out; model resident; whole-grid check_model like the reference
+            r = S.propose(pts2, par, box)
+            S.accept()
+            pv, gv, ie, inval, rc = r["pvel"], r["gvel"], r["ierr"], r["model_invalid"], r["rc"]
+            t1 = time.perf_counter()
+            assert r["window"] == win
+            G[0], G[1], G[2], G[3] = S.get_model()
+        else:
+            capi.kdtree_to_grid(pts2, par, grid, box, *G)
+        if SESSION:
+            pass
+        elif WINDOWED:   # only what changed travels: windowed property maps, window-scoped check_model
             capi.vs2vp_rho_window(G[1], VPG, RHOG, grid, w)
             vpg, rhog = VPG, RHOG
             pv, gv, ie, inval, rc = capi.surf_dispersion(vpg, G[1], rhog, grid, win, freqs, opts_w)
         else:
             vpg, rhog = capi.vs2vp_rho(G[1])
             pv, gv, ie, inval, rc = capi.surf_dispersion(vpg, G[1], rhog, grid, win, freqs, opts)
-        t1 = time.perf_counter()
+        if not SESSION:
+            t1 = time.perf_counter()
         orc.kdtree_to_grid(pts2, par, grid, box, *O)
         vpo, rhoo = orc.vs2vp_rho(O[1], orc.LIBM)
         inv_o = orc.check_model(O[1], grid)
@@ -64,5 +79,5 @@ for ncells in (100, 300):
                                "speedup_median": float(np.median(np.array(tc) / np.array(tg)))}
     print(ncells, out[f"ncells_{ncells}"], flush=True)
 out["what"] = "C1 (101x101x121, 11 periods, Rayleigh phase): move proposals; GPU = host-pointer C ABI incl. all H2D/D2H; CPU = oracle (libm) on all cores"
-out["mode"] = "windowed transfers (mct_vs2vp_rho_window, check_scope=1)" if WINDOWED else "reference-shaped calls (whole-grid vs2vp, whole-grid check_model)"
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "replay_C1_windowed.json" if WINDOWED else "replay_C1.json"), "w"), indent=1)
+out["mode"] = "resident session (mct_session_propose + accept: nuclei in, window maps out, whole-grid check_model)" if SESSION else "windowed transfers (mct_vs2vp_rho_window, check_scope=1)" if WINDOWED else "reference-shaped calls (whole-grid vs2vp, whole-grid check_model)"
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "replay_C1_session.json" if SESSION else "replay_C1_windowed.json" if WINDOWED else "replay_C1.json"), "w"), indent=1)
