@@ -417,7 +417,7 @@ def main():
                           if batch * ncell * 28 > (126 << 20) else "256 MiB buffer written between timed steps (L2 flush)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["n_launches"]), "roofline": roof, "cpu_baseline": cpu,
                "proposal_latency": {"columns": (pw[1] - pw[0] + 1) * (pw[3] - pw[2] + 1), "ms": proposal_ms,
-                                    "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, warp-per-column kernel"},
+                                    "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, cooperative kernel (4 warps per column)"},
                "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
                         "columns_per_step": st["n_columns"] / args.steps}}
         GUARD.emit(json.dumps(out))
