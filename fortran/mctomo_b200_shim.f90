@@ -93,6 +93,50 @@ module m_mctomo_b200
             type(c_ptr), value    :: pvel, gvel, ierr
             type(c_ptr), value    :: model_invalid       ! c_null_ptr = skip check_model
         end function
+        ! ---- resident session (INTEGRATION.md 5a): the chain's model stays in HBM between proposals ----
+        integer(c_int) function mct_session_create(g, freqs, np, opt, derive_vp_rho, sess) bind(C, name='mct_session_create')
+            import :: c_int, c_ptr, mct_grid, mct_disp_opts
+            type(mct_grid), intent(in) :: g
+            type(c_ptr), value    :: freqs
+            integer(c_int), value :: np
+            type(mct_disp_opts), intent(in) :: opt
+            integer(c_int), value :: derive_vp_rho
+            type(c_ptr), intent(out) :: sess
+        end function
+        integer(c_int) function mct_session_destroy(sess) bind(C, name='mct_session_destroy')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess
+        end function
+        integer(c_int) function mct_session_set_model(sess, points, params, ncells, pvel, gvel, ierr, model_invalid) &
+                bind(C, name='mct_session_set_model')
+            import :: c_int, c_ptr
+            type(c_ptr), value    :: sess, points, params
+            integer(c_int), value :: ncells
+            type(c_ptr), value    :: pvel, gvel, ierr, model_invalid   ! c_null_ptr: keep on the device
+        end function
+        integer(c_int) function mct_session_propose(sess, points, params, ncells, box, pm, win, pvel_w, gvel_w, ierr_w, &
+                model_invalid) bind(C, name='mct_session_propose')
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value    :: sess, points, params
+            integer(c_int), value :: ncells
+            real(c_double), intent(in) :: box(6)
+            type(c_ptr), value    :: pm                              ! c_null_ptr, or (vp,vs,rho) of a value-only move
+            integer(c_int), intent(out) :: win(4)                    ! ix0, ix1, iy0, iy1 (1-based, box + halo)
+            type(c_ptr), value    :: pvel_w, gvel_w, ierr_w          ! packed (nout,wy,wx) / (wy,wx); room for nx*ny columns
+            integer(c_int), intent(out) :: model_invalid
+        end function
+        integer(c_int) function mct_session_accept(sess) bind(C, name='mct_session_accept')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess
+        end function
+        integer(c_int) function mct_session_reject(sess) bind(C, name='mct_session_reject')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess
+        end function
+        integer(c_int) function mct_session_get_model(sess, vp, vs, rho, sites_id) bind(C, name='mct_session_get_model')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess, vp, vs, rho, sites_id
+        end function
     end interface
 
 contains
