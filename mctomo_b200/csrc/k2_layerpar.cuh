@@ -43,7 +43,7 @@ __device__ __forceinline__ bool compute_ca(const float4 L, const double4 Rc, dou
     const bool na_ = exa < 60.0;
     double facp = 0.0, facq = 0.0;
     a0 = 0.0;
-    if (np_ | nq_ | na_) {
+    if (!(p >= 16.0 && q >= 16.0 && exa >= 60.0)) { // (chained compares; `np_ | nq_ | na_` made the compiler build min(p, q) with NaN handling)
       const double fp = mct_exp_core(np_ ? -2.0 * p : -1.0);
       const double fq = mct_exp_core(nq_ ? -2.0 * q : -1.0);
       const double fa = mct_exp_core(na_ ? -exa : -1.0);
@@ -139,7 +139,7 @@ __device__ __forceinline__ bool apply_ca_from(const CaMat& Mine, int src, double
   double ee3 = e1 * ca13; ee3 = ee3 + e2 * ca23; ee3 = ee3 + e3 * ca33; ee3 = ee3 + e4 * ca43; ee3 = ee3 + e5 * ca53;
   double ee4 = e1 * ca14; ee4 = ee4 + e2 * ca24; ee4 = ee4 + e3 * ca34; ee4 = ee4 + e4 * ca22; ee4 = ee4 + e5 * ca21;
   double ee5 = e1 * ca15; ee5 = ee5 + e2 * ca14; ee5 = ee5 + e3 * ca35; ee5 = ee5 + e4 * ca12; ee5 = ee5 + e5 * ca11;
-  double t1 = fmax(fmax(fmax(fabs(ee1), fabs(ee2)), fmax(fabs(ee3), fabs(ee4))), fabs(ee5));
+  double t1 = dmax_nn(dmax_nn(dmax_nn(fabs(ee1), fabs(ee2)), dmax_nn(fabs(ee3), fabs(ee4))), fabs(ee5));
   if (t1 < 1.e-40) t1 = 1.0;
   const double y_t1 = mct_rcp(t1);
   // (starting the reciprocal for all five candidates before the maximum is known shortens the dependent chain by

@@ -58,7 +58,7 @@ __device__ __forceinline__ bool love_step_fast(const float4 L, const double4 Rc,
   const double n20 = E.e1 * y;
   R.add(n20);
   const double e20 = mct_div_r(n20, xmu, y_mu) + E.e2 * cosq;
-  double xnor = fmax(fabs(e10), fabs(e20));
+  double xnor = dmax_nn(fabs(e10), fabs(e20));
   if (xnor < 1.e-40) xnor = 1.0;
   const double y_n = mct_rcp(xnor);
   R.add(e10); R.add(e20); // xnor is one of them (or 1.0)

@@ -18,6 +18,10 @@
 
 struct EVec { double e1, e2, e3, e4, e5; };
 
+// max of two doubles that are known not to be NaN when the result is used (a NaN operand fails the step's range check):
+// one DSETP and two selects, where fmax() costs eight instructions for its NaN semantics
+__device__ __forceinline__ double dmax_nn(double a, double b) { return a > b ? a : b; }
+
 // exponent-word tracker: all operands of fast divisions must be normal with |x| in [2^-400, 2^400]
 struct RangeTrack {
   unsigned lo, hi;
@@ -128,7 +132,7 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc
     const bool na_ = exa < 60.0;
     double facp = 0.0, facq = 0.0;
     a0 = 0.0;
-    if (np_ | nq_ | na_) {
+    if (!(p >= 16.0 && q >= 16.0 && exa >= 60.0)) { // (chained compares; `np_ | nq_ | na_` made the compiler build min(p, q) with NaN handling)
       const double fp = mct_exp_core(np_ ? -2.0 * p : -1.0);
       const double fq = mct_exp_core(nq_ ? -2.0 * q : -1.0);
       const double fa = mct_exp_core(na_ ? -exa : -1.0);
@@ -214,7 +218,7 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc
   double ee4 = e1 * ca14; ee4 = ee4 + e2 * ca24; ee4 = ee4 + e3 * ca34; ee4 = ee4 + e4 * ca22; ee4 = ee4 + e5 * ca21;
   double ee5 = e1 * ca15; ee5 = ee5 + e2 * ca14; ee5 = ee5 + e3 * ca35; ee5 = ee5 + e4 * ca12; ee5 = ee5 + e5 * ca11;
   // normc (:1350-1360): max |ee|, then five quotients by the same scale
-  double t1 = fmax(fmax(fmax(fabs(ee1), fabs(ee2)), fmax(fabs(ee3), fabs(ee4))), fabs(ee5));
+  double t1 = dmax_nn(dmax_nn(dmax_nn(fabs(ee1), fabs(ee2)), dmax_nn(fabs(ee3), fabs(ee4))), fabs(ee5));
   if (t1 < 1.e-40) t1 = 1.0;
   const double y_t1 = mct_rcp(t1);
   /* t1 is one of the |ee| (or 1.0) */ R.add(ee1); R.add(ee2); R.add(ee3); R.add(ee4); R.add(ee5);
