@@ -104,11 +104,16 @@ __device__ __noinline__ EVec layer_step_exact(const float4 L, double wvno, doubl
 // Returns false (E untouched) when the step must be redone by layer_step_exact.
 // Rc = {1/alpha, 1/beta, 1/rho, 1/rho^2}: the refined reciprocals of this layer's constants, computed once per
 // forward evaluation by layer_recips_kernel with the same mct_rcp sequence (bit-identical to computing them here).
-__device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc, double wvno, double wvno2, double omega, double y_om, EVec& E) {
+// L, Rc: this layer's records on entry; when `more`, the NEXT layer's records (from nl, nr) on exit -- each reloaded
+// right after its last use, so that the prefetch lands in the registers it vacates (a separate "next" copy cost 12
+// register moves per step).
+__device__ __forceinline__ bool layer_step_fast(float4& L, double4& Rc, const float4* __restrict__ nl, const double4* __restrict__ nr, bool more,
+                                                double wvno, double wvno2, double omega, double y_om, EVec& E) {
   RangeTrack R;
   const double a = (double)L.y, b = (double)L.z, dpth = (double)L.x, rho = (double)L.w;
   const double rho2 = rho * rho;
   const double y_a = Rc.x, y_b = Rc.y, y_rho = Rc.z, y_rho2 = Rc.w;
+  if (more) L = __ldg(nl);
   // (a, b, rho, rho2 are range-checked once per layer by layer_recips_kernel: an out-of-range constant poisons
   //  y_a with NaN, which reaches ra below and sends the step to the exact path)
   const double xka = mct_div_r(omega, a, y_a);
@@ -196,6 +201,7 @@ __device__ __forceinline__ bool layer_step_fast(const float4 L, const double4 Rc
   const double ca13 = mct_div_r(n13, rho, y_rho);
   const double ca14 = mct_div_r(n14, rho, y_rho);
   const double ca15 = mct_div_r(n15, rho2, y_rho2);
+  if (more) Rc = *nr;
   const double ca21 = (gmgmk * cpz - gm1sq * cqw) * rho;
   const double ca22 = cpcq;
   const double ca23 = gammk * cpz - gamm1 * cqw;
@@ -267,16 +273,11 @@ __device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, c
   int m = mmax - 2;
   if (om_ok) {
     float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
-    double4 Rn = layr[(size_t)max(m, 0) * stride];
+    double4 Rc = layr[(size_t)max(m, 0) * stride];
 #pragma unroll 1
-    for (; m >= llw - 1; --m) {
-      const float4 Lc = L;
-      const double4 Rc = Rn;
-      if (m > 0) { // next layer's records are in flight during this step
-        L = __ldg(&lay[(size_t)(m - 1) * stride]);
-        Rn = layr[(size_t)(m - 1) * stride];
-      }
-      if (!layer_step_fast(Lc, Rc, wvno, wvno2, omega, y_om, E)) break;
+    for (; m >= llw - 1; --m) { // the next layer's records are fetched inside the step
+      const size_t nxt = (size_t)max(m - 1, 0) * stride;
+      if (!layer_step_fast(L, Rc, lay + nxt, layr + nxt, m > 0, wvno, wvno2, omega, y_om, E)) break;
     }
   }
 #pragma unroll 1
