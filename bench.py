@@ -101,6 +101,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def k2_kernel_name(ncol, sm_count):
+    """The dispersion kernel launch_k2 (mct_api.cu) picks for a batch of ncol columns (automatic mode)."""
+    cap = sm_count * 16 * 32                      # resident lanes
+    if ncol >= cap * 17 // 10:
+        return "k2_dispersion_fast_r128"
+    g = 32
+    while g > 2 and ncol * g * 5 > cap * 11:
+        g //= 2
+    if g == 32:
+        slots = sm_count * 16
+        while g < 128 and ncol * (g // 32) * 2 <= slots:
+            g *= 2
+    return {128: "k2_coopw4_kernel", 64: "k2_coopw2_kernel", 32: "k2_coop_kernel"}.get(g, f"k2_coop{g}_kernel")
+
+
 def workload(args, rank, world):
     from mctomo_b200 import synth
     c = dict(synth.CONFIGS[args.config])
@@ -378,7 +393,8 @@ def main():
             pass
         roof = {"bound": "fp64", "achieved": achieved, "peak": probe["dfma_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / probe["dfma_tflops"] if achieved else None, "traffic": traffic,
-                "kernel": "k2_dispersion_fast_r128" if batch * wx * grid.ny > 16384 else "k2_coop_kernel", "k2_ms_per_step": kt["k2_ms"] / args.steps,
+                "kernel": k2_kernel_name(batch * wx * grid.ny, torch.cuda.get_device_properties(dev).multi_processor_count),
+                "k2_ms_per_step": kt["k2_ms"] / args.steps,
                 "k2_share_of_step": kt["k2_ms"] / sum(step_ms),
                 "peak_source": "measured live: 8 independent DFMA chains/thread (mct_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_dmul_dadd_tflops": probe["dmul_dadd_tflops"],
