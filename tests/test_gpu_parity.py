@@ -292,6 +292,49 @@ def test_full_size_c3_sampled_against_oracle(mct, raylov):
         assert np.array_equal(p0, r["pvel"][i, j]) and np.array_equal(g0, r["gvel"][i, j])
 
 
+def test_full_size_c5_sampled_against_oracle(mct):
+    """BASELINE config C5 at full size (1024x1024x80, 60 periods = the NP limit, 5000 nuclei, Rayleigh phase): all
+    1 048 576 columns are solved on one GPU; 200 random columns are re-solved by the oracle (bit-identical), the cell
+    map is checked by brute force on a sample of nodes, and the maps must be complete and inside the model's range."""
+    grid, pts, par, freqs = synth.config("C5")
+    assert (grid.nx, grid.ny, grid.nz, len(freqs), len(pts)) == (1024, 1024, 80, 60, 5000)
+    opts = disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    r = mct.forward_eval(pts, par, grid, freqs, opts, want_model=True)
+    assert r["model_invalid"] == 0 and r["rc"] == 0
+    pv, ie = r["pvel"], r["ierr"]
+    assert pv.shape == (1024, 1024, 60) and not ie.any()
+    assert (pv > 1.5).all() and (pv < 6.1).all()
+    assert (np.diff(pv, axis=-1) > -1e-3).all()          # normal dispersion for depth-increasing velocities
+    rng = np.random.default_rng(5)
+    ii = rng.integers(0, grid.nx, 1500); jj = rng.integers(0, grid.ny, 1500); kk = rng.integers(0, grid.nz, 1500)
+    q = np.stack([grid.xmin + ii * grid.dx, grid.ymin + jj * grid.dy, grid.zmin + kk * grid.dz], 1)
+    d = ((q[:, None, :] - pts[None]) ** 2).sum(-1)
+    assert np.array_equal(r["sites_id"][ii, jj, kk], d.argmin(1) + 1)
+    for i, j in zip(rng.integers(0, grid.nx, 200), rng.integers(0, grid.ny, 200)):
+        n, (th, al, be, rk) = orc.convert_column(r["vp"][i, j], r["vs"][i, j], r["rho"][i, j], grid.dz)
+        rc, p0, g0, e0, _ = orc.surfmodes(th, al, be, rk, freqs, 1, 0, 0)
+        assert rc == 0 and e0 == 0
+        assert np.array_equal(p0, pv[i, j])
+
+
+def test_full_size_c4_chains_per_gpu(mct):
+    """BASELINE config C4, one GPU's share at full size: 8 chains x 128x128x50, 20 periods, ncells ~ U{25..300} per
+    chain, in ONE batched call; 25 random columns of every chain are re-solved by the oracle (bit-identical)."""
+    grid = synth.make_grid(128, 128, 50)
+    freqs = synth.freqs(20)
+    rng = np.random.default_rng(1004)
+    models = [synth.generate_model(grid, int(rng.integers(25, 301)), 1004 + c) for c in range(8)]
+    pts, par, off = mct.pack_models(models)
+    opts = disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    r = mct.forward_eval_batch(pts, par, off, grid, freqs, opts, want_model=True)
+    assert r["rc"] == 0 and not r["model_invalid"].any() and not r["ierr"].any()
+    for b in range(8):
+        for i, j in zip(rng.integers(0, grid.nx, 25), rng.integers(0, grid.ny, 25)):
+            n, (th, al, be, rk) = orc.convert_column(r["vp"][b, i, j], r["vs"][b, i, j], r["rho"][b, i, j], grid.dz)
+            rc, p0, g0, e0, _ = orc.surfmodes(th, al, be, rk, freqs, 1, 0, 0)
+            assert rc == 0 and e0 == 0 and np.array_equal(p0, r["pvel"][b, i, j])
+
+
 def test_forward_eval_batch_of_chains(mct):
     """Several independent models (chains) with different numbers of nuclei in ONE call (config C4's shape)."""
     grid = synth.make_grid(20, 18, 30)
