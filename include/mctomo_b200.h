@@ -264,6 +264,18 @@ int mct_session_reject(mct_session* s);
 int mct_session_get_model(mct_session* s, double* vp, double* vs, double* rho, int32_t* sites_id);
 int mct_session_get_maps(mct_session* s, double* pvel, double* gvel, int32_t* ierr);
 
+/* CalGroupTime / GetVelocity (src/likelihood_surf.F90:454-521) on a DEVICE (np,ny,nx) velocity map: travel time of
+ * every ray through the map of its period (bilinear interpolation at the ray points, dist*2/(vhead+vtail)
+ * accumulated point by point, in the reference's order: same bits).  Rays are HOST data, packed: ray r of period ip
+ * owns points ray_offsets[ip*nrays + r] .. ray_offsets[ip*nrays + r + 1]-1 of ray_points (x,y pairs); a ray with
+ * fewer than two points gets time 0.  time: HOST out, (nrays, np), ray index fastest (= time(k,j,i) of the
+ * reference flattened over (k,j)).  mct_session_group_times runs it on the session's resident group-velocity map,
+ * so that map never leaves the device. */
+int mct_group_times_dev(const double* d_vel, int np, const mct_grid* g, const double* ray_points,
+                        const int64_t* ray_offsets, int nrays, double* time, void* stream);
+int mct_session_group_times(mct_session* s, const double* ray_points, const int64_t* ray_offsets, int nrays,
+                            double* time);
+
 #ifdef __cplusplus
 }
 #endif

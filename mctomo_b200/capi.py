@@ -469,6 +469,17 @@ def selftest_division(emax: int = 300):
     return t.value, m.value
 
 
+def group_times_dev(d_vel, np_, grid: Grid, ray_points, ray_offsets, nrays, stream=None):
+    """mct_group_times_dev: travel times (np, nrays) of packed host rays through a device (np,ny,nx) map."""
+    L = lib()
+    L.mct_group_times_dev.argtypes = [C.c_void_p, C.c_int, C.POINTER(mct_grid), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    pts = _f64(ray_points)
+    off = np.ascontiguousarray(ray_offsets, dtype=np.int64)
+    t = np.zeros((np_, nrays))
+    _check(L.mct_group_times_dev(d_vel, np_, C.byref(grid.c()), pts.ctypes.data, off.ctypes.data, nrays, t.ctypes.data, stream))
+    return t
+
+
 class Session:
     """One chain's model resident in HBM between proposals (mct_session_*, include/mctomo_b200.h).
 
@@ -552,6 +563,15 @@ class Session:
         sid = np.zeros(g.shape, np.int32)
         _check(self._L.mct_session_get_model(self._h, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, sid.ctypes.data))
         return vp, vs, rho, sid
+
+    def group_times(self, ray_points, ray_offsets, nrays):
+        """CalGroupTime on the resident group-velocity map: (np, nrays) travel times."""
+        pts = _f64(ray_points)
+        off = np.ascontiguousarray(ray_offsets, dtype=np.int64)
+        t = np.zeros((len(self.freqs), nrays))
+        self._L.mct_session_group_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _check(self._L.mct_session_group_times(self._h, pts.ctypes.data, off.ctypes.data, nrays, t.ctypes.data))
+        return t
 
     def get_maps(self):
         g = self.grid

@@ -71,6 +71,7 @@ struct Ctx {
   DevBuf flags;    // int32[4]: [0] model_invalid, [1] max status, [2] k1 error
   DevBuf bflags;   // int32[2*nb] for host-pointer batch calls
   DevBuf counters; // u64[4]
+  DevBuf ray_pts, ray_off, ray_time; // mct_group_times_dev staging
   PinBuf pin_a, pin_b, pin_small;
   mct_stats host_stats = {0, 0, 0, 0, 0};
 };
@@ -554,7 +555,7 @@ int mct_shutdown(void) {
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
   DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins,
-                    &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters};
+                    &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.ray_pts, &g.ray_off, &g.ray_time};
   for (DevBuf* b : bufs) release(*b);
   release(g.pin_a);
   release(g.pin_b);
@@ -1093,3 +1094,4 @@ int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, 
 } // extern "C"
 
 #include "mct_session.cuh" // mct_session_*: a chain's model resident in HBM between proposals
+#include "k3_raytime.cuh"  // mct_group_times_dev: CalGroupTime on the device map

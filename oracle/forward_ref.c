@@ -167,3 +167,48 @@ void orc_assemble_vel(const double* pvel, int np, int nx, int ny, int ix0, int i
     for (int i = 0; i < nx + 2; ++i)
       memcpy(vel + i * sx + (size_t)(ny + 1) * sy, vel + i * sx + (size_t)ny * sy, sizeof(double) * np);
 }
+
+/* GetVelocity (likelihood_surf.F90:496-521): bilinear interpolation of one period's (ny,nx) map at a point.
+ * vel is the (np,ny,nx) map (element (i,iy,ix) at i + np*(iy + ny*ix), 0-based), ip the 0-based period. */
+static double orc_get_velocity(const double* vel, int np, int ip, int nx, int ny, double xmin, double ymin, double dx,
+                               double dy, double px, double py) {
+  int ix = (int)floor((px - xmin) / dx) + 1;
+  int iy = (int)floor((py - ymin) / dy) + 1;
+  if (ix < 1) ix = 1;
+  if (iy < 1) iy = 1;
+  if (ix >= nx) ix = nx - 1;
+  if (iy >= ny) iy = ny - 1;
+  const double dsx = px - (xmin + (ix - 1) * dx);
+  const double dsy = py - (ymin + (iy - 1) * dy);
+  double qv = 0;
+  for (int i = 1; i <= 2; ++i)
+    for (int j = 1; j <= 2; ++j) {
+      const double weight = (1.0 - fabs((i - 1) * dx - dsx) / dx) * (1.0 - fabs((j - 1) * dy - dsy) / dy);
+      qv = qv + weight * vel[(size_t)ip + (size_t)np * ((size_t)(iy + j - 2) + (size_t)ny * (size_t)(ix + i - 2))];
+    }
+  return qv;
+}
+
+/* CalGroupTime (likelihood_surf.F90:454-494): travel time of every ray through the map of its period, trapezoidal
+ * in slowness-free form dist*2/(vhead+vtail), accumulated point by point.  Rays are packed: ray r of period ip owns
+ * points off[ip*nrays + r] .. off[ip*nrays + r + 1]-1 of pts (x,y pairs); time is (nrays, np), ray index fastest. */
+void orc_cal_group_time(const double* vel, int np, int nx, int ny, double xmin, double ymin, double dx, double dy,
+                        const double* pts, const int64_t* off, int nrays, double* time) {
+  for (int ip = 0; ip < np; ++ip)
+    for (int r = 0; r < nrays; ++r) {
+      const int64_t a = off[(size_t)ip * nrays + r], b = off[(size_t)ip * nrays + r + 1];
+      double t = 0;
+      if (b - a >= 2) {
+        double vhead = orc_get_velocity(vel, np, ip, nx, ny, xmin, ymin, dx, dy, pts[2 * a], pts[2 * a + 1]);
+        for (int64_t n = a + 1; n < b; ++n) {
+          const double ex = pts[2 * n] - pts[2 * (n - 1)], ey = pts[2 * n + 1] - pts[2 * (n - 1) + 1];
+          double dist = ex * ex + ey * ey;
+          dist = sqrt(dist);
+          const double vtail = orc_get_velocity(vel, np, ip, nx, ny, xmin, ymin, dx, dy, pts[2 * n], pts[2 * n + 1]);
+          t = t + dist * 2 / (vhead + vtail);
+          vhead = vtail;
+        }
+      }
+      time[(size_t)ip * nrays + r] = t;
+    }
+}

@@ -53,6 +53,7 @@ def L():
         _L.orc_gtsolh.restype = C.c_float
         _L.orc_gtsolh.argtypes = [C.c_float, C.c_float]
         _L.orc_nlvls1.argtypes = [vp, vp, C.c_int, C.c_int]
+        _L.orc_cal_group_time.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4 + [vp, vp, C.c_int, vp]
     return _L
 
 
@@ -192,3 +193,14 @@ def forward_eval(points, params, grid, freqs, derive_vp_rho=True, math_mode=PORT
                                                math_mode=math_mode, nthreads=nthreads, **kw)
         res.update(pvel=pv, gvel=gv, ierr=ie, counters=cnt)
     return res
+
+
+def cal_group_time(vel, grid, ray_points, ray_offsets, nrays):
+    """CalGroupTime (likelihood_surf.F90:454-494): vel is the (nx, ny, np) C-ordered view of the (np,ny,nx) map."""
+    vel, pts = f64(vel), f64(ray_points)
+    off = np.ascontiguousarray(ray_offsets, dtype=np.int64)
+    np_ = vel.shape[2]
+    t = np.zeros((np_, nrays))
+    L().orc_cal_group_time(vel.ctypes.data, np_, grid.nx, grid.ny, grid.xmin, grid.ymin, grid.dx, grid.dy, pts.ctypes.data,
+                           off.ctypes.data, nrays, t.ctypes.data)
+    return t

@@ -129,3 +129,50 @@ def test_session_protocol_errors(mct):
         S.propose(pts, par, grid.cover_box())          # previous proposal unresolved
     S.reject()
     S.close()
+
+
+def _random_rays(grid, np_, nrays, rng):
+    """Packed rays in the shape fm2d hands to CalGroupTime: wiggly paths of 2-40 points, plus degenerate ones
+    (0 or 1 point -> time 0), points on the domain edges and slightly outside (the stencil clamps)."""
+    pts, off = [], [0]
+    for ip in range(np_):
+        for r in range(nrays):
+            n = int(rng.choice([0, 1, 2, 3, 17, 40]))
+            a = np.array([rng.uniform(grid.xmin, grid.xmax), rng.uniform(grid.ymin, grid.ymax)])
+            b = np.array([rng.uniform(grid.xmin, grid.xmax), rng.uniform(grid.ymin, grid.ymax)])
+            if n:
+                s = np.linspace(0.0, 1.0, n)[:, None]
+                p = a + s * (b - a) + rng.normal(0, 0.05, (n, 2))
+                if r % 5 == 0:
+                    p[0] = [grid.xmin, grid.ymax]              # exactly on a corner
+                if r % 7 == 0:
+                    p[-1] = [grid.xmax + 0.3, grid.ymin - 0.2]  # outside: index clamps, weights extrapolate
+                pts.append(p)
+            off.append(off[-1] + n)
+    return (np.concatenate(pts) if pts else np.zeros((0, 2))), np.array(off, np.int64)
+
+
+def test_group_times_on_resident_map(mct):
+    """CalGroupTime/GetVelocity on the device (likelihood_surf.F90:454-521) == the oracle, bit for bit."""
+    grid = synth.make_grid(20, 18, 30)
+    freqs = synth.freqs(6)
+    S = mct.Session(grid, freqs, disp_opts(raylov=1, phaseGroup=1, nmodes=0))
+    pts, par = synth.generate_model(grid, 40, 4242)
+    r0 = S.set_model(pts, par)
+    rng = np.random.default_rng(9)
+    nrays = 23
+    rp, ro = _random_rays(grid, len(freqs), nrays, rng)
+    t = S.group_times(rp, ro, nrays)
+    ref = orc.cal_group_time(r0["gvel"], grid, rp, ro, nrays)
+    assert t.shape == ref.shape == (len(freqs), nrays)
+    assert np.array_equal(t, ref)
+    assert (t[ro[1:].reshape(len(freqs), nrays) - ro[:-1].reshape(len(freqs), nrays) < 2] == 0).all() and (t > 0).any()
+    # a straight ray through a constant map: time = length / velocity
+    import torch
+    const = torch.full((grid.nx * grid.ny * 6,), 2.5, dtype=torch.float64, device="cuda")
+    line = np.array([[-4.0, -3.0], [0.0, 0.0], [4.0, 3.0]])
+    off = np.array([0] + [3] * 6, np.int64)
+    off = np.concatenate([[0], np.cumsum([3] * 6)]).astype(np.int64)
+    tl = mct.group_times_dev(const.data_ptr(), 6, grid, np.tile(line, (6, 1)), off, 1)
+    assert np.allclose(tl, 10.0 / 2.5, rtol=1e-14)
+    S.close()
