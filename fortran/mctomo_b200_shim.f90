@@ -133,6 +133,15 @@ module m_mctomo_b200
             import :: c_int, c_ptr
             type(c_ptr), value :: sess
         end function
+        integer(c_int) function mct_session_group_times(sess, ray_points, ray_offsets, nrays, time) &
+                bind(C, name='mct_session_group_times')
+            import :: c_int, c_ptr
+            type(c_ptr), value    :: sess
+            type(c_ptr), value    :: ray_points      ! real(c_double) (2, total points), rays packed back to back
+            type(c_ptr), value    :: ray_offsets     ! integer(c_int64_t) (nrays*np + 1), 0-based first point of each ray
+            integer(c_int), value :: nrays
+            type(c_ptr), value    :: time            ! real(c_double) (nrays, np) out = like%phaseTime flattened over (nrev,nsrc)
+        end function
         integer(c_int) function mct_session_get_model(sess, vp, vs, rho, sites_id) bind(C, name='mct_session_get_model')
             import :: c_int, c_ptr
             type(c_ptr), value :: sess, vp, vs, rho, sites_id
