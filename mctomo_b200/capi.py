@@ -446,7 +446,8 @@ def set_k1_mode(mode: int = 0):
 
 
 def set_k2_mode(mode: int = 0, coop_max_columns: int = -1):
-    """0 auto (warp per column up to coop_max_columns, else thread per column), 1 thread per column, 2 warp per column."""
+    """0 auto (lane groups per column below coop_max_columns, else one thread per column), 1 always one thread per column,
+    2 always lane groups (size: set_k2_lanes)."""
     L = _bind_batch()
     L.mct_set_k2_mode.argtypes = [C.c_int, C.c_int]
     _check(L.mct_set_k2_mode(mode, coop_max_columns))

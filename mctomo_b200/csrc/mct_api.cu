@@ -60,7 +60,7 @@ struct Ctx {
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
   int k2_warps_per_smsp_x4 = 16; // multi-warp columns are used while the launch stays within this many warps per SM sub-partition (in quarters): 4 warps = full residency (lanes sweep, tools/lanes_sweep.py)
   int k2_coop_max = 0;      // auto mode: batches below this many columns take the lane-cooperative kernels
-                            // (0 = the resident-lane capacity of the GPU, 75 776 on a B200)
+                            // (0 = 1.7 x the resident lanes of the GPU: 128 819 columns on a B200)
   int k2_coop_lanes = 0;    // lanes per column of the cooperative kernel: 0 = choose per launch (MCT_K2_COOP_LANES)
   int sort_stable = 1;      // stable counting sort of the columns (MCT_SORT_STABLE=0: atomic-cursor sort)
   int k2_variant = 7; // 7 production, 3 plain secular functions (A/B reference), 0 plain + unsorted: launch shape of K2 (see launch_k2); MCT_K2_VARIANT overrides (experiments)
@@ -545,7 +545,11 @@ int mct_init(int device) {
   g.host_stats = mct_stats{0, 0, 0, 0, 0};
   if (const char* v = getenv("MCT_K2_VARIANT")) g.k2_variant = atoi(v);
   if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
-  if (const char* v = getenv("MCT_K2_COOP_LANES")) g.k2_coop_lanes = atoi(v);  g.init = true;
+  if (const char* v = getenv("MCT_K2_COOP_LANES")) { // experiments only; same validation as mct_set_k2_lanes
+    const int l = atoi(v);
+    if (l == 0 || (l >= 2 && l <= 128 && (l & (l - 1)) == 0)) g.k2_coop_lanes = l;
+  }
+  g.init = true;
   return MCT_OK;
 }
 
