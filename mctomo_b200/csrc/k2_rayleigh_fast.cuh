@@ -274,10 +274,12 @@ __device__ __noinline__ double dltar4_fast_dev(const float4* __restrict__ lay, c
   if (om_ok) {
     float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
     double4 Rc = layr[(size_t)max(m, 0) * stride];
+    const float4* nl = lay + (size_t)max(m - 1, 0) * stride;   // next layer's records: running pointers, one subtraction
+    const double4* nr = layr + (size_t)max(m - 1, 0) * stride; // per step instead of a 64-bit multiply-add each
 #pragma unroll 1
     for (; m >= llw - 1; --m) { // the next layer's records are fetched inside the step
-      const size_t nxt = (size_t)max(m - 1, 0) * stride;
-      if (!layer_step_fast(L, Rc, lay + nxt, layr + nxt, m > 0, wvno, wvno2, omega, y_om, E)) break;
+      if (!layer_step_fast(L, Rc, nl, nr, m > 0, wvno, wvno2, omega, y_om, E)) break;
+      if (m > 1) { nl -= stride; nr -= stride; }
     }
   }
 #pragma unroll 1
