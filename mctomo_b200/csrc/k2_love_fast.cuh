@@ -30,11 +30,17 @@ __device__ __noinline__ E2 love_step_exact(const float4 L, double wvno, double o
 }
 
 // Rc = {1/beta, 1/(rho beta^2), -, -} from layer_recips_kernel
-__device__ __forceinline__ bool love_step_fast(const float4 L, const double4 Rc, double wvno, double omega, E2& E) {
+// L, Rc: this layer's records on entry, the next layer's on exit when `more` (reloaded in place, see layer_step_fast)
+__device__ __forceinline__ bool love_step_fast(float4& L, double2& Rc, const float4* __restrict__ nl, const double4* __restrict__ nr, bool more,
+                                               double wvno, double omega, E2& E) {
   RangeTrack R;
   const double b = (double)L.z, rho = (double)L.w, dm = (double)L.x;
   const double xmu = rho * b * b;
   const double y_b = Rc.x, y_mu = Rc.y;
+  if (more) {
+    L = __ldg(nl);
+    Rc = *reinterpret_cast<const double2*>(nr); // only the first two of the four table entries are used by Love
+  }
   const double xkb = mct_div_r(omega, b, y_b);
   const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
   const double q = dm * rb;
@@ -85,16 +91,13 @@ __device__ __noinline__ double dltar1_fast_dev(const float4* __restrict__ lay, c
   int m = mmax - 2;
   if (om_ok) {
     float4 L = __ldg(&lay[(size_t)max(m, 0) * stride]);
-    double4 Rn = layr[(size_t)max(m, 0) * stride];
+    double2 Rc = *reinterpret_cast<const double2*>(&layr[(size_t)max(m, 0) * stride]);
+    const float4* nl = lay + (size_t)max(m - 1, 0) * stride;
+    const double4* nr = layr + (size_t)max(m - 1, 0) * stride;
 #pragma unroll 1
     for (; m >= llw - 1; --m) {
-      const float4 Lc = L;
-      const double4 Rc = Rn;
-      if (m > 0) {
-        L = __ldg(&lay[(size_t)(m - 1) * stride]);
-        Rn = layr[(size_t)(m - 1) * stride];
-      }
-      if (!love_step_fast(Lc, Rc, wvno, omega, E)) break;
+      if (!love_step_fast(L, Rc, nl, nr, m > 0, wvno, omega, E)) break;
+      if (m > 1) { nl -= stride; nr -= stride; }
     }
   }
 #pragma unroll 1
