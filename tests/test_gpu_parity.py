@@ -525,3 +525,40 @@ def test_sample_postprocessor_accumulation(mct):
     st.synchronize()
     for a, r in zip(acc, ref):
         assert np.array_equal(a.cpu().numpy().reshape(grid.shape), r)
+
+
+def test_status_codes_and_degenerate_inputs(mct):
+    """Conditions the reference answers with `stop`, array overruns or empty loops: too many layers (ierr = 3), a fluid
+    layer below the top (ierr = 4), boxes outside the grid (nothing is touched), no nuclei (argument error)."""
+    freqs = synth.freqs(4)
+    opts = disp_opts()
+    # 230 distinct layers > NL = 200 (surfdisp96.f:57) next to an ordinary column and one with a fluid layer in the middle
+    n_big = 230
+    th = np.concatenate([np.full(n_big - 1, 0.05), [0.0], [1.0, 2.0, 0.0], [1.0, 1.0, 2.0, 0.0]])
+    vs = np.concatenate([np.linspace(1.0, 4.5, n_big), [2.0, 3.0, 4.0], [2.0, 0.0, 3.0, 4.0]])
+    vp = 1.73 * vs
+    vp[n_big + 3 + 1] = 1.5
+    rho = np.full_like(vs, 2.5)
+    offs = [0, n_big, n_big + 3, n_big + 7]
+    ph, gr, ie, rc = mct.surfmodes_batch(th, vp, vs, rho, offs, freqs, opts)
+    assert list(ie) == [3, 0, 4]
+    assert rc in (mct.MCT_E_TOO_MANY_LAYERS, mct.MCT_E_FLUID_BELOW_TOP)
+    assert (ph[0] == opts.preset).all() and (ph[2] == opts.preset).all()
+    rc0, p0, g0, e0, _ = orc.surfmodes(th[n_big:n_big + 3], vp[n_big:n_big + 3], vs[n_big:n_big + 3], rho[n_big:n_big + 3], freqs, 1, 0, 0)
+    assert np.array_equal(ph[1], p0)                      # the ordinary column is solved regardless of its neighbours
+    # boxes that miss the grid: the Fortran loops run zero times, nothing is written
+    grid = synth.make_grid(8, 7, 10)
+    pts, par = synth.generate_model(grid, 20, 3)
+    base = [np.full(grid.shape, -7.0), np.full(grid.shape, -7.0), np.full(grid.shape, -7.0), np.full(grid.shape, -7, np.int32)]
+    for box in ([grid.xmax + 1, grid.ymin, grid.zmin, grid.xmax + 2, grid.ymax, grid.zmax],
+                [grid.xmin, grid.ymin, grid.zmax + 1, grid.xmax, grid.ymax, grid.zmax + 5],
+                [grid.xmin, grid.ymin, grid.zmin, grid.xmin - 3, grid.ymax, grid.zmax]):
+        arrs = [a.copy() for a in base]
+        mct.kdtree_to_grid(pts, par, grid, np.array(box, float), *arrs)
+        ref = [a.copy() for a in base]
+        orc.kdtree_to_grid(pts, par, grid, np.array(box, float), *ref)
+        for a, b in zip(arrs, ref):
+            assert np.array_equal(a, b)
+    with pytest.raises(mct.MctError) as e:
+        mct.kdtree_to_grid(pts[:0], par[:0], grid, grid.cover_box(), *[a.copy() for a in base])
+    assert e.value.code == mct.MCT_E_INVALID_ARG
