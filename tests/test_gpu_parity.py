@@ -562,3 +562,32 @@ def test_status_codes_and_degenerate_inputs(mct):
     with pytest.raises(mct.MctError) as e:
         mct.kdtree_to_grid(pts[:0], par[:0], grid, grid.cover_box(), *[a.copy() for a in base])
     assert e.value.code == mct.MCT_E_INVALID_ARG
+
+
+def test_maximum_layer_count(mct):
+    """Columns with exactly NL = 200 layers (surfdisp96.f:57) and 199: solved, bit-identical to the oracle, in the
+    thread-per-column kernel and in the cooperative ones (7 passes of the layer-parallel evaluation)."""
+    cols, offs = [], [0]
+    for n in (200, 199, 64, 33):
+        vs = np.linspace(1.2, 4.6, n) + 0.003 * np.sin(np.arange(n))
+        vs = np.sort(vs)
+        th = np.full(n, 0.06)
+        th[-1] = 0.0
+        vp = 1.8 * vs
+        cols.append(np.stack([th, vp, vs, np.full(n, 2.6)], 1))
+        offs.append(offs[-1] + n)
+    a = np.concatenate(cols)
+    freqs = 1.0 / np.array([0.3, 1.0, 4.0, 12.0])
+    for raylov in (1, 0):
+        opts = disp_opts(raylov=raylov, phaseGroup=1, nmodes=0)
+        for mode, lanes in ((1, 0), (2, 128), (2, 32), (2, 4)):
+            mct.set_k2_mode(mode)
+            mct.set_k2_lanes(lanes)
+            ph, gr, ie, rc = mct.surfmodes_batch(a[:, 0], a[:, 1], a[:, 2], a[:, 3], offs, freqs, opts)
+            for c in range(4):
+                s = slice(offs[c], offs[c + 1])
+                rc0, p0, g0, e0, _ = orc.surfmodes(a[s, 0], a[s, 1], a[s, 2], a[s, 3], freqs, raylov, 1, 0)
+                assert rc0 == 0 and e0 == ie[c], (raylov, lanes, c)
+                assert np.array_equal(ph[c], p0) and np.array_equal(gr[c], g0), (raylov, lanes, c)
+    mct.set_k2_mode(0)
+    mct.set_k2_lanes(0)
