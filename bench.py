@@ -111,9 +111,8 @@ def k2_kernel_name(ncol, sm_count):
         g //= 2
     if g == 32:
         slots = sm_count * 16
-        while g < 128 and ncol * (g // 32) * 2 <= slots:
-            g *= 2
-    return {128: "k2_coopw4_kernel", 64: "k2_coopw2_kernel", 32: "k2_coop_kernel"}.get(g, f"k2_coop{g}_kernel")
+        g = 256 if ncol * 8 <= slots else 128 if ncol * 4 <= slots else 64 if ncol * 3 <= slots else 32
+    return {256: "k2_coopw8_kernel", 128: "k2_coopw4_kernel", 64: "k2_coopw2_kernel", 32: "k2_coop_kernel"}.get(g, f"k2_coop{g}_kernel")
 
 
 def workload(args, rank, world):
@@ -433,7 +432,7 @@ def main():
                           if batch * ncell * 28 > (126 << 20) else "256 MiB buffer written between timed steps (L2 flush)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["n_launches"]), "roofline": roof, "cpu_baseline": cpu,
                "proposal_latency": {"columns": (pw[1] - pw[0] + 1) * (pw[3] - pw[2] + 1), "ms": proposal_ms,
-                                    "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, cooperative kernel (4 warps per column)"},
+                                    "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, cooperative kernel (several warps per column)"},
                "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
                         "columns_per_step": st["n_columns"] / args.steps}}
         GUARD.emit(json.dumps(out))

@@ -219,10 +219,10 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
 int mct_set_k1_mode(int mode);
 /* Shape of the dispersion kernel.  mode 0 (default): batches of fewer than coop_max_columns columns (default 0 =
  * 1.7x the resident lanes of the GPU, 128 819 columns on a B200; pass -1 to keep) give every column a GROUP OF G LANES that
- * split getsol's bracketing scan: G = 128 or 64 (a block of 4 or 2 warps per column, while that keeps the launch
- * within the GPU's resident warps: proposal-sized calls), 32 (one warp), down to 2 -- the largest power of two
+ * split getsol's bracketing scan: G = 256, 128 or 64 (a block of 8, 4 or 2 warps per column, while that keeps the
+ * launch within the GPU's resident warps: proposal-sized calls), 32 (one warp), down to 2 -- the largest power of two
  * that keeps the launch within about two waves of resident lanes.  Larger batches run one THREAD per column.  mode 1 / 2 force
- * one or the other; mct_set_k2_lanes fixes G (0 = automatic, else a power of two from 2 to 128).  Results are
+ * one or the other; mct_set_k2_lanes fixes G (0 = automatic, else a power of two from 2 to 256).  Results are
  * identical in every shape. */
 int mct_set_k2_mode(int mode, int coop_max_columns);
 int mct_set_k2_lanes(int lanes_per_column);

@@ -454,7 +454,7 @@ def set_k2_mode(mode: int = 0, coop_max_columns: int = -1):
 
 
 def set_k2_lanes(lanes_per_column: int = 0):
-    """Lanes per column of the cooperative dispersion kernel: 0 automatic, else a power of two from 2 to 128."""
+    """Lanes per column of the cooperative dispersion kernel: 0 automatic, else a power of two from 2 to 256."""
     L = _bind_batch()
     L.mct_set_k2_lanes.argtypes = [C.c_int]
     _check(L.mct_set_k2_lanes(lanes_per_column))

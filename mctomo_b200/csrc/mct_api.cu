@@ -58,7 +58,6 @@ struct Ctx {
   DevBuf lay, layr, nlay, status, perm, bins;
   int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
-  int k2_warps_per_smsp_x4 = 16; // multi-warp columns are used while the launch stays within this many warps per SM sub-partition (in quarters): 4 warps = full residency (lanes sweep, tools/lanes_sweep.py)
   int k2_coop_max = 0;      // auto mode: batches below this many columns take the lane-cooperative kernels
                             // (0 = 1.7 x the resident lanes of the GPU: 128 819 columns on a B200)
   int k2_coop_lanes = 0;    // lanes per column of the cooperative kernel: 0 = choose per launch (MCT_K2_COOP_LANES)
@@ -332,6 +331,7 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   P.igr = opt->phaseGroup;
   P.count = g.count_on;
   P.ddc0 = (float)opt->dphase; // ddc0 = dphase (surfdisp96.f:130)
+  P.dc = fabs((double)P.ddc0);
   P.preset_unsolved = opt->preset;
   P.pvel = d_pvel;
   P.gvel = d_gvel;
@@ -391,15 +391,19 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
       else while (G > 2 && (long long)ncol * G * 5 > capacity * 11) G /= 2; // largest G within 2.2x the resident lanes:
       // measured optimum (tools/lanes_sweep.py big): shorter serial chains beat a fully resident grid up to ~2 waves
       // The smallest batches get several warps per column (one block per column, its warps on different SM
-      // sub-partitions): as many as keep the total at or below g.k2_warps_per_smsp warps per sub-partition.
+      // sub-partitions): 8 or 4 while the launch stays within the GPU's resident warps, 2 up to two thirds of them
+      // (tools/lanes_sweep.py: 576 columns 1.54 ms with 4 warps against 1.90 with one; 1024 columns: one warp is best).
       if (g.k2_coop_lanes == 0 && G == 32) {
-        const long long slots = (long long)g.sm_count * 4 * g.k2_warps_per_smsp_x4 / 4;
-        while (G < 128 && (long long)ncol * (G / 32) * 2 <= slots) G *= 2;
+        const long long slots = (long long)g.sm_count * 16; // resident warps
+        if ((long long)ncol * 8 <= slots) G = 256;
+        else if ((long long)ncol * 4 <= slots) G = 128;
+        else if ((long long)ncol * 3 <= slots) G = 64;
       }
       const int nblk = G > 32 ? ncol : (ncol + (32 / G) - 1) / (32 / G);
       switch (G) {
         case 64: k2_coopw2_kernel<<<nblk, 64, 0, st>>>(P); break;
         case 128: k2_coopw4_kernel<<<nblk, 128, 0, st>>>(P); break;
+        case 256: k2_coopw8_kernel<<<nblk, 256, 0, st>>>(P); break;
         case 2: k2_coop2_kernel<<<nblk, 32, 0, st>>>(P); break;
         case 4: k2_coop4_kernel<<<nblk, 32, 0, st>>>(P); break;
         case 8: k2_coop8_kernel<<<nblk, 32, 0, st>>>(P); break;
@@ -547,7 +551,7 @@ int mct_init(int device) {
   if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
   if (const char* v = getenv("MCT_K2_COOP_LANES")) { // experiments only; same validation as mct_set_k2_lanes
     const int l = atoi(v);
-    if (l == 0 || (l >= 2 && l <= 128 && (l & (l - 1)) == 0)) g.k2_coop_lanes = l;
+    if (l == 0 || (l >= 2 && l <= 256 && (l & (l - 1)) == 0)) g.k2_coop_lanes = l;
   }
   g.init = true;
   return MCT_OK;
@@ -1049,8 +1053,8 @@ int mct_set_k2_mode(int mode, int coop_max_columns) {
 
 int mct_set_k2_lanes(int lanes_per_column) {
   const int l = lanes_per_column;
-  if (l != 0 && (l < 2 || l > 128 || (l & (l - 1)) != 0))
-    return fail(MCT_E_INVALID_ARG, "set_k2_lanes: lanes per column must be 0 (auto) or a power of two from 2 to 128");
+  if (l != 0 && (l < 2 || l > 256 || (l & (l - 1)) != 0))
+    return fail(MCT_E_INVALID_ARG, "set_k2_lanes: lanes per column must be 0 (auto) or a power of two from 2 to 256");
   g.k2_coop_lanes = lanes_per_column;
   return MCT_OK;
 }

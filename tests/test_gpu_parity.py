@@ -126,7 +126,7 @@ def _check_disp(mct, grid, vp, vs, rho, window, freqs, raylov, pg, nmodes, varia
     warps per column); all must agree bit for bit with each other and with the oracle, counters included."""
     opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=nmodes, variant=variant)
     res = []
-    for mode, lanes in ((1, 0), (2, 128), (2, 64), (2, 32), (2, 16), (2, 8), (2, 4), (2, 2)):
+    for mode, lanes in ((1, 0), (2, 256), (2, 128), (2, 64), (2, 32), (2, 16), (2, 8), (2, 4), (2, 2)):
         mct.set_k2_mode(mode)
         mct.set_k2_lanes(lanes)
         mct.reset_stats()

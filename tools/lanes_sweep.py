@@ -44,7 +44,7 @@ capi.set_k2_mode(2)
 BIG = len(sys.argv) > 2 and sys.argv[2] == "big"
 HUGE = len(sys.argv) > 2 and sys.argv[2] == "huge"
 WINS = [(90, 90), (128, 128), (181, 181), (222, 222), (256, 256)] if HUGE else [(45, 45), (64, 64), (80, 80), (grid.nx, grid.ny)] if BIG else [(4, 4), (8, 8), (12, 12), (16, 16), (20, 20), (24, 24), (32, 32), (45, 45)]
-LANES = (1, 2, 4, 8, 16, 0) if HUGE else (2, 4, 8, 16, 32, 0) if BIG else (16, 32, 64, 128, 0)   # 1 = one thread per column
+LANES = (1, 2, 4, 8, 16, 0) if HUGE else (2, 4, 8, 16, 32, 0) if BIG else (32, 64, 128, 256, 0)   # 1 = one thread per column
 for (wx, wy) in WINS:
     wx = min(wx, grid.nx); wy = min(wy, grid.ny)
     win = (1, wx, 1, wy)
