@@ -305,6 +305,7 @@ int plan_disp(const mct_grid* gr, int ix0, int ix1, int iy0, int iy1, int np, co
   if (ix0 < 1 || iy0 < 1 || ix1 > gr->nx || iy1 > gr->ny || ix1 < ix0 || iy1 < iy0)
     return fail(MCT_E_INVALID_ARG, "dispersion: window %d..%d x %d..%d outside the %d x %d grid", ix0, ix1, iy0, iy1, gr->nx, gr->ny);
   if (opt->raylov != 0 && opt->raylov != 1) return fail(MCT_E_INVALID_ARG, "dispersion: raylov must be 0 (Love) or 1 (Rayleigh)");
+  if (opt->nmodes > 1000) return fail(MCT_E_INVALID_ARG, "dispersion: nmodes must not exceed 1000 (the mode counter of the search state is 16 bits)");
   if (!(gr->scaling != 0.0)) return fail(MCT_E_INVALID_ARG, "dispersion: grid scaling must be non-zero");
   pl.ix0 = ix0; pl.ix1 = ix1; pl.iy0 = iy0; pl.iy1 = iy1;
   pl.wx = ix1 - ix0 + 1; pl.wy = iy1 - iy0 + 1;
