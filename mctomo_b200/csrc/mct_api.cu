@@ -821,6 +821,7 @@ int mct_surfmodes_batch(const double* thick, const double* vp, const double* vs,
     return fail(MCT_E_INVALID_ARG, "surfmodes_batch: bad arguments");
   if (np < 1 || np > MCT_MAX_PERIODS) return fail(MCT_E_INVALID_ARG, "surfmodes_batch: np must be in 1..%d", MCT_MAX_PERIODS);
   if (opt->raylov != 0 && opt->raylov != 1) return fail(MCT_E_INVALID_ARG, "surfmodes_batch: raylov must be 0 or 1");
+  if (opt->nmodes > 1000) return fail(MCT_E_INVALID_ARG, "surfmodes_batch: nmodes must not exceed 1000");
   const int64_t ntot = offsets[ncol] - offsets[0];
   int maxl = 1;
   for (int c = 0; c < ncol; ++c) {
