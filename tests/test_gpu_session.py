@@ -176,3 +176,23 @@ def test_group_times_on_resident_map(mct):
     tl = mct.group_times_dev(const.data_ptr(), 6, grid, np.tile(line, (6, 1)), off, 1)
     assert np.allclose(tl, 10.0 / 2.5, rtol=1e-14)
     S.close()
+
+
+def test_shutdown_and_reinit(mct):
+    """mct_shutdown frees every buffer; calls then fail with MCT_E_NOINIT (no fallback), and a new mct_init brings the
+    library back with identical results.  A session outliving the shutdown can still be destroyed."""
+    grid = synth.make_grid(8, 7, 12)
+    freqs = synth.freqs(4)
+    pts, par = synth.generate_model(grid, 15, 2)
+    opts = disp_opts()
+    a = mct.forward_eval(pts, par, grid, freqs, opts)
+    S = mct.Session(grid, freqs, opts)
+    S.set_model(pts, par)
+    mct.shutdown()
+    with pytest.raises(mct.MctError) as e:
+        mct.forward_eval(pts, par, grid, freqs, opts)
+    assert e.value.code == mct.MCT_E_NOINIT
+    S.close()
+    mct.init(0)
+    b = mct.forward_eval(pts, par, grid, freqs, opts)
+    assert np.array_equal(a["pvel"], b["pvel"]) and np.array_equal(a["ierr"], b["ierr"])
