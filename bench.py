@@ -111,7 +111,7 @@ def k2_kernel_name(ncol, sm_count):
         g //= 2
     if g == 32:
         slots = sm_count * 16
-        g = 256 if ncol * 8 <= slots else 128 if ncol * 4 <= slots else 64 if ncol * 3 <= slots else 32
+        g = 128 if ncol * 5 <= slots else 64 if ncol * 3 <= slots else 32
     return {256: "k2_coopw8_kernel", 128: "k2_coopw4_kernel", 64: "k2_coopw2_kernel", 32: "k2_coop_kernel"}.get(g, f"k2_coop{g}_kernel")
 
 

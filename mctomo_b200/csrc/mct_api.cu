@@ -392,12 +392,12 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
       else while (G > 2 && (long long)ncol * G * 5 > capacity * 11) G /= 2; // largest G within 2.2x the resident lanes:
       // measured optimum (tools/lanes_sweep.py big): shorter serial chains beat a fully resident grid up to ~2 waves
       // The smallest batches get several warps per column (one block per column, its warps on different SM
-      // sub-partitions): 8 or 4 while the launch stays within the GPU's resident warps, 2 up to two thirds of them
-      // (tools/lanes_sweep.py: 576 columns 1.54 ms with 4 warps against 1.90 with one; 1024 columns: one warp is best).
+      // sub-partitions): 4 up to a fifth of the GPU's resident warps, 2 up to a third (tools/lanes_sweep.py: 400 columns
+      // 1.39 ms with 4 warps against 1.80 with one; 576: 1.54 with 2; 1024: one warp is best; 8 warps never pay off
+      // since the warps of a block are all busy during nevill's bisections too).
       if (g.k2_coop_lanes == 0 && G == 32) {
         const long long slots = (long long)g.sm_count * 16; // resident warps
-        if ((long long)ncol * 8 <= slots) G = 256;
-        else if ((long long)ncol * 4 <= slots) G = 128;
+        if ((long long)ncol * 5 <= slots) G = 128;
         else if ((long long)ncol * 3 <= slots) G = 64;
       }
       const int nblk = G > 32 ? ncol : (ncol + (32 / G) - 1) / (32 / G);
