@@ -33,8 +33,10 @@ extern "C" {
 #define MCT_E_INVALID_ARG 1    /* bad sizes / NULL pointers */
 #define MCT_E_GRT_NEEDED 2     /* >= 1 column has a low-velocity layer (surfmodes.f90:84-87,96-99): ierr=2 */
 #define MCT_E_TOO_MANY_LAYERS 3 /* a column needs more than MCT_MAX_LAYERS layers: ierr=3 */
-#define MCT_E_DEGENERATE_NUCLEI 4 /* > 12 coincident nuclei: the reference kd-tree build never terminates */
+#define MCT_E_DEGENERATE_NUCLEI 4 /* > 13 nuclei coincident in ALL coordinates: the reference kd-tree build never terminates
+                                     (nuclei that merely share one or two coordinates are fine: kdtree2.f90:818-826) */
 #define MCT_E_FLUID_BELOW_TOP 5 /* vs ~ 0 below the first layer: the reference `stop`s (surfmodes.f90:342-345): ierr=4 */
+#define MCT_E_ZERO_NOISE 6 /* misfit: a ray that carries data has sigma < 1e-10 (likelihood_surf.F90:387-390 raises an error) */
 #define MCT_E_NOINIT (-1)
 #define MCT_E_CUDA (-2)
 
@@ -109,6 +111,12 @@ int mct_voronoi_to_grid(const double* points, const double* params, int ncells, 
 int mct_voronoi_to_grid_dev(const double* points, const double* params, int ncells, const mct_grid* g,
                             const double box[6], const double* pm, double* d_vp, double* d_vs,
                             double* d_rho, int32_t* d_sites_id, void* stream);
+
+/* The *_dev entry points that run the nearest-nucleus kernel (mct_voronoi_to_grid_dev, mct_forward_eval_dev,
+ * mct_forward_batch_dev) cannot report a device-side condition without synchronising.  mct_k1_status synchronises
+ * `stream` and returns MCT_E_CUDA if the last such call on it overflowed the traversal stack of the tie replay
+ * (a tree deeper than 64 levels: never seen with kdtree2's mean splits), MCT_OK otherwise. */
+int mct_k1_status(void* stream);
 
 /* Index window of a box, exactly as mcmc_loc2.f90:2034-2045 computes it (1-based, clamped):
  * w = {ix0,ix1,iy0,iy1,iz0,iz1}. */
@@ -275,6 +283,42 @@ int mct_group_times_dev(const double* d_vel, int np, const mct_grid* g, const do
                         const int64_t* ray_offsets, int nrays, double* time, void* stream);
 int mct_session_group_times(mct_session* s, const double* ray_points, const int64_t* ray_offsets, int nrays,
                             double* time);
+/* mct_session_group_times integrates through like%gvel of the session's CURRENT (accepted) model: the group map
+ * when opt.phaseGroup == 1, the phase map otherwise (likelihood_surf.F90:226-230).  The _pending form does the same for
+ * the pending proposal -- its window maps overlaid on the resident ones -- which is where the sampler calls
+ * CalGroupTime (mcmc_loc2.f90:228 -> likelihood_surf.F90:350).  ray_points == NULL: the rays made resident by
+ * mct_session_set_rays (the reference's straight-ray mode sets its rays up once, likelihood_surf.F90:233-243). */
+int mct_session_group_times_pending(mct_session* s, const double* ray_points, const int64_t* ray_offsets, int nrays,
+                                    double* time);
+int mct_session_set_rays(mct_session* s, const double* ray_points, const int64_t* ray_offsets, int nrays);
+
+/* ---- the Gaussian misfit of surf_likelihood (src/likelihood_surf.F90:356-404) ----------------------------------
+ *   time     (nrr, np)     like%phaseTime(k,j,i) flattened over (k,j): nrr = nsrc*nrev, receiver index fastest
+ *   ttime    (nrr, 3, np)  dat%ttime: [.,1,.] observed time, [.,2,.] noise level (used when sigdep == 0)
+ *   raystat  (nrr, 2, np)  dat%raystat: [.,1,.] == 1 for a ray that carries data
+ *   snoise0/1 (np)         RTI%snoise0, RTI%snoise1 (sigdep /= 0: sigma = snoise0*srdist + snoise1); else NULL
+ *   srdist   (nrr, np)     like%srdist (sigdep /= 0); else NULL
+ *   nrays_total            dat%nrays
+ *   out[3]                 like%like, like%misfit, like%unweighted_misfit; sigma (nrr,np): like%sigma, optional
+ * Sums are accumulated in the reference's order (period, source, receiver): same bits.  Returns MCT_E_ZERO_NOISE
+ * where the reference raises 'The noise level is 0!'. */
+int mct_surf_misfit(const double* time, int nrr, int np, int sigdep, int nrays_total, const double* ttime,
+                    const int32_t* raystat, const double* snoise0, const double* snoise1, const double* srdist,
+                    double out[3], double* sigma);
+/* The same chained after CalGroupTime on a session's resident maps: observed data made resident once
+ * (mct_session_set_data), then per likelihood only the noise parameters go in and three doubles come out.
+ * pending = 0: the current model; 1: the pending proposal.  Rays as for mct_session_group_times.
+ * phase_time, sigma: optional host outputs (nrr, np). */
+int mct_session_set_data(mct_session* s, int nrr, int sigdep, int nrays_total, const double* ttime,
+                         const int32_t* raystat, const double* srdist);
+int mct_session_likelihood(mct_session* s, int pending, const double* ray_points, const int64_t* ray_offsets,
+                           int nrays, const double* snoise0, const double* snoise1, double out[3],
+                           double* phase_time, double* sigma);
+/* stat_rti (src/mcmc_loc2.f90:1966-1978): aveS += vs, stdS += vs**2, aveP += vp, stdP += vp**2 over the session's
+ * resident current model; the accumulators stay on the device until mct_session_stat_get. */
+int mct_session_stat_accumulate(mct_session* s);
+int mct_session_stat_get(mct_session* s, double* aveS, double* stdS, double* aveP, double* stdP, int64_t* nsamples);
+int mct_session_stat_reset(mct_session* s);
 
 #ifdef __cplusplus
 }

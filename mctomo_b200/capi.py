@@ -25,6 +25,7 @@ MCT_E_GRT_NEEDED = 2
 MCT_E_TOO_MANY_LAYERS = 3
 MCT_E_DEGENERATE_NUCLEI = 4
 MCT_E_FLUID_BELOW_TOP = 5
+MCT_E_ZERO_NOISE = 6
 MCT_E_NOINIT = -1
 MCT_E_CUDA = -2
 
@@ -511,6 +512,8 @@ class Session:
         self._pv = np.zeros(ncol * self.nout)      # staging for the largest possible window
         self._gv = np.zeros(ncol * self.nout)
         self._ie = np.zeros(ncol, np.int32)
+        self._nrays_resident = 0
+        self._nrr = 0
 
     def close(self):
         if self._h:
@@ -565,14 +568,69 @@ class Session:
         _check(self._L.mct_session_get_model(self._h, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, sid.ctypes.data))
         return vp, vs, rho, sid
 
-    def group_times(self, ray_points, ray_offsets, nrays):
-        """CalGroupTime on the resident group-velocity map: (np, nrays) travel times."""
+    def group_times(self, ray_points=None, ray_offsets=None, nrays=0, pending=False):
+        """CalGroupTime through like%gvel (group map when phaseGroup == 1, else phase map) of the current model, or of
+        the pending proposal (window maps overlaid): (np, nrays) travel times.  ray_points None: resident rays."""
+        fn = self._L.mct_session_group_times_pending if pending else self._L.mct_session_group_times
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        if ray_points is None:
+            nrays = self._nrays_resident
+            t = np.zeros((len(self.freqs), nrays))
+            _check(fn(self._h, None, None, 0, t.ctypes.data))
+            return t
         pts = _f64(ray_points)
         off = np.ascontiguousarray(ray_offsets, dtype=np.int64)
         t = np.zeros((len(self.freqs), nrays))
-        self._L.mct_session_group_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-        _check(self._L.mct_session_group_times(self._h, pts.ctypes.data, off.ctypes.data, nrays, t.ctypes.data))
+        _check(fn(self._h, pts.ctypes.data, off.ctypes.data, nrays, t.ctypes.data))
         return t
+
+    def set_rays(self, ray_points, ray_offsets, nrays):
+        pts = _f64(ray_points)
+        off = np.ascontiguousarray(ray_offsets, dtype=np.int64)
+        self._L.mct_session_set_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _check(self._L.mct_session_set_rays(self._h, pts.ctypes.data, off.ctypes.data, nrays))
+        self._nrays_resident = nrays
+
+    def set_data(self, ttime, raystat, sigdep=0, nrays_total=None, srdist=None):
+        """ttime (np,3,nrr), raystat (np,2,nrr) [C order == Fortran (nrr,3,np) / (nrr,2,np)], srdist (np,nrr)."""
+        tt = _f64(ttime)
+        rs = np.ascontiguousarray(raystat, dtype=np.int32)
+        sd = None if srdist is None else _f64(srdist)
+        nrr = tt.shape[-1]
+        if nrays_total is None:
+            nrays_total = int((rs[:, 0, :] == 1).sum())
+        self._nrr = nrr
+        self._L.mct_session_set_data.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(self._L.mct_session_set_data(self._h, nrr, sigdep, nrays_total, tt.ctypes.data, rs.ctypes.data, _ptr(sd)))
+
+    def likelihood(self, pending=False, rays=None, snoise0=None, snoise1=None, want_arrays=False):
+        """surf_likelihood's tail on the resident maps: dict(like, misfit, unweighted_misfit[, phase_time, sigma])."""
+        out = np.zeros(3)
+        n0 = None if snoise0 is None else _f64(snoise0)
+        n1 = None if snoise1 is None else _f64(snoise1)
+        pt = np.zeros((len(self.freqs), self._nrr)) if want_arrays else None
+        sg = np.zeros((len(self.freqs), self._nrr)) if want_arrays else None
+        self._L.mct_session_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]
+        if rays is None:
+            rp, ro, nr = None, None, 0
+        else:
+            rp, ro, nr = _f64(rays[0]), np.ascontiguousarray(rays[1], dtype=np.int64), int(rays[2])
+        rc = _check(self._L.mct_session_likelihood(self._h, 1 if pending else 0, _ptr(rp), _ptr(ro), nr, _ptr(n0), _ptr(n1),
+                                                   out.ctypes.data, _ptr(pt), _ptr(sg)), allow=(MCT_E_ZERO_NOISE,))
+        return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], phase_time=pt, sigma=sg, rc=rc)
+
+    def stat_accumulate(self):
+        self._L.mct_session_stat_accumulate.argtypes = [C.c_void_p]
+        _check(self._L.mct_session_stat_accumulate(self._h))
+
+    def stat_get(self):
+        g = self.grid
+        a = [np.zeros(g.shape) for _ in range(4)]
+        n = C.c_int64(0)
+        self._L.mct_session_stat_get.argtypes = [C.c_void_p] * 5 + [C.POINTER(C.c_int64)]
+        _check(self._L.mct_session_stat_get(self._h, *[x.ctypes.data for x in a], C.byref(n)))
+        return a, n.value
 
     def get_maps(self):
         g = self.grid
@@ -580,3 +638,23 @@ class Session:
         ie = np.zeros((g.nx, g.ny), np.int32)
         _check(self._L.mct_session_get_maps(self._h, pv.ctypes.data, gv.ctypes.data, ie.ctypes.data))
         return pv, gv, ie
+
+
+def surf_misfit(time, ttime, raystat, sigdep=0, nrays_total=None, snoise0=None, snoise1=None, srdist=None):
+    """mct_surf_misfit: the Gaussian misfit sums of likelihood_surf.F90:356-404 for HOST ray times (e.g. fm2d's).
+    time (np,nrr), ttime (np,3,nrr), raystat (np,2,nrr), srdist (np,nrr) [C order == Fortran (nrr,..,np)]."""
+    L = lib()
+    t, tt = _f64(time), _f64(ttime)
+    rs = np.ascontiguousarray(raystat, dtype=np.int32)
+    np_, nrr = t.shape
+    if nrays_total is None:
+        nrays_total = int((rs[:, 0, :] == 1).sum())
+    out = np.zeros(3)
+    sg = np.zeros((np_, nrr))
+    n0 = None if snoise0 is None else _f64(snoise0)
+    n1 = None if snoise1 is None else _f64(snoise1)
+    sd = None if srdist is None else _f64(srdist)
+    L.mct_surf_misfit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    rc = _check(L.mct_surf_misfit(t.ctypes.data, nrr, np_, sigdep, nrays_total, tt.ctypes.data, rs.ctypes.data, _ptr(n0), _ptr(n1),
+                                  _ptr(sd), out.ctypes.data, sg.ctypes.data), allow=(MCT_E_ZERO_NOISE,))
+    return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], sigma=sg, rc=rc)

@@ -6,8 +6,23 @@
 // contraction).
 #pragma once
 
-__device__ __forceinline__ double get_velocity_dev(const double* __restrict__ vel, int np, int ip, int nx, int ny, double xmin, double ymin,
-                                                   double dx, double dy, double px, double py) {
+// Optional overlay: a packed (np, wy, wx) window (a session's pending proposal) that replaces the resident map inside
+// columns ix0..ix0+wx-1, iy0..iy0+wy-1 (1-based); wx = 0: no overlay.
+struct VelOverlay {
+  const double* w;
+  int ix0, iy0, wx, wy;
+};
+
+__device__ __forceinline__ double vel_at(const double* __restrict__ vel, const VelOverlay& ov, int np, int ip, int ny, int iy /*1-based*/,
+                                         int ix /*1-based*/) {
+  const int ox = ix - ov.ix0, oy = iy - ov.iy0;
+  if ((unsigned)ox < (unsigned)ov.wx && (unsigned)oy < (unsigned)ov.wy)
+    return ov.w[(size_t)ip + (size_t)np * ((size_t)oy + (size_t)ov.wy * (size_t)ox)];
+  return vel[(size_t)ip + (size_t)np * ((size_t)(iy - 1) + (size_t)ny * (size_t)(ix - 1))];
+}
+
+__device__ __forceinline__ double get_velocity_dev(const double* __restrict__ vel, const VelOverlay& ov, int np, int ip, int nx, int ny,
+                                                   double xmin, double ymin, double dx, double dy, double px, double py) {
   int ix = (int)floor((px - xmin) / dx) + 1;
   int iy = (int)floor((py - ymin) / dy) + 1;
   if (ix < 1) ix = 1;
@@ -22,13 +37,13 @@ __device__ __forceinline__ double get_velocity_dev(const double* __restrict__ ve
 #pragma unroll
     for (int j = 1; j <= 2; ++j) {
       const double weight = (1.0 - fabs((double)(i - 1) * dx - dsx) / dx) * (1.0 - fabs((double)(j - 1) * dy - dsy) / dy);
-      qv = qv + weight * vel[(size_t)ip + (size_t)np * ((size_t)(iy + j - 2) + (size_t)ny * (size_t)(ix + i - 2))];
+      qv = qv + weight * vel_at(vel, ov, np, ip, ny, iy + j - 1, ix + i - 1);
     }
   return qv;
 }
 
-__global__ void __launch_bounds__(128) group_times_kernel(const double* __restrict__ vel, int np, int nx, int ny, double xmin, double ymin,
-                                                          double dx, double dy, const double* __restrict__ pts,
+__global__ void __launch_bounds__(128) group_times_kernel(const double* __restrict__ vel, const VelOverlay ov, int np, int nx, int ny,
+                                                          double xmin, double ymin, double dx, double dy, const double* __restrict__ pts,
                                                           const long long* __restrict__ off, int nrays, double* __restrict__ time) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)np * nrays) return;
@@ -37,13 +52,13 @@ __global__ void __launch_bounds__(128) group_times_kernel(const double* __restri
   double acc = 0.0;
   if (b - a >= 2) {
     double hx = pts[2 * a], hy = pts[2 * a + 1];
-    double vhead = get_velocity_dev(vel, np, ip, nx, ny, xmin, ymin, dx, dy, hx, hy);
+    double vhead = get_velocity_dev(vel, ov, np, ip, nx, ny, xmin, ymin, dx, dy, hx, hy);
     for (long long n = a + 1; n < b; ++n) {
       const double qx = pts[2 * n], qy = pts[2 * n + 1];
       const double ex = qx - hx, ey = qy - hy;
       double dist = ex * ex + ey * ey;
       dist = sqrt(dist);
-      const double vtail = get_velocity_dev(vel, np, ip, nx, ny, xmin, ymin, dx, dy, qx, qy);
+      const double vtail = get_velocity_dev(vel, ov, np, ip, nx, ny, xmin, ymin, dx, dy, qx, qy);
       acc = acc + dist * 2.0 / (vhead + vtail);
       vhead = vtail;
       hx = qx; hy = qy;
@@ -51,6 +66,30 @@ __global__ void __launch_bounds__(128) group_times_kernel(const double* __restri
   }
   time[t] = acc;
 }
+
+namespace {
+// rays -> device (packed), validated
+int upload_rays(const double* ray_points, const int64_t* ray_offsets, long long nt, DevBuf& d_pts, DevBuf& d_off, cudaStream_t st) {
+  const long long npts = ray_offsets[nt];
+  for (long long i = 0; i < nt; ++i)
+    if (ray_offsets[i + 1] < ray_offsets[i] || ray_offsets[i] < 0) return fail(MCT_E_INVALID_ARG, "group_times: offsets must be non-decreasing");
+  int rc;
+  if ((rc = ensure(d_pts, (size_t)std::max<long long>(npts, 1) * 16)) || (rc = ensure(d_off, (size_t)(nt + 1) * 8))) return rc;
+  if (npts > 0) CK(cudaMemcpyAsync(d_pts.p, ray_points, (size_t)npts * 16, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_off.p, ray_offsets, (size_t)(nt + 1) * 8, cudaMemcpyHostToDevice, st));
+  return MCT_OK;
+}
+int launch_group_times(const double* d_vel, const VelOverlay& ov, int np, const mct_grid* gr, const double* d_pts, const long long* d_off,
+                       int nrays, double* d_time, cudaStream_t st) {
+  const long long nt = (long long)np * nrays;
+  ProfScope ps(2, st);
+  group_times_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(d_vel, ov, np, gr->nx, gr->ny, gr->xmin, gr->ymin, gr->dx, gr->dy, d_pts,
+                                                                    d_off, nrays, d_time);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+} // namespace
 
 extern "C" {
 
@@ -65,35 +104,15 @@ int mct_group_times_dev(const double* d_vel, int np, const mct_grid* gr, const d
   if (gr->nx < 2 || gr->ny < 2) return fail(MCT_E_INVALID_ARG, "group_times: the bilinear stencil needs nx, ny >= 2");
   const long long nt = (long long)np * nrays;
   if (nt == 0) return MCT_OK;
-  const long long npts = ray_offsets[nt];
-  for (long long i = 0; i < nt; ++i)
-    if (ray_offsets[i + 1] < ray_offsets[i] || ray_offsets[i] < 0) return fail(MCT_E_INVALID_ARG, "group_times: offsets must be non-decreasing");
   cudaStream_t st = pick(stream);
   int rc;
-  if ((rc = ensure(g.ray_pts, (size_t)std::max<long long>(npts, 1) * 16)) || (rc = ensure(g.ray_off, (size_t)(nt + 1) * 8)) ||
-      (rc = ensure(g.ray_time, (size_t)nt * 8)))
+  if ((rc = upload_rays(ray_points, ray_offsets, nt, g.ray_pts, g.ray_off, st)) || (rc = ensure(g.ray_time, (size_t)nt * 8))) return rc;
+  const VelOverlay none = {nullptr, 0, 0, 0, 0};
+  if ((rc = launch_group_times(d_vel, none, np, gr, (const double*)g.ray_pts.p, (const long long*)g.ray_off.p, nrays, (double*)g.ray_time.p, st)))
     return rc;
-  if (npts > 0) CK(cudaMemcpyAsync(g.ray_pts.p, ray_points, (size_t)npts * 16, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(g.ray_off.p, ray_offsets, (size_t)(nt + 1) * 8, cudaMemcpyHostToDevice, st));
-  {
-    ProfScope ps(2, st);
-    group_times_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(d_vel, np, gr->nx, gr->ny, gr->xmin, gr->ymin, gr->dx, gr->dy,
-                                                                      (const double*)g.ray_pts.p, (const long long*)g.ray_off.p, nrays,
-                                                                      (double*)g.ray_time.p);
-  }
-  CK(cudaGetLastError());
-  g.host_stats.n_launches += 1;
   CK(cudaMemcpyAsync(time, g.ray_time.p, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MCT_OK;
-}
-
-// the same on a session's resident group-velocity map
-int mct_session_group_times(mct_session* s, const double* ray_points, const int64_t* ray_offsets, int nrays, double* time) {
-  NEED_INIT();
-  if (!s) return fail(MCT_E_INVALID_ARG, "session_group_times: NULL session");
-  if (s->nout != s->np) return fail(MCT_E_INVALID_ARG, "session_group_times: needs a single-mode session (the reference's likelihood uses the fundamental mode)");
-  return mct_group_times_dev((const double*)s->gvel.p, s->np, &s->gr, ray_points, ray_offsets, nrays, time, nullptr);
 }
 
 } // extern "C"

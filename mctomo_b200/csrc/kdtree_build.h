@@ -17,7 +17,7 @@ struct HostKdTree {
   std::vector<int32_t> ind;  // position -> original 1-based index
   std::vector<double> rpts;  // rearranged coordinates (3, n)
   int root = -1;
-  bool degenerate = false;   // the Fortran build would never terminate (> 13 coincident points)
+  bool degenerate = false;   // the Fortran build would never terminate (> 13 points coincident in all dimensions)
 };
 
 class KdBuilder {
@@ -29,7 +29,7 @@ class KdBuilder {
     t_.ind.resize(n_);
     for (int j = 0; j < n_; ++j) t_.ind[j] = j + 1;
     t_.degenerate = false;
-    t_.root = range(0, n_ - 1, -1);
+    t_.root = range(0, n_ - 1, -1, 0);
     t_.rpts.resize(3 * (size_t)n_);
     for (int i = 0; i < n_; ++i)
       for (int d = 0; d < 3; ++d) t_.rpts[3 * (size_t)i + d] = p_[3 * (size_t)(t_.ind[i] - 1) + d];
@@ -37,6 +37,7 @@ class KdBuilder {
 
  private:
   static constexpr int kBucket = 12;
+  static constexpr int kMaxChain = 32;
   double coord(int d, int pos) const { return p_[3 * (size_t)(t_.ind[pos] - 1) + d]; }
 
   // min/max of coordinate d over positions l..u, scanning in pairs like spread_in_coordinate
@@ -68,7 +69,8 @@ class KdBuilder {
     return (coord(d, lb) <= alpha) ? lb : lb - 1;
   }
 
-  int range(int l, int u, int parent) {
+  // chain = number of consecutive ancestors whose split left one child empty (same l..u handed down)
+  int range(int l, int u, int parent, int chain) {
     if (u < l) return -1;
     const int id = (int)t_.nodes.size();
     t_.nodes.emplace_back();
@@ -99,13 +101,27 @@ class KdBuilder {
     for (int i = l; i <= u; ++i) sum += coord(c, i);
     const double mean = sum / (double)(u - l + 1);
     const int m = partition(c, mean, l, u);
-    if (m >= u || m < l) { t_.degenerate = true; return id; }
+    // A split that leaves one side empty (every coordinate of the node equal along the chosen -- inherited, hence
+    // over-estimated -- box dimension) is legal in kdtree2: the node keeps its single child, takes over the child's
+    // box (:818-826), and the child re-measures that dimension and cuts along another one.  The search treats such
+    // a node as terminal and scans its whole range l..u (:1388).  Only when the points of the range coincide in
+    // every dimension does the Fortran recurse for ever; a chain of kMaxChain one-child levels is reported instead.
+    const bool one_child = (m >= u || m < l);
+    if (one_child && chain >= kMaxChain) { t_.degenerate = true; return id; }
     t_.nodes[id].cut_dim = c;
-    const int left = range(l, m, id);
-    const int right = range(m + 1, u, id);
+    const int left = range(l, m, id, one_child ? chain + 1 : 0);
+    const int right = t_.degenerate ? -1 : range(m + 1, u, id, one_child ? chain + 1 : 0);
+    if (t_.degenerate) return id;
     KdNodeDev& N = t_.nodes[id];
     N.left = left;
     N.right = right;
+    if (right < 0 || left < 0) {
+      const KdNodeDev& A = t_.nodes[right < 0 ? left : right];
+      for (int d = 0; d < 3; ++d) { N.lo[d] = A.lo[d]; N.up[d] = A.up[d]; }
+      if (right < 0) { N.cut_left = A.up[c]; N.cut_val = N.cut_left; }
+      else { N.cut_right = A.lo[c]; N.cut_val = N.cut_right; }
+      return id;
+    }
     const KdNodeDev& A = t_.nodes[left];
     const KdNodeDev& B = t_.nodes[right];
     N.cut_right = B.lo[c];

@@ -56,6 +56,8 @@ struct Ctx {
   DevBuf m_vp, m_vs, m_rho, m_sites;
   // layered columns, their processing order, sort scratch
   DevBuf lay, layr, nlay, status, perm, bins;
+  bool k1_smem_set = false; // dynamic shared-memory opt-in of k1_column_kernel done on this device
+  cudaEvent_t stage_ev = nullptr; // last use of the pinned nuclei staging block (pin_small)
   int k1_mode = 0;          // 0 culled brute force per column (+ tree replay for ties), 1 tree walk for every node
   int k2_mode = 0;          // 0 auto, 1 always one thread per column, 2 always one warp per column
   int k2_coop_max = 0;      // auto mode: batches below this many columns take the lane-cooperative kernels
@@ -167,7 +169,7 @@ int upload_nuclei(const double* points, const double* params, const long long* o
     if (n < 1) return fail(MCT_E_INVALID_ARG, "nuclei: model %d has no cells", b);
     KdBuilder(points + 3 * offsets[b], (int)n, g.tree).run();
     if (g.tree.degenerate)
-      return fail(MCT_E_DEGENERATE_NUCLEI, "model %d: more than 13 nuclei coincide: the reference kd-tree build does not terminate", b);
+      return fail(MCT_E_DEGENERATE_NUCLEI, "model %d: more than 13 nuclei coincide in all three coordinates: the reference kd-tree build does not terminate", b);
     g.node_off[b] = (long long)all_nodes.size();
     g.pt_off[b] = offsets[b] - o0;
     g.roots[b] = g.tree.root;
@@ -192,7 +194,9 @@ int upload_nuclei(const double* points, const double* params, const long long* o
   // one pinned staging block so the five small copies are true async DMA
   const size_t tot = nb_nodes + 2 * nb_pts + nb_ind + nb_km;
   if ((rc = ensure_pin(g.pin_small, tot))) return rc;
-  CK(cudaStreamSynchronize(st)); // the staging block may still be in flight from the previous call
+  // the staging block may still be in flight from the previous call -- possibly on another stream: wait for the
+  // event recorded after its last use, not for the caller's stream
+  if (g.stage_ev) CK(cudaEventSynchronize(g.stage_ev));
   char* h = (char*)g.pin_small.p;
   memcpy(h, all_nodes.data(), nb_nodes);
   memcpy(h + nb_nodes, all_rpts.data(), nb_pts);
@@ -204,6 +208,8 @@ int upload_nuclei(const double* points, const double* params, const long long* o
   CK(cudaMemcpyAsync(g.params.p, h + nb_nodes + nb_pts, nb_pts, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(g.kmodels.p, h + nb_nodes + 2 * nb_pts, nb_km, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(g.ind.p, h + nb_nodes + 2 * nb_pts + nb_km, nb_ind, cudaMemcpyHostToDevice, st));
+  if (!g.stage_ev) CK(cudaEventCreateWithFlags(&g.stage_ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(g.stage_ev, st));
   g.nset = nb;
   return MCT_OK;
 }
@@ -274,10 +280,9 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
     if (g.k1_mode == 1) {
       k1_voronoi_kernel<<<grid_blocks(total, 256, 16), 256, 0, st>>>(P); // exact tree walk for every node
     } else {
-      static bool smem_set = false;
-      if (!smem_set) {
+      if (!g.k1_smem_set) {
         CK(cudaFuncSetAttribute(k1_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1C_SMEM_BYTES));
-        smem_set = true;
+        g.k1_smem_set = true;
       }
       const long long ntiles = (long long)((P.wx + K1C_TILE - 1) / K1C_TILE) * ((P.wy + K1C_TILE - 1) / K1C_TILE);
       const int nby = batched ? nbatch : 1;
@@ -494,6 +499,8 @@ int forward_core(const mct_grid* gr, int nb, int derive_vp_rho, const DispPlan& 
   return disp_core(d_vp, d_vs, d_rho, gr, pl, freqs, np, opt, true, cw, d_pvel, d_gvel, d_ierr, d_flags, st);
 }
 
+void release_misfit_globals(); // k4_misfit.cuh
+
 int flags_to_code(int maxst) {
   return maxst == 2 ? MCT_E_GRT_NEEDED : (maxst == 3 ? MCT_E_TOO_MANY_LAYERS : MCT_E_FLUID_BELOW_TOP);
 }
@@ -566,9 +573,13 @@ int mct_shutdown(void) {
   DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins,
                     &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.ray_pts, &g.ray_off, &g.ray_time};
   for (DevBuf* b : bufs) release(*b);
+  release_misfit_globals();
   release(g.pin_a);
   release(g.pin_b);
   release(g.pin_small);
+  if (g.stage_ev) cudaEventDestroy(g.stage_ev);
+  g.stage_ev = nullptr;
+  g.k1_smem_set = false;
   cudaStreamDestroy(g.stream);
   g.stream = nullptr;
   g.init = false;
@@ -616,7 +627,18 @@ int mct_voronoi_to_grid_dev(const double* points, const double* params, int ncel
   if (rc) return rc;
   int32_t w[6];
   box_window(gr, box, w);
+  CK(cudaMemsetAsync((int32_t*)g.flags.p + 2, 0, sizeof(int32_t), st)); // read back by mct_k1_status()
   return launch_k1(gr, w, pm, d_vp, d_vs, d_rho, d_sites_id, 1, 1, 1, gr->ny, gr->nz, st);
+}
+
+int mct_k1_status(void* stream) {
+  NEED_INIT();
+  cudaStream_t st = pick(stream);
+  int32_t k1err = 0;
+  CK(cudaMemcpyAsync(&k1err, (int32_t*)g.flags.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (k1err) return fail(MCT_E_CUDA, "nearest-nucleus traversal stack overflow (tree deeper than %d)", K1_STACK);
+  return MCT_OK;
 }
 
 int mct_voronoi_to_grid(const double* points, const double* params, int ncells, const mct_grid* gr, const double box[6],
@@ -1105,3 +1127,4 @@ int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, 
 
 #include "mct_session.cuh" // mct_session_*: a chain's model resident in HBM between proposals
 #include "k3_raytime.cuh"  // mct_group_times_dev: CalGroupTime on the device map
+#include "k4_misfit.cuh"   // misfit sums, session likelihood / ray times / stat_rti accumulation

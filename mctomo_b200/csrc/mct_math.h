@@ -275,4 +275,41 @@ MCT_HD double mct_pow025(double x) {
   return MCT_ADD(y, corr);
 }
 
+
+/* log(x) for finite x > 0 (natural logarithm; the misfit's sum(log(sigma)), src/likelihood_surf.F90:404).
+ * fdlibm's e_log.c scheme with explicit IEEE operations: x = 2^k (1+f), sqrt(2)/2 < 1+f < sqrt(2);
+ * s = f/(2+f); log(1+f) = f - (f^2/2 - s (f^2/2 + R(s^2))); < 1 ulp.  Subnormal x is scaled by 2^54 first.
+ * x <= 0, NaN and Inf are the caller's business (the kernels check sigma >= EPS before taking its logarithm). */
+MCT_HD double mct_log(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+               Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+               Lg7 = 1.479819860511658591e-01;
+  uint64_t u = mct_d2bits(x);
+  int32_t k = 0;
+  if ((u >> 52) == 0) { /* subnormal */
+    x = MCT_MUL(x, 18014398509481984.0); /* 2^54 */
+    u = mct_d2bits(x);
+    k = -54;
+  }
+  uint32_t hx = (uint32_t)(u >> 32);
+  k += (int32_t)(hx >> 20) - 1023;
+  hx &= 0x000fffffu;
+  const uint32_t i = (hx + 0x95f64u) & 0x100000u; /* 1 when the mantissa exceeds sqrt(2): halve it */
+  k += (int32_t)(i >> 20);
+  u = ((uint64_t)(hx | (i ^ 0x3ff00000u)) << 32) | (u & 0xffffffffull);
+  const double f = MCT_ADD(mct_bits2d(u), -1.0);
+  const double dk = (double)k;
+  const double s = MCT_DIV(f, MCT_ADD(2.0, f));
+  const double z = MCT_MUL(s, s);
+  const double w = MCT_MUL(z, z);
+  const double t1 = MCT_MUL(w, MCT_FMA(w, MCT_FMA(w, Lg6, Lg4), Lg2));
+  const double t2 = MCT_MUL(z, MCT_FMA(w, MCT_FMA(w, MCT_FMA(w, Lg7, Lg5), Lg3), Lg1));
+  const double R = MCT_ADD(t2, t1);
+  const double hfsq = MCT_MUL(0.5, MCT_MUL(f, f));
+  /* k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f) */
+  const double inner = MCT_ADD(MCT_MUL(s, MCT_ADD(hfsq, R)), MCT_MUL(dk, ln2_lo));
+  return MCT_ADD(MCT_MUL(dk, ln2_hi), -MCT_ADD(MCT_ADD(hfsq, -inner), -f));
+}
+
 #endif /* MCT_MATH_H */

@@ -12,6 +12,13 @@
 // cost, because the whole grid is already there.
 #pragma once
 
+// device copies of the likelihood's data (T_DATA%ttime, %raystat, like%srdist) and its work arrays: k4_misfit.cuh
+struct MisfitBufs {
+  DevBuf ttime, raystat, srdist, snoise, sigma, terms, out, time;
+  int nrr = 0, np = 0, sigdep = 0, nrays_total = 0;
+  bool have = false;
+};
+
 struct mct_session {
   mct_grid gr;
   mct_disp_opts opt;
@@ -22,7 +29,15 @@ struct mct_session {
   DevBuf b_vp, b_vs, b_rho, b_sites;  // packed backup of the last proposal's box
   DevBuf w_pvel, w_gvel, w_ierr;      // packed maps of the last proposal's window
   DevBuf flags;                       // int32[2]
+  DevBuf r_pts, r_off;                // resident rays (straight-ray mode: set once), packed like mct_group_times_dev's
+  int r_nrays = 0;
+  DevBuf time;                        // ray times of the last group_times / likelihood call, (nrays, np)
+  int time_nrays = 0;
+  MisfitBufs mf;                      // observed data + misfit work arrays
+  DevBuf acc;                         // stat_rti accumulators: aveS, stdS, aveP, stdP, (nz,ny,nx) each
+  long long nacc = 0;
   bool have_model = false, pending = false;
+  bool maps_valid = false;            // the resident maps belong to a model check_model accepted
   int32_t pbox[6] = {0, 0, 0, 0, 0, 0}; // node window of the pending proposal
   int32_t pwin[4] = {0, 0, 0, 0};       // its column window (with halo)
   int pinvalid = 0, pcode = 0;
@@ -76,9 +91,14 @@ __global__ void __launch_bounds__(256) maps_commit_kernel(const double* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) fill_kernel(double* p, long long n, double v) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) p[t] = v;
+}
+
 void session_release(mct_session* s) {
   DevBuf* bufs[] = {&s->vp, &s->vs, &s->rho, &s->sites, &s->pvel, &s->gvel, &s->ierr, &s->b_vp, &s->b_vs, &s->b_rho,
-                    &s->b_sites, &s->w_pvel, &s->w_gvel, &s->w_ierr, &s->flags};
+                    &s->b_sites, &s->w_pvel, &s->w_gvel, &s->w_ierr, &s->flags, &s->r_pts, &s->r_off, &s->time, &s->acc,
+                    &s->mf.ttime, &s->mf.raystat, &s->mf.srdist, &s->mf.snoise, &s->mf.sigma, &s->mf.terms, &s->mf.out, &s->mf.time};
   for (DevBuf* b : bufs) release(*b);
 }
 
@@ -109,6 +129,15 @@ int mct_session_create(const mct_grid* gr, const double* freqs, int np, const mc
     delete s;
     return rc;
   }
+  // Until a valid model is set the maps hold the reference's presets (likelihood_surf.F90:186-191; 0 in the
+  // multi-mode twin), never raw memory.
+  fill_kernel<<<grid_blocks((long long)(nc * pl.nout), 256, 8), 256, 0, g.stream>>>((double*)s->pvel.p, (long long)(nc * pl.nout),
+                                                                                   opt->nmodes <= 0 ? opt->preset : 0.0);
+  fill_kernel<<<grid_blocks((long long)(nc * pl.nout), 256, 8), 256, 0, g.stream>>>((double*)s->gvel.p, (long long)(nc * pl.nout),
+                                                                                   opt->nmodes <= 0 ? opt->preset : 0.0);
+  cudaMemsetAsync(s->ierr.p, 0, nc * 4, g.stream);
+  if (cudaGetLastError() != cudaSuccess) { session_release(s); delete s; return fail(MCT_E_CUDA, "session_create: initialising the maps failed"); }
+  g.host_stats.n_launches += 2;
   *out = s;
   return MCT_OK;
 }
@@ -149,6 +178,7 @@ int mct_session_set_model(mct_session* s, const double* points, const double* pa
   if (hf[2]) return fail(MCT_E_CUDA, "nearest-nucleus traversal stack overflow (tree deeper than %d)", K1_STACK);
   if (model_invalid) *model_invalid = hf[0];
   s->have_model = true; // (an invalid model is still the current model: its maps are simply not solved)
+  s->maps_valid = !hf[0] && hf[1] < 2;
   if (!hf[0] && hf[1] >= 2) return fail(flags_to_code(hf[1]), "dispersion: at least one column reported condition %d (see ierr)", hf[1]);
   return MCT_OK;
 }
@@ -179,6 +209,7 @@ int mct_session_propose(mct_session* s, const double* points, const double* para
     win[0] = win[2] = 1; win[1] = win[3] = 0;
     memcpy(s->pwin, win, 4 * sizeof(int32_t));
     s->pinvalid = 0;
+    s->pcode = 0;
     s->pending = true;
     return MCT_OK;
   }
@@ -223,6 +254,7 @@ int mct_session_propose(mct_session* s, const double* points, const double* para
   CK(cudaStreamSynchronize(st));
   if (hf[2]) return fail(MCT_E_CUDA, "nearest-nucleus traversal stack overflow (tree deeper than %d)", K1_STACK);
   s->pinvalid = hf[0];
+  s->pcode = hf[0] ? 0 : hf[1];
   *model_invalid = hf[0];
   if (!hf[0] && hf[1] >= 2) return fail(flags_to_code(hf[1]), "dispersion: at least one column reported condition %d (see ierr)", hf[1]);
   return MCT_OK;

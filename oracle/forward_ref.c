@@ -212,3 +212,46 @@ void orc_cal_group_time(const double* vel, int np, int nx, int ny, double xmin, 
       time[(size_t)ip * nrays + r] = t;
     }
 }
+
+/* The Gaussian misfit of surf_likelihood (likelihood_surf.F90:356-404).  Arrays in the Fortran layout:
+ * time (nrr,np) = like%phaseTime(k,j,i) flattened over (k,j); ttime (nrr,3,np); raystat (nrr,2,np); srdist (nrr,np);
+ * snoise0/1 (np).  out = {like, misfit, unweighted_misfit}; sigma (nrr,np) out.  Returns 6 where the reference raises
+ * 'The noise level is 0!' (:387-390), else 0.  math_mode 1: log from mct_math.h (what the device uses), 0: libm. */
+int orc_surf_misfit(const double* time, int nrr, int np, int sigdep, int nrays_total, const double* ttime, const int* raystat,
+                    const double* snoise0, const double* snoise1, const double* srdist, int math_mode, double* out, double* sigma) {
+  const double EPS = (double)1.0E-10f; /* real(ii10), parameter :: EPS = 1.0E-10 (:37) */
+  const double PI2 = (double)6.283185f; /* :36 */
+  int bad = 0;
+  /* noise level, :357-373 */
+  for (int i = 0; i < np; ++i)
+    for (int r = 0; r < nrr; ++r) {
+      const size_t t = (size_t)r + (size_t)nrr * i;
+      if (sigdep != 0) {
+        if (raystat[(size_t)r + (size_t)nrr * 2 * i] == 1) sigma[t] = snoise0[i] * srdist[t] + snoise1[i];
+        else sigma[t] = 1.0;
+      } else {
+        sigma[t] = ttime[(size_t)r + (size_t)nrr * (1 + 3 * (size_t)i)];
+      }
+    }
+  double like = 0, misfit = 0, unw = 0;
+  for (int i = 0; i < np; ++i)
+    for (int r = 0; r < nrr; ++r) { /* nrr runs over j (sources) then k (receivers), receiver fastest: :381-385 */
+      const size_t t = (size_t)r + (size_t)nrr * i;
+      if (raystat[(size_t)r + (size_t)nrr * 2 * i] == 1) {
+        if (sigma[t] < EPS) bad = 1;
+        const double d = time[t] - ttime[(size_t)r + (size_t)nrr * 3 * (size_t)i];
+        like = like + (d * d) / (2 * (sigma[t] * sigma[t]));
+        misfit = misfit + (d * d) / (sigma[t] * sigma[t]);
+        unw = unw + (d * d);
+      } else {
+        sigma[t] = 1.0;
+      }
+    }
+  double slog = 0;
+  for (size_t t = 0; t < (size_t)nrr * np; ++t) slog = slog + (math_mode ? mct_log(sigma[t]) : log(sigma[t]));
+  like = like + slog + (double)((float)nrays_total / 2.0f) * (math_mode ? mct_log(PI2) : log(PI2));
+  out[0] = like; out[1] = misfit; out[2] = unw;
+  return bad ? 6 : 0;
+}
+
+double orc_mct_log(double x) { return mct_log(x); }

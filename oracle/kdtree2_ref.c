@@ -101,7 +101,7 @@ static int new_node(ktree* T) {
 }
 
 /* build_tree_for_range: kdtree2.f90:704-840.  parent = -1 for the root. */
-static int build_range(ktree* T, int l, int u, int parent) {
+static int build_range(ktree* T, int l, int u, int parent, int chain) {
   if (u < l) return -1;
   int id = new_node(T);
   if ((u - l) <= BUCKET) {
@@ -135,9 +135,11 @@ static int build_range(ktree* T, int l, int u, int parent) {
   double average = sum / (double)(u - l + 1);
   T->nodes[id].cut_val = average;
   int m = select_value(T, c, average, l, u);
-  if (m >= u || m < l) {
-    /* A child would cover the parent's whole range again: the Fortran recurses until the stack
-     * overflows (happens when > bucket_size points coincide).  Report instead of crashing. */
+  /* An empty side is legal (kdtree2.f90:818-826: the node keeps its one child and the child's box; the search
+   * then treats it as terminal, :1388).  Only points coincident in EVERY dimension make the Fortran recurse
+   * for ever: a chain of 32 one-child levels over the same range is reported instead of overflowing the stack. */
+  int one_child = (m >= u || m < l);
+  if (one_child && chain >= 32) {
     T->fail = 1;
     T->nodes[id].l = l;
     T->nodes[id].u = u;
@@ -146,8 +148,9 @@ static int build_range(ktree* T, int l, int u, int parent) {
   T->nodes[id].cut_dim = c;
   T->nodes[id].l = l;
   T->nodes[id].u = u;
-  int left = build_range(T, l, m, id);
-  int right = build_range(T, m + 1, u, id);
+  int left = build_range(T, l, m, id, one_child ? chain + 1 : 0);
+  int right = T->fail ? -1 : build_range(T, m + 1, u, id, one_child ? chain + 1 : 0);
+  if (T->fail) return id;
   knode* N = &T->nodes[id]; /* (re-fetch: realloc may have moved the array) */
   N->left = left;
   N->right = right;
@@ -179,7 +182,7 @@ void* orc_kdtree2_create(const double* points, int n) {
   T->data = points;
   T->ind = (int*)malloc(sizeof(int) * (size_t)(n + 1));
   for (int j = 1; j <= n; ++j) T->ind[j] = j;
-  T->root = build_range(T, 1, n, -1);
+  T->root = build_range(T, 1, n, -1, 0);
   if (T->fail) { free(T->ind); free(T->nodes); free(T); return NULL; }
   T->rdata = (double*)malloc(sizeof(double) * DIM * (size_t)n);
   for (int i = 1; i <= n; ++i)

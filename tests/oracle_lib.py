@@ -204,3 +204,23 @@ def cal_group_time(vel, grid, ray_points, ray_offsets, nrays):
     L().orc_cal_group_time(vel.ctypes.data, np_, grid.nx, grid.ny, grid.xmin, grid.ymin, grid.dx, grid.dy, pts.ctypes.data,
                            off.ctypes.data, nrays, t.ctypes.data)
     return t
+
+
+def surf_misfit(time, ttime, raystat, sigdep=0, nrays_total=None, snoise0=None, snoise1=None, srdist=None, math_mode=PORTABLE):
+    """The Gaussian misfit of likelihood_surf.F90:356-404.  time (np,nrr), ttime (np,3,nrr), raystat (np,2,nrr),
+    srdist (np,nrr) in C order (== the Fortran (nrr,..,np) arrays)."""
+    t, tt = f64(time), f64(ttime)
+    rs = np.ascontiguousarray(raystat, dtype=np.int32)
+    np_, nrr = t.shape
+    if nrays_total is None:
+        nrays_total = int((rs[:, 0, :] == 1).sum())
+    out, sg = np.zeros(3), np.zeros((np_, nrr))
+    n0 = None if snoise0 is None else f64(snoise0)
+    n1 = None if snoise1 is None else f64(snoise1)
+    sd = None if srdist is None else f64(srdist)
+    fn = L().orc_surf_misfit
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+    p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    rc = fn(t.ctypes.data, nrr, np_, sigdep, nrays_total, tt.ctypes.data, rs.ctypes.data, p(n0), p(n1), p(sd), math_mode,
+            out.ctypes.data, sg.ctypes.data)
+    return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], sigma=sg, rc=rc)

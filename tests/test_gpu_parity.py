@@ -5,6 +5,8 @@ within 1e-5 km/s of surfdisp96; identical ierr / mode counts.  Against the oracl
 (same sin/cos/exp as the device) the stronger statement is tested: every output and both work counters
 are bit-identical.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -102,6 +104,19 @@ def test_k1_many_nuclei_and_thin_window(mct):
     box = np.array([-5.0, -5.0, 6.0, 5.0, 5.0, 6.05])
     g, o = _both_k1(mct, pts, par, grid, box)
     _assert_k1_equal(g, o)
+
+
+def test_k1_one_child_tree_nodes(mct):
+    """Nuclei sharing a coordinate (a line, a plane, a cluster of duplicates): kdtree2's split leaves one child empty,
+    the node keeps its single child and is scanned as a terminal (kdtree2.f90:818-826,1388).  The oracle is pinned on
+    these sets against kdtree2.o (fixtures collinear / plane / dup12); the library must accept them and agree."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kdtree2_ref.npz"))
+    grid = Grid(21, 19, 23, -0.1, 1.1, -0.1, 1.1, -0.1, 1.1)
+    for case in ("collinear", "plane", "dup12"):
+        nuc = np.ascontiguousarray(g[f"{case}_points"])
+        par = np.stack([np.arange(len(nuc)) + 1.0, np.arange(len(nuc)) + 0.5, np.ones(len(nuc))], 1)
+        a, o = _both_k1(mct, nuc, par, grid, grid.full_box())
+        _assert_k1_equal(a, o)
 
 
 def test_k1_degenerate_nuclei_reported(mct):

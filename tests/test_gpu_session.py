@@ -178,6 +178,127 @@ def test_group_times_on_resident_map(mct):
     S.close()
 
 
+def _straight_rays(grid, src, rev, np_, raystat):
+    """setup_straightRays (likelihood_surf.F90:408-452): points every dl = min(dx,dy)/2 from source to receiver."""
+    dl = min(grid.dx, grid.dy) / 2
+    pts, off, dist = [], [0], np.zeros((np_, len(src) * len(rev)))
+    for i in range(np_):
+        n = 0
+        for j in range(len(src)):
+            for k in range(len(rev)):
+                dx, dy = rev[k, 0] - src[j, 0], rev[k, 1] - src[j, 1]
+                ds = np.sqrt(dx ** 2 + dy ** 2)
+                dist[i, n] = ds
+                if raystat[i, 0, n] == 1:
+                    m = int(np.floor(ds / dl)) + 1
+                    p = np.zeros((m, 2))
+                    for l in range(1, m):
+                        p[l - 1] = [src[j, 0] + (l - 1) * dl * dx / ds, src[j, 1] + (l - 1) * dl * dy / ds]
+                    p[m - 1] = rev[k]
+                    pts.append(p)
+                    off.append(off[-1] + m)
+                else:
+                    off.append(off[-1])
+                n += 1
+    return np.concatenate(pts), np.array(off, np.int64), dist
+
+
+@pytest.mark.parametrize("phaseGroup,sigdep", [(1, 0), (0, 1)])
+def test_session_likelihood_straight_rays(mct, phaseGroup, sigdep):
+    """The whole surface-wave likelihood of the reference's straight-ray mode (likelihood_surf.F90:226-243,356-404) on
+    the resident maps: CalGroupTime through like%gvel (= pvel when phaseGroup /= 1: ADVICE r1) + sigma + the Gaussian
+    sums, for the current model and for a PENDING proposal (window maps overlaid), bit-identical to the restatement."""
+    grid = synth.make_grid(22, 20, 24)
+    freqs = synth.freqs(5)
+    np_ = len(freqs)
+    S = mct.Session(grid, freqs, disp_opts(raylov=1, phaseGroup=phaseGroup, nmodes=0))
+    pts, par = synth.generate_model(grid, 30, 77)
+    r0 = S.set_model(pts, par)
+    rng = np.random.default_rng(5)
+    src = rng.uniform([-4, -4], [4, 4], (4, 2))
+    rev = rng.uniform([-4, -4], [4, 4], (6, 2))
+    nrr = 24
+    raystat = np.zeros((np_, 2, nrr), np.int32)
+    raystat[:, 0, :] = rng.uniform(size=(np_, nrr)) < 0.8
+    ttime = np.zeros((np_, 3, nrr))
+    ttime[:, 0, :] = rng.uniform(1.0, 4.0, (np_, nrr))
+    ttime[:, 1, :] = rng.uniform(0.05, 0.3, (np_, nrr))
+    rp, ro, dist = _straight_rays(grid, src, rev, np_, raystat)
+    sn0, sn1 = rng.uniform(0.01, 0.05, np_), rng.uniform(0.02, 0.1, np_)
+    S.set_rays(rp, ro, nrr)
+    S.set_data(ttime, raystat, sigdep=sigdep, srdist=dist)
+    kw = dict(snoise0=sn0, snoise1=sn1) if sigdep else {}
+
+    def ref(maps):
+        t = orc.cal_group_time(maps, grid, rp, ro, nrr)
+        return t, orc.surf_misfit(t, ttime, raystat, sigdep=sigdep, srdist=dist, **kw)
+
+    cur_map = r0["gvel"] if phaseGroup == 1 else r0["pvel"]
+    t_ref, m_ref = ref(cur_map)
+    got = S.likelihood(want_arrays=True, **kw)
+    assert np.array_equal(got["phase_time"], t_ref) and np.array_equal(got["sigma"], m_ref["sigma"])
+    for k in ("like", "misfit", "unweighted_misfit"):
+        assert got[k] == m_ref[k], k
+    assert np.array_equal(S.group_times(), t_ref)
+    # pending proposal: move one nucleus, evaluate its likelihood before deciding
+    pts2 = pts.copy()
+    pts2[3] += [0.7, -0.5, 0.4]
+    box = np.array([-5.0, -5.0, 0.0, 5.0, 5.0, 12.0])
+    pr = S.propose(pts2, par, box)
+    assert pr["model_invalid"] == 0
+    full = mct.forward_eval(pts2, par, grid, freqs, disp_opts(raylov=1, phaseGroup=phaseGroup, nmodes=0))
+    t_ref2, m_ref2 = ref(full["gvel"] if phaseGroup == 1 else full["pvel"])
+    got2 = S.likelihood(pending=True, want_arrays=True, **kw)
+    assert np.array_equal(got2["phase_time"], t_ref2)
+    assert got2["like"] == m_ref2["like"] and got2["misfit"] == m_ref2["misfit"]
+    with pytest.raises(mct.MctError):
+        S.likelihood(**kw)                      # the current model is not addressable while a proposal is pending
+    S.reject()
+    got3 = S.likelihood(**kw)
+    assert got3["like"] == m_ref["like"]
+    # host-time entry point (fm2d's times) and the zero-noise condition
+    h = mct.surf_misfit(t_ref, ttime, raystat, sigdep=sigdep, srdist=dist, **kw)
+    assert h["like"] == m_ref["like"] and h["rc"] == 0
+    if sigdep == 0:
+        tt0 = ttime.copy()
+        tt0[0, 1, np.argmax(raystat[0, 0] == 1)] = 0.0
+        assert mct.surf_misfit(t_ref, tt0, raystat)["rc"] == mct.MCT_E_ZERO_NOISE
+        assert orc.surf_misfit(t_ref, tt0, raystat)["rc"] == 6
+    S.close()
+
+
+def test_session_invalid_initial_model_and_stat_accumulation(mct):
+    """a session whose first model check_model rejects must not expose raw memory; stat_rti's sums."""
+    grid = synth.make_grid(10, 9, 12)
+    freqs = synth.freqs(4)
+    S = mct.Session(grid, freqs, disp_opts())
+    pts, par = synth.generate_model(grid, 12, 3)
+    bad = par.copy()
+    top = np.argmin(pts[:, 2])
+    bad[top, 1] = 9.0                                   # fastest cell on top: vs(k) < vs(1) below it
+    r = S.set_model(pts, bad)
+    assert r["model_invalid"] == 1
+    pv, gv, ie = S.get_maps()
+    assert (pv == 100.0).all() and (gv == 100.0).all() and (ie == 0).all()
+    with pytest.raises(mct.MctError):
+        S.group_times(np.zeros((2, 2)), np.array([0, 2] + [2] * (len(freqs) - 1), np.int64), 1)
+    r = S.set_model(pts, par)
+    assert r["model_invalid"] == 0
+    acc = [np.zeros(grid.shape) for _ in range(4)]
+    for it in range(3):
+        p2 = pts.copy()
+        p2[it] += 0.3
+        S.set_model(p2, par, want_maps=False)
+        S.stat_accumulate()
+        vp, vs, rho, sid = S.get_model()
+        acc[0] += vs; acc[1] += vs ** 2; acc[2] += vp; acc[3] += vp ** 2
+    got, n = S.stat_get()
+    assert n == 3
+    for a, b in zip(got, acc):
+        assert np.array_equal(a, b)
+    S.close()
+
+
 def test_shutdown_and_reinit(mct):
     """mct_shutdown frees every buffer; calls then fail with MCT_E_NOINIT (no fallback), and a new mct_init brings the
     library back with identical results.  A session outliving the shutdown can still be destroyed."""

@@ -43,3 +43,15 @@ def test_pow025_accuracy():
     xs = np.random.default_rng(3).uniform(0.5, 12, 3000)
     worst = max(_ulps(L.orc_mct_pow025(float(x)), mp.mpf(float(x)) ** mp.mpf(0.25)) for x in xs)
     assert worst < 0.51
+
+
+def test_log_accuracy():
+    L = orc.L()
+    L.orc_mct_log.restype = C.c_double
+    L.orc_mct_log.argtypes = [C.c_double]
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([rng.uniform(1e-3, 10, 3000), np.exp(rng.uniform(-700, 700, 1000)), rng.uniform(0.99, 1.01, 500),
+                         [1e-310, 5e-324, 2.0, 0.5, np.sqrt(2.0)]])
+    worst = max(_ulps(L.orc_mct_log(float(x)), mp.log(mp.mpf(float(x)))) for x in xs)
+    assert worst < 1.0
+    assert L.orc_mct_log(1.0) == 0.0

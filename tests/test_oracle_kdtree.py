@@ -9,7 +9,7 @@ import pytest
 import oracle_lib as orc
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "kdtree2_ref.npz")
-CASES = ["random300", "vertices2", "lattice_ties", "tiny13", "tiny14"]
+CASES = ["random300", "vertices2", "lattice_ties", "tiny13", "tiny14", "collinear", "plane", "dup12"]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -46,8 +46,25 @@ def test_oracle_matches_reference_live(n, seed):
 
 
 def test_degenerate_nuclei_detected():
+    """Only nuclei coincident in EVERY dimension (more than a bucket of them) make kdtree2's build recurse for ever;
+    a split that merely leaves one child empty is legal (see the collinear/plane fixtures)."""
     with pytest.raises(ValueError):
         orc.kd_nearest(np.ones((40, 3)), np.zeros((1, 3)))
+
+
+@pytest.mark.skipif(not orc.have_ref_binary(), reason="oracle/_ref/kdtree2_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(6))
+def test_one_child_nodes_match_reference_live(seed):
+    """Random mixtures of points sharing one or two coordinates (one-child nodes, kdtree2.f90:818-826)."""
+    rng = np.random.default_rng(100 + seed)
+    n_line, n_plane, n_free = rng.integers(14, 60, 3)
+    line = np.column_stack([np.full(n_line, 0.5), np.full(n_line, rng.uniform()), rng.uniform(0, 1, n_line)])
+    plane = np.column_stack([rng.uniform(0, 1, n_plane), np.full(n_plane, 0.125), rng.uniform(0, 1, n_plane)])
+    pts = rng.permutation(np.concatenate([line, plane, rng.uniform(0, 1, (n_free, 3))]))
+    q = np.concatenate([rng.uniform(-0.2, 1.2, (3000, 3)), np.round(rng.uniform(0, 1, (1000, 3)), 1)])
+    i1, d1 = orc.kd_nearest(pts, q)
+    i2, d2 = orc.ref_kd_nearest(pts, q)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
 
 
 def test_kdtree_to_grid_window_and_pm():

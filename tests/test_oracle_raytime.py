@@ -35,3 +35,41 @@ def test_bilinear_interpolation_reproduces_a_bilinear_field():
     fine = a + np.linspace(0.0, 1.0, 200001)[:, None] * (b - a)
     exact = np.trapezoid(1.0 / v(fine), dx=L / 200000)
     assert abs(t[0, 0] - exact) < 1e-7 and abs(t[1, 0] - L / 4.0) < 1e-12
+
+
+def test_misfit_restatement_against_numpy():
+    """orc_surf_misfit (likelihood_surf.F90:356-404) against a direct numpy statement of the same sums (sequential
+    order kept with math.fsum-free python loops), both noise models, rays without data, zero-noise condition."""
+    import math
+    rng = np.random.default_rng(8)
+    np_, nrr = 4, 15
+    time = rng.uniform(1, 5, (np_, nrr))
+    ttime = np.zeros((np_, 3, nrr))
+    ttime[:, 0] = rng.uniform(1, 5, (np_, nrr))
+    ttime[:, 1] = rng.uniform(0.1, 0.4, (np_, nrr))
+    raystat = np.zeros((np_, 2, nrr), np.int32)
+    raystat[:, 0] = rng.uniform(size=(np_, nrr)) < 0.7
+    srdist = rng.uniform(1, 9, (np_, nrr))
+    sn0, sn1 = rng.uniform(0.01, 0.1, np_), rng.uniform(0.01, 0.1, np_)
+    for sigdep in (0, 1):
+        got = orc.surf_misfit(time, ttime, raystat, sigdep=sigdep, snoise0=sn0, snoise1=sn1, srdist=srdist, math_mode=orc.LIBM)
+        like = mis = unw = 0.0
+        sig = np.ones((np_, nrr))
+        for i in range(np_):
+            for r in range(nrr):
+                if raystat[i, 0, r] == 1:
+                    sg = sn0[i] * srdist[i, r] + sn1[i] if sigdep else ttime[i, 1, r]
+                    sig[i, r] = sg
+                    d2 = (time[i, r] - ttime[i, 0, r]) ** 2
+                    like += d2 / (2 * sg * sg)
+                    mis += d2 / (sg * sg)
+                    unw += d2
+        slog = 0.0
+        for v in sig.reshape(-1):
+            slog += math.log(v)
+        nr = int((raystat[:, 0] == 1).sum())
+        like = like + slog + float(np.float32(nr) / np.float32(2.0)) * math.log(float(np.float32(6.283185)))
+        assert np.array_equal(got["sigma"], sig)
+        assert got["like"] == like and got["misfit"] == mis and got["unweighted_misfit"] == unw and got["rc"] == 0
+        port = orc.surf_misfit(time, ttime, raystat, sigdep=sigdep, snoise0=sn0, snoise1=sn1, srdist=srdist)
+        assert abs(port["like"] - like) <= 1e-12 * abs(like) and port["misfit"] == mis

@@ -12,6 +12,11 @@ Cases:
   lattice_ties: 5x5x5 integer lattice + 10 exact duplicates, shuffled; queries on the half-integer
                 grid, where up to 8 nuclei are exactly equidistant -- pins the tie-breaking
   tiny13/14   : the leaf/first-split boundary of bucket_size = 12
+  collinear   : 20 distinct nuclei sharing x = y (a line along z) + 20 scattered: the inherited, over-estimated box
+                picks a dimension in which a node's >= 14 points are all equal, the split leaves one child empty and
+                kdtree2 keeps the one-child node (kdtree2.f90:818-826), which its search scans as a terminal (:1388)
+  plane       : 60 nuclei on the plane x = 0.3 + 5 off it (same situation one dimension up), and 30 duplicates of
+                ONE point among 50 others (coincident in all dimensions but fewer than the whole range)
 """
 import os
 import sys
@@ -39,6 +44,12 @@ def main():
     cases["lattice_ties"] = (lat, hx)
     for n in (13, 14):
         cases[f"tiny{n}"] = (rng.uniform(0, 1, (n, 3)), rng.uniform(-0.2, 1.2, (500, 3)))
+    line = np.stack([np.full(20, 0.25), np.full(20, 0.25), np.linspace(0.0, 1.0, 20)], -1)
+    cases["collinear"] = (rng.permutation(np.concatenate([line, rng.uniform(0, 1, (20, 3))])), rng.uniform(-0.2, 1.2, (1500, 3)))
+    plane = np.concatenate([np.column_stack([np.full(60, 0.3), rng.uniform(0, 1, (60, 2))]), rng.uniform(0, 1, (5, 3))])
+    cases["plane"] = (rng.permutation(plane), rng.uniform(-0.2, 1.2, (1500, 3)))
+    dup = np.concatenate([np.tile(np.array([[0.4, 0.6, 0.5]]), (12, 1)), rng.uniform(0, 1, (50, 3))])
+    cases["dup12"] = (rng.permutation(dup), rng.uniform(-0.2, 1.2, (1500, 3)))
     out = {}
     for name, (p, q) in cases.items():
         idx, dis = orc.ref_kd_nearest(p, q)
