@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="models per GPU per step (default: 32 for C2, 8 for C4, else 1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the column-sharded C5 block (one chain's columns over the ranks)")
+    ap.add_argument("--c5-steps", type=int, default=2)
     return ap.parse_args()
 
 
@@ -204,6 +206,110 @@ def run_reference(args):
     GUARD.emit(json.dumps(out))
 
 
+def c5_block(args, torch, dist, capi, dev, rank, world, stream):
+    """BASELINE config 5 next to the headline: ONE chain on the 1024x1024x80 grid, 60 periods, 5000 nuclei, its columns
+    sharded over the ranks in x-slabs; every rank runs mct_forward_sharded_dev (K1 + maps + check + dispersion of its slab,
+    then the in-place ncclAllGather of the (60,1024,1024) map + ierr and the flag all-reduce, all inside the library).
+    Strong scaling: per-rank K1/K2 device times, collective time, and the same evaluation unsharded on rank 0 for the
+    efficiency.  Communicator bootstrap: the 128-byte id travels by torch.distributed.broadcast (MPI_Bcast in MCTomo)."""
+    from mctomo_b200 import synth
+    c = synth.CONFIGS["C5"]
+    grid = synth.make_grid(c["nx"], c["ny"], c["nz"])
+    freqs = synth.freqs(c["np"])
+    nout = len(freqs)
+    opts = capi.disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    pts, par = synth.generate_model(grid, c["ncells"], 1005)   # the same model on every rank
+    off = np.array([0, len(pts)], np.int64)
+    if world > 1 and not capi.comm_info()["active"]:
+        capi.comm_init_torch(dist, dev)
+    lo, hi, per = capi.slab_bounds(grid.nx, world, rank)
+    n = grid.nx * grid.ny * grid.nz
+    cols = per * world * grid.ny
+    d_vp = torch.empty(n, dtype=torch.float64, device=dev); d_vs = torch.empty_like(d_vp); d_rho = torch.empty_like(d_vp)
+    d_sid = torch.empty(n, dtype=torch.int32, device=dev)
+    d_pv = torch.empty(cols * nout, dtype=torch.float64, device=dev); d_gv = torch.empty_like(d_pv)
+    d_ie = torch.empty(cols, dtype=torch.int32, device=dev); d_fl = torch.zeros(2, dtype=torch.int32, device=dev)
+    capi.set_nuclei_batch(pts, par, off)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        capi.forward_sharded_dev(grid, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
+                                 d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream)
+
+    step()  # warm-up (buffers grow, NCCL connects)
+    sync()
+    capi.set_profiling(True)
+    capi.kernel_times(reset=True)
+    capi.reset_stats()
+    ms, comm_ms = [], []
+    for _ in range(args.c5_steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        a.record()
+        step()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+        comm_ms.append(capi.comm_last_ms())
+    kt = capi.kernel_times(reset=True)
+    st = capi.stats()
+    mine = torch.tensor([sum(ms) / len(ms), kt["k1_ms"] / len(ms), kt["k2_ms"] / len(ms), kt["other_ms"] / len(ms),
+                         sum(comm_ms) / len(ms), float(st["n_columns_solved"]) / len(ms), float((hi - lo + 1) * grid.ny)],
+                        dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    allr = torch.stack(allr).cpu().numpy()
+    ms_eval = float(allr[:, 0].max())
+    # the same evaluation unsharded on ONE GPU (rank 0; the others wait): the strong-scaling denominator
+    n1_ms = ms_eval
+    if world > 1:
+        if rank == 0:
+            d_p1 = torch.empty(grid.nx * grid.ny * nout, dtype=torch.float64, device=dev); d_g1 = torch.empty_like(d_p1)
+            d_i1 = torch.empty(grid.nx * grid.ny, dtype=torch.int32, device=dev)
+            t = []
+            for it in range(2):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                capi.forward_batch_dev(grid, 1, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
+                                       d_p1.data_ptr(), d_g1.data_ptr(), d_i1.data_ptr(), d_fl.data_ptr(), stream)
+                b.record()
+                torch.cuda.synchronize()
+                t.append(a.elapsed_time(b))
+            n1_ms = t[-1]
+            same = bool(torch.equal(d_p1, d_pv[: d_p1.numel()]))  # gathered map == unsharded map, bit for bit
+        else:
+            same = True
+        sync()
+        t1 = torch.tensor([n1_ms], dtype=torch.float64, device=dev)
+        dist.broadcast(t1, 0)
+        n1_ms = float(t1.item())
+    else:
+        same = True
+    capi.kernel_times(reset=True)
+    capi.set_profiling(False)
+    solves = grid.nx * grid.ny * nout
+    return {"workload": f"C5: {grid.nx}x{grid.ny}x{grid.nz} grid, {nout} periods, Rayleigh phase, {len(pts)} nuclei, ONE chain, "
+                        f"x-slabs of {per} columns per rank", "scaling": "strong", "n_gpus": world, "steps": args.c5_steps,
+            "ms_per_eval": ms_eval, "solves_per_sec": solves / (ms_eval * 1e-3),
+            "per_rank_ms": [float(v) for v in allr[:, 0]], "per_rank_k1_ms": [float(v) for v in allr[:, 1]],
+            "per_rank_k2_ms": [float(v) for v in allr[:, 2]], "per_rank_other_kernels_ms": [float(v) for v in allr[:, 3]],
+            "allgather_ms": float(allr[:, 4].max()), "per_rank_allgather_ms": [float(v) for v in allr[:, 4]],
+            "allgather_bytes_per_rank": int(per * grid.ny * (nout * 8 + 4)),
+            "per_rank_distinct_columns_solved": [float(v) for v in allr[:, 5]], "per_rank_columns": [float(v) for v in allr[:, 6]],
+            "n1_ms_per_eval": n1_ms, "efficiency_vs_n1": n1_ms / (world * ms_eval),
+            "gathered_equals_unsharded": same,
+            "collective": "in-place ncclAllGather (pvel f64 + ierr i32) + ncclAllReduce(MAX) of 2 flags, inside libmctomo_b200.so "
+                          f"(NCCL {capi.comm_info()['nccl_version']})" if world > 1 else "none (one rank)"}
+
+
 class StdoutGuard:
     """Keeps stdout clean for the ONE JSON line: anything libraries print to fd 1 meanwhile (NCCL's version banner,
     torchrun notices) is sent to stderr; emit() writes to the real stdout."""
@@ -262,11 +368,13 @@ def main():
     d_vs = torch.empty_like(d_vp)
     d_rho = torch.empty_like(d_vp)
     d_sid = torch.empty(batch * ncell, dtype=torch.int32, device=dev)
-    d_pv = torch.empty(batch * wx * grid.ny * nout, dtype=torch.float64, device=dev)
+    out_cols = per * world * grid.ny if column_sharded else batch * wx * grid.ny  # sharded: the FULL maps, gathered in place
+    d_pv = torch.empty(out_cols * nout, dtype=torch.float64, device=dev)
     d_gv = torch.empty_like(d_pv)
-    d_ie = torch.empty(batch * wx * grid.ny, dtype=torch.int32, device=dev)
+    d_ie = torch.empty(out_cols, dtype=torch.int32, device=dev)
     d_fl = torch.zeros(2 * batch, dtype=torch.int32, device=dev)
-    gathered = torch.empty(world * d_pv.numel(), dtype=torch.float64, device=dev) if column_sharded else None
+    if column_sharded:
+        capi.comm_init_torch(dist, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     # a dedicated (non-default) stream: the library launches on the handle it is given, torch's events and
     # NCCL calls are recorded on the same one
@@ -284,13 +392,15 @@ def main():
         d_fl2 = torch.zeros(2 * batch, dtype=torch.int32, device=dev)
 
     def resident_step():
+        if column_sharded:  # slab + in-place NCCL all-gather of the maps + flag all-reduce, all inside the library
+            capi.forward_sharded_dev(grid, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
+                                     d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream)
+            return
         capi.forward_batch_dev(grid, batch, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
                                d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream, slab=slab)
         if love:
             capi.surf_dispersion_dev(d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), grid, (slab[0], slab[1], 1, grid.ny), freqs,
                                      love_opts, d_pv2.data_ptr(), d_gv2.data_ptr(), d_ie2.data_ptr(), d_fl2.data_ptr(), stream)
-        if column_sharded:
-            dist.all_gather_into_tensor(gathered, d_pv)
 
     def barrier():
         torch.cuda.synchronize()
@@ -377,6 +487,11 @@ def main():
                "ms_per_step": float(t_e2e.item()) / args.steps * 1e3,
                "api": "mct_forward_eval_batch (host pointers in/out, tree build + H2D + kernels + D2H inside the timed region)"}
 
+    c5 = None
+    if not args.no_c5 and args.config == "C2":
+        del d_vp, d_vs, d_rho, d_sid, d_pv, d_gv, d_ie
+        torch.cuda.empty_cache()
+        c5 = c5_block(args, torch, dist, capi, dev, rank, world, stream)
     if rank == 0:
         fl, fc = (F_LAYER_R, F_CALL_R) if spec["raylov"] == 1 else (F_LAYER_L, F_CALL_L)
         w2 = st["n_dltar"] * fc + st["n_layer_steps"] * fl      # nominal FP64 ops of all timed K2 launches on rank 0
@@ -426,13 +541,14 @@ def main():
                "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
                                       f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={nm}, "
                                       f"{len(models[0][0])} nuclei",
-                          "batch_per_gpu": batch, "parallelism": ("x-slab column sharding + NCCL all_gather" if column_sharded
+                          "batch_per_gpu": batch, "parallelism": ("x-slab column sharding + in-place ncclAllGather of the maps inside the library (mct_forward_sharded_dev)" if column_sharded
                                                                  else f"chains sharded, {world} x {batch} independent models, no collective"),
                           "l2": "256 MiB buffer written between timed steps (L2 flush); model arrays per step also exceed L2"
                           if batch * ncell * 28 > (126 << 20) else "256 MiB buffer written between timed steps (L2 flush)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["n_launches"]), "roofline": roof, "cpu_baseline": cpu,
                "proposal_latency": {"columns": (pw[1] - pw[0] + 1) * (pw[3] - pw[2] + 1), "ms": proposal_ms,
                                     "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, cooperative kernel (several warps per column)"},
+               "c5": c5,
                "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
                         "columns_per_step": st["n_columns"] / args.steps}}
         GUARD.emit(json.dumps(out))

@@ -74,12 +74,29 @@ typedef struct {
 
 /* Counters accumulated since mct_init / mct_reset_stats. */
 typedef struct {
+  /* REPRESENTED work: what the reference's own loops count for the same input (every column solved on its own).
+   * These equal the oracle's counters -- an identical search path is itself a parity check. */
   int64_t n_dltar;       /* secular-function evaluations (surfdisp96.f:1036) */
   int64_t n_layer_steps; /* layer steps inside them (loops surfdisp96.f:1078,1159) */
   int64_t n_columns;     /* columns solved */
   int64_t n_nodes;       /* grid nodes assigned by the nearest-nucleus kernel */
   int64_t n_launches;    /* kernels launched by this library */
+  /* EXECUTED work: what the dispersion kernel really ran.  Smaller than the represented figures when bit-identical
+   * layer stacks were folded (mct_set_dedup); the roofline is computed from these. */
+  int64_t n_dltar_executed;
+  int64_t n_layer_steps_executed;
+  int64_t n_columns_solved;
 } mct_stats;
+
+/* What the last dispersion launch did (the bench's roofline block reports the kernel from here). */
+typedef struct {
+  char kernel[48];          /* __global__ function launched, e.g. "k2_dispersion_fast_r128" */
+  int32_t columns;          /* columns of the call */
+  int32_t columns_solved;   /* distinct layer stacks actually solved; -1 = not read back (calls below 8192 columns
+                               stay asynchronous) */
+  int32_t lanes_per_column; /* 1 = one thread per column, else the cooperative group size */
+  int32_t sm_count;
+} mct_launch_info;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
 int mct_init(int device);       /* selects the device, creates the stream; idempotent */
@@ -206,6 +223,38 @@ int mct_forward_eval_batch(const double* points, const double* params, const int
                            const mct_disp_opts* opt, double* pvel, double* gvel, int32_t* ierr,
                            int32_t* model_invalid, double* vp, double* vs, double* rho, int32_t* sites_id);
 
+/* ---- multi-GPU: one chain's columns sharded over several GPUs (BASELINE config 5) ------------------
+ * MCTomo runs one MPI rank per chain (src/MCTomo.F90:82-86,131-133) and chains never talk on the data path: chains ->
+ * GPUs needs nothing from this section.  For ONE chain on a large grid the x axis is cut into contiguous slabs, one
+ * per rank (process per GPU); nuclei are replicated (48 B each), every rank grids and solves its slab, and the
+ * dispersion maps are all-gathered IN PLACE with NCCL so that every rank holds the full (np,ny,nx) field for fm2d
+ * (src/likelihood_surf.F90:295-336); check_model's whole-grid `any` (:631-646) is a MAX all-reduce of one flag.
+ * NCCL is bound at run time (dlopen libnccl.so.2; MCT_NCCL_LIB overrides): no link-time dependency.
+ *   rank 0:  mct_comm_unique_id(id)  ->  host broadcasts the 128 bytes (MPI_Bcast)  ->  all: mct_comm_init(id, rank, n)
+ */
+#define MCT_COMM_ID_BYTES 128
+int mct_comm_unique_id(void* id128);
+int mct_comm_init(const void* id128, int rank, int nranks); /* after mct_init(device); collective over the ranks */
+int mct_comm_destroy(void);
+int mct_comm_info(int* rank, int* nranks, int* nccl_version); /* MCT_E_INVALID_ARG when no communicator exists */
+/* x-slab of `rank`: 1-based inclusive ix0..ix1, equal width per = ceil(nx/nranks); trailing slabs may be short or
+ * empty (ix1 < ix0). */
+int mct_slab_bounds(int nx, int nranks, int rank, int* ix0, int* ix1, int* per);
+/* In-place all-gather of a device buffer of nranks chunks of bytes_per_rank bytes (this rank owns the rank-th). */
+int mct_allgather_inplace(void* d_buf, int64_t bytes_per_rank, void* stream);
+/* MAX all-reduce of n int32 flags in place ({model_invalid, max condition code}). */
+int mct_allreduce_flags(int32_t* d_flags, int n, void* stream);
+/* The sharded forward evaluation: K1 + property maps + check_model + dispersion on this rank's slab of the resident
+ * nuclei set (mct_set_nuclei_batch, nb = 1, same nuclei on every rank), outputs written into this rank's chunk of the
+ * FULL maps d_pvel/d_gvel (nout, ny, per*nranks), d_ierr (ny, per*nranks); then in-place all-gather of pvel, ierr
+ * (and gvel when opt->phaseGroup == 1) and MAX all-reduce of d_flags[2], all enqueued on `stream`.  With one rank (no
+ * communicator) it is mct_forward_batch_dev over the whole grid. */
+int mct_forward_sharded_dev(const mct_grid* g, int derive_vp_rho, const double* freqs, int np, const mct_disp_opts* opt,
+                            double* d_vp, double* d_vs, double* d_rho, int32_t* d_sites_id, double* d_pvel,
+                            double* d_gvel, int32_t* d_ierr, int32_t* d_flags, void* stream);
+/* Device milliseconds the collectives of the last mct_forward_sharded_dev call took (synchronises). */
+int mct_comm_last_ms(double* ms);
+
 /* ---- measurement helpers ----------------------------------------------------------------------
  * mct_set_profiling(1) brackets every kernel launch with CUDA events on the launching stream;
  * mct_kernel_times returns accumulated milliseconds {K1 nearest-nucleus, K2 dispersion, other kernels,
@@ -233,6 +282,11 @@ int mct_set_k1_mode(int mode);
  * one or the other; mct_set_k2_lanes fixes G (0 = automatic, else a power of two from 2 to 256).  Results are
  * identical in every shape. */
 int mct_set_k2_mode(int mode, int coop_max_columns);
+/* Exact de-duplication of columns in front of the dispersion kernel (default on): columns whose float32 layer stacks
+ * are bit-identical (same model of a batch) are solved once and the outputs copied.  Results are identical either way;
+ * calls of 8192 columns or more read the distinct count back (one stream synchronisation) to size the launch. */
+int mct_set_dedup(int on);
+int mct_last_launch(mct_launch_info* out);
 int mct_set_k2_lanes(int lanes_per_column);
 /* Device self-test: the shared-reciprocal division the dispersion kernel uses is compared, bit for
  * bit, with the compiler's IEEE division on *tested random operand pairs whose exponents are drawn

@@ -56,7 +56,13 @@ class mct_disp_opts(C.Structure):
 
 class mct_stats(C.Structure):
     _fields_ = [("n_dltar", C.c_int64), ("n_layer_steps", C.c_int64), ("n_columns", C.c_int64),
-                ("n_nodes", C.c_int64), ("n_launches", C.c_int64)]
+                ("n_nodes", C.c_int64), ("n_launches", C.c_int64), ("n_dltar_executed", C.c_int64),
+                ("n_layer_steps_executed", C.c_int64), ("n_columns_solved", C.c_int64)]
+
+
+class mct_launch_info(C.Structure):
+    _fields_ = [("kernel", C.c_char * 48), ("columns", C.c_int32), ("columns_solved", C.c_int32),
+                ("lanes_per_column", C.c_int32), ("sm_count", C.c_int32)]
 
 
 @dataclass
@@ -454,6 +460,17 @@ def set_k2_mode(mode: int = 0, coop_max_columns: int = -1):
     _check(L.mct_set_k2_mode(mode, coop_max_columns))
 
 
+def set_dedup(on: bool = True):
+    _check(lib().mct_set_dedup(1 if on else 0))
+
+
+def last_launch() -> dict:
+    li = mct_launch_info()
+    _check(lib().mct_last_launch(C.byref(li)))
+    return dict(kernel=li.kernel.decode(), columns=li.columns, columns_solved=li.columns_solved,
+                lanes_per_column=li.lanes_per_column, sm_count=li.sm_count)
+
+
 def set_k2_lanes(lanes_per_column: int = 0):
     """Lanes per column of the cooperative dispersion kernel: 0 automatic, else a power of two from 2 to 256."""
     L = _bind_batch()
@@ -658,3 +675,80 @@ def surf_misfit(time, ttime, raystat, sigdep=0, nrays_total=None, snoise0=None, 
     rc = _check(L.mct_surf_misfit(t.ctypes.data, nrr, np_, sigdep, nrays_total, tt.ctypes.data, rs.ctypes.data, _ptr(n0), _ptr(n1),
                                   _ptr(sd), out.ctypes.data, sg.ctypes.data), allow=(MCT_E_ZERO_NOISE,))
     return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], sigma=sg, rc=rc)
+
+
+# ---- multi-GPU data plane (mct_comm_*, include/mctomo_b200.h) -------------------------------------------------------
+MCT_COMM_ID_BYTES = 128
+
+
+def slab_bounds(nx: int, nranks: int, rank: int):
+    """mct_slab_bounds: (ix0, ix1, per), 1-based inclusive; needs no device."""
+    a, b, p = C.c_int(0), C.c_int(0), C.c_int(0)
+    L = lib()
+    L.mct_slab_bounds.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _check(L.mct_slab_bounds(nx, nranks, rank, C.byref(a), C.byref(b), C.byref(p)))
+    return a.value, b.value, p.value
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(MCT_COMM_ID_BYTES)
+    _check(lib().mct_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(id128: bytes, rank: int, nranks: int):
+    L = lib()
+    L.mct_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    assert len(id128) == MCT_COMM_ID_BYTES
+    _check(L.mct_comm_init(id128, rank, nranks))
+
+
+def comm_destroy():
+    _check(lib().mct_comm_destroy())
+
+
+def comm_info():
+    r, n, v = C.c_int(0), C.c_int(1), C.c_int(0)
+    rc = lib().mct_comm_info(C.byref(r), C.byref(n), C.byref(v))
+    return dict(rank=r.value, nranks=n.value, nccl_version=v.value, active=(rc == 0))
+
+
+def comm_init_torch(dist, device):
+    """Bootstrap for a torch.distributed host program: rank 0 draws the id, one broadcast moves the 128 bytes."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t = torch.zeros(MCT_COMM_ID_BYTES, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+
+def allgather_inplace(d_buf, bytes_per_rank: int, stream):
+    L = lib()
+    L.mct_allgather_inplace.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    _check(L.mct_allgather_inplace(d_buf, bytes_per_rank, stream))
+
+
+def allreduce_flags(d_flags, n: int, stream):
+    L = lib()
+    L.mct_allreduce_flags.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    _check(L.mct_allreduce_flags(d_flags, n, stream))
+
+
+def forward_sharded_dev(grid: Grid, freqs, opts, d_vp, d_vs, d_rho, d_sites, d_pvel, d_gvel, d_ierr, d_flags, stream,
+                        derive_vp_rho=True):
+    """mct_forward_sharded_dev: this rank's x-slab of the resident nuclei set + in-place all-gather of the maps."""
+    L = lib()
+    vp = C.c_void_p
+    L.mct_forward_sharded_dev.argtypes = [C.POINTER(mct_grid), C.c_int, vp, C.c_int, C.POINTER(mct_disp_opts)] + [vp] * 9
+    freqs = _f64(freqs)
+    return _check(L.mct_forward_sharded_dev(C.byref(grid.c()), 1 if derive_vp_rho else 0, freqs.ctypes.data, len(freqs),
+                                            C.byref(opts), d_vp, d_vs, d_rho, d_sites, d_pvel, d_gvel, d_ierr, d_flags, stream),
+                  allow=(MCT_E_GRT_NEEDED, MCT_E_TOO_MANY_LAYERS, MCT_E_FLUID_BELOW_TOP))
+
+
+def comm_last_ms() -> float:
+    v = C.c_double(0.0)
+    _check(lib().mct_comm_last_ms(C.byref(v)))
+    return v.value

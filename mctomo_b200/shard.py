@@ -1,4 +1,5 @@
-"""Column sharding of ONE model over the ranks of a torch.distributed group (BASELINE config 5).
+"""(Test/bench plumbing; the production data plane is mct_comm_* / mct_forward_sharded_dev inside the library.)
+Column sharding of ONE model over the ranks of a torch.distributed group (BASELINE config 5).
 
 The reference shards nothing inside a chain except OpenMP loops over x (src/likelihood_surf.F90:197-206);
 here the same x axis is cut into contiguous slabs, one per rank: (nz,ny,nx) and (np,ny,nx) arrays make a

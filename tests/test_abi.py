@@ -67,3 +67,28 @@ def test_product_does_not_reference_oracle():
     import subprocess
     out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_slab_bounds_is_host_logic_and_covers_the_grid():
+    """mct_slab_bounds needs no device; slabs are contiguous, equal width, cover 1..nx once; same rule as shard.py."""
+    from mctomo_b200 import shard
+    for nx in (1, 5, 7, 8, 64, 1000, 1024):
+        for world in (1, 2, 3, 8):
+            cols = []
+            for r in range(world):
+                lo, hi, per = capi.slab_bounds(nx, world, r)
+                assert (lo, hi, per) == shard.slab_bounds(nx, world, r)
+                cols += list(range(lo, hi + 1))
+            assert cols == list(range(1, nx + 1))
+
+
+def test_comm_without_device_fails_loudly_and_library_has_no_nccl_dependency():
+    import subprocess
+    import torch
+    out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out                       # bound with dlopen at mct_comm_init, not at link time
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    L = capi.lib()
+    assert L.mct_comm_init(b"\0" * 128, 0, 2) == capi.MCT_E_NOINIT
+    assert capi.comm_info()["active"] is False
