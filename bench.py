@@ -103,18 +103,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def k2_kernel_name(ncol, sm_count):
-    """The dispersion kernel launch_k2 (mct_api.cu) picks for a batch of ncol columns (automatic mode)."""
-    cap = sm_count * 16 * 32                      # resident lanes
-    if ncol >= cap * 17 // 10:
-        return "k2_dispersion_fast_r128"
-    g = 32
-    while g > 2 and ncol * g * 5 > cap * 11:
-        g //= 2
-    if g == 32:
-        slots = sm_count * 16
-        g = 128 if ncol * 5 <= slots else 64 if ncol * 3 <= slots else 32
-    return {256: "k2_coopw8_kernel", 128: "k2_coopw4_kernel", 64: "k2_coopw2_kernel", 32: "k2_coop_kernel"}.get(g, f"k2_coop{g}_kernel")
+def k2_source_sha():
+    """Fingerprint of everything the dispersion kernel is compiled from: ties profiles/k2_traffic.json to a build."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "mctomo_b200", "csrc")
+    for f in ("k2_dispersion.cuh", "k2_rayleigh_fast.cuh", "k2_love_fast.cuh", "k2_coop.cuh", "k2_layerpar.cuh", "mct_math.h", "Makefile"):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def hbm_peak():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the recipe's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6500.0
 
 
 def workload(args, rank, world):
@@ -434,6 +438,7 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kt = capi.kernel_times(reset=True)
     st = capi.stats()
+    main_launch = capi.last_launch()
     if love:  # roofline figures refer to the Rayleigh pass only: re-measure it alone (untimed for `value`)
         capi.reset_stats()
         for _ in range(args.steps):
@@ -494,29 +499,41 @@ def main():
         c5 = c5_block(args, torch, dist, capi, dev, rank, world, stream)
     if rank == 0:
         fl, fc = (F_LAYER_R, F_CALL_R) if spec["raylov"] == 1 else (F_LAYER_L, F_CALL_L)
-        w2 = st["n_dltar"] * fc + st["n_layer_steps"] * fl      # nominal FP64 ops of all timed K2 launches on rank 0
+        # EXECUTED work of all timed K2 launches on rank 0 (bit-identical columns are solved once: the represented
+        # counts, equal to the reference's own, are reported under "work")
+        w2 = st["n_dltar_executed"] * fc + st["n_layer_steps_executed"] * fl
         k2_s = kt["k2_ms"] * 1e-3
         probe = capi.fp64_peak_probe()
         achieved = w2 / k2_s / 1e12 if k2_s > 0 else None
-        traffic = None
-        try:  # DRAM bytes per K2 launch from the committed ncu capture of this same workload (default config only)
+        li = main_launch                                          # what the library itself says it launched
+        sm_count = li["sm_count"]
+        traffic, traffic_note = None, "no ncu capture of this build's K2 sources under profiles/k2_traffic.json"
+        try:  # DRAM bytes per K2 launch from the ncu capture of THIS build: dropped when the K2 sources have changed since
             tj = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
             if args.config == "C2" and batch == 32 and not column_sharded:
-                traffic = tj["dram_bytes_per_launch"]
+                if tj.get("k2_source_sha") == k2_source_sha() and tj.get("kernel") == li["kernel"]:
+                    traffic, traffic_note = tj["dram_bytes_per_launch"], tj.get("source", "")
+                else:
+                    traffic_note = "profiles/k2_traffic.json was captured from different K2 sources or another kernel: dropped"
         except Exception:
             pass
+        nominal = sm_count * 64 * 2 * (clocks.get("sm_max_mhz") or 0) * 1e6 / 1e12  # 64 FP64 FMA lanes per SM
         roof = {"bound": "fp64", "achieved": achieved, "peak": probe["dfma_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / probe["dfma_tflops"] if achieved else None, "traffic": traffic,
-                "kernel": k2_kernel_name(batch * wx * grid.ny, torch.cuda.get_device_properties(dev).multi_processor_count),
+                "frac": achieved / probe["dfma_tflops"] if achieved else None, "traffic": traffic, "traffic_source": traffic_note,
+                "kernel": li["kernel"], "kernel_columns": li["columns"], "kernel_columns_solved": li["columns_solved"],
+                "kernel_lanes_per_column": li["lanes_per_column"],
                 "k2_ms_per_step": kt["k2_ms"] / args.steps,
                 "k2_share_of_step": kt["k2_ms"] / sum(step_ms),
                 "peak_source": "measured live: 8 independent DFMA chains/thread (mct_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry",
+                "peak_nominal_tflops": nominal, "peak_nominal_what": f"{sm_count} SMs x 64 FP64 lanes x 2 flop x {clocks.get('sm_max_mhz')} MHz",
                 "peak_dmul_dadd_tflops": probe["dmul_dadd_tflops"],
-                "note": "achieved = nominal FP64 ops (184/layer step + 31/call, Rayleigh; SURVEY 8d) / K2 time; the kernel is "
+                "note": "achieved = nominal FP64 ops EXECUTED (184/layer step + 31/call, Rayleigh; SURVEY 8d) / K2 time; the kernel is "
                         "compiled without FMA contraction for bit-parity, so its ceiling is the DMUL+DADD rate",
-                "layer_steps_per_s": st["n_layer_steps"] / k2_s if k2_s > 0 else None,
+                "layer_steps_per_s": st["n_layer_steps_executed"] / k2_s if k2_s > 0 else None,
                 "k1_ms_per_step": kt["k1_ms"] / args.steps,
-                "k1_hbm_gbs": (28.0 * batch * wx * grid.ny * grid.nz) * args.steps / (kt["k1_ms"] * 1e-3) / 1e9 if kt["k1_ms"] > 0 else None}
+                "k1_hbm_gbs": (28.0 * batch * wx * grid.ny * grid.nz) * args.steps / (kt["k1_ms"] * 1e-3) / 1e9 if kt["k1_ms"] > 0 else None,
+                "k1_hbm_peak_gbs": hbm_peak(), "k1_frac": ((28.0 * batch * wx * grid.ny * grid.nz) * args.steps / (kt["k1_ms"] * 1e-3) / 1e9 / hbm_peak())
+                if kt["k1_ms"] > 0 else None}
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -550,7 +567,12 @@ def main():
                                     "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, cooperative kernel (several warps per column)"},
                "c5": c5,
                "work": {"dltar_calls_per_step": st["n_dltar"] / args.steps, "layer_steps_per_step": st["n_layer_steps"] / args.steps,
-                        "columns_per_step": st["n_columns"] / args.steps}}
+                        "columns_per_step": st["n_columns"] / args.steps,
+                        "executed": {"dltar_calls_per_step": st["n_dltar_executed"] / args.steps,
+                                     "layer_steps_per_step": st["n_layer_steps_executed"] / args.steps,
+                                     "distinct_columns_per_step": st["n_columns_solved"] / args.steps},
+                        "what": "represented = the reference's own call counts for these inputs (identical to the oracle's); "
+                                "executed = after folding bit-identical columns"}}
         GUARD.emit(json.dumps(out))
     if world > 1:
         dist.barrier()

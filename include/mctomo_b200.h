@@ -270,9 +270,11 @@ int mct_fp64_peak_probe(double* tflops_fma, double* tflops_mul_add);
 int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_aveS, double* d_stdS, double* d_aveP,
                              double* d_stdP, int64_t n, void* stream);
 
-/* Shape of the nearest-nucleus kernel.  mode 0 (default): one warp per grid column, brute force over the
- * nuclei that survive a conservative per-column cull, kdtree2's traversal replayed only for (near-)tied
- * nodes.  mode 1: kdtree2's traversal for every node.  Results are identical either way. */
+/* Shape of the nearest-nucleus kernel.  mode 0 (default): a block per tile of 4 x 16 columns; conservative culls leave,
+ * per column and per z-segment of 8 nodes, a list of at most 7 candidate nuclei in shared memory; nodes are resolved
+ * two at a time and written with 16-byte stores; kdtree2's traversal is replayed only for (near-)tied nodes.  mode 2:
+ * the round-1 shape (a warp per column, every node scans its column's survivors).  mode 1: kdtree2's traversal for
+ * every node.  Results are identical in all three. */
 int mct_set_k1_mode(int mode);
 /* Shape of the dispersion kernel.  mode 0 (default): batches of fewer than coop_max_columns columns (default 0 =
  * 1.7x the resident lanes of the GPU, 128 819 columns on a B200; pass -1 to keep) give every column a GROUP OF G LANES that

@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(256) k1_voronoi_kernel(const __grid_constant__
   }
 }
 
-#include "k1_column.cuh" // k1_column_kernel: culled brute force per column, tree walk only for (near-)ties
+#include "k1_column.cuh" // k1_column_kernel: culled brute force per column, tree walk only for (near-)ties (round-1 shape)
+#include "k1_tile.cuh"   // k1_tile_kernel: per-(column, z-segment) candidate lists, vector stores (production)
 
 // vs2vp_3d + vp2rho_3d (src/utils.f90:107-110,131-133), elementwise over n values.
 __global__ void __launch_bounds__(256) vs2vp_rho_kernel(const double* __restrict__ vs, double* __restrict__ vp,

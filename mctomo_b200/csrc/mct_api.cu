@@ -284,7 +284,7 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
     ProfScope ps(0, st);
     if (g.k1_mode == 1) {
       k1_voronoi_kernel<<<grid_blocks(total, 256, 16), 256, 0, st>>>(P); // exact tree walk for every node
-    } else {
+    } else if (g.k1_mode == 2 || P.wz > 500) { // round-1 shape (also for columns beyond the tile kernel's 16-bit item index): warp per column, every node scans the column's survivors
       if (!g.k1_smem_set) {
         CK(cudaFuncSetAttribute(k1_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1C_SMEM_BYTES));
         g.k1_smem_set = true;
@@ -293,6 +293,32 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
       const int nby = batched ? nbatch : 1;
       const int blocks = (int)std::min<long long>(ntiles, std::max<long long>(1, (long long)g.sm_count * 3 / nby));
       k1_column_kernel<<<dim3(blocks, nby), 32 * K1C_WARPS, K1C_SMEM_BYTES, st>>>(P);
+    } else { // per-(tile, z-segment) candidate lists, flattened nodes, vector stores (k1_tile.cuh)
+      // Tile and segment are sized against the nucleus spacing h = (grid volume / n)^(1/3): the tile's half diagonal up
+      // to h/2, segments of h/2.  Larger boxes make the bound U_B loose (long lists), smaller ones repeat the passes over
+      // the nuclei for too few nodes (measured: C2 with 1 x 4 tiles spent 90 % of its instructions in those passes).
+      const double vol = std::max(gr->dx * (gr->nx - 1), gr->dx) * std::max(gr->dy * (gr->ny - 1), gr->dy) * std::max(gr->dz * (gr->nz - 1), gr->dz);
+      const double h = std::cbrt(vol / (double)std::max(1, P.n));
+      static const int shapes[5][2] = {{8, 32}, {4, 16}, {2, 8}, {1, 8}, {1, 4}};
+      int ttx = 1, tty = 4;
+      for (const auto& sh : shapes) {
+        const double hd = 0.5 * std::sqrt((sh[0] * gr->dx) * (sh[0] * gr->dx) + (sh[1] * gr->dy) * (sh[1] * gr->dy));
+        if (hd <= 0.5 * h) { ttx = sh[0]; tty = sh[1]; break; }
+      }
+      int seglen = (int)std::floor(0.5 * h / gr->dz);
+      seglen = std::max(seglen, (P.wz + K1T_MAXSEG - 1) / K1T_MAXSEG);
+      seglen = std::max(2, seglen + (seglen & 1)); // even: a 16-byte pair of nodes then lies inside one segment
+      const long long ntiles = (long long)((P.wx + ttx - 1) / ttx) * ((P.wy + tty - 1) / tty);
+      const int nby = batched ? nbatch : 1;
+      // two resident blocks per SM (registers); several blocks per slot so the hardware scheduler evens out tiles of
+      // different cost, each block striding over the tiles
+      const long long want = std::max<long long>(1, ((long long)g.sm_count * 16 + nby - 1) / nby);
+      const int blocks = (int)std::min<long long>(ntiles, want);
+      const int npairs = (P.wz + 2) / 2;
+      const int nitems = ttx * tty * npairs;
+      const int threads = nitems <= 640 ? 128 : 256;
+      k1_tile_kernel<<<dim3(blocks, nby), threads, 0, st>>>(P, ttx, tty, seglen, (float)(2.5 * h), k1t_magic(npairs), k1t_magic(tty),
+                                                            k1t_magic(seglen));
     }
   }
   CK(cudaGetLastError());
@@ -1135,7 +1161,7 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
 }
 
 int mct_set_k1_mode(int mode) {
-  if (mode < 0 || mode > 1) return fail(MCT_E_INVALID_ARG, "set_k1_mode: mode must be 0 (culled brute force) or 1 (tree walk)");
+  if (mode < 0 || mode > 2) return fail(MCT_E_INVALID_ARG, "set_k1_mode: mode must be 0 (segment lists), 1 (tree walk) or 2 (column scan)");
   g.k1_mode = mode;
   return MCT_OK;
 }

@@ -34,9 +34,15 @@ def freqs(np_: int) -> np.ndarray:
     return 1.0 / periods(np_)
 
 
+# examples/example1/otimes.dat:2 as shipped (six decimals: 0.333333, not 1/3); read_times_3 reads them with a
+# list-directed read into real(ii10) (src/likelihood_settings.f90:332-421), i.e. the nearest double of each decimal
+EXAMPLE1_FREQS_SHIPPED = (2.000000, 1.000000, 0.500000, 0.333333, 0.250000, 0.200000, 0.166667, 0.142857, 0.125000,
+                          0.111111, 0.100000)
+
+
 def example1_freqs() -> np.ndarray:
-    """The 11 frequencies of examples/example1/otimes.dat:2 (periods 0.5,1,2,...,10 s)."""
-    return 1.0 / np.array([0.5, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10], dtype=np.float64)
+    """The 11 frequencies of examples/example1/otimes.dat:2 exactly as the file ships them (periods ~0.5,1,2,...,10 s)."""
+    return np.array(EXAMPLE1_FREQS_SHIPPED, dtype=np.float64)
 
 
 def generate_model(grid: Grid, ncells: int, seed: int, vsmin=2.0, vsmax=6.0):

@@ -24,18 +24,19 @@ def _empty_model(grid):
 
 
 def _both_k1(mct, pts, par, grid, box, pm=None, init=None):
-    """GPU (both kernel shapes: culled brute force per column, tree walk per node) and oracle."""
+    """GPU (all three kernel shapes: tree walk per node, round-1 column scan, segment lists) and oracle."""
     outs = []
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         mct.set_k1_mode(mode)
         vp, vs, rho, sid = _empty_model(grid) if init is None else [a.copy() for a in init]
         mct.kdtree_to_grid(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
         outs.append((vp, vs, rho, sid))
-    for x, y in zip(outs[0], outs[1]):
-        assert np.array_equal(x, y), "the two nearest-nucleus kernels disagree"
+    for other in (outs[1], outs[2]):
+        for x, y in zip(outs[0], other):
+            assert np.array_equal(x, y), f"the nearest-nucleus kernels disagree in {(x != y).sum()} nodes"
     vp, vs, rho, sid = _empty_model(grid) if init is None else [a.copy() for a in init]
     orc.kdtree_to_grid(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
-    return [outs[1], (vp, vs, rho, sid)]
+    return [outs[2], (vp, vs, rho, sid)]
 
 
 def _assert_k1_equal(a, b):
@@ -104,6 +105,37 @@ def test_k1_many_nuclei_and_thin_window(mct):
     box = np.array([-5.0, -5.0, 6.0, 5.0, 5.0, 6.05])
     g, o = _both_k1(mct, pts, par, grid, box)
     _assert_k1_equal(g, o)
+
+
+@pytest.mark.parametrize("shape", [(9, 7, 41), (5, 33, 121), (3, 3, 1), (17, 16, 7), (6, 5, 150)])
+def test_k1_odd_shapes_and_windows(mct, shape):
+    """Odd nz (columns start on odd element offsets: the 16-byte stores shift by one node per column), a single plane,
+    columns taller than 128 nodes (segments longer than 8), and sub-windows starting on odd z."""
+    nx, ny, nz = shape
+    grid = synth.make_grid(nx, ny, nz) if nz > 1 else Grid(nx, ny, 2, -5, 5, -5, 5, 0, 12)
+    pts, par = synth.generate_model(grid, 90, 5 + nz)
+    g, o = _both_k1(mct, pts, par, grid, grid.cover_box())
+    _assert_k1_equal(g, o)
+    rng = np.random.default_rng(nz)
+    init = (rng.uniform(1, 2, grid.shape), rng.uniform(1, 2, grid.shape), rng.uniform(1, 2, grid.shape),
+            rng.integers(1, 90, grid.shape).astype(np.int32))
+    for box in ([-3.1, -2.0, 1.3, 2.2, 3.9, 7.7], [-5.0, -5.0, 0.31, 5.0, 5.0, 0.32], [0.1, 0.1, 5.0, 0.2, 0.2, 11.9]):
+        g, o = _both_k1(mct, pts, par, grid, np.array(box), init=init)
+        _assert_k1_equal(g, o)
+
+
+def test_k1_batch_with_odd_model_stride(mct):
+    """A batch whose models have an odd number of nodes: model b's arrays start 8 bytes off a 16-byte boundary for odd b."""
+    from mctomo_b200 import capi
+    grid = synth.make_grid(7, 5, 9)   # 315 nodes
+    freqs = synth.freqs(3)
+    models = [synth.generate_model(grid, 20 + 3 * b, 50 + b) for b in range(3)]
+    pts, par, off = capi.pack_models(models)
+    r = mct.forward_eval_batch(pts, par, off, grid, freqs, disp_opts(), want_model=True)
+    for b in range(3):
+        o = orc.forward_eval(*models[b], grid, freqs)
+        assert np.array_equal(r["sites_id"][b], o["sites_id"]) and np.array_equal(r["vs"][b], o["vs"])
+        assert np.array_equal(r["rho"][b], o["rho"]) and np.array_equal(r["pvel"][b], o["pvel"])
 
 
 def test_k1_one_child_tree_nodes(mct):
@@ -305,6 +337,116 @@ def test_full_size_c3_sampled_against_oracle(mct, raylov):
         rc, p0, g0, e0, _ = orc.surfmodes(th, al, be, rk, freqs, raylov, 1, 2)
         assert rc == 0 and e0 == ie[i, j]
         assert np.array_equal(p0, r["pvel"][i, j]) and np.array_equal(g0, r["gvel"][i, j])
+
+
+def test_full_size_c2x32_sampled_against_oracle(mct):
+    """The very workload bench.py times: BASELINE config C2 (64x64x40, 20 periods, Rayleigh phase, 300 nuclei) as a
+    batch of 32 models through mct_forward_eval_batch.  Model 0 and model 17 are compared with the oracle in full
+    (PORTABLE: bit-identical incl. both work counters; LIBM: float32-identical count reported, phase within 1e-5 km/s);
+    ten random columns of every other model are re-solved by the oracle."""
+    from mctomo_b200 import capi
+    grid = synth.make_grid(64, 64, 40)
+    freqs = synth.freqs(20)
+    models = [synth.generate_model(grid, 300, 1000 + 2 + b) for b in range(32)]   # bench.py's seeds on rank 0
+    pts, par, off = capi.pack_models(models)
+    opts = disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    mct.reset_stats()
+    r = mct.forward_eval_batch(pts, par, off, grid, freqs, opts, want_model=True)
+    st = mct.stats()
+    assert r["pvel"].shape == (32, 64, 64, 20) and not r["ierr"].any() and not np.any(r["model_invalid"])
+    assert (r["pvel"] > 1.5).all() and (r["pvel"] < 6.1).all() and (np.diff(r["pvel"], axis=-1) > -1e-3).all()
+    assert st["n_columns"] == 32 * 4096 and 0 < st["n_columns_solved"] <= st["n_columns"]
+    nd = nl = 0
+    for b in (0, 17):
+        o = orc.forward_eval(*models[b], grid, freqs)
+        assert np.array_equal(r["sites_id"][b], o["sites_id"]) and np.array_equal(r["vs"][b], o["vs"])
+        assert np.array_equal(r["pvel"][b], o["pvel"]) and np.array_equal(r["ierr"][b], o["ierr"])
+        ol = orc.forward_eval(*models[b], grid, freqs, math_mode=orc.LIBM)
+        diff = r["pvel"][b] != ol["pvel"]
+        print(f"model {b}: {int(diff.sum())} of {diff.size} phase velocities differ from the libm-mode oracle "
+              f"(max {np.abs(r['pvel'][b] - ol['pvel']).max():.3g} km/s)")
+        assert diff.mean() <= 1e-4 and np.abs(r["pvel"][b] - ol["pvel"]).max() <= TOL
+    rng = np.random.default_rng(32)
+    for b in range(32):
+        for i, j in zip(rng.integers(0, 64, 10), rng.integers(0, 64, 10)):
+            n, (th, al, be, rk) = orc.convert_column(r["vp"][b, i, j], r["vs"][b, i, j], r["rho"][b, i, j], grid.dz)
+            rc, p0, g0, e0, _ = orc.surfmodes(th, al, be, rk, freqs, 1, 0, 0)
+            assert rc == 0 and e0 == 0 and np.array_equal(p0, r["pvel"][b, i, j])
+
+
+@pytest.mark.parametrize("ncells", [25, 100, 300])
+def test_full_size_c1_example1_as_shipped(mct, ncells):
+    """BASELINE config C1: example1's grid (101x101x121, examples/example1/MCTomo.inp:20-22) with the 11 frequencies of
+    examples/example1/otimes.dat:2 AS SHIPPED (0.333333, 0.166667, ... not exact reciprocals), Rayleigh phase, 25 / 100 /
+    300 cells (the prior's bounds).  Every one of the 10 201 columns is compared with the oracle: outputs, ierr and both
+    work counters; with few cells most columns are duplicates of each other, which the library folds (exactly)."""
+    grid = synth.make_grid(101, 101, 121)
+    freqs = synth.example1_freqs()
+    assert freqs[3] == 0.333333 and len(freqs) == 11
+    pts, par = synth.generate_model(grid, ncells, 1001 + ncells)
+    opts = disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    o = orc.forward_eval(pts, par, grid, freqs)
+    res = {}
+    for dd in (True, False):
+        mct.set_dedup(dd)
+        mct.reset_stats()
+        res[dd] = (mct.forward_eval(pts, par, grid, freqs, opts, want_model=True), mct.stats(), mct.last_launch())
+    mct.set_dedup(True)
+    for dd in (True, False):
+        r, st, li = res[dd]
+        assert np.array_equal(r["sites_id"], o["sites_id"])
+        assert np.array_equal(r["pvel"], o["pvel"]) and np.array_equal(r["ierr"], o["ierr"]), f"dedup={dd}"
+        assert st["n_dltar"] == o["counters"][0] and st["n_layer_steps"] == o["counters"][1] and st["n_columns"] == 10201
+    on, off_ = res[True][1], res[False][1]
+    assert off_["n_columns_solved"] == 10201 and off_["n_dltar_executed"] == off_["n_dltar"]
+    vs = o["vs"].astype(np.float32).reshape(-1, grid.nz)
+    distinct = len(np.unique(vs, axis=0))
+    assert on["n_columns_solved"] == res[True][2]["columns_solved"]
+    assert abs(on["n_columns_solved"] - distinct) <= 2   # (the key is the layered stack; float32 cell sequences agree with it
+    #                                                       unless two nuclei's vs collide within float32 rounding)
+    assert on["n_dltar_executed"] < on["n_dltar"] or distinct == 10201
+    print(f"C1 {ncells} cells: {distinct} distinct columns of 10201, kernel {res[True][2]['kernel']}")
+    ol = orc.forward_eval(pts, par, grid, freqs, math_mode=orc.LIBM)
+    diff = res[True][0]["pvel"] != ol["pvel"]
+    print(f"  {int(diff.sum())} of {diff.size} phase velocities differ from the libm-mode oracle")
+    assert diff.mean() <= 1e-4 and np.abs(res[True][0]["pvel"] - ol["pvel"]).max() <= TOL
+
+
+def test_dedup_forced_duplicates_all_kernel_shapes(mct):
+    """A model of 5 cells on a 40x40 grid: ~20 distinct columns among 1600.  Every kernel shape must reproduce the
+    oracle for EVERY column (the duplicates' outputs are copied from their representative), with represented counters
+    equal to the oracle's and executed counters equal to the distinct columns' share; phase+group, two modes; a second
+    model in the batch that check_model rejects must stay untouched."""
+    import torch
+    grid = synth.make_grid(40, 40, 30)
+    freqs = synth.freqs(7)
+    pts, par = synth.generate_model(grid, 5, 77)
+    o = orc.forward_eval(pts, par, grid, freqs, phaseGroup=1, nmodes=2)
+    opts = disp_opts(raylov=1, phaseGroup=1, nmodes=2)
+    vs32 = o["vs"].astype(np.float32).reshape(-1, grid.nz)
+    distinct = len(np.unique(vs32, axis=0))
+    assert distinct < 800
+    for lanes in (0, 2, 8, 32, 128):
+        mct.set_k2_lanes(lanes)
+        for mode in ((0, 1) if lanes == 0 else (0,)):
+            mct.set_k2_mode(mode, -1)
+            mct.reset_stats()
+            r = mct.forward_eval(pts, par, grid, freqs, opts)
+            st = mct.stats()
+            assert np.array_equal(r["pvel"], o["pvel"]) and np.array_equal(r["gvel"], o["gvel"]) and np.array_equal(r["ierr"], o["ierr"])
+            assert st["n_dltar"] == o["counters"][0] and st["n_layer_steps"] == o["counters"][1]
+            assert abs(st["n_columns_solved"] - distinct) <= 1 and st["n_columns"] == 1600
+    mct.set_k2_lanes(0)
+    mct.set_k2_mode(0, -1)
+    # batch of two: the second model is invalid (fast cell on top) -> its outputs stay as they were
+    from mctomo_b200 import capi
+    bad = par.copy()
+    bad[int(np.argmin(pts[:, 2])), 1] = 9.0
+    p2, a2, off = capi.pack_models([(pts, par), (pts, bad)])
+    out = {"pvel": np.full((2, 40, 40, 14), -3.0), "gvel": np.full((2, 40, 40, 14), -3.0), "ierr": np.full((2, 40, 40), -3, np.int32)}
+    r = mct.forward_eval_batch(p2, a2, off, grid, freqs, opts, out=out)
+    assert list(r["model_invalid"]) == [0, 1]
+    assert np.array_equal(r["pvel"][0], o["pvel"])
 
 
 def test_full_size_c5_sampled_against_oracle(mct):

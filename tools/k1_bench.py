@@ -11,7 +11,7 @@ for name in sys.argv[1:] or ["C2", "C1", "C3"]:
     ncell = grid.nx * grid.ny * grid.nz
     bufs = [torch.zeros(ncell, dtype=torch.float64, device=dev) for _ in range(3)] + [torch.zeros(ncell, dtype=torch.int32, device=dev)]
     res = []
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         capi.set_k1_mode(mode)
         for b in bufs: b.zero_()
         for _ in range(2):
@@ -24,4 +24,4 @@ for name in sys.argv[1:] or ["C2", "C1", "C3"]:
         ms = kt["k1_ms"] / 5
         res.append([b.clone() for b in bufs])
         print(f"{name} mode {mode}: {ms:8.3f} ms  {ncell/ms/1e6:8.2f} G nodes/s  {28.0*ncell/ms/1e6:8.1f} GB/s", flush=True)
-    print("   identical:", all(torch.equal(a, b) for a, b in zip(*res)))
+    print("   identical:", all(torch.equal(a, b) for a, b in zip(res[0], res[1])) and all(torch.equal(a, b) for a, b in zip(res[0], res[2])))
