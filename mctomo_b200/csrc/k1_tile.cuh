@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256, 2) k1_tile_kernel(const __grid_constant__
       if (lane == 0) atomicMin(&S.phimin, hmin);
     }
     __syncthreads();
-    // a'. compact the nuclei whose nearest approach to the rectangle is within ~2.5 spacings of that one: the only ones
+    // a'. compact the nuclei whose nearest approach to the rectangle is within ~1.25 spacings of that one: the only ones
     //     the segment loops below look at (relative float coordinates + position, 16 bytes each)
     const float r1 = sqrtf(__uint_as_float(S.phimin)) * 1.0001f + near_r;
     const float phi_cut = r1 * r1;
@@ -142,8 +142,11 @@ __global__ void __launch_bounds__(256, 2) k1_tile_kernel(const __grid_constant__
     // b. U_B per segment: lane = segment, the warps share the list (any subset of the nuclei gives a valid upper bound;
     //    the nucleus of step a is in this one, so every U_B is finite)
     if (near_ok) {
-      const int wib = tid >> 5, nw = nthr >> 5;
-      for (int s = lane; s < nseg; s += 32) {
+      // up to 16 segments: the two half-warps split the list between them (lane & 15 = segment)
+      const int split = nseg <= 16 ? 2 : 1;
+      const int sub = split == 2 ? (lane >> 4) : 0;
+      const int wib = (tid >> 5) * split + sub, nw = (nthr >> 5) * split;
+      for (int s = (split == 2 ? (lane & 15) : lane); s < nseg; s += 32) {
         const float mid = S.smid[s], hu = S.shalf_up[s];
         float um = 3.0e38f;
         for (int e = wib; e < N; e += nw) {

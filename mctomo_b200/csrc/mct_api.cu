@@ -317,7 +317,7 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
       const int npairs = (P.wz + 2) / 2;
       const int nitems = ttx * tty * npairs;
       const int threads = nitems <= 640 ? 128 : 256;
-      k1_tile_kernel<<<dim3(blocks, nby), threads, 0, st>>>(P, ttx, tty, seglen, (float)(2.5 * h), k1t_magic(npairs), k1t_magic(tty),
+      k1_tile_kernel<<<dim3(blocks, nby), threads, 0, st>>>(P, ttx, tty, seglen, (float)(1.25 * h), k1t_magic(npairs), k1t_magic(tty),
                                                             k1t_magic(seglen));
     }
   }
