@@ -1,5 +1,8 @@
 #!/bin/bash
-# oracle/build_ref.sh -- builds oracle/_ref/kdtree2_ref from the reference's OWN pre-built
+# oracle/build_ref.sh -- builds the reference-derived checkers under the git-ignored oracle/_ref/:
+#   libsurfdisp96_f2c.so  the reference's surfdisp96.f through oracle/f77toc.py (mechanical F77 -> C) + gcc
+#   surfdisp96_gfortran   the same file compiled by gfortran, where one exists (oracle/build_ref_surfdisp.sh)
+#   kdtree2_ref           from the reference's OWN pre-built
 # object utils/libutils.a:kdtree2.o (linked where it lies; nothing is copied into the repo
 # except the resulting binary under the git-ignored oracle/_ref/).  Needs /root/reference and a
 # libgfortran.so.5 (the one bundled with scipy's wheel).  Exits 0 with a message if either is
@@ -8,6 +11,19 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${MCT_REFERENCE:-/root/reference}"
 OUT="$HERE/_ref"
+# ---- stage 2: the reference's surfmodes/surfdisp96.f, translated mechanically to C (oracle/f77toc.py) and compiled
+# with the strict-IEEE flags of the restatement.  No Fortran compiler is needed; the source is read where it lies.
+if [ -f "$REF/surfmodes/surfdisp96.f" ]; then
+  mkdir -p "$OUT"
+  python "$HERE/f77toc.py" "$REF/surfmodes/surfdisp96.f" "$OUT/surfdisp96_f2c.c"
+  gcc -O2 -fPIC -std=gnu11 -ffp-contract=off -fno-fast-math -shared -o "$OUT/libsurfdisp96_f2c.so" "$OUT/surfdisp96_f2c.c" -lm
+  echo "build_ref: built $OUT/libsurfdisp96_f2c.so from $REF/surfmodes/surfdisp96.f"
+else
+  echo "build_ref: $REF/surfmodes/surfdisp96.f not present, skipping the translated surfdisp96"
+fi
+# ---- and, where a Fortran compiler exists, the real thing (oracle/build_ref_surfdisp.sh)
+if command -v gfortran >/dev/null 2>&1; then "$HERE/build_ref_surfdisp.sh" || true; fi
+# ---- stage 1: the reference's own pre-built kd-tree object
 if [ ! -f "$REF/utils/libutils.a" ]; then echo "build_ref: $REF/utils/libutils.a not present, skipping"; exit 0; fi
 GF="$(python - <<'PY'
 import glob, os, sys

@@ -224,3 +224,38 @@ def surf_misfit(time, ttime, raystat, sigdep=0, nrays_total=None, snoise0=None, 
     rc = fn(t.ctypes.data, nrr, np_, sigdep, nrays_total, tt.ctypes.data, rs.ctypes.data, p(n0), p(n1), p(sd), math_mode,
             out.ctypes.data, sg.ctypes.data)
     return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], sigma=sg, rc=rc)
+
+
+# ---- the reference's own surfdisp96.f, mechanically translated to C (oracle/f77toc.py, oracle/build_ref.sh) ---------
+F2C_LIB = os.path.join(ORACLE_DIR, "_ref", "libsurfdisp96_f2c.so")
+_F2C = None
+
+
+def have_f2c():
+    return os.path.exists(F2C_LIB)
+
+
+def f2c_surfdisp(thick, vp, vs, rho, freqs, iwave, igr, nmodes=0, dphase=1e-3):
+    """Calls the translated surfdisp96 (nmodes <= 0) / surfdisp_mmodes exactly as surfmodes.f90:81-83,93-95 / :155-180
+    call the Fortran: the model narrowed to real*4, periods dble(1/freqs), iflsph = 0.  Returns (cp, cg, ierr) with
+    cp, cg of shape (nm*np,), mode-major like surfmodes.f90:179-180."""
+    global _F2C
+    if _F2C is None:
+        _F2C = C.CDLL(F2C_LIB)
+    n = len(thick)
+    a = [np.zeros(200, np.float32) for _ in range(4)]      # real*4 thkm(NLAY) ...: NLAY = 200
+    for dst, src in zip(a, (thick, vp, vs, rho)):
+        dst[:n] = np.asarray(src, np.float64).astype(np.float32)
+    np_ = len(freqs)
+    t = np.zeros(60)                                       # double precision t(NP), NP = 60
+    t[:np_] = 1.0 / np.asarray(freqs, np.float64)
+    nm = max(nmodes, 1)
+    cp, cg = np.zeros(np_ * nm), np.zeros(np_ * nm)
+    ci = lambda v: C.byref(C.c_int(v))  # noqa: E731
+    ierr = C.c_int(0)
+    dph = C.c_double(dphase)
+    fn = _F2C.surfdisp96_ if nmodes <= 0 else _F2C.surfdisp_mmodes_
+    fn(a[0].ctypes.data_as(C.c_void_p), a[1].ctypes.data_as(C.c_void_p), a[2].ctypes.data_as(C.c_void_p),
+       a[3].ctypes.data_as(C.c_void_p), ci(n), ci(0), ci(iwave), ci(nm), ci(igr), ci(np_), t.ctypes.data_as(C.c_void_p),
+       C.byref(dph), cp.ctypes.data_as(C.c_void_p), cg.ctypes.data_as(C.c_void_p), C.byref(ierr))
+    return cp, cg, ierr.value
