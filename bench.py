@@ -140,10 +140,24 @@ def workload(args, rank, world):
     return grid, models, freqs, batch, spec
 
 
+def workload_config(args, grid, freqs, spec, ncells, batch):
+    """`config` of the JSON line: the SAME dict for both arms (the driver compares them); how each arm runs the
+    workload is described under that arm's own keys (`execution` here, cpu_baseline.sample for the reference)."""
+    return {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
+                        f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={max(spec['nmodes'], 1)}, {ncells} nuclei",
+            "batch_per_gpu": batch,
+            "l2": "GPU arm: a 256 MiB buffer is written between timed steps (L2 flush), and a step's model arrays exceed the "
+                  "126 MB L2 at the default batch; CPU arm: not applicable"}
+
+
 def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
     """Times the oracle (libm math = what the Fortran binary calls) on a bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as orc
+    # the reference's own surfdisp96.f (oracle/_ref: translated to C by oracle/f77toc.py, gcc -O2) when it travelled
+    # with the repository; else the port (libm math, what the Fortran binary calls)
+    mode = orc.REFERENCE if orc.use_reference_solver() else orc.LIBM
+    cpu_sample.kind = "reference" if mode == orc.REFERENCE else "port"
     solves = 0
     t_used = 0.0
     n_evals = 0
@@ -162,7 +176,7 @@ def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
         t2 = time.perf_counter()
         specs = spec if isinstance(spec, list) else [spec]
         for sp in specs:
-            pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (1, wx, 1, grid.ny), freqs, math_mode=orc.LIBM,
+            pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (1, wx, 1, grid.ny), freqs, math_mode=mode,
                                                      nthreads=nthreads, **sp)
             solves += wx * grid.ny * len(freqs) * max(sp["nmodes"], 1)
         t3 = time.perf_counter()
@@ -173,7 +187,14 @@ def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
                   "slab_columns": wx * grid.ny}
         if t_used > budget_s:
             break
-    return solves / t_used, n_evals / t_used, f"{n_evals:.2f} forward evals ({solves} solves) of the workload, {t_used:.1f} s", detail
+    what = ("dispersion by the reference's own surfdisp96.f (oracle/_ref: mechanical C translation, gcc -O2 -- the reference builds "
+            "it without optimisation flags), kd-tree/layering/loops by the C port, OpenMP over x like the reference"
+            if mode == orc.REFERENCE else "C port of the path (oracle/, libm math), OpenMP over x like the reference")
+    return solves / t_used, n_evals / t_used, f"{n_evals:.2f} forward evals ({solves} solves) of the workload, {t_used:.1f} s; {what}", detail
+
+
+cpu_sample.kind = "port"
+
 
 
 def run_reference(args):
@@ -202,10 +223,9 @@ def run_reference(args):
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "forward_evals_per_sec": evr,
-           "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
-                                  f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={max(spec['nmodes'],1)}",
-                      "per_step": "bounded sample of the workload on the host CPU"},
-           "cpu_baseline": {"value": rate, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": workload_config(args, grid, freqs, spec, len(models[0][0]), batch),
+           "execution": {"per_step": "bounded sample of the workload on the host CPU, all host threads"},
+           "cpu_baseline": {"value": rate, "unit": "column*period solves/s", "cores": cores, "kind": cpu_sample.kind, "sample": sample},
            "e2e": {"value": rate, "unit": "column*period solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     GUARD.emit(json.dumps(out))
 
@@ -539,7 +559,7 @@ def main():
             cores = os.cpu_count() or 1
             cspec = [spec, dict(raylov=0, phaseGroup=1, nmodes=2)] if love else spec
             r, e, sample, detail = cpu_sample(grid, models, freqs, cspec, args.cpu_seconds, cores)
-            cpu = {"value": r, "unit": "column*period solves/s", "cores": cores, "kind": "port", "sample": sample,
+            cpu = {"value": r, "unit": "column*period solves/s", "cores": cores, "kind": cpu_sample.kind, "sample": sample,
                    "forward_evals_per_sec": e, "detail": detail}
             if e2e:
                 # share of the forward model's wall time that now runs on the GPU: what is left on the host in the
@@ -555,13 +575,10 @@ def main():
                "waves": "Rayleigh + Love" if love else "Rayleigh",
                # one solve = one (column, period, wave, mode) output; a group-velocity output costs two root searches
                "getsol_calls_per_sec": value * (2 if spec["phaseGroup"] else 1),
-               "config": {"workload": f"{args.config}: {grid.nx}x{grid.ny}x{grid.nz} grid, {len(freqs)} periods, Rayleigh "
-                                      f"{'phase+group' if spec['phaseGroup'] else 'phase'}, modes={nm}, "
-                                      f"{len(models[0][0])} nuclei",
-                          "batch_per_gpu": batch, "parallelism": ("x-slab column sharding + in-place ncclAllGather of the maps inside the library (mct_forward_sharded_dev)" if column_sharded
-                                                                 else f"chains sharded, {world} x {batch} independent models, no collective"),
-                          "l2": "256 MiB buffer written between timed steps (L2 flush); model arrays per step also exceed L2"
-                          if batch * ncell * 28 > (126 << 20) else "256 MiB buffer written between timed steps (L2 flush)"},
+               "config": workload_config(args, grid, freqs, spec, len(models[0][0]), batch),
+               "execution": {"parallelism": ("x-slab column sharding + in-place ncclAllGather of the maps inside the library (mct_forward_sharded_dev)" if column_sharded
+                                             else f"chains sharded, {world} x {batch} independent models, no collective"),
+                             "model_bytes_per_step": int(batch * ncell * 28)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["n_launches"]), "roofline": roof, "cpu_baseline": cpu,
                "proposal_latency": {"columns": (pw[1] - pw[0] + 1) * (pw[3] - pw[2] + 1), "ms": proposal_ms,
                                     "what": "check_model + layering + dispersion of a 20x20-column window, device-resident model, cooperative kernel (several warps per column)"},

@@ -595,6 +595,15 @@ int orc_nlvls1(const double* vp, const double* vs, int n, int modetype) {
  * (nlvls1 != 0), which this oracle does not restate; outputs are then left untouched.
  * counters[0] += dltar calls, counters[1] += layer steps (may be NULL).
  */
+/* Optional: the REFERENCE'S OWN surfdisp96 / surfdisp_mmodes (oracle/_ref/libsurfdisp96_f2c.so, the reference's
+ * surfdisp96.f translated to C by oracle/f77toc.py; Fortran calling convention: every argument by reference).  When
+ * set, math_mode == 2 routes the solve through them instead of the restatement: used by bench.py's reference arm
+ * (cpu_baseline.kind "reference") and by the tests that compare the two.  Work counters are then not available. */
+typedef void (*ref_surfdisp_fn)(void* thk, void* vp, void* vs, void* rho, void* nlayer, void* iflsph, void* iwave, void* mode,
+                                void* igr, void* kmax, void* t, void* dphase, void* cp, void* cg, void* ierr);
+static ref_surfdisp_fn g_ref96 = 0, g_refmm = 0;
+void orc_set_reference_solver(void* f96, void* fmm) { g_ref96 = (ref_surfdisp_fn)f96; g_refmm = (ref_surfdisp_fn)fmm; }
+
 int orc_surfmodes(const double* thick, const double* vp, const double* vs, const double* rho, int n,
                   const double* freqs, int np, int modetype, int phaseGroup, int nmodes, double dc,
                   int math_mode, double* phase, double* group, int* ierr, int64_t* counters) {
@@ -602,6 +611,20 @@ int orc_surfmodes(const double* thick, const double* vp, const double* vs, const
   int lv = orc_nlvls1(vp, vs, n, modetype);
   *ierr = 0;
   if (lv != 0) return 2;
+  if (math_mode == 2) {
+    if (!g_ref96 || !g_refmm) return 9;
+    float th4[NL], a4[NL], b4[NL], r4[NL];
+    memset(th4, 0, sizeof th4); memset(a4, 0, sizeof a4); memset(b4, 0, sizeof b4); memset(r4, 0, sizeof r4);
+    for (int i = 0; i < n; ++i) { th4[i] = (float)thick[i]; a4[i] = (float)vp[i]; b4[i] = (float)vs[i]; r4[i] = (float)rho[i]; }
+    double tt[NP];
+    memset(tt, 0, sizeof tt);
+    for (int i = 0; i < np; ++i) tt[i] = 1 / freqs[i];
+    int iflsph = 0, iwave = (modetype == 1) ? 2 : 1, mode = nmodes <= 0 ? 1 : nmodes, igr = phaseGroup, kmax = np, ie = 0;
+    double dph = dc;
+    (nmodes <= 0 ? g_ref96 : g_refmm)(th4, a4, b4, r4, &n, &iflsph, &iwave, &mode, &igr, &kmax, tt, &dph, phase, group, &ie);
+    *ierr = ie;
+    return 0;
+  }
   sd_ctx S;
   memset(&S, 0, sizeof S);
   S.mmax = n;

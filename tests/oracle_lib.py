@@ -12,6 +12,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "kdtree2_ref")
 
 LIBM, PORTABLE = 0, 1
+REFERENCE = 2   # math_mode 2: the reference's own surfdisp96.f (oracle/_ref, see use_reference_solver)
 
 
 class orc_grid(C.Structure):
@@ -259,3 +260,17 @@ def f2c_surfdisp(thick, vp, vs, rho, freqs, iwave, igr, nmodes=0, dphase=1e-3):
        a[3].ctypes.data_as(C.c_void_p), ci(n), ci(0), ci(iwave), ci(nm), ci(igr), ci(np_), t.ctypes.data_as(C.c_void_p),
        C.byref(dph), cp.ctypes.data_as(C.c_void_p), cg.ctypes.data_as(C.c_void_p), C.byref(ierr))
     return cp, cg, ierr.value
+
+
+def use_reference_solver():
+    """Hands the translated reference's surfdisp96_ / surfdisp_mmodes_ to liboracle: math_mode=REFERENCE then solves every
+    column with the reference's own code (layering, kd-tree and loops stay the port's).  False when oracle/_ref is absent."""
+    global _F2C
+    if not have_f2c():
+        return False
+    if _F2C is None:
+        _F2C = C.CDLL(F2C_LIB)
+    fn = L().orc_set_reference_solver
+    fn.argtypes = [C.c_void_p, C.c_void_p]
+    fn(C.cast(_F2C.surfdisp96_, C.c_void_p), C.cast(_F2C.surfdisp_mmodes_, C.c_void_p))
+    return True
