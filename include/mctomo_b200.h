@@ -255,6 +255,23 @@ int mct_forward_sharded_dev(const mct_grid* g, int derive_vp_rho, const double* 
 /* Device milliseconds the collectives of the last mct_forward_sharded_dev call took (synchronises). */
 int mct_comm_last_ms(double* ms);
 
+/* ---- the 2-D product and point location ---------------------------------------------------------------
+ * kdtree_to_grid of the 2-D variant (mcmc2d/mcmc.f90:1469-1526): nuclei points2 (2,ncells), every node of the (ny,nx)
+ * grid (element (j,i) at [(i-1)*ny + (j-1)]), query point (xmin+(i-1)dx, ymin+(j-1)dy).  Same cells as kdtree2 run with
+ * two dimensions, ties included. */
+int mct_voronoi_to_grid_2d(const double* points2, const double* params, int ncells, int nx, int ny, double xmin,
+                           double ymin, double dx, double dy, double* vp, double* vs, double* rho, int32_t* sites_id);
+/* kdtree_locate (mcmc2d/mcmc.f90:1528-1551) for a batch: the nucleus (1-based) nearest to each of nq query points;
+ * points (dim,ncells), queries (dim,nq), dim = 2 or 3. */
+int mct_nearest_nucleus(const double* points, int dim, int ncells, const double* queries, int64_t nq, int32_t* idx);
+/* sites_locate (src/likelihood_body.F90:799-831) for a batch of 3-D points: the cell index of the node below the point
+ * (point2idx, :1038-1054) when its eight neighbours agree, else kdtree2's nearest nucleus.  sites_id (nz,ny,nx): host
+ * array, or device array for the _dev form (e.g. a session's resident cell map). */
+int mct_sites_locate(const double* points, int ncells, const int32_t* sites_id, const mct_grid* g, const double* queries,
+                     int64_t nq, int32_t* idx);
+int mct_sites_locate_dev(const double* points, int ncells, const int32_t* d_sites_id, const mct_grid* g,
+                         const double* queries, int64_t nq, int32_t* idx);
+
 /* ---- measurement helpers ----------------------------------------------------------------------
  * mct_set_profiling(1) brackets every kernel launch with CUDA events on the launching stream;
  * mct_kernel_times returns accumulated milliseconds {K1 nearest-nucleus, K2 dispersion, other kernels,

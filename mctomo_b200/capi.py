@@ -752,3 +752,37 @@ def comm_last_ms() -> float:
     v = C.c_double(0.0)
     _check(lib().mct_comm_last_ms(C.byref(v)))
     return v.value
+
+
+# ---- the 2-D product and point location ---------------------------------------------------------------
+def voronoi_to_grid_2d(points2, params, nx, ny, xmin, ymin, dx, dy):
+    """kdtree_to_grid of the 2-D variant (mcmc2d/mcmc.f90:1469-1526): returns vp, vs, rho (nx, ny) and sites_id."""
+    p2, par = _f64(points2), _f64(params)
+    vp, vs, rho = (np.zeros((nx, ny)) for _ in range(3))
+    sid = np.zeros((nx, ny), np.int32)
+    L = lib()
+    L.mct_voronoi_to_grid_2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4 + [C.c_void_p] * 4
+    _check(L.mct_voronoi_to_grid_2d(p2.ctypes.data, par.ctypes.data, len(p2), nx, ny, xmin, ymin, dx, dy, vp.ctypes.data,
+                                    vs.ctypes.data, rho.ctypes.data, sid.ctypes.data))
+    return vp, vs, rho, sid
+
+
+def nearest_nucleus(points, queries):
+    """kdtree_locate for a batch (dim 2 or 3): 1-based index of the nearest nucleus of every query point."""
+    p, q = _f64(points), _f64(queries)
+    out = np.zeros(len(q), np.int32)
+    L = lib()
+    L.mct_nearest_nucleus.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    _check(L.mct_nearest_nucleus(p.ctypes.data, p.shape[1], len(p), q.ctypes.data, len(q), out.ctypes.data))
+    return out
+
+
+def sites_locate(points, sites_id, grid: Grid, queries):
+    """sites_locate (src/likelihood_body.F90:799-831) for a batch of 3-D points; sites_id: host (nx,ny,nz) int32."""
+    p, q = _f64(points), _f64(queries)
+    sid = np.ascontiguousarray(sites_id, dtype=np.int32)
+    out = np.zeros(len(q), np.int32)
+    L = lib()
+    L.mct_sites_locate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(mct_grid), C.c_void_p, C.c_int64, C.c_void_p]
+    _check(L.mct_sites_locate(p.ctypes.data, len(p), sid.ctypes.data, C.byref(grid.c()), q.ctypes.data, len(q), out.ctypes.data))
+    return out

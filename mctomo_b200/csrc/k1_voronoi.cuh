@@ -153,6 +153,37 @@ __global__ void __launch_bounds__(256) k1_voronoi_kernel(const __grid_constant__
   }
 }
 
+// ---- nearest nucleus of ARBITRARY query points (not grid nodes) ------------------------------------------------------
+// kdtree_locate (reference mcmc2d/mcmc.f90:1528-1551) and sites_locate (src/likelihood_body.F90:799-831): one thread
+// per query walks kdtree2's traversal.  With d_sites != NULL the reference's shortcut is applied first: when the eight
+// nodes around the point carry the same cell index, that index is the answer and the tree is not consulted.
+__global__ void __launch_bounds__(128) k1_points_kernel(const __grid_constant__ K1Params P, const double* __restrict__ q, long long nq,
+                                                        const int32_t* __restrict__ d_sites, int nx, int ny, int nz, double scaling,
+                                                        int32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  const double x = q[3 * t], y = q[3 * t + 1], z = q[3 * t + 2];
+  if (d_sites) {
+    // point2idx, src/likelihood_body.F90:1038-1054 (zmin and dz arrive scaled, as grid_setup stores them)
+    int ix = (int)floor((x - P.xmin) / P.dx) + 1;
+    int iy = (int)floor((y - P.ymin) / P.dy) + 1;
+    int iz = (int)floor((z - P.zmin / scaling) / (P.dz / scaling)) + 1;
+    if (ix < 1) ix = 1;
+    if (iy < 1) iy = 1;
+    if (iz < 1) iz = 1;
+    if (ix >= nx) ix = nx - 1;
+    if (iy >= ny) iy = ny - 1;
+    if (iz >= nz) iz = nz - 1;
+    const int32_t idx = d_sites[((size_t)(ix - 1) * ny + (size_t)(iy - 1)) * nz + (size_t)(iz - 1)];
+    int num = 0;
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k) num += abs(d_sites[((size_t)(ix - 1 + i) * ny + (size_t)(iy - 1 + j)) * nz + (size_t)(iz - 1 + k)] - idx);
+    if (num == 0) { out[t] = idx; return; }
+  }
+  out[t] = kd_nearest_dev(P, x, y, z, P.err);
+}
+
 #include "k1_column.cuh" // k1_column_kernel: culled brute force per column, tree walk only for (near-)ties (round-1 shape)
 #include "k1_tile.cuh"   // k1_tile_kernel: per-(column, z-segment) candidate lists, vector stores (production)
 

@@ -298,7 +298,8 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
       // to h/2, segments of h/2.  Larger boxes make the bound U_B loose (long lists), smaller ones repeat the passes over
       // the nuclei for too few nodes (measured: C2 with 1 x 4 tiles spent 90 % of its instructions in those passes).
       const double vol = std::max(gr->dx * (gr->nx - 1), gr->dx) * std::max(gr->dy * (gr->ny - 1), gr->dy) * std::max(gr->dz * (gr->nz - 1), gr->dz);
-      const double h = std::cbrt(vol / (double)std::max(1, P.n));
+      const double h = gr->nz > 1 ? std::cbrt(vol / (double)std::max(1, P.n))
+                                  : std::sqrt(std::max(gr->dx * (gr->nx - 1), gr->dx) * std::max(gr->dy * (gr->ny - 1), gr->dy) / (double)std::max(1, P.n)); // (the 2-D product)
       static const int shapes[5][2] = {{8, 32}, {4, 16}, {2, 8}, {1, 8}, {1, 4}};
       int ttx = 1, tty = 4;
       for (const auto& sh : shapes) {
@@ -1235,6 +1236,91 @@ int mct_assemble_vel_dev(const double* d_pvel, int np, int nx, int ny, int ix0, 
   }
   g.host_stats.n_launches += 1;
   return MCT_OK;
+}
+
+// ---- the 2-D product and point location -----------------------------------------------------------------
+// 2-D nuclei are embedded with z = 0: kdtree2's build never cuts a zero-extent dimension and a zero third term changes
+// no sum, so tree, traversal and tie order are those of kdtree2 run with dim = 2 (pinned on kdtree2.o: fixture grid2d).
+static void embed_2d(const double* p2, int n, std::vector<double>& p3) {
+  p3.resize(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) { p3[3 * (size_t)i] = p2[2 * (size_t)i]; p3[3 * (size_t)i + 1] = p2[2 * (size_t)i + 1]; p3[3 * (size_t)i + 2] = 0.0; }
+}
+
+int mct_voronoi_to_grid_2d(const double* points2, const double* params, int ncells, int nx, int ny, double xmin, double ymin,
+                           double dx, double dy, double* vp, double* vs, double* rho, int32_t* sites_id) {
+  NEED_INIT();
+  if (!points2 || !params || ncells < 1 || nx < 1 || ny < 1 || !(dx > 0) || !(dy > 0)) return fail(MCT_E_INVALID_ARG, "voronoi_to_grid_2d: bad arguments");
+  std::vector<double> p3;
+  embed_2d(points2, ncells, p3);
+  mct_grid g3 = {nx, ny, 1, xmin, ymin, 0.0, dx, dy, 1.0, 0.0, 1.0};
+  const double box[6] = {xmin - dx, ymin - dy, -1.0, xmin + nx * dx, ymin + ny * dy, 1.0}; // every node (mcmc2d/mcmc.f90:1497-1500)
+  return mct_voronoi_to_grid(p3.data(), params, ncells, &g3, box, nullptr, vp, vs, rho, sites_id);
+}
+
+static int points_query(const double* points, int dim, int ncells, const double* queries, long long nq, const int32_t* d_sites,
+                        const mct_grid* gr, int32_t* out) {
+  if (!points || (dim != 2 && dim != 3) || ncells < 1 || !queries || nq < 0 || !out) return fail(MCT_E_INVALID_ARG, "nearest_nucleus: bad arguments");
+  if (nq == 0) return MCT_OK;
+  cudaStream_t st = g.stream;
+  std::vector<double> p3, q3;
+  const double* P3 = points;
+  const double* Q3 = queries;
+  if (dim == 2) {
+    embed_2d(points, ncells, p3);
+    q3.resize(3 * (size_t)nq);
+    for (long long i = 0; i < nq; ++i) { q3[3 * i] = queries[2 * i]; q3[3 * i + 1] = queries[2 * i + 1]; q3[3 * i + 2] = 0.0; }
+    P3 = p3.data(); Q3 = q3.data();
+  }
+  std::vector<double> dummy_par(3 * (size_t)ncells, 0.0);
+  int rc = upload_nuclei(P3, dummy_par.data(), ncells, st);
+  if (rc) return rc;
+  if ((rc = ensure(g.ray_pts, (size_t)nq * 24)) || (rc = ensure(g.ray_off, (size_t)nq * 4))) return rc;
+  CK(cudaMemcpyAsync(g.ray_pts.p, Q3, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st)); // q3 / p3 are function-local
+  K1Params P;
+  memset(&P, 0, sizeof P);
+  P.nodes = (const KdNodeDev*)g.nodes.p; P.rpts = (const double*)g.rpts.p; P.ind = (const int32_t*)g.ind.p; P.params = (const double*)g.params.p;
+  P.root = g.roots[0]; P.n = ncells;
+  if (gr) { P.xmin = gr->xmin; P.ymin = gr->ymin; P.zmin = gr->zmin; P.dx = gr->dx; P.dy = gr->dy; P.dz = gr->dz; }
+  P.err = (int32_t*)g.flags.p + 2;
+  CK(cudaMemsetAsync(P.err, 0, sizeof(int32_t), st));
+  {
+    ProfScope ps(0, st);
+    k1_points_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(P, (const double*)g.ray_pts.p, nq, d_sites, gr ? gr->nx : 0, gr ? gr->ny : 0,
+                                                                  gr ? gr->nz : 0, gr ? gr->scaling : 1.0, (int32_t*)g.ray_off.p);
+  }
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  int32_t k1err = 0;
+  CK(cudaMemcpyAsync(out, g.ray_off.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&k1err, P.err, sizeof k1err, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (k1err) return fail(MCT_E_CUDA, "nearest-nucleus traversal stack overflow (tree deeper than %d)", K1_STACK);
+  return MCT_OK;
+}
+
+int mct_nearest_nucleus(const double* points, int dim, int ncells, const double* queries, int64_t nq, int32_t* idx) {
+  NEED_INIT();
+  return points_query(points, dim, ncells, queries, (long long)nq, nullptr, nullptr, idx);
+}
+
+int mct_sites_locate_dev(const double* points, int ncells, const int32_t* d_sites_id, const mct_grid* gr, const double* queries,
+                         int64_t nq, int32_t* idx) {
+  NEED_INIT();
+  if (!d_sites_id || !grid_ok(gr) || gr->nx < 2 || gr->ny < 2 || gr->nz < 2 || !(gr->scaling != 0.0))
+    return fail(MCT_E_INVALID_ARG, "sites_locate: bad arguments (the eight-node stencil needs nx, ny, nz >= 2)");
+  return points_query(points, 3, ncells, queries, (long long)nq, d_sites_id, gr, idx);
+}
+
+int mct_sites_locate(const double* points, int ncells, const int32_t* sites_id, const mct_grid* gr, const double* queries, int64_t nq,
+                     int32_t* idx) {
+  NEED_INIT();
+  if (!sites_id || !grid_ok(gr)) return fail(MCT_E_INVALID_ARG, "sites_locate: bad arguments");
+  const size_t nn = (size_t)gr->nx * gr->ny * gr->nz;
+  int rc = ensure(g.m_sites, nn * 4);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(g.m_sites.p, sites_id, nn * 4, cudaMemcpyHostToDevice, g.stream));
+  return mct_sites_locate_dev(points, ncells, (const int32_t*)g.m_sites.p, gr, queries, nq, idx);
 }
 
 } // extern "C"

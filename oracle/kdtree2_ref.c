@@ -342,3 +342,31 @@ void orc_kdtree2_ind(const void* tp, int* ind) {
   const ktree* T = (const ktree*)tp;
   for (int i = 1; i <= T->n; ++i) ind[i - 1] = T->ind[i];
 }
+
+/* sites_locate: src/likelihood_body.F90:799-831 with point2idx :1038-1054.  queries (3,nq); out 1-based cell index. */
+int orc_sites_locate(const double* points, int ncells, const int* sites_id, const orc_grid* g, const double* q, int64_t nq, int* out) {
+  void* T = orc_kdtree2_create(points, ncells);
+  if (!T) return 1;
+  for (int64_t t = 0; t < nq; ++t) {
+    const double* p = q + 3 * t;
+    int ix = (int)floor((p[0] - g->xmin) / g->dx) + 1;
+    int iy = (int)floor((p[1] - g->ymin) / g->dy) + 1;
+    int iz = (int)floor((p[2] - g->zmin / g->scaling) / (g->dz / g->scaling)) + 1;
+    if (ix < 1) ix = 1;
+    if (iy < 1) iy = 1;
+    if (iz < 1) iz = 1;
+    if (ix >= g->nx) ix = g->nx - 1;
+    if (iy >= g->ny) iy = g->ny - 1;
+    if (iz >= g->nz) iz = g->nz - 1;
+#define SID(k, j, i) sites_id[((size_t)((i) - 1) * g->ny + (size_t)((j) - 1)) * g->nz + (size_t)((k) - 1)]
+    const int idx = SID(iz, iy, ix);
+    int num = 0;
+    for (int i = 1; i <= 2; ++i)
+      for (int j = 1; j <= 2; ++j)
+        for (int k = 1; k <= 2; ++k) num = num + abs(SID(iz + k - 1, iy + j - 1, ix + i - 1) - idx);
+#undef SID
+    out[t] = (num == 0) ? idx : orc_kdtree2_nearest(T, p, NULL);
+  }
+  orc_kdtree2_destroy(T);
+  return 0;
+}

@@ -10,8 +10,8 @@
  * exactly as kdtree_to_grid does.  No reference source is copied: the object is linked
  * where it lies (see oracle/build_ref.sh); the executable lands in oracle/_ref/.
  *
- * Usage: kdtree2_ref <in.bin> <out.bin>
- *   in : int64 n, int64 nq, double points[3*n], double queries[3*nq]
+ * Usage: kdtree2_ref <in.bin> <out.bin> [dim]     dim = 3 (default) or 2 (the 2-D product, mcmc2d/mcmc.f90:1469-1556)
+ *   in : int64 n, int64 nq, double points[dim*n], double queries[dim*nq]
  *   out: int32 idx[nq] (1-based), double dis[nq]
  */
 #include <stddef.h>
@@ -34,23 +34,25 @@ extern void __kdtree2_module_MOD_kdtree2_n_nearest(void** tp, gf_desc1* qv, int*
 extern void __kdtree2_module_MOD_kdtree2_destroy(void** tp);
 
 int main(int argc, char** argv) {
-  if (argc != 3) { fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
+  if (argc != 3 && argc != 4) { fprintf(stderr, "usage: %s in.bin out.bin [dim]\n", argv[0]); return 2; }
+  const int D = argc == 4 ? atoi(argv[3]) : 3;
+  if (D != 2 && D != 3) return 2;
   FILE* f = fopen(argv[1], "rb");
   if (!f) { perror("in"); return 2; }
   int64_t n, nq;
   if (fread(&n, 8, 1, f) != 1 || fread(&nq, 8, 1, f) != 1) return 2;
-  double* pts = malloc(sizeof(double) * 3 * (size_t)n);
-  double* q = malloc(sizeof(double) * 3 * (size_t)nq);
-  if (fread(pts, 8, 3 * (size_t)n, f) != 3 * (size_t)n) return 2;
-  if (fread(q, 8, 3 * (size_t)nq, f) != 3 * (size_t)nq) return 2;
+  double* pts = malloc(sizeof(double) * D * (size_t)n);
+  double* q = malloc(sizeof(double) * D * (size_t)nq);
+  if (fread(pts, 8, D * (size_t)n, f) != D * (size_t)n) return 2;
+  if (fread(q, 8, D * (size_t)nq, f) != D * (size_t)nq) return 2;
   fclose(f);
 
   gf_desc2 d;
   d.base = pts;
   d.dtype = DT_R8_RANK2;
-  d.dim[0].stride = 1; d.dim[0].lbound = 1; d.dim[0].ubound = 3;
-  d.dim[1].stride = 3; d.dim[1].lbound = 1; d.dim[1].ubound = n;
-  d.offset = -(1 * 1 + 1 * 3);
+  d.dim[0].stride = 1; d.dim[0].lbound = 1; d.dim[0].ubound = D;
+  d.dim[1].stride = D; d.dim[1].lbound = 1; d.dim[1].ubound = n;
+  d.offset = -(1 * 1 + 1 * D);
   int sort = 0, rearr = 1;
   void* tree = __kdtree2_module_MOD_kdtree2_create(&d, NULL, &sort, &rearr);
 
@@ -59,8 +61,8 @@ int main(int argc, char** argv) {
   for (int64_t i = 0; i < nq; ++i) {
     kd_result res[1];
     gf_desc1 dq, dr;
-    dq.base = q + 3 * i; dq.dtype = DT_R8_RANK1; dq.offset = -1;
-    dq.dim[0].stride = 1; dq.dim[0].lbound = 1; dq.dim[0].ubound = 3;
+    dq.base = q + D * i; dq.dtype = DT_R8_RANK1; dq.offset = -1;
+    dq.dim[0].stride = 1; dq.dim[0].lbound = 1; dq.dim[0].ubound = D;
     dr.base = res; dr.dtype = DT_DERIVED16_RANK1; dr.offset = -1;
     dr.dim[0].stride = 1; dr.dim[0].lbound = 1; dr.dim[0].ubound = 1;
     int nn = 1;

@@ -67,8 +67,13 @@ def f64(a):
 
 
 def kd_nearest(points, queries):
-    """Oracle kdtree2 1-NN: returns (idx 1-based int32, squared distance)."""
+    """Oracle kdtree2 1-NN: returns (idx 1-based int32, squared distance).  2-D points/queries are embedded with z = 0:
+    kdtree2's build never cuts a zero-extent dimension and a zero third term changes no sum (pinned against kdtree2.o
+    run with dim = 2: tests/test_oracle_kdtree.py, fixture grid2d)."""
     points, queries = f64(points), f64(queries)
+    if points.shape[1] == 2:
+        points = np.ascontiguousarray(np.column_stack([points, np.zeros(len(points))]))
+        queries = np.ascontiguousarray(np.column_stack([queries, np.zeros(len(queries))]))
     T = L().orc_kdtree2_create(points.ctypes.data, len(points))
     if not T:
         raise ValueError("degenerate nuclei")
@@ -84,14 +89,15 @@ def have_ref_binary():
 
 
 def ref_kd_nearest(points, queries):
-    """The reference's own kdtree2.o (oracle/_ref/kdtree2_ref, built by oracle/build_ref.sh)."""
+    """The reference's own kdtree2.o (oracle/_ref/kdtree2_ref, built by oracle/build_ref.sh); 3-D or 2-D points."""
     points, queries = f64(points), f64(queries)
+    dim = points.shape[1]
     with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, "in.bin"), "wb") as f:
             f.write(np.array([len(points), len(queries)], np.int64).tobytes())
             f.write(points.tobytes())
             f.write(queries.tobytes())
-        subprocess.check_call([REF_BIN, os.path.join(d, "in.bin"), os.path.join(d, "out.bin")])
+        subprocess.check_call([REF_BIN, os.path.join(d, "in.bin"), os.path.join(d, "out.bin"), str(dim)])
         b = open(os.path.join(d, "out.bin"), "rb").read()
     n = len(queries)
     return np.frombuffer(b[:4 * n], np.int32).copy(), np.frombuffer(b[4 * n:], np.float64).copy()
@@ -274,3 +280,16 @@ def use_reference_solver():
     fn.argtypes = [C.c_void_p, C.c_void_p]
     fn(C.cast(_F2C.surfdisp96_, C.c_void_p), C.cast(_F2C.surfdisp_mmodes_, C.c_void_p))
     return True
+
+
+def sites_locate(points, sites_id, grid, queries):
+    """sites_locate (likelihood_body.F90:799-831) for a batch of 3-D points."""
+    points, queries = f64(points), f64(queries)
+    sid = np.ascontiguousarray(sites_id, dtype=np.int32)
+    out = np.zeros(len(queries), np.int32)
+    fn = L().orc_sites_locate
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(orc_grid), C.c_void_p, C.c_int64, C.c_void_p]
+    og = ogrid(grid)
+    if fn(points.ctypes.data, len(points), sid.ctypes.data, C.byref(og), queries.ctypes.data, len(queries), out.ctypes.data):
+        raise ValueError("degenerate nuclei")
+    return out

@@ -151,6 +151,33 @@ def test_k1_one_child_tree_nodes(mct):
         _assert_k1_equal(a, o)
 
 
+def test_2d_product_and_point_location(mct):
+    """kdtree_to_grid of the 2-D variant (mcmc2d/mcmc.f90:1469-1526), kdtree_locate (:1528-1551) and
+    sites_locate (src/likelihood_body.F90:799-831).  2-D cells against fixtures made with the reference's kdtree2.o run
+    with dim = 2 (random nuclei on grid nodes; a lattice with exact ties and duplicates)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kdtree2_ref.npz"))
+    p2 = np.ascontiguousarray(g["grid2d_points"])
+    par = np.stack([np.arange(len(p2)) + 1.0, np.arange(len(p2)) + 0.5, np.ones(len(p2))], 1)
+    vp, vs, rho, sid = mct.voronoi_to_grid_2d(p2, par, 41, 37, -5.0, -5.0, 0.25, 10.0 / 36)
+    # the fixture's queries are linspace nodes; the library's are xmin + (i-1)*dx: compare through the oracle on ITS nodes
+    q = np.stack(np.meshgrid(-5.0 + np.arange(41) * 0.25, -5.0 + np.arange(37) * (10.0 / 36), indexing="ij"), -1).reshape(-1, 2)
+    ref, _ = orc.kd_nearest(p2, q)
+    assert np.array_equal(sid.reshape(-1), ref) and np.array_equal(vs.reshape(-1), par[ref - 1, 1])
+    assert (sid.reshape(-1) == g["grid2d_idx"]).mean() > 0.99           # same cells as the fixture wherever the nodes coincide bitwise
+    for case in ("grid2d", "lattice2d"):                                 # kdtree_locate on the fixtures' own query points
+        got = mct.nearest_nucleus(g[f"{case}_points"], g[f"{case}_queries"])
+        assert np.array_equal(got, g[f"{case}_idx"]), case
+    got3 = mct.nearest_nucleus(g["lattice_ties_points"], g["lattice_ties_queries"])
+    assert np.array_equal(got3, g["lattice_ties_idx"])
+    # sites_locate
+    grid = synth.make_grid(14, 13, 11)
+    pts, par3 = synth.generate_model(grid, 30, 8)
+    m = _empty_model(grid)
+    orc.kdtree_to_grid(pts, par3, grid, grid.cover_box(), *m)
+    qq = np.random.default_rng(3).uniform([-5.5, -5.5, -0.5], [5.5, 5.5, 12.5], (5000, 3))
+    assert np.array_equal(mct.sites_locate(pts, m[3], grid, qq), orc.sites_locate(pts, m[3], grid, qq))
+
+
 def test_k1_degenerate_nuclei_reported(mct):
     grid = synth.make_grid(8, 8, 8)
     pts = np.tile(np.array([[0.1, 0.2, 3.0]]), (40, 1))

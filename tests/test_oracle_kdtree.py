@@ -9,7 +9,7 @@ import pytest
 import oracle_lib as orc
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "kdtree2_ref.npz")
-CASES = ["random300", "vertices2", "lattice_ties", "tiny13", "tiny14", "collinear", "plane", "dup12"]
+CASES = ["random300", "vertices2", "lattice_ties", "tiny13", "tiny14", "collinear", "plane", "dup12", "grid2d", "lattice2d"]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -103,3 +103,21 @@ def test_full_box_rounding_quirk_is_reference_behaviour():
     assert list(orc.box_window(grid, grid.cover_box())) == [1, 256, 1, 256, 1, 60]
     grid = synth.make_grid(101, 101, 121)          # example1's grid is unaffected
     assert list(orc.box_window(grid, grid.full_box())) == [1, 101, 1, 101, 1, 121]
+
+
+def test_sites_locate_restatement():
+    """sites_locate (likelihood_body.F90:799-831): inside a cell's interior the eight-node shortcut and the tree agree;
+    the shortcut is taken (no tree search) exactly when the eight nodes around the point carry one index."""
+    from mctomo_b200 import synth
+    grid = synth.make_grid(14, 13, 11)
+    pts, par = synth.generate_model(grid, 30, 8)
+    vp, vs, rho = (np.zeros(grid.shape) for _ in range(3))
+    sid = np.zeros(grid.shape, np.int32)
+    orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
+    rng = np.random.default_rng(3)
+    q = rng.uniform([-5.5, -5.5, -0.5], [5.5, 5.5, 12.5], (4000, 3))
+    got = orc.sites_locate(pts, sid, grid, q)
+    near, _ = orc.kd_nearest(pts, q)
+    inside = (np.abs(q[:, :2]) <= 5).all(1) & (q[:, 2] >= 0) & (q[:, 2] <= 12)
+    assert np.array_equal(got[inside], near[inside])          # convex cells: 8 equal corners => the box is inside the cell
+    assert got.min() >= 1 and got.max() <= len(pts)

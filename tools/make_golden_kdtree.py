@@ -50,6 +50,14 @@ def main():
     cases["plane"] = (rng.permutation(plane), rng.uniform(-0.2, 1.2, (1500, 3)))
     dup = np.concatenate([np.tile(np.array([[0.4, 0.6, 0.5]]), (12, 1)), rng.uniform(0, 1, (50, 3))])
     cases["dup12"] = (rng.permutation(dup), rng.uniform(-0.2, 1.2, (1500, 3)))
+    # the 2-D product (mcmc2d/mcmc.f90:1469-1556): kdtree2 with dim = 2 -- random nuclei on a grid of query nodes, and a
+    # lattice with half-integer queries (exact ties) plus duplicates
+    p2 = rng.uniform([-5, -5], [5, 5], (180, 2))
+    g2 = np.stack(np.meshgrid(np.linspace(-5, 5, 41), np.linspace(-5, 5, 37), indexing="ij"), -1).reshape(-1, 2)
+    cases["grid2d"] = (p2, g2)
+    lat2 = np.stack(np.meshgrid(np.arange(6.), np.arange(6.), indexing="ij"), -1).reshape(-1, 2)
+    lat2 = rng.permutation(np.concatenate([lat2, lat2[:7]]))
+    cases["lattice2d"] = (lat2, np.stack(np.meshgrid(np.arange(0, 5.01, .5), np.arange(0, 5.01, .5), indexing="ij"), -1).reshape(-1, 2))
     out = {}
     for name, (p, q) in cases.items():
         idx, dis = orc.ref_kd_nearest(p, q)
