@@ -1,7 +1,7 @@
 ! mctomo_b200_shim.f90 -- ISO_C_BINDING glue between the unchanged MCTomo host and libmctomo_b200.so.
 !
 ! This file is SOURCE ONLY: the build image of this repository has no Fortran compiler, so it has not
-! been compiled here.  It is written against the reference's own types and mirrors the style of the
+! been compiled here (needs the preprocessor: name it .F90 or pass -cpp, as the reference does for its .F90 files).  It is written against the reference's own types and mirrors the style of the
 ! reference's existing C wrappers (src/fastMarching_wrapper.f90:18-74, src/cgal_delaunay_wrapper.f90:51-211).
 !
 ! What a maintainer does (INTEGRATION.md has the step-by-step):
@@ -26,6 +26,20 @@ module m_mctomo_b200
 
     public :: mctomo_b200_init, mctomo_b200_shutdown
     public :: kdtree_to_grid_b200, surf_dispersion_b200, vs2vp_rho_b200
+    ! the resident session: one chain's model kept in HBM between proposals (INTEGRATION.md 5a)
+    public :: T_B200_SESSION, b200_session_create, b200_session_destroy, b200_session_set_model, b200_session_propose, &
+              b200_session_accept, b200_session_reject, b200_session_likelihood, b200_session_stat_rti
+    ! one chain on several GPUs (BASELINE config 5): NCCL communicator bootstrap over MPI
+    public :: mctomo_b200_comm_init
+
+    ! handle + host staging of one session
+    type T_B200_SESSION
+        type(c_ptr) :: h = c_null_ptr
+        integer :: nx = 0, ny = 0, nout = 0
+        real(c_double), allocatable :: pvel_w(:), gvel_w(:)      ! packed window maps of the last proposal
+        integer(c_int), allocatable :: ierr_w(:)
+        integer(c_int) :: win(4) = 0                             ! ix0, ix1, iy0, iy1 of the last proposal (box + halo)
+    end type
 
     ! mirrors `mct_grid` of include/mctomo_b200.h
     type, bind(C) :: mct_grid
@@ -146,16 +160,110 @@ module m_mctomo_b200
             import :: c_int, c_ptr
             type(c_ptr), value :: sess, vp, vs, rho, sites_id
         end function
+        integer(c_int) function mct_session_get_maps(sess, pvel, gvel, ierr) bind(C, name='mct_session_get_maps')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess, pvel, gvel, ierr
+        end function
+        integer(c_int) function mct_session_set_rays(sess, ray_points, ray_offsets, nrays) bind(C, name='mct_session_set_rays')
+            import :: c_int, c_ptr
+            type(c_ptr), value    :: sess, ray_points, ray_offsets
+            integer(c_int), value :: nrays
+        end function
+        integer(c_int) function mct_session_set_data(sess, nrr, sigdep, nrays_total, ttime, raystat, srdist) &
+                bind(C, name='mct_session_set_data')
+            import :: c_int, c_ptr
+            type(c_ptr), value    :: sess
+            integer(c_int), value :: nrr, sigdep, nrays_total
+            type(c_ptr), value    :: ttime, raystat, srdist      ! dat%ttime (nrr,3,np), dat%raystat (nrr,2,np), like%srdist (nrr,np)
+        end function
+        integer(c_int) function mct_session_likelihood(sess, pending, ray_points, ray_offsets, nrays, snoise0, snoise1, &
+                out, phase_time, sigma) bind(C, name='mct_session_likelihood')
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value    :: sess
+            integer(c_int), value :: pending                     ! 0: current model, 1: pending proposal
+            type(c_ptr), value    :: ray_points, ray_offsets     ! c_null_ptr: the rays of mct_session_set_rays
+            integer(c_int), value :: nrays
+            type(c_ptr), value    :: snoise0, snoise1            ! RTI%snoise0, RTI%snoise1 (np) or c_null_ptr (sigdep == 0)
+            real(c_double), intent(out) :: out(3)                ! like%like, like%misfit, like%unweighted_misfit
+            type(c_ptr), value    :: phase_time, sigma           ! optional (nrr,np) outputs, c_null_ptr to skip
+        end function
+        integer(c_int) function mct_surf_misfit(time, nrr, np, sigdep, nrays_total, ttime, raystat, snoise0, snoise1, srdist, &
+                out, sigma) bind(C, name='mct_surf_misfit')
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value    :: time
+            integer(c_int), value :: nrr, np, sigdep, nrays_total
+            type(c_ptr), value    :: ttime, raystat, snoise0, snoise1, srdist
+            real(c_double), intent(out) :: out(3)
+            type(c_ptr), value    :: sigma
+        end function
+        integer(c_int) function mct_session_stat_accumulate(sess) bind(C, name='mct_session_stat_accumulate')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess
+        end function
+        integer(c_int) function mct_session_stat_get(sess, aveS, stdS, aveP, stdP, nsamples) bind(C, name='mct_session_stat_get')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: sess, aveS, stdS, aveP, stdP, nsamples
+        end function
+        ! ---- one chain on several GPUs: NCCL data plane inside the library (include/mctomo_b200.h, "multi-GPU") ----
+        integer(c_int) function mct_comm_unique_id(id128) bind(C, name='mct_comm_unique_id')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: id128                          ! 128 bytes out
+        end function
+        integer(c_int) function mct_comm_init(id128, rank, nranks) bind(C, name='mct_comm_init')
+            import :: c_int, c_ptr
+            type(c_ptr), value    :: id128
+            integer(c_int), value :: rank, nranks
+        end function
+        integer(c_int) function mct_comm_destroy() bind(C, name='mct_comm_destroy')
+            import :: c_int
+        end function
+        integer(c_int) function mct_forward_sharded_dev(g, derive_vp_rho, freqs, np, opt, d_vp, d_vs, d_rho, d_sites, &
+                d_pvel, d_gvel, d_ierr, d_flags, stream) bind(C, name='mct_forward_sharded_dev')
+            import :: c_int, c_ptr, mct_grid, mct_disp_opts
+            type(mct_grid), intent(in) :: g
+            integer(c_int), value :: derive_vp_rho
+            type(c_ptr), value    :: freqs
+            integer(c_int), value :: np
+            type(mct_disp_opts), intent(in) :: opt
+            type(c_ptr), value    :: d_vp, d_vs, d_rho, d_sites, d_pvel, d_gvel, d_ierr, d_flags, stream   ! DEVICE pointers
+        end function
     end interface
 
 contains
 
-    subroutine mctomo_b200_init(rank)
+    ! chains are MPI ranks (src/MCTomo.F90:131-133); several ranks may share a GPU.  local_rank: the rank within the node
+    ! (MPI_Comm_split_type(MPI_COMM_TYPE_SHARED) / OMPI_COMM_WORLD_LOCAL_RANK / SLURM_LOCALID); ngpus: devices of the node
+    ! (cudaGetDeviceCount, or the launcher's setting).  Without them the global rank and 8 devices are assumed.
+    subroutine mctomo_b200_init(rank, local_rank, ngpus)
         integer, intent(in) :: rank
+        integer, intent(in), optional :: local_rank, ngpus
         integer(c_int) :: rc
-        ! chains are MPI ranks (src/MCTomo.F90:131-133); eight GPUs per node, one or more ranks per GPU
-        rc = mct_init(int(mod(rank, 8), c_int))
+        integer :: lr, ng
+        lr = rank
+        if (present(local_rank)) lr = local_rank
+        ng = 8
+        if (present(ngpus)) ng = max(1, ngpus)
+        rc = mct_init(int(mod(lr, ng), c_int))
         if (rc /= 0) call fail('mct_init', rc)
+    end subroutine
+
+    ! NCCL communicator for the column-sharded evaluation of ONE chain: rank 0 draws the 128-byte id, MPI moves it
+    ! (the reference already initialises MPI, src/MCTomo.F90:82-86).  Compile with -DMPI like the reference.
+    subroutine mctomo_b200_comm_init(comm_rank, comm_size, mpi_comm)
+        integer, intent(in) :: comm_rank, comm_size, mpi_comm
+        integer(c_int8_t), target :: id(128)
+        integer(c_int) :: rc
+        integer :: ierror
+        id = 0
+        if (comm_rank == 0) then
+            rc = mct_comm_unique_id(c_loc(id))
+            if (rc /= 0) call fail('mct_comm_unique_id', rc)
+        endif
+#ifdef MPI
+        call mpi_bcast(id, 128, MPI_BYTE, 0, mpi_comm, ierror)
+#endif
+        rc = mct_comm_init(c_loc(id), int(comm_rank, c_int), int(comm_size, c_int))
+        if (rc /= 0) call fail('mct_comm_init', rc)
     end subroutine
 
     subroutine mctomo_b200_shutdown()
@@ -273,9 +381,205 @@ contains
                                      c_loc(freqs), size(freqs), opt, c_loc(pvel), c_loc(gvel), c_loc(ierr), c_null_ptr)
         endif
         invalid = (inval /= 0)
-        ! rc = 2: some column has a low-velocity layer and needs the generalized R/T branch
-        ! (surfmodes.f90:84-87); those columns carry ierr = 2 and the caller may run the Fortran surfmodes on them.
         if (rc < 0 .or. rc == 1) call fail('mct_surf_dispersion', rc)
+        ! rc = 2 (MCT_E_GRT_NEEDED): columns with a low-velocity layer carry ierr = 2 and the preset velocities: the
+        ! reference solves them with its generalized R/T branch (surfmodes.f90:84-87,96-99), so they are handed to the
+        ! Fortran surfmodes here, column by column (unreachable from the sampler, where check_model has already
+        ! rejected such models; `program modelling` has no check_model and can get here).
+        ! rc = 3 / 5 (more than 200 layers / a fluid layer below the top): the reference overruns its arrays or `stop`s
+        ! (surfmodes.f90:342-345); raise instead of carrying bogus velocities into fm2d.
+        if (rc == 3 .or. rc == 5) call fail('mct_surf_dispersion', rc)
+        if (rc == 2) call solve_lvl_columns_on_host(model, grid, ix0, ix1, iy0, iy1, freqs, raylov, phaseGroup, dPhaseVel, &
+                                                    var, pvel, gvel, ierr)
+    end subroutine
+
+    ! The ierr = 2 columns of a dispersion call, through the reference's own surfmodes (GRT branch).
+    subroutine solve_lvl_columns_on_host(model, grid, ix0, ix1, iy0, iy1, freqs, raylov, phaseGroup, dPhaseVel, var, pvel, gvel, ierr, tol)
+        use m_surfmodes, only : surfmodes, T_MODES_PARA
+        type(T_MOD), intent(in) :: model
+        type(T_GRID), intent(in) :: grid
+        integer, intent(in) :: ix0, ix1, iy0, iy1, raylov, phaseGroup, var
+        real(c_double), dimension(:), intent(in) :: freqs
+        real(c_double), intent(in) :: dPhaseVel
+        real(c_double), dimension(:,:,:), intent(inout) :: pvel, gvel
+        integer(c_int), dimension(:,:), intent(inout) :: ierr
+        real(c_double), intent(in), optional :: tol          ! settings%tol (GRT only); default as examples/example1/MCTomo.inp
+        type(T_MODES_PARA) :: paras
+        real(c_double), allocatable :: thick(:), vp(:), vs(:), rho(:)
+        integer :: i, j, n, e
+        ! src/likelihood_surf.F90:173-182
+        paras%modetype = raylov
+        paras%phaseGroup = phaseGroup
+        paras%tolmin = 1.0E-6_c_double
+        if (present(tol)) paras%tolmin = tol
+        paras%tolmax = 10 * paras%tolmin
+        paras%smin_min = 1E-3
+        paras%smin_max = 5E-3
+        paras%dc = dPhaseVel
+        paras%dcm = dPhaseVel
+        paras%dc1 = dPhaseVel
+        paras%dc2 = dPhaseVel
+        do i = ix0, ix1
+            do j = iy0, iy1
+                if (ierr(j - iy0 + 1, i - ix0 + 1) /= 2) cycle
+                call column_to_layers(model, grid, i, j, var, thick, vp, vs, rho, n)
+                call surfmodes(thick(1:n), vp(1:n), vs(1:n), rho(1:n), freqs, paras, pvel(:, j - iy0 + 1, i - ix0 + 1), &
+                               gvel(:, j - iy0 + 1, i - ix0 + 1), e)
+                ierr(j - iy0 + 1, i - ix0 + 1) = e
+            enddo
+        enddo
+    end subroutine
+
+    ! convert_to_layer for ONE column (src/likelihood_surf.F90:541-625 / forward_modelling.f90:72-175, var selects EPS
+    ! and the /scaling step); only used on the rare GRT columns above.
+    subroutine column_to_layers(model, grid, i, j, var, thick, vp, vs, rho, n)
+        type(T_MOD), intent(in) :: model
+        type(T_GRID), intent(in) :: grid
+        integer, intent(in) :: i, j, var
+        real(c_double), allocatable, intent(out) :: thick(:), vp(:), vs(:), rho(:)
+        integer, intent(out) :: n
+        real(c_double) :: eps, last_vs
+        integer :: k, last_k
+        eps = real(1.0E-10, c_double)
+        if (var /= 0) eps = real(1.0E-5, c_double)
+        allocate(thick(grid%nz + 2), vp(grid%nz + 2), vs(grid%nz + 2), rho(grid%nz + 2))
+        n = 0
+        if (grid%waterDepth > merge(eps, 0.0_c_double, var == 0)) then
+            n = 1
+            thick(1) = grid%waterDepth; vp(1) = 1.5_c_double; vs(1) = 0.0_c_double; rho(1) = 1.0_c_double
+        endif
+        last_vs = model%vs(1, j, i); last_k = 1
+        do k = 2, grid%nz
+            if (abs(model%vs(k, j, i) - last_vs) > eps) then
+                n = n + 1
+                thick(n) = (k - last_k) * grid%dz
+                vp(n) = model%vp(last_k, j, i); vs(n) = model%vs(last_k, j, i); rho(n) = model%rho(last_k, j, i)
+                last_vs = model%vs(k, j, i); last_k = k
+            endif
+        enddo
+        n = n + 1                                            ! the last run is the half-space (thickness 0)
+        thick(n) = 0.0_c_double
+        vp(n) = model%vp(grid%nz, j, i); vs(n) = model%vs(grid%nz, j, i); rho(n) = model%rho(grid%nz, j, i)
+        if (var == 0) then
+            thick(1:n) = thick(1:n) / grid%scaling
+            if (grid%waterDepth > eps) thick(1) = grid%waterDepth
+        endif
+    end subroutine
+
+    ! ---- resident session: the sampler's per-iteration sequence (src/mcmc_loc2.f90:199-228,556-566) with the chain's
+    !      model and maps kept on the device.  One session per chain; calls mirror the sampler's own steps:
+    !        mcmc :139-143          -> b200_session_set_model      (kdtree_to_grid(full) + likelihood's dispersion)
+    !        case birth/death/move/value :220-228,279-282,328-330,395-397
+    !                                -> b200_session_propose        (kdtree_to_grid(box[,pm]) + dispersion of box + halo)
+    !        surf_likelihood's tail :226-243,356-404 (straight rays) -> b200_session_likelihood
+    !        accept :244-265 / reject :554-567 -> b200_session_accept / b200_session_reject
+    !        every `thin` samples :587-600  -> b200_session_stat_rti (kdtree_to_grid(full) is not needed: the model IS resident)
+    subroutine b200_session_create(S, grid, freqs, raylov, phaseGroup, dPhaseVel)
+        type(T_B200_SESSION), intent(out) :: S
+        type(T_GRID), intent(in) :: grid
+        real(c_double), dimension(:), intent(in), target :: freqs
+        integer, intent(in) :: raylov, phaseGroup
+        real(c_double), intent(in) :: dPhaseVel
+        type(mct_disp_opts) :: opt
+        integer(c_int) :: rc
+        opt%raylov = raylov; opt%phaseGroup = phaseGroup; opt%nmodes = 0; opt%check_scope = 0
+        opt%dphase = dPhaseVel
+        opt%layer_eps = real(1.0E-10, c_double); opt%water_thresh = real(1.0E-10, c_double); opt%preset = 100.0_c_double
+        rc = mct_session_create(c_grid(grid), c_loc(freqs), size(freqs), opt, 1_c_int, S%h)
+        if (rc /= 0) call fail('mct_session_create', rc)
+        S%nx = grid%nx; S%ny = grid%ny; S%nout = size(freqs)
+        allocate(S%pvel_w(S%nout * grid%nx * grid%ny), S%gvel_w(S%nout * grid%nx * grid%ny), S%ierr_w(grid%nx * grid%ny))
+    end subroutine
+
+    subroutine b200_session_destroy(S)
+        type(T_B200_SESSION), intent(inout) :: S
+        integer(c_int) :: rc
+        rc = mct_session_destroy(S%h)
+        S%h = c_null_ptr
+    end subroutine
+
+    ! full evaluation; pvel/gvel (np,ny,nx), ierr (ny,nx) as surf_likelihood holds them; invalid = check_model's answer
+    subroutine b200_session_set_model(S, RTI, pvel, gvel, ierr, invalid)
+        type(T_B200_SESSION), intent(inout) :: S
+        type(T_RUN_INFO), intent(in), target :: RTI
+        real(c_double), dimension(:,:,:), intent(inout), target :: pvel, gvel
+        integer(c_int), dimension(:,:), intent(inout), target :: ierr
+        logical, intent(out) :: invalid
+        integer(c_int), target :: inval
+        integer(c_int) :: rc
+        inval = 0
+        rc = mct_session_set_model(S%h, c_loc(RTI%points), c_loc(RTI%parameters), int(RTI%ncells, c_int), c_loc(pvel), c_loc(gvel), &
+                                   c_loc(ierr), c_loc(inval))
+        invalid = (inval /= 0)
+        if (rc /= 0 .and. rc /= 2) call fail('mct_session_set_model', rc)
+    end subroutine
+
+    ! one proposal: RTI holds the nuclei AFTER the move, bnd_box what the sampler hands to kdtree_to_grid, pm the moved
+    ! cell's old (vp,vs,rho) for a value move.  On return S%win = (ix0,ix1,iy0,iy1) and S%pvel_w/gvel_w/ierr_w hold the
+    ! window's maps packed (np, iy0:iy1, ix0:ix1): copy them into like%vel / like%gvel exactly as
+    ! likelihood_surf.F90:226-231,259-264 does with its local pvel/gvel.  bad = any(ierr == 1) of the window.
+    subroutine b200_session_propose(S, RTI, bnd_box, invalid, bad, pm)
+        type(T_B200_SESSION), intent(inout), target :: S
+        type(T_RUN_INFO), intent(in), target :: RTI
+        type(d3), dimension(2), intent(in) :: bnd_box
+        logical, intent(out) :: invalid, bad
+        type(p3), intent(in), optional :: pm
+        real(c_double) :: box(6)
+        real(c_double), target :: pmv(3)
+        type(c_ptr) :: pm_ptr
+        integer(c_int) :: rc, inval
+        integer :: ncol
+        box = [bnd_box(1)%x, bnd_box(1)%y, bnd_box(1)%z, bnd_box(2)%x, bnd_box(2)%y, bnd_box(2)%z]
+        pm_ptr = c_null_ptr
+        if (present(pm)) then
+            pmv = [pm%vp, pm%vs, pm%rho]
+            pm_ptr = c_loc(pmv)
+        endif
+        rc = mct_session_propose(S%h, c_loc(RTI%points), c_loc(RTI%parameters), int(RTI%ncells, c_int), box, pm_ptr, S%win, &
+                                 c_loc(S%pvel_w), c_loc(S%gvel_w), c_loc(S%ierr_w), inval)
+        if (rc /= 0 .and. rc /= 2) call fail('mct_session_propose', rc)
+        invalid = (inval /= 0)
+        ncol = max(0, S%win(2) - S%win(1) + 1) * max(0, S%win(4) - S%win(3) + 1)
+        bad = .false.
+        if (.not. invalid .and. ncol > 0) bad = any(S%ierr_w(1:ncol) /= 0)
+    end subroutine
+
+    subroutine b200_session_accept(S)
+        type(T_B200_SESSION), intent(inout) :: S
+        integer(c_int) :: rc
+        rc = mct_session_accept(S%h)
+        if (rc /= 0) call fail('mct_session_accept', rc)
+    end subroutine
+
+    subroutine b200_session_reject(S)
+        type(T_B200_SESSION), intent(inout) :: S
+        integer(c_int) :: rc
+        rc = mct_session_reject(S%h)
+        if (rc /= 0) call fail('mct_session_reject', rc)
+    end subroutine
+
+    ! surf_likelihood's tail for straight rays (likelihood_surf.F90:226-243,356-404) on the resident maps.  The rays
+    ! (setup_straightRays, once) and the data (dat%ttime, dat%raystat, like%srdist) are made resident by
+    ! mct_session_set_rays / mct_session_set_data at start-up; per call only the noise parameters travel.
+    subroutine b200_session_likelihood(S, pending, snoise0, snoise1, like_val, misfit, unweighted_misfit)
+        type(T_B200_SESSION), intent(inout) :: S
+        logical, intent(in) :: pending
+        real(c_double), dimension(:), intent(in), target :: snoise0, snoise1
+        real(c_double), intent(out) :: like_val, misfit, unweighted_misfit
+        real(c_double) :: out(3)
+        integer(c_int) :: rc
+        rc = mct_session_likelihood(S%h, merge(1_c_int, 0_c_int, pending), c_null_ptr, c_null_ptr, 0_c_int, c_loc(snoise0), &
+                                    c_loc(snoise1), out, c_null_ptr, c_null_ptr)
+        if (rc /= 0) call fail('mct_session_likelihood', rc)      ! rc = 6: 'The noise level is 0!' (likelihood_surf.F90:387-390)
+        like_val = out(1); misfit = out(2); unweighted_misfit = out(3)
+    end subroutine
+
+    ! stat_rti's four sums (src/mcmc_loc2.f90:1966-1978) on the resident model; read back with mct_session_stat_get
+    subroutine b200_session_stat_rti(S)
+        type(T_B200_SESSION), intent(inout) :: S
+        integer(c_int) :: rc
+        rc = mct_session_stat_accumulate(S%h)
+        if (rc /= 0) call fail('mct_session_stat_accumulate', rc)
     end subroutine
 
     subroutine fail(what, rc)
