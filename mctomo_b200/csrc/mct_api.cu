@@ -83,7 +83,10 @@ struct Ctx {
 };
 
 Ctx g;
-std::mutex g_mu;
+// One context per process.  Every entry point takes this lock for its whole duration (NEED_INIT), so calls from several
+// host threads -- e.g. two chains driven by OpenMP threads of one rank -- are safe; they serialise on the host side
+// (the *_dev entry points only enqueue, so device work of different streams still overlaps).
+std::recursive_mutex g_mu;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -101,9 +104,8 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 #define NEED_INIT()                                                            \
-  do {                                                                         \
-    if (!g.init) return fail(MCT_E_NOINIT, "mct_init has not been called");    \
-  } while (0)
+  std::lock_guard<std::recursive_mutex> api_lock_(g_mu);                       \
+  if (!g.init) return fail(MCT_E_NOINIT, "mct_init has not been called")
 
 int ensure(DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return MCT_OK;
@@ -627,7 +629,7 @@ extern "C" {
 const char* mct_last_error(void) { return g.err; }
 
 int mct_init(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g.init) {
     if (device == g.device) return MCT_OK;
     return fail(MCT_E_INVALID_ARG, "already initialised on device %d", g.device);
@@ -661,7 +663,7 @@ int mct_init(int device) {
 }
 
 int mct_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (!g.init) return MCT_OK;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);

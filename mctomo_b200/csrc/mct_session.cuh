@@ -143,6 +143,7 @@ int mct_session_create(const mct_grid* gr, const double* freqs, int np, const mc
 }
 
 int mct_session_destroy(mct_session* s) {
+  std::lock_guard<std::recursive_mutex> api_lock_(g_mu);
   if (!s) return MCT_OK;
   if (g.init) cudaStreamSynchronize(g.stream);
   session_release(s);

@@ -299,6 +299,37 @@ def test_session_invalid_initial_model_and_stat_accumulation(mct):
     S.close()
 
 
+def test_concurrent_host_threads(mct):
+    """the library has one context per process; entry points now serialise on a lock, so several host
+    threads (ctypes releases the GIL during the calls) may drive it at once -- results equal the single-threaded ones."""
+    import threading
+    grid = synth.make_grid(12, 10, 20)
+    freqs = synth.freqs(5)
+    opts = disp_opts(phaseGroup=1)
+    models = [synth.generate_model(grid, 20 + 5 * t, 900 + t) for t in range(4)]
+    ref = [mct.forward_eval(p, a, grid, freqs, opts, want_model=True) for p, a in models]
+    out = [None] * 4
+    errs = []
+
+    def work(t):
+        try:
+            for _ in range(6):
+                out[t] = mct.forward_eval(*models[t], grid, freqs, opts, want_model=True)
+                S = mct.Session(grid, freqs, opts)
+                S.set_model(*models[t], want_maps=False)
+                S.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for t in range(4):
+        for k in ("pvel", "gvel", "ierr", "sites_id", "vs"):
+            assert np.array_equal(out[t][k], ref[t][k]), (t, k)
+
+
 def test_shutdown_and_reinit(mct):
     """mct_shutdown frees every buffer; calls then fail with MCT_E_NOINIT (no fallback), and a new mct_init brings the
     library back with identical results.  A session outliving the shutdown can still be destroyed."""
