@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) dedup_finish_kernel(const int32_t* __rest
                                                            const int32_t* __restrict__ mult0, const int32_t* __restrict__ status,
                                                            const int32_t* __restrict__ nlay, int ncol, int32_t* __restrict__ rep,
                                                            int32_t* __restrict__ mult, int32_t* __restrict__ kstat, int32_t* __restrict__ skey,
-                                                           int32_t* neff) {
+                                                           int32_t* neff, const float4* __restrict__ lay, int stride, float qscale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   bool mine = false;
   if (c < ncol) {
@@ -96,7 +96,19 @@ __global__ void __launch_bounds__(256) dedup_finish_kernel(const int32_t* __rest
     if (r == c) {
       mult[c] = mult0[g];
       kstat[c] = status[c];
-      skey[c] = max(nlay[c], 1);
+      int key = max(nlay[c], 1);
+      if (qscale > 0.f) {
+        // secondary key inside a layer-count bin: (bottom vs - 0.79 top vs) / dc is roughly how far getsol's scan walks
+        // over the band, i.e. a proxy of the column's number of secular-function evaluations.  Whole km/s (qscale = 1)
+        // splits a bin in two or three, longer searches first: 1.7-3.2 % on C1/C2/C4, nothing on C3/C5; finer levels
+        // (2..6 per km/s) give the gain back by scattering spatial neighbours (tools/k2_ab.py, MCT_SORT_PROXY)
+        const int n = key;
+        const float btop = lay[c].z > 0.01f ? lay[c].z : lay[(size_t)(n > 1 ? 1 : 0) * stride + c].z;
+        const float proxy = lay[(size_t)(n - 1) * stride + c].z - 0.786f * btop;
+        const int q = min(7, max(0, (int)(proxy * qscale)));
+        key = min(key, 31) * 8 + q;
+      }
+      skey[c] = key;
       mine = true;
     } else {
       mult[c] = 0;

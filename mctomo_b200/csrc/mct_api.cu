@@ -58,6 +58,7 @@ struct Ctx {
   // layered columns, their processing order, sort scratch
   DevBuf lay, layr, nlay, status, perm, bins;
   DevBuf dd_table, dd_i32; // de-duplication: hash table; rep0|minrep|mult0|rep|mult|kstat|skey (7 x stride int32) + neff
+  float sort_proxy = 1.f;  // > 0: secondary sort key (search-length proxy, 8 levels of 1/sort_proxy km/s) inside a layer-count bin (MCT_SORT_PROXY)
   int dedup = 1;           // fold bit-identical layer stacks before K2 (mct_set_dedup / MCT_DEDUP)
   int last_ncol = 0, last_neff = 0, last_lanes = 0; // what the last dispersion launch did (mct_last_launch)
   char last_kernel[48] = {0};
@@ -413,7 +414,8 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
     dedup_insert_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P.lay, P.nlay, P.status, ncol, stride, P.cols_per_model,
                                                            (unsigned long long*)g.dd_table.p, nslots, rep0);
     dedup_group_kernel<<<(ncol + 255) / 256, 256, 0, st>>>(rep0, ncol, minrep, mult0);
-    dedup_finish_kernel<<<(ncol + 255) / 256, 256, 0, st>>>(rep0, minrep, mult0, P.status, P.nlay, ncol, rep, mult, kstat, skey, d_neff);
+    dedup_finish_kernel<<<(ncol + 255) / 256, 256, 0, st>>>(rep0, minrep, mult0, P.status, P.nlay, ncol, rep, mult, kstat, skey, d_neff,
+                                                           P.lay, stride, g.sort_proxy);
     CK(cudaGetLastError());
     g.host_stats.n_launches += 4;
     P.status = kstat;
@@ -654,6 +656,7 @@ int mct_init(int device) {
   if (const char* v = getenv("MCT_K2_VARIANT")) g.k2_variant = atoi(v);
   if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
   if (const char* v = getenv("MCT_DEDUP")) g.dedup = atoi(v) ? 1 : 0;
+  if (const char* v = getenv("MCT_SORT_PROXY")) g.sort_proxy = (float)atof(v);
   if (const char* v = getenv("MCT_K2_COOP_LANES")) { // experiments only; same validation as mct_set_k2_lanes
     const int l = atoi(v);
     if (l == 0 || (l >= 2 && l <= 256 && (l & (l - 1)) == 0)) g.k2_coop_lanes = l;
