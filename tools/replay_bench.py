@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Proposal-replay latency on config C1 (example1's grid): what ONE rjMCMC step costs through the host-pointer
 C ABI (sub-box kdtree_to_grid, whole-grid vs2vp/vp2rho, windowed dispersion incl. check_model) next to the CPU
-restatement of the same three calls on all host cores.  Writes profiles/r1_replay_C1.json."""
+restatement of the same three calls on all host cores.  Writes profiles/r2_replay_C1.json."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
