@@ -265,31 +265,41 @@ def c5_block(args, torch, dist, capi, dev, rank, world, stream):
         capi.forward_sharded_dev(grid, freqs, opts, d_vp.data_ptr(), d_vs.data_ptr(), d_rho.data_ptr(), d_sid.data_ptr(),
                                  d_pv.data_ptr(), d_gv.data_ptr(), d_ie.data_ptr(), d_fl.data_ptr(), stream)
 
-    step()  # warm-up (buffers grow, NCCL connects)
-    sync()
-    capi.set_profiling(True)
-    capi.kernel_times(reset=True)
-    capi.reset_stats()
-    ms, comm_ms = [], []
-    for _ in range(args.c5_steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def measure(mode):
+        capi.comm_set_mode(mode)
+        step()  # warm-up (buffers grow, NCCL connects)
         sync()
-        a.record()
-        step()
-        b.record()
-        torch.cuda.synchronize()
-        ms.append(a.elapsed_time(b))
-        comm_ms.append(capi.comm_last_ms())
-    kt = capi.kernel_times(reset=True)
-    st = capi.stats()
-    mine = torch.tensor([sum(ms) / len(ms), kt["k1_ms"] / len(ms), kt["k2_ms"] / len(ms), kt["other_ms"] / len(ms),
-                         sum(comm_ms) / len(ms), float(st["n_columns_solved"]) / len(ms), float((hi - lo + 1) * grid.ny)],
-                        dtype=torch.float64, device=dev)
-    allr = [torch.zeros_like(mine) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(allr, mine)
-    else:
-        allr = [mine]
+        capi.set_profiling(True)
+        capi.kernel_times(reset=True)
+        capi.reset_stats()
+        ms, comm_ms = [], []
+        for _ in range(args.c5_steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sync()
+            a.record()
+            step()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+            comm_ms.append(capi.comm_last_ms())
+        kt = capi.kernel_times(reset=True)
+        st = capi.stats()
+        capi.set_profiling(False)
+        mine = torch.tensor([sum(ms) / len(ms), kt["k1_ms"] / len(ms), kt["k2_ms"] / len(ms), kt["other_ms"] / len(ms),
+                             sum(comm_ms) / len(ms), float(st["n_columns_solved"]) / len(ms), float((hi - lo + 1) * grid.ny)],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        return allr, d_pv.clone()
+
+    balanced = None
+    if world > 1:  # the balanced division first (its maps are compared with the unsharded ones below)
+        allr_b, pv_b = measure(1)
+        balanced = torch.stack(allr_b).cpu().numpy()
+    allr, _ = measure(0)
     allr = torch.stack(allr).cpu().numpy()
     ms_eval = float(allr[:, 0].max())
     # the same evaluation unsharded on ONE GPU (rank 0; the others wait): the strong-scaling denominator
@@ -309,17 +319,28 @@ def c5_block(args, torch, dist, capi, dev, rank, world, stream):
                 t.append(a.elapsed_time(b))
             n1_ms = t[-1]
             same = bool(torch.equal(d_p1, d_pv[: d_p1.numel()]))  # gathered map == unsharded map, bit for bit
+            same_b = bool(torch.equal(d_p1, pv_b[: d_p1.numel()]))
         else:
-            same = True
+            same = same_b = True
         sync()
         t1 = torch.tensor([n1_ms], dtype=torch.float64, device=dev)
         dist.broadcast(t1, 0)
         n1_ms = float(t1.item())
     else:
-        same = True
+        same = same_b = True
     capi.kernel_times(reset=True)
     capi.set_profiling(False)
     solves = grid.nx * grid.ny * nout
+    bal = None
+    if balanced is not None:
+        bms = float(balanced[:, 0].max())
+        bal = {"what": "mct_comm_set_mode(1): every rank grids, layers and de-duplicates the whole model, solves every n-th entry of "
+                       "the sorted list of distinct columns; compact results all-gathered in place",
+               "ms_per_eval": bms, "solves_per_sec": solves / (bms * 1e-3), "per_rank_k1_ms": [float(v) for v in balanced[:, 1]],
+               "per_rank_k2_ms": [float(v) for v in balanced[:, 2]], "per_rank_other_kernels_ms": [float(v) for v in balanced[:, 3]],
+               "per_rank_allgather_ms": [float(v) for v in balanced[:, 4]],
+               "per_rank_distinct_columns_solved": [float(v) for v in balanced[:, 5]],
+               "efficiency_vs_n1": n1_ms / (world * bms), "gathered_equals_unsharded": same_b}
     return {"workload": f"C5: {grid.nx}x{grid.ny}x{grid.nz} grid, {nout} periods, Rayleigh phase, {len(pts)} nuclei, ONE chain, "
                         f"x-slabs of {per} columns per rank", "scaling": "strong", "n_gpus": world, "steps": args.c5_steps,
             "ms_per_eval": ms_eval, "solves_per_sec": solves / (ms_eval * 1e-3),
@@ -329,7 +350,7 @@ def c5_block(args, torch, dist, capi, dev, rank, world, stream):
             "allgather_bytes_per_rank": int(per * grid.ny * (nout * 8 + 4)),
             "per_rank_distinct_columns_solved": [float(v) for v in allr[:, 5]], "per_rank_columns": [float(v) for v in allr[:, 6]],
             "n1_ms_per_eval": n1_ms, "efficiency_vs_n1": n1_ms / (world * ms_eval),
-            "gathered_equals_unsharded": same,
+            "gathered_equals_unsharded": same, "balanced": bal,
             "collective": "in-place ncclAllGather (pvel f64 + ierr i32) + ncclAllReduce(MAX) of 2 flags, inside libmctomo_b200.so "
                           f"(NCCL {capi.comm_info()['nccl_version']})" if world > 1 else "none (one rank)"}
 

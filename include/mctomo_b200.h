@@ -237,6 +237,11 @@ int mct_comm_unique_id(void* id128);
 int mct_comm_init(const void* id128, int rank, int nranks); /* after mct_init(device); collective over the ranks */
 int mct_comm_destroy(void);
 int mct_comm_info(int* rank, int* nranks, int* nccl_version); /* MCT_E_INVALID_ARG when no communicator exists */
+/* How mct_forward_sharded_dev divides one chain's columns.  0 (default): contiguous x-slabs, as SURVEY.md 8(e) specifies.
+ * 1: balanced -- every rank grids, layers and de-duplicates the WHOLE model (milliseconds), solves every nranks-th entry
+ * of the sorted list of distinct columns, and the compact results are all-gathered in place; robust against models whose
+ * structure -- hence cost -- varies along x.  In mode 1 the outputs are the plain (nout, ny, nx) maps / (ny, nx) ierr. */
+int mct_comm_set_mode(int mode);
 /* x-slab of `rank`: 1-based inclusive ix0..ix1, equal width per = ceil(nx/nranks); trailing slabs may be short or
  * empty (ix1 < ix0). */
 int mct_slab_bounds(int nx, int nranks, int rank, int* ix0, int* ix1, int* per);

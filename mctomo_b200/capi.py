@@ -84,9 +84,10 @@ class Grid:
         # grid_setup: zmin/zmax are scaled, spacing = extent/(n-1)
         self.zmin = self.zmin * self.scaling
         self.zmax = self.zmax * self.scaling
-        self.dx = (self.xmax - self.xmin) / (self.nx - 1)
-        self.dy = (self.ymax - self.ymin) / (self.ny - 1)
-        self.dz = (self.zmax - self.zmin) / (self.nz - 1)
+        # (a single node along an axis -- e.g. ny = 1 for the 2-D product's depth profiles -- gets unit spacing)
+        self.dx = (self.xmax - self.xmin) / (self.nx - 1) if self.nx > 1 else 1.0
+        self.dy = (self.ymax - self.ymin) / (self.ny - 1) if self.ny > 1 else 1.0
+        self.dz = (self.zmax - self.zmin) / (self.nz - 1) if self.nz > 1 else 1.0
 
     def c(self) -> mct_grid:
         return mct_grid(self.nx, self.ny, self.nz, self.xmin, self.ymin, self.zmin, self.dx, self.dy, self.dz,
@@ -701,6 +702,13 @@ def comm_init(id128: bytes, rank: int, nranks: int):
     L.mct_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int]
     assert len(id128) == MCT_COMM_ID_BYTES
     _check(L.mct_comm_init(id128, rank, nranks))
+
+
+def comm_set_mode(mode: int):
+    """0: contiguous x-slabs; 1: balanced (every n-th distinct column of the sorted list)."""
+    L = lib()
+    L.mct_comm_set_mode.argtypes = [C.c_int]
+    _check(L.mct_comm_set_mode(mode))
 
 
 def comm_destroy():

@@ -140,3 +140,53 @@ __global__ void __launch_bounds__(256) dedup_scatter_kernel(const int32_t* __res
 __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* p, long long n, int32_t v) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) p[t] = v;
 }
+
+// ---- balanced sharding of one chain's columns over several ranks (mct_comm.cuh, mode 1) --------------------------------
+// Every rank holds the same sorted list of columns to solve (perm[0..neff)).  It is dealt in CHUNKS of 32 consecutive
+// entries (chunk c goes to rank c % n): a warp of the dispersion kernel then still holds 32 neighbours of the sorted
+// order -- same layer count, adjacent columns, coalesced layer records.  (Dealing single entries was measured first:
+// 1 061 ms per rank against 861 ms for the same number of columns, the warps' columns being n apart.)
+#define SHARD_CHUNK 32
+__host__ __device__ __forceinline__ long long shard_global(int i, int r, int n) { // local entry i of rank r -> list position
+  return ((long long)(i / SHARD_CHUNK) * n + r) * SHARD_CHUNK + (i % SHARD_CHUNK);
+}
+__global__ void __launch_bounds__(256) shard_pick_kernel(const int32_t* __restrict__ perm, int neff, int r, int n, int nmine, int32_t* __restrict__ mine) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmine) return;
+  mine[i] = perm[shard_global(i, r, n)];
+}
+// this rank's results -> its chunk of the exchange buffers (per entries per rank)
+__global__ void __launch_bounds__(256) shard_pack_kernel(const int32_t* __restrict__ perm, int neff, int r, int n, int per, int nout,
+                                                         const double* __restrict__ pvel, const double* __restrict__ gvel,
+                                                         const int32_t* __restrict__ ierr, double* __restrict__ bp, double* __restrict__ bg,
+                                                         int32_t* __restrict__ bi) {
+  const long long total = (long long)per * nout;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / nout), k = (int)(t - (long long)i * nout);
+    const long long j = shard_global(i, r, n);
+    if (j >= neff) continue;
+    const int col = perm[j];
+    const size_t o = ((size_t)r * per + i) * nout + k;
+    bp[o] = pvel[(size_t)col * nout + k];
+    if (bg) bg[o] = gvel[(size_t)col * nout + k];
+    if (k == 0) bi[(size_t)r * per + i] = ierr[col];
+  }
+}
+// the other ranks' results -> the maps
+__global__ void __launch_bounds__(256) shard_unpack_kernel(const int32_t* __restrict__ perm, int neff, int r, int n, int per, int nout,
+                                                           double* __restrict__ pvel, double* __restrict__ gvel, int32_t* __restrict__ ierr,
+                                                           const double* __restrict__ bp, const double* __restrict__ bg,
+                                                           const int32_t* __restrict__ bi) {
+  const long long total = (long long)neff * nout;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t / nout), k = (int)(t - (long long)j * nout);
+    const int c = j / SHARD_CHUNK;
+    const int rk = c % n, i = (c / n) * SHARD_CHUNK + (j % SHARD_CHUNK);
+    if (rk == r) continue;
+    const int col = perm[j];
+    const size_t o = ((size_t)rk * per + i) * nout + k;
+    pvel[(size_t)col * nout + k] = bp[o];
+    if (bg) gvel[(size_t)col * nout + k] = bg[o];
+    if (k == 0) ierr[col] = bi[(size_t)rk * per + i];
+  }
+}

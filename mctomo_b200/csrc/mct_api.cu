@@ -58,6 +58,9 @@ struct Ctx {
   // layered columns, their processing order, sort scratch
   DevBuf lay, layr, nlay, status, perm, bins;
   DevBuf dd_table, dd_i32; // de-duplication: hash table; rep0|minrep|mult0|rep|mult|kstat|skey (7 x stride int32) + neff
+  // balanced sharding of one chain (mct_comm.cuh): rank shard_r of shard_n solves every shard_n-th entry of the sorted list
+  int shard_n = 1, shard_r = 0;
+  DevBuf sh_perm, sh_p, sh_g, sh_i;
   float sort_proxy = 1.f;  // > 0: secondary sort key (search-length proxy, 8 levels of 1/sort_proxy km/s) inside a layer-count bin (MCT_SORT_PROXY)
   int dedup = 1;           // fold bit-identical layer stacks before K2 (mct_set_dedup / MCT_DEDUP)
   int last_ncol = 0, last_neff = 0, last_lanes = 0; // what the last dispersion launch did (mct_last_launch)
@@ -246,6 +249,8 @@ struct ProfScope {
   }
 };
 
+int shard_exchange(int neff, int nout, bool with_group, double* d_pvel, double* d_gvel, int32_t* d_ierr, cudaStream_t st); // mct_comm.cuh
+
 int grid_blocks(long long work_items, int threads, int per_sm) {
   long long b = (work_items + threads - 1) / threads;
   long long cap = (long long)g.sm_count * per_sm;
@@ -312,6 +317,7 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
       int seglen = (int)std::floor(0.5 * h / gr->dz);
       seglen = std::max(seglen, (P.wz + K1T_MAXSEG - 1) / K1T_MAXSEG);
       seglen = std::max(2, seglen + (seglen & 1)); // even: a 16-byte pair of nodes then lies inside one segment
+      if (const char* v = getenv("MCT_K1_TILE")) { int a = 0, b = 0, c = 0; if (sscanf(v, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { ttx = a; tty = b; seglen = std::max(c, (P.wz + K1T_MAXSEG - 1) / K1T_MAXSEG); } } // experiments
       const long long ntiles = (long long)((P.wx + ttx - 1) / ttx) * ((P.wy + tty - 1) / tty);
       const int nby = batched ? nbatch : 1;
       // two resident blocks per SM (registers); several blocks per slot so the hardware scheduler evens out tiles of
@@ -425,7 +431,7 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
     // Large batches: the launch shape below depends on how many columns are really solved, and K2 then runs for tens
     // of milliseconds -- one 4-byte read-back (a stream synchronisation) is noise.  Proposal-sized calls stay fully
     // asynchronous: their shape is chosen from ncol, and the duplicates' blocks exit at once.
-    if (ncol >= 8192) {
+    if (ncol >= 8192 || g.shard_n > 1) {
       int32_t h = ncol;
       CK(cudaMemcpyAsync(&h, d_neff, sizeof h, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -459,10 +465,26 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   CK(cudaGetLastError());
   const int ncol_all = ncol;
   ncol = neff;    // the first neff entries of perm are the columns to visit (all of them when neff was not read back)
+  if (g.shard_n > 1) { // balanced sharding: this rank's share of the sorted list (longest first: every rank gets the same mix)
+    if (!P.perm) return fail(MCT_E_INVALID_ARG, "sharded dispersion needs the column sort (MCT_K2_VARIANT=0 disables it)");
+    // chunks of 32 list entries are dealt round-robin; the last chunk may be short
+    const int nchunks = (neff + SHARD_CHUNK - 1) / SHARD_CHUNK;
+    const int mychunks = nchunks > g.shard_r ? (nchunks - g.shard_r + g.shard_n - 1) / g.shard_n : 0;
+    int nmine = mychunks * SHARD_CHUNK;
+    if (mychunks > 0 && shard_global(nmine - 1, g.shard_r, g.shard_n) >= neff) // my last chunk is the list's (short) last one
+      nmine -= nchunks * SHARD_CHUNK - neff;
+    int rc;
+    if ((rc = ensure(g.sh_perm, sizeof(int32_t) * (size_t)std::max(nmine, 1)))) return rc;
+    if (nmine > 0) shard_pick_kernel<<<(nmine + 255) / 256, 256, 0, st>>>((const int32_t*)g.perm.p, neff, g.shard_r, g.shard_n, nmine, (int32_t*)g.sh_perm.p);
+    CK(cudaGetLastError());
+    g.host_stats.n_launches += 1;
+    P.perm = (const int32_t*)g.sh_perm.p;
+    ncol = nmine;
+  }
   P.ncol = ncol;
   const char* kname = "";
   int lanes = 1;
-  {
+  if (ncol > 0) {
     ProfScope ps(1, st);
     const int nw = (ncol + 31) / 32;
     // Batches that cannot fill the GPU with one thread per column get G lanes per column: the largest power of
@@ -512,6 +534,10 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   g.last_ncol = ncol_all;
   g.last_neff = (g.dedup && ncol_all >= 8192) ? neff : -1;
   g.last_lanes = lanes;
+  if (g.shard_n > 1) { // exchange the representatives' results: pack, in-place all-gather, unpack (mct_comm.cuh)
+    int rc = shard_exchange(neff, P.kmax * P.nmode, P.igr > 0, P.pvel, P.gvel, P.ierr, st);
+    if (rc) return rc;
+  }
   if (d_rep) {
     ProfScope ps(2, st);
     dedup_scatter_kernel<<<grid_blocks((long long)ncol_all * P.kmax * P.nmode, 256, 16), 256, 0, st>>>(
@@ -598,6 +624,7 @@ int forward_core(const mct_grid* gr, int nb, int derive_vp_rho, const DispPlan& 
 
 void release_misfit_globals(); // k4_misfit.cuh
 void comm_release();           // mct_comm.cuh
+int shard_exchange(int neff, int nout, bool with_group, double* d_pvel, double* d_gvel, int32_t* d_ierr, cudaStream_t st); // mct_comm.cuh
 
 int flags_to_code(int maxst) {
   return maxst == 2 ? MCT_E_GRT_NEEDED : (maxst == 3 ? MCT_E_TOO_MANY_LAYERS : MCT_E_FLUID_BELOW_TOP);
@@ -670,7 +697,7 @@ int mct_shutdown(void) {
   if (!g.init) return MCT_OK;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins, &g.dd_table, &g.dd_i32,
+  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins, &g.dd_table, &g.dd_i32, &g.sh_perm, &g.sh_p, &g.sh_g, &g.sh_i,
                     &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.ray_pts, &g.ray_off, &g.ray_time};
   for (DevBuf* b : bufs) release(*b);
   release_misfit_globals();

@@ -32,6 +32,8 @@ struct NcclApi {
 };
 
 struct Comm {
+  int mode = 0; // 0: contiguous x-slabs; 1: balanced -- every rank grids the whole model, solves every n-th
+                // representative of the sorted list, the compact results are all-gathered
   NcclApi api;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -74,6 +76,42 @@ int nccl_load() {
     ncclResult_t r_ = (call);                                                                                 \
     if (r_ != ncclSuccess) return fail(MCT_E_CUDA, "%s failed: %s", #call, gc.api.GetErrorString(r_));        \
   } while (0)
+
+// balanced mode: this rank's results -> exchange buffers, in-place all-gather, the others' results -> maps.  Called by
+// launch_k2 right after the dispersion kernel, before the duplicates are filled from their representatives.
+int shard_exchange(int neff, int nout, bool with_group, double* d_pvel, double* d_gvel, int32_t* d_ierr, cudaStream_t st) {
+  const int n = g.shard_n, r = g.shard_r;
+  const int nchunks = (neff + SHARD_CHUNK - 1) / SHARD_CHUNK;
+  const int per = ((nchunks + n - 1) / n) * SHARD_CHUNK; // list entries per rank (whole chunks)
+  if (per == 0) return MCT_OK;
+  int rc;
+  const size_t np = (size_t)n * per * nout;
+  if ((rc = ensure(g.sh_p, np * 8)) || (rc = ensure(g.sh_i, (size_t)n * per * 4 + 8))) return rc;
+  if (with_group && (rc = ensure(g.sh_g, np * 8))) return rc;
+  double* bp = (double*)g.sh_p.p;
+  double* bg = with_group ? (double*)g.sh_g.p : nullptr;
+  int32_t* bi = (int32_t*)g.sh_i.p;
+  {
+    ProfScope ps(2, st);
+    shard_pack_kernel<<<grid_blocks((long long)per * nout, 256, 16), 256, 0, st>>>((const int32_t*)g.perm.p, neff, r, n, per, nout, d_pvel,
+                                                                                  d_gvel, d_ierr, bp, bg, bi);
+  }
+  CK(cudaGetLastError());
+  if (gc.ev[0]) CK(cudaEventRecord(gc.ev[0], st));
+  const int64_t perb = (int64_t)per * nout * 8;
+  if ((rc = mct_allgather_inplace(bp, perb, st))) return rc;
+  if (bg && (rc = mct_allgather_inplace(bg, perb, st))) return rc;
+  if ((rc = mct_allgather_inplace(bi, (int64_t)per * 4, st))) return rc;
+  if (gc.ev[1]) { CK(cudaEventRecord(gc.ev[1], st)); gc.timed = true; }
+  {
+    ProfScope ps(2, st);
+    shard_unpack_kernel<<<grid_blocks((long long)neff * nout, 256, 16), 256, 0, st>>>((const int32_t*)g.perm.p, neff, r, n, per, nout, d_pvel,
+                                                                                     d_gvel, d_ierr, bp, bg, bi);
+  }
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 2;
+  return MCT_OK;
+}
 
 void comm_release() {
   if (gc.comm && gc.api.CommDestroy) gc.api.CommDestroy(gc.comm);
@@ -118,6 +156,12 @@ int mct_comm_init(const void* id128, int rank, int nranks) {
 
 int mct_comm_destroy(void) {
   comm_release();
+  return MCT_OK;
+}
+
+int mct_comm_set_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(MCT_E_INVALID_ARG, "comm_set_mode: 0 (contiguous x-slabs) or 1 (balanced)");
+  gc.mode = mode;
   return MCT_OK;
 }
 
@@ -179,6 +223,20 @@ int mct_forward_sharded_dev(const mct_grid* gr, int derive_vp_rho, const double*
   NEED_INIT();
   if (!grid_ok(gr) || !opt || !d_pvel || !d_gvel || !d_ierr || !d_flags) return fail(MCT_E_INVALID_ARG, "forward_sharded: bad arguments");
   if (gc.nranks > 1 && !gc.comm) return fail(MCT_E_INVALID_ARG, "forward_sharded: mct_comm_init has not been called");
+  if (gc.mode == 1 && gc.nranks > 1) {
+    // balanced: K1 + maps + check + layering + de-duplication of the WHOLE grid on every rank (milliseconds), then every
+    // rank solves every nranks-th entry of the sorted list of distinct columns; compact results all-gathered in place
+    // (launch_k2 / shard_exchange).  Outputs are the plain (nout, ny, nx) maps, identical on every rank; the flags need
+    // no reduction (every rank checked the whole grid).
+    g.shard_n = gc.nranks;
+    g.shard_r = gc.rank;
+    gc.timed = false;
+    const int rcb = mct_forward_batch_dev(gr, 1, derive_vp_rho, 1, gr->nx, freqs, np, opt, d_vp, d_vs, d_rho, d_sites_id, d_pvel, d_gvel,
+                                          d_ierr, d_flags, stream);
+    g.shard_n = 1;
+    g.shard_r = 0;
+    return rcb;
+  }
   int ix0, ix1, per;
   int rc = mct_slab_bounds(gr->nx, gc.nranks, gc.rank, &ix0, &ix1, &per);
   if (rc) return rc;

@@ -169,6 +169,20 @@ def test_2d_product_and_point_location(mct):
         assert np.array_equal(got, g[f"{case}_idx"]), case
     got3 = mct.nearest_nucleus(g["lattice_ties_points"], g["lattice_ties_queries"])
     assert np.array_equal(got3, g["lattice_ties_idx"])
+    # the 2-D product's surface-wave likelihood (mcmc2d/likelihood_surf_phase.F90:150-190): one dispersion curve per x
+    # node of a (depth, x) profile = the 3-D call with ny = 1 and no check_model
+    nxp, nzp = 37, 33
+    p2d = np.column_stack([np.random.default_rng(4).uniform(-5, 5, 60), np.random.default_rng(5).uniform(0, 12, 60)])  # (x, depth)
+    vsn = 2.0 + p2d[:, 1] / 3.0
+    par2 = np.column_stack([1.73 * vsn, vsn, 1.74 * (1.73 * vsn) ** 0.25])
+    vp2, vs2, rho2, sid2 = mct.voronoi_to_grid_2d(p2d, par2, nxp, nzp, -5.0, 0.0, 10.0 / (nxp - 1), 12.0 / (nzp - 1))
+    prof = Grid(nxp, 1, nzp, -5.0, 5.0, 0.0, 1.0, 0.0, 12.0)
+    fr = synth.freqs(6)
+    pv, gv, ie, inval, rc = mct.surf_dispersion(vp2.reshape(nxp, 1, nzp), vs2.reshape(nxp, 1, nzp), rho2.reshape(nxp, 1, nzp), prof,
+                                                (1, nxp, 1, 1), fr, disp_opts(phaseGroup=1), check=False)
+    po, go, io, _, _ = orc.surf_dispersion(vp2.reshape(nxp, 1, nzp), vs2.reshape(nxp, 1, nzp), rho2.reshape(nxp, 1, nzp), prof,
+                                           (1, nxp, 1, 1), fr, phaseGroup=1)
+    assert np.array_equal(pv, po) and np.array_equal(gv, go) and np.array_equal(ie, io) and (ie <= 1).all()
     # sites_locate
     grid = synth.make_grid(14, 13, 11)
     pts, par3 = synth.generate_model(grid, 30, 8)
