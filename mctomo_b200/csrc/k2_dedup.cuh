@@ -141,6 +141,24 @@ __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* p, long long n, 
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) p[t] = v;
 }
 
+// ---- compact inputs: the columns to solve, gathered in sorted order ---------------------------------------------------------
+// K2 reads a column's layer records once per secular-function evaluation.  In the per-column layout the 32 columns of a warp
+// are neighbours in the SORTED order but lie anywhere in memory (32 separate sectors per load, a footprint of the whole
+// grid -- 4 GB of layer records at C5 against a 126 MB L2); gathered into list order a warp reads contiguous rows and the
+// footprint shrinks to the distinct columns.  One thread per list position; duplicates are not copied.
+__global__ void __launch_bounds__(128) compact_layers_kernel(const float4* __restrict__ lay, const int32_t* __restrict__ nlay,
+                                                             const int32_t* __restrict__ status, const int32_t* __restrict__ list, int n,
+                                                             int stride, int stride_c, float4* __restrict__ layc, int32_t* __restrict__ nlayc,
+                                                             int32_t* __restrict__ statc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int col = list[t];
+  const int nl = nlay[col];
+  nlayc[t] = nl;
+  statc[t] = status[col];
+  for (int m = 0; m < nl; ++m) layc[(size_t)m * stride_c + t] = lay[(size_t)m * stride + col];
+}
+
 // ---- balanced sharding of one chain's columns over several ranks (mct_comm.cuh, mode 1) --------------------------------
 // Every rank holds the same sorted list of columns to solve (perm[0..neff)).  It is dealt in CHUNKS of 32 consecutive
 // entries (chunk c goes to rank c % n): a warp of the dispersion kernel then still holds 32 neighbours of the sorted

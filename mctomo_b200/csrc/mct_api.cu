@@ -57,6 +57,8 @@ struct Ctx {
   DevBuf m_vp, m_vs, m_rho, m_sites;
   // layered columns, their processing order, sort scratch
   DevBuf lay, layr, nlay, status, perm, bins;
+  DevBuf layc, layrc, nlayc; // compact inputs of the columns to solve (sorted-list order)
+  int compact_inputs = 1;    // MCT_COMPACT=0: per-column layout also for large batches (A/B)
   DevBuf dd_table, dd_i32; // de-duplication: hash table; rep0|minrep|mult0|rep|mult|kstat|skey (7 x stride int32) + neff
   // balanced sharding of one chain (mct_comm.cuh): rank shard_r of shard_n solves every shard_n-th entry of the sorted list
   int shard_n = 1, shard_r = 0;
@@ -387,8 +389,11 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   P.cols_per_model = cols_per_model > 0 ? cols_per_model : ncol;
   P.counters = (unsigned long long*)g.counters.p;
   for (int i = 0; i < MCT_MAX_PERIODS; ++i) P.t[i] = (i < np) ? 1 / freqs[i] : 0.0; // dble(1/freqs), surfmodes.f90:82
-  // Per-layer reciprocal table for the fast secular functions.
-  {
+  // Large batches get COMPACT inputs (k2_dedup.cuh): the columns to solve are gathered into sorted-list order after the
+  // sort, and the reciprocal table is then built for those only.  Otherwise: reciprocals for every column, in place.
+  const bool want_compact = g.compact_inputs && ncol >= 8192 && g.k2_variant == 7;
+  P.compact = 0;
+  if (!want_compact) {
     int rc;
     if ((rc = ensure(g.layr, sizeof(double4) * (size_t)stride * (size_t)max_layers))) return rc;
     ProfScope ps(2, st);
@@ -482,6 +487,35 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
     ncol = nmine;
   }
   P.ncol = ncol;
+  if (want_compact && ncol > 0 && P.perm) {
+    const int stride_c = (ncol + 31) & ~31;
+    int rc;
+    if ((rc = ensure(g.layc, sizeof(float4) * (size_t)stride_c * (size_t)max_layers)) ||
+        (rc = ensure(g.layrc, sizeof(double4) * (size_t)stride_c * (size_t)max_layers)) ||
+        (rc = ensure(g.nlayc, sizeof(int32_t) * 2 * (size_t)stride_c)))
+      return rc;
+    int32_t* nlayc = (int32_t*)g.nlayc.p;
+    int32_t* statc = nlayc + stride_c;
+    ProfScope ps(2, st);
+    compact_layers_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(P.lay, P.nlay, P.status, P.perm, ncol, stride, stride_c, (float4*)g.layc.p,
+                                                             nlayc, statc);
+    layer_recips_kernel<<<(ncol + 127) / 128, 128, 0, st>>>((const float4*)g.layc.p, nlayc, ncol, stride_c, P.ifunc, (double4*)g.layrc.p);
+    CK(cudaGetLastError());
+    g.host_stats.n_launches += 2;
+    P.lay = (const float4*)g.layc.p;
+    P.layr = (const double4*)g.layrc.p;
+    P.nlay = nlayc;
+    P.status = statc;
+    P.stride = stride_c;
+    P.compact = 1;
+  } else if (want_compact) { // nothing to gather from (no sort): the plain path after all
+    int rc;
+    if ((rc = ensure(g.layr, sizeof(double4) * (size_t)stride * (size_t)max_layers))) return rc;
+    ProfScope ps(2, st);
+    layer_recips_kernel<<<(ncol_all + 127) / 128, 128, 0, st>>>(P.lay, P.nlay, ncol_all, stride, P.ifunc, (double4*)g.layr.p);
+    g.host_stats.n_launches += 1;
+    P.layr = (const double4*)g.layr.p;
+  }
   const char* kname = "";
   int lanes = 1;
   if (ncol > 0) {
@@ -684,6 +718,7 @@ int mct_init(int device) {
   if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
   if (const char* v = getenv("MCT_DEDUP")) g.dedup = atoi(v) ? 1 : 0;
   if (const char* v = getenv("MCT_SORT_PROXY")) g.sort_proxy = (float)atof(v);
+  if (const char* v = getenv("MCT_COMPACT")) g.compact_inputs = atoi(v) ? 1 : 0;
   if (const char* v = getenv("MCT_K2_COOP_LANES")) { // experiments only; same validation as mct_set_k2_lanes
     const int l = atoi(v);
     if (l == 0 || (l >= 2 && l <= 256 && (l & (l - 1)) == 0)) g.k2_coop_lanes = l;
@@ -697,7 +732,7 @@ int mct_shutdown(void) {
   if (!g.init) return MCT_OK;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins, &g.dd_table, &g.dd_i32, &g.sh_perm, &g.sh_p, &g.sh_g, &g.sh_i,
+  DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins, &g.dd_table, &g.dd_i32, &g.layc, &g.layrc, &g.nlayc, &g.sh_perm, &g.sh_p, &g.sh_g, &g.sh_i,
                     &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.ray_pts, &g.ray_off, &g.ray_time};
   for (DevBuf* b : bufs) release(*b);
   release_misfit_globals();
