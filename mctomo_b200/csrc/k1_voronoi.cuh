@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(128) k1_points_kernel(const __grid_constant__ 
 }
 
 #include "k1_column.cuh" // k1_column_kernel: culled brute force per column, tree walk only for (near-)ties (round-1 shape)
-#include "k1_tile.cuh"   // k1_tile_kernel: per-(column, z-segment) candidate lists, vector stores (production)
+#include "k1_tile.cuh"   // k1_tile_kernel: per-(tile, z-segment) candidate lists, float64 walk, vector stores (mode 3)
+#include "k1_box.cuh"    // k1_box_kernel: the same lists, warp per box, float32 walk with a rigorous error bound (production)
 
 // vs2vp_3d + vp2rho_3d (src/utils.f90:107-110,131-133), elementwise over n values.
 __global__ void __launch_bounds__(256) vs2vp_rho_kernel(const double* __restrict__ vs, double* __restrict__ vp,

@@ -320,17 +320,65 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
       seglen = std::max(seglen, (P.wz + K1T_MAXSEG - 1) / K1T_MAXSEG);
       seglen = std::max(2, seglen + (seglen & 1)); // even: a 16-byte pair of nodes then lies inside one segment
       if (const char* v = getenv("MCT_K1_TILE")) { int a = 0, b = 0, c = 0; if (sscanf(v, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { ttx = a; tty = b; seglen = std::max(c, (P.wz + K1T_MAXSEG - 1) / K1T_MAXSEG); } } // experiments
-      const long long ntiles = (long long)((P.wx + ttx - 1) / ttx) * ((P.wy + tty - 1) / tty);
       const int nby = batched ? nbatch : 1;
-      // two resident blocks per SM (registers); several blocks per slot so the hardware scheduler evens out tiles of
-      // different cost, each block striding over the tiles
-      const long long want = std::max<long long>(1, ((long long)g.sm_count * 16 + nby - 1) / nby);
-      const int blocks = (int)std::min<long long>(ntiles, want);
       const int npairs = (P.wz + 2) / 2;
-      const int nitems = ttx * tty * npairs;
-      const int threads = nitems <= 640 ? 128 : 256;
-      k1_tile_kernel<<<dim3(blocks, nby), threads, 0, st>>>(P, ttx, tty, seglen, (float)(1.25 * h), k1t_magic(npairs), k1t_magic(tty),
-                                                            k1t_magic(seglen));
+      if (g.k1_mode == 3) { // round-2 first shape: float64 walk, items ordered column-major
+        const long long ntiles = (long long)((P.wx + ttx - 1) / ttx) * ((P.wy + tty - 1) / tty);
+        const long long want = std::max<long long>(1, ((long long)g.sm_count * 16 + nby - 1) / nby);
+        const int blocks = (int)std::min<long long>(ntiles, want);
+        const int nitems = ttx * tty * npairs;
+        const int threads = nitems <= 640 ? 128 : 256;
+        k1_tile_kernel<<<dim3(blocks, nby), threads, 0, st>>>(P, ttx, tty, seglen, (float)(1.25 * h), k1t_magic(npairs), k1t_magic(tty),
+                                                              k1t_magic(seglen));
+      } else { // warp per box, float32 walk, 4 (or 2) nodes per thread, persistent over (model, tile) (k1_box.cuh)
+        const bool forced = getenv("MCT_K1_TILE") != nullptr;
+        if (!forced) {
+          if (P.wz > 2) seglen = std::max(4, (seglen + 3) / 4 * 4); // whole 4-node units per segment
+          const int ups = std::max(1, seglen / (P.wz > 2 ? 4 : 2));
+          while (ttx * tty * ups < 32) { // a box (tile x segment) should fill a warp
+            if (2 * ttx <= tty) ttx *= 2;
+            else tty *= 2;
+          }
+        }
+        ttx = std::min(ttx, K1B_MAXC); tty = std::min(tty, K1B_MAXC);
+        // nodes per thread: pairs (measured: quads -- half the index arithmetic per node -- were 20-45 % slower: too
+        // few items per tile to keep the lanes busy); MCT_K1_NPT=4 selects quads where the segment length allows
+        int npt = 2;
+        if (const char* v = getenv("MCT_K1_NPT")) { if (atoi(v) == 4 && seglen % 4 == 0) npt = 4; } // experiments
+        K1BGeom G;
+        G.seglen = seglen; G.nseg = (P.wz + seglen - 1) / seglen;
+        G.nunits = (P.wz + npt) / npt; G.ups = seglen / npt; G.ngroups = (G.nunits + G.ups - 1) / G.ups;
+        while ((long long)G.ngroups * ttx * tty * G.ups >= 65536 && tty > 1) tty /= 2; // 16-bit item index (multiply-shift division)
+        while ((long long)((P.wx + ttx - 1) / ttx) * ((P.wy + tty - 1) / tty) >= 65536 && (ttx < K1B_MAXC || tty < K1B_MAXC)) { // 16-bit tile index
+          if (ttx < tty) ttx *= 2; else tty *= 2;
+        }
+        G.ttx = ttx; G.tty = tty;
+        G.tiles_x = (P.wx + ttx - 1) / ttx; G.tiles_y = (P.wy + tty - 1) / tty;
+        G.tiles_per_model = G.tiles_x * G.tiles_y;
+        const long long total_tiles = (long long)G.tiles_per_model * nby;
+        if (total_tiles >= 65536 && nby > 1) { // k1t_div(t, tiles_per_model) needs t < 2^16: batches of such size go model by model
+          for (int b = 0; b < nbatch; ++b) {
+            int rc = launch_k1(gr, w, pm, d_vp + (long long)b * model_stride, d_vs + (long long)b * model_stride, d_rho + (long long)b * model_stride,
+                               d_sites + (long long)b * model_stride, ia0, ja0, ka0, ny_a, nz_a, st, b);
+            if (rc) return rc;
+          }
+          return MCT_OK;
+        }
+        G.total_tiles = (int)total_tiles;
+        G.per_group = ttx * tty * G.ups;
+        G.near_r = (float)(1.25 * h);
+        G.dv_group = k1t_magic(G.per_group); G.dv_ups = k1t_magic(G.ups); G.dv_ty = k1t_magic(tty); G.dv_seg = k1t_magic(seglen);
+        G.dv_tpm = k1t_magic(G.tiles_per_model); G.dv_tiles_y = k1t_magic(G.tiles_y);
+        // one block per (model, tile) up to 48 per SM: tile costs differ, the hardware block scheduler evens them out
+        // (measured: 6 persistent blocks per SM striding over the tiles were 14 % slower on C2 x 32)
+        long long cap = (long long)g.sm_count * 48;
+        if (const char* v = getenv("MCT_K1_BPS")) { if (atoi(v) > 0) cap = (long long)g.sm_count * atoi(v); } // experiments
+        const long long rounds = (total_tiles + cap - 1) / cap;
+        const int blocks = (int)((total_tiles + rounds - 1) / rounds);
+        const int threads = (long long)G.ngroups * G.per_group <= 1024 ? 128 : 256;
+        if (npt == 4) k1_box_kernel<4><<<blocks, threads, 0, st>>>(P, G);
+        else k1_box_kernel<2><<<blocks, threads, 0, st>>>(P, G);
+      }
     }
   }
   CK(cudaGetLastError());
@@ -1229,7 +1277,7 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
 }
 
 int mct_set_k1_mode(int mode) {
-  if (mode < 0 || mode > 2) return fail(MCT_E_INVALID_ARG, "set_k1_mode: mode must be 0 (segment lists), 1 (tree walk) or 2 (column scan)");
+  if (mode < 0 || mode > 3) return fail(MCT_E_INVALID_ARG, "set_k1_mode: mode must be 0 (box lists, float32 walk), 1 (tree walk), 2 (column scan) or 3 (box lists, float64 walk)");
   g.k1_mode = mode;
   return MCT_OK;
 }

@@ -24,19 +24,20 @@ def _empty_model(grid):
 
 
 def _both_k1(mct, pts, par, grid, box, pm=None, init=None):
-    """GPU (all three kernel shapes: tree walk per node, round-1 column scan, segment lists) and oracle."""
+    """GPU (all four kernel shapes: tree walk per node, round-1 column scan, box lists with the float64 walk, box lists
+    with the float32 walk = production) and oracle."""
     outs = []
-    for mode in (1, 2, 0):
+    for mode in (1, 2, 3, 0):
         mct.set_k1_mode(mode)
         vp, vs, rho, sid = _empty_model(grid) if init is None else [a.copy() for a in init]
         mct.kdtree_to_grid(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
         outs.append((vp, vs, rho, sid))
-    for other in (outs[1], outs[2]):
+    for other in outs[1:]:
         for x, y in zip(outs[0], other):
             assert np.array_equal(x, y), f"the nearest-nucleus kernels disagree in {(x != y).sum()} nodes"
     vp, vs, rho, sid = _empty_model(grid) if init is None else [a.copy() for a in init]
     orc.kdtree_to_grid(pts, par, grid, box, vp, vs, rho, sid, pm=pm)
-    return [outs[2], (vp, vs, rho, sid)]
+    return [outs[3], (vp, vs, rho, sid)]
 
 
 def _assert_k1_equal(a, b):
