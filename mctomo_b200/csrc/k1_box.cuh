@@ -20,7 +20,7 @@
 // The float64 tie rule of the reference (1e-12 relative) is far inside that band, so exact ties always reach the walk.
 #pragma once
 
-#define K1B_MAXT 768  // staged candidates per tile (union over its boxes)
+#define K1B_MAXT 512  // staged candidates per tile (union over its boxes)
 #define K1B_MAXN 768  // nuclei near the tile in the plane
 #define K1B_MAXZ 512  // nodes of a column window (larger windows use the column kernel)
 #define K1B_MAXC 64   // tile extent in x or y
@@ -76,7 +76,7 @@ __device__ __noinline__ int k1b_walk(const K1Params& P0, const KdNodeDev* nodes,
 }
 
 template <int NPT>
-__global__ void __launch_bounds__(256, 3) k1_box_kernel(const __grid_constant__ K1Params P0, const __grid_constant__ K1BGeom G) {
+__global__ void __launch_bounds__(256, 4) k1_box_kernel(const __grid_constant__ K1Params P0, const __grid_constant__ K1BGeom G) {
   __shared__ K1BShared S;
   const K1Params& P = P0; // geometry and window: kernel-uniform (constant bank); per-model pointers are the m_* locals
   const KdNodeDev* m_nodes = P0.nodes;

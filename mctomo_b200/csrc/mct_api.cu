@@ -335,7 +335,7 @@ int launch_k1(const mct_grid* gr, const int32_t w[6], const double* pm, double* 
         if (!forced) {
           if (P.wz > 2) seglen = std::max(4, (seglen + 3) / 4 * 4); // whole 4-node units per segment
           const int ups = std::max(1, seglen / (P.wz > 2 ? 4 : 2));
-          while (ttx * tty * ups < 32) { // a box (tile x segment) should fill a warp
+          while (ttx * tty * ups < 64) { // a box (tile x segment) should fill a warp (measured: two warps' worth of columns is best)
             if (2 * ttx <= tty) ttx *= 2;
             else tty *= 2;
           }
