@@ -298,6 +298,19 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
  * the round-1 shape (a warp per column, every node scans its column's survivors).  mode 1: kdtree2's traversal for
  * every node.  Results are identical in all three. */
 int mct_set_k1_mode(int mode);
+
+/* ---- low-velocity columns: the generalized reflection/transmission branch of surfmodes ------------------------------
+ * Replaces RayleighModes / LoveModes (surfmodes/surfmodes.f90:84-87,96-99,185-306) with SearchRayleigh / SearchLove
+ * (allmodes = 0), C_Interval[_L], the secular functions of Rayleigh.f90 / Love.f90 and bisecim (util.f90).
+ * enable = 1: columns the nlvls1 predicate sends to that branch are solved on the device after the surfdisp96 kernel
+ * (ierr 0/1 as RayleighModes / LoveModes set it; entries the Fortran never assigns keep opt->preset) instead of being
+ * reported as ierr = 2 / MCT_E_GRT_NEEDED.  Applies to nmodes <= 0 only (surfmmodes prints "not supported yet").
+ * par6 = {tolmin, tolmax, smin_min, smin_max, dcm, dc2} of T_MODES_PARA (surfmodes.f90:23-30); NULL keeps the current
+ * values (default: likelihood_surf.F90:175-182 with settings%tol = 1e-6).  paras%dc is opt->dphase.  Default: off. */
+int mct_set_grt(int enable, const double* par6);
+/* out3 = {columns the last dispersion call solved on that branch, secular-function evaluations and interface steps spent
+ * there since mct_reset_stats (as the reference's own loops would count them)} */
+int mct_grt_stats(int64_t out3[3]);
 /* Shape of the dispersion kernel.  mode 0 (default): batches of fewer than coop_max_columns columns (default 0 =
  * 1.7x the resident lanes of the GPU, 128 819 columns on a B200; pass -1 to keep) give every column a GROUP OF G LANES that
  * split getsol's bracketing scan: G = 256, 128 or 64 (a block of 8, 4 or 2 warps per column, while that keeps the

@@ -446,6 +446,26 @@ def fp64_peak_probe() -> dict:
     return {"dfma_tflops": a.value, "dmul_dadd_tflops": b.value}
 
 
+def set_grt(enable: bool, par6=None):
+    """Solve low-velocity columns with the generalized R/T kernel (surfmodes.f90:84-87,96-99) instead of reporting ierr = 2."""
+    L = lib()
+    L.mct_set_grt.argtypes = [C.c_int, C.c_void_p]
+    if par6 is None:
+        _check(L.mct_set_grt(1 if enable else 0, None))
+    else:
+        p = np.ascontiguousarray(par6, dtype=np.float64)
+        assert p.size == 6
+        _check(L.mct_set_grt(1 if enable else 0, p.ctypes.data))
+
+
+def grt_stats():
+    L = lib()
+    L.mct_grt_stats.argtypes = [C.c_void_p]
+    out = np.zeros(3, np.int64)
+    _check(L.mct_grt_stats(out.ctypes.data))
+    return {"columns": int(out[0]), "secfun": int(out[1]), "interface_steps": int(out[2])}
+
+
 def set_k1_mode(mode: int = 0):
     """0 culled brute force per column (default), 1 kdtree2 traversal for every node."""
     L = _bind_batch()

@@ -246,6 +246,7 @@ struct LayParams {
   int32_t modetype; // 1 Rayleigh, 0 Love (for the nlvls1 predicate)
   float4* lay; int32_t* nlay; int32_t* status; int32_t stride;
   int32_t* flags; // per model b: flags[2*b+1] = max status code
+  int32_t grt_on; // low-velocity columns will be solved by the generalized R/T kernel: status 2 is not a condition to report
 };
 
 // convert_to_layer (src/likelihood_surf.F90:523-629 / forward_modelling.f90:72-175) + the real(.,4)
@@ -319,13 +320,13 @@ __global__ void __launch_bounds__(128) layerize_kernel(const __grid_constant__ L
   if (st == 0 && nlvls1 != 0) st = 2;
   P.nlay[c] = nl > MCT_MAX_LAYERS ? MCT_MAX_LAYERS : nl;
   P.status[c] = st;
-  if (st != 0 && P.flags) atomicMax(&P.flags[2 * b + 1], st);
+  if (st != 0 && !(st == 2 && P.grt_on) && P.flags) atomicMax(&P.flags[2 * b + 1], st);
 }
 
 // Layering of pre-layered columns (mct_surfmodes_batch): narrow to float4, evaluate the same predicate.
 struct PreLayParams {
   const double* thick; const double* vp; const double* vs; const double* rho; const long long* offsets;
-  int32_t ncol, modetype, stride;
+  int32_t ncol, modetype, stride, grt_on;
   float4* lay; int32_t* nlay; int32_t* status; int32_t* flags;
 };
 __global__ void __launch_bounds__(128) prelayered_kernel(const __grid_constant__ PreLayParams P) {
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(128) prelayered_kernel(const __grid_constant__
   }
   P.nlay[c] = n < 1 ? 1 : (n > MCT_MAX_LAYERS ? MCT_MAX_LAYERS : n);
   P.status[c] = st;
-  if (st != 0 && P.flags) atomicMax(&P.flags[1], st);
+  if (st != 0 && !(st == 2 && P.grt_on) && P.flags) atomicMax(&P.flags[1], st);
 }
 
 // like%vel(:, iy0+1:iy1+1, ix0+1:ix1+1) = pvel, then edge replication (likelihood_surf.F90:259-264).

@@ -22,6 +22,7 @@
 #include "k1_voronoi.cuh"
 #include "k2_dispersion.cuh"
 #include "k2_dedup.cuh"
+#include "k5_grt.cuh"
 #include "kdtree_build.h"
 
 namespace {
@@ -82,7 +83,12 @@ struct Ctx {
   DevBuf pl_thick, pl_vp, pl_vs, pl_rho, pl_off;
   DevBuf flags;    // int32[4]: [0] model_invalid, [1] max status, [2] k1 error
   DevBuf bflags;   // int32[2*nb] for host-pointer batch calls
-  DevBuf counters; // u64[4]
+  DevBuf counters; // u64[16]: [0..2] represented work, [3] self-test scratch, [4..6] executed work, [8..9] generalized R/T kernel
+  // low-velocity columns (k5_grt.cuh): mct_set_grt
+  int grt_on = 0;
+  double grt_par[6] = {1e-6, 1e-5, (double)1e-3f, (double)5e-3f, 1e-3, 1e-3}; // tolmin, tolmax, smin_min, smin_max, dcm, dc2 (likelihood_surf.F90:175-182, tol = 1e-6)
+  DevBuf grt_list, grt_scratch;
+  long long grt_last_cols = 0;
   DevBuf ray_pts, ray_off, ray_time; // mct_group_times_dev staging
   PinBuf pin_a, pin_b, pin_small;
   mct_stats host_stats = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -632,6 +638,60 @@ int launch_k2(int ncol, int stride, const double* freqs, int np, const mct_disp_
   return MCT_OK;
 }
 
+
+// Low-velocity columns (status 2) after the dispersion kernel: the generalized R/T search of surfmodes.f90:84-87,96-99
+// (k5_grt.cuh).  lp: the layering parameters of the call (model-column form) or null with the pre-layered buffers set.
+int launch_grt(int ncol, const LayParams* lp, const PreLayParams* pp, const double* freqs, int np, const mct_disp_opts* opt, double* d_pvel,
+               double* d_gvel, int32_t* d_ierr, const int32_t* d_skip, int32_t* d_flags, int cols_per_model, cudaStream_t st) {
+  g.grt_last_cols = 0;
+  if (!g.grt_on || opt->nmodes > 0 || g.shard_n > 1 || ncol < 1) return MCT_OK; // surfmmodes has no such branch (surfmodes.f90:153,165)
+  int rc;
+  if ((rc = ensure(g.grt_list, sizeof(int32_t) * ((size_t)ncol + 1)))) return rc;
+  int32_t* list = (int32_t*)g.grt_list.p;
+  int32_t* d_count = list + ncol;
+  CK(cudaMemsetAsync(d_count, 0, sizeof(int32_t), st));
+  grt_collect_kernel<<<(ncol + 255) / 256, 256, 0, st>>>((const int32_t*)g.status.p, ncol, list, d_count);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 1;
+  int32_t count = 0;
+  CK(cudaMemcpyAsync(&count, d_count, sizeof count, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (count <= 0) return MCT_OK;
+  const int chunk = std::min<int>(count, 1024);
+  if ((rc = ensure(g.grt_scratch, sizeof(double) * (size_t)GRT_SCRATCH * (size_t)chunk))) return rc;
+  GrtParams P;
+  memset(&P, 0, sizeof P);
+  if (lp) {
+    P.vp = lp->vp; P.vs = lp->vs; P.rho = lp->rho;
+    P.ny = lp->ny; P.nz = lp->nz; P.ix0 = lp->ix0; P.iy0 = lp->iy0; P.wx = lp->wx; P.wy = lp->wy;
+    P.model_stride = lp->model_stride;
+    P.dz = lp->dz; P.waterDepth = lp->waterDepth; P.scaling = lp->scaling; P.layer_eps = lp->layer_eps; P.water_thresh = lp->water_thresh;
+  } else {
+    P.pl_thick = pp->thick; P.pl_vp = pp->vp; P.pl_vs = pp->vs; P.pl_rho = pp->rho; P.pl_off = pp->offsets;
+  }
+  P.modetype = opt->raylov; P.phaseGroup = opt->phaseGroup; P.np = np;
+  P.dc = opt->dphase;
+  P.tolmin = g.grt_par[0]; P.tolmax = g.grt_par[1]; P.smin_min = g.grt_par[2]; P.smin_max = g.grt_par[3]; P.dcm = g.grt_par[4]; P.dc2 = g.grt_par[5];
+  for (int i = 0; i < MCT_MAX_PERIODS; ++i) P.freqs[i] = i < np ? freqs[i] : 0.0;
+  P.list = list; P.nlist = count;
+  P.skip = d_skip; P.cols_per_model = cols_per_model > 0 ? cols_per_model : ncol;
+  P.scratch = (double*)g.grt_scratch.p;
+  P.pvel = d_pvel; P.gvel = d_gvel; P.ierr = d_ierr;
+  P.counters = g.count_on ? (unsigned long long*)g.counters.p + 8 : nullptr;
+  P.flags = d_flags;
+  {
+    ProfScope ps(2, st);
+    for (int c0 = 0; c0 < count; c0 += chunk) {
+      P.list0 = c0;
+      grt_kernel<<<std::min(chunk, count - c0), 32, 0, st>>>(P);
+      g.host_stats.n_launches += 1;
+    }
+  }
+  CK(cudaGetLastError());
+  g.grt_last_cols = count;
+  return MCT_OK;
+}
+
 // check_model + layerize + K2 on device-resident whole-grid arrays (pl.nb models stacked along x).
 // d_flags: int32[2*nb]: per model {model_invalid, max condition code}.
 int disp_core(const double* d_vp, const double* d_vs, const double* d_rho, const mct_grid* gr, const DispPlan& pl,
@@ -661,13 +721,15 @@ int disp_core(const double* d_vp, const double* d_vs, const double* d_rho, const
   L.lay = (float4*)g.lay.p; L.nlay = (int32_t*)g.nlay.p; L.status = (int32_t*)g.status.p;
   L.stride = pl.stride;
   L.flags = d_flags;
+  L.grt_on = (g.grt_on && opt->nmodes <= 0 && g.shard_n <= 1) ? 1 : 0;
   {
     ProfScope ps(2, st);
     layerize_kernel<<<(pl.ncol + 127) / 128, 128, 0, st>>>(L);
   }
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
-  return launch_k2(pl.ncol, pl.stride, freqs, np, opt, d_pvel, d_gvel, d_ierr, do_check ? d_flags : nullptr, pl.cpm, gr->nz + 1, st);
+  if ((rc = launch_k2(pl.ncol, pl.stride, freqs, np, opt, d_pvel, d_gvel, d_ierr, do_check ? d_flags : nullptr, pl.cpm, gr->nz + 1, st))) return rc;
+  return launch_grt(pl.ncol, &L, nullptr, freqs, np, opt, d_pvel, d_gvel, d_ierr, do_check ? d_flags : nullptr, d_flags, pl.cpm, st);
 }
 
 // K1 per model + property maps + disp_core over the x-slab ixs0..ixs1 of every model of the resident set.
@@ -758,9 +820,9 @@ int mct_init(int device) {
   g.device = device;
   int rc;
   if ((rc = ensure(g.flags, 4 * sizeof(int32_t)))) return rc;
-  if ((rc = ensure(g.counters, 8 * sizeof(unsigned long long)))) return rc;
+  if ((rc = ensure(g.counters, 16 * sizeof(unsigned long long)))) return rc;
   CK(cudaMemset(g.flags.p, 0, 4 * sizeof(int32_t)));
-  CK(cudaMemset(g.counters.p, 0, 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(g.counters.p, 0, 16 * sizeof(unsigned long long)));
   g.host_stats = mct_stats{0, 0, 0, 0, 0, 0, 0, 0};
   if (const char* v = getenv("MCT_K2_VARIANT")) g.k2_variant = atoi(v);
   if (const char* v = getenv("MCT_SORT_STABLE")) g.sort_stable = atoi(v);
@@ -781,7 +843,7 @@ int mct_shutdown(void) {
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
   DevBuf* bufs[] = {&g.nodes, &g.rpts, &g.ind, &g.params, &g.kmodels, &g.m_vp, &g.m_vs, &g.m_rho, &g.m_sites, &g.lay, &g.layr, &g.nlay, &g.status, &g.perm, &g.bins, &g.dd_table, &g.dd_i32, &g.layc, &g.layrc, &g.nlayc, &g.sh_perm, &g.sh_p, &g.sh_g, &g.sh_i,
-                    &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.ray_pts, &g.ray_off, &g.ray_time};
+                    &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.grt_list, &g.grt_scratch, &g.ray_pts, &g.ray_off, &g.ray_time};
   for (DevBuf* b : bufs) release(*b);
   release_misfit_globals();
   comm_release();
@@ -805,7 +867,7 @@ int mct_set_counters(int on) {
 int mct_reset_stats(void) {
   NEED_INIT();
   CK(cudaStreamSynchronize(g.stream));
-  CK(cudaMemset(g.counters.p, 0, 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(g.counters.p, 0, 16 * sizeof(unsigned long long)));
   g.host_stats = mct_stats{0, 0, 0, 0, 0, 0, 0, 0};
   return MCT_OK;
 }
@@ -1097,10 +1159,12 @@ int mct_surfmodes_batch(const double* thick, const double* vp, const double* vs,
   L.offsets = (const long long*)g.pl_off.p;
   L.ncol = ncol; L.modetype = opt->raylov; L.stride = stride;
   L.lay = (float4*)g.lay.p; L.nlay = (int32_t*)g.nlay.p; L.status = (int32_t*)g.status.p; L.flags = fl;
+  L.grt_on = (g.grt_on && opt->nmodes <= 0) ? 1 : 0;
   prelayered_kernel<<<(ncol + 127) / 128, 128, 0, st>>>(L);
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
   if ((rc = launch_k2(ncol, stride, freqs, np, opt, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, nullptr, ncol, maxl, st))) return rc;
+  if ((rc = launch_grt(ncol, nullptr, &L, freqs, np, opt, (double*)g.o_pvel.p, (double*)g.o_gvel.p, (int32_t*)g.o_ierr.p, nullptr, fl, ncol, st))) return rc;
   int32_t hflags[2] = {0, 0};
   CK(cudaMemcpyAsync(phase, g.o_pvel.p, nbo, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(group, g.o_gvel.p, nbo, cudaMemcpyDeviceToHost, st));
@@ -1273,6 +1337,25 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
   accumulate_stats_kernel<<<grid_blocks(n, 256, 8), 256, 0, pick(stream)>>>(d_vs, d_vp, d_aveS, d_stdS, d_aveP, d_stdP, (long long)n);
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
+  return MCT_OK;
+}
+
+int mct_set_grt(int enable, const double* par6) {
+  if (par6) {
+    for (int i = 0; i < 6; ++i) if (!(par6[i] > 0)) return fail(MCT_E_INVALID_ARG, "set_grt: every parameter must be positive");
+    for (int i = 0; i < 6; ++i) g.grt_par[i] = par6[i];
+  }
+  g.grt_on = enable ? 1 : 0;
+  return MCT_OK;
+}
+
+int mct_grt_stats(int64_t out3[3]) {
+  NEED_INIT();
+  if (!out3) return fail(MCT_E_INVALID_ARG, "grt_stats: NULL pointer");
+  unsigned long long c[2];
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(c, (unsigned long long*)g.counters.p + 8, sizeof c, cudaMemcpyDeviceToHost));
+  out3[0] = g.grt_last_cols; out3[1] = (int64_t)c[0]; out3[2] = (int64_t)c[1];
   return MCT_OK;
 }
 

@@ -293,3 +293,36 @@ def sites_locate(points, sites_id, grid, queries):
     if fn(points.ctypes.data, len(points), sid.ctypes.data, C.byref(og), queries.ctypes.data, len(queries), out.ctypes.data):
         raise ValueError("degenerate nuclei")
     return out
+
+
+# GRT parameter sets: (tolmin, tolmax, smin_min, smin_max, dcm, dc2) as the two reference callers set T_MODES_PARA
+GRT_PAR_LIKELIHOOD = (1e-6, 1e-5, float(np.float32(1e-3)), float(np.float32(5e-3)), 1e-3, 1e-3)  # likelihood_surf.F90:173-182 with tol = 1e-6
+GRT_PAR_MODELLING = (float(np.float32(1e-6)), float(np.float32(1e-7)), float(np.float32(1e-3)), float(np.float32(5e-3)),
+                     float(np.float32(1e-3)), float(np.float32(1e-3)))  # forward_modelling.f90:395-404
+
+
+def grt_modes(thick, vp, vs, rho, freqs, modetype=1, phaseGroup=0, dc=1e-3, par=GRT_PAR_LIKELIHOOD, math_mode=PORTABLE, preset=100.0):
+    """The generalized R/T branch of surfmodes (oracle/grt_ref.c).  Returns (ierr, phase, group, counters)."""
+    lib = L()
+    vpt = C.c_void_p
+    lib.orc_grt_modes.argtypes = [vpt] * 4 + [C.c_int, vpt, C.c_int, C.c_int, C.c_int, C.c_double, vpt, C.c_int, vpt, vpt, vpt]
+    thick, vp, vs, rho, freqs = f64(thick), f64(vp), f64(vs), f64(rho), f64(freqs)
+    par = f64(np.array(par))
+    ph = np.full(len(freqs), preset)
+    gr = np.full(len(freqs), preset)
+    cnt = np.zeros(2, np.int64)
+    ierr = lib.orc_grt_modes(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, len(thick), freqs.ctypes.data,
+                             len(freqs), modetype, phaseGroup, dc, par.ctypes.data, math_mode, ph.ctypes.data, gr.ctypes.data,
+                             cnt.ctypes.data)
+    return ierr, ph, gr, cnt
+
+
+def grt_secfun(thick, vp, vs, rho, freq, modetype, c, math_mode=PORTABLE):
+    lib = L()
+    vpt = C.c_void_p
+    lib.orc_grt_secfun.argtypes = [vpt] * 4 + [C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, vpt, vpt]
+    thick, vp, vs, rho = f64(thick), f64(vp), f64(vs), f64(rho)
+    re, im = C.c_double(0), C.c_double(0)
+    rc = lib.orc_grt_secfun(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, len(thick), freq, modetype, c,
+                            math_mode, C.byref(re), C.byref(im))
+    return rc, re.value, im.value

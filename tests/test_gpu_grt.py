@@ -1,0 +1,126 @@
+"""GPU parity of the generalized R/T branch (mctomo_b200/csrc/k5_grt.cuh) against oracle/grt_ref.c through the C ABI.
+
+Bit-identical phase and group velocities, ierr and both work counters against the oracle in PORTABLE math mode (same
+exp / sincos as the device); within north_star's 1e-5 km/s of the oracle with libm.  The oracle of this branch is
+"parity unpinned" (tests/test_oracle_grt.py pins it on physics only)."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from mctomo_b200 import synth
+from mctomo_b200.capi import disp_opts
+from test_oracle_grt import FREQS, MODELS, crust
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(cols):
+    offs = [0]
+    for c in cols:
+        offs.append(offs[-1] + len(c[0]))
+    a = [np.concatenate([c[k] for c in cols]) for k in range(4)]
+    return a, offs
+
+
+def _random_lvl_columns(rng, n, water=False):
+    cols = []
+    while len(cols) < n:
+        nl = int(rng.integers(4, 9))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        k = int(rng.integers(1, nl - 1))
+        vs[k] = vs[0] - rng.uniform(0.1, 0.5)  # a layer slower than the top one: the GRT branch
+        th = rng.uniform(0.5, 4.0, nl)
+        th[-1] = 0
+        c = crust(vs, th, water=rng.uniform(0.3, 2.0) if water else None)
+        cols.append(c)
+    return cols
+
+
+@pytest.mark.parametrize("raylov,pg", [(1, 0), (1, 1), (0, 0), (0, 1)])
+def test_grt_prelayered_columns_bit_identical(mct, raylov, pg):
+    rng = np.random.default_rng(100 + 2 * raylov + pg)
+    cols = [MODELS[k] for k in sorted(MODELS)] + _random_lvl_columns(rng, 21)
+    # ordinary columns in between: they must keep going through surfdisp96
+    vs = np.array([2.5, 3.0, 3.5, 4.2]); cols.insert(2, crust(vs, [1.0, 2.0, 3.0, 0.0]))
+    (th, vp, vs_, rho), offs = _batch(cols)
+    opts = disp_opts(raylov=raylov, phaseGroup=pg, nmodes=0)
+    mct.set_grt(False)
+    ph0, gr0, ie0, rc0 = mct.surfmodes_batch(th, vp, vs_, rho, offs, FREQS, opts)
+    assert rc0 == mct.MCT_E_GRT_NEEDED and (ie0 == 2).sum() == len(cols) - 1
+    mct.reset_stats()
+    mct.set_grt(True, orc.GRT_PAR_LIKELIHOOD)
+    try:
+        ph, gr, ie, rc = mct.surfmodes_batch(th, vp, vs_, rho, offs, FREQS, opts)
+        st = mct.grt_stats()
+    finally:
+        mct.set_grt(False)
+    assert rc == 0 and st["columns"] == len(cols) - 1
+    tot = np.zeros(2, np.int64)
+    nfail = 0
+    for c, col in enumerate(cols):
+        if c == 2:
+            assert ie[c] == 0 and np.array_equal(ph[c], ph0[c]) and np.array_equal(gr[c], gr0[c])
+            continue
+        ierr, p, g, cnt = orc.grt_modes(*col, FREQS, modetype=raylov, phaseGroup=pg, dc=opts.dphase, par=orc.GRT_PAR_LIKELIHOOD,
+                                        math_mode=orc.PORTABLE, preset=opts.preset)
+        tot += cnt
+        nfail += ierr
+        assert ie[c] == ierr, (c, ie[c], ierr)
+        assert np.array_equal(ph[c], p), (c, ph[c], p)
+        if pg:
+            assert np.array_equal(gr[c], g), (c, gr[c], g)
+        if ierr == 0:
+            _, pl, gl, _ = orc.grt_modes(*col, FREQS, modetype=raylov, phaseGroup=pg, dc=opts.dphase, par=orc.GRT_PAR_LIKELIHOOD,
+                                         math_mode=orc.LIBM, preset=opts.preset)
+            assert np.abs(pl - ph[c]).max() < 1e-5
+    assert st["secfun"] == tot[0] and st["interface_steps"] == tot[1], (st, tot)
+    assert nfail < len(cols) // 2
+
+
+def test_grt_stoneley_under_water(mct):
+    rng = np.random.default_rng(7)
+    cols = _random_lvl_columns(rng, 12, water=True)
+    (th, vp, vs_, rho), offs = _batch(cols)
+    opts = disp_opts(raylov=1, phaseGroup=1, nmodes=0)
+    mct.set_grt(True, orc.GRT_PAR_MODELLING)
+    try:
+        ph, gr, ie, rc = mct.surfmodes_batch(th, vp, vs_, rho, offs, FREQS[:7], opts)
+    finally:
+        mct.set_grt(False)
+    for c, col in enumerate(cols):
+        ierr, p, g, _ = orc.grt_modes(*col, FREQS[:7], modetype=1, phaseGroup=1, dc=opts.dphase, par=orc.GRT_PAR_MODELLING,
+                                      math_mode=orc.PORTABLE, preset=opts.preset)
+        assert ie[c] == ierr and np.array_equal(ph[c], p) and np.array_equal(gr[c], g), c
+
+
+def test_grt_on_model_columns_as_program_modelling_calls_it(mct):
+    """Columns of a gridded model (layered on the device in float64), no check_model: forward_modelling.f90:393-429."""
+    grid = synth.make_grid(6, 5, 24)
+    pts, par = synth.generate_model(grid, 40, 11)
+    vp, vs, rho, sid = [np.zeros(grid.shape) for _ in range(3)] + [np.zeros(grid.shape, np.int32)]
+    orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
+    rng = np.random.default_rng(5)
+    lvl = [(1, 2), (3, 0), (4, 4), (0, 1)]
+    for (i, j) in lvl:  # a slow zone below the top cell
+        k0 = int(rng.integers(6, 12))
+        vs[i, j, k0:k0 + 4] = vs[i, j, 0] * 0.8
+        vp[i, j, k0:k0 + 4] = 1.73 * vs[i, j, k0]
+    freqs = FREQS[:8]
+    opts = disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    win = (1, grid.nx, 1, grid.ny)
+    mct.set_grt(True, orc.GRT_PAR_MODELLING)
+    try:
+        pv, gv, ie, inval, rc = mct.surf_dispersion(vp, vs, rho, grid, win, freqs, opts, check=False)
+    finally:
+        mct.set_grt(False)
+    po, go, io, cnt, nun = orc.surf_dispersion(vp, vs, rho, grid, win, freqs)
+    assert nun == len(lvl) and rc == 0
+    for i in range(grid.nx):
+        for j in range(grid.ny):
+            if (i, j) in lvl:
+                n, (th, a, b, r) = orc.convert_column(vp[i, j], vs[i, j], rho[i, j], grid.dz)
+                ierr, p, g, _ = orc.grt_modes(th, a, b, r, freqs, modetype=1, phaseGroup=0, dc=opts.dphase, par=orc.GRT_PAR_MODELLING,
+                                              math_mode=orc.PORTABLE, preset=opts.preset)
+                assert ie[i, j] == ierr and np.array_equal(pv[i, j], p), (i, j)
+            else:
+                assert ie[i, j] == io[i, j] and np.array_equal(pv[i, j], po[i, j])
