@@ -319,34 +319,57 @@ __device__ __forceinline__ double g_secf(const GrtCol& G, int kind, double c, in
   return g_secfun_L(G, c, ll, imf, nlay);
 }
 
-// bisecim: util.f90:68-122 (every lane runs it on the same arguments)
-__device__ double g_bisecim(const GrtCol& G, int kind, int ll, double x1, double x2, double f1, double f2, int* iq, unsigned& nsec, unsigned& nlay) {
-  double xa = x1, xb = x2, ya = f1, yb = f2, x3, y3, xt1, xt2, dx, dxt, u1, u2, imf = 0, imf2 = 0;
+// bisecim: util.f90:68-122.  The bracket follows a pure bisection path (the interpolated estimate xt2 only enters the
+// stopping test and the result), so the warp speculates five levels at a time: lane t-1 evaluates node t of the binary
+// tree of mid-points below the current bracket (heap numbering: left child = the half the Fortran keeps when
+// fa*y(3) < 0), then the path is walked with the reference's own arithmetic and only the evaluations it consumes are
+// counted.  Mid-points are formed from the same operands in the same order as the sequential code forms them.
+__device__ double g_bisecim(const GrtCol& G, int kind, int ll, double x1, double x2, double f1, double f2, int* iq, unsigned& nsec, unsigned& nlay,
+                            int lane) {
+  double xa = x1, xb = x2, ya = f1, yb = f2, xt1, xt2, dx, dxt, u1, u2;
   const double fa = f1;
   const double smin2 = G.smin * G.smin * 2.;
   int nc = 0;
   dx = fabs(x1 - x2);
   xt1 = (xa + xb) / 2.;
+  const int t = lane + 1;                       // node 1..31 (lane 31 repeats node 16's work unused)
+  const int L = 31 - __clz(t > 31 ? 16 : t);    // level of the node, 0..4
+  const int tt = t > 31 ? 16 : t;
   for (;;) {
-    x3 = (xa + xb) / 2.;
-    y3 = g_secf(G, kind, x3, ll, &imf, nlay); nsec++;
-    u1 = (xb - xa) / (yb - ya);
-    u2 = (xb - x3) / (yb - y3);
-    xt2 = xa - ya * (u1 - yb * ((u2 - u1) / (y3 - ya)));
-    dxt = fabs(xt2 - xt1);
-    dx = dx / 2.;
-    if (dx < dxt) dxt = dx;
-    if (dxt < G.tol) {
-      u1 = g_secf(G, kind, xt2, ll, &imf2, nlay); nsec++;
-      u2 = y3;
-      if (u1 * u1 + imf2 * imf2 < smin2 || u2 * u2 + imf * imf < smin2) { *iq = 0; return fabs(u1) < fabs(u2) ? xt2 : x3; }
-      *iq = -1;
-      return 0.;
+    // this lane's node: descend from the current bracket
+    double a = xa, b = xb;
+    for (int d = 0; d < L; ++d) {
+      const double m = (a + b) / 2.;
+      if ((tt >> (L - 1 - d)) & 1) a = m; else b = m;
     }
-    xt1 = xt2;
-    if (fa * y3 < 0) { xb = x3; yb = y3; } else { xa = x3; ya = y3; }
-    nc++;
-    if (nc >= 1000) { *iq = -1; return 0; }
+    const double xn = (a + b) / 2.;
+    double imfn = 0;
+    unsigned layn = 0;
+    const double yn = g_secf(G, kind, xn, ll, &imfn, layn);
+    int cur = 1;
+    for (int lev = 0; lev < 5; ++lev) {
+      const double x3 = __shfl_sync(0xffffffffu, xn, cur - 1), y3 = __shfl_sync(0xffffffffu, yn, cur - 1);
+      const double imf = __shfl_sync(0xffffffffu, imfn, cur - 1);
+      nsec += 1; nlay += __shfl_sync(0xffffffffu, layn, cur - 1);
+      u1 = (xb - xa) / (yb - ya);
+      u2 = (xb - x3) / (yb - y3);
+      xt2 = xa - ya * (u1 - yb * ((u2 - u1) / (y3 - ya)));
+      dxt = fabs(xt2 - xt1);
+      dx = dx / 2.;
+      if (dx < dxt) dxt = dx;
+      if (dxt < G.tol) {
+        double imf2 = 0;
+        u1 = g_secf(G, kind, xt2, ll, &imf2, nlay); nsec++;
+        u2 = y3;
+        if (u1 * u1 + imf2 * imf2 < smin2 || u2 * u2 + imf * imf < smin2) { *iq = 0; return fabs(u1) < fabs(u2) ? xt2 : x3; }
+        *iq = -1;
+        return 0.;
+      }
+      xt1 = xt2;
+      if (fa * y3 < 0) { xb = x3; yb = y3; cur = 2 * cur; } else { xa = x3; ya = y3; cur = 2 * cur + 1; }
+      nc++;
+      if (nc >= 1000) { *iq = -1; return 0; }
+    }
   }
 }
 
@@ -364,13 +387,10 @@ __device__ double g_ncf(const GrtCol& G, double c, int love) {
   return G.w / (2.0 * pi_s) * sum;
 }
 
-// ascending bitonic sort of a[1..n] by the warp (pads to a power of two with +inf; n <= GRT_NVPAD)
-__device__ void g_sort(double* a1, int n, int lane) {
-  double* a = a1 + 1;
-  int m = 1;
-  while (m < n) m <<= 1;
-  for (int i = n + lane; i < m; i += 32) a[i] = 1.0e300;
-  __syncwarp();
+// ascending sort of a[1..n] by the warp: a bitonic network, in shared memory when n <= GRT_SSORT, else in the column's
+// scratch (pads to a power of two with +inf; n <= GRT_NVPAD).  Any ascending sort yields the array util.f90's sort does.
+#define GRT_SSORT 2048
+__device__ void g_bitonic(double* a, int m, int lane) {
   for (int k = 2; k <= m; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = lane; i < m; i += 32) {
@@ -384,9 +404,49 @@ __device__ void g_sort(double* a1, int n, int lane) {
       __syncwarp();
     }
 }
+__device__ void g_sort(double* a1, int n, int lane, double* ssort) {
+  double* a = a1 + 1;
+  int m = 1;
+  while (m < n) m <<= 1;
+  if (m <= GRT_SSORT) {
+    for (int i = lane; i < m; i += 32) ssort[i] = i < n ? a[i] : 1.0e300;
+    __syncwarp();
+    g_bitonic(ssort, m, lane);
+    for (int i = lane; i < n; i += 32) a[i] = ssort[i];
+    __syncwarp();
+    return;
+  }
+  for (int i = n + lane; i < m; i += 32) a[i] = 1.0e300;
+  __syncwarp();
+  g_bitonic(a, m, lane);
+}
+// a[1..n0] ascending already, a[n0+1..n0+t] arbitrary (t <= GRT_SSORT): sort the tail in shared memory, then every element
+// computes its place in the merged order by a binary search in the other run; tmp[1..n0+t] is scratch
+__device__ void g_sort_tail(double* a1, int n0, int t, int lane, double* ssort, double* tmp1) {
+  int m = 1;
+  while (m < t) m <<= 1;
+  for (int i = lane; i < m; i += 32) ssort[i] = i < t ? a1[n0 + 1 + i] : 1.0e300;
+  __syncwarp();
+  g_bitonic(ssort, m, lane);
+  for (int i = 1 + lane; i <= n0; i += 32) { // prefix element: + the tail elements strictly below it
+    const double x = a1[i];
+    int lo = 0, hi = t;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ssort[mid] < x) lo = mid + 1; else hi = mid; }
+    tmp1[i + lo] = x;
+  }
+  for (int k = lane; k < t; k += 32) { // tail element: + the prefix elements not above it
+    const double x = ssort[k];
+    int lo = 0, hi = n0;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a1[1 + mid] <= x) lo = mid + 1; else hi = mid; }
+    tmp1[k + 1 + lo] = x;
+  }
+  __syncwarp();
+  for (int i = 1 + lane; i <= n0 + t; i += 32) a1[i] = tmp1[i];
+  __syncwarp();
+}
 
 // C_Interval / C_Interval_L: fills G.ccc, G.ncc, G.im1 (lane 0 owns the scalars)
-__device__ void g_cinterval(GrtCol& G, int love, int lane) {
+__device__ void g_cinterval(GrtCol& G, int love, int lane, double* ssort) {
   double* vvv = G.vvv;
   double* ccc = G.ccc;
   const double pi_c = love ? 3.1415926535897932 : (double)3.1415926f;
@@ -395,6 +455,7 @@ __device__ void g_cinterval(GrtCol& G, int love, int lane) {
   const double lowv = love ? G.vsm : G.v1;
   int index0 = 0, ovf = 0;
   int NN = 0;
+  int sorted_prefix = 0; // vvv(1..sorted_prefix) is ascending by construction (the arithmetic fill of the first branch)
   if (lane == 0) { // nint: halves away from zero
     const double dn = g_ncf(G, G.vsy, love) - g_ncf(G, G.vsm, love);
     NN = dn >= 0 ? (int)floor(dn + 0.5) : -(int)floor(-dn + 0.5);
@@ -406,6 +467,7 @@ __device__ void g_cinterval(GrtCol& G, int love, int lane) {
     const double off = love ? 0.01 : 0.1;
     for (int i = 1 + lane; i <= n0; i += 32) vvv[i] = lowv - off + (double)i * (G.vsy - lowv + off) / (double)n0;
     index0 = n0 < 0 ? 0 : n0;
+    sorted_prefix = index0;
     for (int i = 1 + lane; i <= 100; i += 32) vvv[index0 + i] = G.vsy * (1. - .008 * i);
     index0 += 100;
     __syncwarp();
@@ -445,7 +507,7 @@ __device__ void g_cinterval(GrtCol& G, int love, int lane) {
     index0 = __shfl_sync(0xffffffffu, index0, 0);
     ovf = __shfl_sync(0xffffffffu, ovf, 0);
     __syncwarp();
-    g_sort(vvv, index0, lane);
+    g_sort(vvv, index0, lane, ssort);
     for (int j = 1; j <= 2; ++j) { // the mid-point of every sequential pair, twice (the second round runs over the unsorted result of the first)
       const int intemp = index0;
       int add = intemp - 1;
@@ -473,7 +535,8 @@ __device__ void g_cinterval(GrtCol& G, int love, int lane) {
   index0 = __shfl_sync(0xffffffffu, index0, 0);
   ovf = __shfl_sync(0xffffffffu, ovf, 0);
   __syncwarp();
-  g_sort(vvv, index0, lane);
+  if (sorted_prefix > GRT_SSORT / 2 && index0 - sorted_prefix <= GRT_SSORT) g_sort_tail(vvv, sorted_prefix, index0 - sorted_prefix, lane, ssort, ccc);
+  else g_sort(vvv, index0, lane, ssort);
   // "ensure no points are less than vsm": the sequence becomes s(1) = vsm + tol, s(m) = vvv(i0 + m - 2), m = 2 .. ; sorted input, so
   // i0 = 1 + #{vvv <= vsm}; when nothing exceeds vsm the array stays as it is
   int le = 0;
@@ -561,7 +624,7 @@ __device__ bool g_scan(const GrtCol& G, int kind, const double* pts, int npts, b
       const double f1 = __shfl_sync(0xffffffffu, fl, l), f2 = __shfl_sync(0xffffffffu, f, l);
       const int llb = __shfl_sync(0xffffffffu, ll, l);
       int iq = -1;
-      const double kt = swap ? g_bisecim(G, kind, llb, k2, k1, f2, f1, &iq, nsec, nlay) : g_bisecim(G, kind, llb, k1, k2, f1, f2, &iq, nsec, nlay);
+      const double kt = swap ? g_bisecim(G, kind, llb, k2, k1, f2, f1, &iq, nsec, nlay, lane) : g_bisecim(G, kind, llb, k1, k2, f1, f2, &iq, nsec, nlay, lane);
       if (iq == 0) { *root = kt; return true; }
     }
     const int nact = __popc(act);
@@ -624,11 +687,10 @@ __device__ double g_stfinder(const GrtCol& G, int n, double cst_in, int* ok) {
 }
 
 // SearchRayleigh / SearchLove, allmodes = 0: one root.  Returns ierr (0/1).
-__device__ int g_search_one(GrtCol& G, double c0, double* root, int lane, unsigned& nsec, unsigned& nlay) {
+__device__ int g_search_one(GrtCol& G, double c0, double* root, int lane, unsigned& nsec, unsigned& nlay, double* ssort) {
   const int love = G.modetype == 0;
-  for (int i = 1 + lane; i <= GRT_NV; i += 32) G.ccc[i] = 0.0; // ccc = 0
-  __syncwarp();
-  g_cinterval(G, love, lane);
+  // (the Fortran zeroes ccc(20000) here; only ccc(1..ncc), which C_Interval fills, is ever read)
+  g_cinterval(G, love, lane, ssort);
   if (G.overflow) return 1;
   const int index0 = G.ncc, im1 = G.im1;
   double* pts = G.vvv; // free again: the generated point lists of the fixed-step scans live here
@@ -816,6 +878,7 @@ __global__ void __launch_bounds__(32) grt_kernel(const __grid_constant__ GrtPara
   mct_exptab_stage();
   __shared__ GrtCol G;
   __shared__ int s_n;
+  __shared__ double s_sort[GRT_SSORT];
   const int lane = threadIdx.x;
   const int col = P.list[P.list0 + blockIdx.x];
   if (P.skip && P.skip[2 * (col / P.cols_per_model)] != 0) return; // a model check_model rejected: nothing is solved
@@ -849,7 +912,7 @@ __global__ void __launch_bounds__(32) grt_kernel(const __grid_constant__ GrtPara
     }
     __syncwarp();
     double root = 0;
-    const int ierr1 = g_search_one(G, c0, &root, lane, nsec, nlay);
+    const int ierr1 = g_search_one(G, c0, &root, lane, nsec, nlay, s_sort);
     if (ierr1 == 1) { ierr = 1; break; }
     if (lane == 0) pv[i - 1] = root;
     c0 = root;
@@ -859,7 +922,7 @@ __global__ void __launch_bounds__(32) grt_kernel(const __grid_constant__ GrtPara
       if (lane == 0) G.w = freq0 * 2 * pi_m;
       __syncwarp();
       double root0 = 0;
-      ierr = g_search_one(G, c0, &root0, lane, nsec, nlay);
+      ierr = g_search_one(G, c0, &root0, lane, nsec, nlay, s_sort);
       if (ierr == 1) break;
       const double gg = (P.freqs[i - 1] + dh) / root0 - P.freqs[i - 1] / root;
       if (lane == 0) gv[i - 1] = gg > 0 ? dh / gg : 0;
