@@ -204,6 +204,12 @@ module m_mctomo_b200
             import :: c_int, c_ptr
             type(c_ptr), value :: sess, aveS, stdS, aveP, stdP, nsamples
         end function
+        ! ---- low-velocity columns: the generalized R/T branch of surfmodes on the device (k5_grt.cuh) ----
+        integer(c_int) function mct_set_grt(enable, par6) bind(C, name='mct_set_grt')
+            import :: c_int, c_ptr
+            integer(c_int), value :: enable
+            type(c_ptr), value    :: par6        ! {tolmin, tolmax, smin_min, smin_max, dcm, dc2} of T_MODES_PARA, or NULL
+        end function
         ! ---- one chain on several GPUs: NCCL data plane inside the library (include/mctomo_b200.h, "multi-GPU") ----
         integer(c_int) function mct_comm_unique_id(id128) bind(C, name='mct_comm_unique_id')
             import :: c_int, c_ptr
@@ -335,7 +341,7 @@ contains
     ! variant 1: forward_modelling.f90 constants (EPS = 1E-5, presets 1000, no check_model).
     ! pvel, gvel: (np*max(nmodes,1), iy0:iy1, ix0:ix1); ierr: (iy0:iy1, ix0:ix1)
     subroutine surf_dispersion_b200(model, grid, ix0, ix1, iy0, iy1, freqs, raylov, phaseGroup, nmodes, &
-                                    dPhaseVel, pvel, gvel, ierr, invalid, variant)
+                                    dPhaseVel, pvel, gvel, ierr, invalid, variant, tol)
         type(T_MOD), intent(in), target :: model
         type(T_GRID), intent(in) :: grid
         integer, intent(in) :: ix0, ix1, iy0, iy1
@@ -346,12 +352,14 @@ contains
         integer(c_int), dimension(:,:), intent(inout), target :: ierr
         logical, intent(out) :: invalid
         integer, intent(in), optional :: variant
+        real(c_double), intent(in), optional :: tol           ! settings%tol: only the generalized R/T branch reads it
 
         type(mct_grid) :: g
         type(mct_disp_opts) :: opt
         integer(c_int), target :: inval
         integer(c_int) :: rc
         integer :: var
+        real(c_double), target :: grtpar(6)
 
         var = 0
         if (present(variant)) var = variant
@@ -372,6 +380,22 @@ contains
             opt%water_thresh = 0.0_c_double
             opt%preset = 1000.0_c_double
         endif
+        ! T_MODES_PARA of the generalized R/T branch, as the two callers set it: likelihood_surf.F90:175-182
+        ! (tolmin = settings%tol, tolmax = 10*tol) and forward_modelling.f90:397-404 (1E-6, 1e-7); smin and the steps are
+        ! default-real literals there, hence real(.., c_double) of a single-precision constant.  Columns with a
+        ! low-velocity layer are then solved on the device (surfmodes.f90:84-87,96-99), not reported as ierr = 2.
+        if (var == 0) then
+            grtpar(1) = 1.0E-6_c_double
+            if (present(tol)) grtpar(1) = tol
+            grtpar(2) = 10 * grtpar(1)
+            grtpar(5) = dPhaseVel; grtpar(6) = dPhaseVel
+        else
+            grtpar(1) = real(1E-6, c_double); grtpar(2) = real(1e-7, c_double)
+            grtpar(5) = real(1E-3, c_double); grtpar(6) = real(1E-3, c_double)
+        endif
+        grtpar(3) = real(1E-3, c_double); grtpar(4) = real(5E-3, c_double)
+        rc = mct_set_grt(1_c_int, c_loc(grtpar))
+        if (rc /= 0) call fail('mct_set_grt', rc)
         inval = 0
         if (var == 0) then
             rc = mct_surf_dispersion(c_loc(model%vp), c_loc(model%vs), c_loc(model%rho), g, ix0, ix1, iy0, iy1, &
@@ -382,10 +406,9 @@ contains
         endif
         invalid = (inval /= 0)
         if (rc < 0 .or. rc == 1) call fail('mct_surf_dispersion', rc)
-        ! rc = 2 (MCT_E_GRT_NEEDED): columns with a low-velocity layer carry ierr = 2 and the preset velocities: the
-        ! reference solves them with its generalized R/T branch (surfmodes.f90:84-87,96-99), so they are handed to the
-        ! Fortran surfmodes here, column by column (unreachable from the sampler, where check_model has already
-        ! rejected such models; `program modelling` has no check_model and can get here).
+        ! rc = 2 (MCT_E_GRT_NEEDED) can only remain for a column the device branch does not cover (a multi-mode call:
+        ! surfmmodes prints "not supported yet" there, surfmodes.f90:153,165; more than one fluid layer): such columns
+        ! carry ierr = 2 and the preset velocities and are handed to the Fortran surfmodes here, column by column.
         ! rc = 3 / 5 (more than 200 layers / a fluid layer below the top): the reference overruns its arrays or `stop`s
         ! (surfmodes.f90:342-345); raise instead of carrying bogus velocities into fm2d.
         if (rc == 3 .or. rc == 5) call fail('mct_surf_dispersion', rc)

@@ -124,3 +124,57 @@ def test_grt_on_model_columns_as_program_modelling_calls_it(mct):
                 assert ie[i, j] == ierr and np.array_equal(pv[i, j], p), (i, j)
             else:
                 assert ie[i, j] == io[i, j] and np.array_equal(pv[i, j], po[i, j])
+
+
+def test_grt_more_columns_than_one_scratch_chunk(mct):
+    """1500 low-velocity columns (the kernel's scratch holds 1024 at a time): three distinct stacks repeated; every copy
+    must equal the oracle's answer for its stack."""
+    base = [MODELS[k] for k in sorted(MODELS)]
+    cols = [base[c % 3] for c in range(1500)]
+    (th, vp, vs_, rho), offs = _batch(cols)
+    opts = disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    fr = FREQS[:4]
+    mct.set_grt(True, orc.GRT_PAR_LIKELIHOOD)
+    try:
+        ph, gr, ie, rc = mct.surfmodes_batch(th, vp, vs_, rho, offs, fr, opts)
+        st = mct.grt_stats()
+    finally:
+        mct.set_grt(False)
+    assert rc == 0 and st["columns"] == 1500
+    want = [orc.grt_modes(*b, fr, modetype=1, phaseGroup=0, dc=opts.dphase, par=orc.GRT_PAR_LIKELIHOOD, math_mode=orc.PORTABLE) for b in base]
+    for c in range(1500):
+        assert ie[c] == want[c % 3][0] and np.array_equal(ph[c], want[c % 3][1]), c
+
+
+@pytest.mark.parametrize("raylov", [1, 0])
+def test_grt_model_columns_under_water_phase_and_group(mct, raylov):
+    """waterDepth > 0: the device layers the column with the water layer on top (Rayleigh: the Stoneley search; Love: the
+    fluid is skipped by index), phase + group, the modelling variant's constants."""
+    grid = synth.make_grid(4, 4, 30, waterDepth=0.8)
+    pts, par = synth.generate_model(grid, 30, 3)
+    vp, vs, rho, sid = [np.zeros(grid.shape) for _ in range(3)] + [np.zeros(grid.shape, np.int32)]
+    orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
+    for (i, j, k0) in [(0, 0, 8), (2, 1, 12), (3, 3, 15)]:
+        vs[i, j, k0:k0 + 5] = vs[i, j, 0] * 0.8
+    vp[:] = 1.73 * vs
+    rho[:] = 1.74 * vp ** 0.25
+    freqs = FREQS[:6]
+    eps5, pre = float(np.float32(1e-5)), 1000.0
+    opts = disp_opts(raylov=raylov, phaseGroup=1, nmodes=0, variant="modelling")
+    win = (1, grid.nx, 1, grid.ny)
+    mct.set_grt(True, orc.GRT_PAR_MODELLING)
+    try:
+        pv, gv, ie, inval, rc = mct.surf_dispersion(vp, vs, rho, grid, win, freqs, opts, check=False)
+    finally:
+        mct.set_grt(False)
+    nlvl = 0
+    for i in range(grid.nx):
+        for j in range(grid.ny):
+            n, (th, a, b, r) = orc.convert_column(vp[i, j], vs[i, j], rho[i, j], grid.dz, waterDepth=grid.waterDepth, layer_eps=eps5, water_thresh=0.0)
+            if orc.L().orc_nlvls1(orc.f64(a).ctypes.data, orc.f64(b).ctypes.data, n, raylov) == 0:
+                continue
+            nlvl += 1
+            ierr, p, g, _ = orc.grt_modes(th, a, b, r, freqs, modetype=raylov, phaseGroup=1, dc=opts.dphase, par=orc.GRT_PAR_MODELLING,
+                                          math_mode=orc.PORTABLE, preset=pre)
+            assert ie[i, j] == ierr and np.array_equal(pv[i, j], p) and np.array_equal(gv[i, j], g), (i, j, ierr)
+    assert nlvl >= 3
