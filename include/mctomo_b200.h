@@ -297,6 +297,39 @@ int mct_accumulate_stats_dev(const double* d_vs, const double* d_vp, double* d_a
  * two at a time and written with 16-byte stores; kdtree2's traversal is replayed only for (near-)tied nodes.  mode 2:
  * the round-1 shape (a warp per column, every node scans its column's survivors).  mode 1: kdtree2's traversal for
  * every node.  Results are identical in all three. */
+/* ---- 2-D fast-marching travel times ----------------------------------------------------------------
+ * Replaces `modrays` as surf_likelihood calls it for phase-velocity data (src/likelihood_surf.F90:295-336 with uar = 1:
+ * travel times at the receivers, no ray geometry): gridder, bsplrefine, the source loop with source-grid refinement,
+ * srtimes (fm2d/fm2dray_cartesian.f90:67-478,490-668,676-770) and travel / fouds1 / fouds2 / the narrow-band heap
+ * (fm2d/fm2d_ttime.f90).  All np periods x nsrc sources are independent problems and go out in ONE launch.
+ * Options mirror settings%gridx, gridy, sgref, sgdic, sgext, order, band (likelihood_surf.F90:247-253). */
+typedef struct {
+  int32_t gridx, gridy; /* dicing of the propagation grid */
+  int32_t sgref;        /* source-grid refinement on (1) / off (0) */
+  int32_t sgdic, sgext; /* its dicing level and extent */
+  int32_t order;        /* 0 first-order, 1 mixed-order stencils */
+  double band;          /* narrow band size as a fraction of nx*ny */
+} mct_fm2d_opts;
+/* Host form.  src/rcv coordinates: x along the FIRST grid axis (grid%x), z along the second (grid%y).
+ *   srs  (nrc, nsrc, nmaps) int32: 1 where the pair carries data (dat%raystat(:,1,period));
+ *   vel  (nvz+2, nvx+2, nmaps): like%vel(period,:,:) with its replicated edge, one period after the other;
+ *   ttime (nrc, nsrc, nmaps) in/out: entries without data are left untouched (like%phaseTime);
+ *   field optional (nnz, nnx, nsrc, nmaps): the travel-time field of every problem (like%field4d), or NULL.
+ * nvx = grid%nx, nvz = grid%ny, gox/goz = xmin/ymin, dvx/dvz = dx/dy. */
+int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc,
+                   const int32_t* srs, const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz,
+                   const mct_fm2d_opts* o, double* ttime, double* field);
+/* Device form, asynchronous on `stream`.  d_src_xz = [x(nsrc) | z(nsrc)], d_rcv_xz = [x(nrc) | z(nrc)].  The velocity
+ * maps are addressed as d_vel[m*vel_map_stride + (b*(nvz+2) + a)*vel_elem_stride], so the padded map that
+ * mct_assemble_vel_dev builds -- the Fortran's like%vel(np, ny+2, nx+2) -- is consumed in place with
+ * (vel_elem_stride, vel_map_stride) = (np, 1); srs_map_stride = nrc*nsrc, or 2*nrc*nsrc for dat%raystat(nrev*nsrc, 2, np).
+ * d_err int32[nmaps*nsrc]: 0, 1 source outside the model, 2 narrow band overflow, 3 receiver outside the model. */
+int mct_fm2d_times_dev(const double* d_src_xz, int nsrc, const double* d_rcv_xz, int nrc, const int32_t* d_srs, long long srs_map_stride,
+                       const double* d_vel, long long vel_elem_stride, long long vel_map_stride, int nmaps, int nvx, int nvz, double gox,
+                       double goz, double dvx, double dvz, const mct_fm2d_opts* o, double* d_ttime, int32_t* d_err, void* stream);
+/* out2 = {nodes accepted, stencil updates} since mct_reset_stats, as the reference's own loops count them */
+int mct_fm2d_stats(int64_t out2[2]);
+
 int mct_set_k1_mode(int mode);
 
 /* ---- low-velocity columns: the generalized reflection/transmission branch of surfmodes ------------------------------

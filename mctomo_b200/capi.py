@@ -446,6 +446,45 @@ def fp64_peak_probe() -> dict:
     return {"dfma_tflops": a.value, "dmul_dadd_tflops": b.value}
 
 
+class mct_fm2d_opts(C.Structure):
+    _fields_ = [("gridx", C.c_int32), ("gridy", C.c_int32), ("sgref", C.c_int32), ("sgdic", C.c_int32), ("sgext", C.c_int32),
+                ("order", C.c_int32), ("band", C.c_double)]
+
+
+def fm2d_opts(gridx=1, gridy=1, sgref=1, sgdic=4, sgext=8, order=1, band=0.5) -> mct_fm2d_opts:
+    """examples/example1/MCTomo.inp:61-72 by default."""
+    return mct_fm2d_opts(gridx, gridy, sgref, sgdic, sgext, order, band)
+
+
+def fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, opts: mct_fm2d_opts, ttime=None, want_field=False):
+    """modrays for phase-velocity data (travel times only): src (nsrc,2), rcv (nrc,2) as (x, z); srs (nmaps, nsrc, nrc) 0/1;
+    vel (nmaps, nvx+2, nvz+2) C-order = the Fortran (nvz+2, nvx+2, nmaps).  Returns (ttime (nmaps, nsrc, nrc), field or None)."""
+    L = lib()
+    vp = C.c_void_p
+    L.mct_fm2d_times.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4 + \
+                                [C.POINTER(mct_fm2d_opts), vp, vp]
+    src, rcv, vel = _f64(src), _f64(rcv), _f64(vel)
+    nmaps, nsrc, nrc = vel.shape[0], len(src), len(rcv)
+    nvx, nvz = vel.shape[1] - 2, vel.shape[2] - 2
+    sx, sz = _f64(src[:, 0].copy()), _f64(src[:, 1].copy())
+    rx, rz = _f64(rcv[:, 0].copy()), _f64(rcv[:, 1].copy())
+    srs = np.ascontiguousarray(np.broadcast_to(srs, (nmaps, nsrc, nrc)), dtype=np.int32)
+    tt = np.full((nmaps, nsrc, nrc), -1.0) if ttime is None else np.ascontiguousarray(ttime, dtype=np.float64)
+    nnx, nnz = (nvx - 1) * opts.gridx + 1, (nvz - 1) * opts.gridy + 1
+    field = np.zeros((nmaps, nsrc, nnx, nnz)) if want_field else None
+    _check(L.mct_fm2d_times(sx.ctypes.data, sz.ctypes.data, nsrc, rx.ctypes.data, rz.ctypes.data, nrc, srs.ctypes.data, vel.ctypes.data,
+                            nmaps, nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), tt.ctypes.data, field.ctypes.data if want_field else None))
+    return tt, field
+
+
+def fm2d_stats():
+    L = lib()
+    L.mct_fm2d_stats.argtypes = [C.c_void_p]
+    out = np.zeros(2, np.int64)
+    _check(L.mct_fm2d_stats(out.ctypes.data))
+    return {"accepted": int(out[0]), "updates": int(out[1])}
+
+
 def set_grt(enable: bool, par6=None):
     """Solve low-velocity columns with the generalized R/T kernel (surfmodes.f90:84-87,96-99) instead of reporting ierr = 2."""
     L = lib()

@@ -1,0 +1,636 @@
+// k6_fm2d.cuh -- SURVEY 8(f)2: the reference's 2-D fast-marching eikonal solver for phase-velocity data on the device:
+// `modrays` as surf_likelihood drives it (src/likelihood_surf.F90:295-336, uar = 1: travel times at the receivers, no ray
+// geometry): gridder, bsplrefine, the source loop with source-grid refinement (fm2d/fm2dray_cartesian.f90:67-478,490-668),
+// srtimes (:676-770), travel / fouds1 / fouds2 / addtree / downtree / updtree / bilinear (fm2d/fm2d_ttime.f90).
+//
+// The unit of parallelism is the reference's own: every (period, source) pair is an independent eikonal problem
+// (the Fortran loops over sources inside an OpenMP loop over periods).  One warp per problem.  Fast marching accepts
+// nodes strictly in the order of a binary heap, and the reference's travel times depend on that order (which neighbours
+// are alive when a node is updated), so the march itself is kept exactly as the Fortran runs it -- same heap, same
+// stencils, same operation order -- on lane 0; what is data-parallel inside a problem (B-spline velocities of the
+// propagation grid and of the refined source grid, the narrow-band completion sweep, the receiver interpolation) is
+// spread over the lanes.  Results are bit-identical to oracle/fm2d_ref.c.  Throughput comes from the number of problems
+// in flight (np x nsrc: 88 in example1, thousands in the multi-mode configurations), not from one problem's latency.
+#pragma once
+
+struct FmParams {
+  int nmaps, nsrc, nrc;
+  const double *scx, *scz, *rcx, *rcz;
+  const int32_t* srs;        // (nrc, nsrc, nmaps): raystat(:,1,period) as the Fortran holds it
+  int nvx, nvz;
+  double gox, goz, dvx, dvz;
+  const double* velv;        // like%vel with its replicated edge: element (a, b) of map m at velv[m*vel_ms + (b*(nvz+2) + a)*vel_es]
+  long long vel_es, vel_ms;  // (1, (nvz+2)*(nvx+2)) for maps stored one after the other; (nmaps, 1) for the Fortran's like%vel(np, ny+2, nx+2)
+  long long srs_ms;          // map stride of srs: nrc*nsrc, or 2*nrc*nsrc for dat%raystat(nrev*nsrc, 2, np)
+  int gdx, gdz, asgr, sgdl, sgs, fom;
+  double snb;
+  int nnx, nnz, ldr;         // propagation grid; leading dimension of the refined arrays
+  double* veln;              // (nnz, nnx, nmaps): gridder's output (fm2d_gridder_kernel)
+  char* scratch; size_t scratch_per_problem;
+  double* ttime;             // (nrc, nsrc, nmaps); entries without data untouched
+  double* field;             // optional (nnz, nnx, nsrc, nmaps): ttn of every problem
+  int32_t* err;              // per problem: 0, 1 source outside, 2 narrow band overflow, 3 receiver outside
+  unsigned long long* counters; // [0] nodes accepted, [1] stencil updates
+};
+
+__device__ __forceinline__ void fm_bspl(double u, double w[5]) {
+  const double um = 1.0 - u;
+  w[1] = ((um * um) * um) / 6.0;
+  w[2] = (4.0 - 6.0 * (u * u) + 3.0 * ((u * u) * u)) / 6.0;
+  w[3] = (1.0 + 3.0 * u + 3.0 * (u * u) - 3.0 * ((u * u) * u)) / 6.0;
+  w[4] = ((u * u) * u) / 6.0;
+}
+
+// gridder (fm2dray_cartesian.f90:490-590): one thread per propagation node, the Fortran's (i,j,l,m) recovered from it
+__global__ void fm2d_gridder_kernel(const __grid_constant__ FmParams P) {
+  const long long total = (long long)P.nnx * P.nnz * P.nmaps;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int map = (int)(t / ((long long)P.nnx * P.nnz));
+    const int r = (int)(t - (long long)map * P.nnx * P.nnz);
+    const int stx = r / P.nnz + 1, stz = r % P.nnz + 1;
+    int i = (stz - 1) / P.gdz + 1; if (i > P.nvz - 1) i = P.nvz - 1;
+    int j = (stx - 1) / P.gdx + 1; if (j > P.nvx - 1) j = P.nvx - 1;
+    const int l = stz - P.gdz * (i - 1), m = stx - P.gdx * (j - 1);
+    double ui[5], vi[5], u;
+    u = P.gdx; u = (m - 1) / u; fm_bspl(u, ui);
+    u = P.gdz; u = (l - 1) / u; fm_bspl(u, vi);
+    const double* velv = P.velv + (size_t)map * P.vel_ms;
+    double sumi = 0.0;
+    for (int i1 = 1; i1 <= 4; ++i1) {
+      double sumj = 0.0;
+      for (int j1 = 1; j1 <= 4; ++j1) sumj = sumj + ui[j1] * velv[((size_t)(j - 2 + j1) * (P.nvz + 2) + (i - 2 + i1)) * P.vel_es];
+      sumi = sumi + vi[i1] * sumj;
+    }
+    P.veln[(size_t)map * P.nnx * P.nnz + (size_t)(stx - 1) * P.nnz + (stz - 1)] = sumi;
+  }
+}
+
+// one marching grid: arrays with leading dimension ld (rows = z), 1-based accessors
+struct FmGrid {
+  int nnx, nnz, ld;
+  double gox, goz, dnx, dnz;
+  const double* veln;
+  double* ttn;
+  int32_t* nsts;
+  int32_t* heap; // packed (pz << 16) | px, 1-based
+  int ntr, maxbt, fom;
+  int vnl, vnr, vnt, vnb;
+  int error;
+  unsigned n_accept, n_update;
+};
+#define FVELN(G, k, j) (G).veln[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
+#define FTTN(G, k, j) (G).ttn[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
+#define FNSTS(G, k, j) (G).nsts[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
+#define HPX(h) ((h) & 0xffff)
+#define HPZ(h) ((h) >> 16)
+
+__device__ __forceinline__ double fm_heap_t(const FmGrid& G, int pos) { const int h = G.heap[pos]; return FTTN(G, HPZ(h), HPX(h)); }
+__device__ void fm_sift_up(FmGrid& G, int iz, int ix, int tpc) {
+  const double t = FTTN(G, iz, ix);
+  int tpp = tpc / 2;
+  while (tpp > 0) {
+    const int hp = G.heap[tpp];
+    if (t < FTTN(G, HPZ(hp), HPX(hp))) {
+      FNSTS(G, iz, ix) = tpp;
+      FNSTS(G, HPZ(hp), HPX(hp)) = tpc;
+      const int ex = G.heap[tpc];
+      G.heap[tpc] = hp;
+      G.heap[tpp] = ex;
+      tpc = tpp;
+      tpp = tpc / 2;
+    } else tpp = 0;
+  }
+}
+__device__ __forceinline__ void fm_addtree(FmGrid& G, int iz, int ix) {
+  if (G.ntr + 1 > G.maxbt) { G.error = 2; return; }
+  G.ntr++;
+  FNSTS(G, iz, ix) = G.ntr;
+  G.heap[G.ntr] = (iz << 16) | ix;
+  fm_sift_up(G, iz, ix, G.ntr);
+}
+__device__ __forceinline__ void fm_swap(FmGrid& G, int tpp, int tpc) {
+  const int hp = G.heap[tpp], hc = G.heap[tpc];
+  FNSTS(G, HPZ(hp), HPX(hp)) = tpc;
+  FNSTS(G, HPZ(hc), HPX(hc)) = tpp;
+  G.heap[tpc] = hp;
+  G.heap[tpp] = hc;
+}
+__device__ void fm_downtree(FmGrid& G) {
+  if (G.ntr == 1) { G.ntr--; return; }
+  const int hl = G.heap[G.ntr];
+  FNSTS(G, HPZ(hl), HPX(hl)) = 1;
+  G.heap[1] = hl;
+  G.ntr--;
+  int tpp = 1, tpc = 2;
+  while (tpc < G.ntr) {
+    double rd1 = fm_heap_t(G, tpc), rd2 = fm_heap_t(G, tpc + 1);
+    if (rd1 > rd2) tpc = tpc + 1;
+    rd1 = fm_heap_t(G, tpc);
+    rd2 = fm_heap_t(G, tpp);
+    if (rd1 < rd2) { fm_swap(G, tpp, tpc); tpp = tpc; tpc = 2 * tpp; }
+    else tpc = G.ntr + 1;
+  }
+  if (tpc == G.ntr) {
+    const double rd1 = fm_heap_t(G, tpc), rd2 = fm_heap_t(G, tpp);
+    if (rd1 < rd2) fm_swap(G, tpp, tpc);
+  }
+}
+__device__ __forceinline__ double fm_qsolve(double a, double b, double c) {
+  double rd1 = b * b - 4.0 * a * c;
+  if (rd1 < 0.0) rd1 = 0.0;
+  return (-b + sqrt(rd1)) / (2.0 * a);
+}
+// fouds1 (fm2d_ttime.f90:138-197)
+__device__ void fm_fouds1(FmGrid& G, int iz, int ix) {
+  int tsw1 = 0;
+  double travm = 0;
+  const double slown = 1.0 / FVELN(G, iz, ix), dnx = G.dnx, dnz = G.dnz;
+  G.n_update++;
+  for (int j = ix - 1; j <= ix + 1; j += 2)
+    for (int k = iz - 1; k <= iz + 1; k += 2) {
+      if (j < 1 || j > G.nnx || k < 1 || k > G.nnz) continue;
+      int swsol = 0;
+      double a = 0, b = 0, c = 0, tref = 0;
+      if (FNSTS(G, iz, j) == 0) {
+        swsol = 1;
+        if (FNSTS(G, k, ix) == 0) {
+          const double u = dnx, v = dnz, em = FTTN(G, k, ix) - FTTN(G, iz, j);
+          a = u * u + v * v;
+          b = -2.0 * (u * u) * em;
+          c = (u * u) * (em * em - (v * v) * (slown * slown));
+          tref = FTTN(G, iz, j);
+        } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = FTTN(G, iz, j); }
+      } else if (FNSTS(G, k, ix) == 0) {
+        swsol = 1;
+        const double sd = slown * dnz;
+        a = 1.0; b = 0.0; c = -(sd * sd); tref = FTTN(G, k, ix);
+      }
+      if (swsol) {
+        const double trav = tref + fm_qsolve(a, b, c);
+        if (tsw1) travm = trav < travm ? trav : travm; else { travm = trav; tsw1 = 1; }
+      }
+    }
+  FTTN(G, iz, ix) = travm;
+}
+// fouds2 (fm2d_ttime.f90:199-345)
+__device__ void fm_fouds2(FmGrid& G, int iz, int ix) {
+  int tsw1 = 0;
+  double travm = 0;
+  const double slown = 1.0 / FVELN(G, iz, ix), dnx = G.dnx, dnz = G.dnz;
+  G.n_update++;
+  for (int j = ix - 1; j <= ix + 1; j += 2) {
+    if (j < 1 || j > G.nnx) continue;
+    int swj = -1, j2;
+    if (j == ix - 1) { j2 = j - 1; if (j2 >= 1) { if (FNSTS(G, iz, j2) == 0) swj = 0; } }
+    else { j2 = j + 1; if (j2 <= G.nnx) { if (FNSTS(G, iz, j2) == 0) swj = 0; } }
+    const int sj = FNSTS(G, iz, j);
+    const double tj = FTTN(G, iz, j);
+    double tj2 = 0;
+    if (sj == 0 && swj == 0) { swj = -1; tj2 = FTTN(G, iz, j2); if (tj > tj2) swj = 0; }
+    else swj = -1;
+    for (int k = iz - 1; k <= iz + 1; k += 2) {
+      if (k < 1 || k > G.nnz) continue;
+      int swk = -1, k2;
+      if (k == iz - 1) { k2 = k - 1; if (k2 >= 1) { if (FNSTS(G, k2, ix) == 0) swk = 0; } }
+      else { k2 = k + 1; if (k2 <= G.nnz) { if (FNSTS(G, k2, ix) == 0) swk = 0; } }
+      const int sk = FNSTS(G, k, ix);
+      const double tk = FTTN(G, k, ix);
+      double tk2 = 0;
+      if (sk == 0 && swk == 0) { swk = -1; tk2 = FTTN(G, k2, ix); if (tk > tk2) swk = 0; }
+      else swk = -1;
+      int swsol = 0;
+      double a = 0, b = 0, c = 0, tref = 0, tdiv = 1.0, u, v, em;
+      if (swj == 0) {
+        swsol = 1;
+        if (swk == 0) {
+          u = 2.0 * dnx; v = 2.0 * dnz;
+          em = 4.0 * tj - tj2 - 4.0 * tk;
+          em = em + tk2;
+          a = v * v + u * u;
+          b = 2.0 * em * (u * u);
+          c = (u * u) * (em * em - (slown * slown) * (v * v));
+          tref = 4.0 * tj - tj2;
+          tdiv = 3.0;
+        } else if (sk == 0) {
+          u = dnz; v = 2.0 * dnx;
+          em = 3.0 * tk - 4.0 * tj + tj2;
+          a = v * v + 9.0 * (u * u);
+          b = 6.0 * em * (u * u);
+          c = (u * u) * (em * em - (slown * slown) * (v * v));
+          tref = tk;
+          tdiv = 1.0;
+        } else {
+          u = 2.0 * dnx;
+          a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
+          tref = 4.0 * tj - tj2;
+          tdiv = 3.0;
+        }
+      } else if (sj == 0) {
+        swsol = 1;
+        if (swk == 0) {
+          u = dnx; v = 2.0 * dnz;
+          em = 3.0 * tj - 4.0 * tk + tk2;
+          a = v * v + 9.0 * (u * u);
+          b = 6.0 * em * (u * u);
+          c = (u * u) * (em * em - (v * v) * (slown * slown));
+          tref = tj;
+          tdiv = 1.0;
+        } else if (sk == 0) {
+          u = dnx; v = dnz;
+          em = tk - tj;
+          a = u * u + v * v;
+          b = -2.0 * (u * u) * em;
+          c = (u * u) * (em * em - (v * v) * (slown * slown));
+          tref = tj;
+          tdiv = 1.0;
+        } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; tdiv = 1.0; }
+      } else {
+        if (swk == 0) {
+          swsol = 1;
+          u = 2.0 * dnz;
+          a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
+          tref = 4.0 * tk - tk2;
+          tdiv = 3.0;
+        } else if (sk == 0) {
+          swsol = 1;
+          a = 1.0; b = 0.0; c = -(slown * slown) * (dnz * dnz);
+          tref = tk;
+          tdiv = 1.0;
+        }
+      }
+      if (swsol) {
+        const double trav = (tref + fm_qsolve(a, b, c)) / tdiv;
+        if (tsw1) travm = trav < travm ? trav : travm; else { travm = trav; tsw1 = 1; }
+      }
+    }
+  }
+  FTTN(G, iz, ix) = travm;
+}
+__device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3][3], double dsx, double dsz) {
+  double biv = 0.0;
+  for (int i = 1; i <= 2; ++i)
+    for (int j = 1; j <= 2; ++j) {
+      const double produ = (1.0 - fabs(((i - 1) * G.dnx - dsx) / G.dnx)) * (1.0 - fabs(((j - 1) * G.dnz - dsz) / G.dnz));
+      biv = biv + nv[i][j] * produ;
+    }
+  return biv;
+}
+__device__ __forceinline__ void fm_update(FmGrid& G, int iz, int ix) {
+  const int s = FNSTS(G, iz, ix);
+  if (s == -1) {
+    if (G.fom == 0) fm_fouds1(G, iz, ix); else fm_fouds2(G, iz, ix);
+    fm_addtree(G, iz, ix);
+  } else if (s > 0) {
+    if (G.fom == 0) fm_fouds1(G, iz, ix); else fm_fouds2(G, iz, ix);
+    fm_sift_up(G, iz, ix, FNSTS(G, iz, ix));
+  }
+}
+// travel (fm2d_ttime.f90:27-136); lane 0 only.  urg 0/1: nsts must already be -1 everywhere (the caller's lanes fill it)
+__device__ void fm_travel(FmGrid& G, double scx, double scz, int urg) {
+  int isx = (int)((scx - G.gox) / G.dnx) + 1;
+  int isz = (int)((scz - G.goz) / G.dnz) + 1;
+  if (isx < 1 || isx > G.nnx || isz < 1 || isz > G.nnz) { G.error = 1; return; }
+  if (isx == G.nnx) isx--;
+  if (isz == G.nnz) isz--;
+  G.ntr = 0;
+  if (urg == 2) {
+    for (int i = 1; i <= G.nnx; ++i)
+      for (int j = 1; j <= G.nnz; ++j)
+        if (FNSTS(G, j, i) > 0) fm_addtree(G, j, i);
+  } else {
+    double vss[3][3];
+    for (int i = 1; i <= 2; ++i) for (int j = 1; j <= 2; ++j) vss[i][j] = FVELN(G, isz - 1 + j, isx - 1 + i);
+    const double dsx = (scx - G.gox) - (isx - 1) * G.dnx;
+    const double dsz = (scz - G.goz) - (isz - 1) * G.dnz;
+    const double vsrc = fm_bilinear(G, vss, dsx, dsz);
+    for (int i = 1; i <= 2; ++i)
+      for (int j = 1; j <= 2; ++j) {
+        const double ex = dsx - (i - 1) * G.dnx, ez = dsz - (j - 1) * G.dnz;
+        const double ds = sqrt(ex * ex + ez * ez);
+        FTTN(G, isz - 1 + j, isx - 1 + i) = 2.0 * ds / (vss[i][j] + vsrc);
+        fm_addtree(G, isz - 1 + j, isx - 1 + i);
+      }
+  }
+  while (G.ntr > 0 && !G.error) {
+    const int h = G.heap[1];
+    const int ix = HPX(h), iz = HPZ(h);
+    if (urg == 1) {
+      int swrg = 0;
+      if (ix == 1 && G.vnl != 1) swrg = 1;
+      if (ix == G.nnx && G.vnr != G.nnx) swrg = 1; // (refined extent against a coarse index, as the Fortran has it)
+      if (iz == 1 && G.vnt != 1) swrg = 1;
+      if (iz == G.nnz && G.vnb != G.nnz) swrg = 1;
+      if (swrg) { FNSTS(G, iz, ix) = 0; break; }
+    }
+    FNSTS(G, iz, ix) = 0;
+    G.n_accept++;
+    fm_downtree(G);
+    for (int i = ix - 1; i <= ix + 1; i += 2) if (i >= 1 && i <= G.nnx) fm_update(G, iz, i);
+    for (int i = iz - 1; i <= iz + 1; i += 2) if (i >= 1 && i <= G.nnz) fm_update(G, i, ix);
+  }
+}
+
+__global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmParams P) {
+  const int lane = threadIdx.x;
+  const int prob = blockIdx.x;
+  const int map = prob / P.nsrc, isrc = prob - map * P.nsrc; // 0-based
+  const int32_t* srs = P.srs + (size_t)map * P.srs_ms + (size_t)isrc * P.nrc;
+  int any = 0;
+  for (int r = lane; r < P.nrc; r += 32) any += srs[r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) any += __shfl_xor_sync(0xffffffffu, any, o);
+  if (lane == 0) P.err[prob] = 0;
+  if (any == 0 && isrc != 0) return; // no valid rays for this source (unless it is the first): cycle
+  const double x = P.scx[isrc], z = P.scz[isrc];
+  const double dnx0 = P.dvx / P.gdx, dnz0 = P.dvz / P.gdz;
+  // scratch: coarse ttn | coarse nsts | refined veln | refined ttn | refined nsts | heap
+  const size_t cc = (size_t)P.nnx * P.nnz, cr = (size_t)P.ldr * P.ldr;
+  char* base = P.scratch + (size_t)prob * P.scratch_per_problem;
+  double* ttn_c = (double*)base;
+  double* veln_r = ttn_c + cc;
+  double* ttn_r = veln_r + cr;
+  int32_t* nsts_c = (int32_t*)(ttn_r + cr);
+  int32_t* nsts_r = nsts_c + cc;
+  int32_t* heap = nsts_r + cr;
+  __shared__ FmGrid G;
+  __shared__ int s_err;
+  int isx = (int)((x - P.gox) / dnx0) + 1, isz = (int)((z - P.goz) / dnz0) + 1;
+  if (isx < 1 || isx > P.nnx || isz < 1 || isz > P.nnz) { if (lane == 0) P.err[prob] = 1; return; }
+  if (isx == P.nnx) isx--;
+  if (isz == P.nnz) isz--;
+  int vnl = isx - P.sgs; if (vnl < 1) vnl = 1;
+  int vnr = isx + P.sgs; if (vnr > P.nnx) vnr = P.nnx;
+  int vnt = isz - P.sgs; if (vnt < 1) vnt = 1;
+  int vnb = isz + P.sgs; if (vnb > P.nnz) vnb = P.nnz;
+  const double* veln_c = P.veln + (size_t)map * cc;
+  const int maxbt0 = (int)floor(P.snb * P.nnx * P.nnz + 0.5); // NINT of a positive value
+  unsigned nacc = 0, nupd = 0;
+  if (P.asgr == 1) {
+    const int nrnx = (vnr - vnl) * P.sgdl + 1, nrnz = (vnb - vnt) * P.sgdl + 1;
+    const double drnx = P.dvx / (double)(float)(P.gdx * P.sgdl), drnz = P.dvz / (double)(float)(P.gdz * P.sgdl);
+    const double gorx = P.gox + dnx0 * (vnl - 1), gorz = P.goz + dnz0 * (vnt - 1);
+    // bsplrefine (fm2dray_cartesian.f90:598-668): every refined node, the Fortran's (i,j,k,l) recovered from it
+    const int nrxr = P.gdx * P.sgdl, nrzr = P.gdz * P.sgdl;
+    const int origx = (vnl - 1) * P.sgdl + 1, origz = (vnt - 1) * P.sgdl + 1;
+    const double* velv = P.velv + (size_t)map * P.vel_ms;
+    for (int t = lane; t < nrnx * nrnz; t += 32) {
+      const int idm2 = t / nrnz + 1, idm1 = t % nrnz + 1;
+      const int st1 = idm1 + origz - 1, st2 = idm2 + origx - 1;
+      int i = (st1 - 1) / nrzr + 1; if (i > P.nvz - 1) i = P.nvz - 1;
+      int j = (st2 - 1) / nrxr + 1; if (j > P.nvx - 1) j = P.nvx - 1;
+      const int k = st1 - nrzr * (i - 1), l = st2 - nrxr * (j - 1);
+      double ui[5], vi[5], u;
+      u = nrxr; u = (l - 1) / u; fm_bspl(u, ui);
+      u = nrzr; u = (k - 1) / u; fm_bspl(u, vi);
+      double sum[5];
+      for (int i1 = 1; i1 <= 4; ++i1) {
+        sum[i1] = 0.0;
+        for (int j1 = 1; j1 <= 4; ++j1) sum[i1] = sum[i1] + ui[j1] * velv[((size_t)(j - 2 + j1) * (P.nvz + 2) + (i - 2 + i1)) * P.vel_es];
+        sum[i1] = vi[i1] * sum[i1];
+      }
+      veln_r[(size_t)(idm2 - 1) * P.ldr + (idm1 - 1)] = sum[1] + sum[2] + sum[3] + sum[4];
+    }
+    for (size_t q = lane; q < cr; q += 32) nsts_r[q] = -1;
+    __syncwarp();
+    if (lane == 0) {
+      G.nnx = nrnx; G.nnz = nrnz; G.ld = P.ldr; G.gox = gorx; G.goz = gorz; G.dnx = drnx; G.dnz = drnz;
+      G.veln = veln_r; G.ttn = ttn_r; G.nsts = nsts_r; G.heap = heap; G.fom = P.fom;
+      G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
+      int mb = maxbt0;
+      if (nrnx > P.nnx || nrnz > P.nnz) { const int a = nrnx > P.nnx ? nrnx : P.nnx, b = nrnz > P.nnz ? nrnz : P.nnz; mb = (int)floor(P.snb * a * b + 0.5); }
+      G.maxbt = mb;
+      fm_travel(G, x, z, 1);
+      s_err = G.error;
+      nacc = G.n_accept; nupd = G.n_update;
+    }
+    __syncwarp();
+    if (s_err) { if (lane == 0) P.err[prob] = s_err; return; }
+    // map the refined grid onto the coarse one (:341-372), then complete the narrow band (:398-417)
+    for (size_t q = lane; q < cc; q += 32) nsts_c[q] = -1;
+    __syncwarp();
+    const int nk = (nrnz - 1) / P.sgdl + 1, nl = (nrnx - 1) / P.sgdl + 1;
+    for (int t = lane; t < nk * nl; t += 32) {
+      const int kk = t % nk, ll = t / nk;
+      const int k = 1 + kk * P.sgdl, l = 1 + ll * P.sgdl;
+      const int idm1 = vnt + kk, idm2 = vnl + ll;
+      const int s = nsts_r[(size_t)(l - 1) * P.ldr + (k - 1)];
+      nsts_c[(size_t)(idm2 - 1) * P.nnz + (idm1 - 1)] = s;
+      if (s >= 0) ttn_c[(size_t)(idm2 - 1) * P.nnz + (idm1 - 1)] = ttn_r[(size_t)(l - 1) * P.ldr + (k - 1)];
+    }
+    __syncwarp();
+    // alive nodes with a far neighbour become close: decided on the mapped state (a node set to 1 is neither 0 nor -1, so the
+    // Fortran's in-place sweep sees the same neighbours); only the mapped window can hold alive nodes
+    for (int t = lane; t < nk * nl; t += 32) {
+      const int l = vnt + t % nk, k = vnl + t / nk; // l: z index, k: x index (the Fortran's names)
+      if (nsts_c[(size_t)(k - 1) * P.nnz + (l - 1)] == 0) {
+        bool far = false;
+        if (l - 1 >= 1 && nsts_c[(size_t)(k - 1) * P.nnz + (l - 2)] == -1) far = true;
+        if (l + 1 <= P.nnz && nsts_c[(size_t)(k - 1) * P.nnz + l] == -1) far = true;
+        if (k - 1 >= 1 && nsts_c[(size_t)(k - 2) * P.nnz + (l - 1)] == -1) far = true;
+        if (k + 1 <= P.nnx && nsts_c[(size_t)k * P.nnz + (l - 1)] == -1) far = true;
+        heap[1 + t] = far ? 1 : 0; // staged in the (idle) heap array: applied after every lane has looked
+      } else heap[1 + t] = 0;
+    }
+    __syncwarp();
+    for (int t = lane; t < nk * nl; t += 32) {
+      const int l = vnt + t % nk, k = vnl + t / nk;
+      if (heap[1 + t]) nsts_c[(size_t)(k - 1) * P.nnz + (l - 1)] = 1;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
+      G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.n_accept = 0; G.n_update = 0;
+      fm_travel(G, x, z, 2);
+      s_err = G.error;
+      nacc += G.n_accept; nupd += G.n_update;
+    }
+  } else {
+    for (size_t q = lane; q < cc; q += 32) nsts_c[q] = -1;
+    __syncwarp();
+    if (lane == 0) {
+      G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
+      G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.heap = heap; G.fom = P.fom; G.maxbt = maxbt0;
+      G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
+      fm_travel(G, x, z, 0);
+      s_err = G.error;
+      nacc = G.n_accept; nupd = G.n_update;
+    }
+  }
+  __syncwarp();
+  if (lane == 0 && P.counters) { atomicAdd(&P.counters[0], (unsigned long long)nacc); atomicAdd(&P.counters[1], (unsigned long long)nupd); }
+  if (s_err) { if (lane == 0) P.err[prob] = s_err; return; }
+  if (P.field) {
+    double* f = P.field + (size_t)prob * cc;
+    for (size_t q = lane; q < cc; q += 32) f[q] = ttn_c[q];
+  }
+  // srtimes (fm2dray_cartesian.f90:676-770): one receiver per lane
+  double* tt = P.ttime + ((size_t)map * P.nsrc + isrc) * P.nrc;
+  for (int r = lane; r < P.nrc; r += 32) {
+    if (srs[r] == 0) continue;
+    const double rx = P.rcx[r], rz = P.rcz[r];
+    int irx = (int)floor((rx - P.gox) / dnx0) + 1, irz = (int)floor((rz - P.goz) / dnz0) + 1;
+    if (irx < 1 || irx > P.nnx || irz < 1 || irz > P.nnz) { P.err[prob] = 3; continue; }
+    if (irx == P.nnx) irx--;
+    if (irz == P.nnz) irz--;
+    const int jsx = (int)floor((x - P.gox) / dnx0) + 1, jsz = (int)floor((z - P.goz) / dnz0) + 1;
+    double dpl = dnx0;
+    if (dnz0 < dpl) dpl = dnz0;
+    double sred = (x - rx) * (x - rx);
+    sred = sred + (z - rz) * (z - rz);
+    sred = sqrt(sred);
+    int sw = 0;
+    if (sred < dpl) sw = 1;
+    if (jsx == irx && jsz == irz) sw = 1;
+    double trr;
+    if (sw) {
+      FmGrid H; H.dnx = dnx0; H.dnz = dnz0;
+      double vss[3][3];
+      for (int k = 1; k <= 2; ++k) for (int l = 1; l <= 2; ++l) vss[k][l] = veln_c[(size_t)(jsx - 1 + k - 1) * P.nnz + (jsz - 1 + l - 1)];
+      double drx = (x - P.gox) - (jsx - 1) * dnx0, drz = (z - P.goz) - (jsz - 1) * dnz0;
+      const double vels = fm_bilinear(H, vss, drx, drz);
+      for (int k = 1; k <= 2; ++k) for (int l = 1; l <= 2; ++l) vss[k][l] = veln_c[(size_t)(irx - 1 + k - 1) * P.nnz + (irz - 1 + l - 1)];
+      drx = (rx - P.gox) - (irx - 1) * dnx0; drz = (rz - P.goz) - (irz - 1) * dnz0;
+      const double velr = fm_bilinear(H, vss, drx, drz);
+      trr = 2.0 * sred / (vels + velr);
+    } else {
+      const double drx = (rx - P.gox) - (irx - 1) * dnx0, drz = (rz - P.goz) - (irz - 1) * dnz0;
+      trr = 0.0;
+      for (int k = 1; k <= 2; ++k)
+        for (int l = 1; l <= 2; ++l) {
+          const double produ = (1.0 - fabs(((l - 1) * dnz0 - drz) / dnz0)) * (1.0 - fabs(((k - 1) * dnx0 - drx) / dnx0));
+          trr = trr + ttn_c[(size_t)(irx - 1 + k - 1) * P.nnz + (irz - 1 + l - 1)] * produ;
+        }
+    }
+    tt[r] = trr;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+namespace {
+DevBuf fm_veln, fm_scratch, fm_err, fm_geo, fm_srs, fm_vel, fm_tt;
+
+int fm2d_launch(FmParams& P, cudaStream_t st) {
+  int rc;
+  P.nnx = (P.nvx - 1) * P.gdx + 1; P.nnz = (P.nvz - 1) * P.gdz + 1;
+  if (P.nnx > 32767 || P.nnz > 32767) return fail(MCT_E_INVALID_ARG, "fm2d: propagation grid larger than 32767 nodes along an axis");
+  P.ldr = 2 * P.sgs * P.sgdl + 1;
+  const size_t cc = (size_t)P.nnx * P.nnz, cr = (size_t)P.ldr * P.ldr;
+  const int a = std::max(P.ldr, P.nnx), b = std::max(P.ldr, P.nnz);
+  const size_t maxbt = (size_t)std::max(floor(P.snb * P.nnx * P.nnz + 0.5), floor(P.snb * a * b + 0.5)) + 4;
+  size_t per = 8 * (cc + 2 * cr) + 4 * (cc + cr + maxbt);
+  per = (per + 15) & ~(size_t)15;
+  P.scratch_per_problem = per;
+  const int nprob = P.nmaps * P.nsrc;
+  if ((rc = ensure(fm_veln, 8 * cc * (size_t)P.nmaps))) return rc;
+  if ((rc = ensure(fm_scratch, per * (size_t)nprob))) return rc;
+  P.veln = (double*)fm_veln.p; P.scratch = (char*)fm_scratch.p;
+  P.counters = g.count_on ? (unsigned long long*)g.counters.p + 10 : nullptr;
+  ProfScope ps(2, st);
+  fm2d_gridder_kernel<<<grid_blocks((long long)cc * P.nmaps, 256, 8), 256, 0, st>>>(P);
+  fm2d_kernel<<<nprob, 32, 0, st>>>(P);
+  CK(cudaGetLastError());
+  g.host_stats.n_launches += 2;
+  return MCT_OK;
+}
+int fm2d_check(int nsrc, int nrc, int nmaps, int nvx, int nvz, double dvx, double dvz, const mct_fm2d_opts* o) {
+  if (!o || nsrc < 1 || nrc < 1 || nmaps < 1 || nvx < 2 || nvz < 2 || !(dvx > 0) || !(dvz > 0)) return fail(MCT_E_INVALID_ARG, "fm2d: bad sizes");
+  if (o->gridx < 1 || o->gridy < 1 || o->sgdic < 1 || o->sgext < 1 || (o->order != 0 && o->order != 1) || !(o->band > 0))
+    return fail(MCT_E_INVALID_ARG, "fm2d: bad options");
+  return MCT_OK;
+}
+void fm2d_fill(FmParams& P, int nsrc, int nrc, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz, const mct_fm2d_opts* o) {
+  memset(&P, 0, sizeof P);
+  P.nmaps = nmaps; P.nsrc = nsrc; P.nrc = nrc; P.nvx = nvx; P.nvz = nvz;
+  P.gox = gox; P.goz = goz; P.dvx = dvx; P.dvz = dvz;
+  P.gdx = o->gridx; P.gdz = o->gridy; P.asgr = o->sgref ? 1 : 0; P.sgdl = o->sgdic; P.sgs = o->sgext; P.fom = o->order; P.snb = o->band;
+}
+} // namespace
+
+extern "C" {
+
+int mct_fm2d_times_dev(const double* d_src_xz, int nsrc, const double* d_rcv_xz, int nrc, const int32_t* d_srs, long long srs_map_stride,
+                       const double* d_vel, long long vel_elem_stride, long long vel_map_stride, int nmaps, int nvx, int nvz, double gox,
+                       double goz, double dvx, double dvz, const mct_fm2d_opts* o, double* d_ttime, int32_t* d_err, void* stream) {
+  NEED_INIT();
+  int rc;
+  if ((rc = fm2d_check(nsrc, nrc, nmaps, nvx, nvz, dvx, dvz, o))) return rc;
+  if (!d_src_xz || !d_rcv_xz || !d_srs || !d_vel || !d_ttime || !d_err) return fail(MCT_E_INVALID_ARG, "fm2d: NULL pointer");
+  FmParams P;
+  fm2d_fill(P, nsrc, nrc, nmaps, nvx, nvz, gox, goz, dvx, dvz, o);
+  P.scx = d_src_xz; P.scz = d_src_xz + nsrc; P.rcx = d_rcv_xz; P.rcz = d_rcv_xz + nrc;
+  P.srs = d_srs; P.srs_ms = srs_map_stride;
+  P.velv = d_vel; P.vel_es = vel_elem_stride; P.vel_ms = vel_map_stride;
+  P.ttime = d_ttime; P.err = d_err;
+  return fm2d_launch(P, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc, const int32_t* srs,
+                   const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz, const mct_fm2d_opts* o,
+                   double* ttime, double* field) {
+  NEED_INIT();
+  int rc;
+  if ((rc = fm2d_check(nsrc, nrc, nmaps, nvx, nvz, dvx, dvz, o))) return rc;
+  if (!src_x || !src_z || !rcv_x || !rcv_z || !srs || !vel || !ttime) return fail(MCT_E_INVALID_ARG, "fm2d: NULL pointer");
+  cudaStream_t st = g.stream;
+  const size_t nv = (size_t)(nvz + 2) * (nvx + 2) * nmaps, nt = (size_t)nrc * nsrc * nmaps;
+  const int nprob = nmaps * nsrc;
+  if ((rc = ensure(fm_geo, 8 * (size_t)(2 * nsrc + 2 * nrc)))) return rc;
+  if ((rc = ensure(fm_srs, 4 * nt))) return rc;
+  if ((rc = ensure(fm_vel, 8 * nv))) return rc;
+  if ((rc = ensure(fm_tt, 8 * nt))) return rc;
+  if ((rc = ensure(fm_err, 4 * (size_t)nprob))) return rc;
+  double* geo = (double*)fm_geo.p;
+  CK(cudaMemcpyAsync(geo, src_x, 8 * (size_t)nsrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(geo + nsrc, src_z, 8 * (size_t)nsrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(geo + 2 * nsrc, rcv_x, 8 * (size_t)nrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(geo + 2 * nsrc + nrc, rcv_z, 8 * (size_t)nrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(fm_srs.p, srs, 4 * nt, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(fm_vel.p, vel, 8 * nv, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(fm_tt.p, ttime, 8 * nt, cudaMemcpyHostToDevice, st)); // entries without data keep the caller's values
+  FmParams P;
+  fm2d_fill(P, nsrc, nrc, nmaps, nvx, nvz, gox, goz, dvx, dvz, o);
+  P.scx = geo; P.scz = geo + nsrc; P.rcx = geo + 2 * nsrc; P.rcz = geo + 2 * nsrc + nrc;
+  P.srs = (const int32_t*)fm_srs.p; P.srs_ms = (long long)nrc * nsrc;
+  P.velv = (const double*)fm_vel.p; P.vel_es = 1; P.vel_ms = (long long)(nvz + 2) * (nvx + 2);
+  P.ttime = (double*)fm_tt.p; P.err = (int32_t*)fm_err.p;
+  if (field) {
+    const size_t nf = (size_t)((nvx - 1) * o->gridx + 1) * ((nvz - 1) * o->gridy + 1) * nprob;
+    void* pf = nullptr;
+    CK(cudaMalloc(&pf, 8 * nf));
+    P.field = (double*)pf;
+  }
+  rc = fm2d_launch(P, st);
+  std::vector<int32_t> herr((size_t)nprob);
+  if (!rc) {
+    cudaMemcpyAsync(ttime, fm_tt.p, 8 * nt, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(herr.data(), fm_err.p, 4 * (size_t)nprob, cudaMemcpyDeviceToHost, st);
+    if (field) cudaMemcpyAsync(field, P.field, 8 * (size_t)P.nnx * P.nnz * nprob, cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (P.field) cudaFree(P.field);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(MCT_E_CUDA, "fm2d: %s", cudaGetErrorString(e));
+  for (int p = 0; p < nprob; ++p)
+    if (herr[p]) return fail(MCT_E_INVALID_ARG, "fm2d: problem %d (period %d, source %d): %s", p, p / nsrc + 1, p % nsrc + 1,
+                             herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" : "receiver outside the model");
+  return MCT_OK;
+}
+
+int mct_fm2d_stats(int64_t out2[2]) {
+  NEED_INIT();
+  if (!out2) return fail(MCT_E_INVALID_ARG, "fm2d_stats: NULL pointer");
+  unsigned long long c[2];
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(c, (unsigned long long*)g.counters.p + 10, sizeof c, cudaMemcpyDeviceToHost));
+  out2[0] = (int64_t)c[0]; out2[1] = (int64_t)c[1];
+  return MCT_OK;
+}
+
+} // extern "C"
+
+namespace {
+void release_fm2d_globals() {
+  DevBuf* bufs[] = {&fm_veln, &fm_scratch, &fm_err, &fm_geo, &fm_srs, &fm_vel, &fm_tt};
+  for (DevBuf* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+}
+} // namespace

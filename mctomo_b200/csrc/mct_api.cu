@@ -767,6 +767,7 @@ int forward_core(const mct_grid* gr, int nb, int derive_vp_rho, const DispPlan& 
 }
 
 void release_misfit_globals(); // k4_misfit.cuh
+void release_fm2d_globals();   // k6_fm2d.cuh
 void comm_release();           // mct_comm.cuh
 int shard_exchange(int neff, int nout, bool with_group, double* d_pvel, double* d_gvel, int32_t* d_ierr, cudaStream_t st); // mct_comm.cuh
 
@@ -846,6 +847,7 @@ int mct_shutdown(void) {
                     &g.o_pvel, &g.o_gvel, &g.o_ierr, &g.bflags, &g.pl_thick, &g.pl_vp, &g.pl_vs, &g.pl_rho, &g.pl_off, &g.flags, &g.counters, &g.grt_list, &g.grt_scratch, &g.ray_pts, &g.ray_off, &g.ray_time};
   for (DevBuf* b : bufs) release(*b);
   release_misfit_globals();
+  release_fm2d_globals();
   comm_release();
   release(g.pin_a);
   release(g.pin_b);
@@ -1527,3 +1529,4 @@ int mct_sites_locate(const double* points, int ncells, const int32_t* sites_id, 
 #include "k3_raytime.cuh"  // mct_group_times_dev: CalGroupTime on the device map
 #include "mct_comm.cuh"    // mct_comm_*, mct_allgather_inplace, mct_forward_sharded_dev: NCCL data plane (config 5)
 #include "k4_misfit.cuh"   // misfit sums, session likelihood / ray times / stat_rti accumulation
+#include "k6_fm2d.cuh"     // mct_fm2d_times[_dev]: the 2-D fast-marching travel times of modrays

@@ -326,3 +326,27 @@ def grt_secfun(thick, vp, vs, rho, freq, modetype, c, math_mode=PORTABLE):
     rc = lib.orc_grt_secfun(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, len(thick), freq, modetype, c,
                             math_mode, C.byref(re), C.byref(im))
     return rc, re.value, im.value
+
+
+def fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, asgr=1, sgdl=4, sgs=8, fom=1, snb=0.5, want_field=False):
+    """modrays for one velocity map, travel times only (oracle/fm2d_ref.c).  src (nsrc,2), rcv (nrc,2) as (x, z);
+    srs (nsrc, nrc) 0/1; vel (nvx+2, nvz+2) C-order = the Fortran like%vel(period,:,:) (nvz+2, nvx+2) with its edge.
+    Returns (err, ttime (nsrc, nrc), field (nsrc, nnx, nnz) or None, counters)."""
+    lib = L()
+    vpt = C.c_void_p
+    lib.orc_fm2d_times.argtypes = [C.c_int, vpt, vpt, C.c_int, vpt, vpt, vpt, C.c_int, C.c_int] + [C.c_double] * 4 + [vpt] + [C.c_int] * 6 + \
+                                  [C.c_double, vpt, vpt, vpt]
+    src, rcv, vel = f64(src), f64(rcv), f64(vel)
+    nsrc, nrc = len(src), len(rcv)
+    nvx, nvz = vel.shape[0] - 2, vel.shape[1] - 2
+    scx, scz = f64(src[:, 0].copy()), f64(src[:, 1].copy())
+    rcx, rcz = f64(rcv[:, 0].copy()), f64(rcv[:, 1].copy())
+    srs = np.ascontiguousarray(srs, dtype=np.int32)
+    tt = np.full((nsrc, nrc), -1.0)
+    nnx, nnz = (nvx - 1) * gdx + 1, (nvz - 1) * gdz + 1
+    field = np.zeros((nsrc, nnx, nnz)) if want_field else None
+    cnt = np.zeros(2, np.int64)
+    err = lib.orc_fm2d_times(nsrc, scx.ctypes.data, scz.ctypes.data, nrc, rcx.ctypes.data, rcz.ctypes.data, srs.ctypes.data, nvx, nvz,
+                             gox, goz, dvx, dvz, vel.ctypes.data, gdx, gdz, asgr, sgdl, sgs, fom, snb, tt.ctypes.data,
+                             field.ctypes.data if want_field else None, cnt.ctypes.data)
+    return err, tt, field, cnt

@@ -1,0 +1,77 @@
+"""GPU parity of the 2-D fast-marching travel times (mctomo_b200/csrc/k6_fm2d.cuh) against oracle/fm2d_ref.c through
+the C ABI: receiver times AND the whole travel-time field bit-identical, node / stencil counters identical, for both
+stencil orders, with and without source-grid refinement, diced grids, sources on the model's edge, receivers inside the
+source cell, sources without data, several periods in one call.  The oracle of this path is "parity unpinned"
+(tests/test_oracle_fm2d.py pins it on analytic travel times)."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from test_oracle_fm2d import SRC, RCV
+
+pytestmark = pytest.mark.gpu
+
+
+def _maps(nmaps, nx, ny, seed):
+    """smooth random phase-velocity maps with the replicated edge of like%vel"""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((nmaps, nx + 2, ny + 2))
+    x, y = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny), indexing="ij")
+    for m in range(nmaps):
+        v = 2.5 + 0.2 * m
+        for _ in range(5):
+            kx, ky, ph, a = rng.uniform(1, 6), rng.uniform(1, 6), rng.uniform(0, 6.28), rng.uniform(0.05, 0.25)
+            v = v + a * np.sin(kx * x * 3 + ky * y * 3 + ph)
+        out[m, 1:-1, 1:-1] = v
+        out[m, 0, :] = out[m, 1, :]; out[m, -1, :] = out[m, -2, :]
+        out[m, :, 0] = out[m, :, 1]; out[m, :, -1] = out[m, :, -2]
+    return out
+
+
+def _compare(mct, src, rcv, srs, vel, x0, y0, dx, dy, **kw):
+    o = mct.fm2d_opts(gridx=kw.get("gdx", 1), gridy=kw.get("gdz", 1), sgref=kw.get("asgr", 1), sgdic=kw.get("sgdl", 4),
+                      sgext=kw.get("sgs", 8), order=kw.get("fom", 1), band=kw.get("snb", 0.5))
+    mct.reset_stats()
+    tt, field = mct.fm2d_times(src, rcv, srs, vel, x0, y0, dx, dy, o, want_field=True)
+    st = mct.fm2d_stats()
+    tot = np.zeros(2, np.int64)
+    for m in range(vel.shape[0]):
+        err, to, fo, cnt = orc.fm2d_times(src, rcv, srs[m] if np.ndim(srs) == 3 else srs, vel[m], x0, y0, dx, dy, want_field=True, **kw)
+        assert err == 0
+        tot += cnt
+        assert np.array_equal(tt[m], to), (m, np.abs(tt[m] - to).max())
+        marched = [i for i in range(len(src)) if i == 0 or (srs[m] if np.ndim(srs) == 3 else srs)[i].any()]
+        assert np.array_equal(field[m][marched], fo[marched]), m
+    assert st["accepted"] == tot[0] and st["updates"] == tot[1], (st, tot)
+    return tt
+
+
+@pytest.mark.parametrize("fom,asgr", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_fm2d_example1_geometry_bit_identical(mct, fom, asgr):
+    vel = _maps(3, 101, 101, 5)
+    srs = np.ones((4, 10), np.int32)
+    srs[2, :] = 0
+    srs[1, 3] = 0
+    tt = _compare(mct, SRC, RCV, srs, vel, -5.0, -5.0, 0.1, 0.1, fom=fom, asgr=asgr)
+    assert (tt[:, 2] == -1.0).all() and (tt[:, 1, 3] == -1.0).all()
+
+
+def test_fm2d_diced_anisotropic_grid_and_per_period_raystat(mct):
+    vel = _maps(2, 37, 53, 9)
+    rng = np.random.default_rng(3)
+    src = np.column_stack([rng.uniform(0.0, 7.2, 6), rng.uniform(10.0, 23.0, 6)])
+    src[0] = [0.0, 10.0]            # on the model's corner
+    src[1] = [7.19, 22.99]
+    rcv = np.column_stack([rng.uniform(0.0, 7.2, 17), rng.uniform(10.0, 23.0, 17)])
+    srs = (rng.uniform(size=(2, 6, 17)) < 0.7).astype(np.int32)
+    _compare(mct, src, rcv, srs, vel, 0.0, 10.0, 0.2, 0.25, gdx=2, gdz=3, sgdl=3, sgs=5)
+    _compare(mct, src, rcv, srs, vel, 0.0, 10.0, 0.2, 0.25, gdx=1, gdz=1, sgdl=8, sgs=12, fom=0)  # refined grid larger than the model's
+
+
+def test_fm2d_errors_are_reported(mct):
+    vel = _maps(1, 21, 21, 1)
+    o = mct.fm2d_opts()
+    with pytest.raises(RuntimeError):
+        mct.fm2d_times(np.array([[9.0, 0.0]]), RCV[:3] * 0.1, np.ones((1, 3), np.int32), vel, -1.0, -1.0, 0.1, 0.1, o)
+    with pytest.raises(RuntimeError):
+        mct.fm2d_times(np.array([[0.0, 0.0]]), RCV[:3] * 0.1, np.ones((1, 3), np.int32), vel, -1.0, -1.0, 0.1, 0.1, mct.fm2d_opts(band=0.001))

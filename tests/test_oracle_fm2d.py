@@ -1,0 +1,74 @@
+"""The oracle's restatement of the 2-D fast-marching solver (oracle/fm2d_ref.c) against physics.
+
+PARITY UNPINNED (no Fortran compiler here, no golden travel times in the reference): the checks are analytic -- a
+homogeneous medium (t = d / v) and a constant vertical gradient (t = acosh(1 + g^2 d^2 / (2 v1 v2)) / g) -- at the
+accuracy fast marching has on example1's 101 x 101 grid, plus the properties the scheme guarantees: refinement and the
+mixed-order stencils reduce the error, every receiver time is positive and no smaller than d / vmax."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+
+NX = NY = 101
+X0 = Y0 = -5.0
+DX = 0.1
+SRC = np.array([[0.03, 0.07], [-3.2, 2.5], [4.9, -4.9], [-5.0, 5.0]])  # inside, inside, near a corner, ON a corner
+RNG = np.random.default_rng(0)
+RCV = np.vstack([RNG.uniform(-4.9, 4.9, (9, 2)), [[0.05, 0.09]]])    # the last one within a cell of source 1
+
+
+def dist():
+    return np.sqrt(((SRC[:, None, :] - RCV[None, :, :]) ** 2).sum(-1))
+
+
+@pytest.mark.parametrize("fom,asgr,tol_mean,tol_max", [(0, 0, 0.03, 0.08), (0, 1, 0.02, 0.04), (1, 0, 0.015, 0.06), (1, 1, 0.005, 0.02)])
+def test_homogeneous_medium(fom, asgr, tol_mean, tol_max):
+    vel = np.full((NX + 2, NY + 2), 3.0)
+    err, tt, field, cnt = orc.fm2d_times(SRC, RCV, np.ones((4, 10), np.int32), vel, X0, Y0, DX, DX, fom=fom, asgr=asgr, want_field=True)
+    assert err == 0 and cnt[0] >= 4 * NX * NY
+    rel = np.abs(tt * 3.0 - dist()) / dist()
+    assert rel.mean() < tol_mean and rel.max() < tol_max, (rel.mean(), rel.max())
+    assert (field >= 0).all() and (tt > 0).all()
+
+
+def test_refinement_and_mixed_order_reduce_the_error():
+    vel = np.full((NX + 2, NY + 2), 3.0)
+    e = {}
+    for fom in (0, 1):
+        for asgr in (0, 1):
+            _, tt, _, _ = orc.fm2d_times(SRC[:2], RCV[:9], np.ones((2, 9), np.int32), vel, X0, Y0, DX, DX, fom=fom, asgr=asgr)
+            d = dist()[:2, :9]
+            e[fom, asgr] = (np.abs(tt * 3.0 - d) / d).mean()
+    assert e[1, 1] < e[1, 0] < e[0, 0] and e[1, 1] < e[0, 1] < e[0, 0]
+
+
+def test_constant_gradient_medium():
+    g = 0.2
+    yy = Y0 + (np.arange(NY + 2) - 1) * DX
+    vel = np.tile(2 + g * (yy + 5), (NX + 2, 1))
+    err, tt, _, _ = orc.fm2d_times(SRC[:3], RCV[:9], np.ones((3, 9), np.int32), vel, X0, Y0, DX, DX)
+    v1, v2 = 2 + g * (SRC[:3, 1] + 5), 2 + g * (RCV[:9, 1] + 5)
+    d2 = ((SRC[:3, None, :] - RCV[None, :9, :]) ** 2).sum(-1)
+    ta = np.arccosh(1 + g * g * d2 / (2 * v1[:, None] * v2[None, :])) / g
+    assert err == 0 and (np.abs(tt - ta) / ta).max() < 0.02
+    assert (tt >= np.sqrt(d2) / vel.max() - 1e-12).all()
+
+
+def test_sources_without_data_are_skipped_and_receivers_without_data_untouched():
+    vel = np.full((NX + 2, NY + 2), 2.5)
+    srs = np.ones((4, 10), np.int32)
+    srs[2, :] = 0      # no valid ray: the source is skipped (it is not the first)
+    srs[1, 3] = 0
+    err, tt, _, cnt = orc.fm2d_times(SRC, RCV, srs, vel, X0, Y0, DX, DX)
+    assert err == 0 and (tt[2] == -1.0).all() and tt[1, 3] == -1.0 and (tt[[0, 1, 3]][:, [0, 1, 2]] > 0).all()
+    srs[:] = 0         # the first source is marched even without data
+    err, tt, _, cnt2 = orc.fm2d_times(SRC, RCV, srs, vel, X0, Y0, DX, DX)
+    assert err == 0 and (tt == -1.0).all() and 0 < cnt2[0] < cnt[0]
+
+
+def test_errors_are_reported_not_fatal():
+    vel = np.full((NX + 2, NY + 2), 2.5)
+    err, _, _, _ = orc.fm2d_times(np.array([[9.0, 0.0]]), RCV, np.ones((1, 10), np.int32), vel, X0, Y0, DX, DX)
+    assert err == 1   # source outside the model: the Fortran STOPs
+    err, _, _, _ = orc.fm2d_times(SRC[:1], RCV, np.ones((1, 10), np.int32), vel, X0, Y0, DX, DX, snb=0.001)
+    assert err == 2   # narrow band larger than snb*nx*ny: the Fortran overruns btg
