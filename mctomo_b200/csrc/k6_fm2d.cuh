@@ -27,6 +27,8 @@ struct FmParams {
   int nnx, nnz, ldr;         // propagation grid; leading dimension of the refined arrays
   double* veln;              // (nnz, nnx, nmaps): gridder's output (fm2d_gridder_kernel)
   char* scratch; size_t scratch_per_problem;
+  int use_smem;              // travel-time, status and heap arrays of a problem live in shared memory (they fit: example1's 101 x 101 grid does)
+  int maxbt_alloc;           // heap entries reserved per problem
   double* ttime;             // (nrc, nsrc, nmaps); entries without data untouched
   double* field;             // optional (nnz, nnx, nsrc, nmaps): ttn of every problem
   int32_t* err;              // per problem: 0, 1 source outside, 2 narrow band overflow, 3 receiver outside
@@ -140,131 +142,108 @@ __device__ __forceinline__ double fm_qsolve(double a, double b, double c) {
   if (rd1 < 0.0) rd1 = 0.0;
   return (-b + sqrt(rd1)) / (2.0 * a);
 }
-// fouds1 (fm2d_ttime.f90:138-197)
-__device__ void fm_fouds1(FmGrid& G, int iz, int ix) {
-  int tsw1 = 0;
-  double travm = 0;
+// ONE quadrant (the neighbour pair j = ix + dj, k = iz + dk) of fouds1 / fouds2 (fm2d_ttime.f90:138-197, 199-345) for the node
+// (iz, ix): the candidate travel time of that stencil, or false when it has no solution.  The Fortran takes the minimum of
+// the (up to) four candidates in the order (j, k) = (-,-), (-,+), (+,-), (+,+); a minimum does not depend on the order.
+__device__ bool fm_quadrant(const FmGrid& G, int iz, int ix, int dj, int dk, double* trav_out) {
+  const int j = ix + dj, k = iz + dk;
+  if (j < 1 || j > G.nnx || k < 1 || k > G.nnz) return false;
   const double slown = 1.0 / FVELN(G, iz, ix), dnx = G.dnx, dnz = G.dnz;
-  G.n_update++;
-  for (int j = ix - 1; j <= ix + 1; j += 2)
-    for (int k = iz - 1; k <= iz + 1; k += 2) {
-      if (j < 1 || j > G.nnx || k < 1 || k > G.nnz) continue;
-      int swsol = 0;
-      double a = 0, b = 0, c = 0, tref = 0;
-      if (FNSTS(G, iz, j) == 0) {
-        swsol = 1;
-        if (FNSTS(G, k, ix) == 0) {
-          const double u = dnx, v = dnz, em = FTTN(G, k, ix) - FTTN(G, iz, j);
-          a = u * u + v * v;
-          b = -2.0 * (u * u) * em;
-          c = (u * u) * (em * em - (v * v) * (slown * slown));
-          tref = FTTN(G, iz, j);
-        } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = FTTN(G, iz, j); }
-      } else if (FNSTS(G, k, ix) == 0) {
-        swsol = 1;
-        const double sd = slown * dnz;
-        a = 1.0; b = 0.0; c = -(sd * sd); tref = FTTN(G, k, ix);
-      }
-      if (swsol) {
-        const double trav = tref + fm_qsolve(a, b, c);
-        if (tsw1) travm = trav < travm ? trav : travm; else { travm = trav; tsw1 = 1; }
-      }
+  const int sj = FNSTS(G, iz, j), sk = FNSTS(G, k, ix);
+  double a = 0, b = 0, c = 0, tref = 0, tdiv = 1.0, u, v, em;
+  int swsol = 0;
+  if (G.fom == 0) {
+    if (sj == 0) {
+      swsol = 1;
+      const double tj = FTTN(G, iz, j);
+      if (sk == 0) {
+        u = dnx; v = dnz; em = FTTN(G, k, ix) - tj;
+        a = u * u + v * v;
+        b = -2.0 * (u * u) * em;
+        c = (u * u) * (em * em - (v * v) * (slown * slown));
+        tref = tj;
+      } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; }
+    } else if (sk == 0) {
+      swsol = 1;
+      const double sd = slown * dnz;
+      a = 1.0; b = 0.0; c = -(sd * sd); tref = FTTN(G, k, ix);
     }
-  FTTN(G, iz, ix) = travm;
-}
-// fouds2 (fm2d_ttime.f90:199-345)
-__device__ void fm_fouds2(FmGrid& G, int iz, int ix) {
-  int tsw1 = 0;
-  double travm = 0;
-  const double slown = 1.0 / FVELN(G, iz, ix), dnx = G.dnx, dnz = G.dnz;
-  G.n_update++;
-  for (int j = ix - 1; j <= ix + 1; j += 2) {
-    if (j < 1 || j > G.nnx) continue;
-    int swj = -1, j2;
-    if (j == ix - 1) { j2 = j - 1; if (j2 >= 1) { if (FNSTS(G, iz, j2) == 0) swj = 0; } }
-    else { j2 = j + 1; if (j2 <= G.nnx) { if (FNSTS(G, iz, j2) == 0) swj = 0; } }
-    const int sj = FNSTS(G, iz, j);
+  } else {
+    int swj = -1, swk = -1;
+    const int j2 = j + dj, k2 = k + dk;
+    if (j2 >= 1 && j2 <= G.nnx) { if (FNSTS(G, iz, j2) == 0) swj = 0; }
     const double tj = FTTN(G, iz, j);
     double tj2 = 0;
     if (sj == 0 && swj == 0) { swj = -1; tj2 = FTTN(G, iz, j2); if (tj > tj2) swj = 0; }
     else swj = -1;
-    for (int k = iz - 1; k <= iz + 1; k += 2) {
-      if (k < 1 || k > G.nnz) continue;
-      int swk = -1, k2;
-      if (k == iz - 1) { k2 = k - 1; if (k2 >= 1) { if (FNSTS(G, k2, ix) == 0) swk = 0; } }
-      else { k2 = k + 1; if (k2 <= G.nnz) { if (FNSTS(G, k2, ix) == 0) swk = 0; } }
-      const int sk = FNSTS(G, k, ix);
-      const double tk = FTTN(G, k, ix);
-      double tk2 = 0;
-      if (sk == 0 && swk == 0) { swk = -1; tk2 = FTTN(G, k2, ix); if (tk > tk2) swk = 0; }
-      else swk = -1;
-      int swsol = 0;
-      double a = 0, b = 0, c = 0, tref = 0, tdiv = 1.0, u, v, em;
-      if (swj == 0) {
-        swsol = 1;
-        if (swk == 0) {
-          u = 2.0 * dnx; v = 2.0 * dnz;
-          em = 4.0 * tj - tj2 - 4.0 * tk;
-          em = em + tk2;
-          a = v * v + u * u;
-          b = 2.0 * em * (u * u);
-          c = (u * u) * (em * em - (slown * slown) * (v * v));
-          tref = 4.0 * tj - tj2;
-          tdiv = 3.0;
-        } else if (sk == 0) {
-          u = dnz; v = 2.0 * dnx;
-          em = 3.0 * tk - 4.0 * tj + tj2;
-          a = v * v + 9.0 * (u * u);
-          b = 6.0 * em * (u * u);
-          c = (u * u) * (em * em - (slown * slown) * (v * v));
-          tref = tk;
-          tdiv = 1.0;
-        } else {
-          u = 2.0 * dnx;
-          a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
-          tref = 4.0 * tj - tj2;
-          tdiv = 3.0;
-        }
-      } else if (sj == 0) {
-        swsol = 1;
-        if (swk == 0) {
-          u = dnx; v = 2.0 * dnz;
-          em = 3.0 * tj - 4.0 * tk + tk2;
-          a = v * v + 9.0 * (u * u);
-          b = 6.0 * em * (u * u);
-          c = (u * u) * (em * em - (v * v) * (slown * slown));
-          tref = tj;
-          tdiv = 1.0;
-        } else if (sk == 0) {
-          u = dnx; v = dnz;
-          em = tk - tj;
-          a = u * u + v * v;
-          b = -2.0 * (u * u) * em;
-          c = (u * u) * (em * em - (v * v) * (slown * slown));
-          tref = tj;
-          tdiv = 1.0;
-        } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; tdiv = 1.0; }
+    if (k2 >= 1 && k2 <= G.nnz) { if (FNSTS(G, k2, ix) == 0) swk = 0; }
+    const double tk = FTTN(G, k, ix);
+    double tk2 = 0;
+    if (sk == 0 && swk == 0) { swk = -1; tk2 = FTTN(G, k2, ix); if (tk > tk2) swk = 0; }
+    else swk = -1;
+    if (swj == 0) {
+      swsol = 1;
+      if (swk == 0) {
+        u = 2.0 * dnx; v = 2.0 * dnz;
+        em = 4.0 * tj - tj2 - 4.0 * tk;
+        em = em + tk2;
+        a = v * v + u * u;
+        b = 2.0 * em * (u * u);
+        c = (u * u) * (em * em - (slown * slown) * (v * v));
+        tref = 4.0 * tj - tj2;
+        tdiv = 3.0;
+      } else if (sk == 0) {
+        u = dnz; v = 2.0 * dnx;
+        em = 3.0 * tk - 4.0 * tj + tj2;
+        a = v * v + 9.0 * (u * u);
+        b = 6.0 * em * (u * u);
+        c = (u * u) * (em * em - (slown * slown) * (v * v));
+        tref = tk;
+        tdiv = 1.0;
       } else {
-        if (swk == 0) {
-          swsol = 1;
-          u = 2.0 * dnz;
-          a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
-          tref = 4.0 * tk - tk2;
-          tdiv = 3.0;
-        } else if (sk == 0) {
-          swsol = 1;
-          a = 1.0; b = 0.0; c = -(slown * slown) * (dnz * dnz);
-          tref = tk;
-          tdiv = 1.0;
-        }
+        u = 2.0 * dnx;
+        a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
+        tref = 4.0 * tj - tj2;
+        tdiv = 3.0;
       }
-      if (swsol) {
-        const double trav = (tref + fm_qsolve(a, b, c)) / tdiv;
-        if (tsw1) travm = trav < travm ? trav : travm; else { travm = trav; tsw1 = 1; }
+    } else if (sj == 0) {
+      swsol = 1;
+      if (swk == 0) {
+        u = dnx; v = 2.0 * dnz;
+        em = 3.0 * tj - 4.0 * tk + tk2;
+        a = v * v + 9.0 * (u * u);
+        b = 6.0 * em * (u * u);
+        c = (u * u) * (em * em - (v * v) * (slown * slown));
+        tref = tj;
+        tdiv = 1.0;
+      } else if (sk == 0) {
+        u = dnx; v = dnz;
+        em = tk - tj;
+        a = u * u + v * v;
+        b = -2.0 * (u * u) * em;
+        c = (u * u) * (em * em - (v * v) * (slown * slown));
+        tref = tj;
+        tdiv = 1.0;
+      } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; tdiv = 1.0; }
+    } else {
+      if (swk == 0) {
+        swsol = 1;
+        u = 2.0 * dnz;
+        a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
+        tref = 4.0 * tk - tk2;
+        tdiv = 3.0;
+      } else if (sk == 0) {
+        swsol = 1;
+        a = 1.0; b = 0.0; c = -(slown * slown) * (dnz * dnz);
+        tref = tk;
+        tdiv = 1.0;
       }
     }
   }
-  FTTN(G, iz, ix) = travm;
+  if (!swsol) return false;
+  const double t = tref + fm_qsolve(a, b, c);
+  *trav_out = G.fom == 0 ? t : t / tdiv;
+  return true;
 }
 __device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3][3], double dsx, double dsz) {
   double biv = 0.0;
@@ -275,58 +254,98 @@ __device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3
     }
   return biv;
 }
-__device__ __forceinline__ void fm_update(FmGrid& G, int iz, int ix) {
-  const int s = FNSTS(G, iz, ix);
-  if (s == -1) {
-    if (G.fom == 0) fm_fouds1(G, iz, ix); else fm_fouds2(G, iz, ix);
-    fm_addtree(G, iz, ix);
-  } else if (s > 0) {
-    if (G.fom == 0) fm_fouds1(G, iz, ix); else fm_fouds2(G, iz, ix);
-    fm_sift_up(G, iz, ix, FNSTS(G, iz, ix));
-  }
-}
-// travel (fm2d_ttime.f90:27-136); lane 0 only.  urg 0/1: nsts must already be -1 everywhere (the caller's lanes fill it)
-__device__ void fm_travel(FmGrid& G, double scx, double scz, int urg) {
-  int isx = (int)((scx - G.gox) / G.dnx) + 1;
-  int isz = (int)((scz - G.goz) / G.dnz) + 1;
-  if (isx < 1 || isx > G.nnx || isz < 1 || isz > G.nnz) { G.error = 1; return; }
-  if (isx == G.nnx) isx--;
-  if (isz == G.nnz) isz--;
-  G.ntr = 0;
-  if (urg == 2) {
-    for (int i = 1; i <= G.nnx; ++i)
-      for (int j = 1; j <= G.nnz; ++j)
-        if (FNSTS(G, j, i) > 0) fm_addtree(G, j, i);
-  } else {
-    double vss[3][3];
-    for (int i = 1; i <= 2; ++i) for (int j = 1; j <= 2; ++j) vss[i][j] = FVELN(G, isz - 1 + j, isx - 1 + i);
-    const double dsx = (scx - G.gox) - (isx - 1) * G.dnx;
-    const double dsz = (scz - G.goz) - (isz - 1) * G.dnz;
-    const double vsrc = fm_bilinear(G, vss, dsx, dsz);
-    for (int i = 1; i <= 2; ++i)
-      for (int j = 1; j <= 2; ++j) {
-        const double ex = dsx - (i - 1) * G.dnx, ez = dsz - (j - 1) * G.dnz;
-        const double ds = sqrt(ex * ex + ez * ez);
-        FTTN(G, isz - 1 + j, isx - 1 + i) = 2.0 * ds / (vss[i][j] + vsrc);
-        fm_addtree(G, isz - 1 + j, isx - 1 + i);
+// travel (fm2d_ttime.f90:27-136), by the whole warp.  The march order is the heap's, so nodes are accepted one at a time
+// (lane 0 owns the heap); the work per accepted node -- up to four neighbour updates of up to four stencil quadrants each
+// -- is independent (a neighbour being updated is not alive, and the stencils only read alive nodes), so lanes 0..15
+// solve one (neighbour, quadrant) each on the state before the updates, a shuffle takes the minima, and lane 0 writes
+// the times and re-orders the heap in the reference's neighbour order (x-1, x+1, z-1, z+1).
+// urg 0/1: nsts must already be -1 everywhere (the caller's lanes fill it).  G lives in shared memory.
+__device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, volatile int* sh) {
+  if (lane == 0) {
+    int isx = (int)((scx - G.gox) / G.dnx) + 1;
+    int isz = (int)((scz - G.goz) / G.dnz) + 1;
+    if (isx < 1 || isx > G.nnx || isz < 1 || isz > G.nnz) G.error = 1;
+    else {
+      if (isx == G.nnx) isx--;
+      if (isz == G.nnz) isz--;
+      G.ntr = 0;
+      if (urg == 2) {
+        for (int i = 1; i <= G.nnx; ++i)
+          for (int j = 1; j <= G.nnz; ++j)
+            if (FNSTS(G, j, i) > 0) fm_addtree(G, j, i);
+      } else {
+        double vss[3][3];
+        for (int i = 1; i <= 2; ++i) for (int j = 1; j <= 2; ++j) vss[i][j] = FVELN(G, isz - 1 + j, isx - 1 + i);
+        const double dsx = (scx - G.gox) - (isx - 1) * G.dnx;
+        const double dsz = (scz - G.goz) - (isz - 1) * G.dnz;
+        const double vsrc = fm_bilinear(G, vss, dsx, dsz);
+        for (int i = 1; i <= 2; ++i)
+          for (int j = 1; j <= 2; ++j) {
+            const double ex = dsx - (i - 1) * G.dnx, ez = dsz - (j - 1) * G.dnz;
+            const double ds = sqrt(ex * ex + ez * ez);
+            FTTN(G, isz - 1 + j, isx - 1 + i) = 2.0 * ds / (vss[i][j] + vsrc);
+            fm_addtree(G, isz - 1 + j, isx - 1 + i);
+          }
       }
-  }
-  while (G.ntr > 0 && !G.error) {
-    const int h = G.heap[1];
-    const int ix = HPX(h), iz = HPZ(h);
-    if (urg == 1) {
-      int swrg = 0;
-      if (ix == 1 && G.vnl != 1) swrg = 1;
-      if (ix == G.nnx && G.vnr != G.nnx) swrg = 1; // (refined extent against a coarse index, as the Fortran has it)
-      if (iz == 1 && G.vnt != 1) swrg = 1;
-      if (iz == G.nnz && G.vnb != G.nnz) swrg = 1;
-      if (swrg) { FNSTS(G, iz, ix) = 0; break; }
     }
-    FNSTS(G, iz, ix) = 0;
-    G.n_accept++;
-    fm_downtree(G);
-    for (int i = ix - 1; i <= ix + 1; i += 2) if (i >= 1 && i <= G.nnx) fm_update(G, iz, i);
-    for (int i = iz - 1; i <= iz + 1; i += 2) if (i >= 1 && i <= G.nnz) fm_update(G, i, ix);
+  }
+  __syncwarp();
+  for (;;) {
+    if (lane == 0) {
+      int go = 0;
+      if (G.ntr > 0 && !G.error) {
+        const int h = G.heap[1];
+        const int ix = HPX(h), iz = HPZ(h);
+        int swrg = 0;
+        if (urg == 1) {
+          if (ix == 1 && G.vnl != 1) swrg = 1;
+          if (ix == G.nnx && G.vnr != G.nnx) swrg = 1; // (refined extent against a coarse index, as the Fortran has it)
+          if (iz == 1 && G.vnt != 1) swrg = 1;
+          if (iz == G.nnz && G.vnb != G.nnz) swrg = 1;
+        }
+        FNSTS(G, iz, ix) = 0;
+        if (!swrg) {
+          G.n_accept++;
+          fm_downtree(G);
+          sh[1] = ix; sh[2] = iz;
+          go = 1;
+        }
+      }
+      sh[0] = go;
+    }
+    __syncwarp();
+    if (!sh[0]) break;
+    const int ix = sh[1], iz = sh[2];
+    // (neighbour n, quadrant q) on lane 4n + q
+    const int n = (lane >> 2) & 3, q = lane & 3;
+    const int nix = n == 0 ? ix - 1 : (n == 1 ? ix + 1 : ix), niz = n == 2 ? iz - 1 : (n == 3 ? iz + 1 : iz);
+    int st = 0; // the neighbour's status; 0 = nothing to do (alive or outside)
+    if (nix >= 1 && nix <= G.nnx && niz >= 1 && niz <= G.nnz) st = FNSTS(G, niz, nix);
+    double trav = 0;
+    bool has = false;
+    if (lane < 16 && st != 0) has = fm_quadrant(G, niz, nix, (q >> 1) ? 1 : -1, (q & 1) ? 1 : -1, &trav);
+    // minimum of the quadrants that have a solution
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const double ot = __shfl_xor_sync(0xffffffffu, trav, o);
+      const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, o) != 0;
+      if (oh && (!has || ot < trav)) trav = ot;
+      has = has || oh;
+    }
+    __syncwarp(); // every stencil has read the state before any update
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double tm = __shfl_sync(0xffffffffu, trav, 4 * m);
+      const int sm = __shfl_sync(0xffffffffu, st, 4 * m);
+      const bool hm = __shfl_sync(0xffffffffu, has ? 1 : 0, 4 * m) != 0;
+      if (lane == 0 && sm != 0) {
+        const int mx = m == 0 ? ix - 1 : (m == 1 ? ix + 1 : ix), mz = m == 2 ? iz - 1 : (m == 3 ? iz + 1 : iz);
+        G.n_update++;
+        FTTN(G, mz, mx) = hm ? tm : 0.0; // (no stencil solved: travm is undefined in the Fortran; cannot happen next to an alive node)
+        if (sm == -1) fm_addtree(G, mz, mx); else fm_sift_up(G, mz, mx, FNSTS(G, mz, mx));
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -352,8 +371,17 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   int32_t* nsts_c = (int32_t*)(ttn_r + cr);
   int32_t* nsts_r = nsts_c + cc;
   int32_t* heap = nsts_r + cr;
+  extern __shared__ __align__(16) unsigned char fm_smem[];
+  if (P.use_smem) { // the march is a chain of dependent loads: shared memory (~30 cycles) instead of L2 (~300) per hop
+    ttn_c = (double*)fm_smem;
+    ttn_r = ttn_c + cc;
+    nsts_c = (int32_t*)(ttn_r + cr);
+    nsts_r = nsts_c + cc;
+    heap = nsts_r + cr;
+  }
   __shared__ FmGrid G;
   __shared__ int s_err;
+  __shared__ int s_sh[4];
   int isx = (int)((x - P.gox) / dnx0) + 1, isz = (int)((z - P.goz) / dnz0) + 1;
   if (isx < 1 || isx > P.nnx || isz < 1 || isz > P.nnz) { if (lane == 0) P.err[prob] = 1; return; }
   if (isx == P.nnx) isx--;
@@ -399,10 +427,10 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
       int mb = maxbt0;
       if (nrnx > P.nnx || nrnz > P.nnz) { const int a = nrnx > P.nnx ? nrnx : P.nnx, b = nrnz > P.nnz ? nrnz : P.nnz; mb = (int)floor(P.snb * a * b + 0.5); }
       G.maxbt = mb;
-      fm_travel(G, x, z, 1);
-      s_err = G.error;
-      nacc = G.n_accept; nupd = G.n_update;
     }
+    __syncwarp();
+    fm_travel(G, x, z, 1, lane, s_sh);
+    if (lane == 0) { s_err = G.error; nacc = G.n_accept; nupd = G.n_update; }
     __syncwarp();
     if (s_err) { if (lane == 0) P.err[prob] = s_err; return; }
     // map the refined grid onto the coarse one (:341-372), then complete the narrow band (:398-417)
@@ -440,10 +468,10 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     if (lane == 0) {
       G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
       G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.n_accept = 0; G.n_update = 0;
-      fm_travel(G, x, z, 2);
-      s_err = G.error;
-      nacc += G.n_accept; nupd += G.n_update;
     }
+    __syncwarp();
+    fm_travel(G, x, z, 2, lane, s_sh);
+    if (lane == 0) { s_err = G.error; nacc += G.n_accept; nupd += G.n_update; }
   } else {
     for (size_t q = lane; q < cc; q += 32) nsts_c[q] = -1;
     __syncwarp();
@@ -451,10 +479,10 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
       G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
       G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.heap = heap; G.fom = P.fom; G.maxbt = maxbt0;
       G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
-      fm_travel(G, x, z, 0);
-      s_err = G.error;
-      nacc = G.n_accept; nupd = G.n_update;
     }
+    __syncwarp();
+    fm_travel(G, x, z, 0, lane, s_sh);
+    if (lane == 0) { s_err = G.error; nacc = G.n_accept; nupd = G.n_update; }
   }
   __syncwarp();
   if (lane == 0 && P.counters) { atomicAdd(&P.counters[0], (unsigned long long)nacc); atomicAdd(&P.counters[1], (unsigned long long)nupd); }
@@ -517,6 +545,12 @@ int fm2d_launch(FmParams& P, cudaStream_t st) {
   const size_t cc = (size_t)P.nnx * P.nnz, cr = (size_t)P.ldr * P.ldr;
   const int a = std::max(P.ldr, P.nnx), b = std::max(P.ldr, P.nnz);
   const size_t maxbt = (size_t)std::max(floor(P.snb * P.nnx * P.nnz + 0.5), floor(P.snb * a * b + 0.5)) + 4;
+  P.maxbt_alloc = (int)maxbt;
+  const size_t smem = 8 * (cc + cr) + 4 * (cc + cr + maxbt);
+  // measured: the march is bound by the latency of its own arithmetic, not of memory -- shared memory gained nothing at
+  // example1's size and limits the problems in flight to one per SM; kept as an experiment (MCT_FM2D_SMEM=1)
+  P.use_smem = smem <= 200 * 1024 && getenv("MCT_FM2D_SMEM") != nullptr;
+  if (P.use_smem) CK(cudaFuncSetAttribute(fm2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   size_t per = 8 * (cc + 2 * cr) + 4 * (cc + cr + maxbt);
   per = (per + 15) & ~(size_t)15;
   P.scratch_per_problem = per;
@@ -527,7 +561,7 @@ int fm2d_launch(FmParams& P, cudaStream_t st) {
   P.counters = g.count_on ? (unsigned long long*)g.counters.p + 10 : nullptr;
   ProfScope ps(2, st);
   fm2d_gridder_kernel<<<grid_blocks((long long)cc * P.nmaps, 256, 8), 256, 0, st>>>(P);
-  fm2d_kernel<<<nprob, 32, 0, st>>>(P);
+  fm2d_kernel<<<nprob, 32, P.use_smem ? smem : 0, st>>>(P);
   CK(cudaGetLastError());
   g.host_stats.n_launches += 2;
   return MCT_OK;
