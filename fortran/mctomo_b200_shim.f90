@@ -26,6 +26,8 @@ module m_mctomo_b200
 
     public :: mctomo_b200_init, mctomo_b200_shutdown
     public :: kdtree_to_grid_b200, surf_dispersion_b200, vs2vp_rho_b200
+    ! the fast-marching travel times of every (period, source) in one call (INTEGRATION.md 6)
+    public :: fm2d_times_b200
     ! the resident session: one chain's model kept in HBM between proposals (INTEGRATION.md 5a)
     public :: T_B200_SESSION, b200_session_create, b200_session_destroy, b200_session_set_model, b200_session_propose, &
               b200_session_accept, b200_session_reject, b200_session_likelihood, b200_session_stat_rti
@@ -48,6 +50,12 @@ module m_mctomo_b200
         real(c_double)     :: dx, dy, dz
         real(c_double)     :: waterDepth
         real(c_double)     :: scaling
+    end type
+
+    ! mirrors `mct_fm2d_opts`
+    type, bind(C) :: mct_fm2d_opts
+        integer(c_int32_t) :: gridx, gridy, sgref, sgdic, sgext, order
+        real(c_double)     :: band
     end type
 
     ! mirrors `mct_disp_opts`
@@ -203,6 +211,15 @@ module m_mctomo_b200
         integer(c_int) function mct_session_stat_get(sess, aveS, stdS, aveP, stdP, nsamples) bind(C, name='mct_session_stat_get')
             import :: c_int, c_ptr
             type(c_ptr), value :: sess, aveS, stdS, aveP, stdP, nsamples
+        end function
+        ! ---- 2-D fast-marching travel times (k6_fm2d.cuh): modrays for phase-velocity data, all periods x sources at once ----
+        integer(c_int) function mct_fm2d_times(src_x, src_z, nsrc, rcv_x, rcv_z, nrc, srs, vel, nmaps, nvx, nvz, gox, goz, dvx, dvz, &
+                opt, ttime, field) bind(C, name='mct_fm2d_times')
+            import :: c_int, c_ptr, c_double, mct_fm2d_opts
+            type(c_ptr), value    :: src_x, src_z, rcv_x, rcv_z, srs, vel, ttime, field
+            integer(c_int), value :: nsrc, nrc, nmaps, nvx, nvz
+            real(c_double), value :: gox, goz, dvx, dvz
+            type(mct_fm2d_opts), intent(in) :: opt
         end function
         ! ---- low-velocity columns: the generalized R/T branch of surfmodes on the device (k5_grt.cuh) ----
         integer(c_int) function mct_set_grt(enable, par6) bind(C, name='mct_set_grt')
@@ -414,6 +431,39 @@ contains
         if (rc == 3 .or. rc == 5) call fail('mct_surf_dispersion', rc)
         if (rc == 2) call solve_lvl_columns_on_host(model, grid, ix0, ix1, iy0, iy1, freqs, raylov, phaseGroup, dPhaseVel, &
                                                     var, pvel, gvel, ierr)
+    end subroutine
+
+    ! Drop-in for the OpenMP loop over periods around `modrays` in surf_likelihood (src/likelihood_surf.F90:295-336) when
+    ! settings%phaseGroup == 0 (uar = 1: travel times only).  src(2,nsrc), rev(2,nrev), raystat(nrev*nsrc,2,np),
+    ! vel(np,ny+2,nx+2) = like%vel, phaseTime(nrev,nsrc,np) = like%phaseTime exactly as the reference declares them.
+    ! Group-velocity data need the ray geometry (rpaths), which stays with the Fortran modrays.
+    subroutine fm2d_times_b200(src, rev, raystat, grid, vel, gridx, gridy, sgref, sgdic, sgext, order, band, phaseTime)
+        real(c_double), dimension(:,:), intent(in) :: src, rev
+        integer(c_int), dimension(:,:,:), intent(in) :: raystat
+        type(T_GRID), intent(in) :: grid
+        real(c_double), dimension(:,:,:), intent(in) :: vel
+        integer, intent(in) :: gridx, gridy, sgref, sgdic, sgext, order
+        real(c_double), intent(in) :: band
+        real(c_double), dimension(:,:,:), intent(inout), target :: phaseTime
+
+        real(c_double), allocatable, target :: sx(:), sz(:), rx(:), rz(:), maps(:,:,:)
+        integer(c_int), allocatable, target :: srs(:,:)
+        type(mct_fm2d_opts) :: o
+        integer(c_int) :: rc
+        integer :: i, np, nsrc, nrev
+
+        nsrc = size(src, 2); nrev = size(rev, 2); np = size(vel, 1)
+        allocate(sx(nsrc), sz(nsrc), rx(nrev), rz(nrev), srs(nrev*nsrc, np), maps(size(vel, 2), size(vel, 3), np))
+        sx = src(1,:); sz = src(2,:); rx = rev(1,:); rz = rev(2,:)
+        srs = raystat(:, 1, :)
+        do i = 1, np
+            maps(:, :, i) = vel(i, :, :)
+        enddo
+        o%gridx = gridx; o%gridy = gridy; o%sgref = sgref; o%sgdic = sgdic; o%sgext = sgext; o%order = order; o%band = band
+        rc = mct_fm2d_times(c_loc(sx), c_loc(sz), int(nsrc, c_int), c_loc(rx), c_loc(rz), int(nrev, c_int), c_loc(srs), c_loc(maps), &
+                            int(np, c_int), int(grid%nx, c_int), int(grid%ny, c_int), grid%xmin, grid%ymin, grid%dx, grid%dy, o, &
+                            c_loc(phaseTime), c_null_ptr)
+        if (rc /= 0) call fail('mct_fm2d_times', rc)
     end subroutine
 
     ! The ierr = 2 columns of a dispersion call, through the reference's own surfmodes (GRT branch).

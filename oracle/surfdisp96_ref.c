@@ -6,11 +6,14 @@
  * product path may link or call this file; only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs use it.
  *
- * PARITY STATUS: "parity unpinned" for stage 2.  The reference ships no golden
- * vectors or tests for surfdisp96 and no Fortran compiler exists in the build image,
- * so this restatement cannot be diffed against the compiled reference.  It is pinned
- * only by physics known-answer tests (tests/test_oracle_dispersion.py: half-space
- * Rayleigh velocity, Love cut-off, monotone dispersion) and by line-by-line review.
+ * PARITY STATUS: pinned on the reference's own source.  oracle/f77toc.py translates
+ * /root/reference/surfmodes/surfdisp96.f mechanically to C (oracle/_ref/, git-ignored);
+ * this restatement agrees with that translation bit for bit on 1 039 committed fixtures
+ * (tests/golden/dispersion_ref.npz) and on fresh random stacks wherever oracle/_ref exists
+ * (tests/test_oracle_vs_reference.py).  Not yet diffed against a gfortran binary: the recipe
+ * (oracle/build_ref_surfdisp.sh) and its test are committed and reported skipped without a
+ * Fortran compiler.  Physics known-answer tests: tests/test_oracle_dispersion.py,
+ * tests/test_oracle_physics.py.
  *
  * Every function cites the reference lines it restates (paths relative to
  * /root/reference).  The Fortran typing is kept variable by variable: what is
