@@ -438,6 +438,16 @@ int mct_session_set_data(mct_session* s, int nrr, int sigdep, int nrays_total, c
 int mct_session_likelihood(mct_session* s, int pending, const double* ray_points, const int64_t* ray_offsets,
                            int nrays, const double* snoise0, const double* snoise1, double out[3],
                            double* phase_time, double* sigma);
+/* Curved rays (settings%isStraight == 0) for phase-velocity data: sources, receivers and the fast-marching settings made
+ * resident once (mct_session_set_fm2d), then mct_session_likelihood_fm2d assembles like%vel from the resident phase map
+ * (+ the pending window), marches every (period, source) (mct_fm2d_times_dev), sets like%srdist = like%phaseTime
+ * (likelihood_surf.F90:327-333) and evaluates the misfit: nuclei in (mct_session_propose), three doubles out.
+ * Needs mct_session_set_data (raystat decides which sources are marched); group-velocity data are refused (ray lengths
+ * need the ray geometry, which stays on the host). */
+int mct_session_set_fm2d(mct_session* s, const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z,
+                         int nrc, const mct_fm2d_opts* o);
+int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snoise0, const double* snoise1, double out[3],
+                                double* phase_time, double* sigma);
 /* stat_rti (src/mcmc_loc2.f90:1966-1978): aveS += vs, stdS += vs**2, aveP += vp, stdP += vp**2 over the session's
  * resident current model; the accumulators stay on the device until mct_session_stat_get. */
 int mct_session_stat_accumulate(mct_session* s);

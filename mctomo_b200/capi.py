@@ -697,6 +697,28 @@ class Session:
                                                    out.ctypes.data, _ptr(pt), _ptr(sg)), allow=(MCT_E_ZERO_NOISE,))
         return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], phase_time=pt, sigma=sg, rc=rc)
 
+    def set_fm2d(self, src, rcv, opts):
+        """sources (nsrc,2), receivers (nrc,2) as (x, y); opts = fm2d_opts(...)"""
+        src, rcv = _f64(src), _f64(rcv)
+        sx, sz, rx, rz = _f64(src[:, 0].copy()), _f64(src[:, 1].copy()), _f64(rcv[:, 0].copy()), _f64(rcv[:, 1].copy())
+        vp = C.c_void_p
+        self._L.mct_session_set_fm2d.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(mct_fm2d_opts)]
+        _check(self._L.mct_session_set_fm2d(self._h, sx.ctypes.data, sz.ctypes.data, len(src), rx.ctypes.data, rz.ctypes.data, len(rcv),
+                                            C.byref(opts)))
+
+    def likelihood_fm2d(self, pending=False, snoise0=None, snoise1=None, want_arrays=False):
+        """surf_likelihood with curved rays (fast marching) on the resident maps: dict(like, misfit, unweighted_misfit[, ...])."""
+        out = np.zeros(3)
+        n0 = None if snoise0 is None else _f64(snoise0)
+        n1 = None if snoise1 is None else _f64(snoise1)
+        pt = np.zeros((len(self.freqs), self._nrr)) if want_arrays else None
+        sg = np.zeros((len(self.freqs), self._nrr)) if want_arrays else None
+        vp = C.c_void_p
+        self._L.mct_session_likelihood_fm2d.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+        rc = _check(self._L.mct_session_likelihood_fm2d(self._h, 1 if pending else 0, _ptr(n0), _ptr(n1), out.ctypes.data, _ptr(pt), _ptr(sg)),
+                    allow=(MCT_E_ZERO_NOISE,))
+        return dict(like=out[0], misfit=out[1], unweighted_misfit=out[2], phase_time=pt, sigma=sg, rc=rc)
+
     def stat_accumulate(self):
         self._L.mct_session_stat_accumulate.argtypes = [C.c_void_p]
         _check(self._L.mct_session_stat_accumulate(self._h))

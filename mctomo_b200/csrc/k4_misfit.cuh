@@ -99,7 +99,7 @@ int misfit_set_data(MisfitBufs& m, int nrr, int np, int sigdep, int nrays_total,
 
 // d_time (nrr,np) on the device -> out[3] (host), optionally sigma (host).  One synchronisation.
 int misfit_run(MisfitBufs& m, const double* d_time, const double* snoise0, const double* snoise1, double out[3], double* sigma,
-               cudaStream_t st) {
+               cudaStream_t st, const double* d_srdist = nullptr /* like%srdist on the device instead of the resident copy */) {
   if (!m.have) return fail(MCT_E_INVALID_ARG, "misfit: no data set");
   if (m.sigdep != 0 && (!snoise0 || !snoise1)) return fail(MCT_E_INVALID_ARG, "misfit: sigdep /= 0 needs snoise0 and snoise1");
   const long long n = (long long)m.nrr * m.np;
@@ -113,7 +113,7 @@ int misfit_run(MisfitBufs& m, const double* d_time, const double* snoise0, const
     ProfScope ps(2, st);
     misfit_terms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_time, m.nrr, m.np, m.sigdep, (const double*)m.ttime.p,
                                                                      (const int32_t*)m.raystat.p, (const double*)m.snoise.p,
-                                                                     (const double*)m.srdist.p, (double*)m.sigma.p, (double*)m.terms.p, flag);
+                                                                     d_srdist ? d_srdist : (const double*)m.srdist.p, (double*)m.sigma.p, (double*)m.terms.p, flag);
     misfit_reduce_kernel<<<1, 32, 0, st>>>((const double*)m.sigma.p, (const double*)m.terms.p, (const int32_t*)m.raystat.p, m.nrr, m.np,
                                            m.nrays_total, (double*)m.out.p);
   }

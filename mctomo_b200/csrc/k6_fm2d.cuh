@@ -662,6 +662,96 @@ int mct_fm2d_stats(int64_t out2[2]) {
 
 } // extern "C"
 
+// ---- session: the curved-ray likelihood of surf_likelihood on resident maps --------------------------------------------
+// like%vel(np, ny+2, nx+2) from the session's phase map (+ the pending proposal's window): interior = the map, edges
+// replicated (likelihood_surf.F90:259-264; a map kept consistent call after call is exactly the clamped copy).
+__global__ void __launch_bounds__(256) fm2d_pad_kernel(const double* __restrict__ vel, VelOverlay ov, int np, int nx, int ny, double* __restrict__ out) {
+  const long long n = (long long)np * (ny + 2) * (nx + 2);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t % np);
+    const long long r = t / np;
+    int iy = (int)(r % (ny + 2)), ix = (int)(r / (ny + 2));
+    iy = iy < 1 ? 1 : (iy > ny ? ny : iy);
+    ix = ix < 1 ? 1 : (ix > nx ? nx : ix);
+    out[t] = vel_at(vel, ov, np, p, ny, iy, ix);
+  }
+}
+
+extern "C" {
+
+// Sources, receivers and the fast-marching settings of a session (made resident once, like the straight rays).
+int mct_session_set_fm2d(mct_session* s, const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc,
+                         const mct_fm2d_opts* o) {
+  NEED_INIT();
+  if (!s || !src_x || !src_z || !rcv_x || !rcv_z) return fail(MCT_E_INVALID_ARG, "session_set_fm2d: NULL pointer");
+  int rc;
+  if ((rc = fm2d_check(nsrc, nrc, s->np, s->gr.nx, s->gr.ny, s->gr.dx, s->gr.dy, o))) return rc;
+  if (s->nout != s->np) return fail(MCT_E_INVALID_ARG, "session_set_fm2d: needs a single-mode session");
+  cudaStream_t st = g.stream;
+  if ((rc = ensure(s->f_geo, 8 * (size_t)(2 * nsrc + 2 * nrc)))) return rc;
+  double* geo = (double*)s->f_geo.p;
+  CK(cudaMemcpyAsync(geo, src_x, 8 * (size_t)nsrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(geo + nsrc, src_z, 8 * (size_t)nsrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(geo + 2 * nsrc, rcv_x, 8 * (size_t)nrc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(geo + 2 * nsrc + nrc, rcv_z, 8 * (size_t)nrc, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  s->f_nsrc = nsrc; s->f_nrc = nrc;
+  s->f_opt_i[0] = o->gridx; s->f_opt_i[1] = o->gridy; s->f_opt_i[2] = o->sgref; s->f_opt_i[3] = o->sgdic; s->f_opt_i[4] = o->sgext; s->f_opt_i[5] = o->order;
+  s->f_band = o->band;
+  s->f_have = true;
+  return MCT_OK;
+}
+
+// surf_likelihood for phase-velocity data with curved rays (settings%isStraight == 0, phaseGroup == 0,
+// likelihood_surf.F90:244-336,356-404) on the session's resident maps: like%vel assembled on the device, every
+// (period, source) marched in one launch, like%srdist = like%phaseTime, noise level and the Gaussian sums.
+// pending = 0: the current model, 1: the pending proposal.  phase_time, sigma: optional host outputs (nrr, np).
+int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snoise0, const double* snoise1, double out[3], double* phase_time,
+                                double* sigma) {
+  NEED_INIT();
+  if (!s || !out) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: NULL pointer");
+  if (!s->f_have) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: no sources / receivers (call mct_session_set_fm2d first)");
+  if (!s->mf.have) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: no data (call mct_session_set_data first)");
+  if (s->opt.phaseGroup == 1) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: group-velocity data need the ray geometry (rpaths), which stays on the host");
+  const int nrr = s->f_nsrc * s->f_nrc;
+  if (s->mf.nrr != nrr) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: the data hold %d source-receiver pairs, the geometry %d", s->mf.nrr, nrr);
+  VelOverlay ov;
+  int rc = session_overlay(s, pending, ov);
+  if (rc) return rc;
+  cudaStream_t st = g.stream;
+  const int np = s->np, nx = s->gr.nx, ny = s->gr.ny;
+  const size_t npad = (size_t)np * (ny + 2) * (nx + 2);
+  if ((rc = ensure(s->f_vel, 8 * npad))) return rc;
+  if ((rc = ensure(s->f_err, 4 * (size_t)np * s->f_nsrc))) return rc;
+  if ((rc = ensure(s->time, 8 * (size_t)np * nrr))) return rc;
+  {
+    ProfScope ps(2, st);
+    fm2d_pad_kernel<<<grid_blocks((long long)npad, 256, 8), 256, 0, st>>>(session_time_map(s), ov, np, nx, ny, (double*)s->f_vel.p);
+  }
+  g.host_stats.n_launches += 1;
+  CK(cudaMemsetAsync(s->time.p, 0, 8 * (size_t)np * nrr, st)); // pairs without data: never read by the misfit
+  mct_fm2d_opts o{s->f_opt_i[0], s->f_opt_i[1], s->f_opt_i[2], s->f_opt_i[3], s->f_opt_i[4], s->f_opt_i[5], s->f_band};
+  FmParams P;
+  fm2d_fill(P, s->f_nsrc, s->f_nrc, np, nx, ny, s->gr.xmin, s->gr.ymin, s->gr.dx, s->gr.dy, &o);
+  const double* geo = (const double*)s->f_geo.p;
+  P.scx = geo; P.scz = geo + s->f_nsrc; P.rcx = geo + 2 * s->f_nsrc; P.rcz = geo + 2 * s->f_nsrc + s->f_nrc;
+  P.srs = (const int32_t*)s->mf.raystat.p; P.srs_ms = 2LL * nrr; // dat%raystat(nrr, 2, np): [.,1,period]
+  P.velv = (const double*)s->f_vel.p; P.vel_es = np; P.vel_ms = 1;  // like%vel(np, ny+2, nx+2) in place
+  P.ttime = (double*)s->time.p; P.err = (int32_t*)s->f_err.p;
+  if ((rc = fm2d_launch(P, st))) return rc;
+  s->time_nrays = nrr;
+  std::vector<int32_t> herr((size_t)np * s->f_nsrc);
+  CK(cudaMemcpyAsync(herr.data(), s->f_err.p, 4 * herr.size(), cudaMemcpyDeviceToHost, st));
+  if (phase_time) CK(cudaMemcpyAsync(phase_time, s->time.p, 8 * (size_t)np * nrr, cudaMemcpyDeviceToHost, st));
+  rc = misfit_run(s->mf, (const double*)s->time.p, snoise0, snoise1, out, sigma, st, (const double*)s->time.p); // srdist = phaseTime (:327-333)
+  for (size_t p = 0; p < herr.size(); ++p)
+    if (herr[p]) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: period %d, source %d: %s", (int)(p / s->f_nsrc) + 1, (int)(p % s->f_nsrc) + 1,
+                             herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" : "receiver outside the model");
+  return rc;
+}
+
+} // extern "C"
+
 namespace {
 void release_fm2d_globals() {
   DevBuf* bufs[] = {&fm_veln, &fm_scratch, &fm_err, &fm_geo, &fm_srs, &fm_vel, &fm_tt};

@@ -35,6 +35,12 @@ struct mct_session {
   int time_nrays = 0;
   MisfitBufs mf;                      // observed data + misfit work arrays
   DevBuf acc;                         // stat_rti accumulators: aveS, stdS, aveP, stdP, (nz,ny,nx) each
+  // curved-ray mode (settings%isStraight == 0, phase-velocity data): sources / receivers, the padded map like%vel, per-problem status
+  DevBuf f_geo, f_vel, f_err;
+  int f_nsrc = 0, f_nrc = 0;
+  int32_t f_opt_i[6] = {1, 1, 1, 4, 8, 1}; // gridx, gridy, sgref, sgdic, sgext, order
+  double f_band = 0.5;
+  bool f_have = false;
   long long nacc = 0;
   bool have_model = false, pending = false;
   bool maps_valid = false;            // the resident maps belong to a model check_model accepted
@@ -98,7 +104,8 @@ __global__ void __launch_bounds__(256) fill_kernel(double* p, long long n, doubl
 void session_release(mct_session* s) {
   DevBuf* bufs[] = {&s->vp, &s->vs, &s->rho, &s->sites, &s->pvel, &s->gvel, &s->ierr, &s->b_vp, &s->b_vs, &s->b_rho,
                     &s->b_sites, &s->w_pvel, &s->w_gvel, &s->w_ierr, &s->flags, &s->r_pts, &s->r_off, &s->time, &s->acc,
-                    &s->mf.ttime, &s->mf.raystat, &s->mf.srdist, &s->mf.snoise, &s->mf.sigma, &s->mf.terms, &s->mf.out, &s->mf.time};
+                    &s->mf.ttime, &s->mf.raystat, &s->mf.srdist, &s->mf.snoise, &s->mf.sigma, &s->mf.terms, &s->mf.out, &s->mf.time,
+                    &s->f_geo, &s->f_vel, &s->f_err};
   for (DevBuf* b : bufs) release(*b);
 }
 

@@ -348,3 +348,71 @@ def test_shutdown_and_reinit(mct):
     mct.init(0)
     b = mct.forward_eval(pts, par, grid, freqs, opts)
     assert np.array_equal(a["pvel"], b["pvel"]) and np.array_equal(a["ierr"], b["ierr"])
+
+
+@pytest.mark.parametrize("sigdep", [0, 1])
+def test_session_likelihood_curved_rays_fm2d(mct, sigdep):
+    """surf_likelihood for phase-velocity data with curved rays (likelihood_surf.F90:244-336,356-404) entirely on the
+    resident maps: like%vel assembled on the device, every (period, source) marched by the fast-marching kernel,
+    like%srdist = like%phaseTime, sigma and the Gaussian sums -- for the current model and for a pending proposal --
+    bit-identical to the composition of the restatements (assemble_vel -> fm2d -> misfit)."""
+    grid = synth.make_grid(31, 27, 20)
+    freqs = synth.freqs(4)
+    np_ = len(freqs)
+    S = mct.Session(grid, freqs, disp_opts(raylov=1, phaseGroup=0, nmodes=0))
+    pts, par = synth.generate_model(grid, 40, 21)
+    r0 = S.set_model(pts, par)
+    rng = np.random.default_rng(8)
+    nsrc, nrc = 3, 5
+    src = rng.uniform(-4.5, 4.5, (nsrc, 2))
+    rcv = rng.uniform(-4.5, 4.5, (nrc, 2))
+    nrr = nsrc * nrc
+    raystat = np.zeros((np_, 2, nrr), np.int32)
+    raystat[:, 0, :] = rng.uniform(size=(np_, nrr)) < 0.8
+    raystat[1, 0, nrc:2 * nrc] = 0          # period 2: the second source carries no data and is not marched
+    ttime = np.zeros((np_, 3, nrr))
+    ttime[:, 0, :] = rng.uniform(1.0, 4.0, (np_, nrr))
+    ttime[:, 1, :] = rng.uniform(0.05, 0.3, (np_, nrr))
+    sn0, sn1 = rng.uniform(0.01, 0.05, np_), rng.uniform(0.02, 0.1, np_)
+    S.set_data(ttime, raystat, sigdep=sigdep, srdist=np.zeros((np_, nrr)) if sigdep else None)
+    S.set_fm2d(src, rcv, mct.fm2d_opts(sgdic=3, sgext=5))
+    kw = dict(snoise0=sn0, snoise1=sn1) if sigdep else {}
+
+    def ref(maps):
+        vel = np.zeros((grid.nx + 2, grid.ny + 2, np_))
+        orc.assemble_vel(maps, np_, grid.nx, grid.ny, (1, grid.nx, 1, grid.ny), vel)
+        t = np.zeros((np_, nrr))
+        for m in range(np_):
+            srs = raystat[m, 0].reshape(nsrc, nrc)
+            err, tt, _, _ = orc.fm2d_times(src, rcv, srs, np.ascontiguousarray(vel[:, :, m]), grid.xmin, grid.ymin, grid.dx, grid.dy, sgdl=3, sgs=5)
+            assert err == 0
+            t[m] = np.where(srs == 1, tt, 0.0).ravel()
+        return t, orc.surf_misfit(t, ttime, raystat, sigdep=sigdep, srdist=t, **kw)
+
+    t_ref, m_ref = ref(r0["pvel"])
+    got = S.likelihood_fm2d(want_arrays=True, **kw)
+    assert np.array_equal(got["phase_time"], t_ref), np.abs(got["phase_time"] - t_ref).max()
+    assert np.array_equal(got["sigma"], m_ref["sigma"])
+    for k in ("like", "misfit", "unweighted_misfit"):
+        assert got[k] == m_ref[k], k
+    # a pending proposal: evaluated before it is accepted or rejected
+    pts2 = pts.copy()
+    pts2[5] += [0.9, -0.6, 0.5]
+    pr = S.propose(pts2, par, np.array([-5.0, -5.0, 0.0, 5.0, 5.0, 12.0]))
+    assert pr["model_invalid"] == 0
+    full = mct.forward_eval(pts2, par, grid, freqs, disp_opts(raylov=1, phaseGroup=0, nmodes=0))
+    t2, m2 = ref(full["pvel"])
+    got2 = S.likelihood_fm2d(pending=True, want_arrays=True, **kw)
+    assert np.array_equal(got2["phase_time"], t2) and got2["like"] == m2["like"] and got2["misfit"] == m2["misfit"]
+    assert not np.array_equal(t2, t_ref)
+    S.reject()
+    assert S.likelihood_fm2d(**kw)["like"] == m_ref["like"]
+    # group-velocity data need ray lengths: refused, not approximated
+    Sg = mct.Session(grid, freqs, disp_opts(raylov=1, phaseGroup=1, nmodes=0))
+    Sg.set_model(pts, par)
+    Sg.set_data(ttime, raystat, sigdep=0)
+    Sg.set_fm2d(src, rcv, mct.fm2d_opts())
+    with pytest.raises(mct.MctError):
+        Sg.likelihood_fm2d()
+    Sg.close()
+    S.close()
