@@ -319,6 +319,18 @@ typedef struct {
 int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc,
                    const int32_t* srs, const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz,
                    const mct_fm2d_opts* o, double* ttime, double* field);
+/* The same with the ray geometry (uar = 0, group-velocity data): rpaths (fm2d/fm2dray_cartesian.f90:773-1456, cfd = 0).
+ *   srsv (nrc, nsrc, nmaps) int32: dat%raystat(:,2,period), the 1-based slot in which the Fortran stores the pair's ray;
+ *   ray_npts (nrc*nsrc, nmaps): rays(slot)%npoints (0 for a pair without data);
+ *   ray_pts (2, ray_cap, nrc*nsrc, nmaps): rays(slot)%points, receiver first, source last;
+ *   ray_len (nrc*nsrc, nmaps): rays(slot)%length() (like%srdist for group-velocity data);
+ *   crazy (nmaps): crazyray of every period (> 0: surf_likelihood returns like = huge).
+ * A slot holds ray_cap points (8*(nnx+nnz) is ample); a ray still wandering after that many steps is counted as crazy
+ * (the Fortran only gives up after nnx*nnz points). */
+int mct_fm2d_rays(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc,
+                  const int32_t* srs, const int32_t* srsv, const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx,
+                  double dvz, const mct_fm2d_opts* o, double* ttime, int ray_cap, int32_t* ray_npts, double* ray_pts, double* ray_len,
+                  int32_t* crazy);
 /* Device form, asynchronous on `stream`.  d_src_xz = [x(nsrc) | z(nsrc)], d_rcv_xz = [x(nrc) | z(nrc)].  The velocity
  * maps are addressed as d_vel[m*vel_map_stride + (b*(nvz+2) + a)*vel_elem_stride], so the padded map that
  * mct_assemble_vel_dev builds -- the Fortran's like%vel(np, ny+2, nx+2) -- is consumed in place with

@@ -477,6 +477,36 @@ def fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, opts: mct_fm2d_opts, ttim
     return tt, field
 
 
+def fm2d_rays(src, rcv, srs, vel, gox, goz, dvx, dvz, opts: mct_fm2d_opts, srsv=None, cap=None):
+    """modrays with uar = 0: travel times and ray geometry.  Returns dict(ttime (nmaps,nsrc,nrc), npts (nmaps,nrr), pts (nmaps,nrr,cap,2),
+    length (nmaps,nrr), crazy (nmaps))."""
+    L = lib()
+    vp = C.c_void_p
+    L.mct_fm2d_rays.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 4 + \
+                               [C.POINTER(mct_fm2d_opts), vp, C.c_int, vp, vp, vp, vp]
+    src, rcv, vel = _f64(src), _f64(rcv), _f64(vel)
+    nmaps, nsrc, nrc = vel.shape[0], len(src), len(rcv)
+    nrr = nsrc * nrc
+    nvx, nvz = vel.shape[1] - 2, vel.shape[2] - 2
+    sx, sz = _f64(src[:, 0].copy()), _f64(src[:, 1].copy())
+    rx, rz = _f64(rcv[:, 0].copy()), _f64(rcv[:, 1].copy())
+    srs = np.ascontiguousarray(np.broadcast_to(srs, (nmaps, nsrc, nrc)), dtype=np.int32)
+    if srsv is None:
+        srsv = np.arange(1, nrr + 1, dtype=np.int32).reshape(nsrc, nrc)
+    srsv = np.ascontiguousarray(np.broadcast_to(srsv, (nmaps, nsrc, nrc)), dtype=np.int32)
+    if cap is None:
+        cap = 8 * (nvx * opts.gridx + nvz * opts.gridy)
+    tt = np.full((nmaps, nsrc, nrc), -1.0)
+    npts = np.zeros((nmaps, nrr), np.int32)
+    pts = np.zeros((nmaps, nrr, cap, 2))
+    ln = np.zeros((nmaps, nrr))
+    crazy = np.zeros(nmaps, np.int32)
+    _check(L.mct_fm2d_rays(sx.ctypes.data, sz.ctypes.data, nsrc, rx.ctypes.data, rz.ctypes.data, nrc, srs.ctypes.data, srsv.ctypes.data,
+                           vel.ctypes.data, nmaps, nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), tt.ctypes.data, cap, npts.ctypes.data,
+                           pts.ctypes.data, ln.ctypes.data, crazy.ctypes.data))
+    return dict(ttime=tt, npts=npts, pts=pts, length=ln, crazy=crazy)
+
+
 def fm2d_stats():
     L = lib()
     L.mct_fm2d_stats.argtypes = [C.c_void_p]

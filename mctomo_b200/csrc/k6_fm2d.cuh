@@ -33,6 +33,13 @@ struct FmParams {
   double* field;             // optional (nnz, nnx, nsrc, nmaps): ttn of every problem
   int32_t* err;              // per problem: 0, 1 source outside, 2 narrow band overflow, 3 receiver outside
   unsigned long long* counters; // [0] nodes accepted, [1] stencil updates
+  // ray geometry (uar = 0, group-velocity data): null ray_npts = travel times only
+  const int32_t* srsv; long long srsv_ms; // raystat(:,2,period): the 1-based slot of every pair's ray
+  int ray_cap;                 // points per slot
+  int32_t* ray_npts;           // (nrc*nsrc, nmaps), zeroed by the caller
+  double* ray_pts;             // (2, ray_cap, nrc*nsrc, nmaps)
+  double* ray_len;             // (nrc*nsrc, nmaps): T_RAY%length
+  int32_t* crazy;              // per problem: rays that ran out of points (crazyrp)
 };
 
 __device__ __forceinline__ void fm_bspl(double u, double w[5]) {
@@ -349,6 +356,102 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
   }
 }
 
+// rpaths for ONE receiver (fm2dray_cartesian.f90:773-1456, cfd = 0): see oracle/fm2d_ref.c for the quirks that are kept.
+struct FmRayCtx {
+  int asgr, nnx, nnz, nnxr, nnzr, ldr;
+  double gox, goz, dnx, dnz, goxr, gozr, dnxr, dnzr;
+  const double* ttn;     // coarse (nnz, nnx)
+  const double* ttnr;    // refined, leading dimension ldr
+  const int32_t* nstsr;
+};
+__device__ int fm_trace_ray(const FmRayCtx& C, double scx, double scz, double rx, double rz, int cap, double* pts /* [cap][2] */, int* crazy,
+                            int* err) {
+#define RTTN(k, j) C.ttn[(size_t)((j) - 1) * C.nnz + ((k) - 1)]
+#define RTTNR(k, j) C.ttnr[(size_t)((j) - 1) * C.ldr + ((k) - 1)]
+#define RNSTSR(k, j) C.nstsr[(size_t)((j) - 1) * C.ldr + ((k) - 1)]
+  int isx, isz;
+  if (C.asgr == 1) { isx = (int)floor((scx - C.goxr) / C.dnxr) + 1; isz = (int)floor((scz - C.gozr) / C.dnzr) + 1; }
+  else { isx = (int)floor((scx - C.gox) / C.dnx) + 1; isz = (int)floor((scz - C.goz) / C.dnz) + 1; }
+  double dpl = C.dnx, rd1 = C.dnz;
+  if (rd1 < dpl) dpl = rd1;
+  dpl = 0.5 * dpl;
+  int ipx = (int)floor((rx - C.gox) / C.dnx) + 1, ipz = (int)floor((rz - C.goz) / C.dnz) + 1;
+  if (ipx < 1 || ipx >= C.nnx || ipz < 1 || ipz >= C.nnz) { *err = 3; return 0; }
+  int ipxr = 0, ipzr = 0, igref = 0, sw = 0, nrp = 1;
+  double cx = rx, cz = rz; // rgx(j), rgz(j)
+  pts[0] = cx; pts[1] = cz;
+  double sred = (scx - cx) * (scx - cx);
+  sred = sred + (scz - cz) * (scz - cz);
+  sred = sqrt(sred);
+  if (sred < 2.0 * dpl) { pts[2] = scx; pts[3] = scz; nrp = 2; sw = 1; }
+#define FM_IGREF(px, pz) do { \
+    ipxr = (int)floor(((px) - C.goxr) / C.dnxr) + 1; ipzr = (int)floor(((pz) - C.gozr) / C.dnzr) + 1; igref = 1; \
+    if (ipxr < 1 || ipxr >= C.nnxr) igref = 0; \
+    if (ipzr < 1 || ipzr >= C.nnzr) igref = 0; \
+    if (igref == 1) { \
+      if (RNSTSR(ipzr, ipxr) != 0 || RNSTSR(ipzr + 1, ipxr) != 0) igref = 0; \
+      if (RNSTSR(ipzr, ipxr + 1) != 0 || RNSTSR(ipzr + 1, ipxr + 1) != 0) igref = 0; \
+    } } while (0)
+  if (C.asgr == 1) FM_IGREF(rx, rz);
+  if (sw == 0) {
+    if (C.asgr == 1) { if (igref == 1 && ipxr == isx && ipzr == isz) { pts[2] = scx; pts[3] = scz; nrp = 2; sw = 1; } }
+    else if (ipx == isx && ipz == isz) { pts[2] = scx; pts[3] = scz; nrp = 2; sw = 1; }
+  }
+  const int maxrp = C.nnx * C.nnz;
+  for (int j = 1; j <= maxrp; ++j) {
+    if (sw == 1) break;
+    double dtx, dtz;
+    if (igref == 1) {
+      if (ipxr == 1) { dtx = RTTNR(ipzr, ipxr + 1) - RTTNR(ipzr, ipxr); dtx = dtx / C.dnxr; }
+      else if (ipxr == C.nnxr) { dtx = RTTNR(ipzr, ipxr) - RTTNR(ipzr, ipxr - 1); dtx = dtx / C.dnxr; }
+      else { dtx = RTTNR(ipzr, ipxr + 1) - RTTNR(ipzr, ipxr - 1); dtx = dtx / (2.0 * C.dnxr); }
+      if (ipzr == 1) { dtz = RTTNR(ipzr + 1, ipxr) - RTTNR(ipzr, ipxr); dtz = dtz / C.dnzr; }
+      else if (ipzr == C.nnzr) { dtz = RTTNR(ipzr, ipxr) - RTTNR(ipzr - 1, ipxr); dtz = dtz / C.dnzr; }
+      else { dtz = RTTNR(ipzr + 1, ipxr) - RTTNR(ipzr - 1, ipxr); dtz = dtz / (2.0 * C.dnzr); }
+    } else {
+      if (ipx == 1) { dtx = RTTN(ipz, ipx + 1) - RTTN(ipz, ipx); dtx = dtx / C.dnx; }
+      else if (ipx == C.nnx) { dtx = RTTN(ipz, ipx) - RTTN(ipz, ipx - 1); dtx = dtx / C.dnx; }
+      else { dtx = RTTN(ipz, ipx + 1) - RTTN(ipz, ipx - 1); dtx = dtx / (2.0 * C.dnx); }
+      if (ipz == 1) { dtz = RTTN(ipz + 1, ipx) - RTTN(ipz, ipx); dtz = dtz / C.dnz; }
+      else if (C.asgr == 1 && ipzr == C.nnzr) { dtz = RTTN(ipz, ipx) - RTTN(ipz - 1, ipx); dtz = dtz / C.dnz; } // sic: the refined indices (:1092)
+      else { dtz = RTTN(ipz + 1, ipx) - RTTN(ipz - 1, ipx); dtz = dtz / (2.0 * C.dnz); }
+    }
+    if (j + 2 > cap) { (*crazy)++; sw = 1; break; }
+    rd1 = sqrt(dtx * dtx + dtz * dtz);
+    if (!(rd1 > 0.0)) { (*crazy)++; nrp = 1; sw = 1; break; }
+    double nx_ = cx - dpl * dtx / rd1, nz_ = cz - dpl * dtz / rd1; // rgx(j+1), rgz(j+1)
+    if (C.asgr == 1) FM_IGREF(nx_, nz_); else igref = 0;
+    ipx = (int)floor((nx_ - C.gox) / C.dnx) + 1;
+    ipz = (int)floor((nz_ - C.goz) / C.dnz) + 1;
+    sred = (scx - nx_) * (scx - nx_);
+    sred = sred + (scz - nz_) * (scz - nz_);
+    sred = sqrt(sred);
+    sw = 0;
+    bool done = false;
+    if (sred < 2.0 * dpl) done = true;
+    else if (C.asgr == 1) { if (igref == 1 && ipxr == isx && ipzr == isz) done = true; }
+    else if (ipx == isx && ipz == isz) done = true;
+    if (done) {
+      pts[2 * j] = nx_; pts[2 * j + 1] = nz_;
+      pts[2 * (j + 1)] = scx; pts[2 * (j + 1) + 1] = scz;
+      nrp = j + 2; sw = 1;
+      break;
+    }
+    if (ipx < 1) { nx_ = C.gox; ipx = 1; }
+    if (ipx >= C.nnx) { nx_ = C.gox + (C.nnx - 1) * C.dnx; ipx = C.nnx - 1; }
+    if (ipz < 1) { nz_ = C.goz; ipz = 1; }
+    if (ipz >= C.nnz) { nz_ = C.goz + (C.nnz - 1) * C.dnz; ipz = C.nnz - 1; }
+    pts[2 * j] = nx_; pts[2 * j + 1] = nz_;
+    cx = nx_; cz = nz_;
+    if (j == maxrp - 1 && sw == 0) { (*crazy)++; sw = 1; break; }
+  }
+#undef FM_IGREF
+#undef RTTN
+#undef RTTNR
+#undef RNSTSR
+  return nrp;
+}
+
 __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmParams P) {
   const int lane = threadIdx.x;
   const int prob = blockIdx.x;
@@ -393,10 +496,12 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   const double* veln_c = P.veln + (size_t)map * cc;
   const int maxbt0 = (int)floor(P.snb * P.nnx * P.nnz + 0.5); // NINT of a positive value
   unsigned nacc = 0, nupd = 0;
+  int nrnx = 0, nrnz = 0;
+  double drnx = 0, drnz = 0, gorx = 0, gorz = 0;
   if (P.asgr == 1) {
-    const int nrnx = (vnr - vnl) * P.sgdl + 1, nrnz = (vnb - vnt) * P.sgdl + 1;
-    const double drnx = P.dvx / (double)(float)(P.gdx * P.sgdl), drnz = P.dvz / (double)(float)(P.gdz * P.sgdl);
-    const double gorx = P.gox + dnx0 * (vnl - 1), gorz = P.goz + dnz0 * (vnt - 1);
+    nrnx = (vnr - vnl) * P.sgdl + 1; nrnz = (vnb - vnt) * P.sgdl + 1;
+    drnx = P.dvx / (double)(float)(P.gdx * P.sgdl); drnz = P.dvz / (double)(float)(P.gdz * P.sgdl);
+    gorx = P.gox + dnx0 * (vnl - 1); gorz = P.goz + dnz0 * (vnt - 1);
     // bsplrefine (fm2dray_cartesian.f90:598-668): every refined node, the Fortran's (i,j,k,l) recovered from it
     const int nrxr = P.gdx * P.sgdl, nrzr = P.gdz * P.sgdl;
     const int origx = (vnl - 1) * P.sgdl + 1, origz = (vnt - 1) * P.sgdl + 1;
@@ -531,11 +636,42 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     }
     tt[r] = trr;
   }
+  // rpaths (uar = 0): one receiver's ray per lane
+  if (P.ray_npts) {
+    FmRayCtx C;
+    C.asgr = P.asgr; C.nnx = P.nnx; C.nnz = P.nnz; C.nnxr = nrnx; C.nnzr = nrnz; C.ldr = P.ldr;
+    C.gox = P.gox; C.goz = P.goz; C.dnx = dnx0; C.dnz = dnz0; C.goxr = gorx; C.gozr = gorz; C.dnxr = drnx; C.dnzr = drnz;
+    C.ttn = ttn_c; C.ttnr = ttn_r; C.nstsr = nsts_r;
+    const int nrr = P.nrc * P.nsrc;
+    const int32_t* srsv = P.srsv + (size_t)map * P.srsv_ms + (size_t)isrc * P.nrc;
+    int crazy = 0;
+    for (int r = lane; r < P.nrc; r += 32) {
+      if (srs[r] == 0) continue;
+      const int slot = srsv[r] - 1;
+      if (slot < 0 || slot >= nrr) { P.err[prob] = 5; continue; }
+      const size_t gs = (size_t)map * nrr + slot;
+      double* pts = P.ray_pts + gs * (size_t)P.ray_cap * 2;
+      int e = 0;
+      const int n = fm_trace_ray(C, x, z, P.rcx[r], P.rcz[r], P.ray_cap, pts, &crazy, &e);
+      if (e) { P.err[prob] = e; continue; }
+      P.ray_npts[gs] = n;
+      double len = 0;
+      for (int k = 1; k < n; ++k) {
+        const double ex = pts[2 * k] - pts[2 * (k - 1)], ez = pts[2 * k + 1] - pts[2 * (k - 1) + 1];
+        const double d = ex * ex + ez * ez;
+        len = len + sqrt(d);
+      }
+      P.ray_len[gs] = len;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) crazy += __shfl_xor_sync(0xffffffffu, crazy, o);
+    if (lane == 0) P.crazy[prob] = crazy;
+  }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 namespace {
-DevBuf fm_veln, fm_scratch, fm_err, fm_geo, fm_srs, fm_vel, fm_tt;
+DevBuf fm_veln, fm_scratch, fm_err, fm_geo, fm_srs, fm_vel, fm_tt, fm_rays;
 
 int fm2d_launch(FmParams& P, cudaStream_t st) {
   int rc;
@@ -598,21 +734,23 @@ int mct_fm2d_times_dev(const double* d_src_xz, int nsrc, const double* d_rcv_xz,
   return fm2d_launch(P, stream ? (cudaStream_t)stream : g.stream);
 }
 
-int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc, const int32_t* srs,
-                   const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz, const mct_fm2d_opts* o,
-                   double* ttime, double* field) {
-  NEED_INIT();
+static int fm2d_host(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc, const int32_t* srs,
+                     const int32_t* srsv, const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz,
+                     const mct_fm2d_opts* o, double* ttime, double* field, int ray_cap, int32_t* ray_npts, double* ray_pts, double* ray_len,
+                     int32_t* crazy) {
   int rc;
   if ((rc = fm2d_check(nsrc, nrc, nmaps, nvx, nvz, dvx, dvz, o))) return rc;
   if (!src_x || !src_z || !rcv_x || !rcv_z || !srs || !vel || !ttime) return fail(MCT_E_INVALID_ARG, "fm2d: NULL pointer");
+  const bool rays = ray_npts != nullptr;
+  if (rays && (!srsv || !ray_pts || !ray_len || !crazy || ray_cap < 4)) return fail(MCT_E_INVALID_ARG, "fm2d_rays: bad ray arguments");
   cudaStream_t st = g.stream;
   const size_t nv = (size_t)(nvz + 2) * (nvx + 2) * nmaps, nt = (size_t)nrc * nsrc * nmaps;
   const int nprob = nmaps * nsrc;
   if ((rc = ensure(fm_geo, 8 * (size_t)(2 * nsrc + 2 * nrc)))) return rc;
-  if ((rc = ensure(fm_srs, 4 * nt))) return rc;
+  if ((rc = ensure(fm_srs, 4 * nt * (rays ? 2 : 1)))) return rc;
   if ((rc = ensure(fm_vel, 8 * nv))) return rc;
   if ((rc = ensure(fm_tt, 8 * nt))) return rc;
-  if ((rc = ensure(fm_err, 4 * (size_t)nprob))) return rc;
+  if ((rc = ensure(fm_err, 4 * (size_t)nprob * 2))) return rc;
   double* geo = (double*)fm_geo.p;
   CK(cudaMemcpyAsync(geo, src_x, 8 * (size_t)nsrc, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(geo + nsrc, src_z, 8 * (size_t)nsrc, cudaMemcpyHostToDevice, st));
@@ -627,6 +765,16 @@ int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const dou
   P.srs = (const int32_t*)fm_srs.p; P.srs_ms = (long long)nrc * nsrc;
   P.velv = (const double*)fm_vel.p; P.vel_es = 1; P.vel_ms = (long long)(nvz + 2) * (nvx + 2);
   P.ttime = (double*)fm_tt.p; P.err = (int32_t*)fm_err.p;
+  if (rays) {
+    if ((rc = ensure(fm_rays, 8 * nt * ((size_t)ray_cap * 2 + 1) + 4 * nt))) return rc;
+    CK(cudaMemcpyAsync((int32_t*)fm_srs.p + nt, srsv, 4 * nt, cudaMemcpyHostToDevice, st));
+    P.srsv = (const int32_t*)fm_srs.p + nt; P.srsv_ms = (long long)nrc * nsrc;
+    P.ray_cap = ray_cap;
+    P.ray_pts = (double*)fm_rays.p; P.ray_len = P.ray_pts + nt * (size_t)ray_cap * 2; P.ray_npts = (int32_t*)(P.ray_len + nt);
+    P.crazy = (int32_t*)fm_err.p + nprob;
+    CK(cudaMemsetAsync(P.ray_len, 0, 8 * nt + 4 * nt, st)); // pairs without data: no ray (npoints = 0, length 0)
+    CK(cudaMemsetAsync(P.crazy, 0, 4 * (size_t)nprob, st));
+  }
   if (field) {
     const size_t nf = (size_t)((nvx - 1) * o->gridx + 1) * ((nvz - 1) * o->gridy + 1) * nprob;
     void* pf = nullptr;
@@ -634,20 +782,44 @@ int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const dou
     P.field = (double*)pf;
   }
   rc = fm2d_launch(P, st);
-  std::vector<int32_t> herr((size_t)nprob);
+  std::vector<int32_t> herr((size_t)nprob * 2, 0);
   if (!rc) {
     cudaMemcpyAsync(ttime, fm_tt.p, 8 * nt, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(herr.data(), fm_err.p, 4 * (size_t)nprob, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(herr.data(), fm_err.p, 4 * (size_t)nprob * (rays ? 2 : 1), cudaMemcpyDeviceToHost, st);
     if (field) cudaMemcpyAsync(field, P.field, 8 * (size_t)P.nnx * P.nnz * nprob, cudaMemcpyDeviceToHost, st);
+    if (rays) {
+      cudaMemcpyAsync(ray_pts, P.ray_pts, 8 * nt * (size_t)ray_cap * 2, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(ray_len, P.ray_len, 8 * nt, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(ray_npts, P.ray_npts, 4 * nt, cudaMemcpyDeviceToHost, st);
+    }
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (P.field) cudaFree(P.field);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(MCT_E_CUDA, "fm2d: %s", cudaGetErrorString(e));
+  if (rays) for (int m = 0; m < nmaps; ++m) { crazy[m] = 0; for (int i = 0; i < nsrc; ++i) crazy[m] += herr[(size_t)nprob + (size_t)m * nsrc + i]; }
   for (int p = 0; p < nprob; ++p)
     if (herr[p]) return fail(MCT_E_INVALID_ARG, "fm2d: problem %d (period %d, source %d): %s", p, p / nsrc + 1, p % nsrc + 1,
-                             herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" : "receiver outside the model");
+                             herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" :
+                             herr[p] == 3 ? "receiver outside the model" : "ray slot (raystat(:,2,:)) outside 1..nrev*nsrc");
   return MCT_OK;
+}
+
+int mct_fm2d_times(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc, const int32_t* srs,
+                   const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz, const mct_fm2d_opts* o,
+                   double* ttime, double* field) {
+  NEED_INIT();
+  return fm2d_host(src_x, src_z, nsrc, rcv_x, rcv_z, nrc, srs, nullptr, vel, nmaps, nvx, nvz, gox, goz, dvx, dvz, o, ttime, field, 0, nullptr,
+                   nullptr, nullptr, nullptr);
+}
+
+int mct_fm2d_rays(const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z, int nrc, const int32_t* srs,
+                  const int32_t* srsv, const double* vel, int nmaps, int nvx, int nvz, double gox, double goz, double dvx, double dvz,
+                  const mct_fm2d_opts* o, double* ttime, int ray_cap, int32_t* ray_npts, double* ray_pts, double* ray_len, int32_t* crazy) {
+  NEED_INIT();
+  if (!ray_npts) return fail(MCT_E_INVALID_ARG, "fm2d_rays: NULL ray_npts");
+  return fm2d_host(src_x, src_z, nsrc, rcv_x, rcv_z, nrc, srs, srsv, vel, nmaps, nvx, nvz, gox, goz, dvx, dvz, o, ttime, nullptr, ray_cap, ray_npts,
+                   ray_pts, ray_len, crazy);
 }
 
 int mct_fm2d_stats(int64_t out2[2]) {
@@ -754,7 +926,7 @@ int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snois
 
 namespace {
 void release_fm2d_globals() {
-  DevBuf* bufs[] = {&fm_veln, &fm_scratch, &fm_err, &fm_geo, &fm_srs, &fm_vel, &fm_tt};
+  DevBuf* bufs[] = {&fm_veln, &fm_scratch, &fm_err, &fm_geo, &fm_srs, &fm_vel, &fm_tt, &fm_rays};
   for (DevBuf* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 } // namespace

@@ -32,6 +32,7 @@ typedef struct {
   int ntr, maxbt;
   size_t cells;           /* allocated nodes of veln / ttn / nsts */
   int64_t n_accept, n_update; /* instrumentation: nodes made alive, fouds calls */
+  int nnxr, nnzr; double goxr, gozr, dnxr, dnzr; /* "Backup refined grid information" (fm2dray_cartesian.f90:374-381) */
   int error;
 } fm_t;
 
@@ -406,6 +407,107 @@ static void srtimes(fm_t* F, double scx, double scz, int csid, int nrc, const do
   }
 }
 
+
+/* rpaths (fm2dray_cartesian.f90:773-1456) with cfd = 0 as the source hard-wires it (the Frechet block is dead code): every
+ * receiver's ray is traced from the receiver towards the source in steps of dpl = half the smaller node spacing along
+ * -grad T, the gradient taken by central (one-sided at the edges) differences at the lower-left node of the cell the point
+ * is in -- of the refined source grid while all four nodes of that refined cell are alive (igref), of the coarse grid
+ * otherwise.  Quirks kept: the coarse branch tests `ipzr == nnzr` (the REFINED indices) for its one-sided z difference
+ * (:1092); receivers in the last cell column/row are refused here (ipx >= nnx) although srtimes accepts them.
+ * Two places where the Fortran's behaviour is undefined are resolved and flagged instead: with asgr = 0 that `ipzr` is
+ * never assigned (taken as "not equal"); a vanishing gradient (0/0) ends the ray as a crazy ray.
+ * ray r of source csid goes to slot srsv(r) - 1: npts[slot], pts[slot*2*cap + 2*k + {0,1}], len[slot] = T_RAY%length. */
+static void rpaths(fm_t* F, int asgr, double scx, double scz, int csid, int nrc, const double* rcx, const double* rcz, const int* srs,
+                   const int* srsv, int nslots, int cap, int* ray_npts, double* ray_pts, double* ray_len, int* crazy) {
+  const int maxrp = F->nnx * F->nnz;
+  double* rgx = malloc(sizeof(double) * (size_t)(maxrp + 3));
+  double* rgz = malloc(sizeof(double) * (size_t)(maxrp + 3));
+  int isx, isz;
+  if (asgr == 1) { isx = (int)floor((scx - F->goxr) / F->dnxr) + 1; isz = (int)floor((scz - F->gozr) / F->dnzr) + 1; }
+  else { isx = (int)floor((scx - F->gox) / F->dnx) + 1; isz = (int)floor((scz - F->goz) / F->dnz) + 1; }
+  double dpl = F->dnx, rd1 = F->dnz;
+  if (rd1 < dpl) dpl = rd1;
+  dpl = 0.5 * dpl;
+  for (int i = 1; i <= nrc; ++i) {
+    if (srs[(size_t)(csid - 1) * nrc + (i - 1)] == 0) continue;
+    int ipx = (int)floor((rcx[i - 1] - F->gox) / F->dnx) + 1;
+    int ipz = (int)floor((rcz[i - 1] - F->goz) / F->dnz) + 1;
+    if (ipx < 1 || ipx >= F->nnx || ipz < 1 || ipz >= F->nnz) { F->error = 3; break; }
+    int ipxr = 0, ipzr = 0, igref = 0, sw = 0, nrp = 1;
+    rgx[1] = rcx[i - 1]; rgz[1] = rcz[i - 1];
+    double sred = (scx - rgx[1]) * (scx - rgx[1]);
+    sred = sred + (scz - rgz[1]) * (scz - rgz[1]);
+    sred = sqrt(sred);
+    if (sred < 2.0 * dpl) { rgx[2] = scx; rgz[2] = scz; nrp = 2; sw = 1; }
+#define IGREF_AT(px, pz) do { \
+      ipxr = (int)floor(((px) - F->goxr) / F->dnxr) + 1; ipzr = (int)floor(((pz) - F->gozr) / F->dnzr) + 1; igref = 1; \
+      if (ipxr < 1 || ipxr >= F->nnxr) igref = 0; \
+      if (ipzr < 1 || ipzr >= F->nnzr) igref = 0; \
+      if (igref == 1) { \
+        if (NSTSR(ipzr, ipxr) != 0 || NSTSR(ipzr + 1, ipxr) != 0) igref = 0; \
+        if (NSTSR(ipzr, ipxr + 1) != 0 || NSTSR(ipzr + 1, ipxr + 1) != 0) igref = 0; \
+      } } while (0)
+    if (asgr == 1) IGREF_AT(rcx[i - 1], rcz[i - 1]); else igref = 0;
+    if (sw == 0) {
+      if (asgr == 1) { if (igref == 1 && ipxr == isx && ipzr == isz) { rgx[2] = scx; rgz[2] = scz; nrp = 2; sw = 1; } }
+      else if (ipx == isx && ipz == isz) { rgx[2] = scx; rgz[2] = scz; nrp = 2; sw = 1; }
+    }
+    for (int j = 1; j <= maxrp; ++j) {
+      if (sw == 1) break;
+      double dtx, dtz;
+      if (igref == 1) {
+        if (ipxr == 1) { dtx = TTNR(ipzr, ipxr + 1) - TTNR(ipzr, ipxr); dtx = dtx / F->dnxr; }
+        else if (ipxr == F->nnxr) { dtx = TTNR(ipzr, ipxr) - TTNR(ipzr, ipxr - 1); dtx = dtx / F->dnxr; }
+        else { dtx = TTNR(ipzr, ipxr + 1) - TTNR(ipzr, ipxr - 1); dtx = dtx / (2.0 * F->dnxr); }
+        if (ipzr == 1) { dtz = TTNR(ipzr + 1, ipxr) - TTNR(ipzr, ipxr); dtz = dtz / F->dnzr; }
+        else if (ipzr == F->nnzr) { dtz = TTNR(ipzr, ipxr) - TTNR(ipzr - 1, ipxr); dtz = dtz / F->dnzr; }
+        else { dtz = TTNR(ipzr + 1, ipxr) - TTNR(ipzr - 1, ipxr); dtz = dtz / (2.0 * F->dnzr); }
+      } else {
+        if (ipx == 1) { dtx = TTN(ipz, ipx + 1) - TTN(ipz, ipx); dtx = dtx / F->dnx; }
+        else if (ipx == F->nnx) { dtx = TTN(ipz, ipx) - TTN(ipz, ipx - 1); dtx = dtx / F->dnx; }
+        else { dtx = TTN(ipz, ipx + 1) - TTN(ipz, ipx - 1); dtx = dtx / (2.0 * F->dnx); }
+        if (ipz == 1) { dtz = TTN(ipz + 1, ipx) - TTN(ipz, ipx); dtz = dtz / F->dnz; }
+        else if (asgr == 1 && ipzr == F->nnzr) { dtz = TTN(ipz, ipx) - TTN(ipz - 1, ipx); dtz = dtz / F->dnz; } /* sic: ipzr, nnzr */
+        else { dtz = TTN(ipz + 1, ipx) - TTN(ipz - 1, ipx); dtz = dtz / (2.0 * F->dnz); }
+      }
+      if (j + 2 > cap) { (*crazy)++; sw = 1; break; } /* output slots hold cap points: a ray still wandering after that many is
+                                                         declared crazy here; the Fortran does so after nnx*nnz points */
+      rd1 = sqrt(dtx * dtx + dtz * dtz);
+      if (!(rd1 > 0.0)) { (*crazy)++; nrp = 1; sw = 1; break; } /* 0/0 in the Fortran */
+      rgx[j + 1] = rgx[j] - dpl * dtx / rd1;
+      rgz[j + 1] = rgz[j] - dpl * dtz / rd1;
+      if (asgr == 1) IGREF_AT(rgx[j + 1], rgz[j + 1]); else igref = 0;
+      ipx = (int)floor((rgx[j + 1] - F->gox) / F->dnx) + 1;
+      ipz = (int)floor((rgz[j + 1] - F->goz) / F->dnz) + 1;
+      sred = (scx - rgx[j + 1]) * (scx - rgx[j + 1]);
+      sred = sred + (scz - rgz[j + 1]) * (scz - rgz[j + 1]);
+      sred = sqrt(sred);
+      sw = 0;
+      if (sred < 2.0 * dpl) { rgx[j + 2] = scx; rgz[j + 2] = scz; nrp = j + 2; sw = 1; break; }
+      if (asgr == 1) { if (igref == 1 && ipxr == isx && ipzr == isz) { rgx[j + 2] = scx; rgz[j + 2] = scz; nrp = j + 2; sw = 1; break; } }
+      else if (ipx == isx && ipz == isz) { rgx[j + 2] = scx; rgz[j + 2] = scz; nrp = j + 2; sw = 1; break; }
+      if (ipx < 1) { rgx[j + 1] = F->gox; ipx = 1; }
+      if (ipx >= F->nnx) { rgx[j + 1] = F->gox + (F->nnx - 1) * F->dnx; ipx = F->nnx - 1; }
+      if (ipz < 1) { rgz[j + 1] = F->goz; ipz = 1; }
+      if (ipz >= F->nnz) { rgz[j + 1] = F->goz + (F->nnz - 1) * F->dnz; ipz = F->nnz - 1; }
+      if (j == maxrp - 1 && sw == 0) { (*crazy)++; sw = 1; break; } /* nrp keeps its last value (1), as in the Fortran */
+    }
+#undef IGREF_AT
+    const int slot = srsv[(size_t)(csid - 1) * nrc + (i - 1)] - 1;
+    if (slot < 0 || slot >= nslots) { F->error = 5; break; }
+    if (nrp > cap) { F->error = 4; break; }
+    ray_npts[slot] = nrp;
+    double len = 0;
+    for (int k = 1; k <= nrp; ++k) {
+      ray_pts[((size_t)slot * cap + (k - 1)) * 2 + 0] = rgx[k];
+      ray_pts[((size_t)slot * cap + (k - 1)) * 2 + 1] = rgz[k];
+      if (k >= 2) { double d = (rgx[k] - rgx[k - 1]) * (rgx[k] - rgx[k - 1]) + (rgz[k] - rgz[k - 1]) * (rgz[k] - rgz[k - 1]); len = len + sqrt(d); }
+    }
+    if (ray_len) ray_len[slot] = len;
+  }
+  free(rgx); free(rgz);
+}
+
 /*
  * modrays for ONE velocity map (one period), travel times only.
  *   scx,scz (nsrc), rcx,rcz (nrc): source / receiver coordinates (x = first grid axis, z = second);
@@ -414,9 +516,10 @@ static void srtimes(fm_t* F, double scx, double scz, int csid, int nrc, const do
  *   ttime (nrc, nsrc) column-major, entries without data untouched; field (optional, nnz*nnx per source) = ttn.
  * Returns 0, or 1 source outside the model, 2 narrow band larger than snb*nnx*nnz, 3 receiver outside the model.
  */
-int orc_fm2d_times(int nsrc, const double* scx, const double* scz, int nrc, const double* rcx, const double* rcz, const int* srs, int nvx,
-                   int nvz, double gox, double goz, double dvx, double dvz, const double* velv, int gdx, int gdz, int asgr, int sgdl, int sgs,
-                   int fom, double snb, double* ttime, double* field, int64_t* counters) {
+static int fm2d_core(int nsrc, const double* scx, const double* scz, int nrc, const double* rcx, const double* rcz, const int* srs, int nvx,
+                     int nvz, double gox, double goz, double dvx, double dvz, const double* velv, int gdx, int gdz, int asgr, int sgdl, int sgs,
+                     int fom, double snb, double* ttime, double* field, int64_t* counters, const int* srsv, int cap, int* ray_npts,
+                     double* ray_pts, double* ray_len, int* crazy) {
   fm_t S, *F = &S;
   memset(F, 0, sizeof S);
   F->nvx = nvx; F->nvz = nvz; F->gdx = gdx; F->gdz = gdz; F->fom = fom; F->sgdl = sgdl;
@@ -477,6 +580,7 @@ int orc_fm2d_times(int nsrc, const double* scx, const double* scz, int nrc, cons
           if (NSTS(idm1, idm2) >= 0) TTN(idm1, idm2) = TTNR(k, l);
         }
       }
+      F->nnxr = F->nnx; F->nnzr = F->nnz; F->goxr = F->gox; F->gozr = F->goz; F->dnxr = F->dnx; F->dnzr = F->dnz;
       F->nnx = nnxb; F->nnz = nnzb; F->dnx = dnxb; F->dnz = dnzb; F->gox = goxb; F->goz = gozb;
       for (int j = 1; j <= F->nnx; ++j) for (int k = 1; k <= F->nnz; ++k) VELN(k, j) = VELNB(k, j);
       for (int k = 1; k <= F->nnx; ++k)
@@ -494,9 +598,27 @@ int orc_fm2d_times(int nsrc, const double* scx, const double* scz, int nrc, cons
     if (F->error) break;
     if (field) for (int j = 1; j <= F->nnx; ++j) for (int k = 1; k <= F->nnz; ++k) field[((size_t)(i - 1) * F->nnx + (j - 1)) * F->nnz + (k - 1)] = TTN(k, j);
     srtimes(F, x, z, i, nrc, rcx, rcz, srs, ttime);
+    if (ray_npts && !F->error) rpaths(F, asgr, x, z, i, nrc, rcx, rcz, srs, srsv, nrc * nsrc, cap, ray_npts, ray_pts, ray_len, crazy); /* uar = 0 */
   }
   if (counters) { counters[0] += F->n_accept; counters[1] += F->n_update; }
   int err = F->error;
   free(F->veln); free(F->velnb); free(F->ttn); free(F->ttnr); free(F->nsts); free(F->nstsr); free(F->bpx); free(F->bpz);
   return err;
+}
+
+int orc_fm2d_times(int nsrc, const double* scx, const double* scz, int nrc, const double* rcx, const double* rcz, const int* srs, int nvx,
+                   int nvz, double gox, double goz, double dvx, double dvz, const double* velv, int gdx, int gdz, int asgr, int sgdl, int sgs,
+                   int fom, double snb, double* ttime, double* field, int64_t* counters) {
+  return fm2d_core(nsrc, scx, scz, nrc, rcx, rcz, srs, nvx, nvz, gox, goz, dvx, dvz, velv, gdx, gdz, asgr, sgdl, sgs, fom, snb, ttime, field,
+                   counters, 0, 0, 0, 0, 0, 0);
+}
+/* The same with uar = 0 (group-velocity data): ray geometry as well.  srsv (nrc, nsrc): raystat(:,2,period), the 1-based ray
+ * slot of every pair; ray_npts[nrc*nsrc] (zeroed by the caller), ray_pts[nrc*nsrc][cap][2], ray_len[nrc*nsrc]; *crazy counts
+ * the rays that ran out of points.  Error 4: a ray longer than cap; 5: a slot outside 1..nrc*nsrc. */
+int orc_fm2d_rays(int nsrc, const double* scx, const double* scz, int nrc, const double* rcx, const double* rcz, const int* srs, const int* srsv,
+                  int nvx, int nvz, double gox, double goz, double dvx, double dvz, const double* velv, int gdx, int gdz, int asgr, int sgdl,
+                  int sgs, int fom, double snb, double* ttime, int cap, int* ray_npts, double* ray_pts, double* ray_len, int* crazy) {
+  *crazy = 0;
+  return fm2d_core(nsrc, scx, scz, nrc, rcx, rcz, srs, nvx, nvz, gox, goz, dvx, dvz, velv, gdx, gdz, asgr, sgdl, sgs, fom, snb, ttime, 0, 0,
+                   srsv, cap, ray_npts, ray_pts, ray_len, crazy);
 }

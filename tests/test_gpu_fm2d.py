@@ -75,3 +75,30 @@ def test_fm2d_errors_are_reported(mct):
         mct.fm2d_times(np.array([[9.0, 0.0]]), RCV[:3] * 0.1, np.ones((1, 3), np.int32), vel, -1.0, -1.0, 0.1, 0.1, o)
     with pytest.raises(RuntimeError):
         mct.fm2d_times(np.array([[0.0, 0.0]]), RCV[:3] * 0.1, np.ones((1, 3), np.int32), vel, -1.0, -1.0, 0.1, 0.1, mct.fm2d_opts(band=0.001))
+
+
+@pytest.mark.parametrize("asgr,fom", [(1, 1), (0, 1), (1, 0)])
+def test_fm2d_ray_geometry_bit_identical(mct, asgr, fom):
+    """rpaths (uar = 0, group-velocity data): every ray's points, point count and length, the crazy-ray count and the travel
+    times equal the restatement's; slots follow raystat(:,2,:); pairs without data get no ray."""
+    vel = _maps(2, 101, 101, 11)
+    rng = np.random.default_rng(4)
+    nsrc, nrc = 5, 12
+    src = rng.uniform(-4.8, 4.8, (nsrc, 2))
+    rcv = rng.uniform(-4.8, 4.8, (nrc, 2))
+    rcv[0] = src[0] + [0.03, 0.02]            # inside the source cell: a two-point ray
+    srs = (rng.uniform(size=(2, nsrc, nrc)) < 0.85).astype(np.int32)
+    srsv = np.stack([rng.permutation(nsrc * nrc).reshape(nsrc, nrc) + 1 for _ in range(2)]).astype(np.int32)
+    o = mct.fm2d_opts(sgref=asgr, order=fom)
+    got = mct.fm2d_rays(src, rcv, srs, vel, -5.0, -5.0, 0.1, 0.1, o, srsv=srsv)
+    cap = got["pts"].shape[2]
+    for m in range(2):
+        err, tt, npts, pts, ln, crazy = orc.fm2d_rays(src, rcv, srs[m], vel[m], -5.0, -5.0, 0.1, 0.1, asgr=asgr, fom=fom, srsv=srsv[m], cap=cap)
+        assert err == 0
+        assert np.array_equal(got["ttime"][m], tt) and np.array_equal(got["npts"][m], npts) and got["crazy"][m] == crazy
+        for s in range(nsrc * nrc):
+            assert np.array_equal(got["pts"][m, s, :npts[s]], pts[s, :npts[s]]), (m, s)
+        assert np.array_equal(got["length"][m], ln)
+        if asgr == 1:  # without source refinement the field around the source is first-order only, its gradient can vanish at a
+            assert (npts[srsv[m][srs[m] == 1] - 1] >= 2).all() and crazy == 0  # node (0/0 in the Fortran): counted as crazy rays
+        assert npts.sum() > 0

@@ -72,3 +72,51 @@ def test_errors_are_reported_not_fatal():
     assert err == 1   # source outside the model: the Fortran STOPs
     err, _, _, _ = orc.fm2d_times(SRC[:1], RCV, np.ones((1, 10), np.int32), vel, X0, Y0, DX, DX, snb=0.001)
     assert err == 2   # narrow band larger than snb*nx*ny: the Fortran overruns btg
+
+
+def test_rays_are_straight_in_a_homogeneous_medium():
+    vel = np.full((NX + 2, NY + 2), 3.0)
+    src, rcv = SRC[:3], RCV[:9]
+    err, tt, npts, pts, ln, crazy = orc.fm2d_rays(src, rcv, np.ones((3, 9), np.int32), vel, X0, Y0, DX, DX)
+    assert err == 0 and crazy == 0
+    d = np.sqrt(((src[:, None, :] - rcv[None, :, :]) ** 2).sum(-1)).ravel()
+    for s in range(27):
+        p = pts[s, :npts[s]]
+        assert np.array_equal(p[0], rcv[s % 9]) and np.array_equal(p[-1], src[s // 9])     # receiver first, source last
+        assert abs(ln[s] - d[s]) < 0.02 * d[s] + 0.11                                    # step = dx/2, last hop up to dx
+        # every point stays close to the straight line
+        a, b = rcv[s % 9], src[s // 9]
+        t = (b - a) / np.linalg.norm(b - a)
+        off = np.abs((p - a) @ np.array([-t[1], t[0]]))
+        assert off.max() < 0.25, (s, off.max())
+        seg = np.linalg.norm(np.diff(p, axis=0), axis=1)
+        assert np.allclose(seg[:-1], 0.05, atol=1e-9)                                     # dpl = half the node spacing
+
+
+def test_rays_in_a_gradient_medium_carry_the_travel_time():
+    g = 0.2
+    yy = Y0 + (np.arange(NY + 2) - 1) * DX
+    vel = np.tile(2 + g * (yy + 5), (NX + 2, 1))
+    src, rcv = SRC[:2], RCV[:9]
+    err, tt, npts, pts, ln, crazy = orc.fm2d_rays(src, rcv, np.ones((2, 9), np.int32), vel, X0, Y0, DX, DX)
+    assert err == 0 and crazy == 0
+    err0, tt0, _, _ = orc.fm2d_times(src, rcv, np.ones((2, 9), np.int32), vel, X0, Y0, DX, DX)
+    assert np.array_equal(tt, tt0)                                                        # the ray tracing does not touch the times
+    for s in range(18):
+        p = pts[s, :npts[s]]
+        mid = 0.5 * (p[1:] + p[:-1])
+        seg = np.linalg.norm(np.diff(p, axis=0), axis=1)
+        t_ray = (seg / (2 + g * (mid[:, 1] + 5))).sum()                                    # slowness integrated along the traced ray
+        assert abs(t_ray - tt.ravel()[s]) < 0.03 * tt.ravel()[s] + 0.02, (s, t_ray, tt.ravel()[s])
+        assert ln[s] >= np.linalg.norm(p[0] - p[-1]) - 1e-9                               # curved: no shorter than the chord
+
+
+def test_ray_slots_follow_raystat_and_pairs_without_data_get_no_ray():
+    vel = np.full((NX + 2, NY + 2), 2.5)
+    srs = np.ones((2, 4), np.int32)
+    srs[1, 2] = 0
+    srsv = np.arange(8, 0, -1, dtype=np.int32).reshape(2, 4)        # reversed slots
+    err, tt, npts, pts, ln, crazy = orc.fm2d_rays(SRC[:2], RCV[:4], srs, vel, X0, Y0, DX, DX, srsv=srsv)
+    assert err == 0
+    assert npts[8 - 7] == 0 and (np.delete(npts, 1) >= 2).all()    # pair (source 2, receiver 3) -> slot 7 - ... stays empty
+    assert np.array_equal(pts[7, 0], RCV[0]) and np.array_equal(pts[0, 0], RCV[3])
