@@ -27,7 +27,7 @@ module m_mctomo_b200
     public :: mctomo_b200_init, mctomo_b200_shutdown
     public :: kdtree_to_grid_b200, surf_dispersion_b200, vs2vp_rho_b200
     ! the fast-marching travel times of every (period, source) in one call (INTEGRATION.md 6)
-    public :: fm2d_times_b200
+    public :: fm2d_times_b200, fm2d_rays_b200
     ! the resident session: one chain's model kept in HBM between proposals (INTEGRATION.md 5a)
     public :: T_B200_SESSION, b200_session_create, b200_session_destroy, b200_session_set_model, b200_session_propose, &
               b200_session_accept, b200_session_reject, b200_session_likelihood, b200_session_stat_rti
@@ -218,6 +218,14 @@ module m_mctomo_b200
             import :: c_int, c_ptr, c_double, mct_fm2d_opts
             type(c_ptr), value    :: src_x, src_z, rcv_x, rcv_z, srs, vel, ttime, field
             integer(c_int), value :: nsrc, nrc, nmaps, nvx, nvz
+            real(c_double), value :: gox, goz, dvx, dvz
+            type(mct_fm2d_opts), intent(in) :: opt
+        end function
+        integer(c_int) function mct_fm2d_rays(src_x, src_z, nsrc, rcv_x, rcv_z, nrc, srs, srsv, vel, nmaps, nvx, nvz, gox, goz, dvx, dvz, &
+                opt, ttime, ray_cap, ray_npts, ray_pts, ray_len, crazy) bind(C, name='mct_fm2d_rays')
+            import :: c_int, c_ptr, c_double, mct_fm2d_opts
+            type(c_ptr), value    :: src_x, src_z, rcv_x, rcv_z, srs, srsv, vel, ttime, ray_npts, ray_pts, ray_len, crazy
+            integer(c_int), value :: nsrc, nrc, nmaps, nvx, nvz, ray_cap
             real(c_double), value :: gox, goz, dvx, dvz
             type(mct_fm2d_opts), intent(in) :: opt
         end function
@@ -464,6 +472,53 @@ contains
                             int(np, c_int), int(grid%nx, c_int), int(grid%ny, c_int), grid%xmin, grid%ymin, grid%dx, grid%dy, o, &
                             c_loc(phaseTime), c_null_ptr)
         if (rc /= 0) call fail('mct_fm2d_times', rc)
+    end subroutine
+
+    ! The same for group-velocity data (settings%phaseGroup == 1, uar = 0): travel times, the rays (phaseRays(:, period), stored
+    ! in the slot dat%raystat(:,2,period) names, as rpaths does) and crazyray(period).  The caller goes on exactly as after
+    ! the Fortran modrays: like%srdist = phaseRays%length(), `any(crazyray > 0)` -> huge, CalGroupTime(like%gvel, ...).
+    subroutine fm2d_rays_b200(src, rev, raystat, grid, vel, gridx, gridy, sgref, sgdic, sgext, order, band, phaseTime, phaseRays, crazyray)
+        use m_fm2d, only : T_RAY
+        real(c_double), dimension(:,:), intent(in) :: src, rev
+        integer(c_int), dimension(:,:,:), intent(in) :: raystat
+        type(T_GRID), intent(in) :: grid
+        real(c_double), dimension(:,:,:), intent(in) :: vel
+        integer, intent(in) :: gridx, gridy, sgref, sgdic, sgext, order
+        real(c_double), intent(in) :: band
+        real(c_double), dimension(:,:,:), intent(inout), target :: phaseTime
+        type(T_RAY), dimension(:,:), intent(inout) :: phaseRays          ! (nrev*nsrc, np)
+        integer, dimension(:), intent(inout) :: crazyray
+
+        real(c_double), allocatable, target :: sx(:), sz(:), rx(:), rz(:), maps(:,:,:), rpts(:,:,:,:), rlen(:,:)
+        integer(c_int), allocatable, target :: srs(:,:), srsv(:,:), rn(:,:), cz(:)
+        type(mct_fm2d_opts) :: o
+        integer(c_int) :: rc, cap
+        integer :: i, n, np, nsrc, nrev, nrr
+
+        nsrc = size(src, 2); nrev = size(rev, 2); np = size(vel, 1); nrr = nrev*nsrc
+        cap = 8 * ((grid%nx - 1)*gridx + 1 + (grid%ny - 1)*gridy + 1)
+        allocate(sx(nsrc), sz(nsrc), rx(nrev), rz(nrev), srs(nrr, np), srsv(nrr, np), maps(size(vel, 2), size(vel, 3), np))
+        allocate(rn(nrr, np), rpts(2, cap, nrr, np), rlen(nrr, np), cz(np))
+        sx = src(1,:); sz = src(2,:); rx = rev(1,:); rz = rev(2,:)
+        srs = raystat(:, 1, :); srsv = raystat(:, 2, :)
+        do i = 1, np
+            maps(:, :, i) = vel(i, :, :)
+        enddo
+        o%gridx = gridx; o%gridy = gridy; o%sgref = sgref; o%sgdic = sgdic; o%sgext = sgext; o%order = order; o%band = band
+        rc = mct_fm2d_rays(c_loc(sx), c_loc(sz), int(nsrc, c_int), c_loc(rx), c_loc(rz), int(nrev, c_int), c_loc(srs), c_loc(srsv), &
+                           c_loc(maps), int(np, c_int), int(grid%nx, c_int), int(grid%ny, c_int), grid%xmin, grid%ymin, grid%dx, grid%dy, &
+                           o, c_loc(phaseTime), cap, c_loc(rn), c_loc(rpts), c_loc(rlen), c_loc(cz))
+        if (rc /= 0) call fail('mct_fm2d_rays', rc)
+        do i = 1, np
+            crazyray(i) = crazyray(i) + cz(i)
+            do n = 1, nrr
+                if (rn(n, i) < 1) cycle
+                if (allocated(phaseRays(n, i)%points)) deallocate(phaseRays(n, i)%points)
+                allocate(phaseRays(n, i)%points(2, rn(n, i)))
+                phaseRays(n, i)%points = rpts(:, 1:rn(n, i), n, i)
+                phaseRays(n, i)%npoints = rn(n, i)
+            enddo
+        enddo
     end subroutine
 
     ! The ierr = 2 columns of a dispersion call, through the reference's own surfmodes (GRT branch).

@@ -454,8 +454,10 @@ int mct_session_likelihood(mct_session* s, int pending, const double* ray_points
  * resident once (mct_session_set_fm2d), then mct_session_likelihood_fm2d assembles like%vel from the resident phase map
  * (+ the pending window), marches every (period, source) (mct_fm2d_times_dev), sets like%srdist = like%phaseTime
  * (likelihood_surf.F90:327-333) and evaluates the misfit: nuclei in (mct_session_propose), three doubles out.
- * Needs mct_session_set_data (raystat decides which sources are marched); group-velocity data are refused (ray lengths
- * need the ray geometry, which stays on the host). */
+ * Needs mct_session_set_data (raystat decides which sources are marched and, for group-velocity data, in which slot a
+ * pair's ray is kept).  A session with phaseGroup == 1 traces the rays as well (uar = 0): a crazy ray gives
+ * out = {huge, 0, 0} as likelihood_surf.F90:338-343, else CalGroupTime integrates the resident group map along the rays
+ * and like%srdist is their length. */
 int mct_session_set_fm2d(mct_session* s, const double* src_x, const double* src_z, int nsrc, const double* rcv_x, const double* rcv_z,
                          int nrc, const mct_fm2d_opts* o);
 int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snoise0, const double* snoise1, double out[3],

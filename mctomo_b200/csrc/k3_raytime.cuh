@@ -67,6 +67,33 @@ __global__ void __launch_bounds__(128) group_times_kernel(const double* __restri
   time[t] = acc;
 }
 
+// The same for rays held in fixed-size slots (the device ray tracer's output, k6_fm2d.cuh): ray t = points
+// pts[t*cap .. t*cap + npts[t] - 1].
+__global__ void __launch_bounds__(128) group_times_slots_kernel(const double* __restrict__ vel, const VelOverlay ov, int np, int nx, int ny,
+                                                                double xmin, double ymin, double dx, double dy, const double* __restrict__ pts,
+                                                                const int32_t* __restrict__ npts, int cap, int nrays, double* __restrict__ time) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)np * nrays) return;
+  const int ip = (int)(t / nrays);
+  const long long a = t * cap, b = a + npts[t];
+  double acc = 0.0;
+  if (b - a >= 2) {
+    double hx = pts[2 * a], hy = pts[2 * a + 1];
+    double vhead = get_velocity_dev(vel, ov, np, ip, nx, ny, xmin, ymin, dx, dy, hx, hy);
+    for (long long n = a + 1; n < b; ++n) {
+      const double qx = pts[2 * n], qy = pts[2 * n + 1];
+      const double ex = qx - hx, ey = qy - hy;
+      double dist = ex * ex + ey * ey;
+      dist = sqrt(dist);
+      const double vtail = get_velocity_dev(vel, ov, np, ip, nx, ny, xmin, ymin, dx, dy, qx, qy);
+      acc = acc + dist * 2.0 / (vhead + vtail);
+      vhead = vtail;
+      hx = qx; hy = qy;
+    }
+  }
+  time[t] = acc;
+}
+
 namespace {
 // rays -> device (packed), validated
 int upload_rays(const double* ray_points, const int64_t* ray_offsets, long long nt, DevBuf& d_pts, DevBuf& d_off, cudaStream_t st) {

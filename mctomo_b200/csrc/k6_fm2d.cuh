@@ -874,34 +874,39 @@ int mct_session_set_fm2d(mct_session* s, const double* src_x, const double* src_
   return MCT_OK;
 }
 
-// surf_likelihood for phase-velocity data with curved rays (settings%isStraight == 0, phaseGroup == 0,
-// likelihood_surf.F90:244-336,356-404) on the session's resident maps: like%vel assembled on the device, every
-// (period, source) marched in one launch, like%srdist = like%phaseTime, noise level and the Gaussian sums.
-// pending = 0: the current model, 1: the pending proposal.  phase_time, sigma: optional host outputs (nrr, np).
+// surf_likelihood with curved rays (settings%isStraight == 0, likelihood_surf.F90:244-404) on the session's resident
+// maps: like%vel assembled on the device from the phase map, every (period, source) marched in one launch; phase-velocity
+// data: like%srdist = like%phaseTime; group-velocity data: the rays are traced as well (uar = 0), any crazy ray makes the
+// likelihood huge, else CalGroupTime integrates like%gvel along them and like%srdist is their length; then the noise
+// level and the Gaussian sums.  pending = 0: the current model, 1: the pending proposal.  phase_time, sigma: optional
+// host outputs (nrr, np).
 int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snoise0, const double* snoise1, double out[3], double* phase_time,
                                 double* sigma) {
   NEED_INIT();
   if (!s || !out) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: NULL pointer");
   if (!s->f_have) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: no sources / receivers (call mct_session_set_fm2d first)");
   if (!s->mf.have) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: no data (call mct_session_set_data first)");
-  if (s->opt.phaseGroup == 1) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: group-velocity data need the ray geometry (rpaths), which stays on the host");
+  const bool group = s->opt.phaseGroup == 1;
   const int nrr = s->f_nsrc * s->f_nrc;
   if (s->mf.nrr != nrr) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: the data hold %d source-receiver pairs, the geometry %d", s->mf.nrr, nrr);
-  VelOverlay ov;
+  VelOverlay ov; // of like%gvel: the group window when phaseGroup == 1, else the phase window
   int rc = session_overlay(s, pending, ov);
   if (rc) return rc;
+  VelOverlay ovp = ov; // of the phase map: rays are always bent by the phase velocity (like%vel = pvel, likelihood_surf.F90:259)
+  if (ov.w) ovp.w = (const double*)s->w_pvel.p;
   cudaStream_t st = g.stream;
   const int np = s->np, nx = s->gr.nx, ny = s->gr.ny;
-  const size_t npad = (size_t)np * (ny + 2) * (nx + 2);
+  const int nprob = np * s->f_nsrc;
+  const size_t npad = (size_t)np * (ny + 2) * (nx + 2), nt = (size_t)np * nrr;
   if ((rc = ensure(s->f_vel, 8 * npad))) return rc;
-  if ((rc = ensure(s->f_err, 4 * (size_t)np * s->f_nsrc))) return rc;
-  if ((rc = ensure(s->time, 8 * (size_t)np * nrr))) return rc;
+  if ((rc = ensure(s->f_err, 4 * (size_t)nprob * 2))) return rc;
+  if ((rc = ensure(s->time, 8 * nt))) return rc;
   {
     ProfScope ps(2, st);
-    fm2d_pad_kernel<<<grid_blocks((long long)npad, 256, 8), 256, 0, st>>>(session_time_map(s), ov, np, nx, ny, (double*)s->f_vel.p);
+    fm2d_pad_kernel<<<grid_blocks((long long)npad, 256, 8), 256, 0, st>>>((const double*)s->pvel.p, ovp, np, nx, ny, (double*)s->f_vel.p);
   }
   g.host_stats.n_launches += 1;
-  CK(cudaMemsetAsync(s->time.p, 0, 8 * (size_t)np * nrr, st)); // pairs without data: never read by the misfit
+  CK(cudaMemsetAsync(s->time.p, 0, 8 * nt, st)); // pairs without data: never read by the misfit
   mct_fm2d_opts o{s->f_opt_i[0], s->f_opt_i[1], s->f_opt_i[2], s->f_opt_i[3], s->f_opt_i[4], s->f_opt_i[5], s->f_band};
   FmParams P;
   fm2d_fill(P, s->f_nsrc, s->f_nrc, np, nx, ny, s->gr.xmin, s->gr.ymin, s->gr.dx, s->gr.dy, &o);
@@ -910,14 +915,44 @@ int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snois
   P.srs = (const int32_t*)s->mf.raystat.p; P.srs_ms = 2LL * nrr; // dat%raystat(nrr, 2, np): [.,1,period]
   P.velv = (const double*)s->f_vel.p; P.vel_es = np; P.vel_ms = 1;  // like%vel(np, ny+2, nx+2) in place
   P.ttime = (double*)s->time.p; P.err = (int32_t*)s->f_err.p;
+  const int cap = 8 * ((nx - 1) * o.gridx + 1 + (ny - 1) * o.gridy + 1);
+  if (group) { // uar = 0: the rays as well (their lengths are like%srdist, CalGroupTime integrates like%gvel along them)
+    if ((rc = ensure(s->f_rays, 8 * nt * ((size_t)cap * 2 + 1) + 4 * nt))) return rc;
+    P.srsv = (const int32_t*)s->mf.raystat.p + nrr; P.srsv_ms = 2LL * nrr; // [.,2,period]
+    P.ray_cap = cap;
+    P.ray_pts = (double*)s->f_rays.p; P.ray_len = P.ray_pts + nt * (size_t)cap * 2; P.ray_npts = (int32_t*)(P.ray_len + nt);
+    P.crazy = (int32_t*)s->f_err.p + nprob;
+    CK(cudaMemsetAsync(P.ray_len, 0, 8 * nt + 4 * nt, st));
+    CK(cudaMemsetAsync(P.crazy, 0, 4 * (size_t)nprob, st));
+  }
   if ((rc = fm2d_launch(P, st))) return rc;
   s->time_nrays = nrr;
-  std::vector<int32_t> herr((size_t)np * s->f_nsrc);
-  CK(cudaMemcpyAsync(herr.data(), s->f_err.p, 4 * herr.size(), cudaMemcpyDeviceToHost, st));
-  if (phase_time) CK(cudaMemcpyAsync(phase_time, s->time.p, 8 * (size_t)np * nrr, cudaMemcpyDeviceToHost, st));
-  rc = misfit_run(s->mf, (const double*)s->time.p, snoise0, snoise1, out, sigma, st, (const double*)s->time.p); // srdist = phaseTime (:327-333)
-  for (size_t p = 0; p < herr.size(); ++p)
-    if (herr[p]) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: period %d, source %d: %s", (int)(p / s->f_nsrc) + 1, (int)(p % s->f_nsrc) + 1,
+  std::vector<int32_t> herr((size_t)nprob * 2, 0);
+  CK(cudaMemcpyAsync(herr.data(), s->f_err.p, 4 * (size_t)nprob * (group ? 2 : 1), cudaMemcpyDeviceToHost, st));
+  const double* d_srdist = (const double*)s->time.p; // like%srdist = like%phaseTime (:327-333)
+  if (group) {
+    CK(cudaStreamSynchronize(st));
+    for (int p = 0; p < nprob; ++p)
+      if (herr[p]) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: period %d, source %d: condition %d", p / s->f_nsrc + 1, p % s->f_nsrc + 1, herr[p]);
+    long long ncrazy = 0;
+    for (int p = 0; p < nprob; ++p) ncrazy += herr[(size_t)nprob + p];
+    if (ncrazy > 0) { // any(crazyray > 0): like%like = huge(like%like), return (likelihood_surf.F90:338-343)
+      out[0] = 1.7976931348623157e308; out[1] = 0.0; out[2] = 0.0;
+      return MCT_OK;
+    }
+    {
+      ProfScope ps(2, st);
+      group_times_slots_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>((const double*)s->gvel.p, ov, np, nx, ny, s->gr.xmin, s->gr.ymin, s->gr.dx,
+                                                                            s->gr.dy, P.ray_pts, P.ray_npts, cap, nrr, (double*)s->time.p);
+    }
+    CK(cudaGetLastError());
+    g.host_stats.n_launches += 1;
+    d_srdist = P.ray_len; // like%srdist = phaseRays%length()
+  }
+  if (phase_time) CK(cudaMemcpyAsync(phase_time, s->time.p, 8 * nt, cudaMemcpyDeviceToHost, st));
+  rc = misfit_run(s->mf, (const double*)s->time.p, snoise0, snoise1, out, sigma, st, d_srdist);
+  for (int p = 0; p < nprob; ++p)
+    if (herr[p]) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: period %d, source %d: %s", p / s->f_nsrc + 1, p % s->f_nsrc + 1,
                              herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" : "receiver outside the model");
   return rc;
 }

@@ -36,7 +36,7 @@ struct mct_session {
   MisfitBufs mf;                      // observed data + misfit work arrays
   DevBuf acc;                         // stat_rti accumulators: aveS, stdS, aveP, stdP, (nz,ny,nx) each
   // curved-ray mode (settings%isStraight == 0, phase-velocity data): sources / receivers, the padded map like%vel, per-problem status
-  DevBuf f_geo, f_vel, f_err;
+  DevBuf f_geo, f_vel, f_err, f_rays;
   int f_nsrc = 0, f_nrc = 0;
   int32_t f_opt_i[6] = {1, 1, 1, 4, 8, 1}; // gridx, gridy, sgref, sgdic, sgext, order
   double f_band = 0.5;
@@ -105,7 +105,7 @@ void session_release(mct_session* s) {
   DevBuf* bufs[] = {&s->vp, &s->vs, &s->rho, &s->sites, &s->pvel, &s->gvel, &s->ierr, &s->b_vp, &s->b_vs, &s->b_rho,
                     &s->b_sites, &s->w_pvel, &s->w_gvel, &s->w_ierr, &s->flags, &s->r_pts, &s->r_off, &s->time, &s->acc,
                     &s->mf.ttime, &s->mf.raystat, &s->mf.srdist, &s->mf.snoise, &s->mf.sigma, &s->mf.terms, &s->mf.out, &s->mf.time,
-                    &s->f_geo, &s->f_vel, &s->f_err};
+                    &s->f_geo, &s->f_vel, &s->f_err, &s->f_rays};
   for (DevBuf* b : bufs) release(*b);
 }
 

@@ -407,12 +407,67 @@ def test_session_likelihood_curved_rays_fm2d(mct, sigdep):
     assert not np.array_equal(t2, t_ref)
     S.reject()
     assert S.likelihood_fm2d(**kw)["like"] == m_ref["like"]
-    # group-velocity data need ray lengths: refused, not approximated
-    Sg = mct.Session(grid, freqs, disp_opts(raylov=1, phaseGroup=1, nmodes=0))
-    Sg.set_model(pts, par)
-    Sg.set_data(ttime, raystat, sigdep=0)
-    Sg.set_fm2d(src, rcv, mct.fm2d_opts())
-    with pytest.raises(mct.MctError):
-        Sg.likelihood_fm2d()
-    Sg.close()
+    S.close()
+
+
+@pytest.mark.parametrize("sigdep", [0, 1])
+def test_session_likelihood_curved_rays_group_velocity(mct, sigdep):
+    """Group-velocity data (uar = 0): rays bent by the PHASE map, traced on the device, CalGroupTime through the GROUP map
+    along them, like%srdist = their lengths (likelihood_surf.F90:259-353) -- against assemble_vel -> fm2d + rpaths ->
+    CalGroupTime -> misfit of the restatements, for the current model and a pending proposal."""
+    grid = synth.make_grid(31, 27, 20)
+    freqs = synth.freqs(3)
+    np_ = len(freqs)
+    opts = disp_opts(raylov=1, phaseGroup=1, nmodes=0)
+    S = mct.Session(grid, freqs, opts)
+    pts, par = synth.generate_model(grid, 40, 21)
+    r0 = S.set_model(pts, par)
+    rng = np.random.default_rng(12)
+    nsrc, nrc = 3, 4
+    src = rng.uniform(-4.3, 4.3, (nsrc, 2))
+    rcv = rng.uniform(-4.3, 4.3, (nrc, 2))
+    nrr = nsrc * nrc
+    raystat = np.zeros((np_, 2, nrr), np.int32)
+    raystat[:, 0, :] = rng.uniform(size=(np_, nrr)) < 0.85
+    raystat[:, 1, :] = np.arange(1, nrr + 1)            # the ray of pair n is kept in slot n, as MCTomo's data files have it
+    ttime = np.zeros((np_, 3, nrr))
+    ttime[:, 0, :] = rng.uniform(1.0, 4.0, (np_, nrr))
+    ttime[:, 1, :] = rng.uniform(0.05, 0.3, (np_, nrr))
+    sn0, sn1 = rng.uniform(0.01, 0.05, np_), rng.uniform(0.02, 0.1, np_)
+    S.set_data(ttime, raystat, sigdep=sigdep, srdist=np.zeros((np_, nrr)) if sigdep else None)
+    S.set_fm2d(src, rcv, mct.fm2d_opts())
+    kw = dict(snoise0=sn0, snoise1=sn1) if sigdep else {}
+
+    def ref(pmap, gmap):
+        vel = np.zeros((grid.nx + 2, grid.ny + 2, np_))
+        orc.assemble_vel(pmap, np_, grid.nx, grid.ny, (1, grid.nx, 1, grid.ny), vel)
+        rp, ro, ln_all = [], [0], np.zeros((np_, nrr))
+        for m in range(np_):
+            srs = raystat[m, 0].reshape(nsrc, nrc)
+            err, tt, npts, rpts, ln, crazy = orc.fm2d_rays(src, rcv, srs, np.ascontiguousarray(vel[:, :, m]), grid.xmin, grid.ymin, grid.dx, grid.dy,
+                                                           srsv=raystat[m, 1].reshape(nsrc, nrc))
+            assert err == 0 and crazy == 0
+            ln_all[m] = ln
+            for s_ in range(nrr):
+                rp.append(rpts[s_, :npts[s_]])
+                ro.append(ro[-1] + npts[s_])
+        t = orc.cal_group_time(gmap, grid, np.concatenate(rp), np.array(ro, np.int64), nrr)
+        return t, ln_all, orc.surf_misfit(t, ttime, raystat, sigdep=sigdep, srdist=ln_all, **kw)
+
+    t_ref, ln_ref, m_ref = ref(r0["pvel"], r0["gvel"])
+    got = S.likelihood_fm2d(want_arrays=True, **kw)
+    assert np.array_equal(got["phase_time"], t_ref), np.abs(got["phase_time"] - t_ref).max()
+    assert np.array_equal(got["sigma"], m_ref["sigma"])
+    for k in ("like", "misfit", "unweighted_misfit"):
+        assert got[k] == m_ref[k], k
+    pts2 = pts.copy()
+    pts2[7] += [-0.8, 0.6, 0.4]
+    pr = S.propose(pts2, par, np.array([-5.0, -5.0, 0.0, 5.0, 5.0, 12.0]))
+    assert pr["model_invalid"] == 0
+    full = mct.forward_eval(pts2, par, grid, freqs, opts)
+    t2, _, m2 = ref(full["pvel"], full["gvel"])
+    got2 = S.likelihood_fm2d(pending=True, want_arrays=True, **kw)
+    assert np.array_equal(got2["phase_time"], t2) and got2["like"] == m2["like"] and got2["misfit"] == m2["misfit"]
+    S.accept()
+    assert S.likelihood_fm2d(**kw)["like"] == m2["like"]
     S.close()
