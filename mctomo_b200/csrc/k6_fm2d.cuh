@@ -82,6 +82,7 @@ struct FmGrid {
   double* ttn;
   int32_t* nsts;
   int32_t* heap; // packed (pz << 16) | px, 1-based
+  double* hkey;  // the travel time of every heap entry, kept beside it: the sift loops compare keys without chasing ttn
   int ntr, maxbt, fom;
   int vnl, vnr, vnt, vnb;
   int error;
@@ -93,56 +94,71 @@ struct FmGrid {
 #define HPX(h) ((h) & 0xffff)
 #define HPZ(h) ((h) >> 16)
 
-__device__ __forceinline__ double fm_heap_t(const FmGrid& G, int pos) { const int h = G.heap[pos]; return FTTN(G, HPZ(h), HPX(h)); }
-__device__ void fm_sift_up(FmGrid& G, int iz, int ix, int tpc) {
-  const double t = FTTN(G, iz, ix);
+// The narrow-band heap (addtree / updtree / downtree of fm2d_ttime.f90), lane 0 only.  Same comparisons in the same
+// order as the Fortran, on a copy of each entry's travel time stored beside the entry; pointers and sizes live in
+// registers (FmHeap is a local of the caller), the heap size is returned.
+struct FmHeap {
+  int32_t* pos; double* key; int32_t* nsts; double* ttn;
+  int ld, ntr, maxbt;
+};
+#define HN(H, h) (H).nsts[(size_t)(HPX(h) - 1) * (H).ld + (HPZ(h) - 1)]
+__device__ __forceinline__ void fm_sift_up(FmHeap& H, int self, double t, int tpc) {
   int tpp = tpc / 2;
   while (tpp > 0) {
-    const int hp = G.heap[tpp];
-    if (t < FTTN(G, HPZ(hp), HPX(hp))) {
-      FNSTS(G, iz, ix) = tpp;
-      FNSTS(G, HPZ(hp), HPX(hp)) = tpc;
-      const int ex = G.heap[tpc];
-      G.heap[tpc] = hp;
-      G.heap[tpp] = ex;
+    const double kp = H.key[tpp];
+    if (t < kp) {
+      const int hp = H.pos[tpp];
+      HN(H, hp) = tpc;
+      H.pos[tpc] = hp; H.key[tpc] = kp;
       tpc = tpp;
       tpp = tpc / 2;
     } else tpp = 0;
   }
+  H.pos[tpc] = self; H.key[tpc] = t;
+  HN(H, self) = tpc;
 }
-__device__ __forceinline__ void fm_addtree(FmGrid& G, int iz, int ix) {
-  if (G.ntr + 1 > G.maxbt) { G.error = 2; return; }
-  G.ntr++;
-  FNSTS(G, iz, ix) = G.ntr;
-  G.heap[G.ntr] = (iz << 16) | ix;
-  fm_sift_up(G, iz, ix, G.ntr);
+__device__ __forceinline__ bool fm_addtree(FmHeap& H, int iz, int ix) { // false: the narrow band is full
+  if (H.ntr + 1 > H.maxbt) return false;
+  H.ntr++;
+  fm_sift_up(H, (iz << 16) | ix, H.ttn[(size_t)(ix - 1) * H.ld + (iz - 1)], H.ntr);
+  return true;
 }
-__device__ __forceinline__ void fm_swap(FmGrid& G, int tpp, int tpc) {
-  const int hp = G.heap[tpp], hc = G.heap[tpc];
-  FNSTS(G, HPZ(hp), HPX(hp)) = tpc;
-  FNSTS(G, HPZ(hc), HPX(hc)) = tpp;
-  G.heap[tpc] = hp;
-  G.heap[tpp] = hc;
+__device__ __forceinline__ void fm_updtree(FmHeap& H, int iz, int ix) {
+  const size_t a = (size_t)(ix - 1) * H.ld + (iz - 1);
+  fm_sift_up(H, (iz << 16) | ix, H.ttn[a], H.nsts[a]);
 }
-__device__ void fm_downtree(FmGrid& G) {
-  if (G.ntr == 1) { G.ntr--; return; }
-  const int hl = G.heap[G.ntr];
-  FNSTS(G, HPZ(hl), HPX(hl)) = 1;
-  G.heap[1] = hl;
-  G.ntr--;
+__device__ __forceinline__ void fm_downtree(FmHeap& H) {
+  if (H.ntr == 1) { H.ntr--; return; }
+  const int self = H.pos[H.ntr];
+  const double t = H.key[H.ntr];
+  H.ntr--;
+  const int ntr = H.ntr;
   int tpp = 1, tpc = 2;
-  while (tpc < G.ntr) {
-    double rd1 = fm_heap_t(G, tpc), rd2 = fm_heap_t(G, tpc + 1);
-    if (rd1 > rd2) tpc = tpc + 1;
-    rd1 = fm_heap_t(G, tpc);
-    rd2 = fm_heap_t(G, tpp);
-    if (rd1 < rd2) { fm_swap(G, tpp, tpc); tpp = tpc; tpc = 2 * tpp; }
-    else tpc = G.ntr + 1;
+  // the entry taken from the end sinks from the root: at each level the smaller child (the left one on a tie) moves up
+  // while it is smaller than the sinking entry -- the Fortran's swaps, without writing the sinking entry at every level
+  while (tpc < ntr) {
+    double kc = H.key[tpc];
+    const double kr = H.key[tpc + 1];
+    if (kc > kr) { tpc = tpc + 1; kc = kr; }
+    if (kc < t) {
+      const int hc = H.pos[tpc];
+      HN(H, hc) = tpp;
+      H.pos[tpp] = hc; H.key[tpp] = kc;
+      tpp = tpc;
+      tpc = 2 * tpp;
+    } else tpc = ntr + 1;
   }
-  if (tpc == G.ntr) {
-    const double rd1 = fm_heap_t(G, tpc), rd2 = fm_heap_t(G, tpp);
-    if (rd1 < rd2) fm_swap(G, tpp, tpc);
+  if (tpc == ntr) {
+    const double kc = H.key[tpc];
+    if (kc < t) {
+      const int hc = H.pos[tpc];
+      HN(H, hc) = tpp;
+      H.pos[tpp] = hc; H.key[tpp] = kc;
+      tpp = tpc;
+    }
   }
+  H.pos[tpp] = self; H.key[tpp] = t;
+  HN(H, self) = tpp;
 }
 __device__ __forceinline__ double fm_qsolve(double a, double b, double c) {
   double rd1 = b * b - 4.0 * a * c;
@@ -263,23 +279,28 @@ __device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3
 }
 // travel (fm2d_ttime.f90:27-136), by the whole warp.  The march order is the heap's, so nodes are accepted one at a time
 // (lane 0 owns the heap); the work per accepted node -- up to four neighbour updates of up to four stencil quadrants each
-// -- is independent (a neighbour being updated is not alive, and the stencils only read alive nodes), so lanes 0..15
-// solve one (neighbour, quadrant) each on the state before the updates, a shuffle takes the minima, and lane 0 writes
-// the times and re-orders the heap in the reference's neighbour order (x-1, x+1, z-1, z+1).
+// -- is independent (a neighbour being updated is not alive, and the stencils only read alive nodes), so lanes 16..31
+// solve one (neighbour, quadrant) each on the state before the updates WHILE lane 0 re-orders the heap after the pop
+// (downtree only moves heap positions, i.e. positive status values, which no stencil distinguishes), a shuffle takes the
+// minima, and lane 0 writes the times and sifts the neighbours in the reference's order (x-1, x+1, z-1, z+1).
 // urg 0/1: nsts must already be -1 everywhere (the caller's lanes fill it).  G lives in shared memory.
 __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, volatile int* sh) {
+  FmHeap H;
+  H.pos = G.heap; H.key = G.hkey; H.nsts = G.nsts; H.ttn = G.ttn; H.ld = G.ld; H.ntr = 0; H.maxbt = G.maxbt;
+  const int nnx = G.nnx, nnz = G.nnz;
+  int error = 0;
+  unsigned n_accept = 0, n_update = 0;
   if (lane == 0) {
     int isx = (int)((scx - G.gox) / G.dnx) + 1;
     int isz = (int)((scz - G.goz) / G.dnz) + 1;
-    if (isx < 1 || isx > G.nnx || isz < 1 || isz > G.nnz) G.error = 1;
+    if (isx < 1 || isx > nnx || isz < 1 || isz > nnz) error = 1;
     else {
-      if (isx == G.nnx) isx--;
-      if (isz == G.nnz) isz--;
-      G.ntr = 0;
+      if (isx == nnx) isx--;
+      if (isz == nnz) isz--;
       if (urg == 2) {
-        for (int i = 1; i <= G.nnx; ++i)
-          for (int j = 1; j <= G.nnz; ++j)
-            if (FNSTS(G, j, i) > 0) fm_addtree(G, j, i);
+        for (int i = 1; i <= nnx && !error; ++i)
+          for (int j = 1; j <= nnz; ++j)
+            if (FNSTS(G, j, i) > 0) { if (!fm_addtree(H, j, i)) { error = 2; break; } }
       } else {
         double vss[3][3];
         for (int i = 1; i <= 2; ++i) for (int j = 1; j <= 2; ++j) vss[i][j] = FVELN(G, isz - 1 + j, isx - 1 + i);
@@ -291,7 +312,7 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
             const double ex = dsx - (i - 1) * G.dnx, ez = dsz - (j - 1) * G.dnz;
             const double ds = sqrt(ex * ex + ez * ez);
             FTTN(G, isz - 1 + j, isx - 1 + i) = 2.0 * ds / (vss[i][j] + vsrc);
-            fm_addtree(G, isz - 1 + j, isx - 1 + i);
+            if (!fm_addtree(H, isz - 1 + j, isx - 1 + i)) error = 2;
           }
       }
     }
@@ -300,37 +321,36 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
   for (;;) {
     if (lane == 0) {
       int go = 0;
-      if (G.ntr > 0 && !G.error) {
-        const int h = G.heap[1];
+      if (H.ntr > 0 && !error) {
+        const int h = H.pos[1];
         const int ix = HPX(h), iz = HPZ(h);
         int swrg = 0;
         if (urg == 1) {
           if (ix == 1 && G.vnl != 1) swrg = 1;
-          if (ix == G.nnx && G.vnr != G.nnx) swrg = 1; // (refined extent against a coarse index, as the Fortran has it)
+          if (ix == nnx && G.vnr != nnx) swrg = 1; // (refined extent against a coarse index, as the Fortran has it)
           if (iz == 1 && G.vnt != 1) swrg = 1;
-          if (iz == G.nnz && G.vnb != G.nnz) swrg = 1;
+          if (iz == nnz && G.vnb != nnz) swrg = 1;
         }
-        FNSTS(G, iz, ix) = 0;
-        if (!swrg) {
-          G.n_accept++;
-          fm_downtree(G);
-          sh[1] = ix; sh[2] = iz;
-          go = 1;
-        }
+        HN(H, h) = 0;
+        if (!swrg) { sh[1] = ix; sh[2] = iz; go = 1; }
       }
       sh[0] = go;
     }
     __syncwarp();
     if (!sh[0]) break;
     const int ix = sh[1], iz = sh[2];
-    // (neighbour n, quadrant q) on lane 4n + q
+    // (neighbour n, quadrant q) on lane 16 + 4n + q; lane 0 sinks the heap's last entry from the root meanwhile
     const int n = (lane >> 2) & 3, q = lane & 3;
     const int nix = n == 0 ? ix - 1 : (n == 1 ? ix + 1 : ix), niz = n == 2 ? iz - 1 : (n == 3 ? iz + 1 : iz);
     int st = 0; // the neighbour's status; 0 = nothing to do (alive or outside)
-    if (nix >= 1 && nix <= G.nnx && niz >= 1 && niz <= G.nnz) st = FNSTS(G, niz, nix);
     double trav = 0;
     bool has = false;
-    if (lane < 16 && st != 0) has = fm_quadrant(G, niz, nix, (q >> 1) ? 1 : -1, (q & 1) ? 1 : -1, &trav);
+    if (lane == 0) { n_accept++; fm_downtree(H); }
+    else if (lane >= 16) {
+      if (nix >= 1 && nix <= nnx && niz >= 1 && niz <= nnz) st = FNSTS(G, niz, nix);
+      if (st != 0) has = fm_quadrant(G, niz, nix, (q >> 1) ? 1 : -1, (q & 1) ? 1 : -1, &trav);
+    }
+    __syncwarp(); // every stencil has read the state before any update; the heap is in order again
     // minimum of the quadrants that have a solution
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
@@ -339,21 +359,22 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
       if (oh && (!has || ot < trav)) trav = ot;
       has = has || oh;
     }
-    __syncwarp(); // every stencil has read the state before any update
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const double tm = __shfl_sync(0xffffffffu, trav, 4 * m);
-      const int sm = __shfl_sync(0xffffffffu, st, 4 * m);
-      const bool hm = __shfl_sync(0xffffffffu, has ? 1 : 0, 4 * m) != 0;
-      if (lane == 0 && sm != 0) {
+      const double tm = __shfl_sync(0xffffffffu, trav, 16 + 4 * m);
+      const int sm = __shfl_sync(0xffffffffu, st, 16 + 4 * m);
+      const bool hm = __shfl_sync(0xffffffffu, has ? 1 : 0, 16 + 4 * m) != 0;
+      if (lane == 0 && sm != 0 && !error) {
         const int mx = m == 0 ? ix - 1 : (m == 1 ? ix + 1 : ix), mz = m == 2 ? iz - 1 : (m == 3 ? iz + 1 : iz);
-        G.n_update++;
+        n_update++;
         FTTN(G, mz, mx) = hm ? tm : 0.0; // (no stencil solved: travm is undefined in the Fortran; cannot happen next to an alive node)
-        if (sm == -1) fm_addtree(G, mz, mx); else fm_sift_up(G, mz, mx, FNSTS(G, mz, mx));
+        if (sm == -1) { if (!fm_addtree(H, mz, mx)) error = 2; } else fm_updtree(H, mz, mx);
       }
     }
     __syncwarp();
   }
+  if (lane == 0) { G.error = error; G.n_accept = n_accept; G.n_update = n_update; G.ntr = H.ntr; }
+  __syncwarp();
 }
 
 // rpaths for ONE receiver (fm2dray_cartesian.f90:773-1456, cfd = 0): see oracle/fm2d_ref.c for the quirks that are kept.
@@ -474,6 +495,7 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   int32_t* nsts_c = (int32_t*)(ttn_r + cr);
   int32_t* nsts_r = nsts_c + cc;
   int32_t* heap = nsts_r + cr;
+  double* hkey = (double*)(((uintptr_t)(heap + P.maxbt_alloc + 2) + 7) & ~(uintptr_t)7);
   extern __shared__ __align__(16) unsigned char fm_smem[];
   if (P.use_smem) { // the march is a chain of dependent loads: shared memory (~30 cycles) instead of L2 (~300) per hop
     ttn_c = (double*)fm_smem;
@@ -481,6 +503,7 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     nsts_c = (int32_t*)(ttn_r + cr);
     nsts_r = nsts_c + cc;
     heap = nsts_r + cr;
+    hkey = (double*)(((uintptr_t)(heap + P.maxbt_alloc + 2) + 7) & ~(uintptr_t)7);
   }
   __shared__ FmGrid G;
   __shared__ int s_err;
@@ -527,7 +550,7 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     __syncwarp();
     if (lane == 0) {
       G.nnx = nrnx; G.nnz = nrnz; G.ld = P.ldr; G.gox = gorx; G.goz = gorz; G.dnx = drnx; G.dnz = drnz;
-      G.veln = veln_r; G.ttn = ttn_r; G.nsts = nsts_r; G.heap = heap; G.fom = P.fom;
+      G.veln = veln_r; G.ttn = ttn_r; G.nsts = nsts_r; G.heap = heap; G.hkey = hkey; G.fom = P.fom;
       G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
       int mb = maxbt0;
       if (nrnx > P.nnx || nrnz > P.nnz) { const int a = nrnx > P.nnx ? nrnx : P.nnx, b = nrnz > P.nnz ? nrnz : P.nnz; mb = (int)floor(P.snb * a * b + 0.5); }
@@ -582,7 +605,7 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     __syncwarp();
     if (lane == 0) {
       G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
-      G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.heap = heap; G.fom = P.fom; G.maxbt = maxbt0;
+      G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.heap = heap; G.hkey = hkey; G.fom = P.fom; G.maxbt = maxbt0;
       G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
     }
     __syncwarp();
@@ -682,12 +705,12 @@ int fm2d_launch(FmParams& P, cudaStream_t st) {
   const int a = std::max(P.ldr, P.nnx), b = std::max(P.ldr, P.nnz);
   const size_t maxbt = (size_t)std::max(floor(P.snb * P.nnx * P.nnz + 0.5), floor(P.snb * a * b + 0.5)) + 4;
   P.maxbt_alloc = (int)maxbt;
-  const size_t smem = 8 * (cc + cr) + 4 * (cc + cr + maxbt);
+  const size_t smem = 8 * (cc + cr) + 4 * (cc + cr + maxbt + 4) + 8 * (maxbt + 2) + 16;
   // measured: the march is bound by the latency of its own arithmetic, not of memory -- shared memory gained nothing at
   // example1's size and limits the problems in flight to one per SM; kept as an experiment (MCT_FM2D_SMEM=1)
   P.use_smem = smem <= 200 * 1024 && getenv("MCT_FM2D_SMEM") != nullptr;
   if (P.use_smem) CK(cudaFuncSetAttribute(fm2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  size_t per = 8 * (cc + 2 * cr) + 4 * (cc + cr + maxbt);
+  size_t per = 8 * (cc + 2 * cr) + 4 * (cc + cr + maxbt + 4) + 8 * (maxbt + 2) + 16;
   per = (per + 15) & ~(size_t)15;
   P.scratch_per_problem = per;
   const int nprob = P.nmaps * P.nsrc;
