@@ -15,6 +15,9 @@ cap k1_box 1 r2_k1_final "Round 2, K1 nearest-nucleus kernel (k1_box_kernel), C2
 cap k2_coopw 0 r2_k2coop_final "Round 2, proposal-sized dispersion call (several warps per column)" python bench.py --steps 1 --warmup 1 --no-cpu --no-c5
 cap k1_box 3 r2_k1_c5 "Round 2, K1 (k1_box_kernel) on C5: 1024x1024x80 nodes, 5000 nuclei" python tools/k1_sweep.py C5 auto
 cap grt_kernel 1 r2_grt "Round 2, generalized R/T kernel (grt_kernel): 1024 low-velocity columns, Rayleigh, 11 frequencies" python tools/grt_bench.py 32 1
+cap fm2d_kernel 1 r2_fm2d "Round 2, fast-marching kernel (fm2d_kernel): example1 geometry, 88 problems of 101x101 nodes" python tools/fm2d_bench.py
+python tools/fm2d_bench.py > $S/r2_fm2d.json 2>$S/fm2d.err
+python tools/likelihood_bench.py > $S/r2_likelihood_step.json 2>$S/like.err
 python tools/grt_bench.py 64 1 > $S/r2_grt_rayleigh.json 2>$S/grt1.err
 python tools/grt_bench.py 64 0 > $S/r2_grt_love.json 2>$S/grt0.err
 for c in C2x32 C5 C3 C1; do python tools/k1_sweep.py $c auto; done > $S/r2_k1_sweep.log 2>&1
