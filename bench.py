@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the column-sharded C5 block (one chain's columns over the ranks)")
     ap.add_argument("--c5-steps", type=int, default=2)
+    ap.add_argument("--no-widened", action="store_true", help="skip the block on the widened path (generalized R/T columns, fm2d travel times)")
     return ap.parse_args()
 
 
@@ -372,6 +373,81 @@ class StdoutGuard:
 GUARD = None
 
 
+
+def widened_block(capi):
+    """SURVEY 8(f)2/3 next to the CPU port on the host cores (rank 0, bounded samples): the generalized R/T branch on a grid whose
+    every column has a low-velocity zone, and the fast-marching travel times of example1's geometry (11 periods x 8 sources)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    from mctomo_b200 import synth
+    cores = os.cpu_count() or 1
+    out = {}
+    # -- generalized R/T: 32 x 32 columns, 40 nodes deep, 11 frequencies, Rayleigh phase
+    nx = 32
+    grid = synth.make_grid(nx, nx, 40)
+    pts, par = synth.generate_model(grid, 300, 1002)
+    vp, vs, rho, sid = [np.zeros(grid.shape) for _ in range(3)] + [np.zeros(grid.shape, np.int32)]
+    orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
+    rng = np.random.default_rng(9)
+    k0 = rng.integers(8, 20, size=(nx, nx))
+    for i in range(nx):
+        for j in range(nx):
+            vs[i, j, k0[i, j]:k0[i, j] + 5] = vs[i, j, 0] * 0.85
+    vp[:] = 1.73 * vs
+    rho[:] = 1.74 * vp ** 0.25
+    freqs = synth.example1_freqs()
+    opts = capi.disp_opts(raylov=1, phaseGroup=0, nmodes=0)
+    win = (1, nx, 1, nx)
+    capi.set_grt(True, orc.GRT_PAR_LIKELIHOOD)
+    try:
+        capi.surf_dispersion(vp, vs, rho, grid, win, freqs, opts, check=False)
+        t = time.perf_counter()
+        pv, gv, ie, inval, rc = capi.surf_dispersion(vp, vs, rho, grid, win, freqs, opts, check=False)
+        gpu_s = time.perf_counter() - t
+        st = capi.grt_stats()
+    finally:
+        capi.set_grt(False)
+    sample = [(i, j) for i in range(0, nx, 4) for j in range(0, nx, 4)][:4 * cores]
+
+    def one(ij):
+        n, (th, a, b, r) = orc.convert_column(vp[ij], vs[ij], rho[ij], grid.dz)
+        return orc.grt_modes(th, a, b, r, freqs, modetype=1, phaseGroup=0, par=orc.GRT_PAR_LIKELIHOOD, math_mode=orc.LIBM)[0]
+    t = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(one, sample))
+    cpu_s = time.perf_counter() - t
+    out["grt"] = {"what": "generalized R/T branch of surfmodes: every column of a 32x32x40 grid has a low-velocity zone, 11 frequencies, Rayleigh phase, "
+                          "host arrays in / maps out (mct_surf_dispersion with mct_set_grt)",
+                  "columns": st["columns"], "gpu_ms": 1e3 * gpu_s, "gpu_columns_per_s": st["columns"] / gpu_s, "ierr1_columns": int((ie == 1).sum()),
+                  "cpu_columns_per_s": len(sample) / cpu_s, "cpu_sample_columns": len(sample), "cpu_cores": cores, "cpu_kind": "port (oracle/grt_ref.c, libm)"}
+    # -- fm2d: example1's geometry
+    n, nmaps, nsrc, nrc = 101, 11, 8, 8
+    x, y = np.meshgrid(np.linspace(0, 1, n), np.linspace(0, 1, n), indexing="ij")
+    vel = np.zeros((nmaps, n + 2, n + 2))
+    for m in range(nmaps):
+        v = 2.5 + 0.1 * m + 0.2 * np.sin(5 * x + 3 * y + m) + 0.15 * np.cos(4 * y - 2 * x)
+        vel[m, 1:-1, 1:-1] = v
+        vel[m, 0, :] = vel[m, 1, :]; vel[m, -1, :] = vel[m, -2, :]; vel[m, :, 0] = vel[m, :, 1]; vel[m, :, -1] = vel[m, :, -2]
+    src = rng.uniform(-4.5, 4.5, (nsrc, 2)); rcv = rng.uniform(-4.5, 4.5, (nrc, 2))
+    srs = np.ones((nsrc, nrc), np.int32)
+    o = capi.fm2d_opts()
+    capi.fm2d_times(src, rcv, srs, vel, -5.0, -5.0, 0.1, 0.1, o)
+    t = time.perf_counter()
+    tt, _ = capi.fm2d_times(src, rcv, srs, vel, -5.0, -5.0, 0.1, 0.1, o)
+    gpu_s = time.perf_counter() - t
+    t = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        res = list(ex.map(lambda m: orc.fm2d_times(src, rcv, srs, vel[m], -5.0, -5.0, 0.1, 0.1)[1], range(nmaps)))
+    cpu_s = time.perf_counter() - t
+    out["fm2d"] = {"what": "fast-marching travel times of modrays (phase-velocity data): example1's geometry, 101x101 nodes, 11 periods x 8 sources = 88 "
+                           "eikonal problems, shipped settings (mixed order, source refinement 4 x 8), host arrays in / times out (mct_fm2d_times)",
+                   "problems": nmaps * nsrc, "gpu_ms": 1e3 * gpu_s, "cpu_ms": 1e3 * cpu_s, "cpu_threads": min(cores, nmaps), "cpu_kind": "port (oracle/fm2d_ref.c), one period per thread",
+                   "bit_identical_to_port": bool(all(np.array_equal(res[m], tt[m]) for m in range(nmaps)))}
+    return out
+
+
 def main():
     global GUARD
     args = parse()
@@ -611,6 +687,11 @@ def main():
                                      "distinct_columns_per_step": st["n_columns_solved"] / args.steps},
                         "what": "represented = the reference's own call counts for these inputs (identical to the oracle's); "
                                 "executed = after folding bit-identical columns"}}
+        if world == 1 and not args.no_widened and not column_sharded:
+            try:
+                out["widened"] = widened_block(capi)
+            except Exception as e:  # never lose the headline line over the side block
+                out["widened"] = {"error": repr(e)}
         GUARD.emit(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -178,3 +178,26 @@ def test_grt_model_columns_under_water_phase_and_group(mct, raylov):
                                           math_mode=orc.PORTABLE, preset=pre)
             assert ie[i, j] == ierr and np.array_equal(pv[i, j], p) and np.array_equal(gv[i, j], g), (i, j, ierr)
     assert nlvl >= 3
+
+
+def test_grt_many_layers_and_sixty_frequencies(mct):
+    """The branch's limits: a 160-layer gradient stack with two slow zones, NP = 60 frequencies (surfdisp96's limit, which
+    the dispersion entry points share); and a batch where the low-velocity column is the only one."""
+    n = 160
+    vs = np.linspace(2.6, 4.6, n)
+    vs[40:50] = 2.3
+    vs[90:96] = 2.45
+    th = np.full(n, 0.12); th[-1] = 0
+    col = crust(vs, th)
+    fr = 1.0 / np.linspace(0.6, 12.0, 60)
+    for raylov in (1, 0):
+        opts = disp_opts(raylov=raylov, phaseGroup=0, nmodes=0)
+        mct.set_grt(True, orc.GRT_PAR_LIKELIHOOD)
+        try:
+            ph, gr, ie, rc = mct.surfmodes_batch(*col, [0, n], fr, opts)
+        finally:
+            mct.set_grt(False)
+        ierr, p, g, cnt = orc.grt_modes(*col, fr, modetype=raylov, phaseGroup=0, dc=opts.dphase, par=orc.GRT_PAR_LIKELIHOOD,
+                                        math_mode=orc.PORTABLE, preset=opts.preset)
+        assert ie[0] == ierr and np.array_equal(ph[0], p), raylov
+        assert (p < 99).sum() >= 10
