@@ -507,6 +507,17 @@ def fm2d_rays(src, rcv, srs, vel, gox, goz, dvx, dvz, opts: mct_fm2d_opts, srsv=
     return dict(ttime=tt, npts=npts, pts=pts, length=ln, crazy=crazy)
 
 
+def fm2d_times_dev(d_src_xz, nsrc, d_rcv_xz, nrc, d_srs, srs_map_stride, d_vel, vel_elem_stride, vel_map_stride, nmaps, nvx, nvz, gox, goz,
+                   dvx, dvz, opts: mct_fm2d_opts, d_ttime, d_err, stream):
+    """Device-pointer form (asynchronous on `stream`); see include/mctomo_b200.h."""
+    L = lib()
+    vp = C.c_void_p
+    L.mct_fm2d_times_dev.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int] + \
+                                    [C.c_double] * 4 + [C.POINTER(mct_fm2d_opts), vp, vp, vp]
+    return _check(L.mct_fm2d_times_dev(d_src_xz, nsrc, d_rcv_xz, nrc, d_srs, srs_map_stride, d_vel, vel_elem_stride, vel_map_stride, nmaps,
+                                       nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), d_ttime, d_err, stream))
+
+
 def fm2d_stats():
     L = lib()
     L.mct_fm2d_stats.argtypes = [C.c_void_p]

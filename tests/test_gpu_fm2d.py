@@ -102,3 +102,33 @@ def test_fm2d_ray_geometry_bit_identical(mct, asgr, fom):
         if asgr == 1:  # without source refinement the field around the source is first-order only, its gradient can vanish at a
             assert (npts[srsv[m][srs[m] == 1] - 1] >= 2).all() and crazy == 0  # node (0/0 in the Fortran): counted as crazy rays
         assert npts.sum() > 0
+
+
+def test_fm2d_device_entry_reads_like_vel_in_place(mct):
+    """mct_fm2d_times_dev on the Fortran's like%vel(np, ny+2, nx+2) layout (element stride np, map stride 1) and on
+    dat%raystat(nrr, 2, np) (map stride 2*nrr), asynchronous on a user stream: equal to the host entry point."""
+    import torch
+    nmaps, nx, ny = 3, 41, 35
+    vel = _maps(nmaps, nx, ny, 21)                                   # (nmaps, nx+2, ny+2)
+    rng = np.random.default_rng(2)
+    nsrc, nrc = 4, 6
+    src = np.column_stack([rng.uniform(0.1, 3.9, nsrc), rng.uniform(0.1, 3.3, nsrc)])
+    rcv = np.column_stack([rng.uniform(0.1, 3.9, nrc), rng.uniform(0.1, 3.3, nrc)])
+    raystat = np.zeros((nmaps, 2, nsrc * nrc), np.int32)
+    raystat[:, 0, :] = rng.uniform(size=(nmaps, nsrc * nrc)) < 0.8
+    raystat[:, 1, :] = 7
+    o = mct.fm2d_opts(sgdic=2, sgext=6)
+    want, _ = mct.fm2d_times(src, rcv, raystat[:, 0, :].reshape(nmaps, nsrc, nrc), vel, 0.0, 0.0, 0.1, 0.1, o)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d_vel = torch.from_numpy(np.ascontiguousarray(np.transpose(vel, (1, 2, 0)))).cuda()   # C (nx+2, ny+2, np) == Fortran (np, ny+2, nx+2)
+        d_src = torch.from_numpy(np.concatenate([src[:, 0], src[:, 1]])).cuda()
+        d_rcv = torch.from_numpy(np.concatenate([rcv[:, 0], rcv[:, 1]])).cuda()
+        d_srs = torch.from_numpy(raystat).cuda()
+        d_tt = torch.full((nmaps, nsrc, nrc), -1.0, dtype=torch.float64, device="cuda")
+        d_err = torch.zeros(nmaps * nsrc, dtype=torch.int32, device="cuda")
+        mct.fm2d_times_dev(d_src.data_ptr(), nsrc, d_rcv.data_ptr(), nrc, d_srs.data_ptr(), 2 * nsrc * nrc, d_vel.data_ptr(), nmaps, 1, nmaps,
+                           nx, ny, 0.0, 0.0, 0.1, 0.1, o, d_tt.data_ptr(), d_err.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert int(d_err.abs().sum()) == 0
+    assert np.array_equal(d_tt.cpu().numpy(), want)

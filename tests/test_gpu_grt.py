@@ -185,16 +185,18 @@ def test_grt_many_layers_and_sixty_frequencies(mct):
     the dispersion entry points share); and a batch where the low-velocity column is the only one."""
     n = 160
     vs = np.linspace(2.6, 4.6, n)
-    vs[40:50] = 2.3
-    vs[90:96] = 2.45
-    th = np.full(n, 0.12); th[-1] = 0
+    vs[40] = 2.3                     # ONE layer each: the reference's predicate wants a strict local minimum of vp
+    vs[90] = 2.45                    # (convert_to_layer merges equal cells, so plateaus do not occur in model columns)
+    th = np.full(n, 0.12); th[40] = 1.2; th[90] = 0.7; th[-1] = 0
     col = crust(vs, th)
+    assert orc.L().orc_nlvls1(orc.f64(col[1]).ctypes.data, orc.f64(col[2]).ctypes.data, n, 1) == 2
     fr = 1.0 / np.linspace(0.6, 12.0, 60)
     for raylov in (1, 0):
         opts = disp_opts(raylov=raylov, phaseGroup=0, nmodes=0)
         mct.set_grt(True, orc.GRT_PAR_LIKELIHOOD)
         try:
             ph, gr, ie, rc = mct.surfmodes_batch(*col, [0, n], fr, opts)
+            assert mct.grt_stats()["columns"] == 1
         finally:
             mct.set_grt(False)
         ierr, p, g, cnt = orc.grt_modes(*col, fr, modetype=raylov, phaseGroup=0, dc=opts.dphase, par=orc.GRT_PAR_LIKELIHOOD,
