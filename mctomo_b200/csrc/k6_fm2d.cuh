@@ -1,16 +1,19 @@
-// k6_fm2d.cuh -- SURVEY 8(f)2: the reference's 2-D fast-marching eikonal solver for phase-velocity data on the device:
-// `modrays` as surf_likelihood drives it (src/likelihood_surf.F90:295-336, uar = 1: travel times at the receivers, no ray
-// geometry): gridder, bsplrefine, the source loop with source-grid refinement (fm2d/fm2dray_cartesian.f90:67-478,490-668),
-// srtimes (:676-770), travel / fouds1 / fouds2 / addtree / downtree / updtree / bilinear (fm2d/fm2d_ttime.f90).
+// k6_fm2d.cuh -- SURVEY 8(f)2: the reference's 2-D fast-marching eikonal solver on the device: `modrays` as surf_likelihood
+// drives it (src/likelihood_surf.F90:295-336): gridder, bsplrefine, the source loop with source-grid refinement
+// (fm2d/fm2dray_cartesian.f90:67-478,490-668), srtimes (:676-770), rpaths with cfd = 0 (:773-1456; uar = 0, group-velocity
+// data), travel / fouds1 / fouds2 / addtree / downtree / updtree / bilinear (fm2d/fm2d_ttime.f90); and the curved-ray
+// branch of surf_likelihood on a session's resident maps (mct_session_likelihood_fm2d).
 //
 // The unit of parallelism is the reference's own: every (period, source) pair is an independent eikonal problem
-// (the Fortran loops over sources inside an OpenMP loop over periods).  One warp per problem.  Fast marching accepts
-// nodes strictly in the order of a binary heap, and the reference's travel times depend on that order (which neighbours
-// are alive when a node is updated), so the march itself is kept exactly as the Fortran runs it -- same heap, same
-// stencils, same operation order -- on lane 0; what is data-parallel inside a problem (B-spline velocities of the
-// propagation grid and of the refined source grid, the narrow-band completion sweep, the receiver interpolation) is
-// spread over the lanes.  Results are bit-identical to oracle/fm2d_ref.c.  Throughput comes from the number of problems
-// in flight (np x nsrc: 88 in example1, thousands in the multi-mode configurations), not from one problem's latency.
+// (the Fortran loops over sources inside an OpenMP loop over periods).  One warp per problem, all of them in one launch.
+// Fast marching accepts nodes strictly in the order of a binary heap, and the reference's travel times depend on that
+// order (which neighbours are alive when a node is updated), so the march keeps the Fortran's heap, stencils and
+// operation order; inside one accepted node the (up to) 4 x 4 stencil quadrants are solved by 16 lanes while lane 0
+// re-orders the heap (fm_travel).  What is data-parallel inside a problem -- B-spline velocities of the propagation grid
+// and of the refined source grid, the narrow-band completion sweep, the receiver interpolation, the ray tracing of rpaths
+// (one receiver per lane) -- is spread over the lanes.  Results are bit-identical to oracle/fm2d_ref.c: receiver times,
+// the whole field, node / stencil counts, every ray point.  Throughput comes from the number of problems in flight
+// (np x nsrc: 88 in example1, thousands in the multi-mode configurations), not from one problem's latency.
 #pragma once
 
 struct FmParams {
