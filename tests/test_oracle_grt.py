@@ -87,3 +87,44 @@ def test_math_modes_agree_and_failure_leaves_presets():
     m = np.loadtxt(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "grt_model_dat.txt"))
     ierr, ph, gr, _ = orc.grt_modes(m[:, 0], m[:, 1], m[:, 2], m[:, 3], FREQS, modetype=1, phaseGroup=1, math_mode=orc.LIBM, preset=1000.0)
     assert ierr == 1 and (ph[:5] < 10).all() and (ph[5:] == 1000.0).all()
+
+
+def _refine_root(F, c, h=2e-4, it=40):
+    """bisection of the independent secular function in a bracket around the oracle's root"""
+    import mpmath as mp
+    a, b = mp.mpf(c - h), mp.mpf(c + h)
+    fa = F(a)
+    assert fa * F(b) < 0
+    for _ in range(it):
+        m = (a + b) / 2
+        fm = F(m)
+        if fa * fm < 0:
+            b = m
+        else:
+            a, fa = m, fm
+    return float((a + b) / 2)
+
+
+@pytest.mark.parametrize("modetype", [1, 0])
+def test_group_velocity_is_the_finite_difference_of_true_roots(modetype):
+    """CalGroup (surfmodes.f90:308-320): U = dh / ((f+dh)/c(f+dh) - f/c(f)), dh = 0.005 Hz.  The same quotient formed from
+    roots of the INDEPENDENT secular function (refined to 1e-15) must agree with the restatement's group velocity to the
+    accuracy its own root tolerance allows (1e-6 km/s in c -> ~2e-4 relative in U at these frequencies)."""
+    th, vp, vs, rho = MODELS["lvl_mid"]
+    fr = FREQS[[1, 4, 8]]
+    ierr, ph, gr, _ = orc.grt_modes(th, vp, vs, rho, fr, modetype=modetype, phaseGroup=1, math_mode=orc.LIBM)
+    assert ierr == 0
+    dh = float(np.float32(0.005))
+    for f, c, u in zip(fr, ph, gr):
+        if modetype == 1:
+            F0 = lambda x: im.rayleigh_secular(x, 1 / f, th, vp, vs, rho)
+            F1 = lambda x: im.rayleigh_secular(x, 1 / (f + dh), th, vp, vs, rho)
+        else:
+            F0 = lambda x: im.love_secular(x, 1 / f, th, vs, rho)
+            F1 = lambda x: im.love_secular(x, 1 / (f + dh), th, vs, rho)
+        c0 = _refine_root(F0, c)
+        # the second search of the reference starts from c(f): its root is the same mode a little lower
+        c1 = _refine_root(F1, c0 - (c0 / u - 1) * c0 * dh / f if u > 0 else c0, h=2e-3)
+        assert abs(c0 - c) < 3e-6, (f, c, c0)
+        u_ind = dh / ((f + dh) / c1 - f / c0)
+        assert abs(u_ind - u) < 2e-3 * u, (f, u, u_ind)
