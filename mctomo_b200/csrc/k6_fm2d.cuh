@@ -84,7 +84,7 @@ struct FmGrid {
   const double* veln;
   double* ttn;
   int32_t* nsts;
-  int32_t* heap; // packed (pz << 16) | px, 1-based
+  int32_t* heap; // the node's linear index (px-1)*ld + (pz-1) of every heap entry, 1-based entries
   double* hkey;  // the travel time of every heap entry, kept beside it: the sift loops compare keys without chasing ttn
   int ntr, maxbt, fom;
   int vnl, vnr, vnt, vnb;
@@ -94,8 +94,6 @@ struct FmGrid {
 #define FVELN(G, k, j) (G).veln[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
 #define FTTN(G, k, j) (G).ttn[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
 #define FNSTS(G, k, j) (G).nsts[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
-#define HPX(h) ((h) & 0xffff)
-#define HPZ(h) ((h) >> 16)
 
 // The narrow-band heap (addtree / updtree / downtree of fm2d_ttime.f90), lane 0 only.  Same comparisons in the same
 // order as the Fortran, on a copy of each entry's travel time stored beside the entry; pointers and sizes live in
@@ -104,7 +102,7 @@ struct FmHeap {
   int32_t* pos; double* key; int32_t* nsts; double* ttn;
   int ld, ntr, maxbt;
 };
-#define HN(H, h) (H).nsts[(size_t)(HPX(h) - 1) * (H).ld + (HPZ(h) - 1)]
+#define HN(H, h) (H).nsts[h]
 __device__ __forceinline__ void fm_sift_up(FmHeap& H, int self, double t, int tpc) {
   int tpp = tpc / 2;
   while (tpp > 0) {
@@ -123,12 +121,13 @@ __device__ __forceinline__ void fm_sift_up(FmHeap& H, int self, double t, int tp
 __device__ __forceinline__ bool fm_addtree(FmHeap& H, int iz, int ix) { // false: the narrow band is full
   if (H.ntr + 1 > H.maxbt) return false;
   H.ntr++;
-  fm_sift_up(H, (iz << 16) | ix, H.ttn[(size_t)(ix - 1) * H.ld + (iz - 1)], H.ntr);
+  const int a = (ix - 1) * H.ld + (iz - 1);
+  fm_sift_up(H, a, H.ttn[a], H.ntr);
   return true;
 }
 __device__ __forceinline__ void fm_updtree(FmHeap& H, int iz, int ix) {
-  const size_t a = (size_t)(ix - 1) * H.ld + (iz - 1);
-  fm_sift_up(H, (iz << 16) | ix, H.ttn[a], H.nsts[a]);
+  const int a = (ix - 1) * H.ld + (iz - 1);
+  fm_sift_up(H, a, H.ttn[a], H.nsts[a]);
 }
 __device__ __forceinline__ void fm_downtree(FmHeap& H) {
   if (H.ntr == 1) { H.ntr--; return; }
@@ -268,7 +267,7 @@ __device__ bool fm_quadrant(const FmGrid& G, int iz, int ix, int dj, int dk, dou
   }
   if (!swsol) return false;
   const double t = tref + fm_qsolve(a, b, c);
-  *trav_out = G.fom == 0 ? t : t / tdiv;
+  *trav_out = tdiv == 3.0 ? t / 3.0 : t; // tdiv is 1 or 3; x / 1.0 == x
   return true;
 }
 __device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3][3], double dsx, double dsz) {
@@ -326,7 +325,7 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
       int go = 0;
       if (H.ntr > 0 && !error) {
         const int h = H.pos[1];
-        const int ix = HPX(h), iz = HPZ(h);
+        const int ix = h / H.ld + 1, iz = h - (ix - 1) * H.ld + 1;
         int swrg = 0;
         if (urg == 1) {
           if (ix == 1 && G.vnl != 1) swrg = 1;
