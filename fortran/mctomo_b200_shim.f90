@@ -444,7 +444,9 @@ contains
     ! Drop-in for the OpenMP loop over periods around `modrays` in surf_likelihood (src/likelihood_surf.F90:295-336) when
     ! settings%phaseGroup == 0 (uar = 1: travel times only).  src(2,nsrc), rev(2,nrev), raystat(nrev*nsrc,2,np),
     ! vel(np,ny+2,nx+2) = like%vel, phaseTime(nrev,nsrc,np) = like%phaseTime exactly as the reference declares them.
-    ! Group-velocity data need the ray geometry (rpaths), which stays with the Fortran modrays.
+    ! Group-velocity data need the ray geometry (rpaths): fm2d_rays_b200 below.  Status 7 (MCT_E_FM2D_STALE: a source inside the
+    ! model's last cell row/column, where the reference's refined march dies and returns the previous source's field) is raised
+    ! like any other error: move the grid edge, or keep modrays for such a geometry.
     subroutine fm2d_times_b200(src, rev, raystat, grid, vel, gridx, gridy, sgref, sgdic, sgext, order, band, phaseTime)
         real(c_double), dimension(:,:), intent(in) :: src, rev
         integer(c_int), dimension(:,:,:), intent(in) :: raystat

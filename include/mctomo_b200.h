@@ -37,6 +37,10 @@ extern "C" {
                                      (nuclei that merely share one or two coordinates are fine: kdtree2.f90:818-826) */
 #define MCT_E_FLUID_BELOW_TOP 5 /* vs ~ 0 below the first layer: the reference `stop`s (surfmodes.f90:342-345): ierr=4 */
 #define MCT_E_ZERO_NOISE 6 /* misfit: a ray that carries data has sigma < 1e-10 (likelihood_surf.F90:387-390 raises an error) */
+#define MCT_E_FM2D_STALE 7 /* fm2d: a source lies in the model's last cell row/column.  The reference's refined march stops at once
+                             there (fm2d_ttime.f90:76-87 compares a refined extent with a coarse index) and returns the PREVIOUS
+                             source's field; outputs are delivered, that source's times are those of the dead march (unreached
+                             nodes read 0) and the per-problem status (d_err) is 6 */
 #define MCT_E_NOINIT (-1)
 #define MCT_E_CUDA (-2)
 
@@ -335,7 +339,8 @@ int mct_fm2d_rays(const double* src_x, const double* src_z, int nsrc, const doub
  * maps are addressed as d_vel[m*vel_map_stride + (b*(nvz+2) + a)*vel_elem_stride], so the padded map that
  * mct_assemble_vel_dev builds -- the Fortran's like%vel(np, ny+2, nx+2) -- is consumed in place with
  * (vel_elem_stride, vel_map_stride) = (np, 1); srs_map_stride = nrc*nsrc, or 2*nrc*nsrc for dat%raystat(nrev*nsrc, 2, np).
- * d_err int32[nmaps*nsrc]: 0, 1 source outside the model, 2 narrow band overflow, 3 receiver outside the model. */
+ * d_err int32[nmaps*nsrc]: 0, 1 source outside the model, 2 narrow band overflow, 3 receiver outside the model, 6 see
+ * MCT_E_FM2D_STALE. */
 int mct_fm2d_times_dev(const double* d_src_xz, int nsrc, const double* d_rcv_xz, int nrc, const int32_t* d_srs, long long srs_map_stride,
                        const double* d_vel, long long vel_elem_stride, long long vel_map_stride, int nmaps, int nvx, int nvz, double gox,
                        double goz, double dvx, double dvz, const mct_fm2d_opts* o, double* d_ttime, int32_t* d_err, void* stream);

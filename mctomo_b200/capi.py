@@ -26,6 +26,7 @@ MCT_E_TOO_MANY_LAYERS = 3
 MCT_E_DEGENERATE_NUCLEI = 4
 MCT_E_FLUID_BELOW_TOP = 5
 MCT_E_ZERO_NOISE = 6
+MCT_E_FM2D_STALE = 7
 MCT_E_NOINIT = -1
 MCT_E_CUDA = -2
 
@@ -451,6 +452,9 @@ class mct_fm2d_opts(C.Structure):
                 ("order", C.c_int32), ("band", C.c_double)]
 
 
+LAST_FM2D_RC = 0  # status of the last fm2d_times / fm2d_rays call (MCT_E_FM2D_STALE: a source in the model's last cell row/column)
+
+
 def fm2d_opts(gridx=1, gridy=1, sgref=1, sgdic=4, sgext=8, order=1, band=0.5) -> mct_fm2d_opts:
     """examples/example1/MCTomo.inp:61-72 by default."""
     return mct_fm2d_opts(gridx, gridy, sgref, sgdic, sgext, order, band)
@@ -472,8 +476,10 @@ def fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, opts: mct_fm2d_opts, ttim
     tt = np.full((nmaps, nsrc, nrc), -1.0) if ttime is None else np.ascontiguousarray(ttime, dtype=np.float64)
     nnx, nnz = (nvx - 1) * opts.gridx + 1, (nvz - 1) * opts.gridy + 1
     field = np.zeros((nmaps, nsrc, nnx, nnz)) if want_field else None
-    _check(L.mct_fm2d_times(sx.ctypes.data, sz.ctypes.data, nsrc, rx.ctypes.data, rz.ctypes.data, nrc, srs.ctypes.data, vel.ctypes.data,
-                            nmaps, nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), tt.ctypes.data, field.ctypes.data if want_field else None))
+    global LAST_FM2D_RC
+    LAST_FM2D_RC = _check(L.mct_fm2d_times(sx.ctypes.data, sz.ctypes.data, nsrc, rx.ctypes.data, rz.ctypes.data, nrc, srs.ctypes.data, vel.ctypes.data,
+                                           nmaps, nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), tt.ctypes.data, field.ctypes.data if want_field else None),
+                          allow=(MCT_E_FM2D_STALE,))
     return tt, field
 
 
@@ -501,9 +507,10 @@ def fm2d_rays(src, rcv, srs, vel, gox, goz, dvx, dvz, opts: mct_fm2d_opts, srsv=
     pts = np.zeros((nmaps, nrr, cap, 2))
     ln = np.zeros((nmaps, nrr))
     crazy = np.zeros(nmaps, np.int32)
-    _check(L.mct_fm2d_rays(sx.ctypes.data, sz.ctypes.data, nsrc, rx.ctypes.data, rz.ctypes.data, nrc, srs.ctypes.data, srsv.ctypes.data,
-                           vel.ctypes.data, nmaps, nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), tt.ctypes.data, cap, npts.ctypes.data,
-                           pts.ctypes.data, ln.ctypes.data, crazy.ctypes.data))
+    global LAST_FM2D_RC
+    LAST_FM2D_RC = _check(L.mct_fm2d_rays(sx.ctypes.data, sz.ctypes.data, nsrc, rx.ctypes.data, rz.ctypes.data, nrc, srs.ctypes.data, srsv.ctypes.data,
+                                          vel.ctypes.data, nmaps, nvx, nvz, gox, goz, dvx, dvz, C.byref(opts), tt.ctypes.data, cap, npts.ctypes.data,
+                                          pts.ctypes.data, ln.ctypes.data, crazy.ctypes.data), allow=(MCT_E_FM2D_STALE,))
     return dict(ttime=tt, npts=npts, pts=pts, length=ln, crazy=crazy)
 
 

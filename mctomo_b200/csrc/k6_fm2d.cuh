@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     heap = nsts_r + cr;
     hkey = (double*)(((uintptr_t)(heap + P.maxbt_alloc + 2) + 7) & ~(uintptr_t)7);
   }
+  for (size_t q = lane; q < cc; q += 32) ttn_c[q] = 0.0; // nodes the march never reaches read 0 (see the check after the march)
   __shared__ FmGrid G;
   __shared__ int s_err;
   __shared__ int s_sh[4];
@@ -617,6 +618,18 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   __syncwarp();
   if (lane == 0 && P.counters) { atomicAdd(&P.counters[0], (unsigned long long)nacc); atomicAdd(&P.counters[1], (unsigned long long)nupd); }
   if (s_err) { if (lane == 0) P.err[prob] = s_err; return; }
+  // Every node must have been accepted.  The Fortran's refined march stops at a refined-grid edge that it takes for an
+  // interior one (its test compares the REFINED extent with a COARSE index, fm2d_ttime.f90:76-87): for a source in the
+  // model's last cell row or column that is the source cell itself, the march dies after one or two nodes, and the Fortran
+  // then returns whatever the shared ttn array held from the PREVIOUS source.  That result is not a function of this
+  // problem's inputs; the problem is flagged (condition 6) and its unreached nodes read 0 here.
+  {
+    int unreached = 0;
+    for (size_t q = lane; q < cc; q += 32) unreached += nsts_c[q] != 0 ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) unreached += __shfl_xor_sync(0xffffffffu, unreached, o);
+    if (unreached > 0 && lane == 0) P.err[prob] = 6;
+  }
   if (P.field) {
     double* f = P.field + (size_t)prob * cc;
     for (size_t q = lane; q < cc; q += 32) f[q] = ttn_c[q];
@@ -824,9 +837,12 @@ static int fm2d_host(const double* src_x, const double* src_z, int nsrc, const d
   if (e != cudaSuccess) return fail(MCT_E_CUDA, "fm2d: %s", cudaGetErrorString(e));
   if (rays) for (int m = 0; m < nmaps; ++m) { crazy[m] = 0; for (int i = 0; i < nsrc; ++i) crazy[m] += herr[(size_t)nprob + (size_t)m * nsrc + i]; }
   for (int p = 0; p < nprob; ++p)
-    if (herr[p]) return fail(MCT_E_INVALID_ARG, "fm2d: problem %d (period %d, source %d): %s", p, p / nsrc + 1, p % nsrc + 1,
+    if (herr[p] && herr[p] != 6) return fail(MCT_E_INVALID_ARG, "fm2d: problem %d (period %d, source %d): %s", p, p / nsrc + 1, p % nsrc + 1,
                              herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" :
                              herr[p] == 3 ? "receiver outside the model" : "ray slot (raystat(:,2,:)) outside 1..nrev*nsrc");
+  for (int p = 0; p < nprob; ++p)
+    if (herr[p] == 6) return fail(MCT_E_FM2D_STALE, "fm2d: period %d, source %d lies in the model's last cell row/column: the reference's refined march "
+                                  "stops at once there and returns the previous source's field; times of that source are not comparable", p / nsrc + 1, p % nsrc + 1);
   return MCT_OK;
 }
 
@@ -977,8 +993,9 @@ int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snois
   if (phase_time) CK(cudaMemcpyAsync(phase_time, s->time.p, 8 * nt, cudaMemcpyDeviceToHost, st));
   rc = misfit_run(s->mf, (const double*)s->time.p, snoise0, snoise1, out, sigma, st, d_srdist);
   for (int p = 0; p < nprob; ++p)
-    if (herr[p]) return fail(MCT_E_INVALID_ARG, "session_likelihood_fm2d: period %d, source %d: %s", p / s->f_nsrc + 1, p % s->f_nsrc + 1,
-                             herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" : "receiver outside the model");
+    if (herr[p]) return fail(herr[p] == 6 ? MCT_E_FM2D_STALE : MCT_E_INVALID_ARG, "session_likelihood_fm2d: period %d, source %d: %s", p / s->f_nsrc + 1, p % s->f_nsrc + 1,
+                             herr[p] == 1 ? "source outside the model" : herr[p] == 2 ? "narrow band exceeds band*nx*ny" :
+                             herr[p] == 3 ? "receiver outside the model" : "source in the model's last cell row/column (the reference returns the previous source's field there)");
   return rc;
 }
 

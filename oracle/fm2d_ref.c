@@ -46,6 +46,11 @@ typedef struct {
 
 static inline double sq(double x) { return x * x; }
 
+/* test hook: where set (per calling thread), fm2d_core writes for every source the number of nodes its march left unreached
+ * (status != alive); such a source's field is the previous source's in the Fortran (see the comment in fm2d_core) */
+static __thread int* g_unreached = 0;
+void orc_fm2d_set_unreached(int* buf) { g_unreached = buf; }
+
 /* heap: fm2d_ttime.f90 addtree / downtree / updtree */
 static void sift_up(fm_t* F, int iz, int ix, int tpc) {
   int tpp = tpc / 2;
@@ -596,6 +601,10 @@ static int fm2d_core(int nsrc, const double* scx, const double* scz, int nrc, co
       travel(F, x, z, 0);
     }
     if (F->error) break;
+    /* A march that dies at once (the refined-grid edge test of travel compares a REFINED extent with a COARSE index, so a source
+     * cell in the model's last cell row/column counts as a refined edge) leaves ttn as the PREVIOUS source left it: the Fortran
+     * shares one ttn array over the source loop, and so does this restatement. */
+    if (g_unreached) { int u = 0; for (int j = 1; j <= F->nnx; ++j) for (int k = 1; k <= F->nnz; ++k) u += NSTS(k, j) != 0; g_unreached[i - 1] = u; }
     if (field) for (int j = 1; j <= F->nnx; ++j) for (int k = 1; k <= F->nnz; ++k) field[((size_t)(i - 1) * F->nnx + (j - 1)) * F->nnz + (k - 1)] = TTN(k, j);
     srtimes(F, x, z, i, nrc, rcx, rcz, srs, ttime);
     if (ray_npts && !F->error) rpaths(F, asgr, x, z, i, nrc, rcx, rcz, srs, srsv, nrc * nsrc, cap, ray_npts, ray_pts, ray_len, crazy); /* uar = 0 */

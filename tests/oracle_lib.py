@@ -328,6 +328,21 @@ def grt_secfun(thick, vp, vs, rho, freq, modetype, c, math_mode=PORTABLE):
     return rc, re.value, im.value
 
 
+def fm2d_unreached(nsrc):
+    """Arms the oracle's per-source count of nodes the march leaves unreached (0 for a skipped source); returns the int32 array the
+    next fm2d_times / fm2d_rays call ON THIS THREAD fills.  A non-zero entry marks a source whose field is, in the reference, the
+    previous source's (tests exclude those sources from bit comparisons and check that the device flags them)."""
+    buf = np.zeros(nsrc, np.int32)
+    L().orc_fm2d_set_unreached.argtypes = [C.c_void_p]
+    L().orc_fm2d_set_unreached(buf.ctypes.data)
+    return buf
+
+
+def fm2d_disarm():
+    L().orc_fm2d_set_unreached.argtypes = [C.c_void_p]
+    L().orc_fm2d_set_unreached(None)
+
+
 def fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, asgr=1, sgdl=4, sgs=8, fom=1, snb=0.5, want_field=False):
     """modrays for one velocity map, travel times only (oracle/fm2d_ref.c).  src (nsrc,2), rcv (nrc,2) as (x, z);
     srs (nsrc, nrc) 0/1; vel (nvx+2, nvz+2) C-order = the Fortran like%vel(period,:,:) (nvz+2, nvx+2) with its edge.

@@ -120,3 +120,30 @@ def test_ray_slots_follow_raystat_and_pairs_without_data_get_no_ray():
     assert err == 0
     assert npts[8 - 7] == 0 and (np.delete(npts, 1) >= 2).all()    # pair (source 2, receiver 3) -> slot 7 - ... stays empty
     assert np.array_equal(pts[7, 0], RCV[0]) and np.array_equal(pts[0, 0], RCV[3])
+
+
+def test_a_source_in_the_last_cell_row_returns_the_previous_sources_field():
+    """Documents a property of the reference, reproduced by the restatement: with source-grid refinement on, travel()'s edge test
+    compares the REFINED extent with the COARSE index vnr (fm2d_ttime.f90:76-87), so a source in the model's last cell row or
+    column stops its own refined march after one or two nodes; ttn is one array over the source loop (fm2d_wrapper.f90), so what
+    the reference then returns for that source is the previous source's field.  The device path reports it (MCT_E_FM2D_STALE)."""
+    rng = np.random.default_rng(5)
+    vel = 3.0 + 0.3 * rng.random((19, 40))               # 17 x 38 nodes + the replicated edge
+    src = np.array([[0.8, 3.1], [1.5, 37 * 0.25 - 0.07], [2.9, 5.0]])
+    rcv = np.array([[0.3, 0.4], [3.1, 8.0]])
+    srs = np.ones((3, 2), np.int32)
+    unreached = orc.fm2d_unreached(3)
+    err, tt, field, _ = orc.fm2d_times(src, rcv, srs, vel, 0.0, 0.0, 0.2, 0.25, sgdl=3, sgs=4, want_field=True)
+    orc.fm2d_disarm()
+    assert err == 0 and unreached[0] == 0 and unreached[2] == 0 and unreached[1] > 600
+    assert (field[1] == field[0]).sum() > 600
+    # alone (or first), the same source leaves the field at its initial zeros
+    unreached = orc.fm2d_unreached(1)
+    err, tt1, field1, _ = orc.fm2d_times(src[1:2], rcv, srs[1:2], vel, 0.0, 0.0, 0.2, 0.25, sgdl=3, sgs=4, want_field=True)
+    orc.fm2d_disarm()
+    assert (field1[0] == 0).sum() > 600 and unreached[0] > 600
+    # without refinement the march is complete
+    unreached = orc.fm2d_unreached(3)
+    orc.fm2d_times(src, rcv, srs, vel, 0.0, 0.0, 0.2, 0.25, asgr=0)
+    orc.fm2d_disarm()
+    assert not unreached.any()
