@@ -29,9 +29,9 @@ struct FmParams {
   double snb;
   int nnx, nnz, ldr;         // propagation grid; leading dimension of the refined arrays
   double* veln;              // (nnz, nnx, nmaps): gridder's output (fm2d_gridder_kernel)
+  double* slow;              // (nnz, nnx, nmaps): 1 / veln, the slowness every stencil of a node starts from (same division, done once)
   char* scratch; size_t scratch_per_problem;
-  int use_smem;              // travel-time, status and heap arrays of a problem live in shared memory (they fit: example1's 101 x 101 grid does)
-  int maxbt_alloc;           // heap entries reserved per problem
+  size_t heap_bytes;         // bytes reserved per problem for the heap entries
   double* ttime;             // (nrc, nsrc, nmaps); entries without data untouched
   double* field;             // optional (nnz, nnx, nsrc, nmaps): ttn of every problem
   int32_t* err;              // per problem: 0, 1 source outside, 2 narrow band overflow, 3 receiver outside
@@ -74,18 +74,21 @@ __global__ void fm2d_gridder_kernel(const __grid_constant__ FmParams P) {
       sumi = sumi + vi[i1] * sumj;
     }
     P.veln[(size_t)map * P.nnx * P.nnz + (size_t)(stx - 1) * P.nnz + (stz - 1)] = sumi;
+    P.slow[(size_t)map * P.nnx * P.nnz + (size_t)(stx - 1) * P.nnz + (stz - 1)] = 1.0 / sumi;
   }
 }
 
 // one marching grid: arrays with leading dimension ld (rows = z), 1-based accessors
+struct __align__(16) FmEnt { double key; int32_t pos; int32_t pad; }; // one heap entry: the node's travel time beside its linear index
 struct FmGrid {
   int nnx, nnz, ld;
+  unsigned ld_magic; // ceil(2^32 / ld): a linear node index is split into (ix, iz) without an integer division
   double gox, goz, dnx, dnz;
   const double* veln;
+  const double* slow;
   double* ttn;
   int32_t* nsts;
-  int32_t* heap; // the node's linear index (px-1)*ld + (pz-1) of every heap entry, 1-based entries
-  double* hkey;  // the travel time of every heap entry, kept beside it: the sift loops compare keys without chasing ttn
+  FmEnt* heap; // 1-based entries
   int ntr, maxbt, fom;
   int vnl, vnr, vnt, vnb;
   int error;
@@ -95,116 +98,150 @@ struct FmGrid {
 #define FTTN(G, k, j) (G).ttn[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
 #define FNSTS(G, k, j) (G).nsts[(size_t)((j) - 1) * (G).ld + ((k) - 1)]
 
-// The narrow-band heap (addtree / updtree / downtree of fm2d_ttime.f90), lane 0 only.  Same comparisons in the same
-// order as the Fortran, on a copy of each entry's travel time stored beside the entry; pointers and sizes live in
-// registers (FmHeap is a local of the caller), the heap size is returned.
+// commands of the heap warp to the stencil warp (>= 0: the linear index of the node just accepted)
+#define FM_CMD_GRID (-2)
+#define FM_CMD_QUIT (-3)
+__device__ __forceinline__ void fm_bar_a() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void fm_bar_b() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+__device__ __forceinline__ int fm_row(int h, int ld, unsigned magic) { // h / ld for 0 <= h < 2^31, ld >= 2
+  int q = (int)__umulhi((unsigned)h, magic);
+  if (q * ld > h) q--;
+  return q;
+}
+
+// The narrow-band heap (addtree / updtree / downtree of fm2d_ttime.f90), lane 0 of the heap warp only.  Same comparisons in
+// the same order as the Fortran, on a copy of each entry's travel time stored beside the entry (one 16-byte load per entry:
+// the sift loops never chase ttn, and a level costs one load latency); sizes live in registers.
 struct FmHeap {
-  int32_t* pos; double* key; int32_t* nsts; double* ttn;
-  int ld, ntr, maxbt;
+  FmEnt* ent; int32_t* nsts; const double* ttn;
+  int ntr, maxbt;
 };
-#define HN(H, h) (H).nsts[h]
+__device__ __forceinline__ FmEnt fm_ld(const FmEnt* p) {
+  const int4 v = *reinterpret_cast<const int4*>(p);
+  FmEnt e; e.key = __hiloint2double(v.y, v.x); e.pos = v.z; e.pad = 0;
+  return e;
+}
+__device__ __forceinline__ void fm_st(FmEnt* p, double key, int pos) {
+  int4 v; v.x = __double2loint(key); v.y = __double2hiint(key); v.z = pos; v.w = 0;
+  *reinterpret_cast<int4*>(p) = v;
+}
 __device__ __forceinline__ void fm_sift_up(FmHeap& H, int self, double t, int tpc) {
-  int tpp = tpc / 2;
+  int tpp = tpc >> 1;
   while (tpp > 0) {
-    const double kp = H.key[tpp];
-    if (t < kp) {
-      const int hp = H.pos[tpp];
-      HN(H, hp) = tpc;
-      H.pos[tpc] = hp; H.key[tpc] = kp;
+    const FmEnt p = fm_ld(H.ent + tpp);
+    if (t < p.key) {
+      H.nsts[p.pos] = tpc;
+      fm_st(H.ent + tpc, p.key, p.pos);
       tpc = tpp;
-      tpp = tpc / 2;
+      tpp = tpc >> 1;
     } else tpp = 0;
   }
-  H.pos[tpc] = self; H.key[tpc] = t;
-  HN(H, self) = tpc;
+  fm_st(H.ent + tpc, t, self);
+  H.nsts[self] = tpc;
 }
-__device__ __forceinline__ bool fm_addtree(FmHeap& H, int iz, int ix) { // false: the narrow band is full
+__device__ __forceinline__ bool fm_addtree(FmHeap& H, int a, double t) { // a: linear node index; false: the narrow band is full
   if (H.ntr + 1 > H.maxbt) return false;
   H.ntr++;
-  const int a = (ix - 1) * H.ld + (iz - 1);
-  fm_sift_up(H, a, H.ttn[a], H.ntr);
+  fm_sift_up(H, a, t, H.ntr);
   return true;
-}
-__device__ __forceinline__ void fm_updtree(FmHeap& H, int iz, int ix) {
-  const int a = (ix - 1) * H.ld + (iz - 1);
-  fm_sift_up(H, a, H.ttn[a], H.nsts[a]);
 }
 __device__ __forceinline__ void fm_downtree(FmHeap& H) {
   if (H.ntr == 1) { H.ntr--; return; }
-  const int self = H.pos[H.ntr];
-  const double t = H.key[H.ntr];
+  const FmEnt last = fm_ld(H.ent + H.ntr);
   H.ntr--;
   const int ntr = H.ntr;
   int tpp = 1, tpc = 2;
   // the entry taken from the end sinks from the root: at each level the smaller child (the left one on a tie) moves up
   // while it is smaller than the sinking entry -- the Fortran's swaps, without writing the sinking entry at every level
   while (tpc < ntr) {
-    double kc = H.key[tpc];
-    const double kr = H.key[tpc + 1];
-    if (kc > kr) { tpc = tpc + 1; kc = kr; }
-    if (kc < t) {
-      const int hc = H.pos[tpc];
-      HN(H, hc) = tpp;
-      H.pos[tpp] = hc; H.key[tpp] = kc;
+    FmEnt c = fm_ld(H.ent + tpc);
+    const FmEnt r = fm_ld(H.ent + tpc + 1);
+    if (c.key > r.key) { tpc = tpc + 1; c = r; }
+    if (c.key < last.key) {
+      H.nsts[c.pos] = tpp;
+      fm_st(H.ent + tpp, c.key, c.pos);
       tpp = tpc;
       tpc = 2 * tpp;
     } else tpc = ntr + 1;
   }
   if (tpc == ntr) {
-    const double kc = H.key[tpc];
-    if (kc < t) {
-      const int hc = H.pos[tpc];
-      HN(H, hc) = tpp;
-      H.pos[tpp] = hc; H.key[tpp] = kc;
+    const FmEnt c = fm_ld(H.ent + tpc);
+    if (c.key < last.key) {
+      H.nsts[c.pos] = tpp;
+      fm_st(H.ent + tpp, c.key, c.pos);
       tpp = tpc;
     }
   }
-  H.pos[tpp] = self; H.key[tpp] = t;
-  HN(H, self) = tpp;
+  fm_st(H.ent + tpp, last.key, last.pos);
+  H.nsts[last.pos] = tpp;
 }
 __device__ __forceinline__ double fm_qsolve(double a, double b, double c) {
   double rd1 = b * b - 4.0 * a * c;
   if (rd1 < 0.0) rd1 = 0.0;
   return (-b + sqrt(rd1)) / (2.0 * a);
 }
+// t / 3.0, correctly rounded, without computing a reciprocal: with y = RN(1/3), q = RN(t y) is within one ulp of t/3, the
+// residual r = t - 3 q is exact in one fma, and RN(q + r y) is the correctly rounded quotient (Markstein's final step -- the
+// same one the compiler's own division sequence ends with).  Outside the range where r cannot underflow: the division itself.
+__device__ __forceinline__ double fm_div3(double t) {
+  const double y = 1.0 / 3.0;
+  const double m = fabs(t);
+  if (m < 1.0e300 && m > 1.0e-280) {
+    const double q = t * y;
+    const double r = fma(-3.0, q, t);
+    return fma(r, y, q);
+  }
+  return t / 3.0;
+}
+// what a stencil needs of the grid, in registers of the stencil warp
+struct FmSten {
+  int nnx, nnz, ld, fom;
+  unsigned ld_magic;
+  double dnx, dnz;
+  const double* slow; double* ttn; const int32_t* nsts;
+};
 // ONE quadrant (the neighbour pair j = ix + dj, k = iz + dk) of fouds1 / fouds2 (fm2d_ttime.f90:138-197, 199-345) for the node
-// (iz, ix): the candidate travel time of that stencil, or false when it has no solution.  The Fortran takes the minimum of
-// the (up to) four candidates in the order (j, k) = (-,-), (-,+), (+,-), (+,+); a minimum does not depend on the order.
-__device__ bool fm_quadrant(const FmGrid& G, int iz, int ix, int dj, int dk, double* trav_out) {
+// (iz, ix) = linear index a: the candidate travel time of that stencil, or false when it has no solution.  The Fortran takes
+// the minimum of the (up to) four candidates in the order (j, k) = (-,-), (-,+), (+,-), (+,+); a minimum does not depend on
+// the order.
+__device__ __forceinline__ bool fm_quadrant(const FmSten& G, int a, int iz, int ix, int dj, int dk, double* trav_out) {
   const int j = ix + dj, k = iz + dk;
   if (j < 1 || j > G.nnx || k < 1 || k > G.nnz) return false;
-  const double slown = 1.0 / FVELN(G, iz, ix), dnx = G.dnx, dnz = G.dnz;
-  const int sj = FNSTS(G, iz, j), sk = FNSTS(G, k, ix);
-  double a = 0, b = 0, c = 0, tref = 0, tdiv = 1.0, u, v, em;
+  const int aj = a + dj * G.ld, ak = a + dk; // (iz, j) and (k, ix)
+  const double slown = G.slow[a], dnx = G.dnx, dnz = G.dnz;
+  const int sj = G.nsts[aj], sk = G.nsts[ak];
+  double a2 = 0, b = 0, c = 0, tref = 0, u, v, em;
+  bool third = false; // the Fortran's final division by 3 (second-order operators)
   int swsol = 0;
   if (G.fom == 0) {
     if (sj == 0) {
       swsol = 1;
-      const double tj = FTTN(G, iz, j);
+      const double tj = G.ttn[aj];
       if (sk == 0) {
-        u = dnx; v = dnz; em = FTTN(G, k, ix) - tj;
-        a = u * u + v * v;
+        u = dnx; v = dnz; em = G.ttn[ak] - tj;
+        a2 = u * u + v * v;
         b = -2.0 * (u * u) * em;
         c = (u * u) * (em * em - (v * v) * (slown * slown));
         tref = tj;
-      } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; }
+      } else { a2 = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; }
     } else if (sk == 0) {
       swsol = 1;
       const double sd = slown * dnz;
-      a = 1.0; b = 0.0; c = -(sd * sd); tref = FTTN(G, k, ix);
+      a2 = 1.0; b = 0.0; c = -(sd * sd); tref = G.ttn[ak];
     }
   } else {
     int swj = -1, swk = -1;
     const int j2 = j + dj, k2 = k + dk;
-    if (j2 >= 1 && j2 <= G.nnx) { if (FNSTS(G, iz, j2) == 0) swj = 0; }
-    const double tj = FTTN(G, iz, j);
+    const int aj2 = aj + dj * G.ld, ak2 = ak + dk;
+    if (j2 >= 1 && j2 <= G.nnx) { if (G.nsts[aj2] == 0) swj = 0; }
+    const double tj = G.ttn[aj];
     double tj2 = 0;
-    if (sj == 0 && swj == 0) { swj = -1; tj2 = FTTN(G, iz, j2); if (tj > tj2) swj = 0; }
+    if (sj == 0 && swj == 0) { swj = -1; tj2 = G.ttn[aj2]; if (tj > tj2) swj = 0; }
     else swj = -1;
-    if (k2 >= 1 && k2 <= G.nnz) { if (FNSTS(G, k2, ix) == 0) swk = 0; }
-    const double tk = FTTN(G, k, ix);
+    if (k2 >= 1 && k2 <= G.nnz) { if (G.nsts[ak2] == 0) swk = 0; }
+    const double tk = G.ttn[ak];
     double tk2 = 0;
-    if (sk == 0 && swk == 0) { swk = -1; tk2 = FTTN(G, k2, ix); if (tk > tk2) swk = 0; }
+    if (sk == 0 && swk == 0) { swk = -1; tk2 = G.ttn[ak2]; if (tk > tk2) swk = 0; }
     else swk = -1;
     if (swj == 0) {
       swsol = 1;
@@ -212,62 +249,58 @@ __device__ bool fm_quadrant(const FmGrid& G, int iz, int ix, int dj, int dk, dou
         u = 2.0 * dnx; v = 2.0 * dnz;
         em = 4.0 * tj - tj2 - 4.0 * tk;
         em = em + tk2;
-        a = v * v + u * u;
+        a2 = v * v + u * u;
         b = 2.0 * em * (u * u);
         c = (u * u) * (em * em - (slown * slown) * (v * v));
         tref = 4.0 * tj - tj2;
-        tdiv = 3.0;
+        third = true;
       } else if (sk == 0) {
         u = dnz; v = 2.0 * dnx;
         em = 3.0 * tk - 4.0 * tj + tj2;
-        a = v * v + 9.0 * (u * u);
+        a2 = v * v + 9.0 * (u * u);
         b = 6.0 * em * (u * u);
         c = (u * u) * (em * em - (slown * slown) * (v * v));
         tref = tk;
-        tdiv = 1.0;
       } else {
         u = 2.0 * dnx;
-        a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
+        a2 = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
         tref = 4.0 * tj - tj2;
-        tdiv = 3.0;
+        third = true;
       }
     } else if (sj == 0) {
       swsol = 1;
       if (swk == 0) {
         u = dnx; v = 2.0 * dnz;
         em = 3.0 * tj - 4.0 * tk + tk2;
-        a = v * v + 9.0 * (u * u);
+        a2 = v * v + 9.0 * (u * u);
         b = 6.0 * em * (u * u);
         c = (u * u) * (em * em - (v * v) * (slown * slown));
         tref = tj;
-        tdiv = 1.0;
       } else if (sk == 0) {
         u = dnx; v = dnz;
         em = tk - tj;
-        a = u * u + v * v;
+        a2 = u * u + v * v;
         b = -2.0 * (u * u) * em;
         c = (u * u) * (em * em - (v * v) * (slown * slown));
         tref = tj;
-        tdiv = 1.0;
-      } else { a = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; tdiv = 1.0; }
+      } else { a2 = 1.0; b = 0.0; c = -(slown * slown) * (dnx * dnx); tref = tj; }
     } else {
       if (swk == 0) {
         swsol = 1;
         u = 2.0 * dnz;
-        a = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
+        a2 = 1.0; b = 0.0; c = -(u * u) * (slown * slown);
         tref = 4.0 * tk - tk2;
-        tdiv = 3.0;
+        third = true;
       } else if (sk == 0) {
         swsol = 1;
-        a = 1.0; b = 0.0; c = -(slown * slown) * (dnz * dnz);
+        a2 = 1.0; b = 0.0; c = -(slown * slown) * (dnz * dnz);
         tref = tk;
-        tdiv = 1.0;
       }
     }
   }
   if (!swsol) return false;
-  const double t = tref + fm_qsolve(a, b, c);
-  *trav_out = tdiv == 3.0 ? t / 3.0 : t; // tdiv is 1 or 3; x / 1.0 == x
+  const double t = tref + fm_qsolve(a2, b, c);
+  *trav_out = third ? fm_div3(t) : t; // the divisor is 1 or 3; x / 1.0 == x
   return true;
 }
 __device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3][3], double dsx, double dsz) {
@@ -279,19 +312,63 @@ __device__ __forceinline__ double fm_bilinear(const FmGrid& G, const double nv[3
     }
   return biv;
 }
-// travel (fm2d_ttime.f90:27-136), by the whole warp.  The march order is the heap's, so nodes are accepted one at a time
-// (lane 0 owns the heap); the work per accepted node -- up to four neighbour updates of up to four stencil quadrants each
-// -- is independent (a neighbour being updated is not alive, and the stencils only read alive nodes), so lanes 16..31
-// solve one (neighbour, quadrant) each on the state before the updates WHILE lane 0 re-orders the heap after the pop
-// (downtree only moves heap positions, i.e. positive status values, which no stencil distinguishes), a shuffle takes the
-// minima, and lane 0 writes the times and sifts the neighbours in the reference's order (x-1, x+1, z-1, z+1).
-// urg 0/1: nsts must already be -1 everywhere (the caller's lanes fill it).  G lives in shared memory.
+// The stencil warp of a problem (warp 1 of the block).  For every node the heap warp accepts it solves the (up to) four
+// stencil quadrants of the (up to) four neighbours, one (neighbour, quadrant) per lane on lanes 0..15, takes the minimum per
+// neighbour and writes the neighbour's new travel time -- on the state before the updates (a neighbour being updated is not
+// alive, and the stencils only read alive nodes), WHILE the heap warp re-orders the heap after the pop (downtree only moves
+// heap positions, i.e. positive status values, which no stencil distinguishes).  Barrier A: a command is ready; barrier B:
+// the travel times are written.
+__device__ void fm_stencil_warp(const FmGrid& G, volatile int* sh, int lane) {
+  FmSten S;
+  S.nnx = S.nnz = S.ld = S.fom = 0; S.ld_magic = 0; S.dnx = S.dnz = 0; S.slow = nullptr; S.ttn = nullptr; S.nsts = nullptr;
+  const int n = (lane >> 2) & 3, q = lane & 3;
+  const int dj = (q >> 1) ? 1 : -1, dk = (q & 1) ? 1 : -1;
+  int off = 0;
+  for (;;) {
+    fm_bar_a();
+    const int h = sh[0];
+    if (h == FM_CMD_QUIT) return;
+    if (h == FM_CMD_GRID) {
+      S.nnx = G.nnx; S.nnz = G.nnz; S.ld = G.ld; S.fom = G.fom; S.ld_magic = G.ld_magic; S.dnx = G.dnx; S.dnz = G.dnz;
+      S.slow = G.slow; S.ttn = G.ttn; S.nsts = G.nsts;
+      off = n == 0 ? -S.ld : (n == 1 ? S.ld : (n == 2 ? -1 : 1));
+      fm_bar_b();
+      continue;
+    }
+    const int ix = fm_row(h, S.ld, S.ld_magic) + 1, iz = h - (ix - 1) * S.ld + 1;
+    const int nix = n == 0 ? ix - 1 : (n == 1 ? ix + 1 : ix), niz = n == 2 ? iz - 1 : (n == 3 ? iz + 1 : iz);
+    const int a = h + off;
+    int st = 0; // the neighbour's status; 0 = nothing to do (alive or outside)
+    double trav = 0;
+    bool has = false;
+    if (lane < 16 && nix >= 1 && nix <= S.nnx && niz >= 1 && niz <= S.nnz) st = S.nsts[a];
+    if (st != 0) has = fm_quadrant(S, a, niz, nix, dj, dk, &trav);
+    // minimum of the quadrants that have a solution
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const double ot = __shfl_xor_sync(0xffffffffu, trav, o);
+      const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, o) != 0;
+      if (oh && (!has || ot < trav)) trav = ot;
+      has = has || oh;
+    }
+    // every stencil has read the state before any time is written: the lanes of a warp are past their loads here
+    if (q == 0 && st != 0) S.ttn[a] = has ? trav : 0.0; // (no stencil solved: travm is undefined in the Fortran; cannot happen next to an alive node)
+    fm_bar_b();
+  }
+}
+// travel (fm2d_ttime.f90:27-136), the heap warp's side (warp 0; lane 0 owns the heap).  The march order is the heap's, so
+// nodes are accepted one at a time; after the stencil warp has written the neighbours' times, lane 0 sifts the neighbours in
+// the reference's order (x-1, x+1, z-1, z+1).  urg 0/1: nsts must already be -1 everywhere (the caller's lanes fill it).
+// G lives in shared memory.
 __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, volatile int* sh) {
   FmHeap H;
-  H.pos = G.heap; H.key = G.hkey; H.nsts = G.nsts; H.ttn = G.ttn; H.ld = G.ld; H.ntr = 0; H.maxbt = G.maxbt;
-  const int nnx = G.nnx, nnz = G.nnz;
+  H.ent = G.heap; H.nsts = G.nsts; H.ttn = G.ttn; H.ntr = 0; H.maxbt = G.maxbt;
+  const int nnx = G.nnx, nnz = G.nnz, ld = G.ld;
+  const unsigned magic = G.ld_magic;
   int error = 0;
   unsigned n_accept = 0, n_update = 0;
+  if (lane == 0) sh[0] = FM_CMD_GRID;
+  fm_bar_a();
   if (lane == 0) {
     int isx = (int)((scx - G.gox) / G.dnx) + 1;
     int isz = (int)((scz - G.goz) / G.dnz) + 1;
@@ -300,9 +377,12 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
       if (isx == nnx) isx--;
       if (isz == nnz) isz--;
       if (urg == 2) {
-        for (int i = 1; i <= nnx && !error; ++i)
-          for (int j = 1; j <= nnz; ++j)
-            if (FNSTS(G, j, i) > 0) { if (!fm_addtree(H, j, i)) { error = 2; break; } }
+        // every node with a positive status, x outer, z inner; only the window mapped from the refined grid can hold one
+        for (int i = G.vnl; i <= G.vnr && !error; ++i)
+          for (int j = G.vnt; j <= G.vnb; ++j) {
+            const int a = (i - 1) * ld + (j - 1);
+            if (H.nsts[a] > 0) { if (!fm_addtree(H, a, H.ttn[a])) { error = 2; break; } }
+          }
       } else {
         double vss[3][3];
         for (int i = 1; i <= 2; ++i) for (int j = 1; j <= 2; ++j) vss[i][j] = FVELN(G, isz - 1 + j, isx - 1 + i);
@@ -313,67 +393,60 @@ __device__ void fm_travel(FmGrid& G, double scx, double scz, int urg, int lane, 
           for (int j = 1; j <= 2; ++j) {
             const double ex = dsx - (i - 1) * G.dnx, ez = dsz - (j - 1) * G.dnz;
             const double ds = sqrt(ex * ex + ez * ez);
-            FTTN(G, isz - 1 + j, isx - 1 + i) = 2.0 * ds / (vss[i][j] + vsrc);
-            if (!fm_addtree(H, isz - 1 + j, isx - 1 + i)) error = 2;
+            const double t0 = 2.0 * ds / (vss[i][j] + vsrc);
+            const int a = (isx - 1 + i - 1) * ld + (isz - 1 + j - 1);
+            G.ttn[a] = t0;
+            if (!fm_addtree(H, a, t0)) error = 2;
           }
       }
     }
   }
-  __syncwarp();
+  fm_bar_b();
   for (;;) {
+    int h = -1, ix = 0, iz = 0;
+    if (lane == 0 && H.ntr > 0 && !error) {
+      h = H.ent[1].pos;
+      ix = fm_row(h, ld, magic) + 1; iz = h - (ix - 1) * ld + 1;
+      H.nsts[h] = 0;
+      if (urg == 1) {
+        bool swrg = false;
+        if (ix == 1 && G.vnl != 1) swrg = true;
+        if (ix == nnx && G.vnr != nnx) swrg = true; // (refined extent against a coarse index, as the Fortran has it)
+        if (iz == 1 && G.vnt != 1) swrg = true;
+        if (iz == nnz && G.vnb != nnz) swrg = true;
+        if (swrg) h = -1;
+      }
+      if (h >= 0) sh[0] = h;
+    }
+    if (__shfl_sync(0xffffffffu, h, 0) < 0) break;
+    fm_bar_a();
+    int s[4] = {0, 0, 0, 0};
     if (lane == 0) {
-      int go = 0;
-      if (H.ntr > 0 && !error) {
-        const int h = H.pos[1];
-        const int ix = h / H.ld + 1, iz = h - (ix - 1) * H.ld + 1;
-        int swrg = 0;
-        if (urg == 1) {
-          if (ix == 1 && G.vnl != 1) swrg = 1;
-          if (ix == nnx && G.vnr != nnx) swrg = 1; // (refined extent against a coarse index, as the Fortran has it)
-          if (iz == 1 && G.vnt != 1) swrg = 1;
-          if (iz == nnz && G.vnb != nnz) swrg = 1;
+      n_accept++;
+      fm_downtree(H);
+      // the neighbours' status, read while the stencils run: its sign is all that matters and no sift changes a sign
+      if (ix > 1) s[0] = H.nsts[h - ld];
+      if (ix < nnx) s[1] = H.nsts[h + ld];
+      if (iz > 1) s[2] = H.nsts[h - 1];
+      if (iz < nnz) s[3] = H.nsts[h + 1];
+    }
+    fm_bar_b();
+    if (lane == 0) {
+      double t[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int a = h + (m == 0 ? -ld : (m == 1 ? ld : (m == 2 ? -1 : 1)));
+        t[m] = s[m] != 0 ? H.ttn[a] : 0.0;
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (s[m] != 0 && !error) {
+          const int a = h + (m == 0 ? -ld : (m == 1 ? ld : (m == 2 ? -1 : 1)));
+          n_update++;
+          if (s[m] == -1) { if (!fm_addtree(H, a, t[m])) error = 2; } else fm_sift_up(H, a, t[m], H.nsts[a]);
         }
-        HN(H, h) = 0;
-        if (!swrg) { sh[1] = ix; sh[2] = iz; go = 1; }
-      }
-      sh[0] = go;
-    }
-    __syncwarp();
-    if (!sh[0]) break;
-    const int ix = sh[1], iz = sh[2];
-    // (neighbour n, quadrant q) on lane 16 + 4n + q; lane 0 sinks the heap's last entry from the root meanwhile
-    const int n = (lane >> 2) & 3, q = lane & 3;
-    const int nix = n == 0 ? ix - 1 : (n == 1 ? ix + 1 : ix), niz = n == 2 ? iz - 1 : (n == 3 ? iz + 1 : iz);
-    int st = 0; // the neighbour's status; 0 = nothing to do (alive or outside)
-    double trav = 0;
-    bool has = false;
-    if (lane == 0) { n_accept++; fm_downtree(H); }
-    else if (lane >= 16) {
-      if (nix >= 1 && nix <= nnx && niz >= 1 && niz <= nnz) st = FNSTS(G, niz, nix);
-      if (st != 0) has = fm_quadrant(G, niz, nix, (q >> 1) ? 1 : -1, (q & 1) ? 1 : -1, &trav);
-    }
-    __syncwarp(); // every stencil has read the state before any update; the heap is in order again
-    // minimum of the quadrants that have a solution
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-      const double ot = __shfl_xor_sync(0xffffffffu, trav, o);
-      const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, o) != 0;
-      if (oh && (!has || ot < trav)) trav = ot;
-      has = has || oh;
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const double tm = __shfl_sync(0xffffffffu, trav, 16 + 4 * m);
-      const int sm = __shfl_sync(0xffffffffu, st, 16 + 4 * m);
-      const bool hm = __shfl_sync(0xffffffffu, has ? 1 : 0, 16 + 4 * m) != 0;
-      if (lane == 0 && sm != 0 && !error) {
-        const int mx = m == 0 ? ix - 1 : (m == 1 ? ix + 1 : ix), mz = m == 2 ? iz - 1 : (m == 3 ? iz + 1 : iz);
-        n_update++;
-        FTTN(G, mz, mx) = hm ? tm : 0.0; // (no stencil solved: travm is undefined in the Fortran; cannot happen next to an alive node)
-        if (sm == -1) { if (!fm_addtree(H, mz, mx)) error = 2; } else fm_updtree(H, mz, mx);
       }
     }
-    __syncwarp();
   }
   if (lane == 0) { G.error = error; G.n_accept = n_accept; G.n_update = n_update; G.ntr = H.ntr; }
   __syncwarp();
@@ -475,8 +548,8 @@ __device__ int fm_trace_ray(const FmRayCtx& C, double scx, double scz, double rx
   return nrp;
 }
 
-__global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmParams P) {
-  const int lane = threadIdx.x;
+// One (period, source) problem, by the heap warp (warp 0 of the block); the stencil warp serves fm_travel.
+__device__ void fm2d_problem(const FmParams& P, FmGrid& G, volatile int& s_err, volatile int* s_sh, int lane) {
   const int prob = blockIdx.x;
   const int map = prob / P.nsrc, isrc = prob - map * P.nsrc; // 0-based
   const int32_t* srs = P.srs + (size_t)map * P.srs_ms + (size_t)isrc * P.nrc;
@@ -488,29 +561,18 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   if (any == 0 && isrc != 0) return; // no valid rays for this source (unless it is the first): cycle
   const double x = P.scx[isrc], z = P.scz[isrc];
   const double dnx0 = P.dvx / P.gdx, dnz0 = P.dvz / P.gdz;
-  // scratch: coarse ttn | coarse nsts | refined veln | refined ttn | refined nsts | heap
+  // scratch: coarse ttn | refined veln | refined slowness | refined ttn | coarse nsts | refined nsts | heap entries
   const size_t cc = (size_t)P.nnx * P.nnz, cr = (size_t)P.ldr * P.ldr;
   char* base = P.scratch + (size_t)prob * P.scratch_per_problem;
   double* ttn_c = (double*)base;
   double* veln_r = ttn_c + cc;
-  double* ttn_r = veln_r + cr;
+  double* slow_r = veln_r + cr;
+  double* ttn_r = slow_r + cr;
   int32_t* nsts_c = (int32_t*)(ttn_r + cr);
   int32_t* nsts_r = nsts_c + cc;
-  int32_t* heap = nsts_r + cr;
-  double* hkey = (double*)(((uintptr_t)(heap + P.maxbt_alloc + 2) + 7) & ~(uintptr_t)7);
-  extern __shared__ __align__(16) unsigned char fm_smem[];
-  if (P.use_smem) { // the march is a chain of dependent loads: shared memory (~30 cycles) instead of L2 (~300) per hop
-    ttn_c = (double*)fm_smem;
-    ttn_r = ttn_c + cc;
-    nsts_c = (int32_t*)(ttn_r + cr);
-    nsts_r = nsts_c + cc;
-    heap = nsts_r + cr;
-    hkey = (double*)(((uintptr_t)(heap + P.maxbt_alloc + 2) + 7) & ~(uintptr_t)7);
-  }
+  FmEnt* heap = (FmEnt*)(((uintptr_t)(nsts_r + cr) + 15) & ~(uintptr_t)15);
+  int32_t* stage = (int32_t*)heap; // the (idle) heap doubles as staging between the two marches
   for (size_t q = lane; q < cc; q += 32) ttn_c[q] = 0.0; // nodes the march never reaches read 0 (see the check after the march)
-  __shared__ FmGrid G;
-  __shared__ int s_err;
-  __shared__ int s_sh[4];
   int isx = (int)((x - P.gox) / dnx0) + 1, isz = (int)((z - P.goz) / dnz0) + 1;
   if (isx < 1 || isx > P.nnx || isz < 1 || isz > P.nnz) { if (lane == 0) P.err[prob] = 1; return; }
   if (isx == P.nnx) isx--;
@@ -520,6 +582,7 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   int vnt = isz - P.sgs; if (vnt < 1) vnt = 1;
   int vnb = isz + P.sgs; if (vnb > P.nnz) vnb = P.nnz;
   const double* veln_c = P.veln + (size_t)map * cc;
+  const double* slow_c = P.slow + (size_t)map * cc;
   const int maxbt0 = (int)floor(P.snb * P.nnx * P.nnz + 0.5); // NINT of a positive value
   unsigned nacc = 0, nupd = 0;
   int nrnx = 0, nrnz = 0;
@@ -547,13 +610,16 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
         for (int j1 = 1; j1 <= 4; ++j1) sum[i1] = sum[i1] + ui[j1] * velv[((size_t)(j - 2 + j1) * (P.nvz + 2) + (i - 2 + i1)) * P.vel_es];
         sum[i1] = vi[i1] * sum[i1];
       }
-      veln_r[(size_t)(idm2 - 1) * P.ldr + (idm1 - 1)] = sum[1] + sum[2] + sum[3] + sum[4];
+      const double vr = sum[1] + sum[2] + sum[3] + sum[4];
+      veln_r[(size_t)(idm2 - 1) * P.ldr + (idm1 - 1)] = vr;
+      slow_r[(size_t)(idm2 - 1) * P.ldr + (idm1 - 1)] = 1.0 / vr;
     }
     for (size_t q = lane; q < cr; q += 32) nsts_r[q] = -1;
     __syncwarp();
     if (lane == 0) {
       G.nnx = nrnx; G.nnz = nrnz; G.ld = P.ldr; G.gox = gorx; G.goz = gorz; G.dnx = drnx; G.dnz = drnz;
-      G.veln = veln_r; G.ttn = ttn_r; G.nsts = nsts_r; G.heap = heap; G.hkey = hkey; G.fom = P.fom;
+      G.ld_magic = 0xFFFFFFFFu / (unsigned)P.ldr + 1u;
+      G.veln = veln_r; G.slow = slow_r; G.ttn = ttn_r; G.nsts = nsts_r; G.heap = heap; G.fom = P.fom;
       G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
       int mb = maxbt0;
       if (nrnx > P.nnx || nrnz > P.nnz) { const int a = nrnx > P.nnx ? nrnx : P.nnx, b = nrnz > P.nnz ? nrnz : P.nnz; mb = (int)floor(P.snb * a * b + 0.5); }
@@ -587,18 +653,19 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
         if (l + 1 <= P.nnz && nsts_c[(size_t)(k - 1) * P.nnz + l] == -1) far = true;
         if (k - 1 >= 1 && nsts_c[(size_t)(k - 2) * P.nnz + (l - 1)] == -1) far = true;
         if (k + 1 <= P.nnx && nsts_c[(size_t)k * P.nnz + (l - 1)] == -1) far = true;
-        heap[1 + t] = far ? 1 : 0; // staged in the (idle) heap array: applied after every lane has looked
-      } else heap[1 + t] = 0;
+        stage[1 + t] = far ? 1 : 0; // applied after every lane has looked
+      } else stage[1 + t] = 0;
     }
     __syncwarp();
     for (int t = lane; t < nk * nl; t += 32) {
       const int l = vnt + t % nk, k = vnl + t / nk;
-      if (heap[1 + t]) nsts_c[(size_t)(k - 1) * P.nnz + (l - 1)] = 1;
+      if (stage[1 + t]) nsts_c[(size_t)(k - 1) * P.nnz + (l - 1)] = 1;
     }
     __syncwarp();
     if (lane == 0) {
       G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
-      G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.n_accept = 0; G.n_update = 0;
+      G.ld_magic = 0xFFFFFFFFu / (unsigned)P.nnz + 1u;
+      G.veln = veln_c; G.slow = slow_c; G.ttn = ttn_c; G.nsts = nsts_c; G.n_accept = 0; G.n_update = 0;
     }
     __syncwarp();
     fm_travel(G, x, z, 2, lane, s_sh);
@@ -608,7 +675,8 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
     __syncwarp();
     if (lane == 0) {
       G.nnx = P.nnx; G.nnz = P.nnz; G.ld = P.nnz; G.gox = P.gox; G.goz = P.goz; G.dnx = dnx0; G.dnz = dnz0;
-      G.veln = veln_c; G.ttn = ttn_c; G.nsts = nsts_c; G.heap = heap; G.hkey = hkey; G.fom = P.fom; G.maxbt = maxbt0;
+      G.ld_magic = 0xFFFFFFFFu / (unsigned)P.nnz + 1u;
+      G.veln = veln_c; G.slow = slow_c; G.ttn = ttn_c; G.nsts = nsts_c; G.heap = heap; G.fom = P.fom; G.maxbt = maxbt0;
       G.vnl = vnl; G.vnr = vnr; G.vnt = vnt; G.vnb = vnb; G.error = 0; G.n_accept = 0; G.n_update = 0;
     }
     __syncwarp();
@@ -707,9 +775,22 @@ __global__ void __launch_bounds__(32) fm2d_kernel(const __grid_constant__ FmPara
   }
 }
 
+// a block = one problem = two warps: warp 0 owns the heap and everything around the march, warp 1 solves the stencils
+__global__ void __launch_bounds__(64) fm2d_kernel(const __grid_constant__ FmParams P) {
+  __shared__ FmGrid G;
+  __shared__ int s_err;
+  __shared__ int s_sh[4];
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) { fm_stencil_warp(G, s_sh, lane); return; }
+  fm2d_problem(P, G, s_err, s_sh, lane);
+  __syncwarp();
+  if (lane == 0) s_sh[0] = FM_CMD_QUIT;
+  fm_bar_a();
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 namespace {
-DevBuf fm_veln, fm_scratch, fm_err, fm_geo, fm_srs, fm_vel, fm_tt, fm_rays;
+DevBuf fm_veln, fm_slow, fm_scratch, fm_err, fm_geo, fm_srs, fm_vel, fm_tt, fm_rays;
 
 int fm2d_launch(FmParams& P, cudaStream_t st) {
   int rc;
@@ -719,23 +800,20 @@ int fm2d_launch(FmParams& P, cudaStream_t st) {
   const size_t cc = (size_t)P.nnx * P.nnz, cr = (size_t)P.ldr * P.ldr;
   const int a = std::max(P.ldr, P.nnx), b = std::max(P.ldr, P.nnz);
   const size_t maxbt = (size_t)std::max(floor(P.snb * P.nnx * P.nnz + 0.5), floor(P.snb * a * b + 0.5)) + 4;
-  P.maxbt_alloc = (int)maxbt;
-  const size_t smem = 8 * (cc + cr) + 4 * (cc + cr + maxbt + 4) + 8 * (maxbt + 2) + 16;
-  // measured: the march is bound by the latency of its own arithmetic, not of memory -- shared memory gained nothing at
-  // example1's size and limits the problems in flight to one per SM; kept as an experiment (MCT_FM2D_SMEM=1)
-  P.use_smem = smem <= 200 * 1024 && getenv("MCT_FM2D_SMEM") != nullptr;
-  if (P.use_smem) CK(cudaFuncSetAttribute(fm2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  size_t per = 8 * (cc + 2 * cr) + 4 * (cc + cr + maxbt + 4) + 8 * (maxbt + 2) + 16;
+  const size_t win = (size_t)(2 * P.sgs + 1) * (2 * P.sgs + 1) + 4; // staging of the refined -> coarse mapping
+  P.heap_bytes = (std::max(sizeof(FmEnt) * maxbt, 4 * win) + 15) & ~(size_t)15;
+  size_t per = 8 * (cc + 3 * cr) + 4 * (cc + cr) + 16 + P.heap_bytes;
   per = (per + 15) & ~(size_t)15;
   P.scratch_per_problem = per;
   const int nprob = P.nmaps * P.nsrc;
   if ((rc = ensure(fm_veln, 8 * cc * (size_t)P.nmaps))) return rc;
+  if ((rc = ensure(fm_slow, 8 * cc * (size_t)P.nmaps))) return rc;
   if ((rc = ensure(fm_scratch, per * (size_t)nprob))) return rc;
-  P.veln = (double*)fm_veln.p; P.scratch = (char*)fm_scratch.p;
+  P.veln = (double*)fm_veln.p; P.slow = (double*)fm_slow.p; P.scratch = (char*)fm_scratch.p;
   P.counters = g.count_on ? (unsigned long long*)g.counters.p + 10 : nullptr;
   ProfScope ps(2, st);
   fm2d_gridder_kernel<<<grid_blocks((long long)cc * P.nmaps, 256, 8), 256, 0, st>>>(P);
-  fm2d_kernel<<<nprob, 32, P.use_smem ? smem : 0, st>>>(P);
+  fm2d_kernel<<<nprob, 64, 0, st>>>(P);
   CK(cudaGetLastError());
   g.host_stats.n_launches += 2;
   return MCT_OK;
@@ -1003,7 +1081,7 @@ int mct_session_likelihood_fm2d(mct_session* s, int pending, const double* snois
 
 namespace {
 void release_fm2d_globals() {
-  DevBuf* bufs[] = {&fm_veln, &fm_scratch, &fm_err, &fm_geo, &fm_srs, &fm_vel, &fm_tt, &fm_rays};
+  DevBuf* bufs[] = {&fm_veln, &fm_slow, &fm_scratch, &fm_err, &fm_geo, &fm_srs, &fm_vel, &fm_tt, &fm_rays};
   for (DevBuf* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 } // namespace
