@@ -5,15 +5,16 @@
 // branch of surf_likelihood on a session's resident maps (mct_session_likelihood_fm2d).
 //
 // The unit of parallelism is the reference's own: every (period, source) pair is an independent eikonal problem
-// (the Fortran loops over sources inside an OpenMP loop over periods).  One warp per problem, all of them in one launch.
-// Fast marching accepts nodes strictly in the order of a binary heap, and the reference's travel times depend on that
-// order (which neighbours are alive when a node is updated), so the march keeps the Fortran's heap, stencils and
-// operation order; inside one accepted node the (up to) 4 x 4 stencil quadrants are solved by 16 lanes while lane 0
-// re-orders the heap (fm_travel).  What is data-parallel inside a problem -- B-spline velocities of the propagation grid
-// and of the refined source grid, the narrow-band completion sweep, the receiver interpolation, the ray tracing of rpaths
-// (one receiver per lane) -- is spread over the lanes.  Results are bit-identical to oracle/fm2d_ref.c: receiver times,
-// the whole field, node / stencil counts, every ray point.  Throughput comes from the number of problems in flight
-// (np x nsrc: 88 in example1, thousands in the multi-mode configurations), not from one problem's latency.
+// (the Fortran loops over sources inside an OpenMP loop over periods).  One block of two warps per problem, all of them in
+// one launch.  Fast marching accepts nodes strictly in the order of a binary heap, and the reference's travel times depend
+// on that order (which neighbours are alive when a node is updated), so the march keeps the Fortran's heap, stencils and
+// operation order; inside one accepted node the (up to) 4 x 4 stencil quadrants are solved by 16 lanes of the stencil warp
+// while lane 0 of the heap warp re-orders the heap (fm_travel / fm_stencil_warp, two named barriers per node).  What is
+// data-parallel inside a problem -- B-spline velocities of the propagation grid and of the refined source grid, the
+// narrow-band completion sweep, the receiver interpolation, the ray tracing of rpaths (one receiver per lane) -- is spread
+// over the lanes of warp 0.  Results are bit-identical to oracle/fm2d_ref.c: receiver times, the whole field, node /
+// stencil counts, every ray point.  Throughput comes from the number of problems in flight (np x nsrc: 88 in example1,
+// thousands in the multi-mode configurations); one problem's latency is the heap warp's dependent instructions.
 #pragma once
 
 struct FmParams {
@@ -101,8 +102,9 @@ struct FmGrid {
 // commands of the heap warp to the stencil warp (>= 0: the linear index of the node just accepted)
 #define FM_CMD_GRID (-2)
 #define FM_CMD_QUIT (-3)
-__device__ __forceinline__ void fm_bar_a() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-__device__ __forceinline__ void fm_bar_b() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+// (barrier.sync, not bar.sync = barrier.sync.aligned: lane 0 of the heap warp arrives from its own branch)
+__device__ __forceinline__ void fm_bar_a() { asm volatile("barrier.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void fm_bar_b() { asm volatile("barrier.sync 2, 64;" ::: "memory"); }
 __device__ __forceinline__ int fm_row(int h, int ld, unsigned magic) { // h / ld for 0 <= h < 2^31, ld >= 2
   int q = (int)__umulhi((unsigned)h, magic);
   if (q * ld > h) q--;
