@@ -1,6 +1,7 @@
 #!/bin/bash
 # oracle/build_ref.sh -- builds the reference-derived checkers under the git-ignored oracle/_ref/:
 #   libsurfdisp96_f2c.so  the reference's surfdisp96.f through oracle/f77toc.py (mechanical F77 -> C) + gcc
+#   libfm2d_ttime_f2c.so  the reference's fm2d/fm2d_ttime.f90 through oracle/f90toc.py (mechanical F90 -> C) + gcc
 #   surfdisp96_gfortran   the same file compiled by gfortran, where one exists (oracle/build_ref_surfdisp.sh)
 #   kdtree2_ref           from the reference's OWN pre-built
 # object utils/libutils.a:kdtree2.o (linked where it lies; nothing is copied into the repo
@@ -20,6 +21,18 @@ if [ -f "$REF/surfmodes/surfdisp96.f" ]; then
   echo "build_ref: built $OUT/libsurfdisp96_f2c.so from $REF/surfmodes/surfdisp96.f"
 else
   echo "build_ref: $REF/surfmodes/surfdisp96.f not present, skipping the translated surfdisp96"
+fi
+# ---- the fast-marching core fm2d/fm2d_ttime.f90 (+ the module variables of fm2d_globalp.f90), translated mechanically to C
+# (oracle/f90toc.py) and compiled behind a small driver that stands in for modrays' allocations
+if [ -f "$REF/fm2d/fm2d_ttime.f90" ] && [ -f "$REF/fm2d/fm2d_globalp.f90" ]; then
+  mkdir -p "$OUT"
+  python "$HERE/f90toc.py" "$REF/fm2d/fm2d_globalp.f90" "$REF/fm2d/fm2d_ttime.f90" \
+      "$REF/fm2d/fm2dray_cartesian.f90:gridder,bsplrefine,srtimes" "$OUT/fm2d_ttime_f2c.c"
+  gcc -O2 -fPIC -std=gnu11 -ffp-contract=off -fno-fast-math -shared -DFM2D_F2C_SOURCE="\"$OUT/fm2d_ttime_f2c.c\"" \
+      -o "$OUT/libfm2d_ttime_f2c.so" "$HERE/ref_harness/fm2d_f90_harness.c" -lm
+  echo "build_ref: built $OUT/libfm2d_ttime_f2c.so from $REF/fm2d/fm2d_ttime.f90 + gridder, bsplrefine, srtimes of fm2dray_cartesian.f90"
+else
+  echo "build_ref: $REF/fm2d/fm2d_ttime.f90 not present, skipping the translated fast-marching core"
 fi
 # ---- and, where a Fortran compiler exists, the real thing (oracle/build_ref_surfdisp.sh)
 if command -v gfortran >/dev/null 2>&1; then "$HERE/build_ref_surfdisp.sh" || true; fi

@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""oracle/f90toc.py -- mechanical Fortran 90 -> C translation of the reference's fast-marching core, fm2d/fm2d_ttime.f90
+(module traveltime: travel, fouds1, fouds2, addtree, downtree, updtree, bilinear) with the module variables of
+fm2d/fm2d_globalp.f90.
+
+TEST INFRASTRUCTURE.  There is no Fortran compiler in the build image; the restatement oracle/fm2d_ref.c would
+otherwise be pinned by physics only.  This script reads the reference's own source WHERE IT LIES (nothing is copied
+into the repository) and translates it statement by statement with the expression machinery of oracle/f77toc.py (every
+node typed as Fortran types it, default-real literals as float literals, integer powers as multiplications, arguments
+by reference, 1-based column-major arrays).  oracle/build_ref.sh compiles the result together with the hand-written
+driver oracle/fm2d_f90_harness.c into the git-ignored oracle/_ref/libfm2d_ttime_f2c.so; tests/test_oracle_fm2d_vs_reference.py
+compares the march of the restatement with it bit for bit (travel times, node status, heap), for urg = 0, 1 and 2.
+
+What is added to f77toc's subset:
+  * free form: `!` comments, blank-insignificant matching after lower-casing (the file has no continuation lines and
+    no character data outside WRITE statements, which are dropped -- they only print);
+  * MODULE / USE / CONTAINS / IMPLICIT NONE; module variables become thread-local C globals (the reference marks them
+    `!$omp threadprivate`); allocatable module arrays become a pointer plus their extents (`x`, `x_d1`, `x_d2`), set by
+    the driver, which plays the part of modrays' ALLOCATE statements;
+  * declarations with attributes (`REAL(KIND=i10), DIMENSION(2,2) :: vss`), kind parameters (i10 = c_double, i5 = single);
+  * the derived type `backpointer` (a C struct), component references `btg(i)%px`, whole-structure assignment;
+  * DO WHILE, EXIT, RETURN, subroutines without dummy arguments; STOP sets `f90_stopped` and returns (it only occurs in
+    `travel` itself).
+
+usage: f90toc.py /root/reference/fm2d/fm2d_globalp.f90 /root/reference/fm2d/fm2d_ttime.f90 \
+                 /root/reference/fm2d/fm2dray_cartesian.f90:gridder,bsplrefine,srtimes out.c
+"""
+import os
+import re
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import f77toc as F                                                     # noqa: E402
+from f77toc import INT, R4, R8, LOG, CT, Node, Unit                     # noqa: E402
+
+STRUCT = 9
+CT[STRUCT] = "backpointer"
+F.TOK = re.compile(F.TOK.pattern.replace("[-+*/(),<>=]", "[-+*/(),<>=%]"), re.X)
+
+
+def read_free_form(path):
+    """[(blank-free lowercase statement text, source line number)]"""
+    out, pending = [], None
+    for ln, raw in enumerate(open(path, errors="replace").read().split("\n"), 1):
+        line = raw.rstrip("\r").replace("\t", " ")
+        s = line.strip()
+        if not s or s.startswith("!"):
+            continue
+        if re.match(r"write\s*\(", s, re.I):            # prints only (its character data may hold `!`)
+            continue
+        bang = line.find("!")
+        if bang >= 0:
+            line = line[:bang]
+        t = re.sub(r"\s+", "", line).lower()
+        if not t:
+            continue
+        if t.startswith("&"):
+            t = t[1:]
+        if pending is not None:                          # the previous line ended in `&`
+            t, ln = pending[0] + t, pending[1]
+            pending = None
+        if t.endswith("&"):
+            pending = (t[:-1], ln)
+            continue
+        out.append((t, ln))
+    return out
+
+
+class Module:
+    """module-scope names: scalars {name: type}, arrays {name: (type, rank)}, parameters {name: (type, C expr)}"""
+
+    def __init__(self):
+        self.scalars, self.arrays, self.params, self.kinds = {}, {}, {}, {}
+        self.order = []
+
+    def type_of(self, spec):
+        if spec == "integer":
+            return INT
+        m = re.fullmatch(r"real\(kind=([a-z0-9_]+)\)", spec)
+        if m:
+            return self.kinds[m.group(1)]
+        if spec == "type(backpointer)":
+            return STRUCT
+        raise SyntaxError(f"type {spec!r}")
+
+    def declare(self, text):
+        """a module-level (or local) declaration -> [(name, type, rank or None, dims or None, init or None)]"""
+        m = re.fullmatch(r"(integer|real\(kind=[a-z0-9_]+\)|type\(backpointer\))((?:,[a-z]+(?:\([^)]*\))?)*)(?:::)?(.*)", text)
+        if not m:
+            return None
+        spec, attrs, ents = m.group(1), m.group(2), m.group(3)
+        if re.match(r"[a-z0-9_]*=", ents) and "::" not in text:
+            return None                                  # an assignment to a variable whose name starts like a type
+        attr = [a for a in Unit.split_top(attrs[1:])] if attrs else []
+        typ = self.type_of(spec)
+        dim = next((a for a in attr if a.startswith("dimension(")), None)
+        out = []
+        for ent in Unit.split_top(ents):
+            m2 = re.fullmatch(r"([a-z][a-z0-9_]*)(?:\((.*)\))?(?:=(.*))?", ent)
+            name, dims, init = m2.group(1), m2.group(2), m2.group(3)
+            if dims is None and dim:
+                dims = dim[len("dimension("):-1]
+            out.append((name, typ, Unit.split_top(dims) if dims else None, init, "parameter" in attr))
+        return out
+
+    def read(self, stmts):
+        for text, ln in stmts:
+            if re.fullmatch(r"(module[a-z0-9_]+|use[a-z0-9_]+|implicitnone|endmodule[a-z0-9_]*|contains)", text):
+                continue
+            d = self.declare(text)
+            if d is None:
+                raise SyntaxError(f"module line {ln}: {text!r}")
+            for name, typ, dims, init, is_par in d:
+                if is_par and typ == INT and init in ("c_double", "selected_real_kind(5,10)"):
+                    self.kinds[name] = R8 if init == "c_double" else R4
+                elif is_par:
+                    u = Unit90(None, self, "subroutine", "_", [])
+                    self.params[name] = (typ, u.cast(u.parse(init), typ))
+                elif dims:
+                    assert all(d_ == ":" for d_ in dims), (name, dims)
+                    self.arrays[name] = (typ, len(dims))
+                else:
+                    self.scalars[name] = typ
+                self.order.append(name)
+
+    def c_decls(self):
+        o = ["typedef struct { int px, pz; } backpointer;", "static __thread int f90_stopped;"]
+        for name in self.order:
+            if name in self.kinds:
+                continue
+            if name in self.params:
+                t, c = self.params[name]
+                o.append(f"static const {CT[t]} {name} = {c};")
+            elif name in self.arrays:
+                t, rank = self.arrays[name]
+                o.append(f"static __thread {CT[t]}* {name}; static __thread int " + ", ".join(f"{name}_d{k + 1}, {name}_l{k + 1} = 1" for k in range(rank)) + ";")
+            else:
+                o.append(f"static __thread {CT[self.scalars[name]]} {name};")
+        return o
+
+
+class Unit90(Unit):
+    def __init__(self, tr, mod, kind, name, args):
+        super().__init__(tr, kind, name, args)
+        self.mod = mod
+        self.alloc = {}      # local allocatable arrays: name -> rank
+
+    def is_mod(self, name):
+        if name in self.types or name in self.args:      # a local declaration hides the module's
+            return False
+        m = self.mod
+        return name in m.scalars or name in m.arrays or name in m.params or re.fullmatch(r"[a-z0-9_]+_[dl][123]", name) is not None
+
+    def vtype(self, name):
+        if name in self.types:
+            return self.types[name]
+        m = self.mod
+        if name in m.scalars:
+            return m.scalars[name]
+        if name in m.arrays:
+            return m.arrays[name][0]
+        if name in m.params:
+            return m.params[name][0]
+        if re.fullmatch(r"[a-z0-9_]+_[dl][123]", name):
+            return INT
+        raise SyntaxError(f"{self.name}: {name!r} is not declared (IMPLICIT NONE)")
+
+    def note(self, name):
+        if not self.is_mod(name):
+            super().note(name)
+
+    def ref(self, name):
+        if self.is_mod(name):
+            return name
+        return super().ref(name)
+
+    def addr(self, name):
+        if self.is_mod(name):
+            return name if name in self.mod.arrays else "&" + name
+        return super().addr(name)
+
+    def rank_alloc(self, name):
+        """rank of an allocatable array (local or of a module), else None"""
+        if name in self.alloc:
+            return self.alloc[name]
+        if name in self.mod.arrays and name not in self.types:
+            return self.mod.arrays[name][1]
+        return None
+
+    def dims_of(self, name):
+        if name in self.dims:
+            return self.dims[name]
+        r = self.rank_alloc(name)
+        if r is not None:
+            return [f"{name}_d{k + 1}" for k in range(r)]
+        return None
+
+    def index(self, name, idx):
+        dims = self.dims_of(name)
+        lb = [f"{name}_l{k + 1}" for k in range(len(idx))] if self.rank_alloc(name) is not None else ["1"] * len(idx)
+        off = f"(({idx[0]})-{lb[0]})"
+        stride = None
+        for k in range(1, len(idx)):
+            d = self.expr_c(dims[k - 1], INT)
+            stride = d if stride is None else f"({stride})*({d})"
+            off += f"+({stride})*(({idx[k]})-{lb[k]})"
+        return off
+
+    def call_or_index(self, name, args):
+        if self.dims_of(name) is not None:
+            idx = [self.cast(a, INT) for a in args]
+            return Node("elem", self.vtype(name), f"{name}[{self.index(name, idx)}]", name=name, idx=idx)
+        if name == "allocated":
+            return Node("call", LOG, f"({args[0].name} != 0)")
+        if name == "floor":
+            return Node("call", INT, f"((int)floor({self.cast(args[0], R8)}))")
+        return super().call_or_index(name, args)
+
+    def p_prim(self):
+        n = super().p_prim()
+        while self.peek()[1] == "%":                     # component of a derived-type value
+            self.take()
+            k, field = self.take()
+            assert n.typ == STRUCT and field in ("px", "pz"), (n.c, field)
+            n = Node("elem", INT, f"{n.c}.{field}", name=None, idx=None)
+        return n
+
+    def assign(self, lhs, rhs):
+        ln = self.parse(lhs)
+        if ln.kind == "var" and self.dims_of(ln.name) is not None:   # whole-array assignment:  nsts = -1
+            rn = self.parse(rhs)
+            n = " * ".join(f"({self.expr_c(d, INT)})" for d in self.dims_of(ln.name))
+            t = self.vtype(ln.name)
+            self.emit(f"{{ {CT[t]} v_ = {self.cast(rn, t)}; for (int i_ = 0; i_ < {n}; ++i_) {ln.name}[i_] = v_; }}")
+            return
+        rn = self.parse(rhs)
+        assert (ln.typ == STRUCT) == (rn.typ == STRUCT), (lhs, rhs)
+        self.emit(f"{ln.c} = {self.cast(rn, ln.typ)};")
+
+    def statement(self, text, ln):
+        t = text
+        m = re.fullmatch(r"dowhile\((.*)\)", t)
+        if m:
+            self.emit(f"while ({self.parse(m.group(1)).c}) {{")
+            self.do_stack.append(("while", None, None))
+            return
+        if t == "enddo" and self.do_stack and self.do_stack[-1][0] == "while":
+            self.do_stack.pop()
+            self.emit("}")
+            return
+        if t == "stop":
+            self.emit("f90_stopped = 1; return;")
+            return
+        if t == "cycle":
+            self.emit("continue;")
+            return
+        m = re.fullmatch(r"allocate\((.*)\)", t)
+        if m:
+            for item in self.split_top(m.group(1)):
+                if item.startswith("stat="):
+                    self.emit(f"{self.ref(item[5:])} = 0;")
+                    continue
+                m2 = re.fullmatch(r"([a-z][a-z0-9_]*)\((.*)\)", item)
+                name, specs = m2.group(1), self.split_top(m2.group(2))
+                assert self.rank_alloc(name) == len(specs), item
+                n = []
+                for k, sp in enumerate(specs):
+                    lo, hi = sp.split(":") if ":" in sp else ("1", sp)
+                    self.emit(f"{name}_l{k + 1} = {self.expr_c(lo, INT)}; {name}_d{k + 1} = ({self.expr_c(hi, INT)}) - {name}_l{k + 1} + 1;")
+                    n.append(f"{name}_d{k + 1}")
+                ct = CT[self.vtype(name)]
+                self.emit(f"{name} = ({ct}*)calloc((size_t)({' * '.join(n)}), sizeof({ct}));")
+            return
+        m = re.fullmatch(r"deallocate\((.*)\)", t)
+        if m:
+            for item in self.split_top(m.group(1)):
+                if item.startswith("stat="):
+                    self.emit(f"{self.ref(item[5:])} = 0;")
+                else:
+                    self.emit(f"free({item}); {item} = 0;")
+            return
+        m = re.fullmatch(r"call([a-z][a-z0-9_]*)", t)
+        if m:
+            self.tr.called.add(m.group(1))
+            self.emit(f"{m.group(1)}_();")
+            return
+        super().statement(text, ln)
+
+
+class Translator90:
+    def __init__(self, mod):
+        self.mod = mod
+        self.units = []
+        self.called = set()
+
+    def run(self, stmts, only=None):
+        """only: names of the subroutines to translate (everything else in the file, module-level statements included, is skipped)"""
+        u, in_spec, skipping = None, False, False
+        for text, ln in stmts:
+            if skipping:
+                skipping = re.fullmatch(r"endsubroutine[a-z0-9_]*", text) is None
+                continue
+            if u is None:
+                m = re.fullmatch(r"subroutine([a-z][a-z0-9_]*)(?:\((.*)\))?", text)
+                if m and only is not None and m.group(1) not in only:
+                    skipping = True
+                    continue
+                if not m and only is not None:
+                    continue
+                if m:
+                    u = Unit90(self, self.mod, "subroutine", m.group(1), m.group(2).split(",") if m.group(2) else [])
+                    self.units.append(u)
+                    in_spec = True
+                    continue
+                if re.fullmatch(r"(module[a-z0-9_]+|use[a-z0-9_]+|implicitnone|contains|endmodule[a-z0-9_]*|typebackpointer|endtypebackpointer)", text):
+                    continue
+                d = self.mod.declare(text)               # module traveltime's own variables: ntr, btg; the type's components
+                if d is None:
+                    raise SyntaxError(f"line {ln}: {text!r} outside a subroutine")
+                for name, typ, dims, init, is_par in d:
+                    if name in ("px", "pz"):
+                        continue
+                    if dims:
+                        self.mod.arrays[name] = (typ, len(dims))
+                    else:
+                        self.mod.scalars[name] = typ
+                    self.mod.order.append(name)
+                continue
+            if re.fullmatch(r"endsubroutine[a-z0-9_]*", text):
+                assert not u.do_stack, f"{ln}: unterminated do in {u.name}"
+                u.emit("return;")
+                u = None
+                continue
+            if in_spec:
+                if text in ("implicitnone",) or re.fullmatch(r"use[a-z0-9_]+", text):
+                    continue
+                d = self.mod.declare(text)
+                if d is not None:
+                    for name, typ, dims, init, is_par in d:
+                        u.types[name] = typ
+                        if dims and all(d_ == ":" for d_ in dims):
+                            u.alloc[name] = len(dims)
+                        elif dims:
+                            u.dims[name] = dims
+                        elif name not in u.args:
+                            u.locals[name] = typ
+                    continue
+                in_spec = False
+            u.statement(text, ln)
+        return self
+
+    def c_source(self, paths):
+        o = [f"/* GENERATED by oracle/f90toc.py from {' and '.join(paths)} -- do not edit, do not commit (oracle/_ref/ is git-ignored). */",
+             "#include <math.h>", "#include <stdlib.h>",
+             "static inline double f_sq(double x) { return x * x; }", "static inline float f_sqf(float x) { return x * x; }",
+             "static inline int f_sqi(int x) { return x * x; }",
+             "static inline double f_powi(double x, int n) { double r = 1.0; int m = n < 0 ? -n : n; while (m--) r *= x; return n < 0 ? 1.0 / r : r; }",
+             "static inline double f_min(double a, double b) { return a < b ? a : b; }", "static inline double f_max(double a, double b) { return a > b ? a : b; }",
+             "static inline int f_mini(int a, int b) { return a < b ? a : b; }", "static inline int f_maxi(int a, int b) { return a > b ? a : b; }", ""]
+        o += self.mod.c_decls() + [""]
+        for u in self.units:
+            o.append(f"static void {u.name}_({', '.join('void* ' + a + '_a' for a in u.args) or 'void'});")
+        o.append("")
+        for u in self.units:
+            o.append(f"static void {u.name}_({', '.join('void* ' + a + '_a' for a in u.args) or 'void'}) {{")
+            for a in u.args:
+                o.append(f"  {CT[u.vtype(a)]}* {a} = ({CT[u.vtype(a)]}*){a}_a;")
+            for name, dims in u.dims.items():
+                if name in u.args:
+                    continue
+                n = " * ".join(f"({u.expr_c(d, INT)})" for d in dims)
+                o.append(f"  {CT[u.vtype(name)]} {name}[{n}];")
+            for name, rank in u.alloc.items():
+                o.append(f"  {CT[u.vtype(name)]}* {name} = 0; int " + ", ".join(f"{name}_d{k + 1} = 0, {name}_l{k + 1} = 1" for k in range(rank)) + ";")
+            for name, typ in sorted(u.locals.items()):
+                if name in u.dims or name in u.args or name in u.alloc:
+                    continue
+                o.append(f"  {CT[typ]} {name} = {{0}};" if typ == STRUCT else f"  {CT[typ]} {name} = 0;")
+            o.extend("  " + s for s in u.body)
+            o.append("}")
+            o.append("")
+        return "\n".join(o)
+
+
+def main():
+    globalp, out = sys.argv[1], sys.argv[-1]
+    mod = Module()
+    mod.read(read_free_form(globalp))
+    tr = Translator90(mod)
+    paths = [globalp]
+    for spec in sys.argv[2:-1]:                          # file  or  file:sub1,sub2
+        path, _, only = spec.partition(":")
+        tr.run(read_free_form(path), only=set(only.split(",")) if only else None)
+        paths.append(spec)
+    open(out, "w").write(tr.c_source(paths))
+    names = [u.name for u in tr.units]
+    missing = sorted(tr.called - set(names))
+    print(f"f90toc: {len(names)} program units ({', '.join(names)}); unresolved externals: {missing or 'none'}")
+
+
+if __name__ == "__main__":
+    main()

@@ -11,8 +11,14 @@
  * Not restated: rpaths (ray geometry; needed for group-velocity data and `crazyray`), the `dynamic` restart (switched
  * off in the reference itself, fm2dray_cartesian.f90:251-252).
  *
- * PARITY STATUS: "parity unpinned" -- no Fortran compiler in this image, no golden values in the reference.  Pinned by
- * physics only (tests/test_oracle_fm2d.py: homogeneous and linear-gradient media against the analytic travel times).
+ * PARITY STATUS: no Fortran compiler in this image, no golden values in the reference.
+ *   PINNED on the reference's own source: travel / fouds1 / fouds2 / addtree / downtree / updtree / bilinear (all of
+ *   fm2d_ttime.f90) and gridder / bsplrefine / srtimes of fm2dray_cartesian.f90, translated statement by statement to C by
+ *   oracle/f90toc.py (oracle/_ref/libfm2d_ttime_f2c.so) -- bit-identical travel-time fields, node status and heap for
+ *   urg = 0, 1, 2, both operator orders, homogeneous (tie-breaking) and rough media (tests/test_oracle_fm2d_vs_reference.py:
+ *   committed fixtures + fresh random cases).
+ *   "parity unpinned" (restatement only, pinned on analytic media by tests/test_oracle_fm2d.py): modrays' own glue between
+ *   those calls (refinement window, refined -> coarse mapping, narrow-band completion, :262-420) and rpaths.
  * All arithmetic is double (REAL(KIND=i10) = c_double); default-real literals in the source are exactly representable;
  * x**2 is x*x, x**3 is (x*x)*x as gfortran expands integer powers.
  */
@@ -294,6 +300,27 @@ static void travel(fm_t* F, double scx, double scz, int urg) {
   }
 }
 
+/* test entry: the march alone, on the caller's arrays (column major, leading dimension nnz) -- what
+ * tests/test_oracle_fm2d_vs_reference.py compares with the mechanical translation of fm2d_ttime.f90 (oracle/f90toc.py).
+ * heap_pxpz receives (px, pz) of the heap entries left when the march ends (urg = 1 stops early), ntr_out their number. */
+int orc_fm2d_travel(int nnx, int nnz, double gox, double goz, double dnx, double dnz, int fom, const double* veln, double* ttn, int* nsts,
+                    int urg, int vnl, int vnr, int vnt, int vnb, double scx, double scz, int* heap_pxpz, int* ntr_out) {
+  fm_t F;
+  memset(&F, 0, sizeof F);
+  F.nnx = nnx; F.nnz = nnz; F.gox = gox; F.goz = goz; F.dnx = dnx; F.dnz = dnz; F.fom = fom;
+  F.vnl = vnl; F.vnr = vnr; F.vnt = vnt; F.vnb = vnb;
+  F.ld = nnz; F.cells = (size_t)nnx * nnz;
+  F.veln = (double*)veln; F.ttn = ttn; F.nsts = nsts;
+  F.maxbt = nnx * nnz + 1;
+  F.bpx = (int*)calloc((size_t)F.maxbt + 2, sizeof(int));
+  F.bpz = (int*)calloc((size_t)F.maxbt + 2, sizeof(int));
+  travel(&F, scx, scz, urg);
+  for (int i = 0; i < F.ntr; ++i) { heap_pxpz[2 * i] = F.bpx[i + 1]; heap_pxpz[2 * i + 1] = F.bpz[i + 1]; }
+  *ntr_out = F.ntr;
+  free(F.bpx); free(F.bpz);
+  return F.error;
+}
+
 /* B-spline basis of gridder / bsplrefine */
 static inline void bspl(double u, double w[5]) {
   double um = 1.0 - u;
@@ -412,6 +439,39 @@ static void srtimes(fm_t* F, double scx, double scz, int csid, int nrc, const do
   }
 }
 
+
+/* test entries for gridder / bsplrefine / srtimes alone (compared with the mechanical translation of the Fortran by
+ * tests/test_oracle_fm2d_vs_reference.py).  velv: (nvx+2, nvz+2) C-order = the Fortran's velvin(nvz+2, nvx+2); veln_out
+ * (nnx, nnz) C-order = veln(nnz, nnx). */
+int orc_fm2d_gridder(int nvx, int nvz, int gdx, int gdz, const double* velv, double* veln_out) {
+  fm_t F;
+  memset(&F, 0, sizeof F);
+  F.nvx = nvx; F.nvz = nvz; F.gdx = gdx; F.gdz = gdz;
+  F.nnx = (nvx - 1) * gdx + 1; F.nnz = (nvz - 1) * gdz + 1; F.ld = F.nnz;
+  F.velv = (double*)velv; F.veln = veln_out;
+  gridder(&F);
+  return 0;
+}
+int orc_fm2d_bsplrefine(int nvx, int nvz, int gdx, int gdz, int sgdl, int vnl, int vnr, int vnt, int vnb, const double* velv, int nnxr,
+                        int nnzr, double* veln_out) {
+  fm_t F;
+  memset(&F, 0, sizeof F);
+  F.nvx = nvx; F.nvz = nvz; F.gdx = gdx; F.gdz = gdz; F.sgdl = sgdl;
+  F.vnl = vnl; F.vnr = vnr; F.vnt = vnt; F.vnb = vnb;
+  F.nnx = nnxr; F.nnz = nnzr; F.ld = nnzr;
+  F.velv = (double*)velv; F.veln = veln_out;
+  bsplrefine(&F);
+  return 0;
+}
+int orc_fm2d_srtimes(int nnx, int nnz, double gox, double goz, double dnx, double dnz, const double* veln, const double* ttn, double scx,
+                     double scz, int nrc, const double* rcx, const double* rcz, const int* srs, double* ttime) {
+  fm_t F;
+  memset(&F, 0, sizeof F);
+  F.nnx = nnx; F.nnz = nnz; F.ld = nnz; F.gox = gox; F.goz = goz; F.dnx = dnx; F.dnz = dnz;
+  F.veln = (double*)veln; F.ttn = (double*)ttn;
+  srtimes(&F, scx, scz, 1, nrc, rcx, rcz, srs, ttime);
+  return F.error;
+}
 
 /* rpaths (fm2dray_cartesian.f90:773-1456) with cfd = 0 as the source hard-wires it (the Frechet block is dead code): every
  * receiver's ray is traced from the receiver towards the source in steps of dpl = half the smaller node spacing along

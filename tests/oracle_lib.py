@@ -394,3 +394,87 @@ def fm2d_rays(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, asgr=1, sgdl
                             nvx, nvz, gox, goz, dvx, dvz, vel.ctypes.data, gdx, gdz, asgr, sgdl, sgs, fom, snb, tt.ctypes.data, cap,
                             npts.ctypes.data, pts.ctypes.data, ln.ctypes.data, C.byref(crazy))
     return err, tt, npts, pts, ln, crazy.value
+
+
+# ---- the reference's own fm2d/fm2d_ttime.f90, mechanically translated to C (oracle/f90toc.py, oracle/build_ref.sh) ----------
+FM2D_F2C_LIB = os.path.join(ORACLE_DIR, "_ref", "libfm2d_ttime_f2c.so")
+_fm2d_f2c = None
+
+
+def have_fm2d_reference():
+    return os.path.exists(FM2D_F2C_LIB)
+
+
+def fm2d_travel(impl, veln, gox, goz, dnx, dnz, fom, scx, scz, urg=0, window=None, ttn=None, nsts=None):
+    """One call of `travel` (fm2d_ttime.f90:27-136) on a propagation grid veln (nnx, nnz) C-order = the Fortran's (nnz, nnx).
+    impl "port": oracle/fm2d_ref.c; "reference": the translated Fortran.  window = (vnl, vnr, vnt, vnb) for urg = 1;
+    ttn / nsts carry the state from call to call (urg = 2 continues).  Returns (stopped/err, ttn, nsts, heap (ntr, 2) as (px, pz))."""
+    global _fm2d_f2c
+    if impl == "reference":
+        if _fm2d_f2c is None:
+            _fm2d_f2c = C.CDLL(FM2D_F2C_LIB)
+        fn = _fm2d_f2c.ref_fm2d_travel
+    else:
+        fn = L().orc_fm2d_travel
+    vpt = C.c_void_p
+    fn.argtypes = [C.c_int, C.c_int] + [C.c_double] * 4 + [C.c_int, vpt, vpt, vpt] + [C.c_int] * 5 + [C.c_double] * 2 + [vpt, vpt]
+    fn.restype = C.c_int
+    veln = f64(veln)
+    nnx, nnz = veln.shape
+    ttn = np.zeros((nnx, nnz)) if ttn is None else f64(ttn).copy()
+    nsts = np.full((nnx, nnz), -1, np.int32) if nsts is None else np.ascontiguousarray(nsts, dtype=np.int32).copy()
+    heap = np.zeros((nnx * nnz + 2, 2), np.int32)
+    ntr = C.c_int(0)
+    vnl, vnr, vnt, vnb = window if window is not None else (1, nnx, 1, nnz)
+    rc = fn(nnx, nnz, gox, goz, dnx, dnz, fom, veln.ctypes.data, ttn.ctypes.data, nsts.ctypes.data, urg, vnl, vnr, vnt, vnb, scx, scz,
+            heap.ctypes.data, C.byref(ntr))
+    return rc, ttn, nsts, heap[:ntr.value].copy()
+
+
+def _fm2d_fn(impl, name):
+    global _fm2d_f2c
+    if impl == "reference":
+        if _fm2d_f2c is None:
+            _fm2d_f2c = C.CDLL(FM2D_F2C_LIB)
+        return getattr(_fm2d_f2c, "ref_fm2d_" + name)
+    return getattr(L(), "orc_fm2d_" + name)
+
+
+def fm2d_gridder(impl, velv, gdx, gdz):
+    """gridder (fm2dray_cartesian.f90:490-590): velv (nvx+2, nvz+2) C-order -> veln (nnx, nnz)"""
+    fn = _fm2d_fn(impl, "gridder")
+    velv = f64(velv)
+    nvx, nvz = velv.shape[0] - 2, velv.shape[1] - 2
+    out = np.zeros(((nvx - 1) * gdx + 1, (nvz - 1) * gdz + 1))
+    fn.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2
+    fn(nvx, nvz, gdx, gdz, velv.ctypes.data, out.ctypes.data)
+    return out
+
+
+def fm2d_bsplrefine(impl, velv, gdx, gdz, sgdl, window):
+    """bsplrefine (fm2dray_cartesian.f90:598-668) on the window (vnl, vnr, vnt, vnb) of the propagation grid"""
+    fn = _fm2d_fn(impl, "bsplrefine")
+    velv = f64(velv)
+    nvx, nvz = velv.shape[0] - 2, velv.shape[1] - 2
+    vnl, vnr, vnt, vnb = window
+    nnxr, nnzr = (vnr - vnl) * sgdl + 1, (vnb - vnt) * sgdl + 1
+    out = np.zeros((nnxr, nnzr))
+    fn.argtypes = [C.c_int] * 9 + [C.c_void_p] + [C.c_int] * 2 + [C.c_void_p]
+    fn(nvx, nvz, gdx, gdz, sgdl, vnl, vnr, vnt, vnb, velv.ctypes.data, nnxr, nnzr, out.ctypes.data)
+    return out
+
+
+def fm2d_srtimes(impl, veln, ttn, gox, goz, dnx, dnz, scx, scz, rcv, srs):
+    """srtimes (fm2dray_cartesian.f90:676-770) for one source: rcv (nrc, 2), srs (nrc) -> (stopped/err, ttime (nrc), -1 where untouched)"""
+    fn = _fm2d_fn(impl, "srtimes")
+    veln, ttn, rcv = f64(veln), f64(ttn), f64(rcv)
+    nnx, nnz = veln.shape
+    rcx, rcz = f64(rcv[:, 0].copy()), f64(rcv[:, 1].copy())
+    srs = np.ascontiguousarray(srs, dtype=np.int32)
+    tt = np.full(len(rcv), -1.0)
+    vpt = C.c_void_p
+    fn.argtypes = [C.c_int] * 2 + [C.c_double] * 4 + [vpt, vpt] + [C.c_double] * 2 + [C.c_int, vpt, vpt, vpt, vpt]
+    fn.restype = C.c_int
+    rc = fn(nnx, nnz, gox, goz, dnx, dnz, veln.ctypes.data, ttn.ctypes.data, scx, scz, len(rcv), rcx.ctypes.data, rcz.ctypes.data,
+            srs.ctypes.data, tt.ctypes.data)
+    return rc, tt

@@ -1,0 +1,174 @@
+"""Pins the march of the fm2d oracle (oracle/fm2d_ref.c: travel, fouds1, fouds2, addtree, downtree, updtree, bilinear) against
+the REFERENCE'S OWN fm2d/fm2d_ttime.f90:
+
+  * tests/golden/fm2d_travel_ref.npz -- calls of `travel` whose outputs (travel-time field, node status, the heap left behind)
+    were produced by the reference source itself, translated statement by statement to C by oracle/f90toc.py and compiled
+    with gcc (tools/make_golden_fm2d_ref.py).  The fixtures travel; this test runs everywhere.
+  * live, where oracle/_ref/libfm2d_ttime_f2c.so exists: fresh random media every run, including homogeneous ones (every
+    wavefront node ties with others: the heap's arrangement decides the order) and strong contrasts (negative discriminants).
+Every output must be BIT-IDENTICAL, for the first-order and the mixed-order operators, for a whole-grid march (urg = 0),
+for the window-limited march of the refined source grid (urg = 1, stops at the first edge node) and for its continuation
+from the nodes left in the narrow band (urg = 2).  Likewise gridder, bsplrefine and srtimes of fm2dray_cartesian.f90, each
+called alone (live only).  What stays by restatement only: modrays' own glue between these calls (the refinement window,
+the refined -> coarse mapping, the narrow-band completion: fm2dray_cartesian.f90:262-420) and rpaths, pinned on analytic
+media in test_oracle_fm2d.py."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "fm2d_travel_ref.npz")
+
+
+def medium(rng, nnx, nnz, kind):
+    if kind == "homogeneous":
+        return np.full((nnx, nnz), 3.0)
+    x, z = np.meshgrid(np.linspace(0, 1, nnx), np.linspace(0, 1, nnz), indexing="ij")
+    v = 3.0 + 0.0 * x
+    for _ in range(4):
+        kx, kz, ph, a = rng.uniform(1, 9), rng.uniform(1, 9), rng.uniform(0, 6.28), rng.uniform(0.05, 0.3)
+        v = v + a * np.sin(kx * x * 3 + kz * z * 3 + ph)
+    if kind == "rough":                        # cell-scale contrasts of a factor 4: stencils without a real root
+        v = v * np.where(rng.random((nnx, nnz)) < 0.3, 0.35, 1.0)
+    return v
+
+
+def cases(seed, n):
+    """(veln, gox, goz, dnx, dnz, fom, scx, scz, window): the grid sizes, spacings and source positions of a case"""
+    rng = np.random.default_rng(seed)
+    for k in range(n):
+        nnx, nnz = int(rng.integers(5, 42)), int(rng.integers(5, 34))
+        dnx, dnz = float(rng.uniform(0.1, 0.6)), float(rng.uniform(0.1, 0.6))
+        if k % 5 == 0:
+            dnz = dnx
+        gox, goz = float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3))
+        kind = ("smooth", "homogeneous", "rough")[k % 3]
+        veln = medium(rng, nnx, nnz, kind)
+        mode = k % 4
+        if mode == 0:                          # anywhere inside
+            scx, scz = gox + rng.uniform(0, (nnx - 1) * dnx), goz + rng.uniform(0, (nnz - 1) * dnz)
+        elif mode == 1:                        # exactly on a node
+            scx, scz = gox + int(rng.integers(0, nnx)) * dnx, goz + int(rng.integers(0, nnz)) * dnz
+        elif mode == 2:                        # in the last cell row / column
+            scx, scz = gox + (nnx - 1) * dnx - rng.uniform(0, dnx), goz + (nnz - 1) * dnz - rng.uniform(0, dnz)
+        else:                                  # on the first edge
+            scx, scz = gox, goz + rng.uniform(0, (nnz - 1) * dnz)
+        isx = min(int((scx - gox) / dnx) + 1, nnx - 1)
+        isz = min(int((scz - goz) / dnz) + 1, nnz - 1)
+        ext = int(rng.integers(1, 5))
+        # a window as modrays builds it (clipped at the grid), seen through travel's own edge test
+        window = (max(isx - ext, 1), min(isx + ext, nnx), max(isz - ext, 1), min(isz + ext, nnz))
+        yield veln, gox, goz, dnx, dnz, k % 2, float(scx), float(scz), window
+
+
+def run_case(impl, case):
+    """whole-grid march; window-limited march; its continuation"""
+    veln, gox, goz, dnx, dnz, fom, scx, scz, window = case
+    out = [orc.fm2d_travel(impl, veln, gox, goz, dnx, dnz, fom, scx, scz, urg=0)]
+    r1 = orc.fm2d_travel(impl, veln, gox, goz, dnx, dnz, fom, scx, scz, urg=1, window=window)
+    out.append(r1)
+    # what modrays does between the two marches, reduced to its effect on the status array: alive nodes with a far neighbour
+    # go back into the narrow band (status 1), everything else that is not alive becomes far
+    t, s = r1[1], r1[2].copy()
+    alive = s == 0
+    s[:] = -1
+    s[alive] = 0
+    pad = np.pad(s, 1, constant_values=0)
+    far_nb = (pad[:-2, 1:-1] == -1) | (pad[2:, 1:-1] == -1) | (pad[1:-1, :-2] == -1) | (pad[1:-1, 2:] == -1)
+    s[alive & far_nb] = 1
+    out.append(orc.fm2d_travel(impl, veln, gox, goz, dnx, dnz, fom, scx, scz, urg=2, ttn=t, nsts=s))
+    return out
+
+
+def same(a, b):
+    return a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
+def test_restatement_reproduces_the_reference_fixtures_bit_for_bit():
+    g = np.load(GOLD)
+    n = int(g["n"])
+    seed = int(g["seed"])
+    stopped_early = ties = 0
+    for k, case in enumerate(cases(seed, n)):
+        got = run_case("port", case)
+        for j, r in enumerate(got):
+            assert r[0] == int(g[f"{k}_{j}_rc"]), (k, j)
+            assert np.array_equal(r[1], g[f"{k}_{j}_ttn"]), f"case {k} march {j}: {(r[1] != g[f'{k}_{j}_ttn']).sum()} travel times differ"
+            assert np.array_equal(r[2], g[f"{k}_{j}_nsts"]), (k, j)
+            assert np.array_equal(r[3], g[f"{k}_{j}_heap"]), (k, j)
+        stopped_early += len(got[1][3]) > 0
+        ties += case[0].std() == 0
+    assert n >= 36 and stopped_early >= 10 and ties >= 10            # the fixture covers the early stop and the tie-breaking
+
+
+@pytest.mark.skipif(not orc.have_fm2d_reference(), reason="oracle/_ref/libfm2d_ttime_f2c.so not built (needs /root/reference)")
+def test_restatement_equals_the_translated_reference_on_fresh_media():
+    seed = int.from_bytes(os.urandom(4), "little")
+    n = nodes = 0
+    for case in cases(seed, 120):
+        ref = run_case("reference", case)
+        got = run_case("port", case)
+        for j in range(3):
+            assert same(ref[j], got[j]), f"seed {seed} case {n} march {j}"
+        n += 1
+        nodes += case[0].size
+    assert n == 120 and nodes > 30000
+
+
+@pytest.mark.skipif(not orc.have_fm2d_reference(), reason="oracle/_ref/libfm2d_ttime_f2c.so not built (needs /root/reference)")
+def test_source_outside_the_grid_is_the_fortran_stop():
+    veln = np.full((8, 9), 3.0)
+    for impl in ("reference", "port"):
+        rc, t, s, h = orc.fm2d_travel(impl, veln, 0.0, 0.0, 0.5, 0.5, 1, 9.0, 1.0)
+        assert rc == 1 and not t.any() and len(h) == 0
+
+
+needs_ref = pytest.mark.skipif(not orc.have_fm2d_reference(), reason="oracle/_ref/libfm2d_ttime_f2c.so not built (needs /root/reference)")
+
+
+@needs_ref
+def test_gridder_and_bsplrefine_equal_the_translated_reference():
+    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    for k in range(60):
+        nvx, nvz = int(rng.integers(2, 14)), int(rng.integers(2, 12))
+        gdx, gdz = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        velv = 2.0 + rng.random((nvx + 2, nvz + 2))
+        a, b = orc.fm2d_gridder("reference", velv, gdx, gdz), orc.fm2d_gridder("port", velv, gdx, gdz)
+        assert a.shape == ((nvx - 1) * gdx + 1, (nvz - 1) * gdz + 1) and np.array_equal(a, b) and a.min() > 1.0, k
+        nnx, nnz = a.shape
+        sgdl, ext = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+        isx, isz = int(rng.integers(1, max(2, nnx))), int(rng.integers(1, max(2, nnz)))
+        window = (max(isx - ext, 1), min(isx + ext, nnx), max(isz - ext, 1), min(isz + ext, nnz))
+        a, b = orc.fm2d_bsplrefine("reference", velv, gdx, gdz, sgdl, window), orc.fm2d_bsplrefine("port", velv, gdx, gdz, sgdl, window)
+        assert np.array_equal(a, b) and a.min() > 1.0, (k, window, sgdl)      # (every refined node is written)
+
+
+@needs_ref
+def test_srtimes_equals_the_translated_reference():
+    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    n_near = 0
+    for k in range(80):
+        nnx, nnz = int(rng.integers(4, 30)), int(rng.integers(4, 30))
+        dnx, dnz = float(rng.uniform(0.1, 0.6)), float(rng.uniform(0.1, 0.6))
+        gox, goz = float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3))
+        veln, ttn = 2.0 + rng.random((nnx, nnz)), 10.0 * rng.random((nnx, nnz))
+        scx, scz = gox + rng.uniform(0, (nnx - 1) * dnx), goz + rng.uniform(0, (nnz - 1) * dnz)
+        nrc = 12
+        rcv = np.stack([gox + rng.uniform(0, (nnx - 1) * dnx, nrc), goz + rng.uniform(0, (nnz - 1) * dnz, nrc)], axis=1)
+        rcv[0] = (scx + 0.3 * min(dnx, dnz), scz)                        # closer than a node spacing: the near-source formula
+        rcv[0, 0] = min(rcv[0, 0], gox + (nnx - 1) * dnx)
+        rcv[1] = (gox + (nnx - 1) * dnx, goz + (nnz - 1) * dnz)          # the far corner: last cell row and column
+        srs = (rng.random(nrc) < 0.8).astype(np.int32)
+        srs[:2] = 1
+        ra, ta = orc.fm2d_srtimes("reference", veln, ttn, gox, goz, dnx, dnz, float(scx), float(scz), rcv, srs)
+        rb, tb = orc.fm2d_srtimes("port", veln, ttn, gox, goz, dnx, dnz, float(scx), float(scz), rcv, srs)
+        assert ra == 0 and rb == 0 and np.array_equal(ta, tb), k
+        assert np.array_equal(ta == -1.0, srs == 0)                       # receivers without data are not touched
+        n_near += 1
+    rcv[2] = (gox - 1.0, goz)                                             # a receiver outside: STOP / error 3
+    srs[2] = 1
+    ra, _ = orc.fm2d_srtimes("reference", veln, ttn, gox, goz, dnx, dnz, float(scx), float(scz), rcv, srs)
+    rb, _ = orc.fm2d_srtimes("port", veln, ttn, gox, goz, dnx, dnz, float(scx), float(scz), rcv, srs)
+    assert ra == 1 and rb == 3

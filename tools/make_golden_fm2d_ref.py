@@ -1,0 +1,26 @@
+"""tools/make_golden_fm2d_ref.py -- writes tests/golden/fm2d_travel_ref.npz: outputs of the reference's own `travel`
+(fm2d/fm2d_ttime.f90, translated mechanically by oracle/f90toc.py into oracle/_ref/libfm2d_ttime_f2c.so; run
+oracle/build_ref.sh first) on the seeded cases of tests/test_oracle_fm2d_vs_reference.py.  Needs /root/reference; the
+fixture itself travels."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as orc                                              # noqa: E402
+from test_oracle_fm2d_vs_reference import cases, run_case             # noqa: E402
+
+SEED, N = 20261018, 40
+assert orc.have_fm2d_reference(), "oracle/_ref/libfm2d_ttime_f2c.so missing: run oracle/build_ref.sh"
+out = {"n": N, "seed": SEED}
+for k, case in enumerate(cases(SEED, N)):
+    for j, (rc, ttn, nsts, heap) in enumerate(run_case("reference", case)):
+        out[f"{k}_{j}_rc"] = rc
+        out[f"{k}_{j}_ttn"] = ttn
+        out[f"{k}_{j}_nsts"] = nsts
+        out[f"{k}_{j}_heap"] = heap
+path = os.path.join(ROOT, "tests", "golden", "fm2d_travel_ref.npz")
+np.savez_compressed(path, **out)
+print("wrote", path, os.path.getsize(path), "bytes")
