@@ -1,22 +1,25 @@
 #!/usr/bin/env python
-"""oracle/f90toc.py -- mechanical Fortran 90 -> C translation of the reference's fast-marching core, fm2d/fm2d_ttime.f90
-(module traveltime: travel, fouds1, fouds2, addtree, downtree, updtree, bilinear) with the module variables of
-fm2d/fm2d_globalp.f90.
+"""oracle/f90toc.py -- mechanical Fortran 90 -> C translation of the reference's fast-marching code: fm2d/fm2d_ttime.f90
+(module traveltime: travel, fouds1, fouds2, addtree, downtree, updtree, bilinear), selected subroutines of
+fm2d/fm2dray_cartesian.f90 (gridder, bsplrefine, srtimes) and the body of modrays' source loop (MODRAYS_SOURCE below), with
+the module variables of fm2d/fm2d_globalp.f90.
 
 TEST INFRASTRUCTURE.  There is no Fortran compiler in the build image; the restatement oracle/fm2d_ref.c would
 otherwise be pinned by physics only.  This script reads the reference's own source WHERE IT LIES (nothing is copied
 into the repository) and translates it statement by statement with the expression machinery of oracle/f77toc.py (every
 node typed as Fortran types it, default-real literals as float literals, integer powers as multiplications, arguments
 by reference, 1-based column-major arrays).  oracle/build_ref.sh compiles the result together with the hand-written
-driver oracle/fm2d_f90_harness.c into the git-ignored oracle/_ref/libfm2d_ttime_f2c.so; tests/test_oracle_fm2d_vs_reference.py
-compares the march of the restatement with it bit for bit (travel times, node status, heap), for urg = 0, 1 and 2.
+driver oracle/ref_harness/fm2d_f90_harness.c into the git-ignored oracle/_ref/libfm2d_ttime_f2c.so;
+tests/test_oracle_fm2d_vs_reference.py compares the restatement with it bit for bit, per routine and for whole calls.
 
 What is added to f77toc's subset:
-  * free form: `!` comments, blank-insignificant matching after lower-casing (the file has no continuation lines and
-    no character data outside WRITE statements, which are dropped -- they only print);
+  * free form: `!` comments, `&` continuation lines, blank-insignificant matching after lower-casing (no character data
+    outside WRITE statements, which are dropped -- they only print);
   * MODULE / USE / CONTAINS / IMPLICIT NONE; module variables become thread-local C globals (the reference marks them
-    `!$omp threadprivate`); allocatable module arrays become a pointer plus their extents (`x`, `x_d1`, `x_d2`), set by
-    the driver, which plays the part of modrays' ALLOCATE statements;
+    `!$omp threadprivate`); allocatable arrays (module or local) become a pointer plus extents and lower bounds (`x`, `x_d1`,
+    `x_l1`, ...), set by ALLOCATE / DEALLOCATE / ALLOCATED and by array = array (the left-hand side is reallocated when the
+    shapes differ: Fortran 2003, gfortran's default) or by the driver where it plays the part of modrays' own ALLOCATEs;
+  * CYCLE, FLOOR, NINT, REAL(); a synthetic subroutine made of statement ranges of a larger one (run_ranges);
   * declarations with attributes (`REAL(KIND=i10), DIMENSION(2,2) :: vss`), kind parameters (i10 = c_double, i5 = single);
   * the derived type `backpointer` (a C struct), component references `btg(i)%px`, whole-structure assignment;
   * DO WHILE, EXIT, RETURN, subroutines without dummy arguments; STOP sets `f90_stopped` and returns (it only occurs in
@@ -214,6 +217,8 @@ class Unit90(Unit):
             return Node("call", LOG, f"({args[0].name} != 0)")
         if name == "floor":
             return Node("call", INT, f"((int)floor({self.cast(args[0], R8)}))")
+        if name == "nint":
+            return Node("call", INT, f"((int)lround({self.cast(args[0], R8)}))")
         return super().call_or_index(name, args)
 
     def p_prim(self):
@@ -227,8 +232,20 @@ class Unit90(Unit):
 
     def assign(self, lhs, rhs):
         ln = self.parse(lhs)
-        if ln.kind == "var" and self.dims_of(ln.name) is not None:   # whole-array assignment:  nsts = -1
+        if ln.kind == "var" and self.dims_of(ln.name) is not None:   # whole-array assignment:  nsts = -1,  ttnr = ttn
             rn = self.parse(rhs)
+            if rn.kind == "var" and self.dims_of(rn.name) is not None:
+                a, b = ln.name, rn.name
+                ra, rb = self.rank_alloc(a), self.rank_alloc(b)
+                assert ra is not None and ra == rb, (lhs, rhs)
+                # Fortran 2003 (gfortran's default, -frealloc-lhs): an allocatable left-hand side of another shape is reallocated
+                differ = " || ".join(f"{a}_d{k + 1} != {b}_d{k + 1}" for k in range(ra))
+                take = " ".join(f"{a}_d{k + 1} = {b}_d{k + 1}; {a}_l{k + 1} = {b}_l{k + 1};" for k in range(ra))
+                n = " * ".join(f"{b}_d{k + 1}" for k in range(ra))
+                ct = CT[self.vtype(a)]
+                self.emit(f"if ({a} == 0 || {differ}) {{ free({a}); {take} {a} = ({ct}*)calloc((size_t)({n}), sizeof({ct})); }}")
+                self.emit(f"for (int i_ = 0; i_ < {n}; ++i_) {a}[i_] = {b}[i_];")
+                return
             n = " * ".join(f"({self.expr_c(d, INT)})" for d in self.dims_of(ln.name))
             t = self.vtype(ln.name)
             self.emit(f"{{ {CT[t]} v_ = {self.cast(rn, t)}; for (int i_ = 0; i_ < {n}; ++i_) {ln.name}[i_] = v_; }}")
@@ -269,7 +286,9 @@ class Unit90(Unit):
                     self.emit(f"{name}_l{k + 1} = {self.expr_c(lo, INT)}; {name}_d{k + 1} = ({self.expr_c(hi, INT)}) - {name}_l{k + 1} + 1;")
                     n.append(f"{name}_d{k + 1}")
                 ct = CT[self.vtype(name)]
-                self.emit(f"{name} = ({ct}*)calloc((size_t)({' * '.join(n)}), sizeof({ct}));")
+                # (+ 64 elements: modrays sizes btg by snb and never checks it; on tiny grids the narrow band outgrows it and the
+                #  Fortran overruns the array -- the pad keeps that undefined behaviour from corrupting the test process)
+                self.emit(f"{name} = ({ct}*)calloc((size_t)({' * '.join(n)}) + 64, sizeof({ct}));")
             return
         m = re.fullmatch(r"deallocate\((.*)\)", t)
         if m:
@@ -349,6 +368,64 @@ class Translator90:
             u.statement(text, ln)
         return self
 
+    def run_ranges(self, stmts, host, name, args, extra_decl, ranges):
+        """A synthetic subroutine `name(args)` made of statement ranges of the subroutine `host`: its declarations are the host's
+        (those of types outside the subset are skipped) plus extra_decl; every range is (first statement, last statement) as
+        blank-free text, searched in order after the end of the previous one."""
+        texts = [t for t, _ in stmts]
+        h0 = next(i for i, t in enumerate(texts) if re.fullmatch(rf"subroutine{host}\(.*\)", t))
+        h1 = next(i for i in range(h0, len(texts)) if texts[i] == f"endsubroutine{host}")
+        u = Unit90(self, self.mod, "subroutine", name, args)
+        self.units.append(u)
+        decls = []
+        for i in range(h0 + 1, h1):                     # the host's specification part
+            t = texts[i]
+            if t == "implicitnone" or re.fullmatch(r"use[a-z0-9_]+", t):
+                continue
+            if not re.match(r"(integer|real|type|logical|complex|character)", t) or ("::" not in t and "=" in t):
+                break
+            decls.append(t)
+        for t in decls + list(extra_decl):
+            try:
+                d = self.mod.declare(t)
+            except SyntaxError:
+                d = None
+            if d is None:
+                continue                                 # logical, type(T_RAY): not used by the ranges (IMPLICIT NONE would tell)
+            for nm, typ, dims, init, is_par in d:
+                u.types[nm] = typ
+                u.dims.pop(nm, None); u.alloc.pop(nm, None); u.locals.pop(nm, None)
+                if dims and all(d_ == ":" for d_ in dims):
+                    u.alloc[nm] = len(dims)
+                elif dims:
+                    u.dims[nm] = dims
+                elif nm not in u.args:
+                    u.locals[nm] = typ
+        pos = h0
+        for first, last in ranges:
+            a = next(i for i in range(pos, h1) if texts[i] == first)
+            if isinstance(last, tuple):                 # ("before", anchor, n): up to n + 1 statements before the anchor
+                b = next(i for i in range(a, h1) if texts[i] == last[1]) - 1 - last[2]
+            else:
+                b = next(i for i in range(a, h1) if texts[i] == last)
+            for i in range(a, b + 1):
+                u.statement(texts[i], stmts[i][1])
+            pos = b + 1
+        assert not u.do_stack
+        u.emit("return;")
+        # locals that the ranges never mention need no storage
+        used = " ".join(u.body)
+        for nm in list(u.locals):
+            if not re.search(rf"\b{nm}\b", used):
+                del u.locals[nm]
+        for nm in list(u.alloc):
+            if not re.search(rf"\b{nm}\b", used):
+                del u.alloc[nm]
+        for nm in list(u.dims):
+            if nm not in u.args and not re.search(rf"\b{nm}\b", used):
+                del u.dims[nm]
+        return self
+
     def c_source(self, paths):
         o = [f"/* GENERATED by oracle/f90toc.py from {' and '.join(paths)} -- do not edit, do not commit (oracle/_ref/ is git-ignored). */",
              "#include <math.h>", "#include <stdlib.h>",
@@ -382,15 +459,36 @@ class Translator90:
         return "\n".join(o)
 
 
+# What modrays (fm2dray_cartesian.f90:67-478) does for ONE source between `DO i=1,nsrc` and `call srtimes`, as a subroutine of
+# its own: the source cell and the refinement window (:213-243), then the branch taken when `dynamic` is false -- it always is,
+# the line before the test sets it (:251-252) -- i.e. source-grid refinement, the refined march, the mapping back onto the
+# propagation grid, the completion of the narrow band and the second march, or the plain march (:283-438).  The statements
+# in between (the `dynamic` restart: optional arguments, array sections, WHERE) are dead code and outside the subset.
+MODRAYS_SOURCE = dict(
+    host="modrays", name="modrays_source", args=["i", "nsrc", "sgs", "scx", "scz", "x", "z"],
+    extra_decl=["real(kind=i10)::scx(nsrc),scz(nsrc)"],
+    ranges=[("x=scx(i)", "if(vnb.gt.nnz)vnb=nnz"),
+            # from the `else` branch of `if(dynamic)` to the ENDIF that closes IF(asgr.EQ.1): one ENDIF (that of `if(dynamic)`)
+            # and the anchor itself are left out
+            ("urg=0", ("before", "if(present(timefield))then", 1))])
+
+
 def main():
     globalp, out = sys.argv[1], sys.argv[-1]
     mod = Module()
     mod.read(read_free_form(globalp))
     tr = Translator90(mod)
     paths = [globalp]
-    for spec in sys.argv[2:-1]:                          # file  or  file:sub1,sub2
+    for spec in sys.argv[2:-1]:                          # file  or  file:sub1,sub2  (`@modrays_source`: see MODRAYS_SOURCE)
         path, _, only = spec.partition(":")
-        tr.run(read_free_form(path), only=set(only.split(",")) if only else None)
+        names = set(only.split(",")) if only else None
+        stmts = read_free_form(path)
+        if names and "@modrays_source" in names:
+            names.discard("@modrays_source")
+            tr.run(stmts, only=names)
+            tr.run_ranges(stmts, **MODRAYS_SOURCE)
+        else:
+            tr.run(stmts, only=names)
         paths.append(spec)
     open(out, "w").write(tr.c_source(paths))
     names = [u.name for u in tr.units]

@@ -12,13 +12,12 @@
  * off in the reference itself, fm2dray_cartesian.f90:251-252).
  *
  * PARITY STATUS: no Fortran compiler in this image, no golden values in the reference.
- *   PINNED on the reference's own source: travel / fouds1 / fouds2 / addtree / downtree / updtree / bilinear (all of
- *   fm2d_ttime.f90) and gridder / bsplrefine / srtimes of fm2dray_cartesian.f90, translated statement by statement to C by
- *   oracle/f90toc.py (oracle/_ref/libfm2d_ttime_f2c.so) -- bit-identical travel-time fields, node status and heap for
- *   urg = 0, 1, 2, both operator orders, homogeneous (tie-breaking) and rough media (tests/test_oracle_fm2d_vs_reference.py:
- *   committed fixtures + fresh random cases).
- *   "parity unpinned" (restatement only, pinned on analytic media by tests/test_oracle_fm2d.py): modrays' own glue between
- *   those calls (refinement window, refined -> coarse mapping, narrow-band completion, :262-420) and rpaths.
+ *   PINNED on the reference's own source (travel times): all of fm2d_ttime.f90 (travel, fouds1, fouds2, addtree, downtree,
+ *   updtree, bilinear), gridder / bsplrefine / srtimes and the body of modrays' source loop, translated statement by
+ *   statement to C by oracle/f90toc.py (oracle/_ref/libfm2d_ttime_f2c.so) -- bit-identical per routine (fields, node
+ *   status, heap; urg 0/1/2; both operator orders; ties; rough media) and for whole calls of orc_fm2d_times (every
+ *   receiver time and field): tests/test_oracle_fm2d_vs_reference.py, committed fixtures + fresh random cases.
+ *   "parity unpinned" (restatement only, pinned on analytic media by tests/test_oracle_fm2d.py): rpaths.
  * All arithmetic is double (REAL(KIND=i10) = c_double); default-real literals in the source are exactly representable;
  * x**2 is x*x, x**3 is (x*x)*x as gfortran expands integer powers.
  */

@@ -478,3 +478,25 @@ def fm2d_srtimes(impl, veln, ttn, gox, goz, dnx, dnz, scx, scz, rcv, srs):
     rc = fn(nnx, nnz, gox, goz, dnx, dnz, veln.ctypes.data, ttn.ctypes.data, scx, scz, len(rcv), rcx.ctypes.data, rcz.ctypes.data,
             srs.ctypes.data, tt.ctypes.data)
     return rc, tt
+
+
+def fm2d_times_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, asgr=1, sgdl=4, sgs=8, fom=1, snb=0.5):
+    """modrays for travel times (uar = 1) through the TRANSLATED reference: gridder, the per-source body of modrays' loop,
+    travel, bsplrefine and srtimes are the Fortran's own statements (oracle/f90toc.py); the allocations and the loop skeleton
+    around them are oracle/ref_harness/fm2d_f90_harness.c.  Same arguments and results as fm2d_times(want_field=True)."""
+    fn = _fm2d_fn("reference", "modrays_times")
+    vpt = C.c_void_p
+    fn.argtypes = [C.c_int, vpt, vpt, C.c_int, vpt, vpt, vpt, C.c_int, C.c_int] + [C.c_double] * 4 + [vpt] + [C.c_int] * 6 + [C.c_double, vpt, vpt]
+    fn.restype = C.c_int
+    src, rcv, vel = f64(src), f64(rcv), f64(vel)
+    nsrc, nrc = len(src), len(rcv)
+    nvx, nvz = vel.shape[0] - 2, vel.shape[1] - 2
+    scx, scz = f64(src[:, 0].copy()), f64(src[:, 1].copy())
+    rcx, rcz = f64(rcv[:, 0].copy()), f64(rcv[:, 1].copy())
+    srs = np.ascontiguousarray(srs, dtype=np.int32)
+    tt = np.full((nsrc, nrc), -1.0)
+    nnx, nnz = (nvx - 1) * gdx + 1, (nvz - 1) * gdz + 1
+    field = np.zeros((nsrc, nnx, nnz))
+    err = fn(nsrc, scx.ctypes.data, scz.ctypes.data, nrc, rcx.ctypes.data, rcz.ctypes.data, srs.ctypes.data, nvx, nvz, gox, goz, dvx, dvz,
+             vel.ctypes.data, gdx, gdz, asgr, sgdl, sgs, fom, snb, tt.ctypes.data, field.ctypes.data)
+    return err, tt, field

@@ -162,3 +162,26 @@ def test_fm2d_source_in_the_last_cell_row_is_flagged(mct):
     assert mct.LAST_FM2D_RC == mct.MCT_E_FM2D_STALE
     assert np.array_equal(tt[0][[0, 2]], to[[0, 2]]) and np.array_equal(field[0][[0, 2]], fo[[0, 2]])
     assert (field[0][1] == 0).sum() > 600                                       # unreached nodes read 0 on the device
+
+
+def test_fm2d_device_equals_the_reference_derived_fixtures_directly(mct):
+    """The device against numbers that come from the reference's own statements (tests/golden/fm2d_travel_ref.npz: whole calls of
+    modrays for travel times through the mechanical translation, tools/make_golden_fm2d_ref.py) -- without the restatement in
+    between: receiver times of every source whose march completes, and the digest of the fields where all of them do."""
+    import os
+    from test_oracle_fm2d_vs_reference import GOLD, times_cases, field_digest
+    g = np.load(GOLD)
+    n = nfield = 0
+    for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw) in enumerate(times_cases(int(g["seed"]), int(g["nt"]))):
+        unreached = orc.fm2d_unreached(len(src))
+        orc.fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, **kw)          # (only to know which marches die)
+        orc.fm2d_disarm()
+        o = mct.fm2d_opts(gridx=kw["gdx"], gridy=kw["gdz"], sgref=kw["asgr"], sgdic=kw["sgdl"], sgext=kw["sgs"], order=kw["fom"])
+        tt, field = mct.fm2d_times(src, rcv, srs[None], vel[None], gox, goz, dvx, dvz, o, ttime=np.full((1,) + srs.shape, -1.0), want_field=True)
+        good = [i for i in range(len(src)) if unreached[i] == 0]
+        assert np.array_equal(tt[0][good], g[f"t{k}_tt"][good]), (k, kw)
+        if len(good) == len(src):
+            assert field_digest(field[0], srs) == g[f"t{k}_digest"].tobytes(), (k, kw)
+            nfield += 1
+        n += len(good)
+    assert n > 40 and nfield > 12

@@ -12,6 +12,7 @@ from the nodes left in the narrow band (urg = 2).  Likewise gridder, bsplrefine 
 called alone (live only).  What stays by restatement only: modrays' own glue between these calls (the refinement window,
 the refined -> coarse mapping, the narrow-band completion: fm2dray_cartesian.f90:262-420) and rpaths, pinned on analytic
 media in test_oracle_fm2d.py."""
+import hashlib
 import os
 
 import numpy as np
@@ -172,3 +173,100 @@ def test_srtimes_equals_the_translated_reference():
     ra, _ = orc.fm2d_srtimes("reference", veln, ttn, gox, goz, dnx, dnz, float(scx), float(scz), rcv, srs)
     rb, _ = orc.fm2d_srtimes("port", veln, ttn, gox, goz, dnx, dnz, float(scx), float(scz), rcv, srs)
     assert ra == 1 and rb == 3
+
+
+def _times_case(rng, k):
+    nvx, nvz = int(rng.integers(3, 26)), int(rng.integers(3, 22))
+    if k % 4 == 1:
+        nvx, nvz = nvx + 9, nvz + 9                                    # room for a refined grid that needs no reallocation
+    gdx, gdz = (1, 1) if k % 3 else (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+    dvx, dvz = float(rng.uniform(0.2, 1.0)), float(rng.uniform(0.2, 1.0))
+    gox, goz = float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3))
+    x, z = np.meshgrid(np.linspace(0, 1, nvx + 2), np.linspace(0, 1, nvz + 2), indexing="ij")
+    vel = 3.0 + 0.4 * np.sin(5 * x + 1.3 * k) * np.cos(4 * z) + 0.2 * rng.random((nvx + 2, nvz + 2))
+    if k % 5 == 0:
+        vel[:] = 3.0                                                   # homogeneous: ties
+    nsrc, nrc = int(rng.integers(1, 6)), int(rng.integers(1, 7))
+    ex, ez = (nvx - 1) * dvx, (nvz - 1) * dvz
+    src = np.stack([gox + rng.uniform(0, ex, nsrc), goz + rng.uniform(0, ez, nsrc)], axis=1)
+    if k % 4 == 1:
+        src[-1] = (gox + ex - 0.3 * dvx / gdx, goz + 0.5 * ez)         # inside the last cell column: the march dies, the field is stale
+    rcv = np.stack([gox + rng.uniform(0, ex, nrc), goz + rng.uniform(0, ez, nrc)], axis=1)
+    srs = (rng.random((nsrc, nrc)) < 0.75).astype(np.int32)
+    if k % 6 == 2 and nsrc > 1:
+        srs[1] = 0                                                     # a source without data is skipped
+    kw = dict(gdx=gdx, gdz=gdz, asgr=int(k % 7 != 3), sgdl=int(rng.integers(1, 6)), sgs=int(rng.integers(1, 9)), fom=int(k % 2))
+    if k % 4 == 1:
+        kw.update(sgdl=int(rng.integers(1, 4)), sgs=int(rng.integers(1, 3)))
+    return src, rcv, srs, vel, gox, goz, dvx, dvz, kw
+
+
+def times_cases(seed, n):
+    """whole-call cases whose outcome is defined in Fortran: no heap overrun, no dead march on reallocated arrays"""
+    rng = np.random.default_rng(seed)
+    k = got = 0
+    while got < n:
+        case = _times_case(rng, k)
+        k += 1
+        src, rcv, srs, vel, gox, goz, dvx, dvz, kw = case
+        unreached = orc.fm2d_unreached(len(src))
+        err, _, field, _ = orc.fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, want_field=True, **kw)
+        orc.fm2d_disarm()
+        realloc = kw["asgr"] == 1 and (2 * kw["sgs"] * kw["sgdl"] + 1 > min(field.shape[1:]))
+        if err == 0 and not (realloc and unreached.max() > 0):
+            got += 1
+            yield case
+
+
+def field_digest(field, srs):
+    marched = [i for i in range(len(srs)) if i == 0 or srs[i].any()]
+    return hashlib.sha256(np.ascontiguousarray(field[marched]).tobytes()).digest()
+
+
+def test_restatement_reproduces_the_reference_fixtures_of_whole_calls():
+    g = np.load(GOLD)
+    nt = int(g["nt"])
+    stale = 0
+    for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw) in enumerate(times_cases(int(g["seed"]), nt)):
+        unreached = orc.fm2d_unreached(len(src))
+        err, tt, field, _ = orc.fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, want_field=True, **kw)
+        orc.fm2d_disarm()
+        assert err == int(g[f"t{k}_err"]) == 0
+        assert np.array_equal(tt, g[f"t{k}_tt"]), (k, kw)
+        assert field_digest(field, srs) == g[f"t{k}_digest"].tobytes(), (k, kw)
+        stale += int(unreached.max() > 0)
+    assert nt >= 24 and stale >= 1
+
+
+@needs_ref
+def test_travel_times_of_whole_calls_equal_the_translated_modrays():
+    """End to end for phase-velocity data: orc_fm2d_times (the oracle every GPU test compares with) against gridder + the body
+    of modrays' source loop + travel + bsplrefine + srtimes as the reference's own statements execute them -- receiver times
+    and the whole field of every marched source, sources whose march dies and return the previous source's field included
+    (the driver keeps ONE ttn array over the source loop, as modrays does); tiny models where the refined grid outgrows the
+    propagation grid and modrays reallocates its arrays; source-grid refinement on and off; dicing 1..3."""
+    seed = int.from_bytes(os.urandom(4), "little")
+    rng = np.random.default_rng(seed)
+    n = stale = big = overrun = 0
+    for k in range(90):
+        src, rcv, srs, vel, gox, goz, dvx, dvz, kw = _times_case(rng, k)
+        unreached = orc.fm2d_unreached(len(src))
+        e0, t0, f0, _ = orc.fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, want_field=True, **kw)
+        orc.fm2d_disarm()
+        e1, t1, f1 = orc.fm2d_times_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, **kw)
+        if e0 == 2:        # narrow band larger than snb * nnx * nnz (tiny grids): the Fortran overruns btg(maxbt) -- undefined
+            overrun += 1
+            continue
+        assert e0 == e1 == 0, (seed, k, e0, e1)
+        nnx, nnz = f0.shape[1:]
+        # does modrays reallocate veln / ttn / nsts for the refined grid (fm2dray_cartesian.f90:316-330)?  Then what a dead march
+        # returns is a fresh ALLOCATE's content -- undefined in Fortran (zeros in the translation, the previous source's field in
+        # the restatement): not compared.  Without reallocation the stale field itself is pinned.
+        realloc = kw["asgr"] == 1 and (2 * kw["sgs"] * kw["sgdl"] + 1 > min(nnx, nnz))
+        cmp = [i for i in range(len(src)) if (i == 0 or srs[i].any()) and (unreached[i] == 0 or not realloc)]
+        assert np.array_equal(t0[cmp], t1[cmp]), (seed, k, kw)
+        assert np.array_equal(f0[cmp], f1[cmp]), (seed, k, kw)
+        n += 1
+        stale += int(any(unreached[i] > 0 for i in cmp))
+        big += int(realloc)
+    assert n + overrun == 90 and overrun <= 10 and stale >= 2 and big >= 5, (seed, n, overrun, stale, big)

@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as orc                                              # noqa: E402
-from test_oracle_fm2d_vs_reference import cases, run_case             # noqa: E402
+from test_oracle_fm2d_vs_reference import cases, run_case, times_cases, field_digest   # noqa: E402
 
 SEED, N = 20261018, 40
 assert orc.have_fm2d_reference(), "oracle/_ref/libfm2d_ttime_f2c.so missing: run oracle/build_ref.sh"
@@ -21,6 +21,15 @@ for k, case in enumerate(cases(SEED, N)):
         out[f"{k}_{j}_ttn"] = ttn
         out[f"{k}_{j}_nsts"] = nsts
         out[f"{k}_{j}_heap"] = heap
+# whole calls of modrays for travel times (gridder + the source loop's body + travel + bsplrefine + srtimes, all translated):
+# receiver times and a digest of every marched source's field
+NT = 24
+out["nt"] = NT
+for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw) in enumerate(times_cases(SEED, NT)):
+    err, tt, field = orc.fm2d_times_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, **kw)
+    out[f"t{k}_err"] = err
+    out[f"t{k}_tt"] = tt
+    out[f"t{k}_digest"] = np.frombuffer(field_digest(field, srs), dtype=np.uint8)
 path = os.path.join(ROOT, "tests", "golden", "fm2d_travel_ref.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes")
