@@ -27,10 +27,10 @@ fi
 if [ -f "$REF/fm2d/fm2d_ttime.f90" ] && [ -f "$REF/fm2d/fm2d_globalp.f90" ]; then
   mkdir -p "$OUT"
   python "$HERE/f90toc.py" "$REF/fm2d/fm2d_globalp.f90" "$REF/fm2d/fm2d_ttime.f90" \
-      "$REF/fm2d/fm2dray_cartesian.f90:gridder,bsplrefine,srtimes,@modrays_source" "$OUT/fm2d_ttime_f2c.c"
+      "$REF/fm2d/fm2dray_cartesian.f90:gridder,bsplrefine,srtimes,rpaths,@modrays_source" "$OUT/fm2d_ttime_f2c.c"
   gcc -O2 -fPIC -std=gnu11 -ffp-contract=off -fno-fast-math -shared -DFM2D_F2C_SOURCE="\"$OUT/fm2d_ttime_f2c.c\"" \
       -o "$OUT/libfm2d_ttime_f2c.so" "$HERE/ref_harness/fm2d_f90_harness.c" -lm
-  echo "build_ref: built $OUT/libfm2d_ttime_f2c.so from $REF/fm2d/fm2d_ttime.f90 + gridder, bsplrefine, srtimes of fm2dray_cartesian.f90"
+  echo "build_ref: built $OUT/libfm2d_ttime_f2c.so from $REF/fm2d/fm2d_ttime.f90 + gridder, bsplrefine, srtimes, rpaths and the body of the source loop of fm2dray_cartesian.f90"
 else
   echo "build_ref: $REF/fm2d/fm2d_ttime.f90 not present, skipping the translated fast-marching core"
 fi

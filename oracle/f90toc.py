@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """oracle/f90toc.py -- mechanical Fortran 90 -> C translation of the reference's fast-marching code: fm2d/fm2d_ttime.f90
 (module traveltime: travel, fouds1, fouds2, addtree, downtree, updtree, bilinear), selected subroutines of
-fm2d/fm2dray_cartesian.f90 (gridder, bsplrefine, srtimes) and the body of modrays' source loop (MODRAYS_SOURCE below), with
+fm2d/fm2dray_cartesian.f90 (gridder, bsplrefine, srtimes, rpaths) and the body of modrays' source loop (MODRAYS_SOURCE below), with
 the module variables of fm2d/fm2d_globalp.f90.
 
 TEST INFRASTRUCTURE.  There is no Fortran compiler in the build image; the restatement oracle/fm2d_ref.c would
@@ -26,7 +26,7 @@ What is added to f77toc's subset:
     `travel` itself).
 
 usage: f90toc.py /root/reference/fm2d/fm2d_globalp.f90 /root/reference/fm2d/fm2d_ttime.f90 \
-                 /root/reference/fm2d/fm2dray_cartesian.f90:gridder,bsplrefine,srtimes out.c
+                 /root/reference/fm2d/fm2dray_cartesian.f90:gridder,bsplrefine,srtimes,rpaths,@modrays_source out.c
 """
 import os
 import re
@@ -64,6 +64,8 @@ def read_free_form(path):
             pending = None
         if t.endswith("&"):
             pending = (t[:-1], ln)
+            continue
+        if re.fullmatch(r"\d+continue", t):             # a labelled CONTINUE nobody jumps to
             continue
         out.append((t, ln))
     return out
@@ -237,6 +239,11 @@ class Unit90(Unit):
             if rn.kind == "var" and self.dims_of(rn.name) is not None:
                 a, b = ln.name, rn.name
                 ra, rb = self.rank_alloc(a), self.rank_alloc(b)
+                if ra is None and rb is None:           # two explicit-shape arrays of one shape:  vio = vi
+                    assert self.dims_of(a) == self.dims_of(b), (lhs, rhs)
+                    n = " * ".join(f"({self.expr_c(d, INT)})" for d in self.dims_of(a))
+                    self.emit(f"for (int i_ = 0; i_ < {n}; ++i_) {a}[i_] = {b}[i_];")
+                    return
                 assert ra is not None and ra == rb, (lhs, rhs)
                 # Fortran 2003 (gfortran's default, -frealloc-lhs): an allocatable left-hand side of another shape is reallocated
                 differ = " || ".join(f"{a}_d{k + 1} != {b}_d{k + 1}" for k in range(ra))
@@ -256,6 +263,14 @@ class Unit90(Unit):
 
     def statement(self, text, ln):
         t = text
+        if t.startswith("rays(") or t.startswith("allocate(rays("):
+            # rpaths hands every traced ray to the caller's container, an array of the derived type T_RAY of module m_fm2d
+            # (allocatable component, type-bound procedure: outside the subset).  The translation hands the same data -- slot,
+            # number of points, the (2, nrp) point array, source and receiver -- to the driver's f90_ray_store instead.
+            if t.endswith("%points=praypts"):
+                self.tr.uses_ray_store = True
+                self.emit(f"f90_ray_store({self.expr_c('pnpts(1,2)', INT)}, {self.expr_c('nrp', INT)}, praypts, {self.expr_c('csid', INT)}, {self.expr_c('i', INT)});")
+            return
         m = re.fullmatch(r"dowhile\((.*)\)", t)
         if m:
             self.emit(f"while ({self.parse(m.group(1)).c}) {{")
@@ -311,6 +326,7 @@ class Translator90:
         self.mod = mod
         self.units = []
         self.called = set()
+        self.uses_ray_store = False
 
     def run(self, stmts, only=None):
         """only: names of the subroutines to translate (everything else in the file, module-level statements included, is skipped)"""
@@ -353,11 +369,16 @@ class Translator90:
             if in_spec:
                 if text in ("implicitnone",) or re.fullmatch(r"use[a-z0-9_]+", text):
                     continue
+                if text.startswith("type(t_ray)"):
+                    continue                             # type(T_RAY) :: rays -- see Unit90.statement
                 d = self.mod.declare(text)
                 if d is not None:
                     for name, typ, dims, init, is_par in d:
                         u.types[name] = typ
-                        if dims and all(d_ == ":" for d_ in dims):
+                        if is_par:
+                            u.params[name] = None
+                            u.params[name] = u.cast(u.parse(init), typ)
+                        elif dims and all(d_ == ":" for d_ in dims):
                             u.alloc[name] = len(dims)
                         elif dims:
                             u.dims[name] = dims
@@ -435,13 +456,18 @@ class Translator90:
              "static inline double f_min(double a, double b) { return a < b ? a : b; }", "static inline double f_max(double a, double b) { return a > b ? a : b; }",
              "static inline int f_mini(int a, int b) { return a < b ? a : b; }", "static inline int f_maxi(int a, int b) { return a > b ? a : b; }", ""]
         o += self.mod.c_decls() + [""]
+        if self.uses_ray_store:
+            o.append("static void f90_ray_store(int slot, int nrp, const double* praypts, int csid, int revid); /* the driver's */")
         for u in self.units:
             o.append(f"static void {u.name}_({', '.join('void* ' + a + '_a' for a in u.args) or 'void'});")
         o.append("")
         for u in self.units:
             o.append(f"static void {u.name}_({', '.join('void* ' + a + '_a' for a in u.args) or 'void'}) {{")
             for a in u.args:
-                o.append(f"  {CT[u.vtype(a)]}* {a} = ({CT[u.vtype(a)]}*){a}_a;")
+                if a in u.types:                         # (the ray container has no C type: it stays an untyped address)
+                    o.append(f"  {CT[u.vtype(a)]}* {a} = ({CT[u.vtype(a)]}*){a}_a;")
+            for k, v in u.params.items():
+                o.append(f"  const {CT[u.types[k]]} {k.upper()} = {v};")
             for name, dims in u.dims.items():
                 if name in u.args:
                     continue

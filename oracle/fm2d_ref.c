@@ -8,16 +8,16 @@
  *   bsplrefine         :598-668                             (B-spline velocities on the refined source grid)
  *   srtimes            :676-770                             (bilinear receiver times; near-source special case)
  *   travel, fouds1, fouds2, addtree, downtree, updtree, bilinear   fm2d/fm2d_ttime.f90
- * Not restated: rpaths (ray geometry; needed for group-velocity data and `crazyray`), the `dynamic` restart (switched
- * off in the reference itself, fm2dray_cartesian.f90:251-252).
+ * Not restated: the `dynamic` restart (switched off in the reference itself, fm2dray_cartesian.f90:251-252).
  *
  * PARITY STATUS: no Fortran compiler in this image, no golden values in the reference.
- *   PINNED on the reference's own source (travel times): all of fm2d_ttime.f90 (travel, fouds1, fouds2, addtree, downtree,
- *   updtree, bilinear), gridder / bsplrefine / srtimes and the body of modrays' source loop, translated statement by
+ *   PINNED on the reference's own source: all of fm2d_ttime.f90 (travel, fouds1, fouds2, addtree, downtree, updtree,
+ *   bilinear), gridder / bsplrefine / srtimes / rpaths and the body of modrays' source loop, translated statement by
  *   statement to C by oracle/f90toc.py (oracle/_ref/libfm2d_ttime_f2c.so) -- bit-identical per routine (fields, node
- *   status, heap; urg 0/1/2; both operator orders; ties; rough media) and for whole calls of orc_fm2d_times (every
- *   receiver time and field): tests/test_oracle_fm2d_vs_reference.py, committed fixtures + fresh random cases.
- *   "parity unpinned" (restatement only, pinned on analytic media by tests/test_oracle_fm2d.py): rpaths.
+ *   status, heap; urg 0/1/2; both operator orders; ties; rough media) and for whole calls of orc_fm2d_times and
+ *   orc_fm2d_rays (every receiver time, field and ray point): tests/test_oracle_fm2d_vs_reference.py, committed fixtures +
+ *   fresh random cases.  Deliberately different where the Fortran is undefined (flagged instead, see rpaths below and
+ *   the test): 0/0 gradient, btg overrun, ipzr unassigned with asgr = 0.
  * All arithmetic is double (REAL(KIND=i10) = c_double); default-real literals in the source are exactly representable;
  * x**2 is x*x, x**3 is (x*x)*x as gfortran expands integer powers.
  */

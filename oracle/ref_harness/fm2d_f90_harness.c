@@ -77,21 +77,41 @@ int ref_fm2d_srtimes(int nnx_, int nnz_, double gox_, double goz_, double dnx_, 
   return f90_stopped;
 }
 
-/* modrays for travel times only (uar = 1, wrgf = 0, no timeField): the statements of fm2dray_cartesian.f90:137-205 and the
- * skeleton of its source loop (:209-212, :440-450) are written out here -- allocations and assignments of dummy arguments to
- * module variables; everything that computes is the translation: gridder, modrays_source (the loop body :213-438), srtimes.
- * velvin (nvz+2, nvx+2), srs_ (nrc, nsrc), ttime (nrc, nsrc), all column major; field: optional (nnz, nnx, nsrc), the
- * travel-time field of every marched source (ttn(1:nnz,1:nnx) as `timeField(:,:,i) = ttn(1:nnz,1:nnx)` would take it).
- * Returns 0, 1 (STOP: a source outside the model) or 3 (STOP: a receiver outside the model). */
-int ref_fm2d_modrays_times(int nsrc_, const double* scx_, const double* scz_, int nrc_, const double* rcx_, const double* rcz_,
-                           const int* srs_, int nvx_, int nvz_, double gox_, double goz_, double dvx_, double dvz_, const double* velvin,
-                           int gdx_, int gdz_, int asgr_, int sgdl_, int sgs_, int fom_, double snb_, double* ttime, double* field) {
-  int rc = 0;
+/* where rpaths' rays go (the translation calls this instead of filling the caller's T_RAY array: oracle/f90toc.py) */
+static __thread int* g_ray_npts;
+static __thread double* g_ray_pts;
+static __thread int g_ray_cap, g_ray_slots, g_ray_err;
+static void f90_ray_store(int slot, int nrp, const double* praypts, int csid, int revid) {
+  (void)csid; (void)revid;
+  if (!g_ray_npts) return;
+  if (slot < 1 || slot > g_ray_slots || nrp > g_ray_cap) { g_ray_err = 1; return; }
+  g_ray_npts[slot - 1] = nrp;
+  for (int j = 0; j < nrp; ++j) {
+    g_ray_pts[((size_t)(slot - 1) * g_ray_cap + j) * 2 + 0] = praypts[2 * j + 0];   /* praypts(1,j) */
+    g_ray_pts[((size_t)(slot - 1) * g_ray_cap + j) * 2 + 1] = praypts[2 * j + 1];   /* praypts(2,j) */
+  }
+}
+
+/* modrays (wrgf = 0, no timeField): the statements of fm2dray_cartesian.f90:137-205 and the skeleton of its source loop
+ * (:209-212, :440-450) are written out here -- allocations and assignments of dummy arguments to module variables; everything
+ * that computes is the translation: gridder, modrays_source (the loop body :213-438), srtimes and, with uar = 0 (group-velocity
+ * data), rpaths.  velvin (nvz+2, nvx+2), srs_ / srsv_ (nrc, nsrc), ttime (nrc, nsrc), all column major; field: optional
+ * (nnz, nnx, nsrc), the travel-time field of every marched source (ttn(1:nnz,1:nnx) as `timeField(:,:,i) = ttn(1:nnz,1:nnx)`
+ * would take it); rays: ray_npts[nrc*nsrc] (zeroed by the caller), ray_pts[nrc*nsrc][cap][2], by slot srsv - 1; *crazy =
+ * modrays' crazyray.  Returns 0, 1 (STOP: a source outside the model), 3 (STOP: a receiver outside the model), 4 (a ray that
+ * does not fit the caller's slots). */
+int ref_fm2d_modrays(int nsrc_, const double* scx_, const double* scz_, int nrc_, const double* rcx_, const double* rcz_,
+                     const int* srs_, int nvx_, int nvz_, double gox_, double goz_, double dvx_, double dvz_, const double* velvin,
+                     int gdx_, int gdz_, int asgr_, int sgdl_, int sgs_, int fom_, double snb_, double* ttime, double* field,
+                     int uar, const int* srsv_, int cap, int* ray_npts, double* ray_pts, int* crazy) {
+  int rc = 0, crazyray = 0;
   nrc = nrc_;
   rcx = (double*)rcx_; rcx_d1 = nrc_; rcz = (double*)rcz_; rcz_d1 = nrc_;
   srs = (int*)srs_; srs_d1 = nrc_; srs_d2 = nsrc_;
+  srsv = (int*)srsv_; srsv_d1 = nrc_; srsv_d2 = nsrc_;
   gdx = gdx_; gdz = gdz_; asgr = asgr_; sgdl = sgdl_; fom = fom_; earth = 6371.0; snb = snb_;
-  veln = 0; velnb = 0; ttnr = 0; nstsr = 0;
+  veln = 0; velnb = 0; ttnr = 0; nstsr = 0; npts = 0; raypts = 0;
+  g_ray_npts = ray_npts; g_ray_pts = ray_pts; g_ray_cap = cap; g_ray_slots = nrc_ * nsrc_; g_ray_err = 0;
   gridder_(&nvx_, &nvz_, &gox_, &goz_, &dvx_, &dvz_, (void*)velvin);
   const int cnx = nnx, cnz = nnz;
   ttn_l1 = ttn_l2 = 1; ttn_d1 = nnz; ttn_d2 = nnx; ttn = (double*)calloc((size_t)nnz * nnx, sizeof(double));   /* ALLOCATE(ttn(nnz,nnx)) */
@@ -99,7 +119,7 @@ int ref_fm2d_modrays_times(int nsrc_, const double* scx_, const double* scz_, in
   btg_l1 = 1; btg_d1 = (int)lround(snb * nnx * nnz); btg = (backpointer*)calloc((size_t)btg_d1 + 64, sizeof(backpointer)); /* maxbt=NINT(snb*nnx*nnz); ALLOCATE(btg(maxbt)) (+ the translator's pad) */
   f90_stopped = 0;
   for (int i = 1; i <= nsrc_ && !rc; ++i) {
-    int any = 0, nsrc = nsrc_, sgs = sgs_;
+    int any = 0, nsrc = nsrc_, sgs = sgs_, wrgf = 0;
     double x = 0, z = 0;
     for (int r = 0; r < nrc_; ++r) any += srs_[(size_t)(i - 1) * nrc_ + r];
     if (any == 0 && i != 1) continue;                     /* IF(SUM(srs(:,i)).EQ.0.AND.i.NE.1) cycle */
@@ -110,9 +130,23 @@ int ref_fm2d_modrays_times(int nsrc_, const double* scx_, const double* scz_, in
         for (int j = 0; j < cnz; ++j) field[((size_t)(i - 1) * cnx + k) * cnz + j] = ttn[(size_t)k * ttn_d1 + j];
     srtimes_(&x, &z, &i, ttime, &nsrc);
     if (f90_stopped) { rc = 3; break; }
+    if (uar == 0) {                                       /* IF(uar .eq. 0 .OR. wrgf.eq.i.OR.wrgf.LT.0)THEN */
+      rpaths_(&wrgf, &uar, &i, &x, &z, 0);
+      if (f90_stopped) { rc = 3; break; }
+      if (g_ray_err) { rc = 4; break; }
+      crazyray = crazyray + crazyrp;
+    }
     if (asgr == 1 && ttnr) { free(ttnr); ttnr = 0; free(nstsr); nstsr = 0; }   /* IF(asgr.EQ.1 .and. allocated(ttnr)) DEALLOCATE(ttnr,nstsr) */
   }
+  if (crazy) *crazy = crazyray;
   free(velnb); velnb = 0; free(ttnr); ttnr = 0; free(nstsr); nstsr = 0;
   free(veln); veln = 0; free(ttn); ttn = 0; free(nsts); nsts = 0; free(btg); btg = 0; free(velv); velv = 0;
+  g_ray_npts = 0;
   return rc;
+}
+int ref_fm2d_modrays_times(int nsrc_, const double* scx_, const double* scz_, int nrc_, const double* rcx_, const double* rcz_,
+                           const int* srs_, int nvx_, int nvz_, double gox_, double goz_, double dvx_, double dvz_, const double* velvin,
+                           int gdx_, int gdz_, int asgr_, int sgdl_, int sgs_, int fom_, double snb_, double* ttime, double* field) {
+  return ref_fm2d_modrays(nsrc_, scx_, scz_, nrc_, rcx_, rcz_, srs_, nvx_, nvz_, gox_, goz_, dvx_, dvz_, velvin, gdx_, gdz_, asgr_, sgdl_,
+                          sgs_, fom_, snb_, ttime, field, 1, srs_, 0, 0, 0, 0);
 }

@@ -500,3 +500,32 @@ def fm2d_times_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, a
     err = fn(nsrc, scx.ctypes.data, scz.ctypes.data, nrc, rcx.ctypes.data, rcz.ctypes.data, srs.ctypes.data, nvx, nvz, gox, goz, dvx, dvz,
              vel.ctypes.data, gdx, gdz, asgr, sgdl, sgs, fom, snb, tt.ctypes.data, field.ctypes.data)
     return err, tt, field
+
+
+def fm2d_rays_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, asgr=1, sgdl=4, sgs=8, fom=1, snb=0.5, cap=None, srsv=None):
+    """modrays with uar = 0 through the TRANSLATED reference (rpaths included): same arguments as fm2d_rays; returns
+    (err, ttime, npts, pts, crazy)."""
+    fn = _fm2d_fn("reference", "modrays")
+    vpt = C.c_void_p
+    fn.argtypes = [C.c_int, vpt, vpt, C.c_int, vpt, vpt, vpt, C.c_int, C.c_int] + [C.c_double] * 4 + [vpt] + [C.c_int] * 6 + \
+                  [C.c_double, vpt, vpt, C.c_int, vpt, C.c_int, vpt, vpt, vpt]
+    fn.restype = C.c_int
+    src, rcv, vel = f64(src), f64(rcv), f64(vel)
+    nsrc, nrc = len(src), len(rcv)
+    nvx, nvz = vel.shape[0] - 2, vel.shape[1] - 2
+    scx, scz = f64(src[:, 0].copy()), f64(src[:, 1].copy())
+    rcx, rcz = f64(rcv[:, 0].copy()), f64(rcv[:, 1].copy())
+    srs = np.ascontiguousarray(srs, dtype=np.int32)
+    if srsv is None:
+        srsv = np.arange(1, nsrc * nrc + 1, dtype=np.int32).reshape(nsrc, nrc)
+    srsv = np.ascontiguousarray(srsv, dtype=np.int32)
+    if cap is None:
+        cap = 8 * (nvx * gdx + nvz * gdz)
+    tt = np.full((nsrc, nrc), -1.0)
+    npts = np.zeros(nsrc * nrc, np.int32)
+    pts = np.zeros((nsrc * nrc, cap, 2))
+    crazy = C.c_int(0)
+    err = fn(nsrc, scx.ctypes.data, scz.ctypes.data, nrc, rcx.ctypes.data, rcz.ctypes.data, srs.ctypes.data, nvx, nvz, gox, goz, dvx, dvz,
+             vel.ctypes.data, gdx, gdz, asgr, sgdl, sgs, fom, snb, tt.ctypes.data, None, 0, srsv.ctypes.data, cap, npts.ctypes.data,
+             pts.ctypes.data, C.byref(crazy))
+    return err, tt, npts, pts, crazy.value

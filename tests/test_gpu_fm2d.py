@@ -185,3 +185,17 @@ def test_fm2d_device_equals_the_reference_derived_fixtures_directly(mct):
             nfield += 1
         n += len(good)
     assert n > 40 and nfield > 12
+
+
+def test_fm2d_device_rays_equal_the_reference_derived_fixtures_directly(mct):
+    """Group-velocity data: the device's ray points, point counts, crazy-ray count and times against the fixtures made by the
+    translated modrays + rpaths (no restatement in between)."""
+    from test_oracle_fm2d_vs_reference import GOLD, rays_cases, check_rays_against_fixture
+    g = np.load(GOLD)
+    rays = 0
+    for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw, cap) in enumerate(rays_cases(int(g["seed"]), int(g["nr"]))):
+        o = mct.fm2d_opts(gridx=kw["gdx"], gridy=kw["gdz"], sgref=1, sgdic=kw["sgdl"], sgext=kw["sgs"], order=kw["fom"])
+        r = mct.fm2d_rays(src, rcv, srs[None], vel[None], gox, goz, dvx, dvz, o, cap=cap)
+        tt = np.where(srs == 1, r["ttime"][0], -1.0)
+        rays += check_rays_against_fixture(g, k, tt, r["npts"][0], r["pts"][0], int(r["crazy"][0]))
+    assert rays > 60

@@ -270,3 +270,110 @@ def test_travel_times_of_whole_calls_equal_the_translated_modrays():
         stale += int(any(unreached[i] > 0 for i in cmp))
         big += int(realloc)
     assert n + overrun == 90 and overrun <= 10 and stale >= 2 and big >= 5, (seed, n, overrun, stale, big)
+
+
+def rays_cases(seed, n):
+    """whole-call cases for group-velocity data: refinement on, receivers off the last cell row / column (rpaths STOPs there),
+    no heap overrun, no dead march"""
+    rng = np.random.default_rng(seed + 1)
+    k = got = 0
+    while got < n:
+        src, rcv, srs, vel, gox, goz, dvx, dvz, kw = _times_case(rng, k)
+        k += 1
+        kw["asgr"] = 1
+        nnx, nnz = (vel.shape[0] - 3) * kw["gdx"] + 1, (vel.shape[1] - 3) * kw["gdz"] + 1
+        rcv[:, 0] = np.minimum(rcv[:, 0], gox + (nnx - 1.001) * dvx / kw["gdx"])
+        rcv[:, 1] = np.minimum(rcv[:, 1], goz + (nnz - 1.001) * dvz / kw["gdz"])
+        unreached = orc.fm2d_unreached(len(src))
+        err = orc.fm2d_times(src, rcv, srs, vel, gox, goz, dvx, dvz, **kw)[0]
+        orc.fm2d_disarm()
+        if err == 0 and unreached.max() == 0:
+            got += 1
+            yield src, rcv, srs, vel, gox, goz, dvx, dvz, kw, nnx * nnz + 2
+
+
+def ray_digests(npts, pts):
+    return np.stack([np.frombuffer(hashlib.sha256(np.ascontiguousarray(pts[s_, :npts[s_]]).tobytes()).digest(), dtype=np.uint8)
+                     for s_ in range(len(npts))])
+
+
+def jumps_of(npts, pts, dpl):
+    """slots whose reference ray contains the corner jump that follows a 0/0 gradient (see the live test below)"""
+    out = np.zeros(len(npts), bool)
+    for s_ in range(len(npts)):
+        q = pts[s_, :npts[s_]]
+        if len(q) > 1:
+            out[s_] = np.sqrt(((q[1:] - q[:-1]) ** 2).sum(1)).max() > 3.0 * dpl
+    return out
+
+
+def check_rays_against_fixture(g, k, tt, npts, pts, crazy):
+    """shared by the CPU test (restatement) and the GPU test (device): times, point counts, every point, crazy-ray count"""
+    assert np.array_equal(tt, g[f"r{k}_tt"]), k
+    ref_n, ref_d, jump = g[f"r{k}_npts"], g[f"r{k}_digest"], g[f"r{k}_jump"]
+    d = ray_digests(npts, pts)
+    for s_ in range(len(ref_n)):
+        if jump[s_]:
+            assert npts[s_] == 1, (k, s_)              # ended as a crazy ray instead of following the jump
+        else:
+            assert npts[s_] == ref_n[s_] and np.array_equal(d[s_], ref_d[s_]), (k, s_, npts[s_], ref_n[s_])
+    assert crazy == int(g[f"r{k}_crazy"]) + int(jump.sum()), k
+    return int((ref_n > 1).sum())
+
+
+def test_restatement_reproduces_the_reference_ray_fixtures():
+    g = np.load(GOLD)
+    rays = 0
+    for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw, cap) in enumerate(rays_cases(int(g["seed"]), int(g["nr"]))):
+        err, tt, npts, pts, _, crazy = orc.fm2d_rays(src, rcv, srs, vel, gox, goz, dvx, dvz, cap=cap, **kw)
+        assert err == 0
+        rays += check_rays_against_fixture(g, k, tt, npts, pts, crazy)
+    assert rays > 60
+
+
+@needs_ref
+def test_rays_of_whole_calls_equal_the_translated_modrays():
+    """Group-velocity data (uar = 0): rpaths too is the reference's own statements here (fm2dray_cartesian.f90:801-1456; its
+    T_RAY container replaced by the driver's store).  Every ray point, the point counts, the crazy-ray count and the receiver
+    times of orc_fm2d_rays must equal the translation's.  Source-grid refinement on, as shipped: without it the Fortran reads
+    a variable it never assigned (ipzr) and divides 0 by 0 next to the source -- outcomes the restatement flags instead."""
+    seed = int.from_bytes(os.urandom(4), "little")
+    rng = np.random.default_rng(seed)
+    n = rays = crazies = jumps = 0
+    for k in range(110):
+        src, rcv, srs, vel, gox, goz, dvx, dvz, kw = _times_case(rng, k)
+        kw["asgr"] = 1
+        nnx, nnz = (vel.shape[0] - 3) * kw["gdx"] + 1, (vel.shape[1] - 3) * kw["gdz"] + 1
+        # rpaths refuses receivers in the last cell row / column (ipx >= nnx: STOP): keep them off it
+        rcv[:, 0] = np.minimum(rcv[:, 0], gox + (nnx - 1.001) * dvx / kw["gdx"])
+        rcv[:, 1] = np.minimum(rcv[:, 1], goz + (nnz - 1.001) * dvz / kw["gdz"])
+        cap = nnx * nnz + 2                                            # the Fortran's own limit (maxrp + 1 points)
+        unreached = orc.fm2d_unreached(len(src))
+        e0, t0, n0, p0, l0, c0 = orc.fm2d_rays(src, rcv, srs, vel, gox, goz, dvx, dvz, cap=cap, **kw)
+        orc.fm2d_disarm()
+        if e0 == 2 or unreached.max() > 0:                             # heap overrun / a dead march: undefined in the Fortran (see above)
+            continue
+        e1, t1, n1, p1, c1 = orc.fm2d_rays_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, cap=cap, **kw)
+        assert e0 == e1 == 0, (seed, k, e0, e1)
+        assert np.array_equal(t0, t1), (seed, k, kw)
+        dpl = 0.5 * min(dvx / kw["gdx"], dvz / kw["gdz"])
+        zero_grad = 0
+        for slot in range(len(n0)):
+            if n0[slot] == n1[slot]:
+                assert np.array_equal(p0[slot, :n0[slot]], p1[slot, :n1[slot]]), (seed, k, slot, kw)
+                continue
+            # The one outcome the restatement (and the device) deliberately do not reproduce: a gradient that vanishes exactly
+            # (symmetry, in a homogeneous medium) is 0/0 in the Fortran; the NaN point becomes INT_MIN + 1 in floor(), the
+            # boundary clamp then puts the "ray" on the model's corner, from where it walks on to the source.  The restatement
+            # ends such a ray as a crazy one (one point).  Recognised here by the jump.
+            q = p1[slot, :n1[slot]]
+            steps = np.sqrt(((q[1:] - q[:-1]) ** 2).sum(1))
+            assert n0[slot] == 1 and steps.max() > 3.0 * dpl, (seed, k, slot, kw, n0[slot], n1[slot])
+            zero_grad += 1
+        assert c0 == c1 + zero_grad, (seed, k, c0, c1, zero_grad)
+        n += 1
+        rays += int((n0 > 1).sum())
+        crazies += c1
+        jumps += zero_grad
+    print(f"rays: {n} calls, {rays} rays traced, {crazies} crazy in the reference, {jumps} zero-gradient jumps")
+    assert n >= 50 and rays > 250 and jumps < rays // 8, (seed, n, rays, crazies, jumps)

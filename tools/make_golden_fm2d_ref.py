@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as orc                                              # noqa: E402
-from test_oracle_fm2d_vs_reference import cases, run_case, times_cases, field_digest   # noqa: E402
+from test_oracle_fm2d_vs_reference import cases, run_case, times_cases, field_digest, rays_cases, ray_digests, jumps_of   # noqa: E402
 
 SEED, N = 20261018, 40
 assert orc.have_fm2d_reference(), "oracle/_ref/libfm2d_ttime_f2c.so missing: run oracle/build_ref.sh"
@@ -30,6 +30,18 @@ for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw) in enumerate(times_cases(SEE
     out[f"t{k}_err"] = err
     out[f"t{k}_tt"] = tt
     out[f"t{k}_digest"] = np.frombuffer(field_digest(field, srs), dtype=np.uint8)
+# whole calls for group-velocity data (rpaths translated too): times, point counts, a digest of every ray's points, the crazy
+# count, and which rays contain the corner jump that follows a 0/0 gradient in the Fortran
+NR = 16
+out["nr"] = NR
+for k, (src, rcv, srs, vel, gox, goz, dvx, dvz, kw, cap) in enumerate(rays_cases(SEED, NR)):
+    err, tt, npts, pts, crazy = orc.fm2d_rays_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, cap=cap, **kw)
+    assert err == 0
+    out[f"r{k}_tt"] = tt
+    out[f"r{k}_npts"] = npts
+    out[f"r{k}_digest"] = ray_digests(npts, pts)
+    out[f"r{k}_jump"] = jumps_of(npts, pts, 0.5 * min(dvx / kw["gdx"], dvz / kw["gdz"]))
+    out[f"r{k}_crazy"] = crazy
 path = os.path.join(ROOT, "tests", "golden", "fm2d_travel_ref.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes")
