@@ -13,7 +13,8 @@
  * PARITY STATUS: "parity unpinned".  The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent
- * 50-digit propagator-matrix secular function and are the lowest mode) and by line-by-line reading.
+ * 50-digit propagator-matrix secular function and are the lowest mode) and by line-by-line reading; the complex
+ * primitives alone are held bit for bit to what gcc emits for double complex under -fcx-fortran-rules and to libm's cexp.
  *
  * Conventions kept from the Fortran: default-real literals are float-rounded (0.12, 0.90, 3.1415926, 0.005, 1E-6, 1.1);
  * complex multiplication is (ac-bd, ad+bc), complex division is the range-reduced form gfortran emits
@@ -84,6 +85,20 @@ static inline cx csq(double c, double vel) {
   double t = c / vel;
   double x = 1 - t * t;
   return x >= 0 ? CX(sqrt(x), 0.0) : CX(0.0, sqrt(-x));
+}
+
+/* test entry: the complex primitives above, so that tests/test_oracle_grt.py can hold them to what the compiler itself emits
+ * for double complex under -fcx-fortran-rules (gfortran's rules, same middle end) and to libm's cexp / csqrt.
+ * op 0: a*b, 1: a/b, 2: exp(a) (libm mode), 3: csq(a.re, b.re). */
+void orc_grt_cprim(int op, double are, double aim, double bre, double bim, double* out2) {
+  grt_t G;
+  G.math_mode = 0;
+  cx a = CX(are, aim), b = CX(bre, bim), r;
+  if (op == 0) r = cmul(a, b);
+  else if (op == 1) r = cdiv(a, b);
+  else if (op == 2) r = g_cexp(&G, a);
+  else r = csq(are, bre);
+  out2[0] = r.re; out2[1] = r.im;
 }
 
 static int cmp_d(const void* a, const void* b) { double x = *(const double*)a, y = *(const double*)b; return (x > y) - (x < y); }

@@ -128,3 +128,50 @@ def test_group_velocity_is_the_finite_difference_of_true_roots(modetype):
         assert abs(c0 - c) < 3e-6, (f, c, c0)
         u_ind = dh / ((f + dh) / c1 - f / c0)
         assert abs(u_ind - u) < 2e-3 * u, (f, u, u_ind)
+
+
+def test_complex_primitives_are_the_compilers_fortran_rules(tmp_path):
+    """The R/T restatement spells complex arithmetic out by hand (oracle/grt_ref.c: cmul, cdiv, g_cexp, csq).  gfortran
+    expands COMPLEX*16 multiplication and division in GCC's middle end under its Fortran rules (-fcx-fortran-rules: the plain
+    product, the range-reduced quotient, no NaN recovery) and calls libm's cexp / csqrt; gcc is here and shares that middle
+    end, so a C file using `double _Complex` compiled with that flag IS the reference's arithmetic.  Bit-identical over random
+    operands of every magnitude mix."""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "cx.c"
+    src.write_text("""
+#include <complex.h>
+void cx_prim(int op, double are, double aim, double bre, double bim, double* out) {
+  double _Complex a = are + aim * I, b = bre + bim * I, r;
+  if (op == 0) r = a * b; else if (op == 1) r = a / b; else if (op == 2) r = cexp(a);
+  else { double t = are / bre; r = csqrt((double _Complex)(1 - t * t)); }
+  out[0] = creal(r); out[1] = cimag(r);
+}
+""")
+    so = tmp_path / "libcx.so"
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-fcx-fortran-rules", "-ffp-contract=off", "-o", str(so), str(src), "-lm"])
+    ref = C.CDLL(str(so)).cx_prim
+    got = orc.L().orc_grt_cprim
+    for fn in (ref, got):
+        fn.argtypes = [C.c_int] + [C.c_double] * 4 + [C.c_void_p]
+        fn.restype = None
+    rng = np.random.default_rng(11)
+    a, b = np.zeros(2), np.zeros(2)
+    n = 0
+    for k in range(40000):
+        op = k % 4
+        sc = 10.0 ** rng.integers(-8, 9, 4) if k % 3 else np.ones(4)
+        v = rng.standard_normal(4) * sc
+        if op == 2:
+            v[0] = np.clip(v[0], -600, 600)
+            if k % 40 == 2:
+                v[1] = 0.0                                   # exp of a real
+        if op == 3:
+            v[0], v[2] = abs(v[0]) + 1e-3, abs(v[2]) + 1e-3  # csq(c, vel): positive velocities
+        if k % 50 == 1 and op < 2:
+            v[rng.integers(0, 4)] = 0.0
+        ref(op, *v, a.ctypes.data)
+        got(op, *v, b.ctypes.data)
+        assert a.tobytes() == b.tobytes() or (np.isnan(a).any() and np.isnan(b).any()), (op, v, a, b)
+        n += 1
+    assert n == 40000
