@@ -37,7 +37,8 @@ struct GrtParams {
   int32_t modetype, phaseGroup, np;
   double dc, tolmin, tolmax, smin_min, smin_max, dcm, dc2;
   double freqs[MCT_MAX_PERIODS];
-  const int32_t* list; int32_t nlist, list0; // columns to solve: list[list0 + blockIdx.x]
+  const int32_t* list; int32_t nlist; // columns to solve
+  int32_t* next;                      // the next list entry to hand out (zeroed by the host): blocks are persistent, columns differ widely in cost
   const int32_t* skip; int32_t cols_per_model;
   double* scratch;
   double* pvel; double* gvel; int32_t* ierr;
@@ -874,64 +875,73 @@ __device__ int g_setup(const GrtParams& P, int col, GrtCol& G, double* lay, doub
   return n;
 }
 
+// One warp per column; a block (= warp) is persistent and fetches columns from the list until it is empty -- the grid is sized
+// to the warps the GPU can hold (214 registers: 9 per SM), so 4 096 columns are one launch with no under-filled chunk tails.
 __global__ void __launch_bounds__(32) grt_kernel(const __grid_constant__ GrtParams P) {
   mct_exptab_stage();
   __shared__ GrtCol G;
-  __shared__ int s_n;
+  __shared__ int s_n, s_next;
   __shared__ double s_sort[GRT_SSORT];
   const int lane = threadIdx.x;
-  const int col = P.list[P.list0 + blockIdx.x];
-  if (P.skip && P.skip[2 * (col / P.cols_per_model)] != 0) return; // a model check_model rejected: nothing is solved
   double* base = P.scratch + (size_t)blockIdx.x * GRT_SCRATCH;
   double* lay = base;                                   // GRT_LAY * (MAX_LAYERS + 2)
   double* v = lay + GRT_LAY * (MCT_MAX_LAYERS + 2);     // 2 * (MAX_LAYERS + 2)
   double* vvv = v + 2 * (MCT_MAX_LAYERS + 2);           // GRT_NVPAD (1-based inside)
   double* ccc = vvv + GRT_NVPAD;                        // GRT_NV + 8
-  if (lane == 0) {
-    G.vvv = vvv - 0; G.ccc = ccc;
-    s_n = g_setup(P, col, G, lay, v);
-  }
-  __syncwarp();
-  double* pv = P.pvel + (size_t)col * P.np;
-  double* gv = P.gvel + (size_t)col * P.np;
-  if (s_n == 0) { // stays as the dispersion kernel left it (ierr = 2, preset values)
-    if (lane == 0 && P.flags) atomicMax(&P.flags[2 * (col / P.cols_per_model) + 1], 2);
-    return;
-  }
-  unsigned nsec = 0, nlay = 0;
-  int ierr = 0;
   const double pi_m = (double)3.1415926f; // m_surfmodes' pi
   const double dh = (double)0.005f;
-  double c0 = 0;
   const int np = P.np;
-  for (int i = 1; i <= np; ++i) {
+  for (;;) {
+    __syncwarp();
+    if (lane == 0) s_next = atomicAdd(P.next, 1);
+    __syncwarp();
+    const int k = s_next;
+    if (k >= P.nlist) break;
+    const int col = P.list[k];
+    if (P.skip && P.skip[2 * (col / P.cols_per_model)] != 0) continue; // a model check_model rejected: nothing is solved
     if (lane == 0) {
-      G.w = P.freqs[i - 1] * 2 * pi_m;
-      G.tol = P.tolmin + (np + 1 - i) * (P.tolmax - P.tolmin) / np;
-      G.smin = P.smin_min + (i - 1) * (P.smin_max - P.smin_min) / np;
+      G.vvv = vvv - 0; G.ccc = ccc;
+      s_n = g_setup(P, col, G, lay, v);
     }
     __syncwarp();
-    double root = 0;
-    const int ierr1 = g_search_one(G, c0, &root, lane, nsec, nlay, s_sort);
-    if (ierr1 == 1) { ierr = 1; break; }
-    if (lane == 0) pv[i - 1] = root;
-    c0 = root;
-    if (P.phaseGroup == 1) {
-      const double freq0 = P.freqs[i - 1] + dh;
-      __syncwarp();
-      if (lane == 0) G.w = freq0 * 2 * pi_m;
-      __syncwarp();
-      double root0 = 0;
-      ierr = g_search_one(G, c0, &root0, lane, nsec, nlay, s_sort);
-      if (ierr == 1) break;
-      const double gg = (P.freqs[i - 1] + dh) / root0 - P.freqs[i - 1] / root;
-      if (lane == 0) gv[i - 1] = gg > 0 ? dh / gg : 0;
+    double* pv = P.pvel + (size_t)col * P.np;
+    double* gv = P.gvel + (size_t)col * P.np;
+    if (s_n == 0) { // stays as the dispersion kernel left it (ierr = 2, preset values)
+      if (lane == 0 && P.flags) atomicMax(&P.flags[2 * (col / P.cols_per_model) + 1], 2);
+      continue;
     }
-    __syncwarp();
-  }
-  if (lane == 0) {
-    P.ierr[col] = ierr;
-    if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)nsec); atomicAdd(&P.counters[1], (unsigned long long)nlay); }
+    unsigned nsec = 0, nlay = 0;
+    int ierr = 0;
+    double c0 = 0;
+    for (int i = 1; i <= np; ++i) {
+      if (lane == 0) {
+        G.w = P.freqs[i - 1] * 2 * pi_m;
+        G.tol = P.tolmin + (np + 1 - i) * (P.tolmax - P.tolmin) / np;
+        G.smin = P.smin_min + (i - 1) * (P.smin_max - P.smin_min) / np;
+      }
+      __syncwarp();
+      double root = 0;
+      const int ierr1 = g_search_one(G, c0, &root, lane, nsec, nlay, s_sort);
+      if (ierr1 == 1) { ierr = 1; break; }
+      if (lane == 0) pv[i - 1] = root;
+      c0 = root;
+      if (P.phaseGroup == 1) {
+        const double freq0 = P.freqs[i - 1] + dh;
+        __syncwarp();
+        if (lane == 0) G.w = freq0 * 2 * pi_m;
+        __syncwarp();
+        double root0 = 0;
+        ierr = g_search_one(G, c0, &root0, lane, nsec, nlay, s_sort);
+        if (ierr == 1) break;
+        const double gg = (P.freqs[i - 1] + dh) / root0 - P.freqs[i - 1] / root;
+        if (lane == 0) gv[i - 1] = gg > 0 ? dh / gg : 0;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      P.ierr[col] = ierr;
+      if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)nsec); atomicAdd(&P.counters[1], (unsigned long long)nlay); }
+    }
   }
 }
 

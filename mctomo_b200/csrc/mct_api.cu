@@ -646,10 +646,10 @@ int launch_grt(int ncol, const LayParams* lp, const PreLayParams* pp, const doub
   g.grt_last_cols = 0;
   if (!g.grt_on || opt->nmodes > 0 || g.shard_n > 1 || ncol < 1) return MCT_OK; // surfmmodes has no such branch (surfmodes.f90:153,165)
   int rc;
-  if ((rc = ensure(g.grt_list, sizeof(int32_t) * ((size_t)ncol + 1)))) return rc;
+  if ((rc = ensure(g.grt_list, sizeof(int32_t) * ((size_t)ncol + 2)))) return rc;
   int32_t* list = (int32_t*)g.grt_list.p;
-  int32_t* d_count = list + ncol;
-  CK(cudaMemsetAsync(d_count, 0, sizeof(int32_t), st));
+  int32_t* d_count = list + ncol; // [0] columns listed, [1] the persistent kernel's work counter
+  CK(cudaMemsetAsync(d_count, 0, 2 * sizeof(int32_t), st));
   grt_collect_kernel<<<(ncol + 255) / 256, 256, 0, st>>>((const int32_t*)g.status.p, ncol, list, d_count);
   CK(cudaGetLastError());
   g.host_stats.n_launches += 1;
@@ -657,8 +657,9 @@ int launch_grt(int ncol, const LayParams* lp, const PreLayParams* pp, const doub
   CK(cudaMemcpyAsync(&count, d_count, sizeof count, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (count <= 0) return MCT_OK;
-  const int chunk = std::min<int>(count, 1024);
-  if ((rc = ensure(g.grt_scratch, sizeof(double) * (size_t)GRT_SCRATCH * (size_t)chunk))) return rc;
+  // persistent one-warp blocks, as many as the GPU holds at 214 registers per thread (9 per SM); each owns one scratch slot
+  const int blocks = std::min<int>(count, g.sm_count * 9);
+  if ((rc = ensure(g.grt_scratch, sizeof(double) * (size_t)GRT_SCRATCH * (size_t)blocks))) return rc;
   GrtParams P;
   memset(&P, 0, sizeof P);
   if (lp) {
@@ -673,7 +674,7 @@ int launch_grt(int ncol, const LayParams* lp, const PreLayParams* pp, const doub
   P.dc = opt->dphase;
   P.tolmin = g.grt_par[0]; P.tolmax = g.grt_par[1]; P.smin_min = g.grt_par[2]; P.smin_max = g.grt_par[3]; P.dcm = g.grt_par[4]; P.dc2 = g.grt_par[5];
   for (int i = 0; i < MCT_MAX_PERIODS; ++i) P.freqs[i] = i < np ? freqs[i] : 0.0;
-  P.list = list; P.nlist = count;
+  P.list = list; P.nlist = count; P.next = d_count + 1;
   P.skip = d_skip; P.cols_per_model = cols_per_model > 0 ? cols_per_model : ncol;
   P.scratch = (double*)g.grt_scratch.p;
   P.pvel = d_pvel; P.gvel = d_gvel; P.ierr = d_ierr;
@@ -681,11 +682,8 @@ int launch_grt(int ncol, const LayParams* lp, const PreLayParams* pp, const doub
   P.flags = d_flags;
   {
     ProfScope ps(2, st);
-    for (int c0 = 0; c0 < count; c0 += chunk) {
-      P.list0 = c0;
-      grt_kernel<<<std::min(chunk, count - c0), 32, 0, st>>>(P);
-      g.host_stats.n_launches += 1;
-    }
+    grt_kernel<<<blocks, 32, 0, st>>>(P);
+    g.host_stats.n_launches += 1;
   }
   CK(cudaGetLastError());
   g.grt_last_cols = count;
