@@ -876,7 +876,7 @@ __device__ int g_setup(const GrtParams& P, int col, GrtCol& G, double* lay, doub
 }
 
 // One warp per column; a block (= warp) is persistent and fetches columns from the list until it is empty -- the grid is sized
-// to the warps the GPU can hold (214 registers: 9 per SM), so 4 096 columns are one launch with no under-filled chunk tails.
+// to the warps the GPU can hold (218 registers: 8 per SM), so 4 096 columns are one launch with no under-filled chunk tails.
 __global__ void __launch_bounds__(32) grt_kernel(const __grid_constant__ GrtParams P) {
   mct_exptab_stage();
   __shared__ GrtCol G;

@@ -657,8 +657,8 @@ int launch_grt(int ncol, const LayParams* lp, const PreLayParams* pp, const doub
   CK(cudaMemcpyAsync(&count, d_count, sizeof count, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (count <= 0) return MCT_OK;
-  // persistent one-warp blocks, as many as the GPU holds at 214 registers per thread (9 per SM); each owns one scratch slot
-  const int blocks = std::min<int>(count, g.sm_count * 9);
+  // persistent one-warp blocks, as many as the GPU holds at 218 registers per thread (8 per SM); each owns one scratch slot
+  const int blocks = std::min<int>(count, g.sm_count * 8);
   if ((rc = ensure(g.grt_scratch, sizeof(double) * (size_t)GRT_SCRATCH * (size_t)blocks))) return rc;
   GrtParams P;
   memset(&P, 0, sizeof P);
