@@ -81,6 +81,8 @@ class Module:
     def type_of(self, spec):
         if spec == "integer":
             return INT
+        if spec == "logical":
+            return LOG
         m = re.fullmatch(r"real\(kind=([a-z0-9_]+)\)", spec)
         if m:
             return self.kinds[m.group(1)]
@@ -90,7 +92,7 @@ class Module:
 
     def declare(self, text):
         """a module-level (or local) declaration -> [(name, type, rank or None, dims or None, init or None)]"""
-        m = re.fullmatch(r"(integer|real\(kind=[a-z0-9_]+\)|type\(backpointer\))((?:,[a-z]+(?:\([^)]*\))?)*)(?:::)?(.*)", text)
+        m = re.fullmatch(r"(integer|logical|real\(kind=[a-z0-9_]+\)|type\(backpointer\))((?:,[a-z]+(?:\([^)]*\))?)*)(?:::)?(.*)", text)
         if not m:
             return None
         spec, attrs, ents = m.group(1), m.group(2), m.group(3)
