@@ -34,6 +34,17 @@ if [ -f "$REF/fm2d/fm2d_ttime.f90" ] && [ -f "$REF/fm2d/fm2d_globalp.f90" ]; the
 else
   echo "build_ref: $REF/fm2d/fm2d_ttime.f90 not present, skipping the translated fast-marching core"
 fi
+# ---- the Love-wave generalized R/T secular function, surfmodes/Love.f90 (+ csq, parameters and T_GRT of GRT.f90), translated
+# mechanically (oracle/f90toc_love.py); -fcx-fortran-rules: complex products and quotients as gfortran's middle end expands them
+if [ -f "$REF/surfmodes/Love.f90" ] && [ -f "$REF/surfmodes/GRT.f90" ]; then
+  mkdir -p "$OUT"
+  python "$HERE/f90toc_love.py" "$REF/surfmodes/GRT.f90" "$REF/surfmodes/Love.f90" "$OUT/love_f2c.c"
+  gcc -O2 -fPIC -std=gnu11 -fcx-fortran-rules -ffp-contract=off -fno-fast-math -shared -DLOVE_F2C_SOURCE="\"$OUT/love_f2c.c\"" \
+      -o "$OUT/liblove_f2c.so" "$HERE/ref_harness/love_f90_harness.c" -lm
+  echo "build_ref: built $OUT/liblove_f2c.so from $REF/surfmodes/Love.f90"
+else
+  echo "build_ref: $REF/surfmodes/Love.f90 not present, skipping the translated Love secular function"
+fi
 # ---- and, where a Fortran compiler exists, the real thing (oracle/build_ref_surfdisp.sh)
 if command -v gfortran >/dev/null 2>&1; then "$HERE/build_ref_surfdisp.sh" || true; fi
 # ---- stage 1: the reference's own pre-built kd-tree object

@@ -529,3 +529,36 @@ def fm2d_rays_reference(src, rcv, srs, vel, gox, goz, dvx, dvz, gdx=1, gdz=1, as
              vel.ctypes.data, gdx, gdz, asgr, sgdl, sgs, fom, snb, tt.ctypes.data, None, 0, srsv.ctypes.data, cap, npts.ctypes.data,
              pts.ctypes.data, C.byref(crazy))
     return err, tt, npts, pts, crazy.value
+
+
+# ---- the reference's own surfmodes/Love.f90, mechanically translated to C (oracle/f90toc_love.py, oracle/build_ref.sh) ------
+LOVE_F2C_LIB = os.path.join(ORACLE_DIR, "_ref", "liblove_f2c.so")
+_love_f2c = None
+
+
+def have_love_reference():
+    return os.path.exists(LOVE_F2C_LIB)
+
+
+def grt_love_secfun_reference(thick, vp, vs, rho, freq, c):
+    """SecFuns_L(1 + ifs, c, GRT, Imf) of the TRANSLATED Love.f90 on the T_GRT that the restatement's setup_grt + startl build
+    for this column (the search logic and the set-up stay the restatement's).  Returns (value, imf)."""
+    global _love_f2c
+    if _love_f2c is None:
+        _love_f2c = C.CDLL(LOVE_F2C_LIB)
+    vpt = C.c_void_p
+    st = L().orc_grt_love_state
+    st.argtypes = [vpt] * 4 + [C.c_int, C.c_double, C.c_double, vpt, vpt, vpt, vpt, vpt]
+    thick, vp, vs, rho = f64(thick), f64(vp), f64(vs), f64(rho)
+    n = len(thick)
+    d, v, mu = np.zeros(n), np.zeros(n), np.zeros(n)
+    ints = np.zeros(2, np.int32)
+    w = C.c_double(0)
+    rc = st(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, n, freq, c, d.ctypes.data, v.ctypes.data, mu.ctypes.data,
+            ints.ctypes.data, C.byref(w))
+    assert rc == 0
+    fn = _love_f2c.ref_love_secfun
+    fn.argtypes = [C.c_int, vpt, vpt, vpt, C.c_int, C.c_int, C.c_double, C.c_double, vpt, vpt]
+    val, imf = C.c_double(0), C.c_double(0)
+    fn(n, d.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[0]), int(ints[1]), w.value, c, C.byref(val), C.byref(imf))
+    return val.value, imf.value

@@ -175,3 +175,55 @@ void cx_prim(int op, double are, double aim, double bre, double bim, double* out
         assert a.tobytes() == b.tobytes() or (np.isnan(a).any() and np.isnan(b).any()), (op, v, a, b)
         n += 1
     assert n == 40000
+
+
+@pytest.mark.skipif(not orc.have_love_reference(), reason="oracle/_ref/liblove_f2c.so not built (needs /root/reference)")
+def test_love_secular_function_equals_the_translated_reference():
+    """The Love secular function of the R/T branch (Love.f90: EinvE_L, propup_L, SecFuns_L, with csq and T_GRT of GRT.f90) is
+    the one part of those 3 000 lines inside the reach of a mechanical translation (oracle/f90toc_love.py: complex arithmetic
+    under gcc's Fortran rules, array sections / constructors / MATMUL scalarised).  The restatement's secfun_L must equal it
+    BIT FOR BIT -- value and Imf -- over random low-velocity columns, with and without a water layer, at every frequency and
+    over the whole range of trial velocities the search scans (evanescent and propagating layers, the deep-layer cut-off of
+    startl).  The searches around it (SearchLove, C_Interval_L, bisecim) and the Rayleigh functions stay "parity unpinned"."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    n = 0
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    for _ in range(40):
+        nl = int(rng.integers(4, 14))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        k = int(rng.integers(1, nl - 1))
+        vs[k] = vs[k - 1] * rng.uniform(0.7, 0.95)                      # a low-velocity layer
+        th = np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0)
+        cols.append(crust(vs, th, water=float(rng.uniform(0.2, 3.0)) if rng.random() < 0.3 else None))
+    for th, vp, vs, rho in cols:
+        lo, hi = 0.8 * vs[vs > 0].min(), 1.05 * vs.max()
+        for f in FREQS[::2]:
+            for c in rng.uniform(lo, hi, 25):
+                rc, re, im_ = orc.grt_secfun(th, vp, vs, rho, float(f), 0, float(c), math_mode=orc.LIBM)
+                assert rc == 0
+                v, imf = orc.grt_love_secfun_reference(th, vp, vs, rho, float(f), float(c))
+                same = (np.float64(re).tobytes() == np.float64(v).tobytes() or (np.isnan(re) and np.isnan(v))) and \
+                       (np.float64(im_).tobytes() == np.float64(imf).tobytes() or (np.isnan(im_) and np.isnan(imf)))
+                assert same, (vs, th, f, c, (re, im_), (v, imf))
+                n += 1
+    assert n > 5000
+
+
+def love_fixture_points():
+    """(column, frequency, trial velocity) of the committed fixture tests/golden/grt_love_secfun_ref.npz"""
+    rng = np.random.default_rng(77)
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    cols.append(crust([3.1, 2.7, 3.5, 3.0, 4.0, 4.5], [1.0, 2.0, 2.5, 3.0, 5.0, 0.0], water=1.2))
+    for th, vp, vs, rho in cols:
+        lo, hi = 0.8 * vs[vs > 0].min(), 1.05 * vs.max()
+        for f in FREQS:
+            for c in rng.uniform(lo, hi, 12):
+                yield th, vp, vs, rho, float(f), float(c)
+
+
+def test_love_secular_function_reproduces_the_reference_fixture():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grt_love_secfun_ref.npz"))["values"]
+    got = np.array([orc.grt_secfun(th, vp, vs, rho, f, 0, c, math_mode=orc.LIBM)[1:] for th, vp, vs, rho, f, c in love_fixture_points()])
+    assert got.shape == g.shape == (4 * 11 * 12, 2)
+    assert got.tobytes() == g.tobytes(), f"{(got != g).sum()} of {g.size} values differ"
