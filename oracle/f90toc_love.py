@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's Love-wave generalized R/T secular function:
-surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) with `csq`, the parameters and the derived
-type T_GRT of surfmodes/GRT.f90.
+"""oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's generalized R/T secular functions:
+surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) and the units of surfmodes/Rayleigh.f90 a
+column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), with `csq`, the
+parameters and the derived type T_GRT of surfmodes/GRT.f90.
 
 TEST INFRASTRUCTURE, in the line of oracle/f77toc.py and oracle/f90toc.py: the sources are read where they lie, nothing is
 copied.  What this subset adds to f90toc's:
@@ -10,13 +11,16 @@ copied.  What this subset adds to f90toc's:
     exp / sqrt of a complex go to libm's cexp / csqrt as gfortran's do; AIMAG, DBLE, DCMPLX, complex literals `(re,im)`;
   * fixed-shape arrays with lower bounds at module scope (`cs(0:1)`), whole arrays and sections with constant bounds as VALUES:
     an array expression is scalarised at translation time into its element expressions (column-major) -- array constructors
-    `[a,b]`, sections `a22(:,2)`, array (op) scalar, MATMUL (k ascending, as gfortran's inline and library versions sum),
-    array-valued function results -- and an assignment evaluates every right-hand-side element into a temporary before the
+    `[a,b]`, sections `a22(:,2)` / `a44(2:3,3:4)` / `Rdu(:,:,j)` (leading extents of a rank-3 allocatable fixed by its
+    ALLOCATE), array (op) scalar or array, MATMUL (k ascending, as gfortran's inline and library versions sum), RESHAPE,
+    elementwise EXP, array-valued function results and array actual arguments (copy-in), pointers associated with a section
+    (`pp=>a44(2:3,3:4); pp=-pp`: an alias) -- and an assignment evaluates every right-hand-side element into a temporary before the
     first store (Fortran's semantics: `b22 = b22/(2.*b22(1,1))` divides by the OLD b22(1,1));
   * the derived type T_GRT as a C struct (allocatable components = pointer + extent + lower bound), passed by reference;
   * FUNCTION units (scalar or array result), SELECT CASE on an integer, DO with a negative step, USE ... ONLY / PRIVATE / PUBLIC.
 
 usage: f90toc_love.py /root/reference/surfmodes/GRT.f90 /root/reference/surfmodes/Love.f90 out.c
+       f90toc_love.py /root/reference/surfmodes/GRT.f90 /root/reference/surfmodes/Rayleigh.f90 inv2,init_rayleigh,delete_rayleigh,startl,secfunsurf,einve,propup out.c
 """
 import os
 import re
@@ -49,6 +53,7 @@ class Mod:
         self.kinds, self.params, self.scalars, self.fixed, self.alloc, self.struct = {}, {}, {}, {}, {}, {}
         self.order = []
         self.ints = {}           # integer parameters by value (array bounds)
+        self.lead = {}           # rank-3 allocatable arrays: bounds of the two leading dimensions, fixed by their ALLOCATE
         self.func_types = {}     # function name -> scalar result type, or ("arr", type, shape)
 
     def type_of(self, spec):
@@ -169,6 +174,7 @@ class UnitG(Unit):
         super().__init__(tr, kind, name, args)
         self.mod = mod
         self.pre = []            # statements to run before the one being translated (array-function calls into temporaries)
+        self.ptr = {}            # pointer name -> the array section it is associated with (an Arr of lvalues)
         self.result_shape = None
         self.case_open = []
 
@@ -218,10 +224,14 @@ class UnitG(Unit):
     def bounds(self, name):
         if name == self.name and self.result_shape:
             return [(1, n) for n in self.result_shape]
-        if name in self.dims and name not in self.args:
+        if name in self.ptr:
+            return [(1, n) for n in self.ptr[name].shape]
+        if name in self.dims:
             return [(1, self.mod.const_int(d)) for d in self.dims[name]]
         if name in self.mod.fixed and name not in self.types:
             return self.mod.fixed[name][1]
+        if name in self.mod.lead and name not in self.types:
+            return self.mod.lead[name] + [None]          # the last dimension is allocated at run time
         return None
 
     def elem(self, name, idx):
@@ -236,6 +246,8 @@ class UnitG(Unit):
         return Node("elem", self.vtype(name) if name != self.name else self.result_type, f"{cname}[{off}]", name=name, idx=None)
 
     def whole(self, name):
+        if name in self.ptr:
+            return self.ptr[name]
         b = self.bounds(name)
         shape = [hi - lo + 1 for lo, hi in b]
         elems = []
@@ -316,15 +328,19 @@ class UnitG(Unit):
                 return Node("lit", CPX, f"(({self.cast(a, R8)}) + ({self.cast(b, R8)}) * I)")
             self.pos = save
         if k == "id" and self.bounds(v) is not None:
-            self.take()
-            if self.peek()[1] != "(":
+            if self.pos + 1 >= len(self.toks) or self.toks[self.pos + 1][1] != "(":
+                if v in self.mod.lead and v not in self.ptr:
+                    return super().p_prim()               # a whole rank-3 allocatable (Rdu = 0): handled by assign
+                self.take()
                 return self.whole(v)
+            self.take()
             self.take()
             b = self.bounds(v)
             subs = []                                     # per dimension: int index expression Node, or (lo, hi) for a section
             for d in range(len(b)):
                 if self.peek()[1] == ":":
                     self.take()
+                    assert b[d] is not None, f"{v}: a section over the run-time dimension"
                     subs.append(b[d])
                 else:
                     e = self.p_or()
@@ -332,6 +348,8 @@ class UnitG(Unit):
                         self.take()
                         hi = self.p_or()
                         subs.append((int(eval(e.c)), int(eval(hi.c))))
+                    elif e.kind == "lit" and e.typ == INT:
+                        subs.append(int(e.c))
                     else:
                         subs.append(e)
                 if d + 1 < len(b):
@@ -365,10 +383,22 @@ class UnitG(Unit):
 
     def dyn_elem(self, name, subs):
         """element of a fixed-shape array with (possibly run-time) scalar subscripts"""
+        if name in self.ptr:                              # an element of the section a pointer is associated with
+            a = self.ptr[name]
+            assert all(isinstance(s, int) for s in subs), (name, subs)
+            k, stride = 0, 1
+            for n, s in zip(a.shape, subs):
+                k += (s - 1) * stride
+                stride *= n
+            return a.elems[k]
         b = self.bounds(name)
         off, stride = "0", 1
-        for (lo, hi), s in zip(b, subs):
+        for bd, s in zip(b, subs):
             i = str(s) if isinstance(s, int) else self.cast(s, INT)
+            if bd is None:                                # run-time lower bound of the last dimension
+                off += f" + (({i}) - {name}_l{len(b)}) * {stride}"
+                continue
+            lo, hi = bd
             off += f" + (({i}) - ({lo})) * {stride}"
             stride *= hi - lo + 1
         cname = name + "_result" if name == self.name else name
@@ -378,6 +408,8 @@ class UnitG(Unit):
         m = self.mod
         if name in m.alloc and name not in self.types:   # rank-1 allocatable module array
             return Node("elem", m.alloc[name][0], f"{name}[({self.cast(args[0], INT)}) - {name}_l1]", name=name, idx=None)
+        if name == "allocated":
+            return Node("call", LOG, f"({args[0].name} != 0)")
         if name == "matmul":
             a, b = args
             (n, k1), (k2, p) = a.shape, b.shape
@@ -391,6 +423,10 @@ class UnitG(Unit):
                         acc = t if acc is None else self.binop("+", acc, t)
                     elems.append(acc)
             return Arr((n, p), elems)
+        if name == "exp" and isinstance(args[0], Arr):
+            return Arr(args[0].shape, [self.call_or_index("exp", [e]) for e in args[0].elems])
+        if name == "reshape":
+            return Arr(tuple(int(e.c) for e in args[1].elems), args[0].elems)
         if name == "exp" and args[0].typ == CPX:
             return Node("call", CPX, f"cexp({args[0].c})")
         if name == "sqrt" and args[0].typ == CPX:
@@ -415,6 +451,12 @@ class UnitG(Unit):
     def actuals(self, args):
         out = []
         for a in args:
+            if isinstance(a, Arr):                        # an array value (e.g. a section): copy-in to a contiguous temporary
+                self.tmp += 1
+                t = f"arg{self.tmp}_"
+                self.pre.append(f"{CT[a.typ]} {t}[{len(a.elems)}] = {{" + ", ".join(self.cast(e, a.typ) for e in a.elems) + "};")
+                out.append(f"(void*){t}")
+                continue
             if a.kind == "var" and self.types.get(a.name) == TGRT:
                 out.append(f"(void*){a.name}")
             elif a.kind == "var" and a.name not in self.params:
@@ -450,12 +492,19 @@ class UnitG(Unit):
         if ln.kind == "var" and ln.name in self.mod.alloc and ln.name not in self.types:   # RduL = 0
             a = ln.name
             t = self.vtype(a)
-            self.emit(f"for (int i_ = 0; i_ < {a}_d1; ++i_) {a}[i_] = {self.cast(rn, t)};")
+            rank = self.mod.alloc[a][1]
+            n = f"{a}_d1" if rank == 1 else f"4 * {a}_d3"
+            self.emit(f"for (int i_ = 0; i_ < {n}; ++i_) {a}[i_] = {self.cast(rn, t)};")
             return
         self.emit(f"{ln.c} = {self.cast(rn, ln.typ)};")
 
     def statement(self, text, ln):
         t = text
+        m = re.fullmatch(r"([a-z][a-z0-9_]*)=>(.*)", t)
+        if m:                                             # pointer association with a section: an alias from here on
+            self.ptr.pop(m.group(1), None)
+            self.ptr[m.group(1)] = self.parse(m.group(2))
+            return
         m = re.fullmatch(r"selectcase\((.*)\)", t)
         if m:
             self.emit(f"switch ({self.expr_c(m.group(1), INT)}) {{")
@@ -476,11 +525,16 @@ class UnitG(Unit):
         if m:
             for item in self.split_top(m.group(1)):
                 m2 = re.fullmatch(r"([a-z][a-z0-9_]*)\((.*)\)", item)
-                name, sp = m2.group(1), m2.group(2)
-                lo, hi = sp.split(":") if ":" in sp else ("1", sp)
+                name, sps = m2.group(1), self.split_top(m2.group(2))
+                lead = 1
+                if len(sps) == 3:                         # (2,2,lo:hi): the leading extents are constants
+                    self.mod.lead[name] = [(1, self.mod.const_int(sps[0])), (1, self.mod.const_int(sps[1]))]
+                    lead = self.mod.const_int(sps[0]) * self.mod.const_int(sps[1])
+                k = len(sps)
+                lo, hi = sps[-1].split(":") if ":" in sps[-1] else ("1", sps[-1])
                 ct = CT[self.vtype(name)]
-                self.emit(f"{name}_l1 = {self.expr_c(lo, INT)}; {name}_d1 = ({self.expr_c(hi, INT)}) - {name}_l1 + 1;")
-                self.emit(f"{name} = ({ct}*)calloc((size_t)({name}_d1 > 0 ? {name}_d1 : 0) + 8, sizeof({ct}));")
+                self.emit(f"{name}_l{k} = {self.expr_c(lo, INT)}; {name}_d{k} = ({self.expr_c(hi, INT)}) - {name}_l{k} + 1;")
+                self.emit(f"{name} = ({ct}*)calloc((size_t)({lead} * ({name}_d{k} > 0 ? {name}_d{k} : 0)) + 8, sizeof({ct}));")
             return
         m = re.fullmatch(r"deallocate\((.*)\)", t)
         if m:
@@ -606,18 +660,30 @@ class TranslatorG:
         return "\n".join(o)
 
 
+def read(path):
+    """free-form statements, `;` separators split (no character data in these files' executable statements)"""
+    out = []
+    for text, ln in G.read_free_form(path):
+        for part in text.split(";"):
+            if part:
+                out.append((part, ln))
+    return out
+
+
 def main():
-    grt, love, out = sys.argv[1], sys.argv[2], sys.argv[3]
+    grt, src, out = sys.argv[1], sys.argv[2], sys.argv[-1]
+    only = set(sys.argv[3].split(",")) if len(sys.argv) > 4 else None    # units of the second file to translate (default: all)
     mod = Mod()
     tr = TranslatorG(mod)
-    s1 = G.read_free_form(grt)
+    s1 = read(grt)
     k1 = mod.read_header(s1)
     tr.scan_functions(s1)
     tr.run(s1, k1, only={"csq"})
-    s2 = G.read_free_form(love)
+    s2 = read(src)
     k2 = mod.read_header(s2)
     tr.scan_functions(s2)
-    tr.run(s2, k2)
+    tr.run(s2, k2, only=only)
+    love = src
     open(out, "w").write(tr.c_source([grt, love]))
     print(f"f90toc_love: {len(tr.units)} program units ({', '.join(u.name for u in tr.units)})")
 

@@ -10,8 +10,9 @@
  * Only what `surfmodes` reaches is restated (allmodes = 0: the fundamental / Stoneley mode per frequency);
  * `surfmmodes` prints "not supported yet" for such columns (surfmodes.f90:153,165).
  *
- * PARITY STATUS: "parity unpinned" except the Love secular function (secfun_L / einve_L: bit-identical to surfmodes/Love.f90
- * translated mechanically by oracle/f90toc_love.py -- tests/test_oracle_grt.py).  The reference ships no test, golden value or compiled object for these files and
+ * PARITY STATUS: "parity unpinned" except the secular functions secfun_L (Love.f90) and secfun_surf with startl (Rayleigh.f90,
+ * columns without water): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
+ * (tests/test_oracle_grt.py).  The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent
  * 50-digit propagator-matrix secular function and are the lowest mode) and by line-by-line reading; the complex
@@ -743,17 +744,18 @@ int orc_grt_modes(const double* thick, const double* vp, const double* vs, const
   return ierr;
 }
 
-/* test hook: what setup_grt + startl leave in the T_GRT of a Love column at phase velocity c -- the inputs of SecFuns_L, for
- * the comparison with the mechanical translation of Love.f90 (oracle/f90toc_love.py).  d / vs / mu: n values; ints = {ifs, ll}. */
-int orc_grt_love_state(const double* thick, const double* vp, const double* vs, const double* rho, int n, double freq, double c,
-                       double* d_out, double* vs_out, double* mu_out, int* ints, double* w_out) {
+/* test hook: what setup_grt + startl leave in the T_GRT of a column at phase velocity c -- the inputs of SecFuns_L / SecFunSurf,
+ * for the comparison with the mechanical translations of Love.f90 and Rayleigh.f90 (oracle/f90toc_love.py).
+ * d / vp / vs / mu: n values; ints = {ifs, ll, lvlast}. */
+int orc_grt_state(const double* thick, const double* vp, const double* vs, const double* rho, int n, double freq, int modetype, double c,
+                  double* d_out, double* vp_out, double* vs_out, double* mu_out, int* ints, double* w_out) {
   grt_t* G = (grt_t*)calloc(1, sizeof(grt_t));
   G->math_mode = 0;
-  if (setup_grt(G, thick, vp, vs, rho, n, 0, 1e-3, 1e-3, 1e-3) < 0) { free(G); return -1; }
+  if (setup_grt(G, thick, vp, vs, rho, n, modetype, 1e-3, 1e-3, 1e-3) < 0) { free(G); return -1; }
   G->w = freq * 2 * (double)3.1415926f;
   startl(G, c);
-  for (int j = 1; j <= n; ++j) { d_out[j - 1] = G->d[j]; vs_out[j - 1] = G->vs[j]; mu_out[j - 1] = G->mu[j]; }
-  ints[0] = G->ifs; ints[1] = G->ll;
+  for (int j = 1; j <= n; ++j) { d_out[j - 1] = G->d[j]; vp_out[j - 1] = G->vp[j]; vs_out[j - 1] = G->vs[j]; mu_out[j - 1] = G->mu[j]; }
+  ints[0] = G->ifs; ints[1] = G->ll; ints[2] = G->lvlast;
   *w_out = G->w;
   free(G);
   return 0;

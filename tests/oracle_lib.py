@@ -540,6 +540,21 @@ def have_love_reference():
     return os.path.exists(LOVE_F2C_LIB)
 
 
+def _grt_state(thick, vp, vs, rho, freq, modetype, c):
+    vpt = C.c_void_p
+    st = L().orc_grt_state
+    st.argtypes = [vpt] * 4 + [C.c_int, C.c_double, C.c_int, C.c_double] + [vpt] * 6
+    thick, vp, vs, rho = f64(thick), f64(vp), f64(vs), f64(rho)
+    n = len(thick)
+    d, p, v, mu = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    ints = np.zeros(3, np.int32)
+    w = C.c_double(0)
+    rc = st(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, n, freq, modetype, c, d.ctypes.data, p.ctypes.data,
+            v.ctypes.data, mu.ctypes.data, ints.ctypes.data, C.byref(w))
+    assert rc == 0
+    return n, d, p, v, mu, ints, w.value
+
+
 def grt_love_secfun_reference(thick, vp, vs, rho, freq, c):
     """SecFuns_L(1 + ifs, c, GRT, Imf) of the TRANSLATED Love.f90 on the T_GRT that the restatement's setup_grt + startl build
     for this column (the search logic and the set-up stay the restatement's).  Returns (value, imf)."""
@@ -547,18 +562,33 @@ def grt_love_secfun_reference(thick, vp, vs, rho, freq, c):
     if _love_f2c is None:
         _love_f2c = C.CDLL(LOVE_F2C_LIB)
     vpt = C.c_void_p
-    st = L().orc_grt_love_state
-    st.argtypes = [vpt] * 4 + [C.c_int, C.c_double, C.c_double, vpt, vpt, vpt, vpt, vpt]
-    thick, vp, vs, rho = f64(thick), f64(vp), f64(vs), f64(rho)
-    n = len(thick)
-    d, v, mu = np.zeros(n), np.zeros(n), np.zeros(n)
-    ints = np.zeros(2, np.int32)
-    w = C.c_double(0)
-    rc = st(thick.ctypes.data, vp.ctypes.data, vs.ctypes.data, rho.ctypes.data, n, freq, c, d.ctypes.data, v.ctypes.data, mu.ctypes.data,
-            ints.ctypes.data, C.byref(w))
-    assert rc == 0
+    n, d, p, v, mu, ints, w = _grt_state(thick, vp, vs, rho, freq, 0, c)
     fn = _love_f2c.ref_love_secfun
     fn.argtypes = [C.c_int, vpt, vpt, vpt, C.c_int, C.c_int, C.c_double, C.c_double, vpt, vpt]
     val, imf = C.c_double(0), C.c_double(0)
-    fn(n, d.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[0]), int(ints[1]), w.value, c, C.byref(val), C.byref(imf))
+    fn(n, d.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[0]), int(ints[1]), w, c, C.byref(val), C.byref(imf))
     return val.value, imf.value
+
+
+RAYLEIGH_F2C_LIB = os.path.join(ORACLE_DIR, "_ref", "librayleigh_f2c.so")
+_rayleigh_f2c = None
+
+
+def have_rayleigh_reference():
+    return os.path.exists(RAYLEIGH_F2C_LIB)
+
+
+def grt_rayleigh_secfun_reference(thick, vp, vs, rho, freq, c):
+    """startl + SecFunSurf(0, c, GRT, Imf) of the TRANSLATED Rayleigh.f90 (columns without water: ifs = 0) on the T_GRT that the
+    restatement's setup_grt builds.  Returns (value, imf, ll chosen by the translated startl, ll of the restatement)."""
+    global _rayleigh_f2c
+    if _rayleigh_f2c is None:
+        _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
+    vpt = C.c_void_p
+    n, d, p, v, mu, ints, w = _grt_state(thick, vp, vs, rho, freq, 1, c)
+    assert ints[0] == 0, "a water layer: SecFunSt, not SecFunSurf"
+    fn = _rayleigh_f2c.ref_rayleigh_secfunsurf
+    fn.argtypes = [C.c_int, vpt, vpt, vpt, vpt, C.c_int, C.c_double, C.c_double, vpt, vpt, vpt]
+    val, imf, ll = C.c_double(0), C.c_double(0), C.c_int(0)
+    fn(n, d.ctypes.data, p.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[2]), w, c, C.byref(val), C.byref(imf), C.byref(ll))
+    return val.value, imf.value, ll.value, int(ints[1])
