@@ -19,8 +19,8 @@ copied.  What this subset adds to f90toc's:
   * the derived type T_GRT as a C struct (allocatable components = pointer + extent + lower bound), passed by reference;
   * FUNCTION units (scalar or array result), SELECT CASE on an integer, DO with a negative step, USE ... ONLY / PRIVATE / PUBLIC.
 
-usage: f90toc_love.py /root/reference/surfmodes/GRT.f90 /root/reference/surfmodes/Love.f90 out.c
-       f90toc_love.py /root/reference/surfmodes/GRT.f90 /root/reference/surfmodes/Rayleigh.f90 inv2,init_rayleigh,delete_rayleigh,startl,secfunsurf,einve,propup out.c
+usage: f90toc_love.py GRT.f90 Love.f90 util.f90:bisecim out.c
+       f90toc_love.py GRT.f90 Rayleigh.f90:inv2,init_rayleigh,delete_rayleigh,startl,secfunsurf,einve,propup util.f90:bisecim out.c
 """
 import os
 import re
@@ -410,6 +410,10 @@ class UnitG(Unit):
             return Node("elem", m.alloc[name][0], f"{name}[({self.cast(args[0], INT)}) - {name}_l1]", name=name, idx=None)
         if name == "allocated":
             return Node("call", LOG, f"({args[0].name} != 0)")
+        if name == "merge":
+            a, b, c = args
+            t = max(a.typ, b.typ)
+            return Node("call", t, f"(({c.c}) ? ({self.cast(a, t)}) : ({self.cast(b, t)}))")
         if name == "matmul":
             a, b = args
             (n, k1), (k2, p) = a.shape, b.shape
@@ -505,6 +509,14 @@ class UnitG(Unit):
             self.ptr.pop(m.group(1), None)
             self.ptr[m.group(1)] = self.parse(m.group(2))
             return
+        if t == "do":                                     # DO without a control: left by EXIT / RETURN
+            self.emit("for (;;) {")
+            self.do_stack.append(("while", None, None))
+            return
+        if t == "enddo" and self.do_stack and self.do_stack[-1][0] == "while":
+            self.do_stack.pop()
+            self.emit("}")
+            return
         m = re.fullmatch(r"selectcase\((.*)\)", t)
         if m:
             self.emit(f"switch ({self.expr_c(m.group(1), INT)}) {{")
@@ -560,6 +572,7 @@ class TranslatorG:
         self.mod = mod
         self.units = []
         self.called = set()
+        self.externs = {}        # dummy procedures (REAL*8, EXTERNAL :: f): name -> result type
 
     def scan_functions(self, stmts):
         """result types of the FUNCTION units (needed before their callers are translated)"""
@@ -589,8 +602,8 @@ class TranslatorG:
             if u is None:
                 m = re.fullmatch(r"(?:(?:real\*8|complex\*16|real\(kind=[a-z0-9_]+\)))?(subroutine|function)([a-z][a-z0-9_]*)(?:\((.*)\))?", text)
                 if not m:
-                    if re.fullmatch(r"endmodule[a-z0-9_]*", text):
-                        continue
+                    if re.fullmatch(r"endmodule[a-z0-9_]*", text) or only is not None:
+                        continue                          # (with a selection, statements of unselected units in other forms)
                     raise SyntaxError(f"line {ln}: {text!r} outside a unit")
                 if only is not None and m.group(2) not in only:
                     skipping = True
@@ -613,13 +626,20 @@ class TranslatorG:
             if in_spec:
                 if text == "implicitnone":
                     continue
+                if re.fullmatch(r"use[a-z0-9_,:]+", text):
+                    continue
                 d = self.mod.declare(text)
                 if d is not None:
                     for name, typ, dims, init, is_par in d:
                         if name == u.name:
                             continue                      # the function result: known from scan_functions
                         u.types[name] = typ
-                        if dims:
+                        if is_par:
+                            u.params[name] = None
+                            u.params[name] = u.cast(u.parse(init), typ)
+                        elif "external" in text.split("::")[0]:
+                            self.externs[name] = typ      # a dummy procedure: the driver supplies name_
+                        elif dims:
                             u.dims[name] = dims
                         elif name not in u.args:
                             u.locals[name] = typ
@@ -642,6 +662,8 @@ class TranslatorG:
                 ps.append(f"{CT[u.result_type]}* {u.name}_result")
             ret = "void" if u.kind == "subroutine" or u.result_shape else CT[u.result_type]
             return f"static {ret} {u.name}_({', '.join(ps) or 'void'})"
+        for name, t in self.externs.items():
+            o.append(f"static {CT[t]} {name}_(void*, void*, void*, void*); /* the driver's */")
         for u in self.units:
             o.append(proto(u) + ";")
         o.append("")
@@ -651,8 +673,14 @@ class TranslatorG:
                 o.append(f"  {CT[u.vtype(a)]}* {a} = ({CT[u.vtype(a)]}*){a}_a;")
             if u.kind == "function" and not u.result_shape:
                 o.append(f"  {CT[u.result_type]} {u.name}_result = 0;")
-            for name, typ in sorted(u.locals.items()):
+            for k, v in u.params.items():
+                o.append(f"  const {CT[u.types[k]]} {k.upper()} = {v};")
+            for name, dims in u.dims.items():
                 if name not in u.args and name != u.name:
+                    n = " * ".join(str(self.mod.const_int(d)) for d in dims)
+                    o.append(f"  {CT[u.vtype(name)]} {name}[{n}];")
+            for name, typ in sorted(u.locals.items()):
+                if name not in u.args and name != u.name and name not in self.externs:
                     o.append(f"  {CT[typ]} {name} = 0;")
             o.extend("  " + s for s in u.body)
             o.append("}")
@@ -671,20 +699,21 @@ def read(path):
 
 
 def main():
-    grt, src, out = sys.argv[1], sys.argv[2], sys.argv[-1]
-    only = set(sys.argv[3].split(",")) if len(sys.argv) > 4 else None    # units of the second file to translate (default: all)
+    """f90toc_love.py GRT.f90 file[:unit,unit,...] [file[:units] ...] out.c"""
+    grt, out = sys.argv[1], sys.argv[-1]
     mod = Mod()
     tr = TranslatorG(mod)
     s1 = read(grt)
     k1 = mod.read_header(s1)
     tr.scan_functions(s1)
     tr.run(s1, k1, only={"csq"})
-    s2 = read(src)
-    k2 = mod.read_header(s2)
-    tr.scan_functions(s2)
-    tr.run(s2, k2, only=only)
-    love = src
-    open(out, "w").write(tr.c_source([grt, love]))
+    for spec in sys.argv[2:-1]:
+        path, _, units = spec.partition(":")
+        st = read(path)
+        k = mod.read_header(st) if st[0][0].startswith("module") else 0
+        tr.scan_functions(st)
+        tr.run(st, k, only=set(units.split(",")) if units else None)
+    open(out, "w").write(tr.c_source([grt] + sys.argv[2:-1]))
     print(f"f90toc_love: {len(tr.units)} program units ({', '.join(u.name for u in tr.units)})")
 
 

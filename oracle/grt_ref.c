@@ -11,7 +11,7 @@
  * `surfmmodes` prints "not supported yet" for such columns (surfmodes.f90:153,165).
  *
  * PARITY STATUS: "parity unpinned" except the secular functions secfun_L (Love.f90) and secfun_surf with startl (Rayleigh.f90,
- * columns without water): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
+ * columns without water) and the root refinement bisecim (util.f90): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
  * (tests/test_oracle_grt.py).  The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent
@@ -759,6 +759,27 @@ int orc_grt_state(const double* thick, const double* vp, const double* vs, const
   *w_out = G->w;
   free(G);
   return 0;
+}
+
+/* test hook: one root refinement as the searches issue it -- startl at the upper end k2 of a bracket, the secular function at
+ * both ends, bisecim in between (util.f90:90-167) -- for the comparison with the mechanical translation of bisecim driving the
+ * translated secular functions.  out = {root, f1, f2}; returns iq, or -2 when setup fails. */
+int orc_grt_bisecim(const double* thick, const double* vp, const double* vs, const double* rho, int n, double freq, int modetype,
+                    double k1, double k2, double smin, double tol, double* out) {
+  grt_t* G = (grt_t*)calloc(1, sizeof(grt_t));
+  G->math_mode = 0;
+  if (setup_grt(G, thick, vp, vs, rho, n, modetype, 1e-3, 1e-3, 1e-3) < 0) { free(G); return -2; }
+  G->w = freq * 2 * (double)3.1415926f;
+  G->smin = smin; G->tol = tol;
+  secf f = modetype == 0 ? secfun_L : (G->ifs == 0 ? secfun_surf : secfun_st);
+  double imf = 0;
+  startl(G, k2);
+  const double f1 = f(G, k1, &imf), f2 = f(G, k2, &imf);
+  int iq = -1;
+  out[0] = bisecim(G, f, k1, k2, f1, f2, &iq);
+  out[1] = f1; out[2] = f2;
+  free(G);
+  return iq;
 }
 
 /* test hook: the secular function itself (modetype 1: SecFunSurf / SecFunSt, 0: SecFuns_L) at phase velocity c */

@@ -6,6 +6,9 @@
 #include RAYLEIGH_F2C_SOURCE
 #include <string.h>
 
+/* the dummy procedure of bisecim: SearchRayleigh passes SecFunSurf for a column without water (SearchRayleigh.f90 FundaMode) */
+static double f_(void* ilay, void* c, void* grt, void* imf) { return secfunsurf_(ilay, c, grt, imf); }
+
 int ref_rayleigh_secfunsurf(int n, const double* d, const double* vp, const double* vs, const double* mu, int lvlast, double w, double c,
                             double* value, double* imf, int* ll_out) {
   T_GRT g;
@@ -23,4 +26,26 @@ int ref_rayleigh_secfunsurf(int n, const double* d, const double* vp, const doub
   *value = secfunsurf_(&isurf, &c, &g, imf);
   delete_rayleigh_();
   return 0;
+}
+
+/* one root refinement as FundaMode issues it: startl at k2, SecFunSurf at both ends, bisecim.  out = {root, f1, f2}; returns iq */
+int ref_rayleigh_bisecim(int n, const double* d, const double* vp, const double* vs, const double* mu, int lvlast, double w, double k1,
+                         double k2, double smin, double tol, double* out) {
+  T_GRT g;
+  memset(&g, 0, sizeof g);
+  g.nlayers = n;
+  g.d = (double*)d; g.d_d1 = n; g.d_l1 = 1;
+  g.vp = (double*)vp; g.vp_d1 = n; g.vp_l1 = 1;
+  g.vs = (double*)vs; g.vs_d1 = n; g.vs_l1 = 1;
+  g.mu = (double*)mu; g.mu_d1 = n; g.mu_l1 = 1;
+  g.ifs = 0; g.lvlast = lvlast; g.w = w; g.smin = smin; g.tol = tol;
+  int isurf = 0, iq = -1;
+  double imf = 0;
+  init_rayleigh_(&n);
+  startl_(&k2, &g);
+  double f1 = secfunsurf_(&isurf, &k1, &g, &imf), f2 = secfunsurf_(&isurf, &k2, &g, &imf);
+  out[0] = bisecim_(0, &isurf, &k1, &k2, &f1, &f2, &g, &iq);
+  out[1] = f1; out[2] = f2;
+  delete_rayleigh_();
+  return iq;
 }

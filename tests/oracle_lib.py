@@ -592,3 +592,32 @@ def grt_rayleigh_secfun_reference(thick, vp, vs, rho, freq, c):
     val, imf, ll = C.c_double(0), C.c_double(0), C.c_int(0)
     fn(n, d.ctypes.data, p.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[2]), w, c, C.byref(val), C.byref(imf), C.byref(ll))
     return val.value, imf.value, ll.value, int(ints[1])
+
+
+def grt_bisecim(impl, thick, vp, vs, rho, freq, modetype, k1, k2, smin=1e-4, tol=1e-6):
+    """One root refinement as the searches issue it (startl at k2, the secular function at both ends, bisecim).  impl "port": the
+    restatement; "reference": bisecim of util.f90 driving SecFunSurf / SecFuns_L, all translated.  Returns (iq, root, f1, f2)."""
+    vpt = C.c_void_p
+    out = np.zeros(3)
+    if impl == "port":
+        fn = L().orc_grt_bisecim
+        fn.argtypes = [vpt] * 4 + [C.c_int, C.c_double, C.c_int] + [C.c_double] * 4 + [vpt]
+        a = [f64(x) for x in (thick, vp, vs, rho)]
+        iq = fn(*[x.ctypes.data for x in a], len(a[0]), freq, modetype, k1, k2, smin, tol, out.ctypes.data)
+        return iq, out[0], out[1], out[2]
+    n, d, p, v, mu, ints, w = _grt_state(thick, vp, vs, rho, freq, modetype, k2)
+    global _love_f2c, _rayleigh_f2c
+    if modetype == 0:
+        if _love_f2c is None:
+            _love_f2c = C.CDLL(LOVE_F2C_LIB)
+        fn = _love_f2c.ref_love_bisecim
+        fn.argtypes = [C.c_int, vpt, vpt, vpt, C.c_int, C.c_int] + [C.c_double] * 5 + [vpt]
+        iq = fn(n, d.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[0]), int(ints[1]), w, k1, k2, smin, tol, out.ctypes.data)
+    else:
+        assert ints[0] == 0
+        if _rayleigh_f2c is None:
+            _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
+        fn = _rayleigh_f2c.ref_rayleigh_bisecim
+        fn.argtypes = [C.c_int, vpt, vpt, vpt, vpt, C.c_int] + [C.c_double] * 5 + [vpt]
+        iq = fn(n, d.ctypes.data, p.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[2]), w, k1, k2, smin, tol, out.ctypes.data)
+    return iq, out[0], out[1], out[2]

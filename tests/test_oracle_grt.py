@@ -285,3 +285,34 @@ def test_rayleigh_surface_secular_function_reproduces_the_reference_fixture():
     got = np.array([orc.grt_secfun(th, vp, vs, rho, f, 1, c, math_mode=orc.LIBM)[1:] for th, vp, vs, rho, f, c in rayleigh_fixture_points()])
     assert got.shape == g.shape == (4 * 11 * 12, 2)
     assert all(_bits_equal(a, b) for a, b in zip(got.ravel(), g.ravel())), f"{(got != g).sum()} of {g.size} values differ"
+
+
+@pytest.mark.skipif(not (orc.have_rayleigh_reference() and orc.have_love_reference()), reason="oracle/_ref translations not built (needs /root/reference)")
+@pytest.mark.parametrize("modetype", [1, 0])
+def test_root_refinement_equals_the_translated_reference(modetype):
+    """bisecim (util.f90:90-167: bisection whose inverse-interpolation estimate enters the stopping test and the final choice)
+    as the reference's own statements, driving the reference's own secular functions, against the restatement's -- the same
+    brackets a scan would hand over (neighbouring trial velocities with a sign change), the same smin / tol range the callers
+    set.  Root, iq, and the end values: bit for bit."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    for _ in range(12):
+        nl = int(rng.integers(4, 12))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        k = int(rng.integers(1, nl - 1))
+        vs[k] = vs[k - 1] * rng.uniform(0.7, 0.95)
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0)))
+    n = found = rejected = 0
+    for th, vp, vs, rho in cols:
+        for f in FREQS[1::3]:
+            grid = np.linspace(0.8 * vs.min(), 0.999 * vs.max(), 60)
+            vals = np.array([orc.grt_secfun(th, vp, vs, rho, float(f), modetype, float(c), math_mode=orc.LIBM)[1] for c in grid])
+            for i in np.nonzero(vals[:-1] * vals[1:] < 0)[0][:4]:
+                smin, tol = float(10.0 ** rng.uniform(-5, -2)), float(10.0 ** rng.uniform(-7, -4))
+                a = orc.grt_bisecim("port", th, vp, vs, rho, float(f), modetype, float(grid[i]), float(grid[i + 1]), smin, tol)
+                b = orc.grt_bisecim("reference", th, vp, vs, rho, float(f), modetype, float(grid[i]), float(grid[i + 1]), smin, tol)
+                assert a[0] == b[0] and all(_bits_equal(x, y) for x, y in zip(a[1:], b[1:])), (vs, f, grid[i], a, b)
+                n += 1
+                found += int(a[0] == 0)
+                rejected += int(a[0] == -1)
+    assert n > 100 and found > 50, (n, found, rejected)
