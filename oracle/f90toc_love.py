@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's generalized R/T secular functions:
 surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) and the units of surfmodes/Rayleigh.f90 a
-column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), with `csq`, the
+column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), bisecim and sort
+of util.f90, C_Interval / N_cf (C_interval.f90) and C_Interval_L / N_cf_L (C_interval_L.f90), with `csq`, the
 parameters and the derived type T_GRT of surfmodes/GRT.f90.
 
 TEST INFRASTRUCTURE, in the line of oracle/f77toc.py and oracle/f90toc.py: the sources are read where they lie, nothing is
@@ -17,7 +18,9 @@ copied.  What this subset adds to f90toc's:
     (`pp=>a44(2:3,3:4); pp=-pp`: an alias) -- and an assignment evaluates every right-hand-side element into a temporary before the
     first store (Fortran's semantics: `b22 = b22/(2.*b22(1,1))` divides by the OLD b22(1,1));
   * the derived type T_GRT as a C struct (allocatable components = pointer + extent + lower bound), passed by reference;
-  * FUNCTION units (scalar or array result), SELECT CASE on an integer, DO with a negative step, USE ... ONLY / PRIVATE / PUBLIC.
+  * FUNCTION units (scalar or array result), dummy procedures (bound to a routine of the driver), SELECT CASE on an integer, DO
+    with a negative step, DO without a control, DO WHILE, CYCLE, MERGE, 1-D sections with run-time bounds copied through a
+    temporary (`vvv(2:index0)=vvv(i:ii)`), whole work arrays passed by reference, USE ... ONLY / PRIVATE / PUBLIC.
 
 usage: f90toc_love.py GRT.f90 Love.f90 util.f90:bisecim out.c
        f90toc_love.py GRT.f90 Rayleigh.f90:inv2,init_rayleigh,delete_rayleigh,startl,secfunsurf,einve,propup util.f90:bisecim out.c
@@ -227,7 +230,10 @@ class UnitG(Unit):
         if name in self.ptr:
             return [(1, n) for n in self.ptr[name].shape]
         if name in self.dims:
-            return [(1, self.mod.const_int(d)) for d in self.dims[name]]
+            try:
+                return [(1, self.mod.const_int(d)) for d in self.dims[name]]
+            except Exception:
+                return None                               # a dummy array with run-time extents: plain element references only
         if name in self.mod.fixed and name not in self.types:
             return self.mod.fixed[name][1]
         if name in self.mod.lead and name not in self.types:
@@ -260,9 +266,15 @@ class UnitG(Unit):
                 rec(k - 1, [i] + idx) if False else None
         # column-major: first index fastest
         import itertools
+        if shape and max(shape) > 64:                     # a work array passed whole (call sort(vvv,...)): by reference, never scalarised
+            a = Arr([1], [Node("lit", self.vtype(name), "0")])
+            a.shape, a.whole_name = tuple(shape), name
+            return a
         for idx in itertools.product(*[range(lo, hi + 1) for lo, hi in reversed(b)]):
             elems.append(self.elem(name, list(reversed(idx))))
-        return Arr(shape, elems)
+        a = Arr(shape, elems)
+        a.whole_name = name
+        return a
 
     # ---- expression parser extensions
     def binop(self, op, a, b):
@@ -410,6 +422,10 @@ class UnitG(Unit):
             return Node("elem", m.alloc[name][0], f"{name}[({self.cast(args[0], INT)}) - {name}_l1]", name=name, idx=None)
         if name == "allocated":
             return Node("call", LOG, f"({args[0].name} != 0)")
+        if name == "floor":
+            return Node("call", INT, f"((int)floor({self.cast(args[0], R8)}))")
+        if name == "nint":
+            return Node("call", INT, f"((int)lround({self.cast(args[0], R8)}))")
         if name == "merge":
             a, b, c = args
             t = max(a.typ, b.typ)
@@ -455,6 +471,9 @@ class UnitG(Unit):
     def actuals(self, args):
         out = []
         for a in args:
+            if isinstance(a, Arr) and getattr(a, "whole_name", None) and a.whole_name not in self.ptr:
+                out.append(f"(void*){a.whole_name + '_result' if a.whole_name == self.name else a.whole_name}")   # a whole array: by reference
+                continue
             if isinstance(a, Arr):                        # an array value (e.g. a section): copy-in to a contiguous temporary
                 self.tmp += 1
                 t = f"arg{self.tmp}_"
@@ -509,6 +528,26 @@ class UnitG(Unit):
             self.ptr.pop(m.group(1), None)
             self.ptr[m.group(1)] = self.parse(m.group(2))
             return
+        m = re.fullmatch(r"dowhile\((.*)\)", t)
+        if m:
+            self.emit(f"while ({self.parse(m.group(1)).c}) {{")
+            self.do_stack.append(("while", None, None))
+            return
+        if t == "cycle":
+            self.emit("continue;")
+            return
+        m = re.fullmatch(r"([a-z][a-z0-9_]*)\(([^():,]+):([^():,]+)\)=([a-z][a-z0-9_]*)\(([^():,]+):([^():,]+)\)", t)
+        if m and self.bounds(m.group(1)) is not None and len(self.bounds(m.group(1))) == 1:
+            # a(l1:u1) = b(l2:u2) with run-time bounds (possibly overlapping): the right-hand side is taken first
+            a, l1, u1, b, l2, u2 = m.groups()
+            ct = CT[self.vtype(a)]
+            lo_a, lo_b = self.bounds(a)[0][0], self.bounds(b)[0][0]
+            self.emit(f"{{ int l1_ = {self.expr_c(l1, INT)}, n_ = ({self.expr_c(u1, INT)}) - l1_ + 1, l2_ = {self.expr_c(l2, INT)};")
+            self.emit(f"  {ct}* t_ = ({ct}*)malloc(sizeof({ct}) * (size_t)(n_ > 0 ? n_ : 1));")
+            self.emit(f"  for (int k_ = 0; k_ < n_; ++k_) t_[k_] = {b}[l2_ - ({lo_b}) + k_];")
+            self.emit(f"  for (int k_ = 0; k_ < n_; ++k_) {a}[l1_ - ({lo_a}) + k_] = t_[k_];")
+            self.emit("  free(t_); }")
+            return
         if t == "do":                                     # DO without a control: left by EXIT / RETURN
             self.emit("for (;;) {")
             self.do_stack.append(("while", None, None))
@@ -556,10 +595,11 @@ class UnitG(Unit):
         m = re.fullmatch(r"call([a-z][a-z0-9_]*)\((.*)\)", t)
         if m:
             args = [self.parse(a) for a in self.split_top(m.group(2))]
+            act = self.actuals(args)
             for p in self.pre:
                 self.emit(p)
             self.pre = []
-            self.emit(f"{m.group(1)}_({self.actuals(args)});")
+            self.emit(f"{m.group(1)}_({act});")
             return
         m = re.fullmatch(r"if\((.*)\)then", t)
         if m and "==" in m.group(1):                      # (the == operator is in the base REL table; nothing special)
@@ -663,7 +703,8 @@ class TranslatorG:
             ret = "void" if u.kind == "subroutine" or u.result_shape else CT[u.result_type]
             return f"static {ret} {u.name}_({', '.join(ps) or 'void'})"
         for name, t in self.externs.items():
-            o.append(f"static {CT[t]} {name}_(void*, void*, void*, void*); /* the driver's */")
+            if name not in [u.name for u in self.units]:
+                o.append(f"static {CT[t]} {name}_(void*, void*, void*, void*); /* the driver's */")
         for u in self.units:
             o.append(proto(u) + ";")
         o.append("")

@@ -11,7 +11,8 @@
  * `surfmmodes` prints "not supported yet" for such columns (surfmodes.f90:153,165).
  *
  * PARITY STATUS: "parity unpinned" except the secular functions secfun_L (Love.f90) and secfun_surf with startl (Rayleigh.f90,
- * columns without water) and the root refinement bisecim (util.f90): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
+ * columns without water), the root refinement bisecim (util.f90) and the trial-velocity lists (C_Interval, C_Interval_L, N_cf,
+ * N_cf_L, sort): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
  * (tests/test_oracle_grt.py).  The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent
@@ -780,6 +781,27 @@ int orc_grt_bisecim(const double* thick, const double* vp, const double* vs, con
   out[1] = f1; out[2] = f2;
   free(G);
   return iq;
+}
+
+/* test hooks: the trial phase velocities of a frequency (C_Interval / C_Interval_L with N_cf / N_cf_L and sort) and the rest of
+ * the T_GRT they read.  ccc_out: 20000 doubles; v_out: 2n doubles; extra = {vsy, vsm, vs1}; counts = {ncc, im1, nv, overflow}. */
+int orc_grt_cinterval(const double* thick, const double* vp, const double* vs, const double* rho, int n, double freq, int modetype,
+                      double tol, double* ccc_out, double* v_out, double* extra, int* counts) {
+  grt_t* G = (grt_t*)calloc(1, sizeof(grt_t));
+  G->math_mode = 0;
+  if (setup_grt(G, thick, vp, vs, rho, n, modetype, 1e-3, 1e-3, 1e-3) < 0) { free(G); return -1; }
+  G->w = freq * 2 * (double)3.1415926f;
+  G->tol = tol;
+  G->vvv = (double*)calloc(GNV + 8, sizeof(double));
+  G->ccc = (double*)calloc(GNV + 8, sizeof(double));
+  int ncc = 0, im1 = 0;
+  c_interval(G, modetype == 0, &ncc, &im1);
+  for (int i = 1; i <= ncc && i <= GNV; ++i) ccc_out[i - 1] = G->ccc[i];
+  for (int i = 1; i <= G->nv; ++i) v_out[i - 1] = G->v[i];
+  extra[0] = G->vsy; extra[1] = G->vsm; extra[2] = G->vs1;
+  counts[0] = ncc; counts[1] = im1; counts[2] = G->nv; counts[3] = G->overflow;
+  free(G->vvv); free(G->ccc); free(G);
+  return 0;
 }
 
 /* test hook: the secular function itself (modetype 1: SecFunSurf / SecFunSt, 0: SecFuns_L) at phase velocity c */

@@ -43,3 +43,24 @@ int ref_love_bisecim(int n, const double* d, const double* vs, const double* mu,
   delete_love_();
   return iq;
 }
+
+/* the trial phase velocities of one frequency: C_Interval_L on the T_GRT setup_grt leaves (v: the sorted layer velocities,
+ * nv of them, 2n allocated).  ccc: 20000 doubles.  counts = {ncc, im1}. */
+int ref_love_cinterval(int n, const double* d, const double* vp, const double* vs, const double* v, int nv, double vsy, double vsm, double vs1,
+            double w, double tol, double* ccc, int* counts) {
+  T_GRT g;
+  memset(&g, 0, sizeof g);
+  g.nlayers = n;
+  g.d = (double*)d; g.d_d1 = n; g.d_l1 = 1;
+  g.vp = (double*)vp; g.vp_d1 = n; g.vp_l1 = 1;
+  g.vs = (double*)vs; g.vs_d1 = n; g.vs_l1 = 1;
+  double* vv = (double*)calloc((size_t)2 * n + 8, sizeof(double));   /* allocate( GRT%v(2*nlayers) ); GRT%v = 0 */
+  for (int i = 0; i < nv; ++i) vv[i] = v[i];
+  g.v = vv; g.v_d1 = 2 * n; g.v_l1 = 1;
+  g.vsy = vsy; g.vsm = vsm; g.vs1 = vs1; g.w = w; g.tol = tol;
+  int ncc = 0, im1 = 0;
+  c_interval_l_(&g, ccc, &ncc, &im1);
+  counts[0] = ncc; counts[1] = im1;
+  free(vv);
+  return 0;
+}

@@ -621,3 +621,33 @@ def grt_bisecim(impl, thick, vp, vs, rho, freq, modetype, k1, k2, smin=1e-4, tol
         fn.argtypes = [C.c_int, vpt, vpt, vpt, vpt, C.c_int] + [C.c_double] * 5 + [vpt]
         iq = fn(n, d.ctypes.data, p.ctypes.data, v.ctypes.data, mu.ctypes.data, int(ints[2]), w, k1, k2, smin, tol, out.ctypes.data)
     return iq, out[0], out[1], out[2]
+
+
+def grt_cinterval(impl, thick, vp, vs, rho, freq, modetype, tol=1e-5):
+    """The trial phase velocities of one frequency (C_Interval / C_Interval_L).  impl "port": the restatement; "reference": the
+    translated Fortran on the T_GRT the restatement's setup_grt builds.  Returns (ccc[:ncc], im1, overflow flag of the port)."""
+    vpt = C.c_void_p
+    a = [f64(x) for x in (thick, vp, vs, rho)]
+    n = len(a[0])
+    ccc, v, extra, counts = np.zeros(20008), np.zeros(2 * n + 8), np.zeros(3), np.zeros(4, np.int32)
+    fn = L().orc_grt_cinterval
+    fn.argtypes = [vpt] * 4 + [C.c_int, C.c_double, C.c_int, C.c_double] + [vpt] * 4
+    rc = fn(*[x.ctypes.data for x in a], n, freq, modetype, tol, ccc.ctypes.data, v.ctypes.data, extra.ctypes.data, counts.ctypes.data)
+    assert rc == 0
+    if impl == "port":
+        return ccc[:counts[0]].copy(), int(counts[1]), int(counts[3])
+    _, d, p, vsl, mu, ints, w = _grt_state(thick, vp, vs, rho, freq, modetype, 3.0)
+    global _love_f2c, _rayleigh_f2c
+    if modetype == 0:
+        if _love_f2c is None:
+            _love_f2c = C.CDLL(LOVE_F2C_LIB)
+        g = _love_f2c.ref_love_cinterval
+    else:
+        if _rayleigh_f2c is None:
+            _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
+        g = _rayleigh_f2c.ref_rayleigh_cinterval
+    g.argtypes = [C.c_int, vpt, vpt, vpt, vpt, C.c_int] + [C.c_double] * 5 + [vpt, vpt]
+    out, cnt = np.zeros(20008), np.zeros(2, np.int32)
+    g(n, d.ctypes.data, p.ctypes.data, vsl.ctypes.data, v.ctypes.data, int(counts[2]), extra[0], extra[1], extra[2], w, tol, out.ctypes.data,
+      cnt.ctypes.data)
+    return out[:cnt[0]].copy(), int(cnt[1]), int(counts[3])

@@ -316,3 +316,32 @@ def test_root_refinement_equals_the_translated_reference(modetype):
                 found += int(a[0] == 0)
                 rejected += int(a[0] == -1)
     assert n > 100 and found > 50, (n, found, rejected)
+
+
+@pytest.mark.skipif(not (orc.have_rayleigh_reference() and orc.have_love_reference()), reason="oracle/_ref translations not built (needs /root/reference)")
+@pytest.mark.parametrize("modetype", [1, 0])
+def test_trial_velocity_lists_equal_the_translated_reference(modetype):
+    """C_Interval / C_Interval_L (with N_cf / N_cf_L and util.f90's sort) -- the list of trial phase velocities every frequency's
+    scan walks, and im1 -- as the reference's own statements build them, against the restatement's: every entry bit for bit,
+    at low frequencies (the dense fill) and high ones (the N_cf-driven subdivision, the layer resonances, two midpoint passes)."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    for _ in range(10):
+        nl = int(rng.integers(4, 12))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        k = int(rng.integers(1, nl - 1))
+        vs[k] = vs[k - 1] * rng.uniform(0.7, 0.95)
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0)))
+    n = dense = fine = 0
+    for th, vp, vs, rho in cols:
+        for f in FREQS:
+            tol = float(10.0 ** rng.uniform(-6, -4))
+            a, ia, over = orc.grt_cinterval("port", th, vp, vs, rho, float(f), modetype, tol)
+            if over:
+                continue                      # the Fortran overruns vvv(20000) there: undefined
+            b, ib, _ = orc.grt_cinterval("reference", th, vp, vs, rho, float(f), modetype, tol)
+            assert len(a) == len(b) and ia == ib and a.tobytes() == b.tobytes(), (vs, f, len(a), len(b), ia, ib)
+            n += 1
+            dense += int(f < 0.12)
+            fine += int(f >= 0.12)
+    assert n > 100 and dense > 10 and fine > 50, (n, dense, fine)
