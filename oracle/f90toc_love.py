@@ -2,7 +2,7 @@
 """oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's generalized R/T secular functions:
 surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) and the units of surfmodes/Rayleigh.f90 a
 column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), bisecim and sort
-of util.f90, C_Interval / N_cf (C_interval.f90) and C_Interval_L / N_cf_L (C_interval_L.f90), with `csq`, the
+of util.f90, C_Interval / N_cf (C_interval.f90), C_Interval_L / N_cf_L (C_interval_L.f90) and setup_grt (surfmodes.f90), with `csq`, the
 parameters and the derived type T_GRT of surfmodes/GRT.f90.
 
 TEST INFRASTRUCTURE, in the line of oracle/f77toc.py and oracle/f90toc.py: the sources are read where they lie, nothing is
@@ -17,7 +17,9 @@ copied.  What this subset adds to f90toc's:
     elementwise EXP, array-valued function results and array actual arguments (copy-in), pointers associated with a section
     (`pp=>a44(2:3,3:4); pp=-pp`: an alias) -- and an assignment evaluates every right-hand-side element into a temporary before the
     first store (Fortran's semantics: `b22 = b22/(2.*b22(1,1))` divides by the OLD b22(1,1));
-  * the derived type T_GRT as a C struct (allocatable components = pointer + extent + lower bound), passed by reference;
+  * the derived types T_GRT and T_MODES_PARA as C structs (allocatable components = pointer + extent + lower bound), passed by
+    reference; whole component arrays as actual arguments, under MAXVAL / MINVAL (also of a run-time section) and in
+    `GRT%mu = GRT%mu/mu0`; parameters re-defined by a later module (m_surfmodes' eps, pi) under their own C names;
   * FUNCTION units (scalar or array result), dummy procedures (bound to a routine of the driver), SELECT CASE on an integer, DO
     with a negative step, DO without a control, DO WHILE, CYCLE, MERGE, 1-D sections with run-time bounds copied through a
     temporary (`vvv(2:index0)=vvv(i:ii)`), whole work arrays passed by reference, USE ... ONLY / PRIVATE / PUBLIC.
@@ -34,12 +36,14 @@ import f77toc as F                                                     # noqa: E
 import f90toc as G                                                     # noqa: E402
 from f77toc import INT, R4, R8, LOG, CT, Node, Unit                     # noqa: E402
 
-CPX, TGRT = 4, 10
+CPX, TGRT, TPARA = 4, 10, 11
 CT[CPX] = "double _Complex"
 CT[TGRT] = "T_GRT"
+CT[TPARA] = "T_MODES_PARA"
+STRUCT_OF = {TGRT: "t_grt", TPARA: "t_modes_para"}
 F.TOK = re.compile(F.TOK.pattern.replace("[-+*/(),<>=%]", r"[-+*/(),<>=%:\[\]]"), re.X)
 
-SPEC = r"(integer|logical|real\(kind=[a-z0-9_]+\)|real\*8|complex\*16|type\(t_grt\))"
+SPEC = r"(integer|logical|real\(kind=[a-z0-9_]+\)|real\*8|complex\*16|type\(t_grt\)|type\(t_modes_para\))"
 
 
 class Arr:
@@ -54,6 +58,8 @@ class Arr:
 class Mod:
     def __init__(self):
         self.kinds, self.params, self.scalars, self.fixed, self.alloc, self.struct = {}, {}, {}, {}, {}, {}
+        self.structs = {"t_grt": self.struct}
+        self.param_cname, self.param_decls = {}, []   # a parameter re-defined by a later module (m_surfmodes' eps, pi) gets a new C name
         self.order = []
         self.ints = {}           # integer parameters by value (array bounds)
         self.lead = {}           # rank-3 allocatable arrays: bounds of the two leading dimensions, fixed by their ALLOCATE
@@ -70,6 +76,8 @@ class Mod:
             return CPX
         if spec == "type(t_grt)":
             return TGRT
+        if spec == "type(t_modes_para)":
+            return TPARA
         m = re.fullmatch(r"real\(kind=([a-z0-9_]+)\)", spec)
         return self.kinds[m.group(1)]
 
@@ -102,10 +110,13 @@ class Mod:
             self.kinds[name] = R8
         elif is_par:
             u = UnitG(None, self, "subroutine", "_", [])
-            self.params[name] = (typ, u.cast(u.parse(init), typ))
+            c = u.cast(u.parse(init), typ)
+            cname = name if name not in self.params else f"{name}_{len(self.param_decls)}"
+            self.params[name] = (typ, c)
+            self.param_cname[name] = cname
+            self.param_decls.append((cname, typ, c))
             if typ == INT:
                 self.ints[name] = self.const_int(init)
-            self.order.append(name)
         elif dims and all(d == ":" for d in dims):
             (self.alloc if into is None else into)[name] = (typ, len(dims)) if into is None else ("alloc", typ, len(dims))
             if tgt:
@@ -125,40 +136,43 @@ class Mod:
 
     def read_header(self, stmts):
         """module-level statements up to CONTAINS; returns the index after it"""
-        in_type = False
+        in_type, cur = False, None
         for k, (text, ln) in enumerate(stmts):
             if text == "contains" and not in_type:
                 return k + 1
             if re.fullmatch(r"(module[a-z0-9_]+|use[a-z0-9_,:]+|implicitnone|private|public::.*)", text):
                 continue
-            if text == "typet_grt":
+            m = re.fullmatch(r"type(t_grt|t_modes_para)", text)
+            if m:
                 in_type = True
+                cur = self.structs.setdefault(m.group(1), {})
                 continue
-            if text in ("endtypet_grt", "endtype"):
+            if text in ("endtypet_grt", "endtype", "endtypet_modes_para"):
                 in_type = False
                 continue
             d = self.declare(text)
             if d is None:
                 raise SyntaxError(f"module line {ln}: {text!r}")
             for name, typ, dims, init, is_par in d:
-                self.add(name, typ, dims, init, is_par, into=self.struct if in_type else None)
+                self.add(name, typ, dims, init, is_par, into=cur if in_type else None)
         return len(stmts)
 
     def c_decls(self):
-        o = ["#include <complex.h>", "typedef struct {"]
-        for name, c in self.struct.items():
-            if c[0] == "scalar":
-                o.append(f"  {CT[c[1]]} {name};")
-            elif c[0] == "alloc":
-                o.append(f"  {CT[c[1]]}* {name}; int {name}_d1, {name}_l1;")
-            else:
-                o.append(f"  {CT[c[1]]} {name}[{c[2][0][1] - c[2][0][0] + 1}];")
-        o.append("} T_GRT;")
+        o = ["#include <complex.h>"]
+        for sname, comps in self.structs.items():
+            o.append("typedef struct {")
+            for name, c in comps.items():
+                if c[0] == "scalar":
+                    o.append(f"  {CT[c[1]]} {name};")
+                elif c[0] == "alloc":
+                    o.append(f"  {CT[c[1]]}* {name}; int {name}_d1, {name}_l1;")
+                else:
+                    o.append(f"  {CT[c[1]]} {name}[{c[2][0][1] - c[2][0][0] + 1}];")
+            o.append("} " + sname.upper() + ";")
+        for cname, t, c in self.param_decls:
+            o.append(f"static const {CT[t]} {cname} = {c};")
         for name in self.order:
-            if name in self.params:
-                t, c = self.params[name]
-                o.append(f"static const {CT[t]} {name} = {c};")
-            elif name in self.alloc:
+            if name in self.alloc:
                 t, rank = self.alloc[name]
                 o.append(f"static __thread {CT[t]}* {name}; static __thread int " + ", ".join(f"{name}_d{k + 1}, {name}_l{k + 1} = 1" for k in range(rank)) + ";")
             elif name in self.fixed:
@@ -213,8 +227,8 @@ class UnitG(Unit):
 
     def ref(self, name):
         if self.is_mod(name):
-            return name
-        if name in self.args and self.types.get(name) == TGRT:
+            return self.mod.param_cname.get(name, name) if name in self.mod.params else name
+        if name in self.args and self.types.get(name) in STRUCT_OF:
             return name                                   # a pointer to the struct
         return super().ref(name)
 
@@ -379,18 +393,28 @@ class UnitG(Unit):
                 elems.append(self.dyn_elem(v, full))
             return Arr(shape, elems)
         n = super().p_prim()
-        while self.peek()[1] == "%":                     # component of the T_GRT dummy
+        while self.peek()[1] == "%":                     # component of a derived-type dummy
             self.take()
             _, comp = self.take()
-            c = self.mod.struct[comp]
+            c = self.mod.structs[STRUCT_OF[n.typ]][comp]
             if c[0] == "scalar":
                 n = Node("elem", c[1], f"{n.c}->{comp}", name=None, idx=None)
-            else:
-                self.take("(")
-                i = self.p_or()
+                continue
+            lo = f"{n.c}->{comp}_l1" if c[0] == "alloc" else str(c[2][0][0])
+            if self.peek()[1] != "(":                     # the whole component array: MAXVAL, an actual argument, comp = comp / x
+                n = Node("comp", c[1], f"{n.c}->{comp}", ptr=f"{n.c}->{comp}", count=f"{n.c}->{comp}_d1", name=None)
+                continue
+            self.take("(")
+            i = self.p_or()
+            if self.peek()[1] == ":":                     # a section with run-time bounds (MINVAL(GRT%vs(ifs+1:nlayers)))
+                self.take()
+                hi = self.p_or()
                 self.take(")")
-                lo = f"{n.c}->{comp}_l1" if c[0] == "alloc" else str(c[2][0][0])
-                n = Node("elem", c[1], f"{n.c}->{comp}[({self.cast(i, INT)}) - {lo}]", name=None, idx=None)
+                li = self.cast(i, INT)
+                n = Node("comp", c[1], "?", ptr=f"({n.c}->{comp} + (({li}) - {lo}))", count=f"(({self.cast(hi, INT)}) - ({li}) + 1)", name=None)
+                continue
+            self.take(")")
+            n = Node("elem", c[1], f"{n.c}->{comp}[({self.cast(i, INT)}) - {lo}]", name=None, idx=None)
         return n
 
     def dyn_elem(self, name, subs):
@@ -422,6 +446,8 @@ class UnitG(Unit):
             return Node("elem", m.alloc[name][0], f"{name}[({self.cast(args[0], INT)}) - {name}_l1]", name=name, idx=None)
         if name == "allocated":
             return Node("call", LOG, f"({args[0].name} != 0)")
+        if name in ("maxval", "minval") and args[0].kind == "comp":
+            return Node("call", args[0].typ, f"f_{name}({args[0].ptr}, {args[0].count})")
         if name == "floor":
             return Node("call", INT, f"((int)floor({self.cast(args[0], R8)}))")
         if name == "nint":
@@ -480,7 +506,10 @@ class UnitG(Unit):
                 self.pre.append(f"{CT[a.typ]} {t}[{len(a.elems)}] = {{" + ", ".join(self.cast(e, a.typ) for e in a.elems) + "};")
                 out.append(f"(void*){t}")
                 continue
-            if a.kind == "var" and self.types.get(a.name) == TGRT:
+            if a.kind == "comp":
+                out.append(f"(void*){a.ptr}")
+                continue
+            if a.kind == "var" and self.types.get(a.name) in STRUCT_OF:
                 out.append(f"(void*){a.name}")
             elif a.kind == "var" and a.name not in self.params:
                 out.append(f"(void*){self.addr(a.name)}")
@@ -492,6 +521,12 @@ class UnitG(Unit):
 
     # ---- statements
     def assign(self, lhs, rhs):
+        m = re.fullmatch(r"([a-z][a-z0-9_]*%[a-z][a-z0-9_]*)/(.+)", rhs)
+        if m and m.group(1) == lhs:                       # GRT%mu = GRT%mu/mu0: elementwise over the whole component
+            a = self.parse(lhs)
+            d = self.parse(m.group(2))
+            self.emit(f"{{ {CT[a.typ]} q_ = {self.cast(d, a.typ)}; for (int i_ = 0; i_ < {a.count}; ++i_) {a.ptr}[i_] = {a.ptr}[i_] / q_; }}")
+            return
         ln = self.parse(lhs)
         rn = self.parse(rhs)
         for p in self.pre:
@@ -535,6 +570,9 @@ class UnitG(Unit):
             return
         if t == "cycle":
             self.emit("continue;")
+            return
+        if t == "stop":
+            self.emit("f90_stopped = 1; return;")
             return
         m = re.fullmatch(r"([a-z][a-z0-9_]*)\(([^():,]+):([^():,]+)\)=([a-z][a-z0-9_]*)\(([^():,]+):([^():,]+)\)", t)
         if m and self.bounds(m.group(1)) is not None and len(self.bounds(m.group(1))) == 1:
@@ -693,7 +731,12 @@ class TranslatorG:
              "/* compile with -fcx-fortran-rules -ffp-contract=off */",
              "#include <math.h>", "#include <stdlib.h>",
              "static inline double f_sq(double x) { return x * x; }",
-             "static inline double f_powi(double x, int n) { double r = 1.0; int m = n < 0 ? -n : n; while (m--) r *= x; return n < 0 ? 1.0 / r : r; }", ""]
+             "static inline double f_powi(double x, int n) { double r = 1.0; int m = n < 0 ? -n : n; while (m--) r *= x; return n < 0 ? 1.0 / r : r; }",
+             "static inline int f_mini(int a, int b) { return a < b ? a : b; }", "static inline int f_maxi(int a, int b) { return a > b ? a : b; }",
+             "static inline double f_min(double a, double b) { return a < b ? a : b; }", "static inline double f_max(double a, double b) { return a > b ? a : b; }",
+             "static inline double f_maxval(const double* a, int n) { double r = a[0]; for (int i = 1; i < n; ++i) if (a[i] > r) r = a[i]; return r; }",
+             "static inline double f_minval(const double* a, int n) { double r = a[0]; for (int i = 1; i < n; ++i) if (a[i] < r) r = a[i]; return r; }",
+             "static __thread int f90_stopped;", ""]
         o += self.mod.c_decls() + [""]
 
         def proto(u):

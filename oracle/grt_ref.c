@@ -11,8 +11,8 @@
  * `surfmmodes` prints "not supported yet" for such columns (surfmodes.f90:153,165).
  *
  * PARITY STATUS: "parity unpinned" except the secular functions secfun_L (Love.f90) and secfun_surf with startl (Rayleigh.f90,
- * columns without water), the root refinement bisecim (util.f90) and the trial-velocity lists (C_Interval, C_Interval_L, N_cf,
- * N_cf_L, sort): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
+ * columns without water), the root refinement bisecim (util.f90), the trial-velocity lists (C_Interval, C_Interval_L, N_cf,
+ * N_cf_L, sort) and setup_grt (surfmodes.f90): bit-identical to the reference's sources translated mechanically by oracle/f90toc_love.py
  * (tests/test_oracle_grt.py).  The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent
@@ -802,6 +802,22 @@ int orc_grt_cinterval(const double* thick, const double* vp, const double* vs, c
   counts[0] = ncc; counts[1] = im1; counts[2] = G->nv; counts[3] = G->overflow;
   free(G->vvv); free(G->ccc); free(G);
   return 0;
+}
+
+/* test hook: everything setup_grt (surfmodes.f90:320-450) leaves in the T_GRT.  mu_out: n, v_out: 2n, lvls_out: n/2+1 values;
+ * ints = {ifs, no_lvl, no_lvl_fl, nlvl1, nlvls1, lvlast, L1, nv}; dbl = {mu0, vsy, vs1, vsm, vss1}. */
+int orc_grt_setup(const double* thick, const double* vp, const double* vs, const double* rho, int n, int modetype, double* mu_out,
+                  double* v_out, int* lvls_out, int* ints, double* dbl) {
+  grt_t* G = (grt_t*)calloc(1, sizeof(grt_t));
+  int rc = setup_grt(G, thick, vp, vs, rho, n, modetype, 1e-3, 1e-3, 1e-3);
+  for (int j = 1; j <= n; ++j) mu_out[j - 1] = G->mu[j];
+  for (int j = 1; j <= 2 * n; ++j) v_out[j - 1] = j <= G->nv ? G->v[j] : 0.0;
+  for (int j = 1; j <= n / 2 + 1; ++j) lvls_out[j - 1] = G->lvls[j];
+  ints[0] = G->ifs; ints[1] = G->no_lvl; ints[2] = G->no_lvl_fl; ints[3] = G->nlvl1; ints[4] = G->nlvls1; ints[5] = G->lvlast;
+  ints[6] = G->L1; ints[7] = G->nv;
+  dbl[0] = G->mu0; dbl[1] = G->vsy; dbl[2] = G->vs1; dbl[3] = G->vsm; dbl[4] = G->vss1;
+  free(G);
+  return rc;
 }
 
 /* test hook: the secular function itself (modetype 1: SecFunSurf / SecFunSt, 0: SecFuns_L) at phase velocity c */

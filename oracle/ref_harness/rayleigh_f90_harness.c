@@ -70,3 +70,37 @@ int ref_rayleigh_cinterval(int n, const double* d, const double* vp, const doubl
   free(vv);
   return 0;
 }
+
+/* setup_grt on a fresh T_GRT: the allocations and zero / huge() initial values are init_grt's (GRT.f90:44-91), the assignments of
+ * the column to GRT%d, %vp, %vs, %rho are surfmodes' (surfmodes.f90:60-75); everything else is the translated setup_grt.
+ * Outputs as orc_grt_setup.  Returns 1 when setup_grt STOPs (a fluid layer below the first). */
+int ref_setup_grt(int n, const double* thick, const double* vp, const double* vs, const double* rho, int modetype, double* mu_out,
+                  double* v_out, int* lvls_out, int* ints, double* dbl) {
+  T_GRT g;
+  T_MODES_PARA para;
+  memset(&g, 0, sizeof g);
+  memset(&para, 0, sizeof para);
+  para.modetype = modetype; para.dc = 1e-3; para.dcm = 1e-3; para.dc2 = 1e-3;
+  g.nlayers = n;
+  g.smin = (double)1E-4f; g.tol = (double)1E-5f; g.dc = (double)1E-4f; g.dc2 = (double)1E-4f; g.dcm = (double)1E-4f;
+  double* buf = (double*)calloc((size_t)8 * n + 16, sizeof(double));
+  int* lv = (int*)calloc((size_t)n / 2 + 8, sizeof(int));
+  g.d = buf; g.vp = buf + n; g.vs = buf + 2 * n; g.rho = buf + 3 * n; g.mu = buf + 4 * n; g.v = buf + 5 * n;
+  g.d_d1 = g.vp_d1 = g.vs_d1 = g.rho_d1 = g.mu_d1 = n; g.v_d1 = 2 * n;
+  g.d_l1 = g.vp_l1 = g.vs_l1 = g.rho_l1 = g.mu_l1 = g.v_l1 = 1;
+  g.lvls = lv; g.lvls_d1 = n / 2 + 1; g.lvls_l1 = 1;
+  g.vsy = 1.7976931348623157e308; /* huge(grt%vsy) */
+  for (int i = 0; i < n; ++i) { g.d[i] = thick[i]; g.vp[i] = vp[i]; g.vs[i] = vs[i]; g.rho[i] = rho[i]; }
+  f90_stopped = 0;
+  setup_grt_(&g, &para);
+  int nv = 0;
+  for (int i = 0; i < n; ++i) nv += (vs[i] > 1e-6 || vs[i] < -1e-6) ? 2 : 1;
+  for (int i = 0; i < n; ++i) mu_out[i] = g.mu[i];
+  for (int i = 0; i < 2 * n; ++i) v_out[i] = g.v[i];
+  for (int i = 0; i < n / 2 + 1; ++i) lvls_out[i] = lv[i];
+  ints[0] = g.ifs; ints[1] = g.no_lvl; ints[2] = g.no_lvl_fl; ints[3] = g.nlvl1; ints[4] = g.nlvls1; ints[5] = g.lvlast; ints[6] = g.l1;
+  ints[7] = nv;
+  dbl[0] = g.mu0; dbl[1] = g.vsy; dbl[2] = g.vs1; dbl[3] = g.vsm; dbl[4] = g.vss1;
+  free(buf); free(lv);
+  return f90_stopped;
+}

@@ -651,3 +651,24 @@ def grt_cinterval(impl, thick, vp, vs, rho, freq, modetype, tol=1e-5):
     g(n, d.ctypes.data, p.ctypes.data, vsl.ctypes.data, v.ctypes.data, int(counts[2]), extra[0], extra[1], extra[2], w, tol, out.ctypes.data,
       cnt.ctypes.data)
     return out[:cnt[0]].copy(), int(cnt[1]), int(counts[3])
+
+
+def grt_setup(impl, thick, vp, vs, rho, modetype):
+    """Everything setup_grt leaves in the T_GRT of a column.  impl "port": the restatement; "reference": the translated
+    surfmodes.f90:320-450 on a T_GRT initialised as init_grt does.  Returns (rc, mu, v[:nv], lvls, ints, dbl)."""
+    vpt = C.c_void_p
+    a = [f64(x) for x in (thick, vp, vs, rho)]
+    n = len(a[0])
+    mu, v, lvls, ints, dbl = np.zeros(n), np.zeros(2 * n), np.zeros(n // 2 + 1, np.int32), np.zeros(8, np.int32), np.zeros(5)
+    if impl == "port":
+        fn = L().orc_grt_setup
+        fn.argtypes = [vpt] * 4 + [C.c_int, C.c_int] + [vpt] * 5
+        rc = fn(*[x.ctypes.data for x in a], n, modetype, mu.ctypes.data, v.ctypes.data, lvls.ctypes.data, ints.ctypes.data, dbl.ctypes.data)
+    else:
+        global _rayleigh_f2c
+        if _rayleigh_f2c is None:
+            _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
+        fn = _rayleigh_f2c.ref_setup_grt
+        fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int] + [vpt] * 5
+        rc = fn(n, *[x.ctypes.data for x in a], modetype, mu.ctypes.data, v.ctypes.data, lvls.ctypes.data, ints.ctypes.data, dbl.ctypes.data)
+    return rc, mu, v[:ints[7]].copy(), lvls, ints, dbl

@@ -345,3 +345,37 @@ def test_trial_velocity_lists_equal_the_translated_reference(modetype):
             dense += int(f < 0.12)
             fine += int(f >= 0.12)
     assert n > 100 and dense > 10 and fine > 50, (n, dense, fine)
+
+
+@pytest.mark.skipif(not orc.have_rayleigh_reference(), reason="oracle/_ref/librayleigh_f2c.so not built (needs /root/reference)")
+@pytest.mark.parametrize("modetype", [1, 0])
+def test_setup_grt_equals_the_translated_reference(modetype):
+    """setup_grt (surfmodes.f90:320-450) as the reference's own statements on a T_GRT initialised as init_grt does: the scaled
+    rigidities, the sorted velocity list, the low-velocity layers and their order, ifs / nlvl1 / nlvls1 / lvlast / L1, vsy / vs1 /
+    vsm / vss1 -- everything the searches read -- against the restatement's, with and without a water layer, one and several
+    low-velocity zones."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    for k in range(60):
+        nl = int(rng.integers(3, 16))
+        vs = np.sort(rng.uniform(2.2, 4.6, nl))
+        for _ in range(int(rng.integers(0, 4))):
+            j = int(rng.integers(1, nl - 1)) if nl > 2 else 1
+            vs[j] = vs[j - 1] * rng.uniform(0.6, 0.97)
+        th = np.append(rng.uniform(0.3, 6.0, nl - 1), 0.0)
+        cols.append(crust(vs, th, water=float(rng.uniform(0.2, 3.0)) if k % 3 == 0 else None))
+    n = water = multi = 0
+    for th, vp, vs, rho in cols:
+        a = orc.grt_setup("port", th, vp, vs, rho, modetype)
+        b = orc.grt_setup("reference", th, vp, vs, rho, modetype)
+        assert a[0] == 0 and b[0] == 0
+        assert a[1].tobytes() == b[1].tobytes(), ("mu", vs)
+        assert a[2].tobytes() == b[2].tobytes(), ("v", vs, a[2], b[2])
+        nlv = int(a[4][1])
+        assert np.array_equal(a[3][:nlv + 1], b[3][:nlv + 1]), ("lvls", vs, a[3], b[3])
+        assert np.array_equal(a[4], b[4]), ("ints", vs, a[4], b[4])
+        assert a[5].tobytes() == b[5].tobytes(), ("dbl", vs, a[5], b[5])
+        n += 1
+        water += int(a[4][0] > 0)
+        multi += int(nlv > 1)
+    assert n > 60 and water > 10 and multi > 5, (n, water, multi)
