@@ -38,7 +38,9 @@ fi
 # mechanically (oracle/f90toc_love.py); -fcx-fortran-rules: complex products and quotients as gfortran's middle end expands them
 if [ -f "$REF/surfmodes/Love.f90" ] && [ -f "$REF/surfmodes/GRT.f90" ]; then
   mkdir -p "$OUT"
-  python "$HERE/f90toc_love.py" "$REF/surfmodes/GRT.f90" "$REF/surfmodes/Love.f90" "$REF/surfmodes/util.f90:bisecim,sort" "$REF/surfmodes/C_interval_L.f90" "$OUT/love_f2c.c"
+  python "$HERE/f90toc_love.py" "$REF/surfmodes/GRT.f90" "$REF/surfmodes/Love.f90" "$REF/surfmodes/util.f90:bisecim,sort" "$REF/surfmodes/C_interval_L.f90" \
+      "$REF/surfmodes/Rayleigh.f90:startl:nohdr" "$REF/surfmodes/surfmodes.f90:setup_grt" host=kt:real,c:real,grt:t_grt \
+      "$REF/surfmodes/SearchLove.f90:check,fundamode" "$OUT/love_f2c.c"
   gcc -O2 -fPIC -std=gnu11 -fcx-fortran-rules -ffp-contract=off -fno-fast-math -shared -DLOVE_F2C_SOURCE="\"$OUT/love_f2c.c\"" \
       -o "$OUT/liblove_f2c.so" "$HERE/ref_harness/love_f90_harness.c" -lm
   echo "build_ref: built $OUT/liblove_f2c.so from $REF/surfmodes/Love.f90 + bisecim, sort of util.f90 + the C_Interval file"

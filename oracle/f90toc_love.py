@@ -2,7 +2,8 @@
 """oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's generalized R/T secular functions:
 surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) and the units of surfmodes/Rayleigh.f90 a
 column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), bisecim and sort
-of util.f90, C_Interval / N_cf (C_interval.f90), C_Interval_L / N_cf_L (C_interval_L.f90) and setup_grt (surfmodes.f90), with `csq`, the
+of util.f90, C_Interval / N_cf (C_interval.f90), C_Interval_L / N_cf_L (C_interval_L.f90), setup_grt (surfmodes.f90) and the internal procedures FundaMode and check of
+SearchLove.f90, with `csq`, the
 parameters and the derived type T_GRT of surfmodes/GRT.f90.
 
 TEST INFRASTRUCTURE, in the line of oracle/f77toc.py and oracle/f90toc.py: the sources are read where they lie, nothing is
@@ -20,6 +21,8 @@ copied.  What this subset adds to f90toc's:
   * the derived types T_GRT and T_MODES_PARA as C structs (allocatable components = pointer + extent + lower bound), passed by
     reference; whole component arrays as actual arguments, under MAXVAL / MINVAL (also of a run-time section) and in
     `GRT%mu = GRT%mu/mu0`; parameters re-defined by a later module (m_surfmodes' eps, pi) under their own C names;
+  * internal procedures as units of their own, the host's variables they read at file scope (`host=kt:real,c:real,grt:t_grt`);
+    assumed-shape dummies; a procedure name as actual argument (the callee's dummy procedure is bound by the driver);
   * FUNCTION units (scalar or array result), dummy procedures (bound to a routine of the driver), SELECT CASE on an integer, DO
     with a negative step, DO without a control, DO WHILE, CYCLE, MERGE, 1-D sections with run-time bounds copied through a
     temporary (`vvv(2:index0)=vvv(i:ii)`), whole work arrays passed by reference, USE ... ONLY / PRIVATE / PUBLIC.
@@ -219,9 +222,13 @@ class UnitG(Unit):
             return m.func_types[name]
         if re.fullmatch(r"[a-z0-9_]+_[dl][123]", name):
             return INT
+        if self.tr is not None and name in self.tr.host:
+            return self.tr.host[name]
         raise SyntaxError(f"{self.name}: {name!r} is not declared")
 
     def note(self, name):
+        if self.tr is not None and name in self.tr.host and name not in self.types and name not in self.args:
+            return                                        # the host's variable (file scope)
         if not self.is_mod(name):
             super().note(name)
 
@@ -230,6 +237,8 @@ class UnitG(Unit):
             return self.mod.param_cname.get(name, name) if name in self.mod.params else name
         if name in self.args and self.types.get(name) in STRUCT_OF:
             return name                                   # a pointer to the struct
+        if self.tr is not None and name in self.tr.host and name not in self.types and name not in self.args:
+            return name
         return super().ref(name)
 
     def addr(self, name):
@@ -509,6 +518,9 @@ class UnitG(Unit):
             if a.kind == "comp":
                 out.append(f"(void*){a.ptr}")
                 continue
+            if a.kind == "var" and a.name in self.mod.func_types and a.name not in self.types:
+                out.append("(void*)0")                    # a procedure as actual argument: the translated callee calls the driver's binding
+                continue
             if a.kind == "var" and self.types.get(a.name) in STRUCT_OF:
                 out.append(f"(void*){a.name}")
             elif a.kind == "var" and a.name not in self.params:
@@ -651,6 +663,7 @@ class TranslatorG:
         self.units = []
         self.called = set()
         self.externs = {}        # dummy procedures (REAL*8, EXTERNAL :: f): name -> result type
+        self.host = {}           # host-associated variables of translated internal procedures: name -> type (file-scope in C)
 
     def scan_functions(self, stmts):
         """result types of the FUNCTION units (needed before their callers are translated)"""
@@ -675,8 +688,11 @@ class TranslatorG:
         u, in_spec, skipping = None, False, False
         for text, ln in stmts[start:]:
             if skipping:
-                skipping = re.fullmatch(r"end(subroutine|function)[a-z0-9_]*", text) is None
-                continue
+                m = re.fullmatch(r"(?:(?:real\*8|complex\*16|real\(kind=[a-z0-9_]+\)))?(subroutine|function)([a-z][a-z0-9_]*)(?:\((.*)\))?", text)
+                if not (m and only is not None and m.group(2) in only):   # (an internal procedure of a skipped host may be selected)
+                    skipping = re.fullmatch(r"end(subroutine|function)[a-z0-9_]*", text) is None
+                    continue
+                skipping = False
             if u is None:
                 m = re.fullmatch(r"(?:(?:real\*8|complex\*16|real\(kind=[a-z0-9_]+\)))?(subroutine|function)([a-z][a-z0-9_]*)(?:\((.*)\))?", text)
                 if not m:
@@ -717,6 +733,8 @@ class TranslatorG:
                             u.params[name] = u.cast(u.parse(init), typ)
                         elif "external" in text.split("::")[0]:
                             self.externs[name] = typ      # a dummy procedure: the driver supplies name_
+                        elif dims and all(d_ == ":" for d_ in dims) and name in u.args:
+                            u.dims[name] = ["20000"] * len(dims)   # assumed shape: lower bound 1 (only rank 1 occurs: ccc)
                         elif dims:
                             u.dims[name] = dims
                         elif name not in u.args:
@@ -745,6 +763,8 @@ class TranslatorG:
                 ps.append(f"{CT[u.result_type]}* {u.name}_result")
             ret = "void" if u.kind == "subroutine" or u.result_shape else CT[u.result_type]
             return f"static {ret} {u.name}_({', '.join(ps) or 'void'})"
+        for name, t in self.host.items():
+            o.append(f"static __thread {CT[t]}{'*' if t in STRUCT_OF else ''} {name}; /* a host-associated variable of an internal procedure */")
         for name, t in self.externs.items():
             if name not in [u.name for u in self.units]:
                 o.append(f"static {CT[t]} {name}_(void*, void*, void*, void*); /* the driver's */")
@@ -792,9 +812,17 @@ def main():
     tr.scan_functions(s1)
     tr.run(s1, k1, only={"csq"})
     for spec in sys.argv[2:-1]:
-        path, _, units = spec.partition(":")
+        if spec.startswith("host="):                      # host=kt:real,c:real,grt:t_grt
+            for item in spec[5:].split(","):
+                nm, ty = item.split(":")
+                tr.host[nm] = {"real": R8, "integer": INT, "t_grt": TGRT}[ty]
+            continue
+        parts = spec.split(":")
+        path, units = parts[0], (parts[1] if len(parts) > 1 else "")
         st = read(path)
-        k = mod.read_header(st) if st[0][0].startswith("module") else 0
+        k = 0
+        if st[0][0].startswith("module") and "nohdr" not in parts[2:]:
+            k = mod.read_header(st)
         tr.scan_functions(st)
         tr.run(st, k, only=set(units.split(",")) if units else None)
     open(out, "w").write(tr.c_source([grt] + sys.argv[2:-1]))

@@ -64,3 +64,57 @@ int ref_love_cinterval(int n, const double* d, const double* vp, const double* v
   free(vv);
   return 0;
 }
+
+/* A whole column, phase velocities of the fundamental Love mode -- surfmodes with modetype = 0 for a column with a low-velocity
+ * layer.  Written out here: init_grt (GRT.f90:44-91), surfmodes' assignments and dispatch (surfmodes.f90:57-99), the frequency
+ * loop of LoveModes (:266-281) and the allmodes = 0 path of SearchLove (SearchLove.f90:24-40,179).  Translated, i.e. the
+ * reference's own statements: setup_grt, C_Interval_L (N_cf_L, sort), init_love, FundaMode (check, startl, SecFuns_L and below,
+ * bisecim), delete_love.  par = {tolmin, tolmax, smin_min, smin_max, dcm, dc2}; dc as surfmodes' caller sets it.
+ * Returns ierr; -1 when setup_grt STOPs; -2 when the column has no low-velocity layer (surfdisp96's case). */
+int ref_love_modes(int n, const double* thick, const double* vp, const double* vs, const double* rho, int nf, const double* freqs, double dc,
+                   const double* par, double* phase) {
+  T_GRT g;
+  T_MODES_PARA para;
+  memset(&g, 0, sizeof g);
+  memset(&para, 0, sizeof para);
+  para.modetype = 0; para.tolmin = par[0]; para.tolmax = par[1]; para.smin_min = par[2]; para.smin_max = par[3];
+  para.dc = dc; para.dcm = par[4]; para.dc2 = par[5];
+  g.nlayers = n;
+  g.smin = (double)1E-4f; g.tol = (double)1E-5f; g.dc = (double)1E-4f; g.dc2 = (double)1E-4f; g.dcm = (double)1E-4f;
+  double* buf = (double*)calloc((size_t)8 * n + 16, sizeof(double));
+  int* lv = (int*)calloc((size_t)n / 2 + 8, sizeof(int));
+  double* ccc = (double*)calloc(20008, sizeof(double));
+  g.d = buf; g.vp = buf + n; g.vs = buf + 2 * n; g.rho = buf + 3 * n; g.mu = buf + 4 * n; g.v = buf + 5 * n;
+  g.d_d1 = g.vp_d1 = g.vs_d1 = g.rho_d1 = g.mu_d1 = n; g.v_d1 = 2 * n;
+  g.d_l1 = g.vp_l1 = g.vs_l1 = g.rho_l1 = g.mu_l1 = g.v_l1 = 1;
+  g.lvls = lv; g.lvls_d1 = n / 2 + 1; g.lvls_l1 = 1;
+  g.vsy = 1.7976931348623157e308;
+  for (int i = 0; i < n; ++i) { g.d[i] = thick[i]; g.vp[i] = vp[i]; g.vs[i] = vs[i]; g.rho[i] = rho[i]; }
+  f90_stopped = 0;
+  setup_grt_(&g, &para);
+  int ierr = 0;
+  if (f90_stopped) ierr = -1;
+  else if (g.nlvls1 == 0) ierr = -2;
+  else {
+    grt = &g;                                             /* the host variable the internal procedure `check` reads */
+    double c0 = 0;
+    for (int i = 1; i <= nf; ++i) {
+      g.w = freqs[i - 1] * 2 * pi_8;                      /* m_surfmodes' pi = 3.1415926 */
+      g.tol = para.tolmin + (nf + 1 - i) * (para.tolmax - para.tolmin) / nf;
+      g.smin = para.smin_min + (i - 1) * (para.smin_max - para.smin_min) / nf;
+      g.index_a = i;
+      int index0 = 0, im1 = 0, ierr1 = 0;
+      for (int k = 0; k < 20000; ++k) ccc[k] = 0;         /* ccc = 0 */
+      c_interval_l_(&g, ccc, &index0, &im1);
+      init_love_(&g.nlayers);
+      double cray = c0;
+      fundamode_(&g, ccc, &index0, &cray, &ierr1);
+      delete_love_();
+      if (ierr1 == 1) { ierr = 1; break; }
+      phase[i - 1] = cray;
+      c0 = cray;
+    }
+  }
+  free(buf); free(lv); free(ccc);
+  return ierr;
+}

@@ -672,3 +672,20 @@ def grt_setup(impl, thick, vp, vs, rho, modetype):
         fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int] + [vpt] * 5
         rc = fn(n, *[x.ctypes.data for x in a], modetype, mu.ctypes.data, v.ctypes.data, lvls.ctypes.data, ints.ctypes.data, dbl.ctypes.data)
     return rc, mu, v[:ints[7]].copy(), lvls, ints, dbl
+
+
+def grt_love_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIKELIHOOD):
+    """surfmodes for a Love column with a low-velocity layer, phase velocities, through the TRANSLATED reference (setup_grt,
+    C_Interval_L, FundaMode, SecFuns_L, bisecim ...; the frequency loop and SearchLove's five calls are the driver's).
+    Returns (ierr, phase)."""
+    global _love_f2c
+    if _love_f2c is None:
+        _love_f2c = C.CDLL(LOVE_F2C_LIB)
+    vpt = C.c_void_p
+    fn = _love_f2c.ref_love_modes
+    fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int, vpt, C.c_double, vpt, vpt]
+    a = [f64(x) for x in (thick, vp, vs, rho)]
+    freqs, par = f64(freqs), f64(np.array(par))
+    ph = np.full(len(freqs), 100.0)
+    ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data)
+    return ierr, ph

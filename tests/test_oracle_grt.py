@@ -379,3 +379,49 @@ def test_setup_grt_equals_the_translated_reference(modetype):
         water += int(a[4][0] > 0)
         multi += int(nlv > 1)
     assert n > 60 and water > 10 and multi > 5, (n, water, multi)
+
+
+@pytest.mark.skipif(not orc.have_love_reference(), reason="oracle/_ref/liblove_f2c.so not built (needs /root/reference)")
+def test_love_columns_end_to_end_equal_the_translated_reference():
+    """A whole Love column with a low-velocity layer -- what `surfmodes` returns for it -- through the reference's own
+    statements: setup_grt, C_Interval_L, FundaMode with its internal `check`, startl, SecFuns_L and bisecim are all translated;
+    the driver adds init_grt's allocations, the frequency loop of LoveModes and the five calls of SearchLove's allmodes = 0
+    path.  orc_grt_modes (libm math mode, what every GPU test of the branch is held to in portable mode) must return the same
+    phase velocities bit for bit and the same ierr, with both parameter sets the reference's callers use."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    for k in range(60):
+        nl = int(rng.integers(4, 12))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        j = int(rng.integers(1, nl - 1))
+        vs[j] = vs[j - 1] * rng.uniform(0.7, 0.95)
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0), water=float(rng.uniform(0.3, 2.0)) if k % 4 == 0 else None))
+    n = fail = 0
+    for k, (th, vp, vs, rho) in enumerate(cols):
+        par = orc.GRT_PAR_LIKELIHOOD if k % 2 else orc.GRT_PAR_MODELLING
+        e0, p0, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=0, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
+        e1, p1 = orc.grt_love_modes_reference(th, vp, vs, rho, FREQS, dc=1e-3, par=par)
+        if e1 == -2:
+            continue                          # no low-velocity layer by the reference's predicate: surfdisp96's column
+        assert e0 == e1, (vs, e0, e1)
+        m = len(FREQS) if e0 == 0 else 0
+        assert p0[:m].tobytes() == p1[:m].tobytes(), (vs, th, p0, p1)
+        n += 1
+        fail += int(e0 == 1)
+    assert n >= 25, (n, fail)
+
+
+def love_fixture_columns():
+    for k, name in enumerate(sorted(MODELS)):
+        yield (*MODELS[name], orc.GRT_PAR_LIKELIHOOD if k % 2 else orc.GRT_PAR_MODELLING)
+    yield (*crust([3.1, 2.7, 3.5, 3.0, 4.0, 4.5], [1.0, 2.0, 2.5, 3.0, 5.0, 0.0], water=1.2), orc.GRT_PAR_LIKELIHOOD)
+    yield (*crust([2.9, 3.3, 2.6, 3.6, 3.1, 4.1, 4.6], [0.7, 1.4, 2.2, 1.8, 3.5, 6.0, 0.0]), orc.GRT_PAR_MODELLING)
+
+
+def test_love_columns_reproduce_the_reference_fixture():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grt_love_modes_ref.npz"))["phase"]
+    for k, (th, vp, vs, rho, par) in enumerate(love_fixture_columns()):
+        ierr, ph, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=0, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
+        assert ierr == 0 and ph.tobytes() == g[k].tobytes(), (k, ph, g[k])
+    assert g.shape == (5, len(FREQS)) and (g < 5).all() and (g > 2).all()
