@@ -2,8 +2,8 @@
 """oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's generalized R/T secular functions:
 surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) and the units of surfmodes/Rayleigh.f90 a
 column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), bisecim and sort
-of util.f90, C_Interval / N_cf (C_interval.f90), C_Interval_L / N_cf_L (C_interval_L.f90), setup_grt (surfmodes.f90) and the internal procedures FundaMode and check of
-SearchLove.f90, with `csq`, the
+of util.f90, C_Interval / N_cf (C_interval.f90), C_Interval_L / N_cf_L (C_interval_L.f90), setup_grt (surfmodes.f90), the internal procedures FundaMode and check of
+SearchLove.f90, FundaMode of SearchRayleigh.f90 and CR0_Finder with its internal Rayhomo, with `csq`, the
 parameters and the derived type T_GRT of surfmodes/GRT.f90.
 
 TEST INFRASTRUCTURE, in the line of oracle/f77toc.py and oracle/f90toc.py: the sources are read where they lie, nothing is
@@ -21,7 +21,8 @@ copied.  What this subset adds to f90toc's:
   * the derived types T_GRT and T_MODES_PARA as C structs (allocatable components = pointer + extent + lower bound), passed by
     reference; whole component arrays as actual arguments, under MAXVAL / MINVAL (also of a run-time section) and in
     `GRT%mu = GRT%mu/mu0`; parameters re-defined by a later module (m_surfmodes' eps, pi) under their own C names;
-  * internal procedures as units of their own, the host's variables they read at file scope (`host=kt:real,c:real,grt:t_grt`);
+  * internal procedures as units of their own, the host's variables they read at file scope (`host=kt:real,c:real,grt:t_grt`),
+    a host's dummy arguments through pointers the host stores on entry (`v1:real*@cr0_finder`);
     assumed-shape dummies; a procedure name as actual argument (the callee's dummy procedure is bound by the driver);
   * FUNCTION units (scalar or array result), dummy procedures (bound to a routine of the driver), SELECT CASE on an integer, DO
     with a negative step, DO without a control, DO WHILE, CYCLE, MERGE, 1-D sections with run-time bounds copied through a
@@ -224,10 +225,12 @@ class UnitG(Unit):
             return INT
         if self.tr is not None and name in self.tr.host:
             return self.tr.host[name]
+        if self.tr is not None and name in self.tr.host_ptr:
+            return self.tr.host_ptr[name]
         raise SyntaxError(f"{self.name}: {name!r} is not declared")
 
     def note(self, name):
-        if self.tr is not None and name in self.tr.host and name not in self.types and name not in self.args:
+        if self.tr is not None and (name in self.tr.host or name in self.tr.host_ptr) and name not in self.args:
             return                                        # the host's variable (file scope)
         if not self.is_mod(name):
             super().note(name)
@@ -237,11 +240,17 @@ class UnitG(Unit):
             return self.mod.param_cname.get(name, name) if name in self.mod.params else name
         if name in self.args and self.types.get(name) in STRUCT_OF:
             return name                                   # a pointer to the struct
-        if self.tr is not None and name in self.tr.host and name not in self.types and name not in self.args:
+        if self.tr is not None and name in self.tr.host_ptr and name not in self.args:
+            return f"(*h_{name})"
+        if self.tr is not None and name in self.tr.host and name not in self.args:
             return name
         return super().ref(name)
 
     def addr(self, name):
+        if self.tr is not None and name in self.tr.host_ptr and name not in self.args:
+            return f"h_{name}"
+        if self.tr is not None and name in self.tr.host and name not in self.args:
+            return "&" + name
         if self.is_mod(name):
             return name if (name in self.mod.fixed or name in self.mod.alloc) else "&" + name
         return super().addr(name)
@@ -642,6 +651,10 @@ class UnitG(Unit):
             for item in self.split_top(m.group(1)):
                 self.emit(f"free({item}); {item} = 0;")
             return
+        m = re.fullmatch(r"call([a-z][a-z0-9_]*)", t)
+        if m:
+            self.emit(f"{m.group(1)}_();")
+            return
         m = re.fullmatch(r"call([a-z][a-z0-9_]*)\((.*)\)", t)
         if m:
             args = [self.parse(a) for a in self.split_top(m.group(2))]
@@ -664,6 +677,8 @@ class TranslatorG:
         self.called = set()
         self.externs = {}        # dummy procedures (REAL*8, EXTERNAL :: f): name -> result type
         self.host = {}           # host-associated variables of translated internal procedures: name -> type (file-scope in C)
+        self.host_ptr = {}       # ... that are DUMMY arguments of the host: name -> type; the host stores its pointer in h_<name>
+        self.host_of = set()     # the hosts that do so
 
     def scan_functions(self, stmts):
         """result types of the FUNCTION units (needed before their callers are translated)"""
@@ -693,8 +708,15 @@ class TranslatorG:
                     skipping = re.fullmatch(r"end(subroutine|function)[a-z0-9_]*", text) is None
                     continue
                 skipping = False
+            if u is not None and text == "contains":      # the unit's own statements end here; its internal procedures follow
+                assert not u.do_stack, f"{ln}: unterminated do in {u.name}"
+                u.emit("return;" if u.kind == "subroutine" or u.result_shape else f"return {u.name}_result;")
+                u = None
+                continue
             if u is None:
                 m = re.fullmatch(r"(?:(?:real\*8|complex\*16|real\(kind=[a-z0-9_]+\)))?(subroutine|function)([a-z][a-z0-9_]*)(?:\((.*)\))?", text)
+                if not m and re.fullmatch(r"end(subroutine|function)[a-z0-9_]*", text):
+                    continue                              # the end of a host whose body ended at CONTAINS
                 if not m:
                     if re.fullmatch(r"endmodule[a-z0-9_]*", text) or only is not None:
                         continue                          # (with a selection, statements of unselected units in other forms)
@@ -737,8 +759,8 @@ class TranslatorG:
                             u.dims[name] = ["20000"] * len(dims)   # assumed shape: lower bound 1 (only rank 1 occurs: ccc)
                         elif dims:
                             u.dims[name] = dims
-                        elif name not in u.args:
-                            u.locals[name] = typ
+                        elif name not in u.args and name not in self.host:
+                            u.locals[name] = typ                      # (a host-table name is the file-scope variable, in every unit)
                     continue
                 in_spec = False
             u.statement(text, ln)
@@ -765,6 +787,8 @@ class TranslatorG:
             return f"static {ret} {u.name}_({', '.join(ps) or 'void'})"
         for name, t in self.host.items():
             o.append(f"static __thread {CT[t]}{'*' if t in STRUCT_OF else ''} {name}; /* a host-associated variable of an internal procedure */")
+        for name, t in self.host_ptr.items():
+            o.append(f"static __thread {CT[t]}* h_{name}; /* a dummy argument of a host, read by its internal procedure */")
         for name, t in self.externs.items():
             if name not in [u.name for u in self.units]:
                 o.append(f"static {CT[t]} {name}_(void*, void*, void*, void*); /* the driver's */")
@@ -775,6 +799,10 @@ class TranslatorG:
             o.append(proto(u) + " {")
             for a in u.args:
                 o.append(f"  {CT[u.vtype(a)]}* {a} = ({CT[u.vtype(a)]}*){a}_a;")
+            if u.name in self.host_of:
+                for a in u.args:
+                    if a in self.host_ptr:
+                        o.append(f"  h_{a} = {a};")
             if u.kind == "function" and not u.result_shape:
                 o.append(f"  {CT[u.result_type]} {u.name}_result = 0;")
             for k, v in u.params.items():
@@ -815,7 +843,12 @@ def main():
         if spec.startswith("host="):                      # host=kt:real,c:real,grt:t_grt
             for item in spec[5:].split(","):
                 nm, ty = item.split(":")
-                tr.host[nm] = {"real": R8, "integer": INT, "t_grt": TGRT}[ty]
+                if "*@" in ty:                            # v1:real*@cr0_finder -- a dummy of that host
+                    ty, hostname = ty.split("*@")
+                    tr.host_ptr[nm] = {"real": R8, "integer": INT}[ty]
+                    tr.host_of.add(hostname)
+                else:
+                    tr.host[nm] = {"real": R8, "integer": INT, "t_grt": TGRT}[ty]
             continue
         parts = spec.split(":")
         path, units = parts[0], (parts[1] if len(parts) > 1 else "")

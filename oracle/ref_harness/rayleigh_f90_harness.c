@@ -104,3 +104,58 @@ int ref_setup_grt(int n, const double* thick, const double* vp, const double* vs
   free(buf); free(lv);
   return f90_stopped;
 }
+
+/* A whole column WITHOUT a water layer, phase velocities of the fundamental Rayleigh mode -- surfmodes with modetype = 1 for a
+ * column with a low-velocity layer.  Written out here: init_grt (GRT.f90:44-91), surfmodes' assignments and dispatch
+ * (surfmodes.f90:57-99), the frequency loop of RayleighModes (:209-221) and the allmodes = 0, ifs = 0 path of SearchRayleigh
+ * (SearchRayleigh.f90:26-33,60-64,263).  Translated, i.e. the reference's own statements: setup_grt, C_Interval (N_cf, sort),
+ * init_rayleigh, FundaMode (CR0_Finder with Rayhomo, startl, SecFunSurf and below, bisecim), delete_rayleigh.
+ * par = {tolmin, tolmax, smin_min, smin_max, dcm, dc2}.  Returns ierr; -1: setup_grt STOPs; -2: no low-velocity layer
+ * (surfdisp96's column); -3: a water layer (StMode: not translated). */
+int ref_rayleigh_modes(int n, const double* thick, const double* vp, const double* vs, const double* rho, int nf, const double* freqs,
+                       double dc, const double* par, double* phase) {
+  T_GRT g;
+  T_MODES_PARA para;
+  memset(&g, 0, sizeof g);
+  memset(&para, 0, sizeof para);
+  para.modetype = 1; para.tolmin = par[0]; para.tolmax = par[1]; para.smin_min = par[2]; para.smin_max = par[3];
+  para.dc = dc; para.dcm = par[4]; para.dc2 = par[5];
+  g.nlayers = n;
+  g.smin = (double)1E-4f; g.tol = (double)1E-5f; g.dc = (double)1E-4f; g.dc2 = (double)1E-4f; g.dcm = (double)1E-4f;
+  double* buf = (double*)calloc((size_t)8 * n + 16, sizeof(double));
+  int* lv = (int*)calloc((size_t)n / 2 + 8, sizeof(int));
+  double* ccc = (double*)calloc(20008, sizeof(double));
+  g.d = buf; g.vp = buf + n; g.vs = buf + 2 * n; g.rho = buf + 3 * n; g.mu = buf + 4 * n; g.v = buf + 5 * n;
+  g.d_d1 = g.vp_d1 = g.vs_d1 = g.rho_d1 = g.mu_d1 = n; g.v_d1 = 2 * n;
+  g.d_l1 = g.vp_l1 = g.vs_l1 = g.rho_l1 = g.mu_l1 = g.v_l1 = 1;
+  g.lvls = lv; g.lvls_d1 = n / 2 + 1; g.lvls_l1 = 1;
+  g.vsy = 1.7976931348623157e308;
+  for (int i = 0; i < n; ++i) { g.d[i] = thick[i]; g.vp[i] = vp[i]; g.vs[i] = vs[i]; g.rho[i] = rho[i]; }
+  f90_stopped = 0;
+  setup_grt_(&g, &para);
+  int ierr = 0;
+  if (f90_stopped) ierr = -1;
+  else if (g.nlvls1 == 0) ierr = -2;
+  else if (g.ifs != 0) ierr = -3;
+  else {
+    double c0 = 0;
+    for (int i = 1; i <= nf; ++i) {
+      g.w = freqs[i - 1] * 2 * pi_8;                      /* m_surfmodes' pi = 3.1415926 */
+      g.tol = para.tolmin + (nf + 1 - i) * (para.tolmax - para.tolmin) / nf;
+      g.smin = para.smin_min + (i - 1) * (para.smin_max - para.smin_min) / nf;
+      g.index_a = i;
+      int index0 = 0, im1 = 0, ierr1 = 0;
+      for (int k = 0; k < 20000; ++k) ccc[k] = 0;         /* ccc = 0 */
+      c_interval_(&g, ccc, &index0, &im1);
+      init_rayleigh_(&g.nlayers);
+      double cray = c0;
+      fundamode_(&g, ccc, &index0, &im1, &cray, &ierr1);
+      delete_rayleigh_();
+      if (ierr1 == 1) { ierr = 1; break; }
+      phase[i - 1] = cray;
+      c0 = cray;
+    }
+  }
+  free(buf); free(lv); free(ccc);
+  return ierr;
+}

@@ -689,3 +689,20 @@ def grt_love_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIK
     ph = np.full(len(freqs), 100.0)
     ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data)
     return ierr, ph
+
+
+def grt_rayleigh_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIKELIHOOD):
+    """surfmodes for a Rayleigh column with a low-velocity layer and no water, phase velocities, through the TRANSLATED reference
+    (setup_grt, C_Interval, FundaMode with CR0_Finder, SecFunSurf, bisecim ...).  Returns (ierr, phase); ierr -2: no low-velocity
+    layer, -3: a water layer."""
+    global _rayleigh_f2c
+    if _rayleigh_f2c is None:
+        _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
+    vpt = C.c_void_p
+    fn = _rayleigh_f2c.ref_rayleigh_modes
+    fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int, vpt, C.c_double, vpt, vpt]
+    a = [f64(x) for x in (thick, vp, vs, rho)]
+    freqs, par = f64(freqs), f64(np.array(par))
+    ph = np.full(len(freqs), 100.0)
+    ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data)
+    return ierr, ph

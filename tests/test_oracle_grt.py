@@ -425,3 +425,43 @@ def test_love_columns_reproduce_the_reference_fixture():
         ierr, ph, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=0, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
         assert ierr == 0 and ph.tobytes() == g[k].tobytes(), (k, ph, g[k])
     assert g.shape == (5, len(FREQS)) and (g < 5).all() and (g > 2).all()
+
+
+@pytest.mark.skipif(not orc.have_rayleigh_reference(), reason="oracle/_ref/librayleigh_f2c.so not built (needs /root/reference)")
+def test_rayleigh_columns_end_to_end_equal_the_translated_reference():
+    """A whole Rayleigh column with a low-velocity layer and no water -- what `surfmodes` returns for it -- through the
+    reference's own statements: setup_grt, C_Interval, FundaMode (an internal procedure of SearchRayleigh, with CR0_Finder and its
+    internal Rayhomo), startl, SecFunSurf and bisecim are all translated; the driver adds init_grt's allocations, the
+    frequency loop of RayleighModes and the calls of SearchRayleigh's allmodes = 0, ifs = 0 path.  orc_grt_modes (libm math
+    mode) must return the same phase velocities bit for bit and the same ierr, with both parameter sets of the callers."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    cols = [MODELS[k] for k in sorted(MODELS)]
+    for k in range(60):
+        nl = int(rng.integers(4, 12))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        j = int(rng.integers(1, nl - 1))
+        vs[j] = vs[j - 1] * rng.uniform(0.7, 0.95)
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0)))
+    n = fail = 0
+    for k, (th, vp, vs, rho) in enumerate(cols):
+        par = orc.GRT_PAR_LIKELIHOOD if k % 2 else orc.GRT_PAR_MODELLING
+        e0, p0, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=1, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
+        e1, p1 = orc.grt_rayleigh_modes_reference(th, vp, vs, rho, FREQS, dc=1e-3, par=par)
+        if e1 == -2:
+            continue                          # no low-velocity layer by the reference's predicate: surfdisp96's column
+        assert e0 == e1, (vs, e0, e1)
+        m = len(FREQS) if e0 == 0 else 0
+        assert p0[:m].tobytes() == p1[:m].tobytes(), (vs, th, p0, p1)
+        n += 1
+        fail += int(e0 == 1)
+    assert n >= 25, (n, fail)
+
+
+def test_rayleigh_columns_reproduce_the_reference_fixture():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grt_rayleigh_modes_ref.npz"))["phase"]
+    cols = [c for c in love_fixture_columns() if c[2][0] > 0]          # the water-free ones
+    for k, (th, vp, vs, rho, par) in enumerate(cols):
+        ierr, ph, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=1, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
+        assert ierr == 0 and ph.tobytes() == g[k].tobytes(), (k, ph, g[k])
+    assert g.shape == (4, len(FREQS)) and (g < 5).all() and (g > 2).all()

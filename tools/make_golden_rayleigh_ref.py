@@ -16,3 +16,15 @@ vals = np.array([orc.grt_rayleigh_secfun_reference(th, vp, vs, rho, f, c)[:2] fo
 path = os.path.join(ROOT, "tests", "golden", "grt_rayleigh_secfun_ref.npz")
 np.savez_compressed(path, values=vals)
 print("wrote", path, vals.shape, os.path.getsize(path), "bytes", "NaN:", int(np.isnan(vals).sum()))
+
+# whole water-free columns: what surfmodes returns (phase velocities of the fundamental Rayleigh mode at example1's frequencies)
+from test_oracle_grt import love_fixture_columns, FREQS                # noqa: E402
+out = []
+for th, vp, vs, rho, par in love_fixture_columns():
+    if vs[0] > 0:
+        ierr, ph = orc.grt_rayleigh_modes_reference(th, vp, vs, rho, FREQS, dc=1e-3, par=par)
+        assert ierr == 0
+        out.append(ph)
+path2 = os.path.join(ROOT, "tests", "golden", "grt_rayleigh_modes_ref.npz")
+np.savez_compressed(path2, phase=np.array(out))
+print("wrote", path2, np.array(out).shape)
