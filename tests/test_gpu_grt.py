@@ -203,3 +203,30 @@ def test_grt_many_layers_and_sixty_frequencies(mct):
                                         math_mode=orc.PORTABLE, preset=opts.preset)
         assert ie[0] == ierr and np.array_equal(ph[0], p), raylov
         assert (p < 99).sum() >= 10
+
+
+def test_grt_device_against_the_reference_derived_fixtures_directly(mct):
+    """The device against numbers that come from the reference's own statements (tests/golden/grt_{love,rayleigh}_modes_ref.npz:
+    whole columns through the mechanically translated setup_grt / C_Interval / FundaMode / secular functions / bisecim, libm
+    math) -- without the restatement in between.  The device computes with the portable sin / cos / exp, so the gate is the
+    north-star tolerance of 1e-5 km/s; what is observed is some 1e-15."""
+    import os
+    from test_oracle_grt import love_fixture_columns
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    worst = 0.0
+    for modetype, name in ((0, "grt_love_modes_ref.npz"), (1, "grt_rayleigh_modes_ref.npz")):
+        g = np.load(os.path.join(gold, name))["phase"]
+        cols = [c for c in love_fixture_columns() if modetype == 0 or c[2][0] > 0]
+        assert len(cols) == len(g)
+        for k, (th, vp, vs, rho, par) in enumerate(cols):
+            (t, p, s, r), offs = _batch([(th, vp, vs, rho)])
+            mct.set_grt(True, par)
+            try:
+                ph, gr, ie, rc = mct.surfmodes_batch(t, p, s, r, offs, FREQS, disp_opts(raylov=modetype, phaseGroup=0, nmodes=0))
+            finally:
+                mct.set_grt(False)
+            assert rc == 0 and ie[0] == 0, (modetype, k, rc, ie)
+            d = float(np.abs(ph[0] - g[k]).max())
+            assert d <= 1e-5, (modetype, k, d)
+            worst = max(worst, d)
+    assert worst < 1e-9          # (tighter than required: report a drift long before it matters)
