@@ -159,3 +159,24 @@ int ref_rayleigh_modes(int n, const double* thick, const double* vp, const doubl
   free(buf); free(lv); free(ccc);
   return ierr;
 }
+
+/* the secular function of a column WITH a water layer on top (ifs = 1): startl + SecFunSt(ifs, c, GRT, Imf) -- Stoneley, propdn_f,
+ * EinvE_f, propup, EinvE, det3 all translated */
+int ref_rayleigh_secfunst(int n, const double* d, const double* vp, const double* vs, const double* rho, const double* mu, double mu0,
+                          int ifs, int lvlast, double w, double c, double* value, double* imf, int* ll_out) {
+  T_GRT g;
+  memset(&g, 0, sizeof g);
+  g.nlayers = n;
+  g.d = (double*)d; g.d_d1 = n; g.d_l1 = 1;
+  g.vp = (double*)vp; g.vp_d1 = n; g.vp_l1 = 1;
+  g.vs = (double*)vs; g.vs_d1 = n; g.vs_l1 = 1;
+  g.rho = (double*)rho; g.rho_d1 = n; g.rho_l1 = 1;
+  g.mu = (double*)mu; g.mu_d1 = n; g.mu_l1 = 1;
+  g.mu0 = mu0; g.ifs = ifs; g.lvlast = lvlast; g.w = w;
+  init_rayleigh_(&n);
+  startl_(&c, &g);
+  *ll_out = g.ll;
+  *value = secfunst_(&ifs, &c, &g, imf);
+  delete_rayleigh_();
+  return 0;
+}

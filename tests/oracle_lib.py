@@ -706,3 +706,22 @@ def grt_rayleigh_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR
     ph = np.full(len(freqs), 100.0)
     ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data)
     return ierr, ph
+
+
+def grt_stoneley_secfun_reference(thick, vp, vs, rho, freq, c):
+    """startl + SecFunSt(ifs, c, GRT, Imf) of the TRANSLATED Rayleigh.f90 (a column with a water layer on top) on the T_GRT the
+    restatement's setup_grt builds.  Returns (value, imf, ll of the translated startl, ll of the restatement)."""
+    global _rayleigh_f2c
+    if _rayleigh_f2c is None:
+        _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
+    vpt = C.c_void_p
+    n, d, p, v, mu, ints, w = _grt_state(thick, vp, vs, rho, freq, 1, c)
+    assert ints[0] == 1, "no water layer: SecFunSurf, not SecFunSt"
+    mu0 = grt_setup("port", thick, vp, vs, rho, 1)[5][0]
+    r = f64(rho)
+    fn = _rayleigh_f2c.ref_rayleigh_secfunst
+    fn.argtypes = [C.c_int] + [vpt] * 5 + [C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, vpt, vpt, vpt]
+    val, imf, ll = C.c_double(0), C.c_double(0), C.c_int(0)
+    fn(n, d.ctypes.data, p.ctypes.data, v.ctypes.data, r.ctypes.data, mu.ctypes.data, float(mu0), int(ints[0]), int(ints[2]), w, c,
+       C.byref(val), C.byref(imf), C.byref(ll))
+    return val.value, imf.value, ll.value, int(ints[1])

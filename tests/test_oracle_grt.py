@@ -465,3 +465,27 @@ def test_rayleigh_columns_reproduce_the_reference_fixture():
         ierr, ph, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=1, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
         assert ierr == 0 and ph.tobytes() == g[k].tobytes(), (k, ph, g[k])
     assert g.shape == (4, len(FREQS)) and (g < 5).all() and (g > 2).all()
+
+
+@pytest.mark.skipif(not orc.have_rayleigh_reference(), reason="oracle/_ref/librayleigh_f2c.so not built (needs /root/reference)")
+def test_stoneley_secular_function_equals_the_translated_reference():
+    """Columns with a water layer on top: SecFunSt over Stoneley, propdn_f, EinvE_f, propup, EinvE and det3, and startl, as the
+    reference's own statements compute them -- value, Imf and ll bit for bit (the sign of an exact zero Imf aside)."""
+    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    cols = [crust([3.1, 2.7, 3.5, 3.0, 4.0, 4.5], [1.0, 2.0, 2.5, 3.0, 5.0, 0.0], water=1.2)]
+    for _ in range(30):
+        nl = int(rng.integers(4, 12))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        k = int(rng.integers(1, nl - 1))
+        vs[k] = vs[k - 1] * rng.uniform(0.7, 0.95)
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0), water=float(rng.uniform(0.2, 3.0))))
+    n = 0
+    for th, vp, vs, rho in cols:
+        for f in FREQS[::2]:
+            for c in rng.uniform(0.7, 1.05 * vs.max(), 20):
+                rc, re, im_ = orc.grt_secfun(th, vp, vs, rho, float(f), 1, float(c), math_mode=orc.LIBM)
+                assert rc == 0
+                v, imf, ll_ref, ll = orc.grt_stoneley_secfun_reference(th, vp, vs, rho, float(f), float(c))
+                assert ll_ref == ll and _bits_equal(re, v) and _bits_equal(im_, imf), (vs, th, f, c, (re, im_), (v, imf))
+                n += 1
+    assert n > 3000
