@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """oracle/f90toc_love.py -- mechanical Fortran 90 -> C translation of the reference's generalized R/T secular functions:
 surfmodes/Love.f90 (init_love, delete_love, EinvE_L, propdn_L, propup_L, SecFuns_L) and the units of surfmodes/Rayleigh.f90 a
-column without a water layer reaches (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup), bisecim and sort
+column reaches from `surfmodes` (inv2, init_rayleigh, delete_rayleigh, startl, SecFunSurf, EinvE, propup; with a water layer
+SecFunSt, Stoneley, EinvE_f, propdn_f), bisecim, det3 and sort
 of util.f90, C_Interval / N_cf (C_interval.f90), C_Interval_L / N_cf_L (C_interval_L.f90), setup_grt (surfmodes.f90), the internal procedures FundaMode and check of
-SearchLove.f90, FundaMode of SearchRayleigh.f90 and CR0_Finder with its internal Rayhomo, with `csq`, the
+SearchLove.f90, FundaMode and StMode of SearchRayleigh.f90, CR0_Finder with its internal Rayhomo and St_Finder with its internal getSt, with
+`csq`, the
 parameters and the derived type T_GRT of surfmodes/GRT.f90.
 
 TEST INFRASTRUCTURE, in the line of oracle/f77toc.py and oracle/f90toc.py: the sources are read where they lie, nothing is
@@ -592,8 +594,8 @@ class UnitG(Unit):
         if t == "cycle":
             self.emit("continue;")
             return
-        if t == "stop":
-            self.emit("f90_stopped = 1; return;")
+        if t.startswith("stop"):                         # STOP, STOP 'message'
+            self.emit("f90_stopped = 1; return" + (";" if self.kind == "subroutine" or self.result_shape else f" {self.name}_result;"))
             return
         m = re.fullmatch(r"([a-z][a-z0-9_]*)\(([^():,]+):([^():,]+)\)=([a-z][a-z0-9_]*)\(([^():,]+):([^():,]+)\)", t)
         if m and self.bounds(m.group(1)) is not None and len(self.bounds(m.group(1))) == 1:
@@ -797,6 +799,10 @@ class TranslatorG:
         o.append("")
         for u in self.units:
             o.append(proto(u) + " {")
+            if u.name in self.host_of:
+                for a in u.args:
+                    if a in self.host and self.host[a] in STRUCT_OF:
+                        o.append(f"  {a} = ({CT[self.host[a]]}*){a}_a; /* the file-scope pointer the internal procedures read */")
             for a in u.args:
                 o.append(f"  {CT[u.vtype(a)]}* {a} = ({CT[u.vtype(a)]}*){a}_a;")
             if u.name in self.host_of:
@@ -846,6 +852,10 @@ def main():
                 if "*@" in ty:                            # v1:real*@cr0_finder -- a dummy of that host
                     ty, hostname = ty.split("*@")
                     tr.host_ptr[nm] = {"real": R8, "integer": INT}[ty]
+                    tr.host_of.add(hostname)
+                elif "@" in ty:                           # grt:t_grt@st_finder -- a struct dummy of that host
+                    ty, hostname = ty.split("@")
+                    tr.host[nm] = {"t_grt": TGRT}[ty]
                     tr.host_of.add(hostname)
                 else:
                     tr.host[nm] = {"real": R8, "integer": INT, "t_grt": TGRT}[ty]

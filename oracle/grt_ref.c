@@ -10,11 +10,11 @@
  * Only what `surfmodes` reaches is restated (allmodes = 0: the fundamental / Stoneley mode per frequency);
  * `surfmmodes` prints "not supported yet" for such columns (surfmodes.f90:153,165).
  *
- * PARITY STATUS: Love, and Rayleigh for columns without a water layer: pinned end to end -- orc_grt_modes returns the phase
- * velocities of the reference's own setup_grt, C_Interval[_L], FundaMode (+ CR0_Finder), startl, SecFunSurf / SecFuns_L, bisecim,
- * translated mechanically by oracle/f90toc_love.py, bit for bit; each of those routines is also compared alone.
- * "parity unpinned": the water-layer path -- StMode, St_Finder of SearchRayleigh.f90, SecFunSt, Stoneley, propdn_f, up_fs, dn_fs,
- * LUCC, det3.  tests/test_oracle_grt.py.  The reference ships no test, golden value or compiled object for these files and
+ * PARITY STATUS: pinned end to end -- orc_grt_modes returns, bit for bit, the phase velocities of the reference's own setup_grt,
+ * C_Interval[_L], FundaMode (+ CR0_Finder) / StMode (+ St_Finder), startl, SecFunSurf / SecFunSt / SecFuns_L and bisecim,
+ * translated mechanically by oracle/f90toc_love.py, for Love and for Rayleigh with and without a water layer; each routine
+ * is also compared alone (tests/test_oracle_grt.py).  Restated only: CalGroup's quotient and the drivers' loops.
+ * The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent
  * 50-digit propagator-matrix secular function and are the lowest mode) and by line-by-line reading; the complex

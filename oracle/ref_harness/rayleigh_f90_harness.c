@@ -6,8 +6,10 @@
 #include RAYLEIGH_F2C_SOURCE
 #include <string.h>
 
-/* the dummy procedure of bisecim: SearchRayleigh passes SecFunSurf for a column without water (SearchRayleigh.f90 FundaMode) */
-static double f_(void* ilay, void* c, void* grt, void* imf) { return secfunsurf_(ilay, c, grt, imf); }
+/* the dummy procedure of bisecim: SearchRayleigh passes SecFunSurf for a column without water (FundaMode), SecFunSt for one with a
+ * water layer on top (StMode) */
+static __thread int g_f_st;
+static double f_(void* ilay, void* c, void* grt, void* imf) { return g_f_st ? secfunst_(ilay, c, grt, imf) : secfunsurf_(ilay, c, grt, imf); }
 
 int ref_rayleigh_secfunsurf(int n, const double* d, const double* vp, const double* vs, const double* mu, int lvlast, double w, double c,
                             double* value, double* imf, int* ll_out) {
@@ -110,8 +112,10 @@ int ref_setup_grt(int n, const double* thick, const double* vp, const double* vs
  * (surfmodes.f90:57-99), the frequency loop of RayleighModes (:209-221) and the allmodes = 0, ifs = 0 path of SearchRayleigh
  * (SearchRayleigh.f90:26-33,60-64,263).  Translated, i.e. the reference's own statements: setup_grt, C_Interval (N_cf, sort),
  * init_rayleigh, FundaMode (CR0_Finder with Rayhomo, startl, SecFunSurf and below, bisecim), delete_rayleigh.
- * par = {tolmin, tolmax, smin_min, smin_max, dcm, dc2}.  Returns ierr; -1: setup_grt STOPs; -2: no low-velocity layer
- * (surfdisp96's column); -3: a water layer (StMode: not translated). */
+ * With a water layer on top (ifs = 1): St_Finder (with its internal getSt) when there is no previous root, then StMode
+ * (:65-68), over SecFunSt, Stoneley, propdn_f, EinvE_f, det3 -- translated as well.
+ * par = {tolmin, tolmax, smin_min, smin_max, dcm, dc2}.  Returns ierr; -1: setup_grt or St_Finder STOPs; -2: no low-velocity
+ * layer (surfdisp96's column). */
 int ref_rayleigh_modes(int n, const double* thick, const double* vp, const double* vs, const double* rho, int nf, const double* freqs,
                        double dc, const double* par, double* phase) {
   T_GRT g;
@@ -136,9 +140,9 @@ int ref_rayleigh_modes(int n, const double* thick, const double* vp, const doubl
   int ierr = 0;
   if (f90_stopped) ierr = -1;
   else if (g.nlvls1 == 0) ierr = -2;
-  else if (g.ifs != 0) ierr = -3;
   else {
     double c0 = 0;
+    g_f_st = g.ifs != 0;
     for (int i = 1; i <= nf; ++i) {
       g.w = freqs[i - 1] * 2 * pi_8;                      /* m_surfmodes' pi = 3.1415926 */
       g.tol = para.tolmin + (nf + 1 - i) * (para.tolmax - para.tolmin) / nf;
@@ -149,7 +153,12 @@ int ref_rayleigh_modes(int n, const double* thick, const double* vp, const doubl
       c_interval_(&g, ccc, &index0, &im1);
       init_rayleigh_(&g.nlayers);
       double cray = c0;
-      fundamode_(&g, ccc, &index0, &im1, &cray, &ierr1);
+      if (g.ifs == 0) fundamode_(&g, ccc, &index0, &im1, &cray, &ierr1);
+      else {
+        if (cray <= 0) st_finder_(&g.ifs, &g, &cray);
+        if (f90_stopped) { delete_rayleigh_(); ierr = -1; break; }
+        stmode_(&g, ccc, &index0, &im1, &cray, &ierr1);
+      }
       delete_rayleigh_();
       if (ierr1 == 1) { ierr = 1; break; }
       phase[i - 1] = cray;

@@ -429,10 +429,11 @@ def test_love_columns_reproduce_the_reference_fixture():
 
 @pytest.mark.skipif(not orc.have_rayleigh_reference(), reason="oracle/_ref/librayleigh_f2c.so not built (needs /root/reference)")
 def test_rayleigh_columns_end_to_end_equal_the_translated_reference():
-    """A whole Rayleigh column with a low-velocity layer and no water -- what `surfmodes` returns for it -- through the
-    reference's own statements: setup_grt, C_Interval, FundaMode (an internal procedure of SearchRayleigh, with CR0_Finder and its
-    internal Rayhomo), startl, SecFunSurf and bisecim are all translated; the driver adds init_grt's allocations, the
-    frequency loop of RayleighModes and the calls of SearchRayleigh's allmodes = 0, ifs = 0 path.  orc_grt_modes (libm math
+    """A whole Rayleigh column with a low-velocity layer -- what `surfmodes` returns for it -- through the reference's own
+    statements: setup_grt, C_Interval, FundaMode (an internal procedure of SearchRayleigh, with CR0_Finder and its internal
+    Rayhomo), startl, SecFunSurf and bisecim; with a water layer on top St_Finder (with getSt), StMode, SecFunSt, Stoneley,
+    propdn_f, EinvE_f and det3 -- all translated; the driver adds init_grt's allocations, the frequency loop of RayleighModes
+    and the calls of SearchRayleigh's allmodes = 0 path.  orc_grt_modes (libm math
     mode) must return the same phase velocities bit for bit and the same ierr, with both parameter sets of the callers."""
     rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
     cols = [MODELS[k] for k in sorted(MODELS)]
@@ -441,8 +442,8 @@ def test_rayleigh_columns_end_to_end_equal_the_translated_reference():
         vs = np.sort(rng.uniform(2.4, 4.6, nl))
         j = int(rng.integers(1, nl - 1))
         vs[j] = vs[j - 1] * rng.uniform(0.7, 0.95)
-        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0)))
-    n = fail = 0
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0), water=float(rng.uniform(0.3, 2.5)) if k % 3 == 0 else None))
+    n = fail = water = 0
     for k, (th, vp, vs, rho) in enumerate(cols):
         par = orc.GRT_PAR_LIKELIHOOD if k % 2 else orc.GRT_PAR_MODELLING
         e0, p0, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=1, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
@@ -454,17 +455,18 @@ def test_rayleigh_columns_end_to_end_equal_the_translated_reference():
         assert p0[:m].tobytes() == p1[:m].tobytes(), (vs, th, p0, p1)
         n += 1
         fail += int(e0 == 1)
-    assert n >= 25, (n, fail)
+        water += int(vs[0] == 0)
+    assert n >= 25 and water >= 6, (n, fail, water)
 
 
 def test_rayleigh_columns_reproduce_the_reference_fixture():
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grt_rayleigh_modes_ref.npz"))["phase"]
-    cols = [c for c in love_fixture_columns() if c[2][0] > 0]          # the water-free ones
+    cols = list(love_fixture_columns()) + [(*crust([3.2, 3.6, 2.9, 3.8, 4.5], [2.0, 3.0, 4.0, 6.0, 0.0], water=0.6), orc.GRT_PAR_MODELLING)]
     for k, (th, vp, vs, rho, par) in enumerate(cols):
         ierr, ph, _, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=1, phaseGroup=0, dc=1e-3, par=par, math_mode=orc.LIBM)
         assert ierr == 0 and ph.tobytes() == g[k].tobytes(), (k, ph, g[k])
-    assert g.shape == (4, len(FREQS)) and (g < 5).all() and (g > 2).all()
+    assert g.shape == (6, len(FREQS)) and (g < 5).all() and (g > 1).all()
 
 
 @pytest.mark.skipif(not orc.have_rayleigh_reference(), reason="oracle/_ref/librayleigh_f2c.so not built (needs /root/reference)")

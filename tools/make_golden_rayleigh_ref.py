@@ -17,14 +17,14 @@ path = os.path.join(ROOT, "tests", "golden", "grt_rayleigh_secfun_ref.npz")
 np.savez_compressed(path, values=vals)
 print("wrote", path, vals.shape, os.path.getsize(path), "bytes", "NaN:", int(np.isnan(vals).sum()))
 
-# whole water-free columns: what surfmodes returns (phase velocities of the fundamental Rayleigh mode at example1's frequencies)
-from test_oracle_grt import love_fixture_columns, FREQS                # noqa: E402
+# whole columns: what surfmodes returns (phase velocities of the fundamental Rayleigh mode at example1's frequencies)
+from test_oracle_grt import love_fixture_columns, FREQS, crust         # noqa: E402
 out = []
-for th, vp, vs, rho, par in love_fixture_columns():
-    if vs[0] > 0:
-        ierr, ph = orc.grt_rayleigh_modes_reference(th, vp, vs, rho, FREQS, dc=1e-3, par=par)
-        assert ierr == 0
-        out.append(ph)
+cols = list(love_fixture_columns()) + [(*crust([3.2, 3.6, 2.9, 3.8, 4.5], [2.0, 3.0, 4.0, 6.0, 0.0], water=0.6), orc.GRT_PAR_MODELLING)]
+for th, vp, vs, rho, par in cols:                                       # two of them with a water layer on top (Stoneley mode)
+    ierr, ph = orc.grt_rayleigh_modes_reference(th, vp, vs, rho, FREQS, dc=1e-3, par=par)
+    assert ierr == 0
+    out.append(ph)
 path2 = os.path.join(ROOT, "tests", "golden", "grt_rayleigh_modes_ref.npz")
 np.savez_compressed(path2, phase=np.array(out))
 print("wrote", path2, np.array(out).shape)
