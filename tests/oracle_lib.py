@@ -725,3 +725,15 @@ def grt_stoneley_secfun_reference(thick, vp, vs, rho, freq, c):
     fn(n, d.ctypes.data, p.ctypes.data, v.ctypes.data, r.ctypes.data, mu.ctypes.data, float(mu0), int(ints[0]), int(ints[2]), w, c,
        C.byref(val), C.byref(imf), C.byref(ll))
     return val.value, imf.value, ll.value, int(ints[1])
+
+
+def live_seed(tag):
+    """Seed of a live comparison against a translated reference: fixed per test by default (a CI run must not depend on the
+    draw); MCT_TEST_SEED=random draws a fresh one (what the development soak used), MCT_TEST_SEED=<int> replays one."""
+    import zlib
+    v = os.environ.get("MCT_TEST_SEED", "")
+    if v == "random":
+        return int.from_bytes(os.urandom(4), "little")
+    if v:
+        return int(v) + zlib.crc32(tag.encode()) % 1000
+    return zlib.crc32(tag.encode())

@@ -106,7 +106,7 @@ def test_restatement_reproduces_the_reference_fixtures_bit_for_bit():
 
 @pytest.mark.skipif(not orc.have_fm2d_reference(), reason="oracle/_ref/libfm2d_ttime_f2c.so not built (needs /root/reference)")
 def test_restatement_equals_the_translated_reference_on_fresh_media():
-    seed = int.from_bytes(os.urandom(4), "little")
+    seed = orc.live_seed("test_restatement_equals_the_translated_reference_on_fresh_media")
     n = nodes = 0
     for case in cases(seed, 120):
         ref = run_case("reference", case)
@@ -131,7 +131,7 @@ needs_ref = pytest.mark.skipif(not orc.have_fm2d_reference(), reason="oracle/_re
 
 @needs_ref
 def test_gridder_and_bsplrefine_equal_the_translated_reference():
-    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_gridder_and_bsplrefine_equal_the_translated_reference"))
     for k in range(60):
         nvx, nvz = int(rng.integers(2, 14)), int(rng.integers(2, 12))
         gdx, gdz = int(rng.integers(1, 5)), int(rng.integers(1, 5))
@@ -148,7 +148,7 @@ def test_gridder_and_bsplrefine_equal_the_translated_reference():
 
 @needs_ref
 def test_srtimes_equals_the_translated_reference():
-    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_srtimes_equals_the_translated_reference"))
     n_near = 0
     for k in range(80):
         nnx, nnz = int(rng.integers(4, 30)), int(rng.integers(4, 30))
@@ -245,7 +245,7 @@ def test_travel_times_of_whole_calls_equal_the_translated_modrays():
     and the whole field of every marched source, sources whose march dies and return the previous source's field included
     (the driver keeps ONE ttn array over the source loop, as modrays does); tiny models where the refined grid outgrows the
     propagation grid and modrays reallocates its arrays; source-grid refinement on and off; dicing 1..3."""
-    seed = int.from_bytes(os.urandom(4), "little")
+    seed = orc.live_seed("test_travel_times_of_whole_calls_equal_the_translated_modrays")
     rng = np.random.default_rng(seed)
     n = stale = big = overrun = 0
     for k in range(90):
@@ -337,7 +337,7 @@ def test_rays_of_whole_calls_equal_the_translated_modrays():
     T_RAY container replaced by the driver's store).  Every ray point, the point counts, the crazy-ray count and the receiver
     times of orc_fm2d_rays must equal the translation's.  Source-grid refinement on, as shipped: without it the Fortran reads
     a variable it never assigned (ipzr) and divides 0 by 0 next to the source -- outcomes the restatement flags instead."""
-    seed = int.from_bytes(os.urandom(4), "little")
+    seed = orc.live_seed("test_rays_of_whole_calls_equal_the_translated_modrays")
     rng = np.random.default_rng(seed)
     n = rays = crazies = jumps = 0
     for k in range(110):

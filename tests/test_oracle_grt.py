@@ -185,7 +185,7 @@ def test_love_secular_function_equals_the_translated_reference():
     BIT FOR BIT -- value and Imf -- over random low-velocity columns, with and without a water layer, at every frequency and
     over the whole range of trial velocities the search scans (evanescent and propagating layers, the deep-layer cut-off of
     startl).  The searches around it (SearchLove, C_Interval_L, bisecim) and the Rayleigh functions stay "parity unpinned"."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_love_secular_function_equals_the_translated_reference"))
     n = 0
     cols = [MODELS[k] for k in sorted(MODELS)]
     for _ in range(40):
@@ -243,7 +243,7 @@ def test_rayleigh_surface_secular_function_equals_the_translated_reference():
     sections, array-valued functions scalarised; complex arithmetic under gcc's Fortran rules).  Bit for bit: value, Imf, ll.
     What stays "parity unpinned": the water-layer functions (SecFunSt, Stoneley, propdn_f, up_fs, dn_fs: LUCC, det3) and the
     searches (SearchRayleigh, C_Interval, bisecim)."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_rayleigh_surface_secular_function_equals_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for _ in range(40):
         nl = int(rng.integers(4, 14))
@@ -294,7 +294,7 @@ def test_root_refinement_equals_the_translated_reference(modetype):
     as the reference's own statements, driving the reference's own secular functions, against the restatement's -- the same
     brackets a scan would hand over (neighbouring trial velocities with a sign change), the same smin / tol range the callers
     set.  Root, iq, and the end values: bit for bit."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_root_refinement_equals_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for _ in range(12):
         nl = int(rng.integers(4, 12))
@@ -324,7 +324,7 @@ def test_trial_velocity_lists_equal_the_translated_reference(modetype):
     """C_Interval / C_Interval_L (with N_cf / N_cf_L and util.f90's sort) -- the list of trial phase velocities every frequency's
     scan walks, and im1 -- as the reference's own statements build them, against the restatement's: every entry bit for bit,
     at low frequencies (the dense fill) and high ones (the N_cf-driven subdivision, the layer resonances, two midpoint passes)."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_trial_velocity_lists_equal_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for _ in range(10):
         nl = int(rng.integers(4, 12))
@@ -354,7 +354,7 @@ def test_setup_grt_equals_the_translated_reference(modetype):
     rigidities, the sorted velocity list, the low-velocity layers and their order, ifs / nlvl1 / nlvls1 / lvlast / L1, vsy / vs1 /
     vsm / vss1 -- everything the searches read -- against the restatement's, with and without a water layer, one and several
     low-velocity zones."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_setup_grt_equals_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for k in range(60):
         nl = int(rng.integers(3, 16))
@@ -388,7 +388,7 @@ def test_love_columns_end_to_end_equal_the_translated_reference():
     the driver adds init_grt's allocations, the frequency loop of LoveModes and the five calls of SearchLove's allmodes = 0
     path.  orc_grt_modes (libm math mode, what every GPU test of the branch is held to in portable mode) must return the same
     phase velocities bit for bit and the same ierr, with both parameter sets the reference's callers use."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_love_columns_end_to_end_equal_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for k in range(60):
         nl = int(rng.integers(4, 12))
@@ -435,7 +435,7 @@ def test_rayleigh_columns_end_to_end_equal_the_translated_reference():
     propdn_f, EinvE_f and det3 -- all translated; the driver adds init_grt's allocations, the frequency loop of RayleighModes
     and the calls of SearchRayleigh's allmodes = 0 path.  orc_grt_modes (libm math
     mode) must return the same phase velocities bit for bit and the same ierr, with both parameter sets of the callers."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_rayleigh_columns_end_to_end_equal_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for k in range(60):
         nl = int(rng.integers(4, 12))
@@ -473,7 +473,7 @@ def test_rayleigh_columns_reproduce_the_reference_fixture():
 def test_stoneley_secular_function_equals_the_translated_reference():
     """Columns with a water layer on top: SecFunSt over Stoneley, propdn_f, EinvE_f, propup, EinvE and det3, and startl, as the
     reference's own statements compute them -- value, Imf and ll bit for bit (the sign of an exact zero Imf aside)."""
-    rng = np.random.default_rng(int.from_bytes(__import__("os").urandom(4), "little"))
+    rng = np.random.default_rng(orc.live_seed("test_stoneley_secular_function_equals_the_translated_reference"))
     cols = [crust([3.1, 2.7, 3.5, 3.0, 4.0, 4.5], [1.0, 2.0, 2.5, 3.0, 5.0, 0.0], water=1.2)]
     for _ in range(30):
         nl = int(rng.integers(4, 12))
