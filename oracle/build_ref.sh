@@ -39,12 +39,12 @@ fi
 if [ -f "$REF/surfmodes/Love.f90" ] && [ -f "$REF/surfmodes/GRT.f90" ]; then
   mkdir -p "$OUT"
   python "$HERE/f90toc_love.py" "$REF/surfmodes/GRT.f90" "$REF/surfmodes/Love.f90" "$REF/surfmodes/util.f90:bisecim,sort" "$REF/surfmodes/C_interval_L.f90" \
-      "$REF/surfmodes/Rayleigh.f90:startl:nohdr" "$REF/surfmodes/surfmodes.f90:setup_grt" host=kt:real,c:real,grt:t_grt \
+      "$REF/surfmodes/Rayleigh.f90:startl:nohdr" "$REF/surfmodes/surfmodes.f90:setup_grt,calgroup" host=kt:real,c:real,grt:t_grt \
       "$REF/surfmodes/SearchLove.f90:check,fundamode" "$OUT/love_f2c.c"
   gcc -O2 -fPIC -std=gnu11 -fcx-fortran-rules -ffp-contract=off -fno-fast-math -shared -DLOVE_F2C_SOURCE="\"$OUT/love_f2c.c\"" \
       -o "$OUT/liblove_f2c.so" "$HERE/ref_harness/love_f90_harness.c" -lm
   echo "build_ref: built $OUT/liblove_f2c.so from $REF/surfmodes/Love.f90 + bisecim, sort of util.f90 + the C_Interval file"
-  python "$HERE/f90toc_love.py" "$REF/surfmodes/GRT.f90" "$REF/surfmodes/Rayleigh.f90:inv2,init_rayleigh,delete_rayleigh,startl,secfunsurf,einve,propup,secfunst,stoneley,einve_f,propdn_f" "$REF/surfmodes/util.f90:bisecim,sort,det3" "$REF/surfmodes/C_interval.f90" "$REF/surfmodes/surfmodes.f90:setup_grt" \
+  python "$HERE/f90toc_love.py" "$REF/surfmodes/GRT.f90" "$REF/surfmodes/Rayleigh.f90:inv2,init_rayleigh,delete_rayleigh,startl,secfunsurf,einve,propup,secfunst,stoneley,einve_f,propdn_f" "$REF/surfmodes/util.f90:bisecim,sort,det3" "$REF/surfmodes/C_interval.f90" "$REF/surfmodes/surfmodes.f90:setup_grt,calgroup" \
       "host=iq:integer,j:integer,ip:integer,ilay:integer,k1:real,k2:real,f1:real,f2:real,kt:real,c:real,imf:real,r:real,dr:real,v1:real*@cr0_finder,v2:real*@cr0_finder,grt:t_grt@st_finder" \
       "$REF/surfmodes/SearchRayleigh.f90:fundamode,stmode,cr0_finder,rayhomo,st_finder,getst" "$OUT/rayleigh_f2c.c"
   gcc -O2 -fPIC -std=gnu11 -fcx-fortran-rules -ffp-contract=off -fno-fast-math -shared -DRAYLEIGH_F2C_SOURCE="\"$OUT/rayleigh_f2c.c\"" \

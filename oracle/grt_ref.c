@@ -13,7 +13,7 @@
  * PARITY STATUS: pinned end to end -- orc_grt_modes returns, bit for bit, the phase velocities of the reference's own setup_grt,
  * C_Interval[_L], FundaMode (+ CR0_Finder) / StMode (+ St_Finder), startl, SecFunSurf / SecFunSt / SecFuns_L and bisecim,
  * translated mechanically by oracle/f90toc_love.py, for Love and for Rayleigh with and without a water layer; each routine
- * is also compared alone (tests/test_oracle_grt.py).  Restated only: CalGroup's quotient and the drivers' loops.
+ * is also compared alone; group velocities (second search + CalGroup, translated) likewise (tests/test_oracle_grt.py).
  * The reference ships no test, golden value or compiled object for these files and
  * no Fortran compiler exists in this image (oracle/f77toc.py translates FORTRAN 77, not this Fortran 90).  The
  * restatement is pinned by physics only (tests/test_oracle_grt.py: the roots it returns are zeros of an independent

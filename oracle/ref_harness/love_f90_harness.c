@@ -72,7 +72,7 @@ int ref_love_cinterval(int n, const double* d, const double* vp, const double* v
  * bisecim), delete_love.  par = {tolmin, tolmax, smin_min, smin_max, dcm, dc2}; dc as surfmodes' caller sets it.
  * Returns ierr; -1 when setup_grt STOPs; -2 when the column has no low-velocity layer (surfdisp96's case). */
 int ref_love_modes(int n, const double* thick, const double* vp, const double* vs, const double* rho, int nf, const double* freqs, double dc,
-                   const double* par, double* phase) {
+                   const double* par, double* phase, double* group /* or null: phase velocities only */) {
   T_GRT g;
   T_MODES_PARA para;
   memset(&g, 0, sizeof g);
@@ -113,6 +113,19 @@ int ref_love_modes(int n, const double* thick, const double* vp, const double* v
       if (ierr1 == 1) { ierr = 1; break; }
       phase[i - 1] = cray;
       c0 = cray;
+      if (group) {                                        /* paras%phaseGroup == 1 (LoveModes :282-290): the search again at freq + dh */
+        double dh = (double)0.005f, freq0 = freqs[i - 1] + dh, f = freqs[i - 1];
+        g.w = freq0 * 2 * pi_8;
+        index0 = 0; im1 = 0;
+        for (int k = 0; k < 20000; ++k) ccc[k] = 0;
+        c_interval_l_(&g, ccc, &index0, &im1);
+        init_love_(&g.nlayers);
+        double cp0 = c0;
+        fundamode_(&g, ccc, &index0, &cp0, &ierr);
+        delete_love_();
+        if (ierr == 1) break;
+        calgroup_(&phase[i - 1], &cp0, &f, &dh, &group[i - 1]);
+      }
     }
   }
   free(buf); free(lv); free(ccc);

@@ -117,7 +117,7 @@ int ref_setup_grt(int n, const double* thick, const double* vp, const double* vs
  * par = {tolmin, tolmax, smin_min, smin_max, dcm, dc2}.  Returns ierr; -1: setup_grt or St_Finder STOPs; -2: no low-velocity
  * layer (surfdisp96's column). */
 int ref_rayleigh_modes(int n, const double* thick, const double* vp, const double* vs, const double* rho, int nf, const double* freqs,
-                       double dc, const double* par, double* phase) {
+                       double dc, const double* par, double* phase, double* group /* or null: phase velocities only */) {
   T_GRT g;
   T_MODES_PARA para;
   memset(&g, 0, sizeof g);
@@ -163,6 +163,23 @@ int ref_rayleigh_modes(int n, const double* thick, const double* vp, const doubl
       if (ierr1 == 1) { ierr = 1; break; }
       phase[i - 1] = cray;
       c0 = cray;
+      if (group) {                                        /* paras%phaseGroup == 1 (RayleighModes :226-234): the search again at freq + dh */
+        double dh = (double)0.005f, freq0 = freqs[i - 1] + dh, f = freqs[i - 1];
+        g.w = freq0 * 2 * pi_8;
+        index0 = 0; im1 = 0;
+        for (int k = 0; k < 20000; ++k) ccc[k] = 0;
+        c_interval_(&g, ccc, &index0, &im1);
+        init_rayleigh_(&g.nlayers);
+        double cp0 = c0;
+        if (g.ifs == 0) fundamode_(&g, ccc, &index0, &im1, &cp0, &ierr);
+        else {
+          if (cp0 <= 0) st_finder_(&g.ifs, &g, &cp0);
+          stmode_(&g, ccc, &index0, &im1, &cp0, &ierr);
+        }
+        delete_rayleigh_();
+        if (ierr == 1) break;
+        calgroup_(&phase[i - 1], &cp0, &f, &dh, &group[i - 1]);
+      }
     }
   }
   free(buf); free(lv); free(ccc);

@@ -674,7 +674,7 @@ def grt_setup(impl, thick, vp, vs, rho, modetype):
     return rc, mu, v[:ints[7]].copy(), lvls, ints, dbl
 
 
-def grt_love_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIKELIHOOD):
+def grt_love_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIKELIHOOD, group=False):
     """surfmodes for a Love column with a low-velocity layer, phase velocities, through the TRANSLATED reference (setup_grt,
     C_Interval_L, FundaMode, SecFuns_L, bisecim ...; the frequency loop and SearchLove's five calls are the driver's).
     Returns (ierr, phase)."""
@@ -683,15 +683,17 @@ def grt_love_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIK
         _love_f2c = C.CDLL(LOVE_F2C_LIB)
     vpt = C.c_void_p
     fn = _love_f2c.ref_love_modes
-    fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int, vpt, C.c_double, vpt, vpt]
+    fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int, vpt, C.c_double, vpt, vpt, vpt]
     a = [f64(x) for x in (thick, vp, vs, rho)]
     freqs, par = f64(freqs), f64(np.array(par))
     ph = np.full(len(freqs), 100.0)
-    ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data)
-    return ierr, ph
+    gr = np.full(len(freqs), 100.0)
+    ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data,
+              gr.ctypes.data if group else None)
+    return (ierr, ph, gr) if group else (ierr, ph)
 
 
-def grt_rayleigh_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIKELIHOOD):
+def grt_rayleigh_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR_LIKELIHOOD, group=False):
     """surfmodes for a Rayleigh column with a low-velocity layer and no water, phase velocities, through the TRANSLATED reference
     (setup_grt, C_Interval, FundaMode with CR0_Finder, SecFunSurf, bisecim ...).  Returns (ierr, phase); ierr -2: no low-velocity
     layer, -3: a water layer."""
@@ -700,12 +702,14 @@ def grt_rayleigh_modes_reference(thick, vp, vs, rho, freqs, dc=1e-3, par=GRT_PAR
         _rayleigh_f2c = C.CDLL(RAYLEIGH_F2C_LIB)
     vpt = C.c_void_p
     fn = _rayleigh_f2c.ref_rayleigh_modes
-    fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int, vpt, C.c_double, vpt, vpt]
+    fn.argtypes = [C.c_int] + [vpt] * 4 + [C.c_int, vpt, C.c_double, vpt, vpt, vpt]
     a = [f64(x) for x in (thick, vp, vs, rho)]
     freqs, par = f64(freqs), f64(np.array(par))
     ph = np.full(len(freqs), 100.0)
-    ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data)
-    return ierr, ph
+    gr = np.full(len(freqs), 100.0)
+    ierr = fn(len(a[0]), *[x.ctypes.data for x in a], len(freqs), freqs.ctypes.data, dc, par.ctypes.data, ph.ctypes.data,
+              gr.ctypes.data if group else None)
+    return (ierr, ph, gr) if group else (ierr, ph)
 
 
 def grt_stoneley_secfun_reference(thick, vp, vs, rho, freq, c):

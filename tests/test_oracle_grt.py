@@ -491,3 +491,33 @@ def test_stoneley_secular_function_equals_the_translated_reference():
                 assert ll_ref == ll and _bits_equal(re, v) and _bits_equal(im_, imf), (vs, th, f, c, (re, im_), (v, imf))
                 n += 1
     assert n > 3000
+
+
+@pytest.mark.skipif(not (orc.have_rayleigh_reference() and orc.have_love_reference()), reason="oracle/_ref translations not built (needs /root/reference)")
+@pytest.mark.parametrize("modetype", [1, 0])
+def test_group_velocities_end_to_end_equal_the_translated_reference(modetype):
+    """paras%phaseGroup = 1: every frequency is searched a second time at freq + 0.005 Hz from the phase velocity just found and
+    CalGroup (surfmodes.f90:296-312, translated too) forms the quotient.  Phase AND group velocities of whole columns, bit for
+    bit, with and without a water layer."""
+    rng = np.random.default_rng(orc.live_seed(f"group{modetype}"))
+    cols = [MODELS[k] for k in sorted(MODELS)] + [crust([3.1, 2.7, 3.5, 3.0, 4.0, 4.5], [1.0, 2.0, 2.5, 3.0, 5.0, 0.0], water=1.2)]
+    for k in range(24):
+        nl = int(rng.integers(4, 11))
+        vs = np.sort(rng.uniform(2.4, 4.6, nl))
+        j = int(rng.integers(1, nl - 1))
+        vs[j] = vs[j - 1] * rng.uniform(0.7, 0.95)
+        cols.append(crust(vs, np.append(rng.uniform(0.5, 6.0, nl - 1), 0.0), water=float(rng.uniform(0.3, 2.5)) if k % 3 == 0 else None))
+    ref = orc.grt_rayleigh_modes_reference if modetype == 1 else orc.grt_love_modes_reference
+    n = 0
+    for k, (th, vp, vs, rho) in enumerate(cols):
+        par = orc.GRT_PAR_LIKELIHOOD if k % 2 else orc.GRT_PAR_MODELLING
+        e0, p0, g0, _ = orc.grt_modes(th, vp, vs, rho, FREQS, modetype=modetype, phaseGroup=1, dc=1e-3, par=par, math_mode=orc.LIBM)
+        e1, p1, g1 = ref(th, vp, vs, rho, FREQS, dc=1e-3, par=par, group=True)
+        if e1 == -2:
+            continue
+        assert e0 == e1, (vs, e0, e1)
+        if e0 == 0:
+            assert p0.tobytes() == p1.tobytes() and g0.tobytes() == g1.tobytes(), (vs, th, g0, g1)
+            assert np.isfinite(g0).all() and (g0 >= 0).all()        # (CalGroup returns 0 where its quotient is not positive)
+        n += 1
+    assert n >= 12
