@@ -5,7 +5,7 @@
  * vs2vp_3d / vp2rho_3d, check_model, convert_to_layer and the OpenMP column loop of
  * surf_likelihood / program modelling.  Used as the parity checker and as the timed
  * CPU baseline (bench.py cpu_baseline / --impl reference).  See the headers of
- * surfdisp96_ref.c ("parity unpinned") and kdtree2_ref.c ("pinned").
+ * surfdisp96_ref.c (pinned on the mechanically translated surfdisp96.f) and kdtree2_ref.c (pinned on the reference's kdtree2.o).
  *
  * Reference lines restated (relative to /root/reference):
  *   src/utils.f90:102-112,125-134           vs2vp_3d, vp2rho_3d

@@ -1,8 +1,9 @@
 """GPU parity of the 2-D fast-marching travel times (mctomo_b200/csrc/k6_fm2d.cuh) against oracle/fm2d_ref.c through
 the C ABI: receiver times AND the whole travel-time field bit-identical, node / stencil counters identical, for both
 stencil orders, with and without source-grid refinement, diced grids, sources on the model's edge, receivers inside the
-source cell, sources without data, several periods in one call.  The oracle of this path is "parity unpinned"
-(tests/test_oracle_fm2d.py pins it on analytic travel times)."""
+source cell, sources without data, several periods in one call.  The oracle of this path is itself pinned on the
+reference's own Fortran 90, translated mechanically (tests/test_oracle_fm2d_vs_reference.py), and on analytic travel times
+(tests/test_oracle_fm2d.py); the last tests of this file hold the device to the reference-derived fixtures directly."""
 import numpy as np
 import pytest
 

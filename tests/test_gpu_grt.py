@@ -2,7 +2,8 @@
 
 Bit-identical phase and group velocities, ierr and both work counters against the oracle in PORTABLE math mode (same
 exp / sincos as the device); within north_star's 1e-5 km/s of the oracle with libm.  The oracle of this branch is
-"parity unpinned" (tests/test_oracle_grt.py pins it on physics only)."""
+pinned end to end on the reference's own Fortran 90, translated mechanically (tests/test_oracle_grt.py: oracle/f90toc_love.py),
+and on physics; the last test of this file holds the device to the reference-derived fixtures directly."""
 import numpy as np
 import pytest
 

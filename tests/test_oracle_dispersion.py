@@ -1,7 +1,7 @@
 """Known-answer and regression tests of the dispersion oracle (oracle/surfdisp96_ref.c).
 
-The reference has no tests or golden values for this path ("parity unpinned"): what can be pinned is
-physics (half-space Rayleigh velocity, Love cut-off, monotone dispersion), internal consistency
+The reference has no tests or golden values for this path; the oracle is pinned on the reference's own surfdisp96.f,
+translated mechanically to C, in tests/test_oracle_vs_reference.py.  Here: physics (half-space Rayleigh velocity, Love cut-off, monotone dispersion), internal consistency
 (libm vs portable math, surfdisp96 vs surfdisp_mmodes on the fundamental) and drift (self-generated
 vectors in tests/golden/dispersion_oracle.npz)."""
 import os

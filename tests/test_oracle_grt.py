@@ -1,7 +1,8 @@
 """The oracle's restatement of the generalized R/T branch (oracle/grt_ref.c) against physics.
 
-PARITY UNPINNED: the reference ships no value for this branch and cannot be compiled here.  What can be checked is that
-every phase velocity the restatement returns is a zero of an INDEPENDENT secular function (tests/independent_modal.py:
+The reference ships no value for this branch and cannot be compiled here.  Two kinds of pins: (1) the reference's own
+Fortran 90 translated mechanically to C (oracle/f90toc_love.py) -- every routine alone and whole columns end to end, bit for
+bit (the second half of this file); (2) physics, independent of any reading of the Fortran: every phase velocity the restatement returns is a zero of an INDEPENDENT secular function (tests/independent_modal.py:
 propagator matrices in 50-digit arithmetic, no formula shared with the R/T recursion), that Rayleigh roots of ordinary
 crustal models are the lowest mode, that group velocities equal d(omega)/dk of those roots, and that the search is
 deterministic in both math modes."""
@@ -184,7 +185,7 @@ def test_love_secular_function_equals_the_translated_reference():
     under gcc's Fortran rules, array sections / constructors / MATMUL scalarised).  The restatement's secfun_L must equal it
     BIT FOR BIT -- value and Imf -- over random low-velocity columns, with and without a water layer, at every frequency and
     over the whole range of trial velocities the search scans (evanescent and propagating layers, the deep-layer cut-off of
-    startl).  The searches around it (SearchLove, C_Interval_L, bisecim) and the Rayleigh functions stay "parity unpinned"."""
+    startl)."""
     rng = np.random.default_rng(orc.live_seed("test_love_secular_function_equals_the_translated_reference"))
     n = 0
     cols = [MODELS[k] for k in sorted(MODELS)]
@@ -241,8 +242,7 @@ def test_rayleigh_surface_secular_function_equals_the_translated_reference():
     MATMUL whose block structure the restatement and the device exploit) and inv2, plus startl's choice of the deepest layer --
     as the reference's own Rayleigh.f90 computes it (oracle/f90toc_love.py: sections, constructors, MATMUL, RESHAPE, pointers to
     sections, array-valued functions scalarised; complex arithmetic under gcc's Fortran rules).  Bit for bit: value, Imf, ll.
-    What stays "parity unpinned": the water-layer functions (SecFunSt, Stoneley, propdn_f, up_fs, dn_fs: LUCC, det3) and the
-    searches (SearchRayleigh, C_Interval, bisecim)."""
+    (The water-layer functions and the searches have their own tests below.)"""
     rng = np.random.default_rng(orc.live_seed("test_rayleigh_surface_secular_function_equals_the_translated_reference"))
     cols = [MODELS[k] for k in sorted(MODELS)]
     for _ in range(40):

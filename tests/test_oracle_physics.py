@@ -1,8 +1,8 @@
 """The dispersion oracle against an independent multiprecision eigen-solver (tests/independent_modal.py).
 
 The reference ships no golden dispersion values and no Fortran compiler exists in this image, so the
-oracle's bit-level behaviour cannot be pinned against surfdisp96 itself ("parity unpinned").
-What CAN be pinned is that its answers are the roots of the elastic eigenproblem: here every phase
+oracle's bit-level behaviour is pinned on a mechanical translation of surfdisp96.f (tests/test_oracle_vs_reference.py), not on
+a gfortran binary.  Independent of any reading of the Fortran is that its answers are the roots of the elastic eigenproblem: here every phase
 velocity the oracle returns -- Rayleigh and Love, fundamental and overtones, with and without a water
 layer -- is required to lie within 1e-5 km/s (the north-star tolerance) of a root of a secular function
 derived from the equations of motion alone and evaluated with 50 digits, the number of modes it finds is
