@@ -27,6 +27,14 @@ def test_header_symbols_exported():
     assert not missing, f"declared in the header but not exported: {missing}"
 
 
+def test_integration_index_lists_every_entry_point():
+    """INTEGRATION.md section 8 (entry point -> reference lines it replaces) names exactly the header's symbols."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read().split("## 8. Entry-point index")[1]
+    listed = set(re.findall(r"`(mct_[a-z0-9_]+)`", doc))
+    declared = set(_declared_symbols())
+    assert listed == declared, (sorted(declared - listed), sorted(listed - declared))
+
+
 def test_binding_loads():
     assert capi.lib() is not None and capi._bind_batch() is not None
 
