@@ -162,3 +162,35 @@ def test_shim_derived_types_match_the_c_structs():
         ff = [width[t] for t in ffields]
         assert cf == ff, (name, structs[name], ffields)
     assert seen >= 3, (sorted(types), sorted(structs))
+
+
+def test_shim_wrapper_calls_pass_the_interfaces_argument_counts():
+    """Every call of a bound entry point inside the shim's wrapper routines passes as many actual arguments as the
+    interface has dummies (none of them is optional)."""
+    ifaces, _ = _shim()
+    lines = _shim_lines()
+    in_iface, calls, problems = False, 0, []
+    for ln in lines:
+        low = ln.lower()
+        if re.match(r"interface\b", low):
+            in_iface = True
+        elif re.match(r"end\s+interface", low):
+            in_iface = False
+        if in_iface:
+            continue
+        for m in re.finditer(r"\b(mct_[a-z0-9_]+)\s*\(", low):
+            name = m.group(1)
+            if name not in ifaces or re.search(r"\b(function|subroutine)\s+" + name, low):
+                continue
+            depth, j = 1, m.end()
+            while depth and j < len(low):
+                depth += (low[j] == "(") - (low[j] == ")")
+                j += 1
+            assert depth == 0, ln
+            inner = low[m.end():j - 1]
+            n = len(_split_top(inner)) if inner.strip() else 0
+            calls += 1
+            if n != len(ifaces[name]):
+                problems.append(f"{name}: called with {n} arguments, interface has {len(ifaces[name])}: {ln[:120]}")
+    assert calls >= 15, calls
+    assert not problems, "\n".join(problems)
