@@ -167,7 +167,10 @@ def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
     probe_cols = min(per_eval_cols, 64 * nthreads)
     wx = max(1, min(grid.nx, probe_cols // grid.ny))
     detail = None
-    for pts, par in models:
+    # successive x-slabs of the models, in turn, until the budget is used (slab k of every model before slab k + 1)
+    work = [(k, m) for k in range(max(1, grid.nx // wx)) for m in models]
+    for k, (pts, par) in work:
+        x0 = k * wx
         t0 = time.perf_counter()
         vp = np.zeros(grid.shape); vs = np.zeros(grid.shape); rho = np.zeros(grid.shape); sid = np.zeros(grid.shape, np.int32)
         orc.kdtree_to_grid(pts, par, grid, grid.cover_box(), vp, vs, rho, sid)
@@ -177,7 +180,7 @@ def cpu_sample(grid, models, freqs, spec, budget_s, nthreads):
         t2 = time.perf_counter()
         specs = spec if isinstance(spec, list) else [spec]
         for sp in specs:
-            pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (1, wx, 1, grid.ny), freqs, math_mode=mode,
+            pv, gv, ie, cnt, _ = orc.surf_dispersion(vp, vs, rho, grid, (x0 + 1, x0 + wx, 1, grid.ny), freqs, math_mode=mode,
                                                      nthreads=nthreads, **sp)
             solves += wx * grid.ny * len(freqs) * max(sp["nmodes"], 1)
         t3 = time.perf_counter()
